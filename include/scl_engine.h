@@ -1,0 +1,164 @@
+/*
+ * scl_engine.h — C-ABI of the B200-native Scan Context loop-closure engine.
+ *
+ * This is the thin boundary the reference's host code binds to. The reference has no C ABI of
+ * its own; the interface being replaced is the C++ class boundary
+ *   class scan_descriptor            /root/reference/include/descriptor.h:21-36
+ *   class scan_context_descriptor    /root/reference/include/descriptor.h:1304-1801
+ * as called from distributed_mapping (/root/reference/include/distributedMapping.h:404, 627,
+ * 1002, 1072, 1078, 1274, 1280-1284) plus the ICP block of performIntraLoopClosure
+ * (distributedMapping.h:1108-1132). include/descriptor_b200.h adapts these entry points back to
+ * the six scan_descriptor virtuals; INTEGRATION.md shows the two-line change in
+ * distributedMapping.h.
+ *
+ * Conventions
+ *  - every function returns an scl_status code, 0 = OK; nothing throws across the boundary;
+ *  - plain pointers and sizes only; pointers are HOST pointers unless the name says _dev;
+ *  - descriptors cross the boundary as R*S row-major float32 — the layout of
+ *    global_descriptor.msg `values` (descriptor.h:1446-1455 writer, :1575-1582 reader);
+ *  - keys are dense global insertion indices 0..N-1 as in the reference (descriptor.h:1593-1599);
+ *  - an engine handle is internally serialised (one mutex, one CUDA stream), so the reference's
+ *    {insert on the ROS/LIO threads || query on loopClosureThread} pattern
+ *    (distributedMapping.h:625-628,1001-1003 vs :1078,1280) is safe;
+ *  - there is no CPU fallback: without a CUDA device scl_create fails with SCL_ERR_CUDA.
+ */
+#ifndef SCL_ENGINE_H_
+#define SCL_ENGINE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct scl_engine scl_engine;
+
+typedef enum {
+    SCL_OK = 0,
+    SCL_ERR_INVALID = 1,     /* bad argument */
+    SCL_ERR_CUDA = 2,        /* CUDA runtime error (see scl_last_error) */
+    SCL_ERR_UNSUPPORTED = 3, /* geometry outside what the kernels are built for */
+    SCL_ERR_RANGE = 4,       /* key out of range */
+    SCL_ERR_NOMEM = 5
+} scl_status;
+
+/* constructor arguments of scan_context_descriptor, descriptor.h:1307-1316 (same defaults) */
+typedef struct {
+    int num_ring;            /* 20  */
+    int num_sector;          /* 60  */
+    int num_candidates;      /* 3   */
+    double dist_thres;       /* 0.14 */
+    double lidar_height;     /* 1.65 */
+    double max_radius;       /* 80.0 */
+    int num_exclude_recent;  /* 100 */
+    int tree_making_period;  /* 10  */
+    double search_ratio;     /* 0.1 */
+} scl_params;
+
+void scl_default_params(scl_params* p);
+
+/* replaces: new scan_context_descriptor(...) at distributedMapping.h:404 */
+int scl_create(const scl_params* p, int device, scl_engine** out);
+int scl_destroy(scl_engine* e);
+const char* scl_last_error(scl_engine* e);
+/* run on the caller's CUDA stream (a cudaStream_t) instead of the engine's own */
+int scl_set_stream(scl_engine* e, void* cuda_stream);
+/* pre-size the database arrays in HBM (they otherwise grow by doubling) */
+int scl_reserve(scl_engine* e, int capacity);
+/* Database sharding across ranks: local key l stands for global key
+ * l*world + rank in every id this engine reports. Default rank 0, world 1. */
+int scl_set_shard(scl_engine* e, int rank, int world);
+
+/* ---- descriptor build --------------------------------------------------------------------
+ * replaces makeAndSaveDescriptorAndKey, descriptor.h:1604-1611 (call site distributedMapping.h:1002).
+ * pts: n points, stride_bytes apart (32 for pcl::PointXYZI), float x,y,z at byte 0,4,8.
+ * out_desc (R*S floats, may be NULL) is the return vector of the reference function. */
+int scl_build_insert(scl_engine* e, const void* pts, int n, int stride_bytes, int8_t robot, int index,
+                     float* out_desc);
+/* makeScancontext alone (descriptor.h:1404-1461): no insert. out_ring/out_sector (n ints each,
+ * may be NULL) receive the 1-based bin of every point, 0 for dropped points (parity checks). */
+int scl_make_scancontext(scl_engine* e, const void* pts, int n, int stride_bytes, float* out_desc,
+                         int32_t* out_ring, int32_t* out_sector);
+/* Batched build: n_scans clouds concatenated in pts; scan i is points [offsets[i], offsets[i+1]).
+ * insert != 0 appends them (robots/indices give the metadata, may be NULL -> robot 0, index = key).
+ * out_desc: n_scans*R*S floats or NULL. */
+int scl_build_batch(scl_engine* e, const void* pts, const int32_t* offsets, int n_scans, int stride_bytes,
+                    int insert, const int8_t* robots, const int32_t* indices, float* out_desc);
+/* same with pts/out_desc in device memory (offsets stay on the host) */
+int scl_build_batch_dev(scl_engine* e, const void* pts_dev, const int32_t* offsets, int n_scans, int stride_bytes,
+                        int insert, const int8_t* robots, const int32_t* indices, float* out_desc_dev);
+
+/* ---- database insert ---------------------------------------------------------------------
+ * replaces saveDescriptorAndKey, descriptor.h:1572-1585 (call site distributedMapping.h:627) */
+int scl_insert(scl_engine* e, const float* desc, int8_t robot, int index);
+int scl_insert_batch(scl_engine* e, const float* descs, int n, const int8_t* robots, const int32_t* indices);
+int scl_insert_batch_dev(scl_engine* e, const float* descs_dev, int n, const int8_t* robots, const int32_t* indices);
+
+/* ---- accessors ---------------------------------------------------------------------------
+ * getIndex / getSize, descriptor.h:1758-1766. Out-of-range keys (the reference's getIndex(-1) at
+ * distributedMapping.h:1282) give robot = -1, index = -1 and SCL_OK. */
+int scl_get_index(scl_engine* e, int key, int8_t* robot, int* index);
+int scl_size(scl_engine* e);
+int scl_get_descriptor(scl_engine* e, int key, float* out_desc); /* R*S floats */
+int scl_get_ring_key(scl_engine* e, int key, float* out_key);    /* R floats, descriptor.h:1463-1475 */
+
+/* ---- loop queries ------------------------------------------------------------------------
+ * replaces detectIntraLoopClosureID (descriptor.h:1613-1674, call site distributedMapping.h:1078):
+ *   id = -1 if no loop; second = best shift as a float.
+ * and detectInterLoopClosureID (descriptor.h:1676-1756, call site distributedMapping.h:1280):
+ *   id = -1 if no loop; second = yaw difference in radians; the searched key range is refreshed
+ *   every tree_making_period calls exactly like the reference's KD-tree rebuild. */
+int scl_query_intra(scl_engine* e, int cur, int* id, float* second);
+int scl_query_inter(scl_engine* e, int cur, int* id, float* second);
+
+/* Batched throughput form (ring-key top-K + shift-aligned SC distance for every candidate).
+ *   q_desc : Q*R*S query descriptors, or NULL to take the queries from the database by q_ids
+ *   q_ids  : Q keys; with q_desc they only drive the self-skip rule (descriptor.h:1731), may be NULL
+ *   n_db   : keys [0, n_db) are searched
+ *   metric : 0 = nanoflann accumulation order (nanoflann.hpp:383-408)
+ *            1 = sequential order + libnabo's self-match rule (d2 <= FLT_EPSILON skipped)
+ * Results, any of which may be NULL: cand_* are Q*K in kNN order (id -1 / d2 FLT_MAX / dist NaN for
+ * missing); best_* apply the strict-< scan of descriptor.h:1721-1737 (best_id -1, dist 1e7 if none). */
+typedef struct {
+    const float* q_desc;
+    const int32_t* q_ids;
+    int Q, K, n_db, metric;
+} scl_batch_query;
+typedef struct {
+    int32_t* cand_ids;
+    float* cand_d2;
+    double* cand_dist;
+    int32_t* cand_shift;
+    int32_t* best_id;
+    double* best_dist;
+    int32_t* best_shift;
+} scl_batch_result;
+int scl_query_batch(scl_engine* e, const scl_batch_query* q, scl_batch_result* r);
+/* all pointers in q and r are device pointers; asynchronous on the engine's stream */
+int scl_query_batch_dev(scl_engine* e, const scl_batch_query* q, scl_batch_result* r);
+
+/* Multi-GPU merge: `world` per-rank result blocks of Q*K records, gathered
+ * rank-major in device memory, are reduced to the global top-K by (d2, id) and then to the winner
+ * by the same strict-< scan as the unsharded query. */
+int scl_merge_shards_dev(scl_engine* e, int world, int Q, int K, const int32_t* q_ids,
+                         const int32_t* all_ids, const float* all_d2, const double* all_dist, const int32_t* all_shift,
+                         scl_batch_result* merged);
+
+/* ---- geometric verification --------------------------------------------------------------
+ * replaces the pcl::IterativeClosestPoint block of performIntraLoopClosure,
+ * distributedMapping.h:1108-1132: point-to-point ICP of src onto tgt.
+ * T_out: row-major 4x4 (getFinalTransformation), fitness = getFitnessScore(), converged = hasConverged(). */
+typedef struct {
+    double max_corr_dist;   /* 100.0, distributedMapping.h:1109 */
+    int max_iterations;     /* 50,    :1110 */
+    double trans_eps;       /* 1e-6,  :1111 */
+    double fitness_eps;     /* 1e-6,  :1112 */
+} scl_icp_params;
+void scl_default_icp_params(scl_icp_params* p);
+int scl_icp(scl_engine* e, const void* src, int n_src, const void* tgt, int n_tgt, int stride_bytes,
+            const scl_icp_params* p, float* T_out, float* fitness, int* converged, int* iterations);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -130,7 +130,7 @@ struct NNSearchF {
             float dist = 0;
             for (int d = 0; d < dim; d++) { const float diff = q[d] - cloud(d, j); dist += diff * diff; }
             if (!(dist > std::numeric_limits<float>::epsilon())) continue;
-            if (count == k && !(dist < d2[k - 1])) continue;
+            if (!(dist < (count == k ? d2[k - 1] : std::numeric_limits<float>::infinity()))) continue;
             int i = count < k ? count : k - 1;
             for (; i > 0 && d2[i - 1] > dist; --i) { d2[i] = d2[i - 1]; idx[i] = idx[i - 1]; }
             d2[i] = dist; idx[i] = j;

@@ -281,7 +281,10 @@ struct sco_handle {
             const float* key = polarcontext_invkeys_mat_[j].data();
             const float dist = metric == 0 ? d2_nanoflann(q, key, R) : d2_sequential(q, key, R);
             if (metric == 1 && !(dist > FLT_EPSILON)) continue; /* libnabo self-match rule */
-            if (count == k && !(dist < d2[k - 1])) continue;    /* ties with the worst are rejected */
+            /* both trees accept a point only if dist < current worst; before the set is full the
+             * worst is FLT_MAX in nanoflann (nanoflann.hpp:163) and +inf in libnabo */
+            const float worst = count == k ? d2[k - 1] : (metric == 0 ? FLT_MAX : INFINITY);
+            if (!(dist < worst)) continue;                      /* ties with the worst are rejected */
             int i = count < k ? count : k - 1;
             for (; i > 0 && d2[i - 1] > dist; --i) { d2[i] = d2[i - 1]; ids[i] = ids[i - 1]; }
             d2[i] = dist; ids[i] = j;

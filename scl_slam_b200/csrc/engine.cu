@@ -1,0 +1,488 @@
+// engine.cu — the C-ABI of include/scl_engine.h over the sm_100a kernels.
+//
+// Host-side mirror of class scan_context_descriptor (/root/reference/include/descriptor.h:
+// 1304-1801): same constructor parameters, same insert / query / accessor semantics, with the
+// keyframe database resident in HBM:
+//   d_desc  [cap][R*S] float32  row-major wire image of every descriptor (the reference keeps
+//                               MatrixXd; every value is a float widened to double, so FP32 is lossless)
+//   d_keys  [cap][R]   float32  ring keys, one contiguous row per keyframe (the reference: one
+//                               COLUMN per keyframe in polarcontextRowKey, re-allocated per insert)
+//   d_knorm [cap]      float32  squared key norms for the tensor-core prefilter
+// (robot, index) metadata stays on the host (descriptor.h:1599,1758-1761).
+// There is no CPU fallback anywhere in this file: every data-path call launches kernels.
+#include "../../include/scl_engine.h"
+#include "kernels.h"
+
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() { return static_cast<T*>(p); }
+};
+
+} // namespace
+
+struct scl_engine {
+    scl_params p;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    std::mutex mu;
+    std::string err;
+    int n = 0, cap = 0;
+    float *d_desc = nullptr, *d_keys = nullptr, *d_knorm = nullptr;
+    std::vector<std::pair<int8_t, int>> index;
+    int rank = 0, world = 1;
+    int tree_counter = 0, n_tree = 0;      /* descriptor.h:1691-1703 */
+    int search_radius = 0;                 /* round(0.5*SEARCH_RATIO*S), descriptor.h:1545 */
+    /* scratch */
+    DevBuf pts, offsets, gbins, tickets, stage_desc, stage_keys, stage_knorm, bins_ring, bins_sector;
+    DevBuf qdesc, qids, qlocal, qkeys, qknorm, part_ids, part_d2, cand_ids, cand_d2, cand_local, cand_dist, cand_shift,
+        best_id, best_dist, best_shift;
+    size_t gbins_scans = 0;
+
+    int RS() const { return p.num_ring * p.num_sector; }
+};
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t _e = (call);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            e->err = std::string(#call) + ": " + cudaGetErrorString(_e);                             \
+            return _e == cudaErrorNotSupported ? SCL_ERR_UNSUPPORTED : (_e == cudaErrorMemoryAllocation ? SCL_ERR_NOMEM : SCL_ERR_CUDA); \
+        }                                                                                            \
+    } while (0)
+
+#define FAIL(code, msg) do { e->err = (msg); return (code); } while (0)
+
+namespace {
+
+int grow(scl_engine* e, int need)
+{
+    if (need <= e->cap) return SCL_OK;
+    int ncap = e->cap ? e->cap : 1024;
+    while (ncap < need) ncap = ncap < (1 << 28) ? ncap * 2 : ncap + (1 << 26);
+    const size_t RS = e->RS(), R = e->p.num_ring;
+    float *nd = nullptr, *nk = nullptr, *nn = nullptr;
+    CK(cudaMalloc(&nd, (size_t)ncap * RS * 4));
+    CK(cudaMalloc(&nk, (size_t)ncap * R * 4));
+    CK(cudaMalloc(&nn, (size_t)ncap * 4));
+    if (e->n > 0) {
+        CK(cudaMemcpyAsync(nd, e->d_desc, (size_t)e->n * RS * 4, cudaMemcpyDeviceToDevice, e->stream));
+        CK(cudaMemcpyAsync(nk, e->d_keys, (size_t)e->n * R * 4, cudaMemcpyDeviceToDevice, e->stream));
+        CK(cudaMemcpyAsync(nn, e->d_knorm, (size_t)e->n * 4, cudaMemcpyDeviceToDevice, e->stream));
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(e->d_desc); cudaFree(e->d_keys); cudaFree(e->d_knorm);
+    e->d_desc = nd; e->d_keys = nk; e->d_knorm = nn; e->cap = ncap;
+    return SCL_OK;
+}
+
+void append_index(scl_engine* e, int n, const int8_t* robots, const int32_t* indices)
+{
+    for (int i = 0; i < n; i++)
+        e->index.emplace_back(robots ? robots[i] : (int8_t)0, indices ? indices[i] : e->n + i);
+}
+
+// polar binning of a batch already in device memory
+int build_dev(scl_engine* e, const void* pts_dev, const int32_t* offsets_host, int n_scans, int stride_bytes, int insert,
+              const int8_t* robots, const int32_t* indices, float* out_desc_dev, int* ring_dev, int* sector_dev,
+              float** where_desc)
+{
+    const int R = e->p.num_ring, S = e->p.num_sector;
+    const size_t RS = e->RS();
+    if (n_scans <= 0) return SCL_OK;
+    int max_points = 0;
+    for (int i = 0; i < n_scans; i++) {
+        const int c = offsets_host[i + 1] - offsets_host[i];
+        if (c < 0) FAIL(SCL_ERR_INVALID, "offsets must be non-decreasing");
+        if (c > max_points) max_points = c;
+    }
+    if (insert) { int rc = grow(e, e->n + n_scans); if (rc) return rc; }
+    CK(e->offsets.ensure((size_t)(n_scans + 1) * 4));
+    CK(cudaMemcpyAsync(e->offsets.p, offsets_host, (size_t)(n_scans + 1) * 4, cudaMemcpyHostToDevice, e->stream));
+    if ((size_t)n_scans > e->gbins_scans) {
+        CK(e->gbins.ensure((size_t)n_scans * RS * 4));
+        CK(e->tickets.ensure((size_t)n_scans * 4));
+        CK(cudaMemsetAsync(e->gbins.p, 0, e->gbins.cap, e->stream));   /* kernels leave it zeroed afterwards */
+        CK(cudaMemsetAsync(e->tickets.p, 0, e->tickets.cap, e->stream));
+        e->gbins_scans = e->gbins.cap / (RS * 4);
+        if (e->tickets.cap / 4 < e->gbins_scans) e->gbins_scans = e->tickets.cap / 4;
+    }
+    float *od, *ok, *on;
+    if (insert) {
+        od = e->d_desc + (size_t)e->n * RS; ok = e->d_keys + (size_t)e->n * R; on = e->d_knorm + e->n;
+    } else {
+        CK(e->stage_desc.ensure((size_t)n_scans * RS * 4));
+        CK(e->stage_keys.ensure((size_t)n_scans * R * 4));
+        CK(e->stage_knorm.ensure((size_t)n_scans * 4));
+        od = e->stage_desc.as<float>(); ok = e->stage_keys.as<float>(); on = e->stage_knorm.as<float>();
+    }
+    CK(scl_launch_polar(pts_dev, e->offsets.as<int>(), n_scans, max_points, stride_bytes, R, S, e->p.lidar_height, e->p.max_radius,
+                        e->gbins.as<uint32_t>(), e->tickets.as<int>(), od, ok, on, ring_dev, sector_dev, e->stream));
+    if (out_desc_dev) CK(cudaMemcpyAsync(out_desc_dev, od, (size_t)n_scans * RS * 4, cudaMemcpyDeviceToDevice, e->stream));
+    if (where_desc) *where_desc = od;
+    if (insert) { append_index(e, n_scans, robots, indices); e->n += n_scans; }
+    return SCL_OK;
+}
+
+int build_host(scl_engine* e, const void* pts, const int32_t* offsets, int n_scans, int stride_bytes, int insert,
+               const int8_t* robots, const int32_t* indices, float* out_desc, int32_t* out_ring, int32_t* out_sector)
+{
+    if (n_scans < 0 || stride_bytes < 12 || (stride_bytes & 3)) FAIL(SCL_ERR_INVALID, "stride_bytes must be >= 12 and a multiple of 4");
+    if (n_scans == 0) return SCL_OK;
+    if (!offsets) FAIL(SCL_ERR_INVALID, "offsets is NULL");
+    const size_t total = (size_t)offsets[n_scans];
+    if (total > 0 && !pts) FAIL(SCL_ERR_INVALID, "pts is NULL");
+    /* the copy covers whole strides except after the last point, whose tail may not exist */
+    const size_t bytes = total ? (total - 1) * (size_t)stride_bytes + 12 : 0;
+    CK(e->pts.ensure(total * (size_t)stride_bytes + 16));
+    if (bytes) CK(cudaMemcpyAsync(e->pts.p, pts, bytes, cudaMemcpyHostToDevice, e->stream));
+    int *ring = nullptr, *sector = nullptr;
+    if (out_ring && out_sector && total) {
+        CK(e->bins_ring.ensure(total * 4)); CK(e->bins_sector.ensure(total * 4));
+        ring = e->bins_ring.as<int>(); sector = e->bins_sector.as<int>();
+    }
+    float* where = nullptr;
+    int rc = build_dev(e, e->pts.p, offsets, n_scans, stride_bytes, insert, robots, indices, nullptr, ring, sector, &where);
+    if (rc) return rc;
+    if (out_desc) CK(cudaMemcpyAsync(out_desc, where, (size_t)n_scans * e->RS() * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (ring) {
+        CK(cudaMemcpyAsync(out_ring, ring, total * 4, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(out_sector, sector, total * 4, cudaMemcpyDeviceToHost, e->stream));
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    return SCL_OK;
+}
+
+// the batched query on device pointers; any result pointer may be null (scratch is used)
+int query_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int K, int n_db, int metric, int missing_to_zero,
+              int32_t* cand_ids, float* cand_d2, double* cand_dist, int32_t* cand_shift,
+              int32_t* best_id, double* best_dist, int32_t* best_shift)
+{
+    const int R = e->p.num_ring, S = e->p.num_sector;
+    if (Q <= 0) return SCL_OK;
+    if (K < 1 || K > 32) FAIL(SCL_ERR_INVALID, "K must be in 1..32");
+    if (metric != 0 && metric != 1) FAIL(SCL_ERR_INVALID, "metric must be 0 or 1");
+    if (n_db < 0) n_db = 0;
+    if (n_db > e->n) n_db = e->n;
+    if (!q_desc && !q_ids) FAIL(SCL_ERR_INVALID, "q_desc and q_ids are both NULL");
+    if (!q_desc && e->world != 1) FAIL(SCL_ERR_INVALID, "queries by key need q_desc on a sharded engine");
+    const size_t QK = (size_t)Q * K;
+    if (!cand_ids) { CK(e->cand_ids.ensure(QK * 4)); cand_ids = e->cand_ids.as<int32_t>(); }
+    if (!cand_d2) { CK(e->cand_d2.ensure(QK * 4)); cand_d2 = e->cand_d2.as<float>(); }
+    CK(e->cand_local.ensure(QK * 4));
+    CK(e->qkeys.ensure((size_t)Q * R * 4));
+    int32_t* q_local = nullptr;
+    if (q_desc) {
+        CK(e->qknorm.ensure((size_t)Q * 4));
+        CK(scl_launch_ring_keys(q_desc, Q, R, S, e->qkeys.as<float>(), e->qknorm.as<float>(), e->stream));
+    } else {
+        CK(e->qlocal.ensure((size_t)Q * 4));
+        q_local = e->qlocal.as<int32_t>();
+        CK(scl_launch_ids_to_local(q_ids, Q, e->world, e->rank, -1, nullptr, q_local, e->stream));
+        CK(scl_launch_gather_rows(e->d_keys, q_local, Q, R, e->qkeys.as<float>(), e->stream));
+    }
+    const int splits = scl_knn_splits(Q, n_db);
+    KnnWorkspace ws;
+    CK(e->part_ids.ensure((size_t)Q * splits * K * 4));
+    CK(e->part_d2.ensure((size_t)Q * splits * K * 4));
+    ws.part_ids = e->part_ids.as<int32_t>(); ws.part_d2 = e->part_d2.as<float>(); ws.capacity = (size_t)Q * splits * K;
+    CK(scl_launch_knn_exact(e->qkeys.as<float>(), Q, e->d_keys, n_db, R, K, metric, e->world, e->rank, ws, cand_ids, cand_d2, e->stream));
+    CK(scl_launch_ids_to_local(cand_ids, (int)QK, e->world, e->rank, missing_to_zero ? 0 : -1, missing_to_zero ? cand_ids : nullptr,
+                               e->cand_local.as<int32_t>(), e->stream));
+    CK(scl_launch_scdist(e->d_desc, q_desc, q_local, q_ids, e->cand_local.as<int32_t>(), cand_ids, Q, K, R, S, e->search_radius,
+                         cand_dist, cand_shift, best_id, best_dist, best_shift, e->stream));
+    return SCL_OK;
+}
+
+int query_host(scl_engine* e, const scl_batch_query* q, scl_batch_result* r, int missing_to_zero)
+{
+    if (!q || !r) FAIL(SCL_ERR_INVALID, "null query/result");
+    const int Q = q->Q, K = q->K;
+    if (Q <= 0) return SCL_OK;
+    if (K < 1 || K > 32) FAIL(SCL_ERR_INVALID, "K must be in 1..32");
+    const size_t QK = (size_t)Q * K, RS = e->RS();
+    const float* dq = nullptr; const int32_t* di = nullptr;
+    if (q->q_desc) {
+        CK(e->qdesc.ensure((size_t)Q * RS * 4));
+        CK(cudaMemcpyAsync(e->qdesc.p, q->q_desc, (size_t)Q * RS * 4, cudaMemcpyHostToDevice, e->stream));
+        dq = e->qdesc.as<float>();
+    }
+    if (q->q_ids) {
+        for (int i = 0; i < Q && !q->q_desc; i++)
+            if (q->q_ids[i] < 0 || q->q_ids[i] >= e->n) FAIL(SCL_ERR_RANGE, "query key out of range");
+        CK(e->qids.ensure((size_t)Q * 4));
+        CK(cudaMemcpyAsync(e->qids.p, q->q_ids, (size_t)Q * 4, cudaMemcpyHostToDevice, e->stream));
+        di = e->qids.as<int32_t>();
+    }
+    CK(e->cand_ids.ensure(QK * 4)); CK(e->cand_d2.ensure(QK * 4)); CK(e->cand_dist.ensure(QK * 8)); CK(e->cand_shift.ensure(QK * 4));
+    CK(e->best_id.ensure((size_t)Q * 4)); CK(e->best_dist.ensure((size_t)Q * 8)); CK(e->best_shift.ensure((size_t)Q * 4));
+    int rc = query_dev(e, dq, di, Q, K, q->n_db, q->metric, missing_to_zero, e->cand_ids.as<int32_t>(), e->cand_d2.as<float>(),
+                       e->cand_dist.as<double>(), e->cand_shift.as<int32_t>(), e->best_id.as<int32_t>(), e->best_dist.as<double>(),
+                       e->best_shift.as<int32_t>());
+    if (rc) return rc;
+    if (r->cand_ids) CK(cudaMemcpyAsync(r->cand_ids, e->cand_ids.p, QK * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (r->cand_d2) CK(cudaMemcpyAsync(r->cand_d2, e->cand_d2.p, QK * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (r->cand_dist) CK(cudaMemcpyAsync(r->cand_dist, e->cand_dist.p, QK * 8, cudaMemcpyDeviceToHost, e->stream));
+    if (r->cand_shift) CK(cudaMemcpyAsync(r->cand_shift, e->cand_shift.p, QK * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (r->best_id) CK(cudaMemcpyAsync(r->best_id, e->best_id.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (r->best_dist) CK(cudaMemcpyAsync(r->best_dist, e->best_dist.p, (size_t)Q * 8, cudaMemcpyDeviceToHost, e->stream));
+    if (r->best_shift) CK(cudaMemcpyAsync(r->best_shift, e->best_shift.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SCL_OK;
+}
+
+} // namespace
+
+#define LOCK() if (!e) return SCL_ERR_INVALID; std::lock_guard<std::mutex> _lk(e->mu); cudaSetDevice(e->device)
+
+extern "C" {
+
+void scl_default_params(scl_params* p)
+{
+    p->num_ring = 20; p->num_sector = 60; p->num_candidates = 3; p->dist_thres = 0.14; p->lidar_height = 1.65;
+    p->max_radius = 80.0; p->num_exclude_recent = 100; p->tree_making_period = 10; p->search_ratio = 0.1;
+}
+
+void scl_default_icp_params(scl_icp_params* p)
+{
+    p->max_corr_dist = 100.0; p->max_iterations = 50; p->trans_eps = 1e-6; p->fitness_eps = 1e-6;
+}
+
+int scl_create(const scl_params* p, int device, scl_engine** out)
+{
+    if (!p || !out) return SCL_ERR_INVALID;
+    *out = nullptr;
+    if (p->num_ring < 1 || p->num_sector < 1 || p->num_candidates < 1 || p->num_candidates > 32 || p->tree_making_period < 1 ||
+        !(p->max_radius > 0))
+        return SCL_ERR_INVALID;
+    if (p->num_ring != 10 && p->num_ring != 20 && p->num_ring != 40 && p->num_ring != 80) return SCL_ERR_UNSUPPORTED;
+    if (p->num_ring * p->num_sector > 8192) return SCL_ERR_UNSUPPORTED;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return SCL_ERR_CUDA; /* no CPU fallback */
+    if (cudaSetDevice(device) != cudaSuccess) return SCL_ERR_CUDA;
+    scl_engine* e = new scl_engine();
+    e->p = *p; e->device = device;
+    e->search_radius = (int)std::round(0.5 * p->search_ratio * p->num_sector);
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return SCL_ERR_CUDA; }
+    *out = e;
+    return SCL_OK;
+}
+
+int scl_destroy(scl_engine* e)
+{
+    if (!e) return SCL_ERR_INVALID;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        cudaSetDevice(e->device);
+        cudaStreamSynchronize(e->stream);
+        cudaFree(e->d_desc); cudaFree(e->d_keys); cudaFree(e->d_knorm);
+        DevBuf* bufs[] = {&e->pts, &e->offsets, &e->gbins, &e->tickets, &e->stage_desc, &e->stage_keys, &e->stage_knorm,
+                          &e->bins_ring, &e->bins_sector, &e->qdesc, &e->qids, &e->qlocal, &e->qkeys, &e->qknorm, &e->part_ids,
+                          &e->part_d2, &e->cand_ids, &e->cand_d2, &e->cand_local, &e->cand_dist, &e->cand_shift, &e->best_id,
+                          &e->best_dist, &e->best_shift};
+        for (DevBuf* b : bufs) b->release();
+        if (e->own_stream) cudaStreamDestroy(e->stream);
+    }
+    delete e;
+    return SCL_OK;
+}
+
+const char* scl_last_error(scl_engine* e) { return e ? e->err.c_str() : "null engine"; }
+
+int scl_set_stream(scl_engine* e, void* s)
+{
+    LOCK();
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->own_stream) cudaStreamDestroy(e->stream);
+    e->stream = static_cast<cudaStream_t>(s); e->own_stream = false;
+    return SCL_OK;
+}
+
+int scl_reserve(scl_engine* e, int capacity) { LOCK(); return grow(e, capacity); }
+
+int scl_set_shard(scl_engine* e, int rank, int world)
+{
+    LOCK();
+    if (world < 1 || rank < 0 || rank >= world) FAIL(SCL_ERR_INVALID, "bad shard");
+    e->rank = rank; e->world = world;
+    return SCL_OK;
+}
+
+int scl_build_insert(scl_engine* e, const void* pts, int n, int stride_bytes, int8_t robot, int index, float* out_desc)
+{
+    LOCK();
+    if (n < 0) FAIL(SCL_ERR_INVALID, "n < 0");
+    const int32_t off[2] = {0, n};
+    return build_host(e, pts, off, 1, stride_bytes, 1, &robot, &index, out_desc, nullptr, nullptr);
+}
+
+int scl_make_scancontext(scl_engine* e, const void* pts, int n, int stride_bytes, float* out_desc, int32_t* out_ring, int32_t* out_sector)
+{
+    LOCK();
+    if (n < 0) FAIL(SCL_ERR_INVALID, "n < 0");
+    const int32_t off[2] = {0, n};
+    return build_host(e, pts, off, 1, stride_bytes, 0, nullptr, nullptr, out_desc, out_ring, out_sector);
+}
+
+int scl_build_batch(scl_engine* e, const void* pts, const int32_t* offsets, int n_scans, int stride_bytes, int insert,
+                    const int8_t* robots, const int32_t* indices, float* out_desc)
+{
+    LOCK();
+    return build_host(e, pts, offsets, n_scans, stride_bytes, insert, robots, indices, out_desc, nullptr, nullptr);
+}
+
+int scl_build_batch_dev(scl_engine* e, const void* pts_dev, const int32_t* offsets, int n_scans, int stride_bytes, int insert,
+                        const int8_t* robots, const int32_t* indices, float* out_desc_dev)
+{
+    LOCK();
+    if (n_scans < 0 || stride_bytes < 12 || (stride_bytes & 3)) FAIL(SCL_ERR_INVALID, "bad arguments");
+    return build_dev(e, pts_dev, offsets, n_scans, stride_bytes, insert, robots, indices, out_desc_dev, nullptr, nullptr, nullptr);
+}
+
+int scl_insert_batch(scl_engine* e, const float* descs, int n, const int8_t* robots, const int32_t* indices)
+{
+    LOCK();
+    if (n < 0 || (n > 0 && !descs)) FAIL(SCL_ERR_INVALID, "bad arguments");
+    if (n == 0) return SCL_OK;
+    int rc = grow(e, e->n + n); if (rc) return rc;
+    const size_t RS = e->RS();
+    float* dst = e->d_desc + (size_t)e->n * RS;
+    CK(cudaMemcpyAsync(dst, descs, (size_t)n * RS * 4, cudaMemcpyHostToDevice, e->stream));   /* wire decode, descriptor.h:1575-1582 */
+    CK(scl_launch_ring_keys(dst, n, e->p.num_ring, e->p.num_sector, e->d_keys + (size_t)e->n * e->p.num_ring, e->d_knorm + e->n, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    append_index(e, n, robots, indices); e->n += n;
+    return SCL_OK;
+}
+
+int scl_insert(scl_engine* e, const float* desc, int8_t robot, int index) { return scl_insert_batch(e, desc, 1, &robot, &index); }
+
+int scl_insert_batch_dev(scl_engine* e, const float* descs_dev, int n, const int8_t* robots, const int32_t* indices)
+{
+    LOCK();
+    if (n < 0 || (n > 0 && !descs_dev)) FAIL(SCL_ERR_INVALID, "bad arguments");
+    if (n == 0) return SCL_OK;
+    int rc = grow(e, e->n + n); if (rc) return rc;
+    const size_t RS = e->RS();
+    float* dst = e->d_desc + (size_t)e->n * RS;
+    CK(cudaMemcpyAsync(dst, descs_dev, (size_t)n * RS * 4, cudaMemcpyDeviceToDevice, e->stream));
+    CK(scl_launch_ring_keys(dst, n, e->p.num_ring, e->p.num_sector, e->d_keys + (size_t)e->n * e->p.num_ring, e->d_knorm + e->n, e->stream));
+    append_index(e, n, robots, indices); e->n += n;
+    return SCL_OK;
+}
+
+int scl_get_index(scl_engine* e, int key, int8_t* robot, int* index)
+{
+    LOCK();
+    if (!robot || !index) FAIL(SCL_ERR_INVALID, "null output");
+    if (key < 0 || key >= e->n) { *robot = -1; *index = -1; return SCL_OK; }   /* the reference's getIndex(-1) is UB */
+    *robot = e->index[key].first; *index = e->index[key].second;
+    return SCL_OK;
+}
+
+int scl_size(scl_engine* e) { if (!e) return -1; std::lock_guard<std::mutex> lk(e->mu); return e->n; }
+
+int scl_get_descriptor(scl_engine* e, int key, float* out)
+{
+    LOCK();
+    if (key < 0 || key >= e->n || !out) FAIL(SCL_ERR_RANGE, "key out of range");
+    CK(cudaMemcpyAsync(out, e->d_desc + (size_t)key * e->RS(), (size_t)e->RS() * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SCL_OK;
+}
+
+int scl_get_ring_key(scl_engine* e, int key, float* out)
+{
+    LOCK();
+    if (key < 0 || key >= e->n || !out) FAIL(SCL_ERR_RANGE, "key out of range");
+    CK(cudaMemcpyAsync(out, e->d_keys + (size_t)key * e->p.num_ring, (size_t)e->p.num_ring * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SCL_OK;
+}
+
+int scl_query_batch(scl_engine* e, const scl_batch_query* q, scl_batch_result* r) { LOCK(); return query_host(e, q, r, 0); }
+
+int scl_query_batch_dev(scl_engine* e, const scl_batch_query* q, scl_batch_result* r)
+{
+    LOCK();
+    if (!q || !r) FAIL(SCL_ERR_INVALID, "null query/result");
+    return query_dev(e, q->q_desc, q->q_ids, q->Q, q->K, q->n_db, q->metric, 0, r->cand_ids, r->cand_d2, r->cand_dist, r->cand_shift,
+                     r->best_id, r->best_dist, r->best_shift);
+}
+
+int scl_merge_shards_dev(scl_engine* e, int world, int Q, int K, const int32_t* q_ids, const int32_t* all_ids, const float* all_d2,
+                         const double* all_dist, const int32_t* all_shift, scl_batch_result* m)
+{
+    LOCK();
+    if (!m) FAIL(SCL_ERR_INVALID, "null result");
+    CK(scl_launch_merge_shards(world, Q, K, q_ids, all_ids, all_d2, all_dist, all_shift, m->cand_ids, m->cand_d2, m->cand_dist,
+                               m->cand_shift, m->best_id, m->best_dist, m->best_shift, e->stream));
+    return SCL_OK;
+}
+
+int scl_query_intra(scl_engine* e, int cur, int* id, float* second)
+{
+    LOCK();
+    if (!id || !second) FAIL(SCL_ERR_INVALID, "null output");
+    *id = -1; *second = 0.0f;
+    if (cur < 0 || cur >= e->n) FAIL(SCL_ERR_RANGE, "query key out of range");
+    const int K = e->p.num_candidates;
+    if (cur < e->p.num_exclude_recent + K + 1) return SCL_OK;               /* descriptor.h:1620 */
+    int32_t ids[32]; double dist[32]; int32_t shift[32];
+    scl_batch_query q{nullptr, &cur, 1, K, cur - e->p.num_exclude_recent, 1};  /* :1627; libnabo flavour */
+    scl_batch_result r{ids, nullptr, dist, shift, nullptr, nullptr, nullptr};
+    int rc = query_host(e, &q, &r, 0); if (rc) return rc;
+    float minDis = 10000000.0f; int minIndex = -1, minBias = 0;             /* :1637-1659: minDis is a float there */
+    for (int i = 0; i < K; i++) {
+        if (ids[i] < 0) continue;
+        if (dist[i] < (double)minDis) { minDis = (float)dist[i]; minIndex = ids[i]; minBias = shift[i]; }
+    }
+    if ((double)minDis < e->p.dist_thres) { *id = minIndex; *second = (float)minBias; }
+    return SCL_OK;
+}
+
+int scl_query_inter(scl_engine* e, int cur, int* id, float* second)
+{
+    LOCK();
+    if (!id || !second) FAIL(SCL_ERR_INVALID, "null output");
+    *id = -1; *second = 0.0f;
+    if (cur < 0 || cur >= e->n) FAIL(SCL_ERR_RANGE, "query key out of range");
+    const int K = e->p.num_candidates;
+    if (e->n < e->p.num_exclude_recent + 1) return SCL_OK;                  /* descriptor.h:1684 */
+    if (e->tree_counter % e->p.tree_making_period == 0) e->n_tree = e->n - e->p.num_exclude_recent;   /* :1691-1699 */
+    e->tree_counter++;
+    int32_t ids[32]; double dist[32]; int32_t shift[32];
+    scl_batch_query q{nullptr, &cur, 1, K, e->n_tree, 0};
+    scl_batch_result r{ids, nullptr, dist, shift, nullptr, nullptr, nullptr};
+    int rc = query_host(e, &q, &r, 1 /* unfilled result slots read entry 0, :1710,1723 */); if (rc) return rc;
+    double min_dist = 10000000; int nn_align = 0, nn_idx = -1;
+    for (int i = 0; i < K; i++)
+        if (dist[i] < min_dist && ids[i] != cur) { min_dist = dist[i]; nn_align = shift[i]; nn_idx = ids[i]; }
+    if (min_dist < e->p.dist_thres) *id = nn_idx;
+    const double unit = 360.0 / double(e->p.num_sector);
+    *second = (float)(nn_align * unit * M_PI / 180.0);                      /* :1752 */
+    return SCL_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,239 @@
+// k3_knn.cu — K3, the ring-key kNN that replaces the KD-trees of the reference:
+//   nanoflann findNeighbors   /root/reference/include/descriptor.h:1714-1716 (nanoflann.hpp:1222-1242)
+//   libnabo knn               /root/reference/include/descriptor.h:1631,1642
+//
+// This file holds the EXACT variant: brute force over all keys with the reference's own float
+// accumulation order (nanoflann L2_Adaptor 4-wide groups, nanoflann.hpp:383-408, or libnabo's
+// sequential loop), every operation an explicit round-to-nearest intrinsic, so the distances
+// are bit-identical to the CPU path and the candidate set is identical except on exact ties
+// (ties: lowest key first; the trees keep the first-visited). The tensor-core prefilter
+// (k3_knn_tc.cu) only proposes candidates; what it proposes is re-ranked with the arithmetic here.
+//
+// Shape: grid = (key splits, query tiles of 128). A thread owns one query (its R key values in
+// registers) and streams its split of the key matrix through a shared-memory tile (coalesced
+// float4 loads, broadcast LDS.128 reads), keeping its own sorted top-K in shared memory
+// ([K][128] layout, conflict free). A second kernel k-way-merges the per-split lists of a
+// query with one warp.
+//
+// Roofline: the key matrix (4*R bytes/key) is streamed once per query tile from HBM/L2; the
+// kernel is FP32-issue bound (3 ops per dimension per pair), not memory bound.
+#include "common.cuh"
+#include "kernels.h"
+
+#include <cfloat>
+
+namespace {
+
+constexpr int kTQ = 128;      /* queries per CTA = threads per CTA */
+constexpr int kTK = 64;       /* keys per shared-memory tile */
+constexpr int kMaxK = 32;
+constexpr int kMaxSplits = 256;
+
+template <int R, int METRIC>
+__device__ __forceinline__ float key_d2(const float (&q)[R], const float* __restrict__ k)
+{
+    float result = 0.0f;
+    if (METRIC == 0) {
+        /* nanoflann.hpp:391-397: result += d0*d0 + d1*d1 + d2*d2 + d3*d3 (left to right) */
+#pragma unroll
+        for (int d = 0; d + 3 < R; d += 4) {
+            float4 kv;
+            if (R % 4 == 0) kv = *reinterpret_cast<const float4*>(k + d);      /* broadcast LDS.128 */
+            else kv = make_float4(k[d], k[d + 1], k[d + 2], k[d + 3]);
+            const float d0 = __fsub_rn(q[d], kv.x), d1 = __fsub_rn(q[d + 1], kv.y);
+            const float d2 = __fsub_rn(q[d + 2], kv.z), d3 = __fsub_rn(q[d + 3], kv.w);
+            const float g = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)), __fmul_rn(d3, d3));
+            result = __fadd_rn(result, g);
+        }
+#pragma unroll
+        for (int d = R & ~3; d < R; d++) { const float d0 = __fsub_rn(q[d], k[d]); result = __fadd_rn(result, __fmul_rn(d0, d0)); }
+    } else {
+#pragma unroll
+        for (int d = 0; d < R; d++) { const float d0 = __fsub_rn(q[d], k[d]); result = __fadd_rn(result, __fmul_rn(d0, d0)); }
+    }
+    return result;
+}
+
+template <int R, int METRIC>
+__global__ void __launch_bounds__(kTQ) knn_exact_kernel(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys,
+                                                        int n_db, int K, int split_len, int id_mul, int id_add,
+                                                        int32_t* __restrict__ part_ids, float* __restrict__ part_d2)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sk = reinterpret_cast<float*>(smem_raw);                 /* [kTK][R] */
+    float* ld = sk + kTK * R;                                       /* [K][kTQ] */
+    int* li = reinterpret_cast<int*>(ld + K * kTQ);                 /* [K][kTQ] */
+    const int t = threadIdx.x;
+    const int qi = blockIdx.y * kTQ + t;
+    const bool active = qi < Q;
+    float q[R];
+#pragma unroll
+    for (int d = 0; d < R; d++) q[d] = active ? __ldg(qkeys + (size_t)qi * R + d) : 0.0f;
+
+    const int k0 = blockIdx.x * split_len;
+    const int k1 = min(n_db, k0 + split_len);
+    int count = 0;
+    const float limit = (METRIC == 0) ? FLT_MAX : __int_as_float(0x7f800000);
+    float worst = limit;
+
+    for (int base = k0; base < k1; base += kTK) {
+        const int nk = min(kTK, k1 - base);
+        __syncthreads();
+        {   /* coalesced tile load; base*R*4 is a multiple of 16 because split_len and kTK are multiples of 4 */
+            const float4* src = reinterpret_cast<const float4*>(keys + (size_t)base * R);
+            float4* dst = reinterpret_cast<float4*>(sk);
+            const int n4 = nk * R / 4;
+            for (int i = t; i < n4; i += kTQ) dst[i] = __ldg(src + i);
+            for (int i = n4 * 4 + t; i < nk * R; i += kTQ) sk[i] = __ldg(keys + (size_t)base * R + i);
+        }
+        __syncthreads();
+        if (!active) continue;
+        for (int j = 0; j < nk; j++) {
+            const float d2 = key_d2<R, METRIC>(q, sk + j * R);
+            if (METRIC == 1 && !(d2 > FLT_EPSILON)) continue;       /* libnabo self-match rule */
+            if (!(d2 < worst)) continue;                             /* strict <: ties with the worst are rejected */
+            int i = count < K ? count : K - 1;
+            for (; i > 0 && ld[(i - 1) * kTQ + t] > d2; --i) {
+                ld[i * kTQ + t] = ld[(i - 1) * kTQ + t];
+                li[i * kTQ + t] = li[(i - 1) * kTQ + t];
+            }
+            ld[i * kTQ + t] = d2;
+            li[i * kTQ + t] = (base + j) * id_mul + id_add;
+            if (count < K) count++;
+            if (count == K) worst = ld[(K - 1) * kTQ + t];
+        }
+    }
+    if (!active) return;
+    const size_t o = ((size_t)qi * gridDim.x + blockIdx.x) * K;
+    for (int i = 0; i < K; i++) {
+        part_d2[o + i] = i < count ? ld[i * kTQ + t] : __int_as_float(0x7f800000);
+        part_ids[o + i] = i < count ? li[i * kTQ + t] : 0x7fffffff;
+    }
+}
+
+// k-way merge of the per-split sorted lists of one query by one warp; order = (d2, id).
+__global__ void __launch_bounds__(128) knn_merge_kernel(const int32_t* __restrict__ part_ids, const float* __restrict__ part_d2,
+                                                        int Q, int splits, int K, int32_t* __restrict__ out_ids, float* __restrict__ out_d2)
+{
+    const int lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= Q) return;
+    constexpr int kPer = kMaxSplits / 32;
+    int head[kPer];
+#pragma unroll
+    for (int s = 0; s < kPer; s++) head[s] = 0;
+    const int32_t* pi = part_ids + (size_t)qi * splits * K;
+    const float* pd = part_d2 + (size_t)qi * splits * K;
+    for (int r = 0; r < K; r++) {
+        float bd = __int_as_float(0x7f800000); int bi = 0x7fffffff; int bs = -1;
+#pragma unroll
+        for (int s = 0; s < kPer; s++) {
+            const int sp = lane + 32 * s;
+            if (sp < splits && head[s] < K) {
+                const float d = pd[(size_t)sp * K + head[s]]; const int id = pi[(size_t)sp * K + head[s]];
+                if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; bs = s; }
+            }
+        }
+        /* warp argmin on (d2, id) */
+        float wd = bd; int wi = bi;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, wd, off); const int oi = __shfl_xor_sync(0xffffffffu, wi, off);
+            if (od < wd || (od == wd && oi < wi)) { wd = od; wi = oi; }
+        }
+        const bool found = wi != 0x7fffffff;
+        if (bs >= 0 && bi == wi && bd == wd && found) {
+#pragma unroll
+            for (int s = 0; s < kPer; s++) if (s == bs) head[s]++;
+        }
+        if (lane == 0) {
+            out_ids[(size_t)qi * K + r] = found ? wi : -1;
+            out_d2[(size_t)qi * K + r] = found ? wd : FLT_MAX;
+        }
+    }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ rows, int n, int width, float* __restrict__ dst)
+{
+    const size_t total = (size_t)n * width;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / width), c = (int)(i % width);
+        dst[i] = __ldg(src + (size_t)rows[r] * width + c);
+    }
+}
+
+__global__ void ids_to_local_kernel(const int32_t* __restrict__ ids, int n, int id_mul, int id_add, int missing_to,
+                                    int32_t* __restrict__ ids_rewrite, int32_t* __restrict__ local)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int id = ids[i];
+    local[i] = id < 0 ? missing_to : (id - id_add) / id_mul;
+    if (ids_rewrite != nullptr && id < 0) ids_rewrite[i] = missing_to;
+}
+
+template <int R>
+cudaError_t launch_exact(const float* qkeys, int Q, const float* keys, int n_db, int K, int metric, int splits, int split_len,
+                         int id_mul, int id_add, KnnWorkspace ws, cudaStream_t stream)
+{
+    const size_t smem = (size_t)kTK * R * 4 + (size_t)K * kTQ * 8;
+    dim3 grid(splits, (Q + kTQ - 1) / kTQ);
+    if (metric == 0)
+        knn_exact_kernel<R, 0><<<grid, kTQ, smem, stream>>>(qkeys, Q, keys, n_db, K, split_len, id_mul, id_add, ws.part_ids, ws.part_d2);
+    else
+        knn_exact_kernel<R, 1><<<grid, kTQ, smem, stream>>>(qkeys, Q, keys, n_db, K, split_len, id_mul, id_add, ws.part_ids, ws.part_d2);
+    return cudaGetLastError();
+}
+
+} // namespace
+
+int scl_knn_splits(int Q, int n_db)
+{
+    const int tiles = (Q + kTQ - 1) / kTQ;
+    int splits = (4 * SCL_NUM_SMS + tiles - 1) / tiles;
+    const int max_by_keys = (n_db + 4 * kTK - 1) / (4 * kTK);
+    if (splits > max_by_keys) splits = max_by_keys;
+    if (splits > kMaxSplits) splits = kMaxSplits;
+    if (splits < 1) splits = 1;
+    return splits;
+}
+
+cudaError_t scl_launch_knn_exact(const float* qkeys, int Q, const float* keys, int n_db, int R, int K, int metric,
+                                 int id_mul, int id_add, KnnWorkspace ws, int32_t* out_ids, float* out_d2, cudaStream_t stream)
+{
+    if (Q <= 0) return cudaSuccess;
+    if (K < 1 || K > kMaxK) return cudaErrorInvalidValue;
+    const int splits = scl_knn_splits(Q, n_db);
+    int split_len = (n_db + splits - 1) / splits;
+    split_len = (split_len + kTK - 1) / kTK * kTK;
+    if (split_len < kTK) split_len = kTK;
+    if ((size_t)Q * splits * K > ws.capacity) return cudaErrorInvalidValue;
+    cudaError_t err;
+    if (R == 20) err = launch_exact<20>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, ws, stream);
+    else if (R == 40) err = launch_exact<40>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, ws, stream);
+    else if (R == 10) err = launch_exact<10>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, ws, stream);
+    else if (R == 80) err = launch_exact<80>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, ws, stream);
+    else return cudaErrorNotSupported;
+    if (err != cudaSuccess) return err;
+    const int warps = 4;
+    knn_merge_kernel<<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(ws.part_ids, ws.part_d2, Q, splits, K, out_ids, out_d2);
+    return cudaGetLastError();
+}
+
+cudaError_t scl_launch_gather_rows(const float* src, const int32_t* rows, int n, int width, float* dst, cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    const size_t total = (size_t)n * width;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 16 * SCL_NUM_SMS) blocks = 16 * SCL_NUM_SMS;
+    gather_rows_kernel<<<blocks, 256, 0, stream>>>(src, rows, n, width, dst);
+    return cudaGetLastError();
+}
+
+cudaError_t scl_launch_ids_to_local(const int32_t* ids, int n, int id_mul, int id_add, int missing_to, int32_t* ids_rewrite,
+                                    int32_t* local, cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    ids_to_local_kernel<<<(n + 255) / 256, 256, 0, stream>>>(ids, n, id_mul, id_add, missing_to, ids_rewrite, local);
+    return cudaGetLastError();
+}

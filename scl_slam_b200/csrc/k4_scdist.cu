@@ -1,0 +1,306 @@
+// k4_scdist.cu — K4, the shift-aligned column-cosine Scan Context distance.
+//
+// Replaces distanceBtnScanContext (/root/reference/include/descriptor.h:1538-1569) with its
+// parts makeSectorkeyFromScancontext (:1477-1489), fastAlignUsingVkey (:1491-1511), circshift
+// (:1376-1395) and distDirectSC (:1513-1536), and the candidate scan of
+// detectInterLoopClosureID (:1721-1737), for every (query, candidate) pair of a batch.
+//
+// One CTA per query, one warp per candidate (warps loop when K exceeds the warps that fit in
+// shared memory). The query descriptor and each candidate descriptor (R*S floats, contiguous
+// in the database) are fetched with ONE bulk-copy instruction each (cp.async.bulk, the TMA
+// engine; completion on an mbarrier), so the gather is issued by a single lane and overlaps
+// the arithmetic of the other warps.
+//
+// Arithmetic is FP64 with the reference's own operation order — sequential sums in index
+// order, explicit round-to-nearest mul/add (no FMA), IEEE sqrt and divide — so the distance,
+// and therefore the argmin shift and the winning candidate, are bit-identical to the CPU path:
+//   * lane <-> column for the column sums, norms and per-column cosine terms,
+//   * lane <-> shift for the S sector-key alignment norms,
+//   * one lane per window shift for the in-order sum over columns,
+//   * window shifts visited in ascending order with strict <, candidates in kNN order with
+//     strict < and the self-skip rule.
+// Nothing is cached per database entry: sector keys and column norms are recomputed from the
+// descriptor tile that is in shared memory anyway, so the only HBM traffic is the descriptors.
+//
+// Roofline: HBM gather, 4*R*S*(K+1) bytes per query; ~31k FP64 operations per pair at 20x60.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+constexpr int kShiftChunk = 8;
+
+struct ScLayout {
+    int RS, S, warps;
+    size_t off_q, off_c, off_vq, off_nq, off_warp, warp_stride, off_res, total;
+};
+
+__host__ __device__ inline ScLayout sc_layout(int R, int S, int K, int warps)
+{
+    ScLayout L;
+    L.RS = R * S; L.S = S; L.warps = warps;
+    size_t o = 16 * ((size_t)(1 + warps) * 8 / 16 + 1);        /* mbarriers */
+    L.off_q = o; o += (size_t)L.RS * 4;
+    L.off_c = o; o += (size_t)warps * L.RS * 4;
+    o = (o + 15) / 16 * 16;
+    L.off_vq = o; o += (size_t)S * 8;
+    L.off_nq = o; o += (size_t)S * 8;
+    L.off_warp = o;
+    L.warp_stride = (size_t)(2 + kShiftChunk) * S * 8;          /* vc, nc, sim[kShiftChunk][S] */
+    o += (size_t)warps * L.warp_stride;
+    L.off_res = o; o += (size_t)K * 16;                         /* dist[K] doubles, shift[K] ints */
+    L.total = o;
+    return L;
+}
+
+// sequential column statistics of a row-major R x S float tile: mean (sector key, :1477-1489)
+// and Euclidean norm (col.norm(), :1523) in double
+__device__ __forceinline__ void column_stats(const float* __restrict__ d, int R, int S, int j, double& mean, double& norm)
+{
+    double s = 0.0, ss = 0.0;
+    for (int r = 0; r < R; r++) {
+        const double v = (double)d[r * S + j];
+        s = __dadd_rn(s, v);
+        ss = __dadd_rn(ss, __dmul_rn(v, v));
+    }
+    mean = __ddiv_rn(s, (double)R);
+    norm = __dsqrt_rn(ss);
+}
+
+__global__ void __launch_bounds__(512) scdist_kernel(
+    const float* __restrict__ db_desc, const float* __restrict__ q_desc, const int32_t* __restrict__ q_local,
+    const int32_t* __restrict__ q_ids, const int32_t* __restrict__ cand_local, const int32_t* __restrict__ cand_ids,
+    int K, int R, int S, int search_radius, int use_bulk,
+    double* __restrict__ cand_dist, int32_t* __restrict__ cand_shift,
+    int32_t* __restrict__ best_id, double* __restrict__ best_dist, int32_t* __restrict__ best_shift)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const ScLayout L = sc_layout(R, S, K, warps);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    float* qd = reinterpret_cast<float*>(smem + L.off_q);
+    float* cd = reinterpret_cast<float*>(smem + L.off_c) + (size_t)warp * L.RS;
+    double* vq = reinterpret_cast<double*>(smem + L.off_vq);
+    double* nq = reinterpret_cast<double*>(smem + L.off_nq);
+    double* vc = reinterpret_cast<double*>(smem + L.off_warp + (size_t)warp * L.warp_stride);
+    double* nc = vc + S;
+    double* sim = nc + S;
+    double* res_dist = reinterpret_cast<double*>(smem + L.off_res);
+    int* res_shift = reinterpret_cast<int*>(res_dist + K);
+    const int qi = blockIdx.x;
+    const int RS = L.RS;
+    const uint32_t bytes = (uint32_t)RS * 4u;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 1 + warps; i++) scl_mbar_init(&bars[i], 1);
+        scl_mbar_fence_init();
+    }
+    __syncthreads();
+
+    const float* qsrc = q_desc ? q_desc + (size_t)qi * RS : db_desc + (size_t)q_local[qi] * RS;
+    if (use_bulk) {
+        if (threadIdx.x == 0) { scl_mbar_expect_tx(&bars[0], bytes); scl_bulk_g2s(qd, qsrc, bytes, &bars[0]); }
+    } else {
+        for (int i = threadIdx.x; i < RS; i += blockDim.x) qd[i] = __ldg(qsrc + i);
+    }
+    /* first candidate of every warp goes in flight before anyone waits */
+    int it = warp;
+    int c_local = it < K ? cand_local[(size_t)qi * K + it] : -1;
+    if (use_bulk && lane == 0 && c_local >= 0) {
+        scl_mbar_expect_tx(&bars[1 + warp], bytes);
+        scl_bulk_g2s(cd, db_desc + (size_t)c_local * RS, bytes, &bars[1 + warp]);
+    }
+    if (use_bulk) scl_mbar_wait(&bars[0], 0);
+    else __syncthreads();
+    for (int j = threadIdx.x; j < S; j += blockDim.x) column_stats(qd, R, S, j, vq[j], nq[j]);
+    __syncthreads();
+
+    uint32_t parity = 0;
+    for (; it < K; it += warps) {
+        double out_dist = __longlong_as_double(0x7ff8000000000000LL); /* NaN: candidate missing */
+        int out_shift = 0;
+        if (c_local >= 0) {
+            if (use_bulk) { scl_mbar_wait(&bars[1 + warp], parity); parity ^= 1u; }
+            else { for (int i = lane; i < RS; i += 32) cd[i] = __ldg(db_desc + (size_t)c_local * RS + i); __syncwarp(); }
+            /* a. candidate sector key and column norms */
+            for (int j = lane; j < S; j += 32) column_stats(cd, R, S, j, vc[j], nc[j]);
+            __syncwarp();
+            /* b. fastAlignUsingVkey: lane <-> shift, sequential over columns (:1496-1508) */
+            double bestn = 10000000.0; int bests = 0x7fffffff;
+            for (int s = lane; s < S; s += 32) {
+                double ss = 0.0;
+                int idx = S - s;                       /* (0 - s + S) % S, walks forward with j */
+                if (idx == S) idx = 0;
+                for (int j = 0; j < S; j++) {
+                    const double d = __dsub_rn(vq[j], vc[idx]);
+                    ss = __dadd_rn(ss, __dmul_rn(d, d));
+                    if (++idx == S) idx = 0;
+                }
+                const double nrm = __dsqrt_rn(ss);
+                if (nrm < bestn) { bestn = nrm; bests = s; }   /* ascending s per lane: first minimum wins */
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double on = __shfl_xor_sync(0xffffffffu, bestn, off); const int os = __shfl_xor_sync(0xffffffffu, bests, off);
+                if (on < bestn || (on == bestn && os < bests)) { bestn = on; bests = os; }
+            }
+            const int align = (bests == 0x7fffffff) ? 0 : bests;   /* no norm below 1e7: argmin stays 0 (:1493) */
+            /* c. window of shifts around the alignment, ascending, strict < (:1545-1566) */
+            double min_sc = 10000000.0; int argmin_shift = 0;
+            int s_next = 0;
+            while (s_next < S) {
+                int shifts[kShiftChunk]; int ns = 0;
+                for (; s_next < S && ns < kShiftChunk; s_next++) {
+                    int diff = s_next - align; if (diff < 0) diff += S;
+                    const int cdist = min(diff, S - diff);
+                    if (cdist <= search_radius) shifts[ns++] = s_next;
+                }
+                if (ns == 0) break;
+#pragma unroll
+                for (int w = 0; w < kShiftChunk; w++) {
+                    if (w < ns) {
+                        const int s = shifts[w];
+                        for (int j = lane; j < S; j += 32) {
+                            int cb = j - s; if (cb < 0) cb += S;      /* circshift: shifted.col(j) = sc2.col(j - s) */
+                            const double na = nq[j], nb = nc[cb];
+                            double v = 0.0;
+                            if (!((na == 0.0) | (nb == 0.0))) {
+                                double dot = 0.0;
+                                for (int r = 0; r < R; r++) dot = __dadd_rn(dot, __dmul_rn((double)qd[r * S + j], (double)cd[r * S + cb]));
+                                v = __ddiv_rn(dot, __dmul_rn(na, nb));
+                            }
+                            sim[w * S + j] = v;
+                        }
+                    }
+                }
+                __syncwarp();
+                double dist = 0.0;
+                if (lane < ns) {                                       /* one lane per shift: in-order sum over columns */
+                    int my_s = 0;                                      /* shifts[] is warp-uniform; select by lane */
+#pragma unroll
+                    for (int w = 0; w < kShiftChunk; w++) if (w == lane) my_s = shifts[w];
+                    double sum = 0.0; int cnt = 0;
+                    for (int j = 0; j < S; j++) {
+                        int cb = j - my_s; if (cb < 0) cb += S;
+                        if (!((nq[j] == 0.0) | (nc[cb] == 0.0))) { sum = __dadd_rn(sum, sim[lane * S + j]); cnt++; }
+                    }
+                    dist = __dsub_rn(1.0, __ddiv_rn(sum, (double)cnt));   /* 0/0 = NaN when no column counts (:1534) */
+                }
+#pragma unroll
+                for (int w = 0; w < kShiftChunk; w++) {
+                    const double d = __shfl_sync(0xffffffffu, dist, w);
+                    if (w < ns && d < min_sc) { min_sc = d; argmin_shift = shifts[w]; }
+                }
+                __syncwarp();
+            }
+            out_dist = min_sc; out_shift = argmin_shift;
+        }
+        if (lane == 0) {
+            res_dist[it] = out_dist; res_shift[it] = out_shift;
+            if (cand_dist) cand_dist[(size_t)qi * K + it] = out_dist;
+            if (cand_shift) cand_shift[(size_t)qi * K + it] = out_shift;
+        }
+        /* next candidate of this warp into the same tile */
+        const int nxt = it + warps;
+        c_local = nxt < K ? cand_local[(size_t)qi * K + nxt] : -1;
+        __syncwarp();
+        if (use_bulk && lane == 0 && c_local >= 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            scl_mbar_expect_tx(&bars[1 + warp], bytes);
+            scl_bulk_g2s(cd, db_desc + (size_t)c_local * RS, bytes, &bars[1 + warp]);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        /* candidate scan in kNN order, strict <, query itself skipped (:1721-1737) */
+        double min_dist = 10000000.0; int nn_align = 0, nn_idx = -1;
+        const int self = q_ids ? q_ids[qi] : -1;
+        for (int i = 0; i < K; i++) {
+            const int id = cand_ids[(size_t)qi * K + i];
+            if (id < 0) continue;
+            if (res_dist[i] < min_dist && id != self) { min_dist = res_dist[i]; nn_align = res_shift[i]; nn_idx = id; }
+        }
+        if (best_id) best_id[qi] = nn_idx;
+        if (best_dist) best_dist[qi] = min_dist;
+        if (best_shift) best_shift[qi] = nn_align;
+    }
+}
+
+// Multi-GPU merge: per query, world*K records -> global top-K by (d2, id), then the winner scan.
+__global__ void merge_shards_kernel(int world, int Q, int K, const int32_t* __restrict__ q_ids,
+                                    const int32_t* __restrict__ all_ids, const float* __restrict__ all_d2,
+                                    const double* __restrict__ all_dist, const int32_t* __restrict__ all_shift,
+                                    int32_t* __restrict__ out_ids, float* __restrict__ out_d2, double* __restrict__ out_dist,
+                                    int32_t* __restrict__ out_shift, int32_t* __restrict__ best_id, double* __restrict__ best_dist,
+                                    int32_t* __restrict__ best_shift)
+{
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= Q) return;
+    int head[16];
+    for (int w = 0; w < world; w++) head[w] = 0;
+    double min_dist = 10000000.0; int nn_align = 0, nn_idx = -1;
+    const int self = q_ids ? q_ids[qi] : -1;
+    for (int r = 0; r < K; r++) {
+        int bw = -1; float bd = 0.f; int bi = 0;
+        for (int w = 0; w < world; w++) {
+            if (head[w] >= K) continue;
+            const size_t o = ((size_t)w * Q + qi) * K + head[w];
+            const int id = all_ids[o];
+            if (id < 0) { head[w] = K; continue; }
+            const float d = all_d2[o];
+            if (bw < 0 || d < bd || (d == bd && id < bi)) { bw = w; bd = d; bi = id; }
+        }
+        int id = -1; float d2 = 3.402823466e+38f; double dist = __longlong_as_double(0x7ff8000000000000LL); int shift = 0;
+        if (bw >= 0) {
+            const size_t o = ((size_t)bw * Q + qi) * K + head[bw];
+            id = bi; d2 = bd; dist = all_dist[o]; shift = all_shift[o];
+            head[bw]++;
+            if (dist < min_dist && id != self) { min_dist = dist; nn_align = shift; nn_idx = id; }
+        }
+        if (out_ids) out_ids[(size_t)qi * K + r] = id;
+        if (out_d2) out_d2[(size_t)qi * K + r] = d2;
+        if (out_dist) out_dist[(size_t)qi * K + r] = dist;
+        if (out_shift) out_shift[(size_t)qi * K + r] = shift;
+    }
+    if (best_id) best_id[qi] = nn_idx;
+    if (best_dist) best_dist[qi] = min_dist;
+    if (best_shift) best_shift[qi] = nn_align;
+}
+
+} // namespace
+
+cudaError_t scl_launch_scdist(const float* db_desc, const float* q_desc, const int32_t* q_local, const int32_t* q_ids,
+                              const int32_t* cand_local, const int32_t* cand_ids, int Q, int K, int R, int S, int search_radius,
+                              double* cand_dist, int32_t* cand_shift, int32_t* best_id, double* best_dist, int32_t* best_shift,
+                              cudaStream_t stream)
+{
+    if (Q <= 0) return cudaSuccess;
+    const size_t budget = 200 * 1024;
+    int warps = K < 16 ? K : 16;
+    while (warps > 1 && sc_layout(R, S, K, warps).total > budget) warps--;
+    const ScLayout L = sc_layout(R, S, K, warps);
+    if (L.total > 227 * 1024) return cudaErrorNotSupported;
+    static size_t attr_set = 0;
+    if (L.total > attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(scdist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+        if (e != cudaSuccess) return e;
+        attr_set = 227 * 1024;
+    }
+    const int use_bulk = ((R * S) % 4 == 0) && ((reinterpret_cast<uintptr_t>(db_desc) & 15) == 0) &&
+                         (q_desc == nullptr || (reinterpret_cast<uintptr_t>(q_desc) & 15) == 0);
+    scdist_kernel<<<Q, warps * 32, L.total, stream>>>(db_desc, q_desc, q_local, q_ids, cand_local, cand_ids, K, R, S, search_radius,
+                                                      use_bulk, cand_dist, cand_shift, best_id, best_dist, best_shift);
+    return cudaGetLastError();
+}
+
+cudaError_t scl_launch_merge_shards(int world, int Q, int K, const int32_t* q_ids, const int32_t* all_ids, const float* all_d2,
+                                    const double* all_dist, const int32_t* all_shift, int32_t* out_ids, float* out_d2,
+                                    double* out_dist, int32_t* out_shift, int32_t* best_id, double* best_dist, int32_t* best_shift,
+                                    cudaStream_t stream)
+{
+    if (Q <= 0) return cudaSuccess;
+    if (world < 1 || world > 16) return cudaErrorInvalidValue;
+    merge_shards_kernel<<<(Q + 127) / 128, 128, 0, stream>>>(world, Q, K, q_ids, all_ids, all_d2, all_dist, all_shift,
+                                                            out_ids, out_d2, out_dist, out_shift, best_id, best_dist, best_shift);
+    return cudaGetLastError();
+}

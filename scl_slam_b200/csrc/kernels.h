@@ -1,0 +1,46 @@
+// kernels.h — launchers of the sm_100a kernels (internal; the public boundary is include/scl_engine.h)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// K1 (+K2 epilogue): polar binning of a batch of scans. See k1_polar.cu.
+cudaError_t scl_launch_polar(const void* pts_dev, const int* offsets_dev, int n_scans, int max_points, int stride_bytes,
+                             int R, int S, double lidar_height, double max_radius, uint32_t* gbins, int* tickets,
+                             float* out_desc, float* out_keys, float* out_knorm, int* out_ring, int* out_sector,
+                             cudaStream_t stream);
+// K2: ring keys (+ squared key norms) of descriptors already in device memory.
+cudaError_t scl_launch_ring_keys(const float* desc_dev, int n, int R, int S, float* keys, float* knorm, cudaStream_t stream);
+
+// K3: ring-key kNN. Exact variant (CUDA cores, reference accumulation order). See k3_knn.cu.
+//  qkeys [Q][R], keys [n_db][R]; out ids/d2 [Q][K] ascending by (d2, id); id_mul/id_add map local
+//  key l to the reported global id l*id_mul + id_add (database sharding).
+struct KnnWorkspace {
+    int32_t* part_ids;   // [Q][splits][K]
+    float* part_d2;      // [Q][splits][K]
+    size_t capacity;     // in entries
+};
+int scl_knn_splits(int Q, int n_db);
+cudaError_t scl_launch_knn_exact(const float* qkeys, int Q, const float* keys, int n_db, int R, int K, int metric,
+                                 int id_mul, int id_add, KnnWorkspace ws, int32_t* out_ids, float* out_d2, cudaStream_t stream);
+
+// K4: shift-aligned column-cosine distance for every (query, candidate) + winner scan. See k4_scdist.cu.
+//  q_desc [Q][R*S] or nullptr (then queries are db entries q_local[i]); cand_local [Q][K] local keys (-1 = none);
+//  cand_ids [Q][K] reported ids (for the self-skip rule against q_ids).
+cudaError_t scl_launch_scdist(const float* db_desc, const float* q_desc, const int32_t* q_local, const int32_t* q_ids,
+                              const int32_t* cand_local, const int32_t* cand_ids, int Q, int K, int R, int S, int search_radius,
+                              double* cand_dist, int32_t* cand_shift, int32_t* best_id, double* best_dist, int32_t* best_shift,
+                              cudaStream_t stream);
+
+// Shard merge (multi-GPU): world blocks of [Q][K] records -> global top-K by (d2,id) + winner scan.
+cudaError_t scl_launch_merge_shards(int world, int Q, int K, const int32_t* q_ids, const int32_t* all_ids, const float* all_d2,
+                                    const double* all_dist, const int32_t* all_shift, int32_t* out_ids, float* out_d2,
+                                    double* out_dist, int32_t* out_shift, int32_t* best_id, double* best_dist, int32_t* best_shift,
+                                    cudaStream_t stream);
+
+// small helpers
+cudaError_t scl_launch_gather_rows(const float* src, const int32_t* rows, int n, int width, float* dst, cudaStream_t stream);
+// reported id -> local key ((id - id_add) / id_mul); missing (-1) entries become `missing_to`, and are
+// also rewritten in ids_rewrite when that is non-null
+cudaError_t scl_launch_ids_to_local(const int32_t* ids, int n, int id_mul, int id_add, int missing_to, int32_t* ids_rewrite,
+                                    int32_t* local, cudaStream_t stream);

@@ -1,0 +1,271 @@
+"""Python mirror of the reference's descriptor interface over the C-ABI engine.
+
+`ScanContextB200` exposes the six `scan_descriptor` virtuals of
+/root/reference/include/descriptor.h:21-36 with the reference's own names and argument meaning
+(`makeAndSaveDescriptorAndKey`, `saveDescriptorAndKey`, `detectIntraLoopClosureID`,
+`detectInterLoopClosureID`, `getIndex`, `getSize`) plus the batched throughput calls. Every
+method is one call into scl_slam_b200/libscl_b200.so (include/scl_engine.h); torch is used only
+to own device buffers and streams. There is NO CPU fallback: importing this module without the
+built library, or constructing an engine without a CUDA device, raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libscl_b200.so")
+
+SCL_OK = 0
+_STATUS = {1: "SCL_ERR_INVALID", 2: "SCL_ERR_CUDA", 3: "SCL_ERR_UNSUPPORTED", 4: "SCL_ERR_RANGE", 5: "SCL_ERR_NOMEM"}
+
+# every symbol include/scl_engine.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "scl_default_params", "scl_default_icp_params", "scl_create", "scl_destroy", "scl_last_error", "scl_set_stream",
+    "scl_reserve", "scl_set_shard", "scl_build_insert", "scl_make_scancontext", "scl_build_batch", "scl_build_batch_dev",
+    "scl_insert", "scl_insert_batch", "scl_insert_batch_dev", "scl_get_index", "scl_size", "scl_get_descriptor",
+    "scl_get_ring_key", "scl_query_intra", "scl_query_inter", "scl_query_batch", "scl_query_batch_dev",
+    "scl_merge_shards_dev", "scl_icp",
+]
+
+
+class SclParams(C.Structure):
+    _fields_ = [("num_ring", C.c_int), ("num_sector", C.c_int), ("num_candidates", C.c_int),
+                ("dist_thres", C.c_double), ("lidar_height", C.c_double), ("max_radius", C.c_double),
+                ("num_exclude_recent", C.c_int), ("tree_making_period", C.c_int), ("search_ratio", C.c_double)]
+
+
+class SclBatchQuery(C.Structure):
+    _fields_ = [("q_desc", C.c_void_p), ("q_ids", C.c_void_p), ("Q", C.c_int), ("K", C.c_int),
+                ("n_db", C.c_int), ("metric", C.c_int)]
+
+
+class SclBatchResult(C.Structure):
+    _fields_ = [("cand_ids", C.c_void_p), ("cand_d2", C.c_void_p), ("cand_dist", C.c_void_p),
+                ("cand_shift", C.c_void_p), ("best_id", C.c_void_p), ("best_dist", C.c_void_p),
+                ("best_shift", C.c_void_p)]
+
+
+class SclIcpParams(C.Structure):
+    _fields_ = [("max_corr_dist", C.c_double), ("max_iterations", C.c_int), ("trans_eps", C.c_double),
+                ("fitness_eps", C.c_double)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the engine. Raises if it has not been built (python -m scl_slam_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise RuntimeError(f"{_SO} is missing: build it with `python scl_slam_b200/build.py` "
+                           "(there is no CPU fallback for the Scan Context engine)")
+    lib = C.CDLL(_SO)
+    lib.scl_last_error.restype = C.c_char_p
+    lib.scl_last_error.argtypes = [C.c_void_p]
+    lib.scl_create.argtypes = [C.POINTER(SclParams), C.c_int, C.POINTER(C.c_void_p)]
+    lib.scl_destroy.argtypes = [C.c_void_p]
+    lib.scl_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.scl_reserve.argtypes = [C.c_void_p, C.c_int]
+    lib.scl_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.scl_build_insert.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int8, C.c_int, C.c_void_p]
+    lib.scl_make_scancontext.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.scl_build_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.scl_build_batch_dev.argtypes = lib.scl_build_batch.argtypes
+    lib.scl_insert.argtypes = [C.c_void_p, C.c_void_p, C.c_int8, C.c_int]
+    lib.scl_insert_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.scl_insert_batch_dev.argtypes = lib.scl_insert_batch.argtypes
+    lib.scl_get_index.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int8), C.POINTER(C.c_int)]
+    lib.scl_size.argtypes = [C.c_void_p]
+    lib.scl_get_descriptor.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.scl_get_ring_key.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.scl_query_intra.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+    lib.scl_query_inter.argtypes = lib.scl_query_intra.argtypes
+    lib.scl_query_batch.argtypes = [C.c_void_p, C.POINTER(SclBatchQuery), C.POINTER(SclBatchResult)]
+    lib.scl_query_batch_dev.argtypes = lib.scl_query_batch.argtypes
+    lib.scl_merge_shards_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.POINTER(SclBatchResult)]
+    lib.scl_icp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(SclIcpParams),
+                            C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()  # torch tensor
+
+
+def _cloud(points):
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    if pts.ndim != 2 or pts.shape[1] < 3:
+        raise ValueError("points must be [P, >=3] float32 (x, y, z first)")
+    return pts, pts.shape[0], pts.shape[1] * 4
+
+
+class ScanContextB200:
+    """Drop-in for scan_context_descriptor (descriptor.h:1304-1801); constructor arguments and
+    defaults are those of descriptor.h:1307-1316."""
+
+    def __init__(self, numRing=20, numSector=60, numCandidates=3, distThres=0.14, lidarHeight=1.65,
+                 maxRadius=80.0, numExcludeRecent=100, treeMakingPeriod=10, searchRatio=0.1, device=0):
+        self.lib = load_library()
+        self.params = SclParams(numRing, numSector, numCandidates, distThres, lidarHeight, maxRadius,
+                                numExcludeRecent, treeMakingPeriod, searchRatio)
+        self.R, self.S, self.K = numRing, numSector, numCandidates
+        self.h = C.c_void_p()
+        rc = self.lib.scl_create(C.byref(self.params), device, C.byref(self.h))
+        if rc != SCL_OK:
+            self.h = None
+            raise RuntimeError(f"scl_create failed: {_STATUS.get(rc, rc)} (a CUDA device is required; no CPU fallback)")
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.scl_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc != SCL_OK:
+            raise RuntimeError(f"{_STATUS.get(rc, rc)}: {self.lib.scl_last_error(self.h).decode()}")
+
+    # ---- the six scan_descriptor virtuals (descriptor.h:25-35) ----------------------------
+    def makeAndSaveDescriptorAndKey(self, scan, robot, index):
+        pts, n, stride = _cloud(scan)
+        out = np.empty(self.R * self.S, np.float32)
+        self._ck(self.lib.scl_build_insert(self.h, pts.ctypes.data, n, stride, robot, index, out.ctypes.data))
+        return out
+
+    def saveDescriptorAndKey(self, descriptorMat, robot, index):
+        d = np.ascontiguousarray(descriptorMat, np.float32).reshape(-1)
+        if d.size != self.R * self.S:
+            raise ValueError("descriptor must have R*S floats")
+        self._ck(self.lib.scl_insert(self.h, d.ctypes.data, robot, index))
+
+    def detectIntraLoopClosureID(self, currentPtr):
+        i, f = C.c_int(), C.c_float()
+        self._ck(self.lib.scl_query_intra(self.h, currentPtr, C.byref(i), C.byref(f)))
+        return i.value, f.value
+
+    def detectInterLoopClosureID(self, currentPtr):
+        i, f = C.c_int(), C.c_float()
+        self._ck(self.lib.scl_query_inter(self.h, currentPtr, C.byref(i), C.byref(f)))
+        return i.value, f.value
+
+    def getIndex(self, key):
+        r, i = C.c_int8(), C.c_int()
+        self._ck(self.lib.scl_get_index(self.h, key, C.byref(r), C.byref(i)))
+        return r.value, i.value
+
+    def getSize(self, idIn=-1):
+        return self.lib.scl_size(self.h)
+
+    # ---- pieces of the path, for parity checks --------------------------------------------
+    def make_scancontext(self, scan, want_bins=False):
+        pts, n, stride = _cloud(scan)
+        out = np.empty(self.R * self.S, np.float32)
+        ring = np.zeros(n, np.int32) if want_bins else None
+        sector = np.zeros(n, np.int32) if want_bins else None
+        self._ck(self.lib.scl_make_scancontext(self.h, pts.ctypes.data, n, stride, out.ctypes.data, _ptr(ring), _ptr(sector)))
+        out = out.reshape(self.R, self.S)
+        return (out, ring, sector) if want_bins else out
+
+    def desc(self, key):
+        out = np.empty(self.R * self.S, np.float32)
+        self._ck(self.lib.scl_get_descriptor(self.h, key, out.ctypes.data))
+        return out.reshape(self.R, self.S)
+
+    def ring_key(self, key):
+        out = np.empty(self.R, np.float32)
+        self._ck(self.lib.scl_get_ring_key(self.h, key, out.ctypes.data))
+        return out
+
+    # ---- batched forms ----------------------------------------------------------------------
+    def reserve(self, capacity):
+        self._ck(self.lib.scl_reserve(self.h, capacity))
+
+    def set_shard(self, rank, world):
+        self._ck(self.lib.scl_set_shard(self.h, rank, world))
+
+    def set_stream(self, cuda_stream_handle):
+        self._ck(self.lib.scl_set_stream(self.h, C.c_void_p(cuda_stream_handle)))
+
+    def build_batch(self, clouds, insert=True, robots=None, indices=None):
+        """clouds: list of [P_i, C] float32 arrays with one common C. Returns [n, R, S] descriptors."""
+        arrs = [np.ascontiguousarray(c, np.float32) for c in clouds]
+        stride = arrs[0].shape[1] * 4
+        offs = np.zeros(len(arrs) + 1, np.int32)
+        offs[1:] = np.cumsum([a.shape[0] for a in arrs])
+        pts = np.concatenate(arrs) if arrs else np.zeros((0, 4), np.float32)
+        out = np.empty((len(arrs), self.R, self.S), np.float32)
+        rb = None if robots is None else np.ascontiguousarray(robots, np.int8)
+        ix = None if indices is None else np.ascontiguousarray(indices, np.int32)
+        self._ck(self.lib.scl_build_batch(self.h, pts.ctypes.data, offs.ctypes.data, len(arrs), stride, int(insert),
+                                          _ptr(rb), _ptr(ix), out.ctypes.data))
+        return out
+
+    def build_batch_dev(self, pts_dev, offsets, stride_bytes, insert=True, out_dev=None):
+        offs = np.ascontiguousarray(offsets, np.int32)
+        self._ck(self.lib.scl_build_batch_dev(self.h, _ptr(pts_dev), offs.ctypes.data, offs.size - 1, stride_bytes,
+                                              int(insert), None, None, _ptr(out_dev)))
+
+    def insert_batch(self, descs, robots=None, indices=None):
+        d = np.ascontiguousarray(descs, np.float32).reshape(-1, self.R * self.S)
+        rb = None if robots is None else np.ascontiguousarray(robots, np.int8)
+        ix = None if indices is None else np.ascontiguousarray(indices, np.int32)
+        self._ck(self.lib.scl_insert_batch(self.h, d.ctypes.data, d.shape[0], _ptr(rb), _ptr(ix)))
+
+    def insert_batch_dev(self, descs_dev):
+        """descs_dev: contiguous float32 CUDA tensor [n, R, S] (or [n, R*S])."""
+        n = descs_dev.shape[0]
+        self._ck(self.lib.scl_insert_batch_dev(self.h, descs_dev.data_ptr(), n, None, None))
+
+    def query_batch(self, q_desc=None, q_ids=None, K=None, n_db=None, metric=0):
+        """Host-buffer batch query. Returns a dict of numpy arrays (see scl_batch_result)."""
+        K = K or self.K
+        qd = None if q_desc is None else np.ascontiguousarray(q_desc, np.float32).reshape(-1, self.R * self.S)
+        qi = None if q_ids is None else np.ascontiguousarray(q_ids, np.int32)
+        Q = qd.shape[0] if qd is not None else qi.size
+        n_db = self.getSize() if n_db is None else n_db
+        out = dict(cand_ids=np.empty((Q, K), np.int32), cand_d2=np.empty((Q, K), np.float32),
+                   cand_dist=np.empty((Q, K), np.float64), cand_shift=np.empty((Q, K), np.int32),
+                   best_id=np.empty(Q, np.int32), best_dist=np.empty(Q, np.float64), best_shift=np.empty(Q, np.int32))
+        q = SclBatchQuery(_ptr(qd), _ptr(qi), Q, K, n_db, metric)
+        r = SclBatchResult(*[out[k].ctypes.data for k in
+                             ("cand_ids", "cand_d2", "cand_dist", "cand_shift", "best_id", "best_dist", "best_shift")])
+        self._ck(self.lib.scl_query_batch(self.h, C.byref(q), C.byref(r)))
+        return out
+
+    def query_batch_dev(self, q_desc_dev, q_ids_dev, Q, K, n_db, metric, out):
+        """Device-pointer batch query, asynchronous on the engine's stream. `out` maps the
+        scl_batch_result field names to CUDA tensors (missing names are not produced)."""
+        q = SclBatchQuery(_ptr(q_desc_dev), _ptr(q_ids_dev), Q, K, n_db, metric)
+        r = SclBatchResult(*[_ptr(out.get(k)) for k in
+                             ("cand_ids", "cand_d2", "cand_dist", "cand_shift", "best_id", "best_dist", "best_shift")])
+        self._ck(self.lib.scl_query_batch_dev(self.h, C.byref(q), C.byref(r)))
+
+    def merge_shards_dev(self, world, Q, K, q_ids_dev, all_ids, all_d2, all_dist, all_shift, out):
+        r = SclBatchResult(*[_ptr(out.get(k)) for k in
+                             ("cand_ids", "cand_d2", "cand_dist", "cand_shift", "best_id", "best_dist", "best_shift")])
+        self._ck(self.lib.scl_merge_shards_dev(self.h, world, Q, K, _ptr(q_ids_dev), _ptr(all_ids), _ptr(all_d2),
+                                               _ptr(all_dist), _ptr(all_shift), C.byref(r)))
+
+    # ---- geometric verification (distributedMapping.h:1108-1132) ---------------------------
+    def icp(self, src, tgt, max_corr_dist=100.0, max_iterations=50, trans_eps=1e-6, fitness_eps=1e-6):
+        s, ns, stride = _cloud(src)
+        t, nt, stride_t = _cloud(tgt)
+        if stride != stride_t:
+            raise ValueError("src and tgt must share a point stride")
+        p = SclIcpParams(max_corr_dist, max_iterations, trans_eps, fitness_eps)
+        T = np.empty(16, np.float32)
+        fit, conv, it = C.c_float(), C.c_int(), C.c_int()
+        self._ck(self.lib.scl_icp(self.h, s.ctypes.data, ns, t.ctypes.data, nt, stride, C.byref(p), T.ctypes.data,
+                                  C.byref(fit), C.byref(conv), C.byref(it)))
+        return T.reshape(4, 4), fit.value, bool(conv.value), it.value
