@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — loop queries/s of the Scan Context loop-closure path on B200 (contract in the task brief).
+
+Workload (BASELINE.json configs[2], the one the metric is quoted on; it fits one GPU):
+  1,048,576-keyframe synthetic 20x60 descriptor database (seed 3) resident in
+  HBM, one step = one batch of 1,024 queries (seed 4; perturbed + rotated database entries),
+  each answered with the ring-key top-10 + the shift-aligned SC distance of every candidate and
+  the winning (id, shift).
+
+  value : whole-job queries/s, queries already in HBM when the timed region starts
+  e2e   : the same through the public host-buffer call (scl_query_batch): pinned host queries,
+          H2D + kernels + D2H of the winners inside the timed region
+  N > 1 : the database is sharded by key (key mod N) over the ranks, queries replicated, each
+          rank's local top-K records merged after one NCCL all-gather (strong scaling: the
+          1M database and the 1,024-query batch are fixed)
+  --impl reference : the reference's own CPU path (oracle/_ref: its class text + vendored
+          nanoflann; else the restatement) on the host cores, on a bounded sample of the batch
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_DB = 1 << 20
+Q, K, R, S = 1024, 10, 20, 60
+WORKLOAD = "c3_db1048576_20x60_q1024_top10"
+METRIC = "loop_queries_per_sec"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tc=d["bf16_tflops"], tc_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tc=1590.0, tc_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def gen_shard(dev, rank, world, n_db):
+    """Rows of the global database owned by this rank (global key = local*world + rank)."""
+    from scl_slam_b200 import synth
+    n_local = (n_db - rank + world - 1) // world
+    if world == 1:
+        return n_local, lambda c0, m: synth.desc_db(m, R, S, seed=3, device=dev, start=c0)
+
+    def chunk(c0, m):
+        full = synth.desc_db(m * world, R, S, seed=3, device=dev, start=c0 * world)
+        return full[rank::world][:m].contiguous()
+    return n_local, chunk
+
+
+def gen_queries(dev):
+    from scl_slam_b200 import synth
+    head = synth.desc_db(1 << 16, R, S, seed=3, device=dev)        # queries come from the first 65,536 entries
+    return synth.desc_queries(head, Q, seed=4)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from scl_slam_b200 import build, engine
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    build.build()
+    n_db = args.n_db
+    e = engine.ScanContextB200(numCandidates=K, device=local_rank)
+    stream = torch.cuda.current_stream()
+    e.set_stream(stream.cuda_stream)
+    e.set_shard(rank, world)
+    n_local, chunk = gen_shard(dev, rank, world, n_db)
+    e.reserve(n_local)
+    step_c = 1 << 16
+    for c0 in range(0, n_local, step_c):
+        e.insert_batch_dev(chunk(c0, min(step_c, n_local - c0)))
+    torch.cuda.synchronize()
+    assert e.getSize() == n_local
+    q_dev, src, shift = gen_queries(dev)
+
+    def buf():
+        return dict(cand_ids=torch.empty((Q, K), dtype=torch.int32, device=dev), cand_d2=torch.empty((Q, K), dtype=torch.float32, device=dev),
+                    cand_dist=torch.empty((Q, K), dtype=torch.float64, device=dev), cand_shift=torch.empty((Q, K), dtype=torch.int32, device=dev),
+                    best_id=torch.empty(Q, dtype=torch.int32, device=dev), best_dist=torch.empty(Q, dtype=torch.float64, device=dev),
+                    best_shift=torch.empty(Q, dtype=torch.int32, device=dev))
+    local, merged = buf(), buf()
+    if world > 1:
+        gath = dict(ids=torch.empty((world, Q, K), dtype=torch.int32, device=dev), d2=torch.empty((world, Q, K), dtype=torch.float32, device=dev),
+                    dist=torch.empty((world, Q, K), dtype=torch.float64, device=dev), shift=torch.empty((world, Q, K), dtype=torch.int32, device=dev))
+    launches_per_step = 5 + (1 if world > 1 else 0)
+
+    def step():
+        e.query_batch_dev(q_dev, None, Q, K, n_local, 0, local)
+        if world > 1:
+            dist.all_gather_into_tensor(gath["ids"], local["cand_ids"])
+            dist.all_gather_into_tensor(gath["d2"], local["cand_d2"])
+            dist.all_gather_into_tensor(gath["dist"], local["cand_dist"])
+            dist.all_gather_into_tensor(gath["shift"], local["cand_shift"])
+            e.merge_shards_dev(world, Q, K, None, gath["ids"], gath["d2"], gath["dist"], gath["shift"], merged)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # L2 hygiene: the 84 MB key matrix alone would fit the 126 MB L2, so a 512 MB buffer is
+    # rewritten between steps, OUTSIDE the per-step event pairs (B200_PROFILING.md timing rules).
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(max(args.warmup, 3)):
+        step()
+        flush.zero_()
+    barrier()
+    e.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in evs:
+        a.record()
+        step()
+        b.record()
+        flush.zero_()
+    barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    e.set_profiling(False)
+    stage = {name: e.stage_time(i) for i, name in ((0, "k2_query_keys"), (1, "k3_knn"), (2, "k4_scdist"))}
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = Q / (ms_per_step * 1e-3)
+
+    # ---- e2e through the host-buffer public call (pinned host queries, H2D + D2H inside) ----
+    q_host = q_dev.cpu().pin_memory().numpy()
+    res = dict(best_id=np.empty(Q, np.int32), best_dist=np.empty(Q, np.float64), best_shift=np.empty(Q, np.int32))
+
+    def e2e_step():
+        qq = engine.SclBatchQuery(q_host.ctypes.data, None, Q, K, n_local, 0)
+        rr = engine.SclBatchResult(None, None, None, None, res["best_id"].ctypes.data, res["best_dist"].ctypes.data, res["best_shift"].ctypes.data)
+        e._ck(e.lib.scl_query_batch(e.h, qq, rr))
+    e2e = None
+    if world == 1:
+        for _ in range(3):
+            e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        e2e = {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(q_host.nbytes), "d2h_bytes_per_step": int(sum(v.nbytes for v in res.values()))}
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- parity spot check on what was just measured (size-independent property of D3) ----
+    final = merged if world > 1 else local
+    recovered = float((final["best_id"].cpu().numpy() == src.cpu().numpy()).mean())
+    shift_ok = float((final["best_shift"].cpu().numpy() == shift.cpu().numpy())[final["best_id"].cpu().numpy() == src.cpu().numpy()].mean())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    k3_ms, k3_n = stage["k3_knn"]
+    k3_avg = k3_ms / max(k3_n, 1)
+    alg_bytes = 4 * R * n_local + 4 * R * Q + 8 * Q * K          # key matrix once + query keys + (id, d2) out
+    alg_flops = 2.0 * R * Q * n_local
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("k3_knn_dram_bytes_per_launch")
+    roof = {"kernel": "k3_knn (knn_exact_kernel + merge)", "bound": "hbm", "achieved": alg_bytes / (k3_avg * 1e-3) / 1e9 if k3_avg > 0 else None,
+            "peak": pk["hbm"], "unit": "GB/s", "peak_source": pk["src"], "traffic": traffic,
+            "avg_launch_ms": k3_avg, "launches_timed": k3_n,
+            "tensor_equiv_tflops": alg_flops / (k3_avg * 1e-3) / 1e12 if k3_avg > 0 else None, "tensor_peak_tflops": pk["tc_sustained"]}
+    roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
+    line = {
+        "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+f64",
+        "data": "synthetic", "impl": "ours",
+        "config": {"workload": WORKLOAD, "db_keyframes": n_db, "queries_per_step": Q, "top_k": K, "rings": R, "sectors": S,
+                   "sharding": f"key mod {world}" if world > 1 else "none", "l2": "512 MB buffer rewritten between timed steps (outside the per-step CUDA-event pairs)"},
+        "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+        "stage_ms_per_step": {k: v[0] / max(v[1], 1) for k, v in stage.items()},
+        "roofline": roof, "clocks": clocks,
+        "parity_spot": {"source_recovered": recovered, "shift_recovered_given_source": shift_ok},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(e, n_local, q_dev, final, sample=args.cpu_sample)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _oracle(kind_pref=("ref", "port")):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    for kind in kind_pref:
+        if kind == "ref" and not oracle_lib.have_ref():
+            continue
+        if kind == "port":
+            oracle_lib.build_oracle()
+        return oracle_lib, kind
+    raise RuntimeError("no oracle library")
+
+
+def cpu_baseline(e, n_db, q_dev, gpu_res, sample):
+    """Times the CPU path (bench.py's one allowed use of oracle/) on a bounded sample of the same
+    batch, on this box's host cores, and checks the GPU winners against it on that sample."""
+    oracle_lib, kind = _oracle()
+    cores = os.cpu_count() or 1
+    # the same database the engine holds (regenerated from the seed) followed by the sampled queries
+    from scl_slam_b200 import synth
+    dev = q_dev.device
+    db_host = np.empty((n_db + sample, R * S), np.float32)
+    for c0 in range(0, n_db, 1 << 17):
+        m = min(1 << 17, n_db - c0)
+        db_host[c0:c0 + m] = synth.desc_db(m, R, S, seed=3, device=dev, start=c0).reshape(m, -1).cpu().numpy()
+    db_host[n_db:] = q_dev[:sample].reshape(sample, -1).cpu().numpy()
+    o = oracle_lib.Oracle(num_ring=R, num_sector=S, num_candidates=K, kind=kind)
+    t0 = time.perf_counter()
+    o.bulk_load(db_host, borrow=True)
+    t_load = time.perf_counter() - t0
+    ids = np.arange(n_db, n_db + sample, dtype=np.int32)
+    t0 = time.perf_counter()
+    o.query_batch(ids[:4], n_db, K, 0, nthreads=1)            # builds the KD-tree (kind=ref) / warms caches
+    t_tree = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    exp = o.query_batch(ids, n_db, K, 0, nthreads=cores)
+    t_q = time.perf_counter() - t0
+    same_id = float((exp["best_id"] == gpu_res["best_id"][:sample].cpu().numpy()).mean())
+    same_shift = float((exp["best_shift"] == gpu_res["best_shift"][:sample].cpu().numpy()).mean())
+    same_cand = float((exp["cand_ids"] == gpu_res["cand_ids"][:sample].cpu().numpy()).mean())
+    return {"value": sample / t_q, "unit": "queries/s", "cores": cores, "kind": "reference" if kind == "ref" else "port",
+            "sample": f"{sample} of the {Q} queries of one step against the full {n_db}-key database; "
+                      f"queries only ({t_q:.2f} s); KD-tree build {t_tree:.2f} s and ring-key load {t_load:.2f} s are outside "
+                      f"(the reference rebuilds its tree every 10 queries, descriptor.h:1691)",
+            "gpu_vs_cpu_on_sample": {"best_id_equal": same_id, "best_shift_equal": same_shift, "cand_ids_equal": same_cand}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    oracle_lib, kind = _oracle()
+    from scl_slam_b200 import synth
+    cores = os.cpu_count() or 1
+    dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    n_db = args.n_db
+    db_host = np.empty((n_db + Q, R * S), np.float32)
+    for c0 in range(0, n_db, 1 << 17):
+        m = min(1 << 17, n_db - c0)
+        db_host[c0:c0 + m] = synth.desc_db(m, R, S, seed=3, device=dev, start=c0).reshape(m, -1).cpu().numpy()
+    q, _, _ = synth.desc_queries(synth.desc_db(1 << 16, R, S, seed=3, device=dev), Q, seed=4)
+    db_host[n_db:] = q.reshape(Q, -1).cpu().numpy()
+    o = oracle_lib.Oracle(num_ring=R, num_sector=S, num_candidates=K, kind=kind)
+    o.bulk_load(db_host, borrow=True)
+    sample = args.cpu_sample
+    ids = np.arange(n_db, n_db + Q, dtype=np.int32)
+    o.query_batch(ids[:4], n_db, K, 0, nthreads=1)            # tree build + first touch, outside the timed steps
+    times = []
+    for it in range(args.warmup + args.steps):
+        sel = ids[(it * sample) % Q:][:sample]
+        t0 = time.perf_counter()
+        o.query_batch(sel, n_db, K, 0, nthreads=cores)
+        if it >= args.warmup:
+            times.append((time.perf_counter() - t0) / len(sel))
+    per_q = float(np.mean(times))
+    value = 1.0 / per_q
+    line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": per_q * Q * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+f64",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD, "db_keyframes": n_db, "queries_per_step": Q, "top_k": K, "rings": R, "sectors": S},
+            "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "reference" if kind == "ref" else "port",
+                             "sample": f"each step = {sample} of the {Q} queries of one batch against the full {n_db}-key database on "
+                                       f"{cores} threads (nanoflann kNN + distanceBtnScanContext); ms_per_step is scaled to the full batch; KD-tree build excluded"},
+            "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-db", type=int, default=N_DB, help="database size (default: the 1M workload)")
+    ap.add_argument("--cpu-sample", type=int, default=256, help="queries per CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -144,6 +144,14 @@ int scl_merge_shards_dev(scl_engine* e, int world, int Q, int K, const int32_t* 
                          const int32_t* all_ids, const float* all_d2, const double* all_dist, const int32_t* all_shift,
                          scl_batch_result* merged);
 
+/* ---- per-stage device timing (for roofline reports) ----------------------------------------
+ * With profiling on, every batched query records CUDA events on the engine's stream around each
+ * stage. scl_stage_time synchronises, sums the elapsed time of the recorded launches of `stage`
+ * (0 = query ring keys K2, 1 = ring-key kNN K3, 2 = SC distance K4, 3 = polar binning K1) into
+ * *ms and their number into *launches, and clears the record. */
+int scl_set_profiling(scl_engine* e, int on);
+int scl_stage_time(scl_engine* e, int stage, double* ms, int* launches);
+
 /* ---- geometric verification --------------------------------------------------------------
  * replaces the pcl::IterativeClosestPoint block of performIntraLoopClosure,
  * distributedMapping.h:1108-1132: point-to-point ICP of src onto tgt.

@@ -60,6 +60,10 @@ struct scl_engine {
     DevBuf qdesc, qids, qlocal, qkeys, qknorm, part_ids, part_d2, cand_ids, cand_d2, cand_local, cand_dist, cand_shift,
         best_id, best_dist, best_shift;
     size_t gbins_scans = 0;
+    /* per-stage event timing */
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[4];
+    std::vector<cudaEvent_t> ev_pool;
 
     int RS() const { return p.num_ring * p.num_sector; }
 };
@@ -76,6 +80,27 @@ struct scl_engine {
 #define FAIL(code, msg) do { e->err = (msg); return (code); } while (0)
 
 namespace {
+
+struct StageTimer {
+    scl_engine* e; int stage; cudaEvent_t a = nullptr, b = nullptr;
+    StageTimer(scl_engine* e_, int stage_) : e(e_), stage(stage_)
+    {
+        if (!e->profiling) return;
+        a = take(); b = take();
+        cudaEventRecord(a, e->stream);
+    }
+    ~StageTimer()
+    {
+        if (!a) return;
+        cudaEventRecord(b, e->stream);
+        e->ev[stage].emplace_back(a, b);
+    }
+    cudaEvent_t take()
+    {
+        if (!e->ev_pool.empty()) { cudaEvent_t x = e->ev_pool.back(); e->ev_pool.pop_back(); return x; }
+        cudaEvent_t x; cudaEventCreate(&x); return x;
+    }
+};
 
 int grow(scl_engine* e, int need)
 {
@@ -138,6 +163,7 @@ int build_dev(scl_engine* e, const void* pts_dev, const int32_t* offsets_host, i
         CK(e->stage_knorm.ensure((size_t)n_scans * 4));
         od = e->stage_desc.as<float>(); ok = e->stage_keys.as<float>(); on = e->stage_knorm.as<float>();
     }
+    StageTimer st(e, 3);
     CK(scl_launch_polar(pts_dev, e->offsets.as<int>(), n_scans, max_points, stride_bytes, R, S, e->p.lidar_height, e->p.max_radius,
                         e->gbins.as<uint32_t>(), e->tickets.as<int>(), od, ok, on, ring_dev, sector_dev, e->stream));
     if (out_desc_dev) CK(cudaMemcpyAsync(out_desc_dev, od, (size_t)n_scans * RS * 4, cudaMemcpyDeviceToDevice, e->stream));
@@ -196,6 +222,7 @@ int query_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, i
     int32_t* q_local = nullptr;
     if (q_desc) {
         CK(e->qknorm.ensure((size_t)Q * 4));
+        StageTimer st(e, 0);
         CK(scl_launch_ring_keys(q_desc, Q, R, S, e->qkeys.as<float>(), e->qknorm.as<float>(), e->stream));
     } else {
         CK(e->qlocal.ensure((size_t)Q * 4));
@@ -208,9 +235,13 @@ int query_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, i
     CK(e->part_ids.ensure((size_t)Q * splits * K * 4));
     CK(e->part_d2.ensure((size_t)Q * splits * K * 4));
     ws.part_ids = e->part_ids.as<int32_t>(); ws.part_d2 = e->part_d2.as<float>(); ws.capacity = (size_t)Q * splits * K;
-    CK(scl_launch_knn_exact(e->qkeys.as<float>(), Q, e->d_keys, n_db, R, K, metric, e->world, e->rank, ws, cand_ids, cand_d2, e->stream));
+    {
+        StageTimer st(e, 1);
+        CK(scl_launch_knn_exact(e->qkeys.as<float>(), Q, e->d_keys, n_db, R, K, metric, e->world, e->rank, ws, cand_ids, cand_d2, e->stream));
+    }
     CK(scl_launch_ids_to_local(cand_ids, (int)QK, e->world, e->rank, missing_to_zero ? 0 : -1, missing_to_zero ? cand_ids : nullptr,
                                e->cand_local.as<int32_t>(), e->stream));
+    StageTimer st(e, 2);
     CK(scl_launch_scdist(e->d_desc, q_desc, q_local, q_ids, e->cand_local.as<int32_t>(), cand_ids, Q, K, R, S, e->search_radius,
                          cand_dist, cand_shift, best_id, best_dist, best_shift, e->stream));
     return SCL_OK;
@@ -303,6 +334,8 @@ int scl_destroy(scl_engine* e)
                           &e->part_d2, &e->cand_ids, &e->cand_d2, &e->cand_local, &e->cand_dist, &e->cand_shift, &e->best_id,
                           &e->best_dist, &e->best_shift};
         for (DevBuf* b : bufs) b->release();
+        for (auto& v : e->ev) for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+        for (cudaEvent_t x : e->ev_pool) cudaEventDestroy(x);
         if (e->own_stream) cudaStreamDestroy(e->stream);
     }
     delete e;
@@ -317,6 +350,24 @@ int scl_set_stream(scl_engine* e, void* s)
     CK(cudaStreamSynchronize(e->stream));
     if (e->own_stream) cudaStreamDestroy(e->stream);
     e->stream = static_cast<cudaStream_t>(s); e->own_stream = false;
+    return SCL_OK;
+}
+
+int scl_set_profiling(scl_engine* e, int on) { LOCK(); e->profiling = on != 0; return SCL_OK; }
+
+int scl_stage_time(scl_engine* e, int stage, double* ms, int* launches)
+{
+    LOCK();
+    if (stage < 0 || stage > 3 || !ms || !launches) FAIL(SCL_ERR_INVALID, "bad stage");
+    CK(cudaStreamSynchronize(e->stream));
+    double total = 0.0; int n = 0;
+    for (auto& pr : e->ev[stage]) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, pr.first, pr.second) == cudaSuccess) { total += t; n++; }
+        e->ev_pool.push_back(pr.first); e->ev_pool.push_back(pr.second);
+    }
+    e->ev[stage].clear();
+    *ms = total; *launches = n;
     return SCL_OK;
 }
 

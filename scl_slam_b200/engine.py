@@ -25,7 +25,7 @@ EXPORTS = [
     "scl_reserve", "scl_set_shard", "scl_build_insert", "scl_make_scancontext", "scl_build_batch", "scl_build_batch_dev",
     "scl_insert", "scl_insert_batch", "scl_insert_batch_dev", "scl_get_index", "scl_size", "scl_get_descriptor",
     "scl_get_ring_key", "scl_query_intra", "scl_query_inter", "scl_query_batch", "scl_query_batch_dev",
-    "scl_merge_shards_dev", "scl_icp",
+    "scl_merge_shards_dev", "scl_icp", "scl_set_profiling", "scl_stage_time",
 ]
 
 
@@ -87,6 +87,8 @@ def load_library():
     lib.scl_query_batch_dev.argtypes = lib.scl_query_batch.argtypes
     lib.scl_merge_shards_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.POINTER(SclBatchResult)]
+    lib.scl_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    lib.scl_stage_time.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     lib.scl_icp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(SclIcpParams),
                             C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _lib = lib
@@ -256,6 +258,15 @@ class ScanContextB200:
                              ("cand_ids", "cand_d2", "cand_dist", "cand_shift", "best_id", "best_dist", "best_shift")])
         self._ck(self.lib.scl_merge_shards_dev(self.h, world, Q, K, _ptr(q_ids_dev), _ptr(all_ids), _ptr(all_d2),
                                                _ptr(all_dist), _ptr(all_shift), C.byref(r)))
+
+    def set_profiling(self, on):
+        self._ck(self.lib.scl_set_profiling(self.h, int(on)))
+
+    def stage_time(self, stage):
+        """(total ms, launches) of stage 0=K2 query keys, 1=K3 kNN, 2=K4 SC distance, 3=K1 binning."""
+        ms, n = C.c_double(), C.c_int()
+        self._ck(self.lib.scl_stage_time(self.h, stage, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     # ---- geometric verification (distributedMapping.h:1108-1132) ---------------------------
     def icp(self, src, tgt, max_corr_dist=100.0, max_iterations=50, trans_eps=1e-6, fitness_eps=1e-6):

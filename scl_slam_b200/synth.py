@@ -71,7 +71,10 @@ def desc_db(n, num_ring=20, num_sector=60, seed=3, device="cpu", start=0, chunk=
         fs_t = torch.sin(2 * math.pi * (fs.unsqueeze(-1) * s + ps.unsqueeze(-1)))   # [m,4,S]
         field = torch.einsum("mk,mkr,mks->mrs", amp, fr_t, fs_t)                    # [m,R,S]
         noise = _uniform(e * (R * S) + bins, 21).view(-1, R, S)
-        h = (12.5 + 1.6 * field + 4.0 * (noise - 0.5)).clamp_(0.0, 25.0)
+        # per-entry radial profile: what makes ring keys (row means) discriminative at 1M entries
+        rings = torch.arange(R, device=dev, dtype=torch.int64).view(1, R)
+        profile = 10.0 * (_uniform(e * R + rings, 24) - 0.5)                        # [m,R]
+        h = (12.5 + profile.unsqueeze(-1) + 1.6 * field + 4.0 * (noise - 0.5)).clamp_(0.0, 25.0)
         # radial occlusion: per (entry, sector) a start ring beyond which nothing is seen
         u = _uniform(e * S + secs, 22)                                               # [m,S]
         start_ring = torch.where(u > 0.6, torch.full_like(u, float(R)), torch.floor(R * (0.25 + 1.25 * u)))
