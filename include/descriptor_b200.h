@@ -1,0 +1,146 @@
+/*
+ * descriptor_b200.h — header-only drop-in for the reference's Scan Context descriptor class.
+ *
+ *   class scan_context_descriptor_b200 : public scan_descriptor
+ *
+ * implements the six pure virtuals of class scan_descriptor
+ * (/root/reference/include/descriptor.h:21-36) on top of the C-ABI in scl_engine.h, with the
+ * constructor signature of scan_context_descriptor (descriptor.h:1307-1316), so that
+ * distributedMapping.h:404
+ *       scanDescriptor = unique_ptr<scan_descriptor>(new scan_context_descriptor());
+ * becomes
+ *       scanDescriptor = unique_ptr<scan_descriptor>(new scan_context_descriptor_b200());
+ * and nothing else in distributed_mapping changes (call sites :627, :1002, :1072, :1078, :1274,
+ * :1280-1284). Link with -lscl_b200.
+ *
+ * Include AFTER the header that declares `scan_descriptor` and pcl::PointCloud<pcl::PointXYZI>
+ * (i.e. after descriptor.h's own includes). Error behaviour mirrors the reference, which has no
+ * status channel: "no loop" is first == -1; an engine error is reported on stderr and returns
+ * the same "no loop" / empty values. Unlike the reference, getIndex() tolerates out-of-range
+ * keys (the reference evaluates getIndex(-1) at distributedMapping.h:1282): it returns {-1,-1}.
+ * The class is internally synchronised, so the unlocked queries of loopClosureThread
+ * (distributedMapping.h:1078,1280) are safe against concurrent inserts (:625-628, :1001-1003).
+ */
+#ifndef DESCRIPTOR_B200_H_
+#define DESCRIPTOR_B200_H_
+
+#include <cstdint>
+#include <cstdio>
+#include <utility>
+#include <vector>
+
+#include "scl_engine.h"
+
+class scan_context_descriptor_b200 : public scan_descriptor
+{
+public:
+	scan_context_descriptor_b200(
+		int numRing 			= 20,
+		int numSector 			= 60,
+		int numCandidates 		= 3,
+		double distThres 		= 0.14,
+		double lidarHeight 		= 1.65,
+		double maxRadius 		= 80.0,
+		int numExcludeRecent 	= 100,
+		int treeMakingPeriod 	= 10,
+		double searchRatio 		= 0.1,
+		int cudaDevice 			= 0) : engine_(nullptr)
+	{
+		scl_params p;
+		p.num_ring = numRing; p.num_sector = numSector; p.num_candidates = numCandidates;
+		p.dist_thres = distThres; p.lidar_height = lidarHeight; p.max_radius = maxRadius;
+		p.num_exclude_recent = numExcludeRecent; p.tree_making_period = treeMakingPeriod; p.search_ratio = searchRatio;
+		rs_ = numRing * numSector;
+		const int rc = scl_create(&p, cudaDevice, &engine_);
+		if(rc != SCL_OK)
+		{
+			std::fprintf(stderr, "[scan_context_descriptor_b200] scl_create failed (%d): a CUDA device is required, there is no CPU fallback\n", rc);
+			engine_ = nullptr;
+		}
+	}
+
+	~scan_context_descriptor_b200()
+	{
+		if(engine_) scl_destroy(engine_);
+	}
+
+	scan_context_descriptor_b200(const scan_context_descriptor_b200&) = delete;
+	scan_context_descriptor_b200& operator=(const scan_context_descriptor_b200&) = delete;
+
+	/* descriptor.h:1604-1611 — the returned vector is global_descriptor.msg `values` (row-major R*S) */
+	std::vector<float> makeAndSaveDescriptorAndKey(const pcl::PointCloud<pcl::PointXYZI>& scan, const int8_t robot, const int index)
+	{
+		std::vector<float> vT(rs_, 0.0f);
+		const void* pts = scan.points.empty() ? nullptr : static_cast<const void*>(&scan.points[0]);
+		check(scl_build_insert(engine_, pts, (int)scan.points.size(), (int)sizeof(pcl::PointXYZI), robot, index, vT.data()), "makeAndSaveDescriptorAndKey");
+		return vT;
+	}
+
+	/* descriptor.h:1572-1585 — descriptorMat is msg->values.data(), borrowed for the call */
+	void saveDescriptorAndKey(const float* descriptorMat, const int8_t robot, const int index)
+	{
+		check(scl_insert(engine_, descriptorMat, robot, index), "saveDescriptorAndKey");
+	}
+
+	/* descriptor.h:1613-1674 — {loop id or -1, best shift as float} */
+	std::pair<int, float> detectIntraLoopClosureID(const int currentPtr)
+	{
+		int id = -1; float second = 0.0f;
+		check(scl_query_intra(engine_, currentPtr, &id, &second), "detectIntraLoopClosureID");
+		return std::make_pair(id, second);
+	}
+
+	/* descriptor.h:1676-1756 — {loop id or -1, relative yaw in radians} */
+	std::pair<int, float> detectInterLoopClosureID(const int currentPtr)
+	{
+		int id = -1; float second = 0.0f;
+		check(scl_query_inter(engine_, currentPtr, &id, &second), "detectInterLoopClosureID");
+		return std::make_pair(id, second);
+	}
+
+	/* descriptor.h:1758-1761 */
+	std::pair<int8_t, int> getIndex(const int key)
+	{
+		int8_t robot = -1; int index = -1;
+		check(scl_get_index(engine_, key, &robot, &index), "getIndex");
+		return std::make_pair(robot, index);
+	}
+
+	/* descriptor.h:1763-1766 (idIn is ignored there too) */
+	int getSize(const int idIn = -1)
+	{
+		(void)idIn;
+		return engine_ ? scl_size(engine_) : 0;
+	}
+
+	/* geometric verification for performIntraLoopClosure (distributedMapping.h:1108-1132):
+	 * T is the row-major 4x4 of icp.getFinalTransformation() */
+	bool icpAlign(const pcl::PointCloud<pcl::PointXYZI>& source, const pcl::PointCloud<pcl::PointXYZI>& target,
+		float T[16], float& fitnessScore, double maxCorrespondenceDistance = 100, int maximumIterations = 50,
+		double transformationEpsilon = 1e-6, double euclideanFitnessEpsilon = 1e-6)
+	{
+		scl_icp_params p;
+		p.max_corr_dist = maxCorrespondenceDistance; p.max_iterations = maximumIterations;
+		p.trans_eps = transformationEpsilon; p.fitness_eps = euclideanFitnessEpsilon;
+		int converged = 0, iterations = 0;
+		const int rc = scl_icp(engine_, source.points.empty() ? nullptr : &source.points[0], (int)source.points.size(),
+			target.points.empty() ? nullptr : &target.points[0], (int)target.points.size(), (int)sizeof(pcl::PointXYZI),
+			&p, T, &fitnessScore, &converged, &iterations);
+		check(rc, "icpAlign");
+		return rc == SCL_OK && converged != 0;
+	}
+
+	scl_engine* engine() { return engine_; }
+
+private:
+	void check(int rc, const char* what)
+	{
+		if(rc != SCL_OK)
+			std::fprintf(stderr, "[scan_context_descriptor_b200] %s failed (%d): %s\n", what, rc, engine_ ? scl_last_error(engine_) : "no engine");
+	}
+
+	scl_engine* engine_;
+	int rs_;
+};
+
+#endif

@@ -10,74 +10,7 @@
 //   d_knorm [cap]      float32  squared key norms for the tensor-core prefilter
 // (robot, index) metadata stays on the host (descriptor.h:1599,1758-1761).
 // There is no CPU fallback anywhere in this file: every data-path call launches kernels.
-#include "../../include/scl_engine.h"
-#include "kernels.h"
-
-#include <cfloat>
-#include <cmath>
-#include <cstdio>
-#include <cstring>
-#include <mutex>
-#include <string>
-#include <utility>
-#include <vector>
-
-namespace {
-
-struct DevBuf {
-    void* p = nullptr; size_t cap = 0;
-    cudaError_t ensure(size_t bytes)
-    {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-    template <typename T> T* as() { return static_cast<T*>(p); }
-};
-
-} // namespace
-
-struct scl_engine {
-    scl_params p;
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = true;
-    std::mutex mu;
-    std::string err;
-    int n = 0, cap = 0;
-    float *d_desc = nullptr, *d_keys = nullptr, *d_knorm = nullptr;
-    std::vector<std::pair<int8_t, int>> index;
-    int rank = 0, world = 1;
-    int tree_counter = 0, n_tree = 0;      /* descriptor.h:1691-1703 */
-    int search_radius = 0;                 /* round(0.5*SEARCH_RATIO*S), descriptor.h:1545 */
-    /* scratch */
-    DevBuf pts, offsets, gbins, tickets, stage_desc, stage_keys, stage_knorm, bins_ring, bins_sector;
-    DevBuf qdesc, qids, qlocal, qkeys, qknorm, part_ids, part_d2, cand_ids, cand_d2, cand_local, cand_dist, cand_shift,
-        best_id, best_dist, best_shift;
-    size_t gbins_scans = 0;
-    /* per-stage event timing */
-    bool profiling = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[4];
-    std::vector<cudaEvent_t> ev_pool;
-
-    int RS() const { return p.num_ring * p.num_sector; }
-};
-
-#define CK(call)                                                                                     \
-    do {                                                                                             \
-        cudaError_t _e = (call);                                                                     \
-        if (_e != cudaSuccess) {                                                                     \
-            e->err = std::string(#call) + ": " + cudaGetErrorString(_e);                             \
-            return _e == cudaErrorNotSupported ? SCL_ERR_UNSUPPORTED : (_e == cudaErrorMemoryAllocation ? SCL_ERR_NOMEM : SCL_ERR_CUDA); \
-        }                                                                                            \
-    } while (0)
-
-#define FAIL(code, msg) do { e->err = (msg); return (code); } while (0)
+#include "engine_internal.h"
 
 namespace {
 
@@ -286,8 +219,6 @@ int query_host(scl_engine* e, const scl_batch_query* q, scl_batch_result* r, int
 
 } // namespace
 
-#define LOCK() if (!e) return SCL_ERR_INVALID; std::lock_guard<std::mutex> _lk(e->mu); cudaSetDevice(e->device)
-
 extern "C" {
 
 void scl_default_params(scl_params* p)
@@ -332,7 +263,9 @@ int scl_destroy(scl_engine* e)
         DevBuf* bufs[] = {&e->pts, &e->offsets, &e->gbins, &e->tickets, &e->stage_desc, &e->stage_keys, &e->stage_knorm,
                           &e->bins_ring, &e->bins_sector, &e->qdesc, &e->qids, &e->qlocal, &e->qkeys, &e->qknorm, &e->part_ids,
                           &e->part_d2, &e->cand_ids, &e->cand_d2, &e->cand_local, &e->cand_dist, &e->cand_shift, &e->best_id,
-                          &e->best_dist, &e->best_shift};
+                          &e->best_dist, &e->best_shift, &e->icp_src, &e->icp_tgt, &e->icp_raw, &e->icp_acc, &e->icp_nn,
+                          &e->icp_grid[0][0], &e->icp_grid[0][1], &e->icp_grid[0][2], &e->icp_grid[0][3], &e->icp_grid[0][4],
+                          &e->icp_grid[1][0], &e->icp_grid[1][1], &e->icp_grid[1][2], &e->icp_grid[1][3], &e->icp_grid[1][4]};
         for (DevBuf* b : bufs) b->release();
         for (auto& v : e->ev) for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         for (cudaEvent_t x : e->ev_pool) cudaEventDestroy(x);

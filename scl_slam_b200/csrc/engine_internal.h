@@ -1,0 +1,70 @@
+// engine_internal.h — the engine object shared by engine.cu and k5_icp.cu (not a public header)
+#pragma once
+#include "../../include/scl_engine.h"
+#include "kernels.h"
+
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() { return static_cast<T*>(p); }
+};
+
+struct scl_engine {
+    scl_params p;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    std::mutex mu;
+    std::string err;
+    int n = 0, cap = 0;
+    float *d_desc = nullptr, *d_keys = nullptr, *d_knorm = nullptr;
+    std::vector<std::pair<int8_t, int>> index;
+    int rank = 0, world = 1;
+    int tree_counter = 0, n_tree = 0;      /* descriptor.h:1691-1703 */
+    int search_radius = 0;                 /* round(0.5*SEARCH_RATIO*S), descriptor.h:1545 */
+    /* scratch */
+    DevBuf pts, offsets, gbins, tickets, stage_desc, stage_keys, stage_knorm, bins_ring, bins_sector;
+    DevBuf qdesc, qids, qlocal, qkeys, qknorm, part_ids, part_d2, cand_ids, cand_d2, cand_local, cand_dist, cand_shift,
+        best_id, best_dist, best_shift;
+    DevBuf icp_src, icp_tgt, icp_raw, icp_grid[2][5], icp_acc, icp_nn;
+    size_t gbins_scans = 0;
+    /* per-stage event timing */
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[4];
+    std::vector<cudaEvent_t> ev_pool;
+
+    int RS() const { return p.num_ring * p.num_sector; }
+};
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t _e = (call);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            e->err = std::string(#call) + ": " + cudaGetErrorString(_e);                             \
+            return _e == cudaErrorNotSupported ? SCL_ERR_UNSUPPORTED : (_e == cudaErrorMemoryAllocation ? SCL_ERR_NOMEM : SCL_ERR_CUDA); \
+        }                                                                                            \
+    } while (0)
+
+#define FAIL(code, msg) do { e->err = (msg); return (code); } while (0)
+
+
+#define LOCK() if (!e) return SCL_ERR_INVALID; std::lock_guard<std::mutex> _lk(e->mu); cudaSetDevice(e->device)

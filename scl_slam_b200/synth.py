@@ -165,6 +165,8 @@ def scan(world, pose, dirs, seed=0, sensor_height=1.65, max_range=100.0, sigma=0
     down = dw[:, 2] < -1e-6
     t[down] = -sensor_height / dw[down, 2]
     near = (np.abs((lo[:, 0] + hi[:, 0]) / 2 - x) < box_radius) & (np.abs((lo[:, 1] + hi[:, 1]) / 2 - y) < box_radius)
+    inside = (lo[:, 0] < x) & (x < hi[:, 0]) & (lo[:, 1] < y) & (y < hi[:, 1]) & (hi[:, 2] > sensor_height)
+    near &= ~inside                     # a box the sensor stands in is transparent
     blo, bhi = lo[near], hi[near]
     with np.errstate(divide="ignore", invalid="ignore"):
         inv = 1.0 / dw
