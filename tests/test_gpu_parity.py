@@ -297,3 +297,42 @@ def test_icp_degenerate_inputs(eng_mod):
     assert not conv and np.array_equal(T, np.eye(4, dtype=np.float32))
     T, fit, conv, it = e.icp(np.ones((2, 4), np.float32), np.ones((10, 4), np.float32))
     assert not conv                                             # fewer than 3 correspondences
+
+
+# ---------------------------------------------------------------- multi-GPU merge, emulated on one device
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_equals_unsharded(eng_mod, world):
+    """world engines on one GPU each hold key mod world == rank; their per-shard results pushed
+    through the CUDA merge kernel (scl_merge_shards_dev) equal the unsharded engine bit for bit."""
+    from scl_slam_b200 import sharding
+    n, nq, K = 4001, 96, 10
+    db = synth.desc_db(n, seed=81)
+    q = synth.desc_queries(db, nq, seed=82)[0]
+    dbn = db.numpy()
+    dbn[17] = dbn[16]                                       # a cross-shard exact tie
+    full = eng_mod.ScanContextB200(numCandidates=K)
+    full.insert_batch(dbn)
+    exp = full.query_batch(q_desc=q.numpy(), K=K, n_db=n - 101)
+    dev = torch.device("cuda:0")
+    qd = q.to(dev).contiguous()
+    names = ("cand_ids", "cand_d2", "cand_dist", "cand_shift")
+    dt = dict(cand_ids=torch.int32, cand_d2=torch.float32, cand_dist=torch.float64, cand_shift=torch.int32,
+              best_id=torch.int32, best_dist=torch.float64, best_shift=torch.int32)
+    gath = {k: torch.empty((world, nq, K), dtype=dt[k], device=dev) for k in names}
+    engines = []
+    for r in range(world):
+        e = eng_mod.ScanContextB200(numCandidates=K)
+        e.set_shard(r, world)
+        e.insert_batch(dbn[sharding.local_rows(n, r, world)])
+        out = {k: gath[k][r] for k in names}
+        e.query_batch_dev(qd, None, nq, K, sharding.local_search_bound(n - 101, r, world), 0, out)
+        engines.append(e)
+    torch.cuda.synchronize()
+    merged = {k: torch.empty((nq, K) if k.startswith("cand") else (nq,), dtype=dt[k], device=dev) for k in dt}
+    engines[0].merge_shards_dev(world, nq, K, None, gath["cand_ids"], gath["cand_d2"], gath["cand_dist"], gath["cand_shift"], merged)
+    torch.cuda.synchronize()
+    for k in dt:
+        assert np.array_equal(merged[k].cpu().numpy(), exp[k], equal_nan=True), k
+    ref = sharding.merge_shards_numpy(*[gath[k].cpu().numpy() for k in names])
+    for k in dt:
+        assert np.array_equal(ref[k], exp[k], equal_nan=True), k

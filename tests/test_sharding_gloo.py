@@ -1,0 +1,69 @@
+"""N>1 host logic on CPU: two gloo ranks each hold `key mod 2 == rank` of a seeded database
+(the CPU oracle stands in for the per-rank engine), exchange their local top-K records with one
+all_gather, and the merge rule must reproduce the unsharded oracle result exactly."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, n, nq, K, ret):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle_lib import Oracle
+    from scl_slam_b200 import sharding, synth
+    db = synth.desc_db(n, seed=71).numpy().reshape(n, -1)
+    q = synth.desc_queries(torch.from_numpy(db.reshape(n, 20, 60)), nq, seed=72)[0].numpy().reshape(nq, -1)
+    rows = sharding.local_rows(n, rank, world)
+    n_local = sharding.local_count(n, rank, world)
+    assert len(rows) == n_local
+    o = Oracle(num_candidates=K)
+    o.bulk_load(np.concatenate([db[rows], q]))
+    n_search = sharding.local_search_bound(n - 101, rank, world)          # a global "exclude recent" bound
+    loc = o.query_batch(np.arange(n_local, n_local + nq), n_search, K, 0)
+    ids = np.where(loc["cand_ids"] >= 0, loc["cand_ids"].astype(np.int64) * world + rank, -1).astype(np.int32)
+    gathered = {}
+    for name, arr in (("ids", ids), ("d2", loc["cand_d2"]), ("dist", loc["cand_dist"]), ("shift", loc["cand_shift"])):
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        gathered[name] = np.stack([x.numpy() for x in outs])
+    merged = sharding.merge_shards_numpy(gathered["ids"], gathered["d2"], gathered["dist"], gathered["shift"])
+    if rank == 0:
+        full = Oracle(num_candidates=K)
+        full.bulk_load(np.concatenate([db, q]))
+        exp = full.query_batch(np.arange(n, n + nq), n - 101, K, 0)
+        ok = all(np.array_equal(merged[k], exp[k], equal_nan=True) for k in exp)
+        ret.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_merge_equals_unsharded():
+    world = 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 1501, 64, 10, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) is True
+
+
+def test_local_rows_partition():
+    from scl_slam_b200 import sharding
+    for n in (0, 1, 7, 1000, 1001):
+        for world in (1, 2, 4, 8):
+            rows = [sharding.local_rows(n, r, world) for r in range(world)]
+            assert sorted(np.concatenate(rows).tolist()) == list(range(n))
+            assert [len(x) for x in rows] == [sharding.local_count(n, r, world) for r in range(world)]
