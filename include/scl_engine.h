@@ -144,6 +144,15 @@ int scl_merge_shards_dev(scl_engine* e, int world, int Q, int K, const int32_t* 
                          const int32_t* all_ids, const float* all_d2, const double* all_dist, const int32_t* all_shift,
                          scl_batch_result* merged);
 
+/* ---- ring-key kNN variant ---------------------------------------------
+ * mode 0 = automatic (tensor-core prefilter for batches >= 64 queries on >= 32768 keys, exact
+ * CUDA-core kernel otherwise), 1 = always exact, 2 = always tensor core. Both produce identical
+ * results: the prefilter's proposals are re-ranked exactly and certified, uncertified queries are
+ * redone by the exact kernel. With count_fallbacks != 0 every batch reads back how many queries
+ * needed that (a host sync; for tests and reports). */
+int scl_set_knn_mode(scl_engine* e, int mode, int count_fallbacks);
+int scl_knn_stats(scl_engine* e, long long* tc_queries, long long* fallback_queries);
+
 /* ---- per-stage device timing (for roofline reports) ----------------------------------------
  * With profiling on, every batched query records CUDA events on the engine's stream around each
  * stage. scl_stage_time synchronises, sums the elapsed time of the recorded launches of `stage`

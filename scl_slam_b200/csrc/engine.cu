@@ -98,7 +98,7 @@ int build_dev(scl_engine* e, const void* pts_dev, const int32_t* offsets_host, i
     }
     StageTimer st(e, 3);
     CK(scl_launch_polar(pts_dev, e->offsets.as<int>(), n_scans, max_points, stride_bytes, R, S, e->p.lidar_height, e->p.max_radius,
-                        e->gbins.as<uint32_t>(), e->tickets.as<int>(), od, ok, on, ring_dev, sector_dev, e->stream));
+                        e->gbins.as<uint32_t>(), e->tickets.as<int>(), od, ok, on, insert ? e->d_kn2max : nullptr, ring_dev, sector_dev, e->stream));
     if (out_desc_dev) CK(cudaMemcpyAsync(out_desc_dev, od, (size_t)n_scans * RS * 4, cudaMemcpyDeviceToDevice, e->stream));
     if (where_desc) *where_desc = od;
     if (insert) { append_index(e, n_scans, robots, indices); e->n += n_scans; }
@@ -156,7 +156,7 @@ int query_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, i
     if (q_desc) {
         CK(e->qknorm.ensure((size_t)Q * 4));
         StageTimer st(e, 0);
-        CK(scl_launch_ring_keys(q_desc, Q, R, S, e->qkeys.as<float>(), e->qknorm.as<float>(), e->stream));
+        CK(scl_launch_ring_keys(q_desc, Q, R, S, e->qkeys.as<float>(), e->qknorm.as<float>(), nullptr, e->stream));
     } else {
         CK(e->qlocal.ensure((size_t)Q * 4));
         q_local = e->qlocal.as<int32_t>();
@@ -168,9 +168,35 @@ int query_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, i
     CK(e->part_ids.ensure((size_t)Q * splits * K * 4));
     CK(e->part_d2.ensure((size_t)Q * splits * K * 4));
     ws.part_ids = e->part_ids.as<int32_t>(); ws.part_d2 = e->part_d2.as<float>(); ws.capacity = (size_t)Q * splits * K;
+    /* K3 variant: the tensor-core prefilter pays off once there is a batch to fill 128-row tiles and a
+     * database worth streaming; single queries and small databases take the exact CUDA-core kernel. */
+    bool use_tc = scl_knn_tc_supported(R) && K <= scl_knn_tc_kprime(K) - 2 &&
+                  (e->knn_mode == 2 || (e->knn_mode == 0 && Q >= 64 && n_db >= 32768));
     {
         StageTimer st(e, 1);
-        CK(scl_launch_knn_exact(e->qkeys.as<float>(), Q, e->d_keys, n_db, R, K, metric, e->world, e->rank, ws, cand_ids, cand_d2, e->stream));
+        if (use_tc) {
+            const int ranges = scl_knn_tc_ranges(Q), kp = scl_knn_tc_kprime(K);
+            const size_t ncand = (size_t)Q * ranges * kp;
+            CK(e->tc_prop_s.ensure(ncand * 4)); CK(e->tc_prop_idx.ensure(ncand * 4)); CK(e->tc_exact.ensure(ncand * 4));
+            CK(e->tc_prop_cut.ensure((size_t)Q * ranges * 4));
+            CK(e->tc_fail_list.ensure((size_t)Q * 4)); CK(e->tc_fail_count.ensure(64));
+            KnnTcWorkspace tw{e->tc_prop_s.as<float>(), e->tc_prop_idx.as<int32_t>(), e->tc_prop_cut.as<float>(), e->tc_exact.as<float>(), ncand};
+            CK(scl_launch_knn_tc(e->qkeys.as<float>(), Q, e->d_keys, e->d_knorm, e->d_kn2max, n_db, R, K, metric, e->world, e->rank, tw,
+                                 cand_ids, cand_d2, e->tc_fail_list.as<int32_t>(), e->tc_fail_count.as<int>(), e->stream));
+            /* uncertified queries (normally none) are redone exactly; CTAs beyond the list length exit at once */
+            CK(scl_launch_knn_exact(e->qkeys.as<float>(), Q, e->d_keys, n_db, R, K, metric, e->world, e->rank,
+                                    e->tc_fail_list.as<int32_t>(), e->tc_fail_count.as<int>(), ws, cand_ids, cand_d2, e->stream));
+            e->stat_tc_queries += Q;
+        } else {
+            CK(scl_launch_knn_exact(e->qkeys.as<float>(), Q, e->d_keys, n_db, R, K, metric, e->world, e->rank, nullptr, nullptr, ws,
+                                    cand_ids, cand_d2, e->stream));
+        }
+    }
+    if (use_tc && e->count_fallbacks) {
+        int nfail = 0;
+        CK(cudaMemcpyAsync(&nfail, e->tc_fail_count.p, 4, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        e->stat_fallback_queries += nfail;
     }
     CK(scl_launch_ids_to_local(cand_ids, (int)QK, e->world, e->rank, missing_to_zero ? 0 : -1, missing_to_zero ? cand_ids : nullptr,
                                e->cand_local.as<int32_t>(), e->stream));
@@ -248,6 +274,7 @@ int scl_create(const scl_params* p, int device, scl_engine** out)
     e->p = *p; e->device = device;
     e->search_radius = (int)std::round(0.5 * p->search_ratio * p->num_sector);
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return SCL_ERR_CUDA; }
+    if (cudaMalloc(&e->d_kn2max, 64) != cudaSuccess || cudaMemset(e->d_kn2max, 0, 64) != cudaSuccess) { delete e; return SCL_ERR_CUDA; }
     *out = e;
     return SCL_OK;
 }
@@ -259,11 +286,12 @@ int scl_destroy(scl_engine* e)
         std::lock_guard<std::mutex> lk(e->mu);
         cudaSetDevice(e->device);
         cudaStreamSynchronize(e->stream);
-        cudaFree(e->d_desc); cudaFree(e->d_keys); cudaFree(e->d_knorm);
+        cudaFree(e->d_desc); cudaFree(e->d_keys); cudaFree(e->d_knorm); cudaFree(e->d_kn2max);
         DevBuf* bufs[] = {&e->pts, &e->offsets, &e->gbins, &e->tickets, &e->stage_desc, &e->stage_keys, &e->stage_knorm,
                           &e->bins_ring, &e->bins_sector, &e->qdesc, &e->qids, &e->qlocal, &e->qkeys, &e->qknorm, &e->part_ids,
                           &e->part_d2, &e->cand_ids, &e->cand_d2, &e->cand_local, &e->cand_dist, &e->cand_shift, &e->best_id,
-                          &e->best_dist, &e->best_shift, &e->icp_src, &e->icp_tgt, &e->icp_raw, &e->icp_acc, &e->icp_nn,
+                          &e->best_dist, &e->best_shift, &e->tc_prop_s, &e->tc_prop_idx, &e->tc_prop_cut, &e->tc_exact,
+                          &e->tc_fail_list, &e->tc_fail_count, &e->icp_src, &e->icp_tgt, &e->icp_raw, &e->icp_acc, &e->icp_nn,
                           &e->icp_grid[0][0], &e->icp_grid[0][1], &e->icp_grid[0][2], &e->icp_grid[0][3], &e->icp_grid[0][4],
                           &e->icp_grid[1][0], &e->icp_grid[1][1], &e->icp_grid[1][2], &e->icp_grid[1][3], &e->icp_grid[1][4]};
         for (DevBuf* b : bufs) b->release();
@@ -283,6 +311,23 @@ int scl_set_stream(scl_engine* e, void* s)
     CK(cudaStreamSynchronize(e->stream));
     if (e->own_stream) cudaStreamDestroy(e->stream);
     e->stream = static_cast<cudaStream_t>(s); e->own_stream = false;
+    return SCL_OK;
+}
+
+int scl_set_knn_mode(scl_engine* e, int mode, int count_fallbacks)
+{
+    LOCK();
+    if (mode < 0 || mode > 2) FAIL(SCL_ERR_INVALID, "mode must be 0 (auto), 1 (exact) or 2 (tensor core)");
+    if (mode == 2 && !scl_knn_tc_supported(e->p.num_ring)) FAIL(SCL_ERR_UNSUPPORTED, "tensor-core kNN is built for 20 and 40 rings");
+    e->knn_mode = mode; e->count_fallbacks = count_fallbacks != 0;
+    return SCL_OK;
+}
+
+int scl_knn_stats(scl_engine* e, long long* tc_queries, long long* fallback_queries)
+{
+    LOCK();
+    if (tc_queries) *tc_queries = e->stat_tc_queries;
+    if (fallback_queries) *fallback_queries = e->stat_fallback_queries;
     return SCL_OK;
 }
 
@@ -354,7 +399,7 @@ int scl_insert_batch(scl_engine* e, const float* descs, int n, const int8_t* rob
     const size_t RS = e->RS();
     float* dst = e->d_desc + (size_t)e->n * RS;
     CK(cudaMemcpyAsync(dst, descs, (size_t)n * RS * 4, cudaMemcpyHostToDevice, e->stream));   /* wire decode, descriptor.h:1575-1582 */
-    CK(scl_launch_ring_keys(dst, n, e->p.num_ring, e->p.num_sector, e->d_keys + (size_t)e->n * e->p.num_ring, e->d_knorm + e->n, e->stream));
+    CK(scl_launch_ring_keys(dst, n, e->p.num_ring, e->p.num_sector, e->d_keys + (size_t)e->n * e->p.num_ring, e->d_knorm + e->n, e->d_kn2max, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     append_index(e, n, robots, indices); e->n += n;
     return SCL_OK;
@@ -371,7 +416,7 @@ int scl_insert_batch_dev(scl_engine* e, const float* descs_dev, int n, const int
     const size_t RS = e->RS();
     float* dst = e->d_desc + (size_t)e->n * RS;
     CK(cudaMemcpyAsync(dst, descs_dev, (size_t)n * RS * 4, cudaMemcpyDeviceToDevice, e->stream));
-    CK(scl_launch_ring_keys(dst, n, e->p.num_ring, e->p.num_sector, e->d_keys + (size_t)e->n * e->p.num_ring, e->d_knorm + e->n, e->stream));
+    CK(scl_launch_ring_keys(dst, n, e->p.num_ring, e->p.num_sector, e->d_keys + (size_t)e->n * e->p.num_ring, e->d_knorm + e->n, e->d_kn2max, e->stream));
     append_index(e, n, robots, indices); e->n += n;
     return SCL_OK;
 }

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) polar_bin_kernel(
     PolarParams p, uint32_t* __restrict__ gbins /* [scans][R*S], zero between launches */,
     int* __restrict__ tickets /* [scans], zero between launches */,
     float* __restrict__ out_desc /* [scans][R*S] */, float* __restrict__ out_keys /* [scans][R] */,
-    float* __restrict__ out_knorm /* [scans] */, int* __restrict__ out_ring, int* __restrict__ out_sector)
+    float* __restrict__ out_knorm /* [scans] */, float* __restrict__ kn2max, int* __restrict__ out_ring, int* __restrict__ out_sector)
 {
     extern __shared__ uint32_t sbins[];   /* R*S keys, then R*S floats for the epilogue */
     __shared__ int s_last;
@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(256) polar_bin_kernel(
         float n2 = 0.0f;
         for (int r = 0; r < p.R; r++) n2 = fmaf(sdesc[RS + r], sdesc[RS + r], n2);
         out_knorm[scan] = n2;
+        if (kn2max) atomicMax(reinterpret_cast<int*>(kn2max), __float_as_int(n2));   /* n2 >= 0: int order == float order */
     }
 }
 
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(256) polar_bin_kernel(
 // descriptor.h:1572-1599). One warp per descriptor; the descriptor is staged in shared memory
 // with a padded row pitch so the per-row sequential sums are bank-conflict free.
 __global__ void __launch_bounds__(256) ring_key_kernel(const float* __restrict__ desc, int n, int R, int S,
-                                                       float* __restrict__ keys, float* __restrict__ knorm)
+                                                       float* __restrict__ keys, float* __restrict__ knorm, float* __restrict__ kn2max)
 {
     extern __shared__ float sm[];
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(256) ring_key_kernel(const float* __restrict__
             float n2 = 0.0f;
             for (int r = 0; r < R; r++) n2 = fmaf(mykey[r], mykey[r], n2);
             knorm[d] = n2;
+            if (kn2max) atomicMax(reinterpret_cast<int*>(kn2max), __float_as_int(n2));
         }
         __syncwarp();
     }
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(256) ring_key_kernel(const float* __restrict__
 
 cudaError_t scl_launch_polar(const void* pts_dev, const int* offsets_dev, int n_scans, int max_points, int stride_bytes,
                              int R, int S, double lidar_height, double max_radius, uint32_t* gbins, int* tickets,
-                             float* out_desc, float* out_keys, float* out_knorm, int* out_ring, int* out_sector,
+                             float* out_desc, float* out_keys, float* out_knorm, float* kn2max, int* out_ring, int* out_sector,
                              cudaStream_t stream)
 {
     if (n_scans <= 0) return cudaSuccess;
@@ -198,11 +200,11 @@ cudaError_t scl_launch_polar(const void* pts_dev, const int* offsets_dev, int n_
     const size_t smem = (size_t)R * S * 8 + (size_t)R * 4;
     dim3 grid(chunks, n_scans);
     polar_bin_kernel<kPPT><<<grid, 256, smem, stream>>>(static_cast<const unsigned char*>(pts_dev), offsets_dev, stride_bytes, vec4, p,
-                                                       gbins, tickets, out_desc, out_keys, out_knorm, out_ring, out_sector);
+                                                       gbins, tickets, out_desc, out_keys, out_knorm, kn2max, out_ring, out_sector);
     return cudaGetLastError();
 }
 
-cudaError_t scl_launch_ring_keys(const float* desc_dev, int n, int R, int S, float* keys, float* knorm, cudaStream_t stream)
+cudaError_t scl_launch_ring_keys(const float* desc_dev, int n, int R, int S, float* keys, float* knorm, float* kn2max, cudaStream_t stream)
 {
     if (n <= 0) return cudaSuccess;
     const int warps = 8;
@@ -211,6 +213,6 @@ cudaError_t scl_launch_ring_keys(const float* desc_dev, int n, int R, int S, flo
     if (!attr_done) { cudaFuncSetAttribute(ring_key_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_done = true; }
     int blocks = (n + warps - 1) / warps;
     if (blocks > 8 * SCL_NUM_SMS) blocks = 8 * SCL_NUM_SMS;
-    ring_key_kernel<<<blocks, warps * 32, smem, stream>>>(desc_dev, n, R, S, keys, knorm);
+    ring_key_kernel<<<blocks, warps * 32, smem, stream>>>(desc_dev, n, R, S, keys, knorm, kn2max);
     return cudaGetLastError();
 }

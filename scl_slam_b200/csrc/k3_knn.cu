@@ -57,6 +57,7 @@ __device__ __forceinline__ float key_d2(const float (&q)[R], const float* __rest
 template <int R, int METRIC>
 __global__ void __launch_bounds__(kTQ) knn_exact_kernel(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys,
                                                         int n_db, int K, int split_len, int id_mul, int id_add,
+                                                        const int32_t* __restrict__ qlist, const int* __restrict__ qcount,
                                                         int32_t* __restrict__ part_ids, float* __restrict__ part_d2)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -64,8 +65,12 @@ __global__ void __launch_bounds__(kTQ) knn_exact_kernel(const float* __restrict_
     float* ld = sk + kTK * R;                                       /* [K][kTQ] */
     int* li = reinterpret_cast<int*>(ld + K * kTQ);                 /* [K][kTQ] */
     const int t = threadIdx.x;
-    const int qi = blockIdx.y * kTQ + t;
-    const bool active = qi < Q;
+    /* optional indirection: only the queries in qlist[0..*qcount) (the tensor-core path's fallback) */
+    const int nq = qlist ? *qcount : Q;
+    if (blockIdx.y * kTQ >= nq) return;
+    const int slot = blockIdx.y * kTQ + t;
+    const bool active = slot < nq;
+    const int qi = active ? (qlist ? qlist[slot] : slot) : 0;
     float q[R];
 #pragma unroll
     for (int d = 0; d < R; d++) q[d] = active ? __ldg(qkeys + (size_t)qi * R + d) : 0.0f;
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(kTQ) knn_exact_kernel(const float* __restrict_
         }
     }
     if (!active) return;
-    const size_t o = ((size_t)qi * gridDim.x + blockIdx.x) * K;
+    const size_t o = ((size_t)slot * gridDim.x + blockIdx.x) * K;
     for (int i = 0; i < K; i++) {
         part_d2[o + i] = i < count ? ld[i * kTQ + t] : __int_as_float(0x7f800000);
         part_ids[o + i] = i < count ? li[i * kTQ + t] : 0x7fffffff;
@@ -113,17 +118,19 @@ __global__ void __launch_bounds__(kTQ) knn_exact_kernel(const float* __restrict_
 
 // k-way merge of the per-split sorted lists of one query by one warp; order = (d2, id).
 __global__ void __launch_bounds__(128) knn_merge_kernel(const int32_t* __restrict__ part_ids, const float* __restrict__ part_d2,
-                                                        int Q, int splits, int K, int32_t* __restrict__ out_ids, float* __restrict__ out_d2)
+                                                        int Q, int splits, int K, const int32_t* __restrict__ qlist,
+                                                        const int* __restrict__ qcount, int32_t* __restrict__ out_ids, float* __restrict__ out_d2)
 {
     const int lane = threadIdx.x & 31;
-    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (qi >= Q) return;
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (slot >= (qlist ? *qcount : Q)) return;
+    const int qi = qlist ? qlist[slot] : slot;
     constexpr int kPer = kMaxSplits / 32;
     int head[kPer];
 #pragma unroll
     for (int s = 0; s < kPer; s++) head[s] = 0;
-    const int32_t* pi = part_ids + (size_t)qi * splits * K;
-    const float* pd = part_d2 + (size_t)qi * splits * K;
+    const int32_t* pi = part_ids + (size_t)slot * splits * K;
+    const float* pd = part_d2 + (size_t)slot * splits * K;
     for (int r = 0; r < K; r++) {
         float bd = __int_as_float(0x7f800000); int bi = 0x7fffffff; int bs = -1;
 #pragma unroll
@@ -174,14 +181,14 @@ __global__ void ids_to_local_kernel(const int32_t* __restrict__ ids, int n, int 
 
 template <int R>
 cudaError_t launch_exact(const float* qkeys, int Q, const float* keys, int n_db, int K, int metric, int splits, int split_len,
-                         int id_mul, int id_add, KnnWorkspace ws, cudaStream_t stream)
+                         int id_mul, int id_add, const int32_t* qlist, const int* qcount, KnnWorkspace ws, cudaStream_t stream)
 {
     const size_t smem = (size_t)kTK * R * 4 + (size_t)K * kTQ * 8;
     dim3 grid(splits, (Q + kTQ - 1) / kTQ);
     if (metric == 0)
-        knn_exact_kernel<R, 0><<<grid, kTQ, smem, stream>>>(qkeys, Q, keys, n_db, K, split_len, id_mul, id_add, ws.part_ids, ws.part_d2);
+        knn_exact_kernel<R, 0><<<grid, kTQ, smem, stream>>>(qkeys, Q, keys, n_db, K, split_len, id_mul, id_add, qlist, qcount, ws.part_ids, ws.part_d2);
     else
-        knn_exact_kernel<R, 1><<<grid, kTQ, smem, stream>>>(qkeys, Q, keys, n_db, K, split_len, id_mul, id_add, ws.part_ids, ws.part_d2);
+        knn_exact_kernel<R, 1><<<grid, kTQ, smem, stream>>>(qkeys, Q, keys, n_db, K, split_len, id_mul, id_add, qlist, qcount, ws.part_ids, ws.part_d2);
     return cudaGetLastError();
 }
 
@@ -199,7 +206,8 @@ int scl_knn_splits(int Q, int n_db)
 }
 
 cudaError_t scl_launch_knn_exact(const float* qkeys, int Q, const float* keys, int n_db, int R, int K, int metric,
-                                 int id_mul, int id_add, KnnWorkspace ws, int32_t* out_ids, float* out_d2, cudaStream_t stream)
+                                 int id_mul, int id_add, const int32_t* qlist, const int* qcount, KnnWorkspace ws,
+                                 int32_t* out_ids, float* out_d2, cudaStream_t stream)
 {
     if (Q <= 0) return cudaSuccess;
     if (K < 1 || K > kMaxK) return cudaErrorInvalidValue;
@@ -209,14 +217,14 @@ cudaError_t scl_launch_knn_exact(const float* qkeys, int Q, const float* keys, i
     if (split_len < kTK) split_len = kTK;
     if ((size_t)Q * splits * K > ws.capacity) return cudaErrorInvalidValue;
     cudaError_t err;
-    if (R == 20) err = launch_exact<20>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, ws, stream);
-    else if (R == 40) err = launch_exact<40>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, ws, stream);
-    else if (R == 10) err = launch_exact<10>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, ws, stream);
-    else if (R == 80) err = launch_exact<80>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, ws, stream);
+    if (R == 20) err = launch_exact<20>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, stream);
+    else if (R == 40) err = launch_exact<40>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, stream);
+    else if (R == 10) err = launch_exact<10>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, stream);
+    else if (R == 80) err = launch_exact<80>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, stream);
     else return cudaErrorNotSupported;
     if (err != cudaSuccess) return err;
     const int warps = 4;
-    knn_merge_kernel<<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(ws.part_ids, ws.part_d2, Q, splits, K, out_ids, out_d2);
+    knn_merge_kernel<<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(ws.part_ids, ws.part_d2, Q, splits, K, qlist, qcount, out_ids, out_d2);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,444 @@
+// k3_knn_tc.cu — K3 on the 5th-generation tensor cores: a tcgen05 prefilter for the ring-key kNN,
+// followed by an exact re-rank that keeps the result bit-identical to k3_knn.cu.
+//
+// Replaces (together with k3_knn.cu) nanoflann findNeighbors, /root/reference/include/descriptor.h:1714-1716,
+// and libnabo knn, descriptor.h:1642.
+//
+// Phase A (knn_tc_kernel): the score S(q,k) = |k|^2 - 2 q.k of every (query, key) pair is one
+// augmented GEMM on tcgen05.mma kind::tf32 with FP32 accumulators in TMEM. To get ~FP32 accuracy out
+// of TF32 inputs every value is split x = hi + lo (hi = top 11 significant bits, lo = next 11):
+//      S = [-2q_hi | 1 1 1] . [k_hi | n_hi n_mid n_lo]   (A1 x B_hi)
+//        + [-2q_lo | 0 0 0] . [k_hi | ...]               (A2 x B_hi)
+//        + [-2q_hi | 1 1 1] . [k_lo | 0 0 0]             (A1 x B_lo)
+//   with |k|^2 = n_hi + n_mid + n_lo carried through the same contraction (three more columns).
+//   One CTA per SM: it owns a 128-query tile (M = 128 = TMEM lanes) and one contiguous range of the
+//   key matrix, and is warp-specialised:
+//     warps 0-3  epilogue  : tcgen05.ld 32 columns at a time (thread = query = TMEM lane), compare
+//                            against the thread's running threshold, push hits to a staging buffer,
+//                            fold the staging buffers into per-thread sorted top-K' lists
+//     warps 4-7  producers : stream raw keys (80 B each) from HBM, split hi/lo in registers, write
+//                            the UMMA K-major no-swizzle core-matrix layout into shared memory
+//     warp  8    MMA issuer: one thread issues the 9 tcgen05.mma per key tile and commits to
+//                            mbarriers (smem stage free / accumulator ready)
+//   Shared-memory stages and the two TMEM accumulator stages are handed around with mbarriers only.
+//
+// Phase B (knn_rerank_kernel): one warp per query recomputes the EXACT float distance (the
+//   reference's accumulation order, k3_knn.cu) of every proposed key, selects the top-K by
+//   (d2, id), and CERTIFIES the result: with T the smallest per-range cut-off score and eps the
+//   prefilter's error bound, every key the prefilter dropped has exact d2 > T + |q|^2 - eps; if the
+//   K-th selected distance is below that, no dropped key can belong to (or tie with) the top-K.
+//   Queries that fail the certificate are appended to a list and redone by the exact kernel.
+//
+// Roofline: 2*R*Q*N flops against the tensor pipe, 4*R*N bytes against HBM; in practice bound by
+// the TMEM read-out + compare of Q*N accumulators in the epilogue warps.
+#include "common.cuh"
+#include "kernels.h"
+
+#include <cfloat>
+
+namespace {
+
+constexpr int kKPrimeMax = 24;     /* proposals kept per (query, range) */
+constexpr int kStageCap = 48;      /* staging entries per thread */
+constexpr int kEpiThreads = 128, kProdThreads = 128;
+constexpr int kThreads = kEpiThreads + kProdThreads + 32;
+constexpr float kPadNorm = 1.0e30f, kThrInit = 1.0e29f;
+
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// ---- tcgen05 / mbarrier PTX wrappers ---------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(scl_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(scl_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, no swizzle: core matrix = 8 rows x 16 B stored contiguously; SBO = distance between 8-row
+// groups, LBO = distance between the two 16-byte K chunks of one instruction (cute/arch/mma_sm100_desc.hpp)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;                      /* descriptor version for sm_100 */
+    return d;                                    /* base offset 0, layout type 0 = SWIZZLE_NONE */
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+template <int R, int NT> struct TcCfg {
+    static constexpr int G = ((R / 4 + 1) + 1) / 2 * 2;       /* 16-byte K chunks per row (incl. the norm chunk), even */
+    static constexpr int KSTEPS = G / 2;                      /* tcgen05.mma instructions per product (K = 8 tf32 each) */
+    static constexpr uint32_t A_LBO = 128 * 16, B_LBO = NT * 16, SBO = 128;
+    static constexpr uint32_t A_BLOCK = 128 * G * 16, B_BLOCK = NT * G * 16;
+    static constexpr uint32_t OFF_BAR = 0;                                    /* 8 mbarriers + tmem slot */
+    static constexpr uint32_t OFF_A = 128;                                    /* A1, A2 */
+    static constexpr uint32_t OFF_B = OFF_A + 2 * A_BLOCK;                    /* 2 stages x (B_hi, B_lo) */
+    static constexpr uint32_t OFF_LIST = OFF_B + 4 * B_BLOCK;                 /* [K'][128] val, [K'][128] idx */
+    static constexpr uint32_t OFF_STG = OFF_LIST + 2 * kKPrimeMax * 128 * 4;  /* [cap][128] val, idx */
+    static constexpr uint32_t TOTAL = OFF_STG + 2 * kStageCap * 128 * 4;
+    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+};
+
+template <int R, int NT>
+__global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
+    const float* __restrict__ qkeys, int Q, const float* __restrict__ keys, const float* __restrict__ knorm, int n_db,
+    int range_len, int n_ranges, int kprime,
+    float* __restrict__ prop_s /* [Q][n_ranges][K'] */, int32_t* __restrict__ prop_idx, float* __restrict__ prop_cut /* [Q][n_ranges] */)
+{
+    using C = TcCfg<R, NT>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+    uint64_t *full = bars, *empty = bars + 2, *tfull = bars + 4, *tempty = bars + 6;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qtile = blockIdx.x / n_ranges, range = blockIdx.x % n_ranges;
+    const int k_begin = range * range_len;
+    const int k_end = min(n_db, k_begin + range_len);
+    const int n_tiles = k_end > k_begin ? (k_end - k_begin + NT - 1) / NT : 0;
+
+    // ---- one-time setup -----------------------------------------------------------------------
+    if (threadIdx.x == 0) {
+        scl_mbar_init(&full[0], 4); scl_mbar_init(&full[1], 4);
+        scl_mbar_init(&empty[0], 1); scl_mbar_init(&empty[1], 1);
+        scl_mbar_init(&tfull[0], 1); scl_mbar_init(&tfull[1], 1);
+        scl_mbar_init(&tempty[0], 4); scl_mbar_init(&tempty[1], 4);
+        scl_mbar_fence_init();
+    }
+    if (warp == 8) {   /* TMEM: 2 accumulator stages of NT fp32 columns */
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(scl_smem_u32(tmem_slot)), "r"(2 * NT) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {   /* zero both B stages once (the norm chunk of B_lo and the padding chunk stay zero for ever) */
+        uint4* z = reinterpret_cast<uint4*>(smem + C::OFF_B);
+        for (uint32_t i = threadIdx.x; i < 4 * C::B_BLOCK / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    {   /* A operand: A1 = [-2 q_hi | 1 1 1 0 ...], A2 = [-2 q_lo | 0 ...], rows = the tile's 128 queries */
+        float* A1 = reinterpret_cast<float*>(smem + C::OFF_A);
+        float* A2 = reinterpret_cast<float*>(smem + C::OFF_A + C::A_BLOCK);
+        for (int i = threadIdx.x; i < 128 * C::G; i += kThreads) {
+            const int m = i % 128, g = i / 128;
+            const int qi = qtile * 128 + m;
+            float4 h = make_float4(0, 0, 0, 0), l = make_float4(0, 0, 0, 0);
+            if (g < R / 4) {
+                if (qi < Q) {
+                    const float4 x = __ldg(reinterpret_cast<const float4*>(qkeys + (size_t)qi * R + 4 * g));
+                    const float hx = tf32_trunc(x.x), hy = tf32_trunc(x.y), hz = tf32_trunc(x.z), hw = tf32_trunc(x.w);
+                    h = make_float4(-2.0f * hx, -2.0f * hy, -2.0f * hz, -2.0f * hw);
+                    l = make_float4(-2.0f * tf32_trunc(x.x - hx), -2.0f * tf32_trunc(x.y - hy), -2.0f * tf32_trunc(x.z - hz), -2.0f * tf32_trunc(x.w - hw));
+                }
+            } else if (g == R / 4) {
+                h = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+            }
+            const uint32_t off = (uint32_t)g * C::A_LBO + (uint32_t)(m >> 3) * C::SBO + (uint32_t)(m & 7) * 16;
+            *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(A1) + off) = h;
+            *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(A2) + off) = l;
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ===== epilogue: thread = query = TMEM lane ================================================
+        const int t = threadIdx.x;                 /* 0..127 */
+        float* lv = reinterpret_cast<float*>(smem + C::OFF_LIST);
+        int* li = reinterpret_cast<int*>(lv + kKPrimeMax * 128);
+        float* sv = reinterpret_cast<float*>(smem + C::OFF_STG);
+        int* si = reinterpret_cast<int*>(sv + kStageCap * 128);
+        int count = 0, cnt = 0;
+        float thr = kThrInit;
+        auto fold = [&]() {
+            for (int s = 0; s < cnt; s++) {
+                const float val = sv[s * 128 + t];
+                if (!(val < thr)) continue;
+                const int id = si[s * 128 + t];
+                int i = count < kprime ? count : kprime - 1;
+                for (; i > 0 && lv[(i - 1) * 128 + t] > val; --i) { lv[i * 128 + t] = lv[(i - 1) * 128 + t]; li[i * 128 + t] = li[(i - 1) * 128 + t]; }
+                lv[i * 128 + t] = val; li[i * 128 + t] = id;
+                if (count < kprime) count++;
+                if (count == kprime) thr = lv[(kprime - 1) * 128 + t];
+            }
+            cnt = 0;
+        };
+        for (int tile = 0; tile < n_tiles; tile++) {
+            const int a = tile & 1; const uint32_t ph = (tile >> 1) & 1;
+            scl_mbar_wait(&tfull[a], ph);
+            tc_fence_after();
+            const int key0 = k_begin + tile * NT;
+#pragma unroll 1
+            for (int c = 0; c < NT / 32; c++) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * NT + c * 32), v);
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    if (v[i] < thr) { sv[cnt * 128 + t] = v[i]; si[cnt * 128 + t] = key0 + c * 32 + i; cnt++; }
+                }
+                if (__any_sync(0xffffffffu, cnt > kStageCap - 32)) fold();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[a]);
+        }
+        fold();
+        const int qi = qtile * 128 + t;
+        if (qi < Q) {
+            const size_t o = ((size_t)qi * n_ranges + range) * kprime;
+            for (int i = 0; i < kprime; i++) {
+                prop_s[o + i] = i < count ? lv[i * 128 + t] : __int_as_float(0x7f800000);
+                prop_idx[o + i] = i < count ? li[i * 128 + t] : -1;
+            }
+            /* cut-off of this range: every key NOT proposed has S >= cut (inf if the range was kept whole) */
+            prop_cut[(size_t)qi * n_ranges + range] = count == kprime ? thr : __int_as_float(0x7f800000);
+        }
+    } else if (warp < 8) {
+        // ===== producers: raw keys -> hi/lo split -> UMMA core-matrix layout =======================
+        const int p = threadIdx.x - kEpiThreads;   /* 0..127 */
+        for (int tile = 0; tile < n_tiles; tile++) {
+            const int s = tile & 1; const uint32_t ph = (tile >> 1) & 1;
+            scl_mbar_wait(&empty[s], ph ^ 1u);
+            unsigned char* Bhi = smem + C::OFF_B + (uint32_t)s * 2 * C::B_BLOCK;
+            unsigned char* Blo = Bhi + C::B_BLOCK;
+            const int key0 = k_begin + tile * NT;
+#pragma unroll
+            for (int mm = 0; mm < NT / kProdThreads; mm++) {
+                const int m = p + mm * kProdThreads;
+                const int key = key0 + m;
+                const uint32_t row_off = (uint32_t)(m >> 3) * C::SBO + (uint32_t)(m & 7) * 16;
+                if (key < k_end) {
+                    const float4* src = reinterpret_cast<const float4*>(keys + (size_t)key * R);
+                    float4 x[R / 4];
+#pragma unroll
+                    for (int g = 0; g < R / 4; g++) x[g] = __ldg(src + g);
+                    const float n = __ldg(knorm + key);
+#pragma unroll
+                    for (int g = 0; g < R / 4; g++) {
+                        const float hx = tf32_trunc(x[g].x), hy = tf32_trunc(x[g].y), hz = tf32_trunc(x[g].z), hw = tf32_trunc(x[g].w);
+                        *reinterpret_cast<float4*>(Bhi + (uint32_t)g * C::B_LBO + row_off) = make_float4(hx, hy, hz, hw);
+                        *reinterpret_cast<float4*>(Blo + (uint32_t)g * C::B_LBO + row_off) =
+                            make_float4(tf32_trunc(x[g].x - hx), tf32_trunc(x[g].y - hy), tf32_trunc(x[g].z - hz), tf32_trunc(x[g].w - hw));
+                    }
+                    const float n_hi = tf32_trunc(n), r1 = n - n_hi, n_mid = tf32_trunc(r1), n_lo = tf32_trunc(r1 - n_mid);
+                    *reinterpret_cast<float4*>(Bhi + (uint32_t)(R / 4) * C::B_LBO + row_off) = make_float4(n_hi, n_mid, n_lo, 0.0f);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < R / 4; g++) {
+                        *reinterpret_cast<float4*>(Bhi + (uint32_t)g * C::B_LBO + row_off) = make_float4(0, 0, 0, 0);
+                        *reinterpret_cast<float4*>(Blo + (uint32_t)g * C::B_LBO + row_off) = make_float4(0, 0, 0, 0);
+                    }
+                    *reinterpret_cast<float4*>(Bhi + (uint32_t)(R / 4) * C::B_LBO + row_off) = make_float4(kPadNorm, 0.0f, 0.0f, 0.0f);
+                }
+            }
+            fence_async_smem();                    /* generic-proxy writes -> visible to the tensor core (async proxy) */
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+        }
+    } else {
+        // ===== MMA issuer: one thread ==============================================================
+        if (lane == 0) {
+            const uint32_t a1 = scl_smem_u32(smem + C::OFF_A), a2 = a1 + C::A_BLOCK;
+            for (int tile = 0; tile < n_tiles; tile++) {
+                const int s = tile & 1; const uint32_t ph = (tile >> 1) & 1;
+                scl_mbar_wait(&tempty[s], ph ^ 1u);        /* accumulator stage drained by the epilogue */
+                scl_mbar_wait(&full[s], ph);               /* operands written */
+                tc_fence_after();
+                const uint32_t bhi = scl_smem_u32(smem + C::OFF_B) + (uint32_t)s * 2 * C::B_BLOCK, blo = bhi + C::B_BLOCK;
+                const uint32_t d = tmem_base + (uint32_t)(s * NT);
+                uint32_t acc = 0;
+#pragma unroll
+                for (int k = 0; k < C::KSTEPS; k++) {
+                    tc_mma_tf32(d, make_desc(a1 + 2 * k * C::A_LBO, C::A_LBO, C::SBO), make_desc(bhi + 2 * k * C::B_LBO, C::B_LBO, C::SBO), C::IDESC, acc);
+                    acc = 1;
+                }
+#pragma unroll
+                for (int k = 0; k < C::KSTEPS; k++)
+                    tc_mma_tf32(d, make_desc(a2 + 2 * k * C::A_LBO, C::A_LBO, C::SBO), make_desc(bhi + 2 * k * C::B_LBO, C::B_LBO, C::SBO), C::IDESC, 1);
+#pragma unroll
+                for (int k = 0; k < C::KSTEPS; k++)
+                    tc_mma_tf32(d, make_desc(a1 + 2 * k * C::A_LBO, C::A_LBO, C::SBO), make_desc(blo + 2 * k * C::B_LBO, C::B_LBO, C::SBO), C::IDESC, 1);
+                tc_commit(&empty[s]);                      /* smem stage reusable once these MMAs retire */
+                tc_commit(&tfull[s]);                      /* accumulator ready for the epilogue */
+            }
+        }
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * NT) : "memory");
+    }
+}
+
+template <int METRIC>
+__device__ __forceinline__ float exact_d2(const float* __restrict__ q, const float* __restrict__ k, int R)
+{
+    float result = 0.0f;
+    if (METRIC == 0) {
+        int d = 0;
+        for (; d + 3 < R; d += 4) {
+            const float d0 = __fsub_rn(q[d], k[d]), d1 = __fsub_rn(q[d + 1], k[d + 1]), d2 = __fsub_rn(q[d + 2], k[d + 2]), d3 = __fsub_rn(q[d + 3], k[d + 3]);
+            const float g = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)), __fmul_rn(d3, d3));
+            result = __fadd_rn(result, g);
+        }
+        for (; d < R; d++) { const float d0 = __fsub_rn(q[d], k[d]); result = __fadd_rn(result, __fmul_rn(d0, d0)); }
+    } else {
+        for (int d = 0; d < R; d++) { const float d0 = __fsub_rn(q[d], k[d]); result = __fadd_rn(result, __fmul_rn(d0, d0)); }
+    }
+    return result;
+}
+
+// Phase B: exact re-rank + certificate. One warp per query; n_cand = n_ranges * K' proposals.
+template <int METRIC>
+__global__ void __launch_bounds__(128) knn_rerank_kernel(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys, int R, int K,
+                                                         int n_ranges, int kprime, const int32_t* __restrict__ prop_idx,
+                                                         const float* __restrict__ prop_cut, const float* __restrict__ kn2max,
+                                                         float* __restrict__ exact /* [Q][n_cand] scratch */, int id_mul, int id_add,
+                                                         int32_t* __restrict__ out_ids, float* __restrict__ out_d2,
+                                                         int32_t* __restrict__ fail_list, int* __restrict__ fail_count)
+{
+    const int lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= Q) return;
+    const int n_cand = n_ranges * kprime;
+    const float* q = qkeys + (size_t)qi * R;
+    const int32_t* pidx = prop_idx + (size_t)qi * n_cand;
+    float* ex = exact + (size_t)qi * n_cand;
+    const float inf = __int_as_float(0x7f800000);
+    for (int c = lane; c < n_cand; c += 32) {
+        const int id = pidx[c];
+        float d = inf;
+        if (id >= 0) {
+            d = exact_d2<METRIC>(q, keys + (size_t)id * R, R);
+            if (METRIC == 1 && !(d > FLT_EPSILON)) d = inf;          /* libnabo self-match rule */
+            if (!(d < (METRIC == 0 ? FLT_MAX : inf))) d = inf;       /* never accepted by the trees */
+        }
+        ex[c] = d;
+    }
+    float cut = inf;
+    for (int r = lane; r < n_ranges; r += 32) cut = fminf(cut, prop_cut[(size_t)qi * n_ranges + r]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) cut = fminf(cut, __shfl_xor_sync(0xffffffffu, cut, off));
+    __syncwarp();
+    /* K rounds: smallest (d2, id) strictly after the previous pick */
+    float pd = -1.0f; int pi = -1; float dK = 0.0f; int found = 0;
+    for (int r = 0; r < K; r++) {
+        float bd = inf; int bi = 0x7fffffff;
+        for (int c = lane; c < n_cand; c += 32) {
+            const float d = ex[c];
+            if (!(d < inf)) continue;
+            const int id = pidx[c] * id_mul + id_add;
+            if (d < pd || (d == pd && id <= pi)) continue;
+            if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, bd, off); const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        const bool ok = bi != 0x7fffffff;
+        if (lane == 0) { out_ids[(size_t)qi * K + r] = ok ? bi : -1; out_d2[(size_t)qi * K + r] = ok ? bd : FLT_MAX; }
+        if (ok) { pd = bd; pi = bi; dK = bd; found++; }
+        else break;
+    }
+    if (lane == 0) {
+        for (int r = found; r < K; r++) { out_ids[(size_t)qi * K + r] = -1; out_d2[(size_t)qi * K + r] = FLT_MAX; }
+        bool certified = true;
+        if (cut < inf) {
+            /* dropped keys have S >= cut, i.e. exact d2 > cut + |q|^2 - eps */
+            float qn = 0.0f;
+            for (int d = 0; d < R; d++) qn = fmaf(q[d], q[d], qn);
+            const float s = sqrtf(qn) + sqrtf(__ldg(kn2max));
+            const float eps = 1.52587890625e-05f * s * s + 2.0e-6f * dK;       /* 2^-16 (|q|+|k|max)^2 + exact-side rounding */
+            certified = (found == K) && (dK + eps < cut + qn);
+        }
+        if (!certified) fail_list[atomicAdd(fail_count, 1)] = qi;
+    }
+}
+
+} // namespace
+
+bool scl_knn_tc_supported(int R) { return R == 20 || R == 40; }
+
+int scl_knn_tc_ranges(int Q)
+{
+    const int tiles = (Q + 127) / 128;
+    int r = SCL_NUM_SMS / tiles;
+    return r < 1 ? 1 : r;
+}
+
+int scl_knn_tc_kprime(int K) { int kp = K + 6; if (kp < 8) kp = 8; return kp > kKPrimeMax ? kKPrimeMax : kp; }
+
+template <int R, int NT>
+static cudaError_t launch_tc(const float* qkeys, int Q, const float* keys, const float* knorm, int n_db, int range_len, int n_ranges,
+                             int kprime, float* prop_s, int32_t* prop_idx, float* prop_cut, cudaStream_t stream)
+{
+    using C = TcCfg<R, NT>;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<R, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::TOTAL);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    const int tiles = (Q + 127) / 128;
+    knn_tc_kernel<R, NT><<<tiles * n_ranges, kThreads, C::TOTAL, stream>>>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime,
+                                                                          prop_s, prop_idx, prop_cut);
+    return cudaGetLastError();
+}
+
+cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, const float* knorm, const float* kn2max, int n_db, int R, int K,
+                              int metric, int id_mul, int id_add, KnnTcWorkspace ws, int32_t* out_ids, float* out_d2,
+                              int32_t* fail_list, int* fail_count, cudaStream_t stream)
+{
+    if (Q <= 0) return cudaSuccess;
+    const int n_ranges = scl_knn_tc_ranges(Q);
+    const int kprime = scl_knn_tc_kprime(K);
+    if (K > kprime - 2) return cudaErrorInvalidValue;
+    const int NT = R == 20 ? 256 : 128;
+    int range_len = (n_db + n_ranges - 1) / n_ranges;
+    range_len = (range_len + NT - 1) / NT * NT;
+    if ((size_t)Q * n_ranges * kprime > ws.capacity) return cudaErrorInvalidValue;
+    cudaError_t err = cudaMemsetAsync(fail_count, 0, sizeof(int), stream);
+    if (err != cudaSuccess) return err;
+    if (R == 20) err = launch_tc<20, 256>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
+    else if (R == 40) err = launch_tc<40, 128>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
+    else return cudaErrorNotSupported;
+    if (err != cudaSuccess) return err;
+    const int warps = 4;
+    if (metric == 0)
+        knn_rerank_kernel<0><<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(qkeys, Q, keys, R, K, n_ranges, kprime, ws.prop_idx, ws.prop_cut,
+                                                                                kn2max, ws.exact, id_mul, id_add, out_ids, out_d2, fail_list, fail_count);
+    else
+        knn_rerank_kernel<1><<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(qkeys, Q, keys, R, K, n_ranges, kprime, ws.prop_idx, ws.prop_cut,
+                                                                                kn2max, ws.exact, id_mul, id_add, out_ids, out_d2, fail_list, fail_count);
+    return cudaGetLastError();
+}

@@ -7,10 +7,11 @@
 // K1 (+K2 epilogue): polar binning of a batch of scans. See k1_polar.cu.
 cudaError_t scl_launch_polar(const void* pts_dev, const int* offsets_dev, int n_scans, int max_points, int stride_bytes,
                              int R, int S, double lidar_height, double max_radius, uint32_t* gbins, int* tickets,
-                             float* out_desc, float* out_keys, float* out_knorm, int* out_ring, int* out_sector,
+                             float* out_desc, float* out_keys, float* out_knorm, float* kn2max, int* out_ring, int* out_sector,
                              cudaStream_t stream);
 // K2: ring keys (+ squared key norms) of descriptors already in device memory.
-cudaError_t scl_launch_ring_keys(const float* desc_dev, int n, int R, int S, float* keys, float* knorm, cudaStream_t stream);
+//     kn2max (device scalar, may be null) is raised to the largest squared norm seen (atomicMax on the float bits).
+cudaError_t scl_launch_ring_keys(const float* desc_dev, int n, int R, int S, float* keys, float* knorm, float* kn2max, cudaStream_t stream);
 
 // K3: ring-key kNN. Exact variant (CUDA cores, reference accumulation order). See k3_knn.cu.
 //  qkeys [Q][R], keys [n_db][R]; out ids/d2 [Q][K] ascending by (d2, id); id_mul/id_add map local
@@ -21,8 +22,26 @@ struct KnnWorkspace {
     size_t capacity;     // in entries
 };
 int scl_knn_splits(int Q, int n_db);
+//  qlist/qcount (device, may be null): only queries qlist[0..*qcount) are processed (fallback of the tensor-core path).
 cudaError_t scl_launch_knn_exact(const float* qkeys, int Q, const float* keys, int n_db, int R, int K, int metric,
-                                 int id_mul, int id_add, KnnWorkspace ws, int32_t* out_ids, float* out_d2, cudaStream_t stream);
+                                 int id_mul, int id_add, const int32_t* qlist, const int* qcount, KnnWorkspace ws,
+                                 int32_t* out_ids, float* out_d2, cudaStream_t stream);
+
+// K3 on tcgen05 (k3_knn_tc.cu): tensor-core prefilter + exact re-rank + certificate. Queries whose top-K could not
+// be certified are appended to fail_list (count in *fail_count) for scl_launch_knn_exact.
+struct KnnTcWorkspace {
+    float* prop_s;       // [Q][ranges][K']
+    int32_t* prop_idx;   // [Q][ranges][K']
+    float* prop_cut;     // [Q][ranges]
+    float* exact;        // [Q][ranges*K']
+    size_t capacity;     // in proposal entries
+};
+bool scl_knn_tc_supported(int R);
+int scl_knn_tc_ranges(int Q);
+int scl_knn_tc_kprime(int K);
+cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, const float* knorm, const float* kn2max, int n_db, int R, int K,
+                              int metric, int id_mul, int id_add, KnnTcWorkspace ws, int32_t* out_ids, float* out_d2,
+                              int32_t* fail_list, int* fail_count, cudaStream_t stream);
 
 // K4: shift-aligned column-cosine distance for every (query, candidate) + winner scan. See k4_scdist.cu.
 //  q_desc [Q][R*S] or nullptr (then queries are db entries q_local[i]); cand_local [Q][K] local keys (-1 = none);

@@ -25,7 +25,7 @@ EXPORTS = [
     "scl_reserve", "scl_set_shard", "scl_build_insert", "scl_make_scancontext", "scl_build_batch", "scl_build_batch_dev",
     "scl_insert", "scl_insert_batch", "scl_insert_batch_dev", "scl_get_index", "scl_size", "scl_get_descriptor",
     "scl_get_ring_key", "scl_query_intra", "scl_query_inter", "scl_query_batch", "scl_query_batch_dev",
-    "scl_merge_shards_dev", "scl_icp", "scl_set_profiling", "scl_stage_time",
+    "scl_merge_shards_dev", "scl_icp", "scl_set_profiling", "scl_stage_time", "scl_set_knn_mode", "scl_knn_stats",
 ]
 
 
@@ -87,6 +87,8 @@ def load_library():
     lib.scl_query_batch_dev.argtypes = lib.scl_query_batch.argtypes
     lib.scl_merge_shards_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.POINTER(SclBatchResult)]
+    lib.scl_set_knn_mode.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.scl_knn_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     lib.scl_set_profiling.argtypes = [C.c_void_p, C.c_int]
     lib.scl_stage_time.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     lib.scl_icp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(SclIcpParams),
@@ -258,6 +260,15 @@ class ScanContextB200:
                              ("cand_ids", "cand_d2", "cand_dist", "cand_shift", "best_id", "best_dist", "best_shift")])
         self._ck(self.lib.scl_merge_shards_dev(self.h, world, Q, K, _ptr(q_ids_dev), _ptr(all_ids), _ptr(all_d2),
                                                _ptr(all_dist), _ptr(all_shift), C.byref(r)))
+
+    def set_knn_mode(self, mode, count_fallbacks=False):
+        """0 auto, 1 exact CUDA-core kNN, 2 tensor-core prefilter + exact re-rank (same results)."""
+        self._ck(self.lib.scl_set_knn_mode(self.h, mode, int(count_fallbacks)))
+
+    def knn_stats(self):
+        a, b = C.c_longlong(), C.c_longlong()
+        self._ck(self.lib.scl_knn_stats(self.h, C.byref(a), C.byref(b)))
+        return {"tc_queries": a.value, "fallback_queries": b.value}
 
     def set_profiling(self, on):
         self._ck(self.lib.scl_set_profiling(self.h, int(on)))
