@@ -336,3 +336,57 @@ def test_sharded_equals_unsharded(eng_mod, world):
     ref = sharding.merge_shards_numpy(*[gath[k].cpu().numpy() for k in names])
     for k in dt:
         assert np.array_equal(ref[k], exp[k], equal_nan=True), k
+
+
+# ---------------------------------------------------------------- K3 on tensor cores (tcgen05 prefilter + exact re-rank)
+@pytest.mark.parametrize("R,S,K,n,nq,metric", [(20, 60, 10, 60000, 300, 0), (20, 60, 3, 33000, 129, 1), (40, 120, 10, 40000, 140, 0),
+                                               (20, 60, 16, 50000, 64, 0)])
+def test_tensor_core_knn_equals_oracle(eng_mod, R, S, K, n, nq, metric):
+    """Forced tensor-core mode: candidates, distances, shifts and winners still bit-identical to the
+    CPU oracle, with no query needing the exact fallback on well-separated data."""
+    db = synth.desc_db(n, R, S, seed=91)
+    q, src, shift = synth.desc_queries(db, nq, seed=92)
+    dbn, qn = db.numpy(), q.numpy()
+    o = Oracle(num_ring=R, num_sector=S, num_candidates=K)
+    o.bulk_load(np.concatenate([dbn.reshape(n, -1), qn.reshape(nq, -1)]))
+    e = eng_mod.ScanContextB200(numRing=R, numSector=S, numCandidates=K)
+    e.insert_batch(dbn)
+    e.set_knn_mode(2, True)
+    n_db = n - 77                                            # a search bound that is not a tile multiple
+    got = e.query_batch(q_desc=qn, K=K, n_db=n_db, metric=metric)
+    exp = o.query_batch(np.arange(n, n + nq), n_db, K, metric, nthreads=8)
+    assert np.array_equal(got["cand_ids"], exp["cand_ids"])
+    assert np.array_equal(_bits(got["cand_d2"]), _bits(exp["cand_d2"]))
+    assert np.array_equal(got["cand_shift"], exp["cand_shift"])
+    assert np.array_equal(_bits(got["cand_dist"]), _bits(exp["cand_dist"]))
+    assert np.array_equal(got["best_id"], exp["best_id"]) and np.array_equal(got["best_shift"], exp["best_shift"])
+    st = e.knn_stats()
+    assert st["tc_queries"] == nq and st["fallback_queries"] == 0, st
+
+
+def test_tensor_core_knn_fallback_on_ties(eng_mod):
+    """Adversarial database: hundreds of exact duplicates and near-duplicates around every query, so
+    the prefilter cannot certify a top-K; those queries must be redone exactly and still match."""
+    n, nq, K = 40000, 70, 10
+    db = synth.desc_db(n, seed=93).numpy()
+    rng = np.random.default_rng(5)
+    for b in range(20):                                      # 20 clusters of 120 copies, some perturbed in the last float bits
+        base = db[1000 + b].copy()
+        for j in range(120):
+            d = base.copy()
+            if j % 3 == 1:
+                d[rng.integers(0, 20), rng.integers(0, 60)] += np.float32(1e-5)
+            db[2000 + b * 1500 + j * 7] = d
+    q = np.stack([db[1000 + (i % 20)] for i in range(nq)])   # queries = the cluster centres
+    o = Oracle(num_candidates=K)
+    o.bulk_load(np.concatenate([db.reshape(n, -1), q.reshape(nq, -1)]))
+    e = eng_mod.ScanContextB200(numCandidates=K)
+    e.insert_batch(db)
+    for metric in (0, 1):
+        exp = o.query_batch(np.arange(n, n + nq), n, K, metric, nthreads=8)
+        e.set_knn_mode(2, True)
+        got = e.query_batch(q_desc=q, K=K, n_db=n, metric=metric)
+        assert np.array_equal(got["cand_ids"], exp["cand_ids"]), metric
+        assert np.array_equal(_bits(got["cand_d2"]), _bits(exp["cand_d2"]))
+        assert np.array_equal(got["best_id"], exp["best_id"]) and np.array_equal(got["best_shift"], exp["best_shift"])
+    assert e.knn_stats()["fallback_queries"] > 0
