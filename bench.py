@@ -65,7 +65,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        """Restrict the report to samples taken inside [t0, t1] (the timed region); when the region is
+        shorter than the sampling period, the samples nearest to it (the GPU is under the same load
+        during the warm-up steps right before it)."""
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if not self.proc:
@@ -76,7 +82,17 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
-        for ln in self.lines:
+        lines = self.lines
+        t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
+        where = "whole run"
+        if t0 is not None and lines:
+            inside = [ln for ln in lines if t0 <= ln[0] <= t1]
+            if inside:
+                lines, where = inside, "timed region"
+            else:
+                lines = sorted(lines, key=lambda ln: min(abs(ln[0] - t0), abs(ln[0] - t1)))[:3]
+                where = "nearest to the timed region (region shorter than the 100 ms sampling period)"
+        for _, ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -89,7 +105,8 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm),
+                "window": where}
 
 
 def gen_shard(dev, rank, world, n_db):
@@ -121,6 +138,9 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                      # nvidia-smi needs ~1 s to produce its first line: start it early
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     build.build()
@@ -172,17 +192,16 @@ def run_ours(args):
         flush.zero_()
     barrier()
     e.set_profiling(True)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    t_region0 = time.time()
     for a, b in evs:
         a.record()
         step()
         b.record()
         flush.zero_()
     barrier()
+    sampler.window(t_region0, time.time())
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
     e.set_profiling(False)
     stage = {name: e.stage_time(i) for i, name in ((0, "k2_query_keys"), (1, "k3_knn"), (2, "k4_scdist"))}

@@ -179,8 +179,9 @@ int query_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, i
             const size_t ncand = (size_t)Q * ranges * kp;
             CK(e->tc_prop_s.ensure(ncand * 4)); CK(e->tc_prop_idx.ensure(ncand * 4)); CK(e->tc_exact.ensure(ncand * 4));
             CK(e->tc_prop_cut.ensure((size_t)Q * ranges * 4));
-            CK(e->tc_fail_list.ensure((size_t)Q * 4)); CK(e->tc_fail_count.ensure(64));
-            KnnTcWorkspace tw{e->tc_prop_s.as<float>(), e->tc_prop_idx.as<int32_t>(), e->tc_prop_cut.as<float>(), e->tc_exact.as<float>(), ncand};
+            CK(e->tc_fail_list.ensure((size_t)Q * 4)); CK(e->tc_fail_count.ensure(64)); CK(e->tc_gthr.ensure((size_t)Q * 4));
+            KnnTcWorkspace tw{e->tc_prop_s.as<float>(), e->tc_prop_idx.as<int32_t>(), e->tc_prop_cut.as<float>(), e->tc_exact.as<float>(),
+                              e->tc_gthr.as<int>(), ncand};
             CK(scl_launch_knn_tc(e->qkeys.as<float>(), Q, e->d_keys, e->d_knorm, e->d_kn2max, n_db, R, K, metric, e->world, e->rank, tw,
                                  cand_ids, cand_d2, e->tc_fail_list.as<int32_t>(), e->tc_fail_count.as<int>(), e->stream));
             /* uncertified queries (normally none) are redone exactly; CTAs beyond the list length exit at once */
@@ -291,7 +292,7 @@ int scl_destroy(scl_engine* e)
                           &e->bins_ring, &e->bins_sector, &e->qdesc, &e->qids, &e->qlocal, &e->qkeys, &e->qknorm, &e->part_ids,
                           &e->part_d2, &e->cand_ids, &e->cand_d2, &e->cand_local, &e->cand_dist, &e->cand_shift, &e->best_id,
                           &e->best_dist, &e->best_shift, &e->tc_prop_s, &e->tc_prop_idx, &e->tc_prop_cut, &e->tc_exact,
-                          &e->tc_fail_list, &e->tc_fail_count, &e->icp_src, &e->icp_tgt, &e->icp_raw, &e->icp_acc, &e->icp_nn,
+                          &e->tc_fail_list, &e->tc_fail_count, &e->tc_gthr, &e->icp_src, &e->icp_tgt, &e->icp_raw, &e->icp_acc, &e->icp_nn,
                           &e->icp_grid[0][0], &e->icp_grid[0][1], &e->icp_grid[0][2], &e->icp_grid[0][3], &e->icp_grid[0][4],
                           &e->icp_grid[1][0], &e->icp_grid[1][1], &e->icp_grid[1][2], &e->icp_grid[1][3], &e->icp_grid[1][4]};
         for (DevBuf* b : bufs) b->release();

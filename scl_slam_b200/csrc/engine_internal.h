@@ -49,7 +49,7 @@ struct scl_engine {
     DevBuf pts, offsets, gbins, tickets, stage_desc, stage_keys, stage_knorm, bins_ring, bins_sector;
     DevBuf qdesc, qids, qlocal, qkeys, qknorm, part_ids, part_d2, cand_ids, cand_d2, cand_local, cand_dist, cand_shift,
         best_id, best_dist, best_shift;
-    DevBuf tc_prop_s, tc_prop_idx, tc_prop_cut, tc_exact, tc_fail_list, tc_fail_count;
+    DevBuf tc_prop_s, tc_prop_idx, tc_prop_cut, tc_exact, tc_fail_list, tc_fail_count, tc_gthr;
     DevBuf icp_src, icp_tgt, icp_raw, icp_grid[2][5], icp_acc, icp_nn;
     size_t gbins_scans = 0;
     /* per-stage event timing */

@@ -44,6 +44,10 @@ constexpr int kEpiThreads = 128, kProdThreads = 128;
 constexpr int kThreads = kEpiThreads + kProdThreads + 32;
 constexpr float kPadNorm = 1.0e30f, kThrInit = 1.0e29f;
 
+// order-preserving float <-> signed int image (for atomicMin on scores that may be negative)
+__device__ __forceinline__ int ordered_int(float f) { const int b = __float_as_int(f); return b ^ ((b >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 // ---- tcgen05 / mbarrier PTX wrappers ---------------------------------------------------------
@@ -110,7 +114,7 @@ template <int R, int NT> struct TcCfg {
 template <int R, int NT>
 __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     const float* __restrict__ qkeys, int Q, const float* __restrict__ keys, const float* __restrict__ knorm, int n_db,
-    int range_len, int n_ranges, int kprime,
+    int range_len, int n_ranges, int kprime, int* __restrict__ g_thr /* [Q] shared thresholds (ordered-int image) */,
     float* __restrict__ prop_s /* [Q][n_ranges][K'] */, int32_t* __restrict__ prop_idx, float* __restrict__ prop_cut /* [Q][n_ranges] */)
 {
     using C = TcCfg<R, NT>;
@@ -170,14 +174,21 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
 
     if (warp < 4) {
         // ===== epilogue: thread = query = TMEM lane ================================================
+        // A key is kept only if its score is below the thread's threshold. The threshold is the K'-th
+        // smallest score seen so far for this query — by this CTA, or (through g_thr) by ANY CTA working
+        // on the same query tile: each published value is backed by K' keys at or below it, so it bounds
+        // the global K'-th smallest score from above and nothing in the true top-K' is ever dropped.
         const int t = threadIdx.x;                 /* 0..127 */
+        const int qi = qtile * 128 + t;
         float* lv = reinterpret_cast<float*>(smem + C::OFF_LIST);
         int* li = reinterpret_cast<int*>(lv + kKPrimeMax * 128);
         float* sv = reinterpret_cast<float*>(smem + C::OFF_STG);
         int* si = reinterpret_cast<int*>(sv + kStageCap * 128);
         int count = 0, cnt = 0;
         float thr = kThrInit;
+        int* my_gthr = g_thr + (qi < Q ? qi : 0);
         auto fold = [&]() {
+            const float before = thr;
             for (int s = 0; s < cnt; s++) {
                 const float val = sv[s * 128 + t];
                 if (!(val < thr)) continue;
@@ -189,19 +200,31 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                 if (count == kprime) thr = lv[(kprime - 1) * 128 + t];
             }
             cnt = 0;
+            if (thr < before && count == kprime && qi < Q) atomicMin(my_gthr, ordered_int(thr));
         };
         for (int tile = 0; tile < n_tiles; tile++) {
             const int a = tile & 1; const uint32_t ph = (tile >> 1) & 1;
+            const int shared_thr = __ldcg(my_gthr);            /* in flight while we wait for the accumulator */
             scl_mbar_wait(&tfull[a], ph);
             tc_fence_after();
+            thr = fminf(thr, ordered_float(shared_thr));
             const int key0 = k_begin + tile * NT;
 #pragma unroll 1
             for (int c = 0; c < NT / 32; c++) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * NT + c * 32), v);
+                float m[16];
 #pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    if (v[i] < thr) { sv[cnt * 128 + t] = v[i]; si[cnt * 128 + t] = key0 + c * 32 + i; cnt++; }
+                for (int i = 0; i < 16; i++) m[i] = fminf(v[2 * i], v[2 * i + 1]);
+#pragma unroll
+                for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+                    for (int i = 0; i < w; i++) m[i] = fminf(m[i], m[i + w]);
+                if (m[0] < thr) {                               /* rare once the threshold has tightened */
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        if (v[i] < thr) { sv[cnt * 128 + t] = v[i]; si[cnt * 128 + t] = key0 + c * 32 + i; cnt++; }
+                    }
                 }
                 if (__any_sync(0xffffffffu, cnt > kStageCap - 32)) fold();
             }
@@ -210,57 +233,77 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             if (lane == 0) mbar_arrive(&tempty[a]);
         }
         fold();
-        const int qi = qtile * 128 + t;
         if (qi < Q) {
             const size_t o = ((size_t)qi * n_ranges + range) * kprime;
             for (int i = 0; i < kprime; i++) {
                 prop_s[o + i] = i < count ? lv[i * 128 + t] : __int_as_float(0x7f800000);
                 prop_idx[o + i] = i < count ? li[i * 128 + t] : -1;
             }
-            /* cut-off of this range: every key NOT proposed has S >= cut (inf if the range was kept whole) */
-            prop_cut[(size_t)qi * n_ranges + range] = count == kprime ? thr : __int_as_float(0x7f800000);
+            /* cut-off of this range: every key NOT proposed had S >= the threshold in force when it was
+             * examined >= the final threshold (thresholds only fall); inf if nothing was ever dropped */
+            prop_cut[(size_t)qi * n_ranges + range] = thr < kThrInit ? thr : __int_as_float(0x7f800000);
         }
     } else if (warp < 8) {
         // ===== producers: raw keys -> hi/lo split -> UMMA core-matrix layout =======================
+        // The raw keys of tile t+1 are already in flight (registers) while tile t is split and stored.
         const int p = threadIdx.x - kEpiThreads;   /* 0..127 */
-        for (int tile = 0; tile < n_tiles; tile++) {
-            const int s = tile & 1; const uint32_t ph = (tile >> 1) & 1;
-            scl_mbar_wait(&empty[s], ph ^ 1u);
-            unsigned char* Bhi = smem + C::OFF_B + (uint32_t)s * 2 * C::B_BLOCK;
-            unsigned char* Blo = Bhi + C::B_BLOCK;
-            const int key0 = k_begin + tile * NT;
+        constexpr int KPT = NT / kProdThreads;     /* keys per thread per tile */
+        float4 xa[KPT][R / 4], xb[KPT][R / 4];
+        float na[KPT], nb[KPT];
+        auto load_tile = [&](int tile, float4 (&x)[KPT][R / 4], float (&n)[KPT]) {
 #pragma unroll
-            for (int mm = 0; mm < NT / kProdThreads; mm++) {
-                const int m = p + mm * kProdThreads;
-                const int key = key0 + m;
-                const uint32_t row_off = (uint32_t)(m >> 3) * C::SBO + (uint32_t)(m & 7) * 16;
-                if (key < k_end) {
+            for (int mm = 0; mm < KPT; mm++) {
+                const int key = k_begin + tile * NT + p + mm * kProdThreads;
+                if (tile < n_tiles && key < k_end) {
                     const float4* src = reinterpret_cast<const float4*>(keys + (size_t)key * R);
-                    float4 x[R / 4];
 #pragma unroll
-                    for (int g = 0; g < R / 4; g++) x[g] = __ldg(src + g);
-                    const float n = __ldg(knorm + key);
-#pragma unroll
-                    for (int g = 0; g < R / 4; g++) {
-                        const float hx = tf32_trunc(x[g].x), hy = tf32_trunc(x[g].y), hz = tf32_trunc(x[g].z), hw = tf32_trunc(x[g].w);
-                        *reinterpret_cast<float4*>(Bhi + (uint32_t)g * C::B_LBO + row_off) = make_float4(hx, hy, hz, hw);
-                        *reinterpret_cast<float4*>(Blo + (uint32_t)g * C::B_LBO + row_off) =
-                            make_float4(tf32_trunc(x[g].x - hx), tf32_trunc(x[g].y - hy), tf32_trunc(x[g].z - hz), tf32_trunc(x[g].w - hw));
-                    }
-                    const float n_hi = tf32_trunc(n), r1 = n - n_hi, n_mid = tf32_trunc(r1), n_lo = tf32_trunc(r1 - n_mid);
-                    *reinterpret_cast<float4*>(Bhi + (uint32_t)(R / 4) * C::B_LBO + row_off) = make_float4(n_hi, n_mid, n_lo, 0.0f);
+                    for (int g = 0; g < R / 4; g++) x[mm][g] = __ldg(src + g);
+                    n[mm] = __ldg(knorm + key);
                 } else {
 #pragma unroll
-                    for (int g = 0; g < R / 4; g++) {
-                        *reinterpret_cast<float4*>(Bhi + (uint32_t)g * C::B_LBO + row_off) = make_float4(0, 0, 0, 0);
-                        *reinterpret_cast<float4*>(Blo + (uint32_t)g * C::B_LBO + row_off) = make_float4(0, 0, 0, 0);
-                    }
-                    *reinterpret_cast<float4*>(Bhi + (uint32_t)(R / 4) * C::B_LBO + row_off) = make_float4(kPadNorm, 0.0f, 0.0f, 0.0f);
+                    for (int g = 0; g < R / 4; g++) x[mm][g] = make_float4(0, 0, 0, 0);
+                    n[mm] = kPadNorm;                     /* padded rows can never be proposed */
                 }
             }
-            fence_async_smem();                    /* generic-proxy writes -> visible to the tensor core (async proxy) */
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[s]);
+        };
+        auto store_tile = [&](int s, const float4 (&x)[KPT][R / 4], const float (&n)[KPT]) {
+            unsigned char* Bhi = smem + C::OFF_B + (uint32_t)s * 2 * C::B_BLOCK;
+            unsigned char* Blo = Bhi + C::B_BLOCK;
+#pragma unroll
+            for (int mm = 0; mm < KPT; mm++) {
+                const int m = p + mm * kProdThreads;
+                const uint32_t row_off = (uint32_t)(m >> 3) * C::SBO + (uint32_t)(m & 7) * 16;
+#pragma unroll
+                for (int g = 0; g < R / 4; g++) {
+                    const float hx = tf32_trunc(x[mm][g].x), hy = tf32_trunc(x[mm][g].y), hz = tf32_trunc(x[mm][g].z), hw = tf32_trunc(x[mm][g].w);
+                    *reinterpret_cast<float4*>(Bhi + (uint32_t)g * C::B_LBO + row_off) = make_float4(hx, hy, hz, hw);
+                    *reinterpret_cast<float4*>(Blo + (uint32_t)g * C::B_LBO + row_off) =
+                        make_float4(tf32_trunc(x[mm][g].x - hx), tf32_trunc(x[mm][g].y - hy), tf32_trunc(x[mm][g].z - hz), tf32_trunc(x[mm][g].w - hw));
+                }
+                const float n_hi = tf32_trunc(n[mm]), r1 = n[mm] - n_hi, n_mid = tf32_trunc(r1), n_lo = tf32_trunc(r1 - n_mid);
+                *reinterpret_cast<float4*>(Bhi + (uint32_t)(R / 4) * C::B_LBO + row_off) = make_float4(n_hi, n_mid, n_lo, 0.0f);
+            }
+        };
+        load_tile(0, xa, na);
+        for (int tile = 0; tile < n_tiles; tile += 2) {
+            {
+                load_tile(tile + 1, xb, nb);
+                const uint32_t ph = (tile >> 1) & 1;
+                scl_mbar_wait(&empty[0], ph ^ 1u);
+                store_tile(0, xa, na);
+                fence_async_smem();                /* generic-proxy writes -> visible to the tensor core (async proxy) */
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[0]);
+            }
+            if (tile + 1 < n_tiles) {
+                load_tile(tile + 2, xa, na);
+                const uint32_t ph = ((tile + 1) >> 1) & 1;
+                scl_mbar_wait(&empty[1], ph ^ 1u);
+                store_tile(1, xb, nb);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[1]);
+            }
         }
     } else {
         // ===== MMA issuer: one thread ==============================================================
@@ -400,7 +443,7 @@ int scl_knn_tc_kprime(int K) { int kp = K + 6; if (kp < 8) kp = 8; return kp > k
 
 template <int R, int NT>
 static cudaError_t launch_tc(const float* qkeys, int Q, const float* keys, const float* knorm, int n_db, int range_len, int n_ranges,
-                             int kprime, float* prop_s, int32_t* prop_idx, float* prop_cut, cudaStream_t stream)
+                             int kprime, int* g_thr, float* prop_s, int32_t* prop_idx, float* prop_cut, cudaStream_t stream)
 {
     using C = TcCfg<R, NT>;
     static bool attr = false;
@@ -411,7 +454,7 @@ static cudaError_t launch_tc(const float* qkeys, int Q, const float* keys, const
     }
     const int tiles = (Q + 127) / 128;
     knn_tc_kernel<R, NT><<<tiles * n_ranges, kThreads, C::TOTAL, stream>>>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime,
-                                                                          prop_s, prop_idx, prop_cut);
+                                                                          g_thr, prop_s, prop_idx, prop_cut);
     return cudaGetLastError();
 }
 
@@ -429,8 +472,10 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
     if ((size_t)Q * n_ranges * kprime > ws.capacity) return cudaErrorInvalidValue;
     cudaError_t err = cudaMemsetAsync(fail_count, 0, sizeof(int), stream);
     if (err != cudaSuccess) return err;
-    if (R == 20) err = launch_tc<20, 256>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
-    else if (R == 40) err = launch_tc<40, 128>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
+    err = cudaMemsetAsync(ws.g_thr, 0x7f, (size_t)Q * sizeof(int), stream);   /* 0x7f7f7f7f = 3.4e38: "no threshold yet" */
+    if (err != cudaSuccess) return err;
+    if (R == 20) err = launch_tc<20, 256>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, ws.g_thr, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
+    else if (R == 40) err = launch_tc<40, 128>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, ws.g_thr, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
     else return cudaErrorNotSupported;
     if (err != cudaSuccess) return err;
     const int warps = 4;

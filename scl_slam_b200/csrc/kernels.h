@@ -34,6 +34,7 @@ struct KnnTcWorkspace {
     int32_t* prop_idx;   // [Q][ranges][K']
     float* prop_cut;     // [Q][ranges]
     float* exact;        // [Q][ranges*K']
+    int* g_thr;          // [Q] thresholds shared between the CTAs of a query tile
     size_t capacity;     // in proposal entries
 };
 bool scl_knn_tc_supported(int R);
