@@ -39,7 +39,7 @@
 namespace {
 
 constexpr int kKPrimeMax = 24;     /* proposals kept per (query, range) */
-constexpr int kStageCap = 48;      /* staging entries per thread */
+constexpr int kStageCap = 32;      /* staging entries per thread */
 constexpr int kEpiThreads = 128, kProdThreads = 128;
 constexpr int kThreads = kEpiThreads + kProdThreads + 32;
 constexpr float kPadNorm = 1.0e30f, kThrInit = 1.0e29f;
@@ -97,6 +97,47 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
+
+// 64 consecutive fp32 columns of this warp's 32 TMEM lanes; asynchronous until tmem_wait64 on the same registers
+#define SCL_R8(b) "%" #b
+__device__ __forceinline__ void tmem_ld64_issue(uint32_t taddr, uint32_t (&r)[64])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+          "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+          "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]),
+          "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]),
+          "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr));
+}
+// wait for the outstanding tcgen05.ld; the registers are in/out operands so no use can be scheduled above the wait
+__device__ __forceinline__ void tmem_wait64(uint32_t (&r)[64])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+          "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]),
+          "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+          "+r"(r[30]), "+r"(r[31]), "+r"(r[32]), "+r"(r[33]), "+r"(r[34]), "+r"(r[35]), "+r"(r[36]), "+r"(r[37]), "+r"(r[38]), "+r"(r[39]),
+          "+r"(r[40]), "+r"(r[41]), "+r"(r[42]), "+r"(r[43]), "+r"(r[44]), "+r"(r[45]), "+r"(r[46]), "+r"(r[47]), "+r"(r[48]), "+r"(r[49]),
+          "+r"(r[50]), "+r"(r[51]), "+r"(r[52]), "+r"(r[53]), "+r"(r[54]), "+r"(r[55]), "+r"(r[56]), "+r"(r[57]), "+r"(r[58]), "+r"(r[59]),
+          "+r"(r[60]), "+r"(r[61]), "+r"(r[62]), "+r"(r[63])
+        :: "memory");
+}
+#undef SCL_R8
+__device__ __forceinline__ float fmin3(float a, float b, float c)
+{
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));   /* FMNMX3 */
+    return r;
+}
+
 template <int R, int NT> struct TcCfg {
     static constexpr int G = ((R / 4 + 1) + 1) / 2 * 2;       /* 16-byte K chunks per row (incl. the norm chunk), even */
     static constexpr int KSTEPS = G / 2;                      /* tcgen05.mma instructions per product (K = 8 tf32 each) */
@@ -114,7 +155,8 @@ template <int R, int NT> struct TcCfg {
 template <int R, int NT>
 __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     const float* __restrict__ qkeys, int Q, const float* __restrict__ keys, const float* __restrict__ knorm, int n_db,
-    int range_len, int n_ranges, int kprime, int* __restrict__ g_thr /* [Q] shared thresholds (ordered-int image) */,
+    int range_len, int n_ranges, int kprime,
+    int* __restrict__ g_thr /* [Q] shared thresholds (ordered-int image) */,
     float* __restrict__ prop_s /* [Q][n_ranges][K'] */, int32_t* __restrict__ prop_idx, float* __restrict__ prop_cut /* [Q][n_ranges] */)
 {
     using C = TcCfg<R, NT>;
@@ -202,6 +244,35 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             cnt = 0;
             if (thr < before && count == kprime && qi < Q) atomicMin(my_gthr, ordered_int(thr));
         };
+        // One 64-column TMEM load is always in flight while the previous 64 columns are examined. The common
+        // case is "nothing below the threshold": a min-tree (FMNMX3) over the 64 scores and one compare. Only
+        // the 8-column groups whose minimum beats the threshold are examined element by element.
+        uint32_t va[64], vb[64];
+        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+        auto examine = [&](uint32_t (&r)[64], int key_first) {
+            float g[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float x0 = __uint_as_float(r[8 * j]), x1 = __uint_as_float(r[8 * j + 1]), x2 = __uint_as_float(r[8 * j + 2]),
+                            x3 = __uint_as_float(r[8 * j + 3]), x4 = __uint_as_float(r[8 * j + 4]), x5 = __uint_as_float(r[8 * j + 5]),
+                            x6 = __uint_as_float(r[8 * j + 6]), x7 = __uint_as_float(r[8 * j + 7]);
+                g[j] = fminf(fmin3(fmin3(x0, x1, x2), fmin3(x3, x4, x5), x6), x7);
+            }
+            const float m = fminf(fmin3(fmin3(g[0], g[1], g[2]), fmin3(g[3], g[4], g[5]), g[6]), g[7]);
+            if (m < thr) {                                      /* rare once the threshold has tightened */
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if (g[j] < thr) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const float x = __uint_as_float(r[8 * j + i]);
+                            if (x < thr) { sv[cnt * 128 + t] = x; si[cnt * 128 + t] = key_first + 8 * j + i; cnt++; }
+                        }
+                        if (cnt > kStageCap - 8) fold();
+                    }
+                }
+            }
+        };
         for (int tile = 0; tile < n_tiles; tile++) {
             const int a = tile & 1; const uint32_t ph = (tile >> 1) & 1;
             const int shared_thr = __ldcg(my_gthr);            /* in flight while we wait for the accumulator */
@@ -209,24 +280,18 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             tc_fence_after();
             thr = fminf(thr, ordered_float(shared_thr));
             const int key0 = k_begin + tile * NT;
-#pragma unroll 1
-            for (int c = 0; c < NT / 32; c++) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * NT + c * 32), v);
-                float m[16];
+            const uint32_t col0 = lane_base + (uint32_t)(a * NT);
+            tmem_ld64_issue(col0, va);
 #pragma unroll
-                for (int i = 0; i < 16; i++) m[i] = fminf(v[2 * i], v[2 * i + 1]);
-#pragma unroll
-                for (int w = 8; w > 0; w >>= 1)
-#pragma unroll
-                    for (int i = 0; i < w; i++) m[i] = fminf(m[i], m[i + w]);
-                if (m[0] < thr) {                               /* rare once the threshold has tightened */
-#pragma unroll
-                    for (int i = 0; i < 32; i++) {
-                        if (v[i] < thr) { sv[cnt * 128 + t] = v[i]; si[cnt * 128 + t] = key0 + c * 32 + i; cnt++; }
-                    }
+            for (int c = 0; c < NT / 64; c += 2) {
+                tmem_wait64(va);
+                if (c + 1 < NT / 64) tmem_ld64_issue(col0 + (c + 1) * 64, vb);
+                examine(va, key0 + c * 64);
+                if (c + 1 < NT / 64) {
+                    tmem_wait64(vb);
+                    if (c + 2 < NT / 64) tmem_ld64_issue(col0 + (c + 2) * 64, va);
+                    examine(vb, key0 + (c + 1) * 64);
                 }
-                if (__any_sync(0xffffffffu, cnt > kStageCap - 32)) fold();
             }
             tc_fence_before();
             __syncwarp();
@@ -317,6 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                 const uint32_t bhi = scl_smem_u32(smem + C::OFF_B) + (uint32_t)s * 2 * C::B_BLOCK, blo = bhi + C::B_BLOCK;
                 const uint32_t d = tmem_base + (uint32_t)(s * NT);
                 uint32_t acc = 0;
+                {
 #pragma unroll
                 for (int k = 0; k < C::KSTEPS; k++) {
                     tc_mma_tf32(d, make_desc(a1 + 2 * k * C::A_LBO, C::A_LBO, C::SBO), make_desc(bhi + 2 * k * C::B_LBO, C::B_LBO, C::SBO), C::IDESC, acc);
@@ -328,6 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
 #pragma unroll
                 for (int k = 0; k < C::KSTEPS; k++)
                     tc_mma_tf32(d, make_desc(a1 + 2 * k * C::A_LBO, C::A_LBO, C::SBO), make_desc(blo + 2 * k * C::B_LBO, C::B_LBO, C::SBO), C::IDESC, 1);
+                }
                 tc_commit(&empty[s]);                      /* smem stage reusable once these MMAs retire */
                 tc_commit(&tfull[s]);                      /* accumulator ready for the epilogue */
             }
