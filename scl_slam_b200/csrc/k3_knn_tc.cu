@@ -38,8 +38,8 @@
 
 namespace {
 
-constexpr int kKPrimeMax = 24;     /* proposals kept per (query, range) */
-constexpr int kStageCap = 32;      /* staging entries per thread */
+constexpr int kKPrimeMax = 16;     /* proposals kept per (query, range) */
+constexpr int kStageCap = 80;      /* staging entries per thread: one 64-column chunk can add 64 */
 constexpr int kEpiThreads = 128, kProdThreads = 128;
 constexpr int kThreads = kEpiThreads + kProdThreads + 32;
 constexpr float kPadNorm = 1.0e30f, kThrInit = 1.0e29f;
@@ -268,7 +268,6 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                             const float x = __uint_as_float(r[8 * j + i]);
                             if (x < thr) { sv[cnt * 128 + t] = x; si[cnt * 128 + t] = key_first + 8 * j + i; cnt++; }
                         }
-                        if (cnt > kStageCap - 8) fold();
                     }
                 }
             }
@@ -287,10 +286,12 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                 tmem_wait64(va);
                 if (c + 1 < NT / 64) tmem_ld64_issue(col0 + (c + 1) * 64, vb);
                 examine(va, key0 + c * 64);
+                if (__any_sync(0xffffffffu, cnt > kStageCap - 64)) fold();   /* all lanes fold together: amortised */
                 if (c + 1 < NT / 64) {
                     tmem_wait64(vb);
                     if (c + 2 < NT / 64) tmem_ld64_issue(col0 + (c + 2) * 64, va);
                     examine(vb, key0 + (c + 1) * 64);
+                    if (__any_sync(0xffffffffu, cnt > kStageCap - 64)) fold();
                 }
             }
             tc_fence_before();
