@@ -35,6 +35,9 @@
 #include "kernels.h"
 
 #include <cfloat>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 namespace {
 
@@ -155,7 +158,7 @@ template <int R, int NT> struct TcCfg {
 template <int R, int NT>
 __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     const float* __restrict__ qkeys, int Q, const float* __restrict__ keys, const float* __restrict__ knorm, int n_db,
-    int range_len, int n_ranges, int kprime,
+    int range_len, int n_ranges, int kprime, long long* __restrict__ times /* null, or [grid][8] role timers (SCL_TC_TIMES=1) */,
     int* __restrict__ g_thr /* [Q] shared thresholds (ordered-int image) */,
     float* __restrict__ prop_s /* [Q][n_ranges][K'] */, int32_t* __restrict__ prop_idx, float* __restrict__ prop_cut /* [Q][n_ranges] */)
 {
@@ -272,11 +275,13 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                 }
             }
         };
+        long long tw = 0, tp = 0, c0 = clock64();
         for (int tile = 0; tile < n_tiles; tile++) {
             const int a = tile & 1; const uint32_t ph = (tile >> 1) & 1;
             const int shared_thr = __ldcg(my_gthr);            /* in flight while we wait for the accumulator */
             scl_mbar_wait(&tfull[a], ph);
             tc_fence_after();
+            if (times) { const long long c1 = clock64(); tw += c1 - c0; c0 = c1; }
             thr = fminf(thr, ordered_float(shared_thr));
             const int key0 = k_begin + tile * NT;
             const uint32_t col0 = lane_base + (uint32_t)(a * NT);
@@ -297,7 +302,9 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[a]);
+            if (times) { const long long c1 = clock64(); tp += c1 - c0; c0 = c1; }
         }
+        if (times && threadIdx.x == 0) { times[blockIdx.x * 8 + 0] = tw; times[blockIdx.x * 8 + 1] = tp; }
         fold();
         if (qi < Q) {
             const size_t o = ((size_t)qi * n_ranges + range) * kprime;
@@ -313,14 +320,14 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         // ===== producers: raw keys -> hi/lo split -> UMMA core-matrix layout =======================
         // The raw keys of tile t+1 are already in flight (registers) while tile t is split and stored.
         const int p = threadIdx.x - kEpiThreads;   /* 0..127 */
-        constexpr int KPT = NT / kProdThreads;     /* keys per thread per tile */
+        constexpr int KPT = NT >= kProdThreads ? NT / kProdThreads : 1;     /* keys per thread per tile */
         float4 xa[KPT][R / 4], xb[KPT][R / 4];
         float na[KPT], nb[KPT];
         auto load_tile = [&](int tile, float4 (&x)[KPT][R / 4], float (&n)[KPT]) {
 #pragma unroll
             for (int mm = 0; mm < KPT; mm++) {
                 const int key = k_begin + tile * NT + p + mm * kProdThreads;
-                if (tile < n_tiles && key < k_end) {
+                if (tile < n_tiles && key < k_end && p + mm * kProdThreads < NT) {
                     const float4* src = reinterpret_cast<const float4*>(keys + (size_t)key * R);
 #pragma unroll
                     for (int g = 0; g < R / 4; g++) x[mm][g] = __ldg(src + g);
@@ -338,6 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
 #pragma unroll
             for (int mm = 0; mm < KPT; mm++) {
                 const int m = p + mm * kProdThreads;
+                if (m >= NT) continue;
                 const uint32_t row_off = (uint32_t)(m >> 3) * C::SBO + (uint32_t)(m & 7) * 16;
 #pragma unroll
                 for (int g = 0; g < R / 4; g++) {
@@ -350,35 +358,44 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                 *reinterpret_cast<float4*>(Bhi + (uint32_t)(R / 4) * C::B_LBO + row_off) = make_float4(n_hi, n_mid, n_lo, 0.0f);
             }
         };
+        long long tw = 0, tp = 0, c0 = clock64();
         load_tile(0, xa, na);
         for (int tile = 0; tile < n_tiles; tile += 2) {
             {
                 load_tile(tile + 1, xb, nb);
                 const uint32_t ph = (tile >> 1) & 1;
                 scl_mbar_wait(&empty[0], ph ^ 1u);
+                if (times) { const long long c1 = clock64(); tw += c1 - c0; c0 = c1; }
                 store_tile(0, xa, na);
                 fence_async_smem();                /* generic-proxy writes -> visible to the tensor core (async proxy) */
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[0]);
+                if (times) { const long long c1 = clock64(); tp += c1 - c0; c0 = c1; }
             }
             if (tile + 1 < n_tiles) {
                 load_tile(tile + 2, xa, na);
                 const uint32_t ph = ((tile + 1) >> 1) & 1;
                 scl_mbar_wait(&empty[1], ph ^ 1u);
+                if (times) { const long long c1 = clock64(); tw += c1 - c0; c0 = c1; }
                 store_tile(1, xb, nb);
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[1]);
+                if (times) { const long long c1 = clock64(); tp += c1 - c0; c0 = c1; }
             }
         }
+        if (times && p == 0) { times[blockIdx.x * 8 + 2] = tw; times[blockIdx.x * 8 + 3] = tp; }
     } else {
         // ===== MMA issuer: one thread ==============================================================
         if (lane == 0) {
             const uint32_t a1 = scl_smem_u32(smem + C::OFF_A), a2 = a1 + C::A_BLOCK;
+            long long t_te = 0, t_fu = 0, t_is = 0, c0 = clock64();
             for (int tile = 0; tile < n_tiles; tile++) {
                 const int s = tile & 1; const uint32_t ph = (tile >> 1) & 1;
                 scl_mbar_wait(&tempty[s], ph ^ 1u);        /* accumulator stage drained by the epilogue */
+                if (times) { const long long c1 = clock64(); t_te += c1 - c0; c0 = c1; }
                 scl_mbar_wait(&full[s], ph);               /* operands written */
+                if (times) { const long long c1 = clock64(); t_fu += c1 - c0; c0 = c1; }
                 tc_fence_after();
                 const uint32_t bhi = scl_smem_u32(smem + C::OFF_B) + (uint32_t)s * 2 * C::B_BLOCK, blo = bhi + C::B_BLOCK;
                 const uint32_t d = tmem_base + (uint32_t)(s * NT);
@@ -398,7 +415,9 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                 }
                 tc_commit(&empty[s]);                      /* smem stage reusable once these MMAs retire */
                 tc_commit(&tfull[s]);                      /* accumulator ready for the epilogue */
+                if (times) { const long long c1 = clock64(); t_is += c1 - c0; c0 = c1; }
             }
+            if (times) { times[blockIdx.x * 8 + 4] = t_te; times[blockIdx.x * 8 + 5] = t_fu; times[blockIdx.x * 8 + 6] = t_is; times[blockIdx.x * 8 + 7] = n_tiles; }
         }
         __syncwarp();
     }
@@ -521,8 +540,22 @@ static cudaError_t launch_tc(const float* qkeys, int Q, const float* keys, const
         attr = true;
     }
     const int tiles = (Q + 127) / 128;
-    knn_tc_kernel<R, NT><<<tiles * n_ranges, kThreads, C::TOTAL, stream>>>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime,
+    long long* times = nullptr;
+    const bool want_times = getenv("SCL_TC_TIMES") != nullptr;       /* developer aid: per-role cycle counters on stderr */
+    if (want_times) { cudaMalloc(&times, (size_t)tiles * n_ranges * 8 * sizeof(long long)); cudaMemset(times, 0, (size_t)tiles * n_ranges * 64); }
+    knn_tc_kernel<R, NT><<<tiles * n_ranges, kThreads, C::TOTAL, stream>>>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, times,
                                                                           g_thr, prop_s, prop_idx, prop_cut);
+    if (want_times) {
+        const int nb = tiles * n_ranges;
+        std::vector<long long> h((size_t)nb * 8);
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h.data(), times, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        double a[8] = {0};
+        for (int b = 0; b < nb; b++) for (int i = 0; i < 8; i++) a[i] += (double)h[(size_t)b * 8 + i] / nb;
+        fprintf(stderr, "[tc times, cycles per tile] tiles=%.0f | epilogue wait %.0f work %.0f | producer wait %.0f work %.0f | mma wait_tmem %.0f wait_operands %.0f issue %.0f\n",
+                a[7], a[0] / a[7], a[1] / a[7], a[2] / a[7], a[3] / a[7], a[4] / a[7], a[5] / a[7], a[6] / a[7]);
+        cudaFree(times);
+    }
     return cudaGetLastError();
 }
 
@@ -534,7 +567,7 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
     const int n_ranges = scl_knn_tc_ranges(Q);
     const int kprime = scl_knn_tc_kprime(K);
     if (K > kprime - 2) return cudaErrorInvalidValue;
-    const int NT = R == 20 ? 256 : 128;
+    const int NT = R == 20 ? 256 : 64;
     int range_len = (n_db + n_ranges - 1) / n_ranges;
     range_len = (range_len + NT - 1) / NT * NT;
     if ((size_t)Q * n_ranges * kprime > ws.capacity) return cudaErrorInvalidValue;
@@ -543,7 +576,7 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
     err = cudaMemsetAsync(ws.g_thr, 0x7f, (size_t)Q * sizeof(int), stream);   /* 0x7f7f7f7f = 3.4e38: "no threshold yet" */
     if (err != cudaSuccess) return err;
     if (R == 20) err = launch_tc<20, 256>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, ws.g_thr, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
-    else if (R == 40) err = launch_tc<40, 128>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, ws.g_thr, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
+    else if (R == 40) err = launch_tc<40, 64>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, ws.g_thr, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
     else return cudaErrorNotSupported;
     if (err != cudaSuccess) return err;
     const int warps = 4;
