@@ -13,12 +13,12 @@
 //   with |k|^2 = n_hi + n_mid + n_lo carried through the same contraction (three more columns).
 //   One CTA per SM: it owns a 128-query tile (M = 128 = TMEM lanes) and one contiguous range of the
 //   key matrix, and is warp-specialised:
-//     warps 0-3  epilogue  : tcgen05.ld 32 columns at a time (thread = query = TMEM lane), compare
+//     warps 5-8  epilogue  : tcgen05.ld 32 columns at a time (thread = query = TMEM lane), compare
 //                            against the thread's running threshold, push hits to a staging buffer,
 //                            fold the staging buffers into per-thread sorted top-K' lists
-//     warps 4-7  producers : stream raw keys (80 B each) from HBM, split hi/lo in registers, write
+//     warps 1-4  producers : stream raw keys (80 B each) from HBM, split hi/lo in registers, write
 //                            the UMMA K-major no-swizzle core-matrix layout into shared memory
-//     warp  8    MMA issuer: one thread issues the 9 tcgen05.mma per key tile and commits to
+//     warp  0    MMA issuer: one thread issues the 9 tcgen05.mma per key tile and commits to
 //                            mbarriers (smem stage free / accumulator ready)
 //   Shared-memory stages and the two TMEM accumulator stages are handed around with mbarriers only.
 //
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         scl_mbar_init(&tempty[0], 4); scl_mbar_init(&tempty[1], 4);
         scl_mbar_fence_init();
     }
-    if (warp == 8) {   /* TMEM: 2 accumulator stages of NT fp32 columns */
+    if (warp == 0) {   /* TMEM: 2 accumulator stages of NT fp32 columns */
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(scl_smem_u32(tmem_slot)), "r"(2 * NT) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -217,13 +217,16 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    // Role -> warp mapping: the scheduler favours higher warp ids, so the epilogue (the busiest role) gets
+    // warps 5-8, the producers 1-4 and the single MMA-issuing thread warp 0. tcgen05.ld lets warp w touch
+    // TMEM lanes 32*(w%4).., so epilogue warp w serves queries 32*(w%4)..32*(w%4)+31 of the tile.
+    if (warp >= 5) {
         // ===== epilogue: thread = query = TMEM lane ================================================
         // A key is kept only if its score is below the thread's threshold. The threshold is the K'-th
         // smallest score seen so far for this query — by this CTA, or (through g_thr) by ANY CTA working
         // on the same query tile: each published value is backed by K' keys at or below it, so it bounds
         // the global K'-th smallest score from above and nothing in the true top-K' is ever dropped.
-        const int t = threadIdx.x;                 /* 0..127 */
+        const int t = (warp & 3) * 32 + lane;      /* row of the tile = TMEM lane, 0..127 */
         const int qi = qtile * 128 + t;
         float* lv = reinterpret_cast<float*>(smem + C::OFF_LIST);
         int* li = reinterpret_cast<int*>(lv + kKPrimeMax * 128);
@@ -251,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         // case is "nothing below the threshold": a min-tree (FMNMX3) over the 64 scores and one compare. Only
         // the 8-column groups whose minimum beats the threshold are examined element by element.
         uint32_t va[64], vb[64];
-        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         auto examine = [&](uint32_t (&r)[64], int key_first) {
             float g[8];
 #pragma unroll
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             if (lane == 0) mbar_arrive(&tempty[a]);
             if (times) { const long long c1 = clock64(); tp += c1 - c0; c0 = c1; }
         }
-        if (times && threadIdx.x == 0) { times[blockIdx.x * 8 + 0] = tw; times[blockIdx.x * 8 + 1] = tp; }
+        if (times && t == 0) { times[blockIdx.x * 8 + 0] = tw; times[blockIdx.x * 8 + 1] = tp; }
         fold();
         if (qi < Q) {
             const size_t o = ((size_t)qi * n_ranges + range) * kprime;
@@ -316,10 +319,10 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
              * examined >= the final threshold (thresholds only fall); inf if nothing was ever dropped */
             prop_cut[(size_t)qi * n_ranges + range] = thr < kThrInit ? thr : __int_as_float(0x7f800000);
         }
-    } else if (warp < 8) {
+    } else if (warp >= 1) {
         // ===== producers: raw keys -> hi/lo split -> UMMA core-matrix layout =======================
         // The raw keys of tile t+1 are already in flight (registers) while tile t is split and stored.
-        const int p = threadIdx.x - kEpiThreads;   /* 0..127 */
+        const int p = threadIdx.x - 32;            /* 0..127 */
         constexpr int KPT = NT >= kProdThreads ? NT / kProdThreads : 1;     /* keys per thread per tile */
         float4 xa[KPT][R / 4], xb[KPT][R / 4];
         float na[KPT], nb[KPT];
@@ -423,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * NT) : "memory");
     }
