@@ -41,8 +41,8 @@
 
 namespace {
 
-constexpr int kKPrimeMax = 16;     /* proposals kept per (query, range) */
-constexpr int kStageCap = 80;      /* staging entries per thread: one 64-column chunk can add 64 */
+constexpr int kKPrimeMax = 24;     /* proposals kept per (query, range) */
+constexpr int kStageCap = 24;      /* staging entries per thread: one 8-column group can add 8 */
 constexpr int kEpiThreads = 128, kProdThreads = 128;
 constexpr int kThreads = kEpiThreads + kProdThreads + 32;
 constexpr float kPadNorm = 1.0e30f, kThrInit = 1.0e29f;
@@ -134,6 +134,17 @@ __device__ __forceinline__ void tmem_wait64(uint32_t (&r)[64])
         :: "memory");
 }
 #undef SCL_R8
+// 8 columns, synchronous (used only on the rare "some score beats the threshold" path)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8])
+{
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]) :: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ float fmin3(float a, float b, float c)
 {
     float r;
@@ -233,9 +244,11 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         float* sv = reinterpret_cast<float*>(smem + C::OFF_STG);
         int* si = reinterpret_cast<int*>(sv + kStageCap * 128);
         int count = 0, cnt = 0;
+        int n_slow = 0, n_push = 0, n_fold = 0;      /* developer counters (SCL_TC_TIMES) */
         float thr = kThrInit;
         int* my_gthr = g_thr + (qi < Q ? qi : 0);
         auto fold = [&]() {
+            n_fold++; n_push += cnt;
             const float before = thr;
             for (int s = 0; s < cnt; s++) {
                 const float val = sv[s * 128 + t];
@@ -255,27 +268,32 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         // the 8-column groups whose minimum beats the threshold are examined element by element.
         uint32_t va[64], vb[64];
         const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        auto examine = [&](uint32_t (&r)[64], int key_first) {
-            float g[8];
+        // examine(): 64 scores of this thread's query. Fast path: an FMNMX3 min-tree and one compare. If ANY lane
+        // of the warp has a score below its threshold, the warp walks the (few) 8-column groups concerned in a
+        // ROLLED loop, re-reading just those columns from TMEM — one copy of the push code keeps the kernel small
+        // enough for the instruction cache (the fully unrolled version ran 4x slower on instruction fetch).
+        auto examine = [&](uint32_t (&r)[64], uint32_t col_first, int key_first) {
+            unsigned mask = 0;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const float x0 = __uint_as_float(r[8 * j]), x1 = __uint_as_float(r[8 * j + 1]), x2 = __uint_as_float(r[8 * j + 2]),
                             x3 = __uint_as_float(r[8 * j + 3]), x4 = __uint_as_float(r[8 * j + 4]), x5 = __uint_as_float(r[8 * j + 5]),
                             x6 = __uint_as_float(r[8 * j + 6]), x7 = __uint_as_float(r[8 * j + 7]);
-                g[j] = fminf(fmin3(fmin3(x0, x1, x2), fmin3(x3, x4, x5), x6), x7);
+                const float gj = fminf(fmin3(fmin3(x0, x1, x2), fmin3(x3, x4, x5), x6), x7);
+                mask |= (gj < thr ? 1u : 0u) << j;
             }
-            const float m = fminf(fmin3(fmin3(g[0], g[1], g[2]), fmin3(g[3], g[4], g[5]), g[6]), g[7]);
-            if (m < thr) {                                      /* rare once the threshold has tightened */
+            unsigned wm = __reduce_or_sync(0xffffffffu, mask);
+            if (wm) n_slow++;
+#pragma unroll 1
+            while (wm) {
+                const int j = __ffs(wm) - 1;
+                wm &= wm - 1;
+                float v[8];
+                tmem_ld8(col_first + 8 * j, v);
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    if (g[j] < thr) {
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const float x = __uint_as_float(r[8 * j + i]);
-                            if (x < thr) { sv[cnt * 128 + t] = x; si[cnt * 128 + t] = key_first + 8 * j + i; cnt++; }
-                        }
-                    }
-                }
+                for (int i = 0; i < 8; i++)
+                    if (v[i] < thr) { sv[cnt * 128 + t] = v[i]; si[cnt * 128 + t] = key_first + 8 * j + i; cnt++; }
+                if (__any_sync(0xffffffffu, cnt > kStageCap - 8)) fold();     /* all lanes fold together: amortised */
             }
         };
         long long tw = 0, tp = 0, c0 = clock64();
@@ -289,17 +307,15 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             const int key0 = k_begin + tile * NT;
             const uint32_t col0 = lane_base + (uint32_t)(a * NT);
             tmem_ld64_issue(col0, va);
-#pragma unroll
+#pragma unroll 1
             for (int c = 0; c < NT / 64; c += 2) {
                 tmem_wait64(va);
                 if (c + 1 < NT / 64) tmem_ld64_issue(col0 + (c + 1) * 64, vb);
-                examine(va, key0 + c * 64);
-                if (__any_sync(0xffffffffu, cnt > kStageCap - 64)) fold();   /* all lanes fold together: amortised */
+                examine(va, col0 + c * 64, key0 + c * 64);
                 if (c + 1 < NT / 64) {
                     tmem_wait64(vb);
                     if (c + 2 < NT / 64) tmem_ld64_issue(col0 + (c + 2) * 64, va);
-                    examine(vb, key0 + (c + 1) * 64);
-                    if (__any_sync(0xffffffffu, cnt > kStageCap - 64)) fold();
+                    examine(vb, col0 + (c + 1) * 64, key0 + (c + 1) * 64);
                 }
             }
             tc_fence_before();
@@ -307,7 +323,12 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             if (lane == 0) mbar_arrive(&tempty[a]);
             if (times) { const long long c1 = clock64(); tp += c1 - c0; c0 = c1; }
         }
-        if (times && t == 0) { times[blockIdx.x * 8 + 0] = tw; times[blockIdx.x * 8 + 1] = tp; }
+        if (times) {
+            const int ws = __reduce_add_sync(0xffffffffu, n_slow), wp = __reduce_add_sync(0xffffffffu, n_push + cnt);
+            const unsigned any_slow_chunks = 0;
+            (void)any_slow_chunks;
+            if (t == 0) { times[blockIdx.x * 16 + 0] = tw; times[blockIdx.x * 16 + 1] = tp; times[blockIdx.x * 16 + 8] = ws; times[blockIdx.x * 16 + 9] = wp; times[blockIdx.x * 16 + 10] = n_fold; }
+        }
         fold();
         if (qi < Q) {
             const size_t o = ((size_t)qi * n_ranges + range) * kprime;
@@ -324,8 +345,8 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         // The raw keys of tile t+1 are already in flight (registers) while tile t is split and stored.
         const int p = threadIdx.x - 32;            /* 0..127 */
         constexpr int KPT = NT >= kProdThreads ? NT / kProdThreads : 1;     /* keys per thread per tile */
-        float4 xa[KPT][R / 4], xb[KPT][R / 4];
-        float na[KPT], nb[KPT];
+        float4 xa[KPT][R / 4];
+        float na[KPT];
         auto load_tile = [&](int tile, float4 (&x)[KPT][R / 4], float (&n)[KPT]) {
 #pragma unroll
             for (int mm = 0; mm < KPT; mm++) {
@@ -363,31 +384,19 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         };
         long long tw = 0, tp = 0, c0 = clock64();
         load_tile(0, xa, na);
-        for (int tile = 0; tile < n_tiles; tile += 2) {
-            {
-                load_tile(tile + 1, xb, nb);
-                const uint32_t ph = (tile >> 1) & 1;
-                scl_mbar_wait(&empty[0], ph ^ 1u);
-                if (times) { const long long c1 = clock64(); tw += c1 - c0; c0 = c1; }
-                store_tile(0, xa, na);
-                fence_async_smem();                /* generic-proxy writes -> visible to the tensor core (async proxy) */
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[0]);
-                if (times) { const long long c1 = clock64(); tp += c1 - c0; c0 = c1; }
-            }
-            if (tile + 1 < n_tiles) {
-                load_tile(tile + 2, xa, na);
-                const uint32_t ph = ((tile + 1) >> 1) & 1;
-                scl_mbar_wait(&empty[1], ph ^ 1u);
-                if (times) { const long long c1 = clock64(); tw += c1 - c0; c0 = c1; }
-                store_tile(1, xb, nb);
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[1]);
-                if (times) { const long long c1 = clock64(); tp += c1 - c0; c0 = c1; }
-            }
+#pragma unroll 1
+        for (int tile = 0; tile < n_tiles; tile++) {
+            const int s = tile & 1; const uint32_t ph = (tile >> 1) & 1;
+            scl_mbar_wait(&empty[s], ph ^ 1u);
+            if (times) { const long long c1 = clock64(); tw += c1 - c0; c0 = c1; }
+            store_tile(s, xa, na);
+            fence_async_smem();                    /* generic-proxy writes -> visible to the tensor core (async proxy) */
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+            load_tile(tile + 1, xa, na);           /* in flight while we wait for the next free stage */
+            if (times) { const long long c1 = clock64(); tp += c1 - c0; c0 = c1; }
         }
-        if (times && p == 0) { times[blockIdx.x * 8 + 2] = tw; times[blockIdx.x * 8 + 3] = tp; }
+        if (times && p == 0) { times[blockIdx.x * 16 + 2] = tw; times[blockIdx.x * 16 + 3] = tp; }
     } else {
         // ===== MMA issuer: one thread ==============================================================
         if (lane == 0) {
@@ -420,7 +429,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                 tc_commit(&tfull[s]);                      /* accumulator ready for the epilogue */
                 if (times) { const long long c1 = clock64(); t_is += c1 - c0; c0 = c1; }
             }
-            if (times) { times[blockIdx.x * 8 + 4] = t_te; times[blockIdx.x * 8 + 5] = t_fu; times[blockIdx.x * 8 + 6] = t_is; times[blockIdx.x * 8 + 7] = n_tiles; }
+            if (times) { times[blockIdx.x * 16 + 4] = t_te; times[blockIdx.x * 16 + 5] = t_fu; times[blockIdx.x * 16 + 6] = t_is; times[blockIdx.x * 16 + 7] = n_tiles; }
         }
         __syncwarp();
     }
@@ -545,16 +554,18 @@ static cudaError_t launch_tc(const float* qkeys, int Q, const float* keys, const
     const int tiles = (Q + 127) / 128;
     long long* times = nullptr;
     const bool want_times = getenv("SCL_TC_TIMES") != nullptr;       /* developer aid: per-role cycle counters on stderr */
-    if (want_times) { cudaMalloc(&times, (size_t)tiles * n_ranges * 8 * sizeof(long long)); cudaMemset(times, 0, (size_t)tiles * n_ranges * 64); }
+    if (want_times) { cudaMalloc(&times, (size_t)tiles * n_ranges * 16 * sizeof(long long)); cudaMemset(times, 0, (size_t)tiles * n_ranges * 128); }
     knn_tc_kernel<R, NT><<<tiles * n_ranges, kThreads, C::TOTAL, stream>>>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, times,
                                                                           g_thr, prop_s, prop_idx, prop_cut);
     if (want_times) {
         const int nb = tiles * n_ranges;
-        std::vector<long long> h((size_t)nb * 8);
+        std::vector<long long> h((size_t)nb * 16);
         cudaStreamSynchronize(stream);
         cudaMemcpy(h.data(), times, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-        double a[8] = {0};
-        for (int b = 0; b < nb; b++) for (int i = 0; i < 8; i++) a[i] += (double)h[(size_t)b * 8 + i] / nb;
+        double a[16] = {0};
+        for (int b = 0; b < nb; b++) for (int i = 0; i < 16; i++) a[i] += (double)h[(size_t)b * 16 + i] / nb;
+        fprintf(stderr, "[tc counters, warp 0 of each CTA] lane-chunks in slow path %.0f of %.0f, pushes %.0f (per lane %.1f), folds %.0f\n",
+                a[8], a[7] * 32 * 4, a[9], a[9] / 32, a[10]);
         fprintf(stderr, "[tc times, cycles per tile] tiles=%.0f | epilogue wait %.0f work %.0f | producer wait %.0f work %.0f | mma wait_tmem %.0f wait_operands %.0f issue %.0f\n",
                 a[7], a[0] / a[7], a[1] / a[7], a[2] / a[7], a[3] / a[7], a[4] / a[7], a[5] / a[7], a[6] / a[7]);
         cudaFree(times);
