@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         int* my_v4 = g_v4 + (size_t)(qi < Q ? qi : 0) * n_ranges;
         int v4_pub = 0x7f7f7f7f;
         const int m_need = (kprime + 3) / 4;               /* <= 6 for K' <= 24 */
-        const int n_peek = n_ranges < 16 ? n_ranges : 16;
+        const int n_peek = n_ranges < 24 ? n_ranges : 24;
         auto fold = [&]() {
             n_fold++; n_push += cnt;
             const float before = thr;
@@ -275,12 +275,12 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                 if (o < v4_pub) { v4_pub = o; __stcg(my_v4 + range, o); }
             }
         };
-        // refresh: m-th smallest of the published 4th-smallest scores. The (<= 16) loads are issued together
+        // refresh: m-th smallest of the published 4th-smallest scores. The (<= 24) loads are issued together
         // before the accumulator wait (refresh_load) and consumed after it (refresh_apply).
-        int peek[16];
+        int peek[24];
         auto refresh_load = [&]() {
 #pragma unroll
-            for (int r = 0; r < 16; r++) {
+            for (int r = 0; r < 24; r++) {
                 int rr = range + r; if (rr >= n_ranges) rr -= n_ranges;
                 peek[r] = r < n_peek ? __ldcg(my_v4 + rr) : 0x7f7f7f7f;
             }
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         auto refresh_apply = [&]() {
             float b0 = kThrInit, b1 = kThrInit, b2 = kThrInit, b3 = kThrInit, b4 = kThrInit, b5 = kThrInit;
 #pragma unroll
-            for (int r = 0; r < 16; r++) {
+            for (int r = 0; r < 24; r++) {
                 float x = ordered_float(peek[r]);
                 float y;
                 y = fminf(b0, x); x = fmaxf(b0, x); b0 = y;
@@ -301,8 +301,6 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             const float b = m_need <= 1 ? b0 : m_need == 2 ? b1 : m_need == 3 ? b2 : m_need == 4 ? b3 : m_need == 5 ? b4 : b5;
             thr = fminf(thr, b);
         };
-        uint32_t va[64], vb[64];
-        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         // examine(): 64 scores of this thread's query. Fast path: an FMNMX3 min-tree and one compare. If ANY lane
         // of the warp has a score below its threshold, the warp walks the (few) 8-column groups concerned in a
         // ROLLED loop, re-reading just those columns from TMEM — one copy of the push code keeps the kernel small
