@@ -275,21 +275,12 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                 if (o < v4_pub) { v4_pub = o; __stcg(my_v4 + range, o); }
             }
         };
-        // refresh: m-th smallest of the published 4th-smallest scores. The (<= 24) loads are issued together
-        // before the accumulator wait (refresh_load) and consumed after it (refresh_apply).
-        int peek[24];
-        auto refresh_load = [&]() {
-#pragma unroll
-            for (int r = 0; r < 24; r++) {
-                int rr = range + r; if (rr >= n_ranges) rr -= n_ranges;
-                peek[r] = r < n_peek ? __ldcg(my_v4 + rr) : 0x7f7f7f7f;
-            }
-        };
-        auto refresh_apply = [&]() {
+        auto refresh = [&]() {                               /* m-th smallest of the published 4th-smallest scores */
             float b0 = kThrInit, b1 = kThrInit, b2 = kThrInit, b3 = kThrInit, b4 = kThrInit, b5 = kThrInit;
-#pragma unroll
-            for (int r = 0; r < 24; r++) {
-                float x = ordered_float(peek[r]);
+#pragma unroll 1
+            for (int r = 0; r < n_peek; r++) {
+                int rr = range + r; if (rr >= n_ranges) rr -= n_ranges;
+                float x = ordered_float(__ldcg(my_v4 + rr));
                 float y;
                 y = fminf(b0, x); x = fmaxf(b0, x); b0 = y;
                 y = fminf(b1, x); x = fmaxf(b1, x); b1 = y;
@@ -301,6 +292,11 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             const float b = m_need <= 1 ? b0 : m_need == 2 ? b1 : m_need == 3 ? b2 : m_need == 4 ? b3 : m_need == 5 ? b4 : b5;
             thr = fminf(thr, b);
         };
+        // One 64-column TMEM load is always in flight while the previous 64 columns are examined. The common
+        // case is "nothing below the threshold": a min-tree (FMNMX3) over the 64 scores and one compare. Only
+        // the 8-column groups whose minimum beats the threshold are examined element by element.
+        uint32_t va[64], vb[64];
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         // examine(): 64 scores of this thread's query. Fast path: an FMNMX3 min-tree and one compare. If ANY lane
         // of the warp has a score below its threshold, the warp walks the (few) 8-column groups concerned in a
         // ROLLED loop, re-reading just those columns from TMEM — one copy of the push code keeps the kernel small
@@ -333,13 +329,11 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         for (int tile = 0; tile < n_tiles; tile++) {
             const int a = tile & 1; const uint32_t ph = (tile >> 1) & 1;
             const int shared_thr = __ldcg(my_gthr);            /* in flight while we wait for the accumulator */
-            const bool do_refresh = tile > 0 && (tile < 8 || (tile & 3) == 3);   /* thresholds move fastest at the start */
-            if (do_refresh) refresh_load();
             scl_mbar_wait(&tfull[a], ph);
             tc_fence_after();
             if (times) { const long long c1 = clock64(); tw += c1 - c0; c0 = c1; }
             thr = fminf(thr, ordered_float(shared_thr));
-            if (do_refresh) refresh_apply();
+            if ((tile & 3) == 3) refresh();
             const int key0 = k_begin + tile * NT;
             const uint32_t col0 = lane_base + (uint32_t)(a * NT);
             tmem_ld64_issue(col0, va);
