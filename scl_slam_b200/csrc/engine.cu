@@ -179,9 +179,9 @@ int query_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, i
             const size_t ncand = (size_t)Q * ranges * kp;
             CK(e->tc_prop_s.ensure(ncand * 4)); CK(e->tc_prop_idx.ensure(ncand * 4)); CK(e->tc_exact.ensure(ncand * 4));
             CK(e->tc_prop_cut.ensure((size_t)Q * ranges * 4));
-            CK(e->tc_fail_list.ensure((size_t)Q * 4)); CK(e->tc_fail_count.ensure(64)); CK(e->tc_gthr.ensure((size_t)Q * 4 + (size_t)Q * ranges * 4));
+            CK(e->tc_fail_list.ensure((size_t)Q * 4)); CK(e->tc_fail_count.ensure(64)); CK(e->tc_gthr.ensure((size_t)Q * 4));
             KnnTcWorkspace tw{e->tc_prop_s.as<float>(), e->tc_prop_idx.as<int32_t>(), e->tc_prop_cut.as<float>(), e->tc_exact.as<float>(),
-                              e->tc_gthr.as<int>(), e->tc_gthr.as<int>() + Q, ncand};
+                              e->tc_gthr.as<int>(), ncand};
             CK(scl_launch_knn_tc(e->qkeys.as<float>(), Q, e->d_keys, e->d_knorm, e->d_kn2max, n_db, R, K, metric, e->world, e->rank, tw,
                                  cand_ids, cand_d2, e->tc_fail_list.as<int32_t>(), e->tc_fail_count.as<int>(), e->stream));
             /* uncertified queries (normally none) are redone exactly; CTAs beyond the list length exit at once */

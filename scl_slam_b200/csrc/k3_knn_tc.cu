@@ -170,7 +170,7 @@ template <int R, int NT>
 __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     const float* __restrict__ qkeys, int Q, const float* __restrict__ keys, const float* __restrict__ knorm, int n_db,
     int range_len, int n_ranges, int kprime, long long* __restrict__ times /* null, or [grid][8] role timers (SCL_TC_TIMES=1) */,
-    int* __restrict__ g_thr /* [Q] shared thresholds (ordered-int image) */, int* __restrict__ g_v4 /* [Q][n_ranges] 4th-smallest scores */,
+    int* __restrict__ g_thr /* [Q] shared thresholds (ordered-int image) */,
     float* __restrict__ prop_s /* [Q][n_ranges][K'] */, int32_t* __restrict__ prop_idx, float* __restrict__ prop_cut /* [Q][n_ranges] */)
 {
     using C = TcCfg<R, NT>;
@@ -247,14 +247,6 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         int n_slow = 0, n_push = 0, n_fold = 0;      /* developer counters (SCL_TC_TIMES) */
         float thr = kThrInit;
         int* my_gthr = g_thr + (qi < Q ? qi : 0);
-        // Union-level threshold: every CTA publishes the 4th smallest score it holds for each query. If b is the
-        // m-th smallest of those published values (any subset of ranges), at least 4m keys of the database score
-        // <= b, so with 4m >= K' nothing in the true top-K' can score above b: b is a valid threshold, and it is
-        // close to the K'-th smallest over ALL keys examined so far by all CTAs, not just by this one.
-        int* my_v4 = g_v4 + (size_t)(qi < Q ? qi : 0) * n_ranges;
-        int v4_pub = 0x7f7f7f7f;
-        const int m_need = (kprime + 3) / 4;               /* <= 6 for K' <= 24 */
-        const int n_peek = n_ranges < 24 ? n_ranges : 24;
         auto fold = [&]() {
             n_fold++; n_push += cnt;
             const float before = thr;
@@ -270,27 +262,6 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             }
             cnt = 0;
             if (thr < before && count == kprime && qi < Q) atomicMin(my_gthr, ordered_int(thr));
-            if (count >= 4 && qi < Q) {
-                const int o = ordered_int(lv[3 * 128 + t]);
-                if (o < v4_pub) { v4_pub = o; __stcg(my_v4 + range, o); }
-            }
-        };
-        auto refresh = [&]() {                               /* m-th smallest of the published 4th-smallest scores */
-            float b0 = kThrInit, b1 = kThrInit, b2 = kThrInit, b3 = kThrInit, b4 = kThrInit, b5 = kThrInit;
-#pragma unroll 1
-            for (int r = 0; r < n_peek; r++) {
-                int rr = range + r; if (rr >= n_ranges) rr -= n_ranges;
-                float x = ordered_float(__ldcg(my_v4 + rr));
-                float y;
-                y = fminf(b0, x); x = fmaxf(b0, x); b0 = y;
-                y = fminf(b1, x); x = fmaxf(b1, x); b1 = y;
-                y = fminf(b2, x); x = fmaxf(b2, x); b2 = y;
-                y = fminf(b3, x); x = fmaxf(b3, x); b3 = y;
-                y = fminf(b4, x); x = fmaxf(b4, x); b4 = y;
-                b5 = fminf(b5, x);
-            }
-            const float b = m_need <= 1 ? b0 : m_need == 2 ? b1 : m_need == 3 ? b2 : m_need == 4 ? b3 : m_need == 5 ? b4 : b5;
-            thr = fminf(thr, b);
         };
         // One 64-column TMEM load is always in flight while the previous 64 columns are examined. The common
         // case is "nothing below the threshold": a min-tree (FMNMX3) over the 64 scores and one compare. Only
@@ -333,7 +304,6 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             tc_fence_after();
             if (times) { const long long c1 = clock64(); tw += c1 - c0; c0 = c1; }
             thr = fminf(thr, ordered_float(shared_thr));
-            if ((tile & 3) == 3) refresh();
             const int key0 = k_begin + tile * NT;
             const uint32_t col0 = lane_base + (uint32_t)(a * NT);
             tmem_ld64_issue(col0, va);
@@ -572,7 +542,7 @@ int scl_knn_tc_kprime(int K) { int kp = K + 6; if (kp < 8) kp = 8; return kp > k
 
 template <int R, int NT>
 static cudaError_t launch_tc(const float* qkeys, int Q, const float* keys, const float* knorm, int n_db, int range_len, int n_ranges,
-                             int kprime, int* g_thr, int* g_v4, float* prop_s, int32_t* prop_idx, float* prop_cut, cudaStream_t stream)
+                             int kprime, int* g_thr, float* prop_s, int32_t* prop_idx, float* prop_cut, cudaStream_t stream)
 {
     using C = TcCfg<R, NT>;
     static bool attr = false;
@@ -586,7 +556,7 @@ static cudaError_t launch_tc(const float* qkeys, int Q, const float* keys, const
     const bool want_times = getenv("SCL_TC_TIMES") != nullptr;       /* developer aid: per-role cycle counters on stderr */
     if (want_times) { cudaMalloc(&times, (size_t)tiles * n_ranges * 16 * sizeof(long long)); cudaMemset(times, 0, (size_t)tiles * n_ranges * 128); }
     knn_tc_kernel<R, NT><<<tiles * n_ranges, kThreads, C::TOTAL, stream>>>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, times,
-                                                                          g_thr, g_v4, prop_s, prop_idx, prop_cut);
+                                                                          g_thr, prop_s, prop_idx, prop_cut);
     if (want_times) {
         const int nb = tiles * n_ranges;
         std::vector<long long> h((size_t)nb * 16);
@@ -619,10 +589,8 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
     if (err != cudaSuccess) return err;
     err = cudaMemsetAsync(ws.g_thr, 0x7f, (size_t)Q * sizeof(int), stream);   /* 0x7f7f7f7f = 3.4e38: "no threshold yet" */
     if (err != cudaSuccess) return err;
-    err = cudaMemsetAsync(ws.g_v4, 0x7f, (size_t)Q * n_ranges * sizeof(int), stream);
-    if (err != cudaSuccess) return err;
-    if (R == 20) err = launch_tc<20, 256>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, ws.g_thr, ws.g_v4, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
-    else if (R == 40) err = launch_tc<40, 64>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, ws.g_thr, ws.g_v4, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
+    if (R == 20) err = launch_tc<20, 256>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, ws.g_thr, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
+    else if (R == 40) err = launch_tc<40, 64>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, ws.g_thr, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
     else return cudaErrorNotSupported;
     if (err != cudaSuccess) return err;
     const int warps = 4;

@@ -35,7 +35,6 @@ struct KnnTcWorkspace {
     float* prop_cut;     // [Q][ranges]
     float* exact;        // [Q][ranges*K']
     int* g_thr;          // [Q] thresholds shared between the CTAs of a query tile
-    int* g_v4;           // [Q][ranges] 4th-smallest score published by each CTA (union-level threshold)
     size_t capacity;     // in proposal entries
 };
 bool scl_knn_tc_supported(int R);
