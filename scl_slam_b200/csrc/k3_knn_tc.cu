@@ -13,7 +13,7 @@
 //   with |k|^2 = n_hi + n_mid + n_lo carried through the same contraction (three more columns).
 //   One CTA per SM: it owns a 128-query tile (M = 128 = TMEM lanes) and one contiguous range of the
 //   key matrix, and is warp-specialised:
-//     warps 5-8  epilogue  : tcgen05.ld 32 columns at a time (thread = query = TMEM lane), compare
+//     warps 5-12 epilogue  : tcgen05.ld 32 columns at a time (thread = query = TMEM lane), compare
 //                            against the thread's running threshold, push hits to a staging buffer,
 //                            fold the staging buffers into per-thread sorted top-K' lists
 //     warps 1-4  producers : stream raw keys (80 B each) from HBM, split hi/lo in registers, write
@@ -41,10 +41,10 @@
 
 namespace {
 
-constexpr int kKPrimeMax = 24;     /* proposals kept per (query, range) */
-constexpr int kStageCap = 24;      /* staging entries per thread: one 8-column group can add 8 */
-constexpr int kEpiThreads = 128, kProdThreads = 128;
-constexpr int kThreads = kEpiThreads + kProdThreads + 32;
+constexpr int kKPrimeMax = 16;     /* proposals kept per (query, sub-range) */
+constexpr int kStageCap = 16;      /* staging entries per thread: one 8-column group can add 8 */
+constexpr int kEpiThreads = 256, kProdThreads = 128;   /* two epilogue warps per TMEM lane quadrant, each takes half of the columns */
+constexpr int kThreads = 32 + kProdThreads + kEpiThreads;
 constexpr float kPadNorm = 1.0e30f, kThrInit = 1.0e29f;
 
 // order-preserving float <-> signed int image (for atomicMin on scores that may be negative)
@@ -160,9 +160,9 @@ template <int R, int NT> struct TcCfg {
     static constexpr uint32_t OFF_BAR = 0;                                    /* 8 mbarriers + tmem slot */
     static constexpr uint32_t OFF_A = 128;                                    /* A1, A2 */
     static constexpr uint32_t OFF_B = OFF_A + 2 * A_BLOCK;                    /* 2 stages x (B_hi, B_lo) */
-    static constexpr uint32_t OFF_LIST = OFF_B + 4 * B_BLOCK;                 /* [K'][128] val, [K'][128] idx */
-    static constexpr uint32_t OFF_STG = OFF_LIST + 2 * kKPrimeMax * 128 * 4;  /* [cap][128] val, idx */
-    static constexpr uint32_t TOTAL = OFF_STG + 2 * kStageCap * 128 * 4;
+    static constexpr uint32_t OFF_LIST = OFF_B + 4 * B_BLOCK;                 /* [K'][256] val, [K'][256] idx */
+    static constexpr uint32_t OFF_STG = OFF_LIST + 2 * kKPrimeMax * kEpiThreads * 4;  /* [cap][256] val, idx */
+    static constexpr uint32_t TOTAL = OFF_STG + 2 * kStageCap * kEpiThreads * 4;
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
 
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         scl_mbar_init(&full[0], 4); scl_mbar_init(&full[1], 4);
         scl_mbar_init(&empty[0], 1); scl_mbar_init(&empty[1], 1);
         scl_mbar_init(&tfull[0], 1); scl_mbar_init(&tfull[1], 1);
-        scl_mbar_init(&tempty[0], 4); scl_mbar_init(&tempty[1], 4);
+        scl_mbar_init(&tempty[0], kEpiThreads / 32); scl_mbar_init(&tempty[1], kEpiThreads / 32);
         scl_mbar_fence_init();
     }
     if (warp == 0) {   /* TMEM: 2 accumulator stages of NT fp32 columns */
@@ -232,17 +232,21 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     // warps 5-8, the producers 1-4 and the single MMA-issuing thread warp 0. tcgen05.ld lets warp w touch
     // TMEM lanes 32*(w%4).., so epilogue warp w serves queries 32*(w%4)..32*(w%4)+31 of the tile.
     if (warp >= 5) {
-        // ===== epilogue: thread = query = TMEM lane ================================================
+        // ===== epilogue: thread = (query = TMEM lane, half of the columns) ================================================
         // A key is kept only if its score is below the thread's threshold. The threshold is the K'-th
         // smallest score seen so far for this query — by this CTA, or (through g_thr) by ANY CTA working
         // on the same query tile: each published value is backed by K' keys at or below it, so it bounds
         // the global K'-th smallest score from above and nothing in the true top-K' is ever dropped.
-        const int t = (warp & 3) * 32 + lane;      /* row of the tile = TMEM lane, 0..127 */
-        const int qi = qtile * 128 + t;
+        constexpr int E = kEpiThreads;
+        const int half = (warp - 5) >> 2;          /* which half of every tile's columns this warp examines */
+        const int row = (warp & 3) * 32 + lane;    /* row of the tile = TMEM lane, 0..127 */
+        const int t = half * 128 + row;            /* slot of this thread in the shared-memory lists */
+        const int qi = qtile * 128 + row;
+        const int n_sub = 2 * n_ranges, sub = 2 * range + half;
         float* lv = reinterpret_cast<float*>(smem + C::OFF_LIST);
-        int* li = reinterpret_cast<int*>(lv + kKPrimeMax * 128);
+        int* li = reinterpret_cast<int*>(lv + kKPrimeMax * E);
         float* sv = reinterpret_cast<float*>(smem + C::OFF_STG);
-        int* si = reinterpret_cast<int*>(sv + kStageCap * 128);
+        int* si = reinterpret_cast<int*>(sv + kStageCap * E);
         int count = 0, cnt = 0;
         int n_slow = 0, n_push = 0, n_fold = 0;      /* developer counters (SCL_TC_TIMES) */
         float thr = kThrInit;
@@ -251,14 +255,14 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             n_fold++; n_push += cnt;
             const float before = thr;
             for (int s = 0; s < cnt; s++) {
-                const float val = sv[s * 128 + t];
+                const float val = sv[s * E + t];
                 if (!(val < thr)) continue;
-                const int id = si[s * 128 + t];
+                const int id = si[s * E + t];
                 int i = count < kprime ? count : kprime - 1;
-                for (; i > 0 && lv[(i - 1) * 128 + t] > val; --i) { lv[i * 128 + t] = lv[(i - 1) * 128 + t]; li[i * 128 + t] = li[(i - 1) * 128 + t]; }
-                lv[i * 128 + t] = val; li[i * 128 + t] = id;
+                for (; i > 0 && lv[(i - 1) * E + t] > val; --i) { lv[i * E + t] = lv[(i - 1) * E + t]; li[i * E + t] = li[(i - 1) * E + t]; }
+                lv[i * E + t] = val; li[i * E + t] = id;
                 if (count < kprime) count++;
-                if (count == kprime) thr = lv[(kprime - 1) * 128 + t];
+                if (count == kprime) thr = lv[(kprime - 1) * E + t];
             }
             cnt = 0;
             if (thr < before && count == kprime && qi < Q) atomicMin(my_gthr, ordered_int(thr));
@@ -266,12 +270,8 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         // One 64-column TMEM load is always in flight while the previous 64 columns are examined. The common
         // case is "nothing below the threshold": a min-tree (FMNMX3) over the 64 scores and one compare. Only
         // the 8-column groups whose minimum beats the threshold are examined element by element.
-        uint32_t va[64], vb[64];
+        uint32_t va[64];
         const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        // examine(): 64 scores of this thread's query. Fast path: an FMNMX3 min-tree and one compare. If ANY lane
-        // of the warp has a score below its threshold, the warp walks the (few) 8-column groups concerned in a
-        // ROLLED loop, re-reading just those columns from TMEM — one copy of the push code keeps the kernel small
-        // enough for the instruction cache (the fully unrolled version ran 4x slower on instruction fetch).
         auto examine = [&](uint32_t (&r)[64], uint32_t col_first, int key_first) {
             unsigned mask = 0;
 #pragma unroll
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                 tmem_ld8(col_first + 8 * j, v);
 #pragma unroll
                 for (int i = 0; i < 8; i++)
-                    if (v[i] < thr) { sv[cnt * 128 + t] = v[i]; si[cnt * 128 + t] = key_first + 8 * j + i; cnt++; }
+                    if (v[i] < thr) { sv[cnt * E + t] = v[i]; si[cnt * E + t] = key_first + 8 * j + i; cnt++; }
                 if (__any_sync(0xffffffffu, cnt > kStageCap - 8)) fold();     /* all lanes fold together: amortised */
             }
         };
@@ -306,17 +306,12 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             thr = fminf(thr, ordered_float(shared_thr));
             const int key0 = k_begin + tile * NT;
             const uint32_t col0 = lane_base + (uint32_t)(a * NT);
-            tmem_ld64_issue(col0, va);
 #pragma unroll 1
-            for (int c = 0; c < NT / 64; c += 2) {
+            for (int c = 0; c < NT / 128; c++) {               /* this warp's half of the tile, 64 columns at a time */
+                const int cc = half * (NT / 128) + c;
+                tmem_ld64_issue(col0 + cc * 64, va);
                 tmem_wait64(va);
-                if (c + 1 < NT / 64) tmem_ld64_issue(col0 + (c + 1) * 64, vb);
-                examine(va, col0 + c * 64, key0 + c * 64);
-                if (c + 1 < NT / 64) {
-                    tmem_wait64(vb);
-                    if (c + 2 < NT / 64) tmem_ld64_issue(col0 + (c + 2) * 64, va);
-                    examine(vb, col0 + (c + 1) * 64, key0 + (c + 1) * 64);
-                }
+                examine(va, col0 + cc * 64, key0 + cc * 64);
             }
             tc_fence_before();
             __syncwarp();
@@ -331,14 +326,14 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         }
         fold();
         if (qi < Q) {
-            const size_t o = ((size_t)qi * n_ranges + range) * kprime;
+            const size_t o = ((size_t)qi * n_sub + sub) * kprime;
             for (int i = 0; i < kprime; i++) {
-                prop_s[o + i] = i < count ? lv[i * 128 + t] : __int_as_float(0x7f800000);
-                prop_idx[o + i] = i < count ? li[i * 128 + t] : -1;
+                prop_s[o + i] = i < count ? lv[i * E + t] : __int_as_float(0x7f800000);
+                prop_idx[o + i] = i < count ? li[i * E + t] : -1;
             }
             /* cut-off of this range: every key NOT proposed had S >= the threshold in force when it was
              * examined >= the final threshold (thresholds only fall); inf if nothing was ever dropped */
-            prop_cut[(size_t)qi * n_ranges + range] = thr < kThrInit ? thr : __int_as_float(0x7f800000);
+            prop_cut[(size_t)qi * n_sub + sub] = thr < kThrInit ? thr : __int_as_float(0x7f800000);
         }
     } else if (warp >= 1) {
         // ===== producers: raw keys -> hi/lo split -> UMMA core-matrix layout =======================
@@ -581,24 +576,24 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
     const int n_ranges = scl_knn_tc_ranges(Q);
     const int kprime = scl_knn_tc_kprime(K);
     if (K > kprime - 2) return cudaErrorInvalidValue;
-    const int NT = R == 20 ? 256 : 64;
+    const int NT = R == 20 ? 256 : 128;
     int range_len = (n_db + n_ranges - 1) / n_ranges;
     range_len = (range_len + NT - 1) / NT * NT;
-    if ((size_t)Q * n_ranges * kprime > ws.capacity) return cudaErrorInvalidValue;
+    if ((size_t)Q * 2 * n_ranges * kprime > ws.capacity) return cudaErrorInvalidValue;   /* two sub-ranges (column halves) per CTA */
     cudaError_t err = cudaMemsetAsync(fail_count, 0, sizeof(int), stream);
     if (err != cudaSuccess) return err;
     err = cudaMemsetAsync(ws.g_thr, 0x7f, (size_t)Q * sizeof(int), stream);   /* 0x7f7f7f7f = 3.4e38: "no threshold yet" */
     if (err != cudaSuccess) return err;
     if (R == 20) err = launch_tc<20, 256>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, ws.g_thr, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
-    else if (R == 40) err = launch_tc<40, 64>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, ws.g_thr, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
+    else if (R == 40) err = launch_tc<40, 128>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, ws.g_thr, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
     else return cudaErrorNotSupported;
     if (err != cudaSuccess) return err;
     const int warps = 4;
     if (metric == 0)
-        knn_rerank_kernel<0><<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(qkeys, Q, keys, R, K, n_ranges, kprime, ws.prop_idx, ws.prop_cut,
+        knn_rerank_kernel<0><<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(qkeys, Q, keys, R, K, 2 * n_ranges, kprime, ws.prop_idx, ws.prop_cut,
                                                                                 kn2max, ws.exact, id_mul, id_add, out_ids, out_d2, fail_list, fail_count);
     else
-        knn_rerank_kernel<1><<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(qkeys, Q, keys, R, K, n_ranges, kprime, ws.prop_idx, ws.prop_cut,
+        knn_rerank_kernel<1><<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(qkeys, Q, keys, R, K, 2 * n_ranges, kprime, ws.prop_idx, ws.prop_cut,
                                                                                 kn2max, ws.exact, id_mul, id_add, out_ids, out_d2, fail_list, fail_count);
     return cudaGetLastError();
 }
