@@ -175,7 +175,7 @@ int query_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, i
     {
         StageTimer st(e, 1);
         if (use_tc) {
-            const int ranges = 2 * scl_knn_tc_ranges(Q), kp = scl_knn_tc_kprime(K);   /* two column halves per CTA */
+            const int ranges = 4 * scl_knn_tc_ranges(Q), kp = scl_knn_tc_kprime(K);   /* two passes x two column halves per CTA */
             const size_t ncand = (size_t)Q * ranges * kp;
             CK(e->tc_prop_s.ensure(ncand * 4)); CK(e->tc_prop_idx.ensure(ncand * 4)); CK(e->tc_exact.ensure(ncand * 4));
             CK(e->tc_prop_cut.ensure((size_t)Q * ranges * 4));

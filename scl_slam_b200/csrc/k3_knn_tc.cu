@@ -168,8 +168,8 @@ template <int R, int NT> struct TcCfg {
 
 template <int R, int NT>
 __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
-    const float* __restrict__ qkeys, int Q, const float* __restrict__ keys, const float* __restrict__ knorm, int n_db,
-    int range_len, int n_ranges, int kprime, long long* __restrict__ times /* null, or [grid][8] role timers (SCL_TC_TIMES=1) */,
+    const float* __restrict__ qkeys, int Q, const float* __restrict__ keys, const float* __restrict__ knorm, int key_lo, int key_hi,
+    int range_len, int n_ranges, int kprime, int sub_base, int n_sub_total, long long* __restrict__ times /* null, or [grid][8] role timers (SCL_TC_TIMES=1) */,
     int* __restrict__ g_thr /* [Q] shared thresholds (ordered-int image) */,
     float* __restrict__ prop_s /* [Q][n_ranges][K'] */, int32_t* __restrict__ prop_idx, float* __restrict__ prop_cut /* [Q][n_ranges] */)
 {
@@ -180,8 +180,8 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qtile = blockIdx.x / n_ranges, range = blockIdx.x % n_ranges;
-    const int k_begin = range * range_len;
-    const int k_end = min(n_db, k_begin + range_len);
+    const int k_begin = key_lo + range * range_len;       /* this launch covers keys [key_lo, key_hi) */
+    const int k_end = min(key_hi, k_begin + range_len);
     const int n_tiles = k_end > k_begin ? (k_end - k_begin + NT - 1) / NT : 0;
 
     // ---- one-time setup -----------------------------------------------------------------------
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         const int row = (warp & 3) * 32 + lane;    /* row of the tile = TMEM lane, 0..127 */
         const int t = half * 128 + row;            /* slot of this thread in the shared-memory lists */
         const int qi = qtile * 128 + row;
-        const int n_sub = 2 * n_ranges, sub = 2 * range + half;
+        const int sub = sub_base + 2 * range + half;       /* slot of this thread's proposal list among all sub-ranges */
         float* lv = reinterpret_cast<float*>(smem + C::OFF_LIST);
         int* li = reinterpret_cast<int*>(lv + kKPrimeMax * E);
         float* sv = reinterpret_cast<float*>(smem + C::OFF_STG);
@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         // case is "nothing below the threshold": a min-tree (FMNMX3) over the 64 scores and one compare. Only
         // the 8-column groups whose minimum beats the threshold are examined element by element.
         uint32_t va[64];
+        long long t_ld = 0, t_slow = 0;                      /* developer probes (SCL_TC_TIMES) */
         const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         auto examine = [&](uint32_t (&r)[64], uint32_t col_first, int key_first) {
             unsigned mask = 0;
@@ -284,6 +285,9 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             }
             unsigned wm = __reduce_or_sync(0xffffffffu, mask);
             if (wm) n_slow++;
+            long long e0 = 0;
+            if (times && wm) e0 = clock64();
+            const bool was_slow = wm != 0;
 #pragma unroll 1
             while (wm) {
                 const int j = __ffs(wm) - 1;
@@ -295,22 +299,27 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                     if (v[i] < thr) { sv[cnt * E + t] = v[i]; si[cnt * E + t] = key_first + 8 * j + i; cnt++; }
                 if (__any_sync(0xffffffffu, cnt > kStageCap - 8)) fold();     /* all lanes fold together: amortised */
             }
+            if (times && was_slow) t_slow += clock64() - e0;
         };
         long long tw = 0, tp = 0, c0 = clock64();
+        int shared_thr = __ldcg(my_gthr);                      /* then fetched one tile ahead: its L2 latency is never exposed */
         for (int tile = 0; tile < n_tiles; tile++) {
             const int a = tile & 1; const uint32_t ph = (tile >> 1) & 1;
-            const int shared_thr = __ldcg(my_gthr);            /* in flight while we wait for the accumulator */
             scl_mbar_wait(&tfull[a], ph);
             tc_fence_after();
             if (times) { const long long c1 = clock64(); tw += c1 - c0; c0 = c1; }
             thr = fminf(thr, ordered_float(shared_thr));
+            shared_thr = __ldcg(my_gthr);
             const int key0 = k_begin + tile * NT;
             const uint32_t col0 = lane_base + (uint32_t)(a * NT);
 #pragma unroll 1
             for (int c = 0; c < NT / 128; c++) {               /* this warp's half of the tile, 64 columns at a time */
                 const int cc = half * (NT / 128) + c;
+                long long d0 = 0;
+                if (times) d0 = clock64();
                 tmem_ld64_issue(col0 + cc * 64, va);
                 tmem_wait64(va);
+                if (times) { const long long d1 = clock64(); t_ld += d1 - d0; }
                 examine(va, col0 + cc * 64, key0 + cc * 64);
             }
             tc_fence_before();
@@ -322,18 +331,18 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             const int ws = __reduce_add_sync(0xffffffffu, n_slow), wp = __reduce_add_sync(0xffffffffu, n_push + cnt);
             const unsigned any_slow_chunks = 0;
             (void)any_slow_chunks;
-            if (t == 0) { times[blockIdx.x * 16 + 0] = tw; times[blockIdx.x * 16 + 1] = tp; times[blockIdx.x * 16 + 8] = ws; times[blockIdx.x * 16 + 9] = wp; times[blockIdx.x * 16 + 10] = n_fold; }
+            if (t == 0) { times[blockIdx.x * 16 + 0] = tw; times[blockIdx.x * 16 + 1] = tp; times[blockIdx.x * 16 + 8] = ws; times[blockIdx.x * 16 + 9] = wp; times[blockIdx.x * 16 + 10] = n_fold; times[blockIdx.x * 16 + 11] = t_ld; times[blockIdx.x * 16 + 12] = t_slow; }
         }
         fold();
         if (qi < Q) {
-            const size_t o = ((size_t)qi * n_sub + sub) * kprime;
+            const size_t o = ((size_t)qi * n_sub_total + sub) * kprime;
             for (int i = 0; i < kprime; i++) {
                 prop_s[o + i] = i < count ? lv[i * E + t] : __int_as_float(0x7f800000);
                 prop_idx[o + i] = i < count ? li[i * E + t] : -1;
             }
             /* cut-off of this range: every key NOT proposed had S >= the threshold in force when it was
              * examined >= the final threshold (thresholds only fall); inf if nothing was ever dropped */
-            prop_cut[(size_t)qi * n_sub + sub] = thr < kThrInit ? thr : __int_as_float(0x7f800000);
+            prop_cut[(size_t)qi * n_sub_total + sub] = thr < kThrInit ? thr : __int_as_float(0x7f800000);
         }
     } else if (warp >= 1) {
         // ===== producers: raw keys -> hi/lo split -> UMMA core-matrix layout =======================
@@ -436,6 +445,38 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     }
 }
 
+// Between the sample pass and the main pass: the K'-th smallest score over the sample keys (= over the union of
+// the sample pass' proposal lists) becomes every CTA's starting threshold for that query. One warp per query.
+__global__ void __launch_bounds__(128) knn_sample_thr_kernel(const float* __restrict__ prop_s, int Q, int n_sub_total, int n_sub_sample,
+                                                             int kprime, int* __restrict__ g_thr)
+{
+    const int lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= Q) return;
+    const float* ps = prop_s + (size_t)qi * n_sub_total * kprime;
+    const int n = n_sub_sample * kprime;
+    const float inf = __int_as_float(0x7f800000);
+    float pv = -inf; int pc = -1;                       /* previous pick (value, slot): picks are strictly increasing in (value, slot) */
+    float kth = inf;
+    for (int r = 0; r < kprime; r++) {
+        float bv = inf; int bc = 0x7fffffff;
+        for (int c = lane; c < n; c += 32) {
+            const float v = ps[c];
+            if (!(v < inf)) continue;
+            if (v < pv || (v == pv && c <= pc)) continue;
+            if (v < bv || (v == bv && c < bc)) { bv = v; bc = c; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, off); const int oc = __shfl_xor_sync(0xffffffffu, bc, off);
+            if (ov < bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
+        }
+        if (bc == 0x7fffffff) { kth = inf; break; }     /* fewer than K' sample keys: no threshold */
+        pv = bv; pc = bc; kth = bv;
+    }
+    if (lane == 0 && kth < inf) atomicMin(g_thr + qi, ordered_int(kth));
+}
+
 template <int METRIC>
 __device__ __forceinline__ float exact_d2(const float* __restrict__ q, const float* __restrict__ k, int R)
 {
@@ -536,8 +577,9 @@ int scl_knn_tc_ranges(int Q)
 int scl_knn_tc_kprime(int K) { int kp = K + 6; if (kp < 8) kp = 8; return kp > kKPrimeMax ? kKPrimeMax : kp; }
 
 template <int R, int NT>
-static cudaError_t launch_tc(const float* qkeys, int Q, const float* keys, const float* knorm, int n_db, int range_len, int n_ranges,
-                             int kprime, int* g_thr, float* prop_s, int32_t* prop_idx, float* prop_cut, cudaStream_t stream)
+static cudaError_t launch_tc(const float* qkeys, int Q, const float* keys, const float* knorm, int key_lo, int key_hi, int n_ranges,
+                             int kprime, int sub_base, int n_sub_total, int* g_thr, float* prop_s, int32_t* prop_idx, float* prop_cut,
+                             cudaStream_t stream)
 {
     using C = TcCfg<R, NT>;
     static bool attr = false;
@@ -546,12 +588,15 @@ static cudaError_t launch_tc(const float* qkeys, int Q, const float* keys, const
         if (e != cudaSuccess) return e;
         attr = true;
     }
+    int range_len = (key_hi - key_lo + n_ranges - 1) / n_ranges;
+    range_len = (range_len + NT - 1) / NT * NT;
+    if (range_len < NT) range_len = NT;
     const int tiles = (Q + 127) / 128;
     long long* times = nullptr;
     const bool want_times = getenv("SCL_TC_TIMES") != nullptr;       /* developer aid: per-role cycle counters on stderr */
     if (want_times) { cudaMalloc(&times, (size_t)tiles * n_ranges * 16 * sizeof(long long)); cudaMemset(times, 0, (size_t)tiles * n_ranges * 128); }
-    knn_tc_kernel<R, NT><<<tiles * n_ranges, kThreads, C::TOTAL, stream>>>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, times,
-                                                                          g_thr, prop_s, prop_idx, prop_cut);
+    knn_tc_kernel<R, NT><<<tiles * n_ranges, kThreads, C::TOTAL, stream>>>(qkeys, Q, keys, knorm, key_lo, key_hi, range_len, n_ranges, kprime,
+                                                                          sub_base, n_sub_total, times, g_thr, prop_s, prop_idx, prop_cut);
     if (want_times) {
         const int nb = tiles * n_ranges;
         std::vector<long long> h((size_t)nb * 16);
@@ -559,13 +604,24 @@ static cudaError_t launch_tc(const float* qkeys, int Q, const float* keys, const
         cudaMemcpy(h.data(), times, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
         double a[16] = {0};
         for (int b = 0; b < nb; b++) for (int i = 0; i < 16; i++) a[i] += (double)h[(size_t)b * 16 + i] / nb;
-        fprintf(stderr, "[tc counters, warp 0 of each CTA] lane-chunks in slow path %.0f of %.0f, pushes %.0f (per lane %.1f), folds %.0f\n",
-                a[8], a[7] * 32 * 4, a[9], a[9] / 32, a[10]);
-        fprintf(stderr, "[tc times, cycles per tile] tiles=%.0f | epilogue wait %.0f work %.0f | producer wait %.0f work %.0f | mma wait_tmem %.0f wait_operands %.0f issue %.0f\n",
-                a[7], a[0] / a[7], a[1] / a[7], a[2] / a[7], a[3] / a[7], a[4] / a[7], a[5] / a[7], a[6] / a[7]);
+        fprintf(stderr, "[tc keys %d..%d] tiles/CTA %.0f | cycles per tile: epilogue wait %.0f work %.0f (tmem %.0f, slow path %.0f) | producer wait %.0f work %.0f | "
+                        "mma wait_tmem %.0f wait_operands %.0f issue %.0f | per warp: slow chunks %.0f, pushes/lane %.1f, folds %.0f\n",
+                key_lo, key_hi, a[7], a[0] / a[7], a[1] / a[7], a[11] / a[7], a[12] / a[7], a[2] / a[7], a[3] / a[7], a[4] / a[7], a[5] / a[7], a[6] / a[7],
+                a[8] / 32, a[9] / 32, a[10]);
         cudaFree(times);
     }
     return cudaGetLastError();
+}
+
+// The sample pass covers the first keys of the database (1/16 of it, at most 65,536): its only purpose is to hand the
+// main pass a tight starting threshold per query, which removes the start-up transient of the streaming top-K'
+// (~K' ln(n/K') hits per thread) from 15/16 of the stream.
+int scl_knn_tc_sample(int n_db)
+{
+    int n_s = n_db / 16;
+    if (n_s > 65536) n_s = 65536;
+    n_s &= ~255;
+    return n_s < 4096 ? 0 : n_s;
 }
 
 cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, const float* knorm, const float* kn2max, int n_db, int R, int K,
@@ -576,24 +632,33 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
     const int n_ranges = scl_knn_tc_ranges(Q);
     const int kprime = scl_knn_tc_kprime(K);
     if (K > kprime - 2) return cudaErrorInvalidValue;
-    const int NT = R == 20 ? 256 : 128;
-    int range_len = (n_db + n_ranges - 1) / n_ranges;
-    range_len = (range_len + NT - 1) / NT * NT;
-    if ((size_t)Q * 2 * n_ranges * kprime > ws.capacity) return cudaErrorInvalidValue;   /* two sub-ranges (column halves) per CTA */
+    const int n_sub = 2 * n_ranges;                       /* proposal lists per launch: two column halves per CTA */
+    const int n_s = scl_knn_tc_sample(n_db);
+    const int n_sub_total = n_s > 0 ? 2 * n_sub : n_sub;
+    if ((size_t)Q * n_sub_total * kprime > ws.capacity) return cudaErrorInvalidValue;
     cudaError_t err = cudaMemsetAsync(fail_count, 0, sizeof(int), stream);
     if (err != cudaSuccess) return err;
     err = cudaMemsetAsync(ws.g_thr, 0x7f, (size_t)Q * sizeof(int), stream);   /* 0x7f7f7f7f = 3.4e38: "no threshold yet" */
     if (err != cudaSuccess) return err;
-    if (R == 20) err = launch_tc<20, 256>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, ws.g_thr, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
-    else if (R == 40) err = launch_tc<40, 128>(qkeys, Q, keys, knorm, n_db, range_len, n_ranges, kprime, ws.g_thr, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
-    else return cudaErrorNotSupported;
-    if (err != cudaSuccess) return err;
+    if (R != 20 && R != 40) return cudaErrorNotSupported;
+    for (int pass = (n_s > 0 ? 0 : 1); pass < 2; pass++) {
+        const int lo = pass == 0 ? 0 : n_s, hi = pass == 0 ? n_s : n_db;
+        const int sub_base = (pass == 1 && n_s > 0) ? n_sub : 0;
+        if (R == 20) err = launch_tc<20, 256>(qkeys, Q, keys, knorm, lo, hi, n_ranges, kprime, sub_base, n_sub_total, ws.g_thr, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
+        else err = launch_tc<40, 128>(qkeys, Q, keys, knorm, lo, hi, n_ranges, kprime, sub_base, n_sub_total, ws.g_thr, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
+        if (err != cudaSuccess) return err;
+        if (pass == 0) {
+            knn_sample_thr_kernel<<<(Q + 3) / 4, 128, 0, stream>>>(ws.prop_s, Q, n_sub_total, n_sub, kprime, ws.g_thr);
+            err = cudaGetLastError();
+            if (err != cudaSuccess) return err;
+        }
+    }
     const int warps = 4;
     if (metric == 0)
-        knn_rerank_kernel<0><<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(qkeys, Q, keys, R, K, 2 * n_ranges, kprime, ws.prop_idx, ws.prop_cut,
+        knn_rerank_kernel<0><<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(qkeys, Q, keys, R, K, n_sub_total, kprime, ws.prop_idx, ws.prop_cut,
                                                                                 kn2max, ws.exact, id_mul, id_add, out_ids, out_d2, fail_list, fail_count);
     else
-        knn_rerank_kernel<1><<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(qkeys, Q, keys, R, K, 2 * n_ranges, kprime, ws.prop_idx, ws.prop_cut,
+        knn_rerank_kernel<1><<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(qkeys, Q, keys, R, K, n_sub_total, kprime, ws.prop_idx, ws.prop_cut,
                                                                                 kn2max, ws.exact, id_mul, id_add, out_ids, out_d2, fail_list, fail_count);
     return cudaGetLastError();
 }
