@@ -445,6 +445,74 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     }
 }
 
+// Bootstrap: before any tensor-core work, every query gets a valid starting threshold from a strided sample of
+// kBootKeys keys scored on the CUDA cores. Each lane keeps the 4 smallest scores of its share; if b is the m-th
+// smallest of the lanes' 4th-smallest scores, at least 4m sample keys score <= b, so with 4m >= K' the K'-th
+// smallest score of the whole database is <= b. b (+ the prefilter's error bound, so that the bound also holds for
+// the tensor-core scores) removes most of the start-up transient of the streaming top-K' in the sample pass.
+constexpr int kBootKeys = 4096;
+template <int R>
+__global__ void __launch_bounds__(256) knn_bootstrap_kernel(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys,
+                                                            const float* __restrict__ knorm, const float* __restrict__ kn2max, int n_db,
+                                                            int kprime, int* __restrict__ g_thr)
+{
+    __shared__ float sk[256][R + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * 8 + warp;
+    float q[R];
+#pragma unroll
+    for (int d = 0; d < R; d++) q[d] = qi < Q ? __ldg(qkeys + (size_t)qi * R + d) : 0.0f;
+    const int n_s = n_db < kBootKeys ? n_db : kBootKeys;
+    const long long stride = n_db / n_s;                 /* sample key j is database key j*stride */
+    float b0 = kThrInit, b1 = kThrInit, b2 = kThrInit, b3 = kThrInit;
+    for (int base = 0; base < n_s; base += 256) {
+        __syncthreads();
+        {
+            const int j = base + threadIdx.x;
+            if (j < n_s) {
+                const size_t key = (size_t)j * stride;
+#pragma unroll
+                for (int g = 0; g < R / 4; g++) {
+                    const float4 x = __ldg(reinterpret_cast<const float4*>(keys + key * R) + g);
+                    sk[threadIdx.x][4 * g] = x.x; sk[threadIdx.x][4 * g + 1] = x.y; sk[threadIdx.x][4 * g + 2] = x.z; sk[threadIdx.x][4 * g + 3] = x.w;
+                }
+                sk[threadIdx.x][R] = __ldg(knorm + key);
+            }
+        }
+        __syncthreads();
+        const int nk = min(256, n_s - base);
+        for (int j = lane; j < nk; j += 32) {
+            float dot = 0.0f;
+#pragma unroll
+            for (int d = 0; d < R; d++) dot = fmaf(q[d], sk[j][d], dot);
+            float x = fmaf(-2.0f, dot, sk[j][R]);
+            float y;
+            y = fminf(b0, x); x = fmaxf(b0, x); b0 = y;
+            y = fminf(b1, x); x = fmaxf(b1, x); b1 = y;
+            y = fminf(b2, x); x = fmaxf(b2, x); b2 = y;
+            b3 = fminf(b3, x);
+        }
+    }
+    /* m-th smallest of the 32 lanes' 4th-smallest scores */
+    const int m = (kprime + 3) / 4;
+    float mine = b3, picked = kThrInit;
+    for (int r = 0; r < m; r++) {
+        float w = mine;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) w = fminf(w, __shfl_xor_sync(0xffffffffu, w, off));
+        picked = w;
+        const unsigned who = __ballot_sync(0xffffffffu, mine == w);
+        if (lane == __ffs(who) - 1) mine = kThrInit;       /* remove one instance of the minimum */
+    }
+    if (lane == 0 && qi < Q && picked < kThrInit) {
+        float qn = 0.0f;
+#pragma unroll
+        for (int d = 0; d < R; d++) qn = fmaf(q[d], q[d], qn);
+        const float sn = sqrtf(qn) + sqrtf(__ldg(kn2max));
+        atomicMin(g_thr + qi, ordered_int(picked + 3.0517578125e-05f * sn * sn));   /* + 2^-15 (|q|+|k|max)^2 */
+    }
+}
+
 // Between the sample pass and the main pass: the K'-th smallest score over the sample keys (= over the union of
 // the sample pass' proposal lists) becomes every CTA's starting threshold for that query. One warp per query.
 __global__ void __launch_bounds__(128) knn_sample_thr_kernel(const float* __restrict__ prop_s, int Q, int n_sub_total, int n_sub_sample,
@@ -641,6 +709,12 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
     err = cudaMemsetAsync(ws.g_thr, 0x7f, (size_t)Q * sizeof(int), stream);   /* 0x7f7f7f7f = 3.4e38: "no threshold yet" */
     if (err != cudaSuccess) return err;
     if (R != 20 && R != 40) return cudaErrorNotSupported;
+    if (n_db >= 4 * kBootKeys) {
+        if (R == 20) knn_bootstrap_kernel<20><<<(Q + 7) / 8, 256, 0, stream>>>(qkeys, Q, keys, knorm, kn2max, n_db, kprime, ws.g_thr);
+        else knn_bootstrap_kernel<40><<<(Q + 7) / 8, 256, 0, stream>>>(qkeys, Q, keys, knorm, kn2max, n_db, kprime, ws.g_thr);
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+    }
     for (int pass = (n_s > 0 ? 0 : 1); pass < 2; pass++) {
         const int lo = pass == 0 ? 0 : n_s, hi = pass == 0 ? n_s : n_db;
         const int sub_base = (pass == 1 && n_s > 0) ? n_sub : 0;
