@@ -290,10 +290,12 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             const bool was_slow = wm != 0;
 #pragma unroll 1
             while (wm) {
-                const int j = __ffs(wm) - 1;
+                const int j = __ffs(wm) - 1;                 /* warp-uniform: the switch below does not diverge */
                 wm &= wm - 1;
                 float v[8];
-                tmem_ld8(col_first + 8 * j, v);
+#define SCL_GROUP(J) case J: _Pragma("unroll") for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[8 * J + i]); break;
+                switch (j) { SCL_GROUP(0) SCL_GROUP(1) SCL_GROUP(2) SCL_GROUP(3) SCL_GROUP(4) SCL_GROUP(5) SCL_GROUP(6) default: SCL_GROUP(7) }
+#undef SCL_GROUP
 #pragma unroll
                 for (int i = 0; i < 8; i++)
                     if (v[i] < thr) { sv[cnt * E + t] = v[i]; si[cnt * E + t] = key_first + 8 * j + i; cnt++; }
