@@ -13,10 +13,10 @@
 //   with |k|^2 = n_hi + n_mid + n_lo carried through the same contraction (three more columns).
 //   One CTA per SM: it owns a 128-query tile (M = 128 = TMEM lanes) and one contiguous range of the
 //   key matrix, and is warp-specialised:
-//     warps 5-12 epilogue  : tcgen05.ld 32 columns at a time (thread = query = TMEM lane), compare
+//     warps 4-11 epilogue  : tcgen05.ld 32 columns at a time (thread = query = TMEM lane), compare
 //                            against the thread's running threshold, push hits to a staging buffer,
 //                            fold the staging buffers into per-thread sorted top-K' lists
-//     warps 1-4  producers : stream raw keys (80 B each) from HBM, split hi/lo in registers, write
+//     warps 1-3  producers : stream raw keys (80 B each) from HBM, split hi/lo in registers, write
 //                            the UMMA K-major no-swizzle core-matrix layout into shared memory
 //     warp  0    MMA issuer: one thread issues the 9 tcgen05.mma per key tile and commits to
 //                            mbarriers (smem stage free / accumulator ready)
@@ -41,9 +41,9 @@
 
 namespace {
 
-constexpr int kKPrimeMax = 16;     /* proposals kept per (query, sub-range) */
+constexpr int kKPrime = 16;        /* proposals kept per (query, sub-range): a sorted list in REGISTERS */
 constexpr int kStageCap = 16;      /* staging entries per thread: one 8-column group can add 8 */
-constexpr int kEpiThreads = 256, kProdThreads = 128;   /* two epilogue warps per TMEM lane quadrant, each takes half of the columns */
+constexpr int kEpiThreads = 256, kProdThreads = 96;   /* 8 epilogue warps (two per TMEM lane quadrant, half of the columns each); 384 threads: 168 registers each */
 constexpr int kThreads = 32 + kProdThreads + kEpiThreads;
 constexpr float kPadNorm = 1.0e30f, kThrInit = 1.0e29f;
 
@@ -160,8 +160,7 @@ template <int R, int NT> struct TcCfg {
     static constexpr uint32_t OFF_BAR = 0;                                    /* 8 mbarriers + tmem slot */
     static constexpr uint32_t OFF_A = 128;                                    /* A1, A2 */
     static constexpr uint32_t OFF_B = OFF_A + 2 * A_BLOCK;                    /* 2 stages x (B_hi, B_lo) */
-    static constexpr uint32_t OFF_LIST = OFF_B + 4 * B_BLOCK;                 /* [K'][256] val, [K'][256] idx */
-    static constexpr uint32_t OFF_STG = OFF_LIST + 2 * kKPrimeMax * kEpiThreads * 4;  /* [cap][256] val, idx */
+    static constexpr uint32_t OFF_STG = OFF_B + 4 * B_BLOCK;                  /* staging [cap][256] val, idx */
     static constexpr uint32_t TOTAL = OFF_STG + 2 * kStageCap * kEpiThreads * 4;
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
@@ -186,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
 
     // ---- one-time setup -----------------------------------------------------------------------
     if (threadIdx.x == 0) {
-        scl_mbar_init(&full[0], 4); scl_mbar_init(&full[1], 4);
+        scl_mbar_init(&full[0], kProdThreads / 32); scl_mbar_init(&full[1], kProdThreads / 32);
         scl_mbar_init(&empty[0], 1); scl_mbar_init(&empty[1], 1);
         scl_mbar_init(&tfull[0], 1); scl_mbar_init(&tfull[1], 1);
         scl_mbar_init(&tempty[0], kEpiThreads / 32); scl_mbar_init(&tempty[1], kEpiThreads / 32);
@@ -229,25 +228,28 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     const uint32_t tmem_base = *tmem_slot;
 
     // Role -> warp mapping: the scheduler favours higher warp ids, so the epilogue (the busiest role) gets
-    // warps 5-8, the producers 1-4 and the single MMA-issuing thread warp 0. tcgen05.ld lets warp w touch
+    // the highest warps (4-11), the producers 1-3 and the single MMA-issuing thread warp 0. tcgen05.ld lets warp w touch
     // TMEM lanes 32*(w%4).., so epilogue warp w serves queries 32*(w%4)..32*(w%4)+31 of the tile.
-    if (warp >= 5) {
+    if (warp >= 4) {
         // ===== epilogue: thread = (query = TMEM lane, half of the columns) ================================================
         // A key is kept only if its score is below the thread's threshold. The threshold is the K'-th
         // smallest score seen so far for this query — by this CTA, or (through g_thr) by ANY CTA working
         // on the same query tile: each published value is backed by K' keys at or below it, so it bounds
         // the global K'-th smallest score from above and nothing in the true top-K' is ever dropped.
         constexpr int E = kEpiThreads;
-        const int half = (warp - 5) >> 2;          /* which half of every tile's columns this warp examines */
+        const int half = (warp - 4) >> 2;          /* which half of every tile's columns this warp examines */
         const int row = (warp & 3) * 32 + lane;    /* row of the tile = TMEM lane, 0..127 */
         const int t = half * 128 + row;            /* slot of this thread in the shared-memory lists */
         const int qi = qtile * 128 + row;
         const int sub = sub_base + 2 * range + half;       /* slot of this thread's proposal list among all sub-ranges */
-        float* lv = reinterpret_cast<float*>(smem + C::OFF_LIST);
-        int* li = reinterpret_cast<int*>(lv + kKPrimeMax * E);
         float* sv = reinterpret_cast<float*>(smem + C::OFF_STG);
         int* si = reinterpret_cast<int*>(sv + kStageCap * E);
-        int count = 0, cnt = 0;
+        // The thread's K' best (score, key) so far live in registers, kept sorted by a branch-free bubble-through
+        // insert (the shared-memory insertion sort this replaces cost ~10x more: a chain of dependent LDS/STS).
+        float lv[kKPrime]; int li[kKPrime];
+#pragma unroll
+        for (int i = 0; i < kKPrime; i++) { lv[i] = kThrInit; li[i] = -1; }
+        int cnt = 0;
         int n_slow = 0, n_push = 0, n_fold = 0;      /* developer counters (SCL_TC_TIMES) */
         float thr = kThrInit;
         int* my_gthr = g_thr + (qi < Q ? qi : 0);
@@ -255,17 +257,20 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             n_fold++; n_push += cnt;
             const float before = thr;
             for (int s = 0; s < cnt; s++) {
-                const float val = sv[s * E + t];
+                float val = sv[s * E + t];
+                int id = si[s * E + t];
                 if (!(val < thr)) continue;
-                const int id = si[s * E + t];
-                int i = count < kprime ? count : kprime - 1;
-                for (; i > 0 && lv[(i - 1) * E + t] > val; --i) { lv[i * E + t] = lv[(i - 1) * E + t]; li[i * E + t] = li[(i - 1) * E + t]; }
-                lv[i * E + t] = val; li[i * E + t] = id;
-                if (count < kprime) count++;
-                if (count == kprime) thr = lv[(kprime - 1) * E + t];
+#pragma unroll
+                for (int i = 0; i < kKPrime; i++) {
+                    const bool lt = val < lv[i];
+                    const float tv = lt ? lv[i] : val; const int ti = lt ? li[i] : id;
+                    lv[i] = lt ? val : lv[i]; li[i] = lt ? id : li[i];
+                    val = tv; id = ti;
+                }
+                thr = lv[kKPrime - 1];
             }
             cnt = 0;
-            if (thr < before && count == kprime && qi < Q) atomicMin(my_gthr, ordered_int(thr));
+            if (thr < before && qi < Q) atomicMin(my_gthr, ordered_int(thr));
         };
         // One 64-column TMEM load is always in flight while the previous 64 columns are examined. The common
         // case is "nothing below the threshold": a min-tree (FMNMX3) over the 64 scores and one compare. Only
@@ -337,20 +342,21 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         }
         fold();
         if (qi < Q) {
-            const size_t o = ((size_t)qi * n_sub_total + sub) * kprime;
-            for (int i = 0; i < kprime; i++) {
-                prop_s[o + i] = i < count ? lv[i * E + t] : __int_as_float(0x7f800000);
-                prop_idx[o + i] = i < count ? li[i * E + t] : -1;
+            const size_t o = ((size_t)qi * n_sub_total + sub) * kKPrime;
+#pragma unroll
+            for (int i = 0; i < kKPrime; i++) {
+                prop_s[o + i] = li[i] >= 0 ? lv[i] : __int_as_float(0x7f800000);
+                prop_idx[o + i] = li[i];
             }
-            /* cut-off of this range: every key NOT proposed had S >= the threshold in force when it was
+            /* cut-off of this sub-range: every key NOT proposed had S >= the threshold in force when it was
              * examined >= the final threshold (thresholds only fall); inf if nothing was ever dropped */
             prop_cut[(size_t)qi * n_sub_total + sub] = thr < kThrInit ? thr : __int_as_float(0x7f800000);
         }
     } else if (warp >= 1) {
         // ===== producers: raw keys -> hi/lo split -> UMMA core-matrix layout =======================
         // The raw keys of tile t+1 are already in flight (registers) while tile t is split and stored.
-        const int p = threadIdx.x - 32;            /* 0..127 */
-        constexpr int KPT = NT >= kProdThreads ? NT / kProdThreads : 1;     /* keys per thread per tile */
+        const int p = threadIdx.x - 32;            /* 0..95 */
+        constexpr int KPT = (NT + kProdThreads - 1) / kProdThreads;     /* keys per thread per tile */
         float4 xa[KPT][R / 4];
         float na[KPT];
         auto load_tile = [&](int tile, float4 (&x)[KPT][R / 4], float (&n)[KPT]) {
@@ -644,7 +650,7 @@ int scl_knn_tc_ranges(int Q)
     return r < 1 ? 1 : r;
 }
 
-int scl_knn_tc_kprime(int K) { int kp = K + 6; if (kp < 8) kp = 8; return kp > kKPrimeMax ? kKPrimeMax : kp; }
+int scl_knn_tc_kprime(int K) { (void)K; return kKPrime; }   /* fixed: the list is a register array */
 
 template <int R, int NT>
 static cudaError_t launch_tc(const float* qkeys, int Q, const float* keys, const float* knorm, int key_lo, int key_hi, int n_ranges,
