@@ -253,8 +253,11 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         int n_slow = 0, n_push = 0, n_fold = 0;      /* developer counters (SCL_TC_TIMES) */
         float thr = kThrInit;
         int* my_gthr = g_thr + (qi < Q ? qi : 0);
+        long long t_fold = 0;
         auto fold = [&]() {
             n_fold++; n_push += cnt;
+            long long f0 = 0;
+            if (times) f0 = clock64();
             const float before = thr;
             for (int s = 0; s < cnt; s++) {
                 float val = sv[s * E + t];
@@ -267,10 +270,11 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                     lv[i] = lt ? val : lv[i]; li[i] = lt ? id : li[i];
                     val = tv; id = ti;
                 }
-                thr = lv[kKPrime - 1];
+                thr = fminf(thr, lv[kKPrime - 1]);     /* never loosen a threshold learned from other CTAs */
             }
             cnt = 0;
             if (thr < before && qi < Q) atomicMin(my_gthr, ordered_int(thr));
+            if (times) t_fold += clock64() - f0;
         };
         // One 64-column TMEM load is always in flight while the previous 64 columns are examined. The common
         // case is "nothing below the threshold": a min-tree (FMNMX3) over the 64 scores and one compare. Only
@@ -338,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             const int ws = __reduce_add_sync(0xffffffffu, n_slow), wp = __reduce_add_sync(0xffffffffu, n_push + cnt);
             const unsigned any_slow_chunks = 0;
             (void)any_slow_chunks;
-            if (t == 0) { times[blockIdx.x * 16 + 0] = tw; times[blockIdx.x * 16 + 1] = tp; times[blockIdx.x * 16 + 8] = ws; times[blockIdx.x * 16 + 9] = wp; times[blockIdx.x * 16 + 10] = n_fold; times[blockIdx.x * 16 + 11] = t_ld; times[blockIdx.x * 16 + 12] = t_slow; }
+            if (t == 0) { times[blockIdx.x * 16 + 0] = tw; times[blockIdx.x * 16 + 1] = tp; times[blockIdx.x * 16 + 8] = ws; times[blockIdx.x * 16 + 9] = wp; times[blockIdx.x * 16 + 10] = n_fold; times[blockIdx.x * 16 + 11] = t_ld; times[blockIdx.x * 16 + 12] = t_slow; times[blockIdx.x * 16 + 13] = t_fold; }
         }
         fold();
         if (qi < Q) {
@@ -680,9 +684,9 @@ static cudaError_t launch_tc(const float* qkeys, int Q, const float* keys, const
         cudaMemcpy(h.data(), times, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
         double a[16] = {0};
         for (int b = 0; b < nb; b++) for (int i = 0; i < 16; i++) a[i] += (double)h[(size_t)b * 16 + i] / nb;
-        fprintf(stderr, "[tc keys %d..%d] tiles/CTA %.0f | cycles per tile: epilogue wait %.0f work %.0f (tmem %.0f, slow path %.0f) | producer wait %.0f work %.0f | "
+        fprintf(stderr, "[tc keys %d..%d] tiles/CTA %.0f | cycles per tile: epilogue wait %.0f work %.0f (tmem %.0f, slow path %.0f of which folds %.0f) | producer wait %.0f work %.0f | "
                         "mma wait_tmem %.0f wait_operands %.0f issue %.0f | per warp: slow chunks %.0f, pushes/lane %.1f, folds %.0f\n",
-                key_lo, key_hi, a[7], a[0] / a[7], a[1] / a[7], a[11] / a[7], a[12] / a[7], a[2] / a[7], a[3] / a[7], a[4] / a[7], a[5] / a[7], a[6] / a[7],
+                key_lo, key_hi, a[7], a[0] / a[7], a[1] / a[7], a[11] / a[7], a[12] / a[7], a[13] / a[7], a[2] / a[7], a[3] / a[7], a[4] / a[7], a[5] / a[7], a[6] / a[7],
                 a[8] / 32, a[9] / 32, a[10]);
         cudaFree(times);
     }
