@@ -578,8 +578,8 @@ __device__ __forceinline__ float exact_d2(const float* __restrict__ q, const flo
 // Phase B: exact re-rank + certificate. One warp per query; n_cand = n_ranges * K' proposals.
 template <int METRIC>
 __global__ void __launch_bounds__(128) knn_rerank_kernel(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys, int R, int K,
-                                                         int n_ranges, int kprime, const int32_t* __restrict__ prop_idx,
-                                                         const float* __restrict__ prop_cut, const float* __restrict__ kn2max,
+                                                         int n_ranges, int kprime, const float* __restrict__ prop_s,
+                                                         const int32_t* __restrict__ prop_idx, const float* __restrict__ prop_cut, const float* __restrict__ kn2max,
                                                          float* __restrict__ exact /* [Q][n_cand] scratch */, int id_mul, int id_add,
                                                          int32_t* __restrict__ out_ids, float* __restrict__ out_d2,
                                                          int32_t* __restrict__ fail_list, int* __restrict__ fail_count)
@@ -592,20 +592,24 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(const float* __restrict
     const int32_t* pidx = prop_idx + (size_t)qi * n_cand;
     float* ex = exact + (size_t)qi * n_cand;
     const float inf = __int_as_float(0x7f800000);
+    float cut = inf;
+    for (int r = lane; r < n_ranges; r += 32) cut = fminf(cut, prop_cut[(size_t)qi * n_ranges + r]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) cut = fminf(cut, __shfl_xor_sync(0xffffffffu, cut, off));
+    const float* ps = prop_s + (size_t)qi * n_cand;
     for (int c = lane; c < n_cand; c += 32) {
         const int id = pidx[c];
         float d = inf;
-        if (id >= 0) {
+        /* A proposal scoring above the cut cannot be in a CERTIFIED top-K (its exact d2 exceeds cut + |q|^2 - eps,
+         * which the certificate requires to exceed the K-th distance); if the certificate fails the query is redone
+         * exactly anyway. Skipping them leaves a few dozen exact evaluations per query instead of >1000. */
+        if (id >= 0 && !(ps[c] > cut)) {
             d = exact_d2<METRIC>(q, keys + (size_t)id * R, R);
             if (METRIC == 1 && !(d > FLT_EPSILON)) d = inf;          /* libnabo self-match rule */
             if (!(d < (METRIC == 0 ? FLT_MAX : inf))) d = inf;       /* never accepted by the trees */
         }
         ex[c] = d;
     }
-    float cut = inf;
-    for (int r = lane; r < n_ranges; r += 32) cut = fminf(cut, prop_cut[(size_t)qi * n_ranges + r]);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) cut = fminf(cut, __shfl_xor_sync(0xffffffffu, cut, off));
     __syncwarp();
     /* K rounds: smallest (d2, id) strictly after the previous pick */
     float pd = -1.0f; int pi = -1; float dK = 0.0f; int found = 0;
@@ -741,10 +745,10 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
     }
     const int warps = 4;
     if (metric == 0)
-        knn_rerank_kernel<0><<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(qkeys, Q, keys, R, K, n_sub_total, kprime, ws.prop_idx, ws.prop_cut,
+        knn_rerank_kernel<0><<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(qkeys, Q, keys, R, K, n_sub_total, kprime, ws.prop_s, ws.prop_idx, ws.prop_cut,
                                                                                 kn2max, ws.exact, id_mul, id_add, out_ids, out_d2, fail_list, fail_count);
     else
-        knn_rerank_kernel<1><<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(qkeys, Q, keys, R, K, n_sub_total, kprime, ws.prop_idx, ws.prop_cut,
+        knn_rerank_kernel<1><<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(qkeys, Q, keys, R, K, n_sub_total, kprime, ws.prop_s, ws.prop_idx, ws.prop_cut,
                                                                                 kn2max, ws.exact, id_mul, id_add, out_ids, out_d2, fail_list, fail_count);
     return cudaGetLastError();
 }
