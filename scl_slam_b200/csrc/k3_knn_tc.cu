@@ -530,29 +530,40 @@ __global__ void __launch_bounds__(256) knn_bootstrap_kernel(const float* __restr
 __global__ void __launch_bounds__(128) knn_sample_thr_kernel(const float* __restrict__ prop_s, int Q, int n_sub_total, int n_sub_sample,
                                                              int kprime, int* __restrict__ g_thr)
 {
+    /* every proposal list is sorted ascending: a K'-step k-way merge, each lane holding the heads of its lists */
     const int lane = threadIdx.x & 31;
     const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (qi >= Q) return;
     const float* ps = prop_s + (size_t)qi * n_sub_total * kprime;
-    const int n = n_sub_sample * kprime;
     const float inf = __int_as_float(0x7f800000);
-    float pv = -inf; int pc = -1;                       /* previous pick (value, slot): picks are strictly increasing in (value, slot) */
+    constexpr int kHeads = 10;                          /* up to 320 lists (148 ranges x 2 halves) */
+    int head[kHeads];
+    float hv[kHeads];
+#pragma unroll
+    for (int h = 0; h < kHeads; h++) {
+        const int l = lane + 32 * h;
+        head[h] = 0;
+        hv[h] = l < n_sub_sample ? ps[(size_t)l * kprime] : inf;
+    }
     float kth = inf;
     for (int r = 0; r < kprime; r++) {
-        float bv = inf; int bc = 0x7fffffff;
-        for (int c = lane; c < n; c += 32) {
-            const float v = ps[c];
-            if (!(v < inf)) continue;
-            if (v < pv || (v == pv && c <= pc)) continue;
-            if (v < bv || (v == bv && c < bc)) { bv = v; bc = c; }
-        }
+        float bv = inf; int bh = -1;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, off); const int oc = __shfl_xor_sync(0xffffffffu, bc, off);
-            if (ov < bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
+        for (int h = 0; h < kHeads; h++) if (hv[h] < bv) { bv = hv[h]; bh = h; }
+        float wv = bv;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) wv = fminf(wv, __shfl_xor_sync(0xffffffffu, wv, off));
+        if (!(wv < inf)) { kth = inf; break; }          /* fewer than K' sample keys: no threshold */
+        kth = wv;
+        const unsigned who = __ballot_sync(0xffffffffu, bh >= 0 && bv == wv);
+        if (lane == __ffs(who) - 1) {
+#pragma unroll
+            for (int h = 0; h < kHeads; h++)
+                if (h == bh) {
+                    head[h]++;
+                    hv[h] = head[h] < kprime ? ps[(size_t)(lane + 32 * h) * kprime + head[h]] : inf;
+                }
         }
-        if (bc == 0x7fffffff) { kth = inf; break; }     /* fewer than K' sample keys: no threshold */
-        pv = bv; pc = bc; kth = bv;
     }
     if (lane == 0 && kth < inf) atomicMin(g_thr + qi, ordered_int(kth));
 }
@@ -575,50 +586,61 @@ __device__ __forceinline__ float exact_d2(const float* __restrict__ q, const flo
     return result;
 }
 
-// Phase B: exact re-rank + certificate. One warp per query; n_cand = n_ranges * K' proposals.
+// Phase B: exact re-rank + certificate. One warp per query; n_cand = n_ranges * K' proposals, of which only those
+// scoring at or below the cut (a few dozen) can matter — see below — and are compacted into shared memory.
+constexpr int kMaxSurvivors = 256;
 template <int METRIC>
 __global__ void __launch_bounds__(128) knn_rerank_kernel(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys, int R, int K,
                                                          int n_ranges, int kprime, const float* __restrict__ prop_s,
-                                                         const int32_t* __restrict__ prop_idx, const float* __restrict__ prop_cut, const float* __restrict__ kn2max,
-                                                         float* __restrict__ exact /* [Q][n_cand] scratch */, int id_mul, int id_add,
+                                                         const int32_t* __restrict__ prop_idx, const float* __restrict__ prop_cut,
+                                                         const float* __restrict__ kn2max, int id_mul, int id_add,
                                                          int32_t* __restrict__ out_ids, float* __restrict__ out_d2,
                                                          int32_t* __restrict__ fail_list, int* __restrict__ fail_count)
 {
-    const int lane = threadIdx.x & 31;
-    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    __shared__ int s_id[4][kMaxSurvivors];
+    __shared__ float s_d[4][kMaxSurvivors];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int qi = blockIdx.x * (blockDim.x >> 5) + w;
     if (qi >= Q) return;
     const int n_cand = n_ranges * kprime;
     const float* q = qkeys + (size_t)qi * R;
     const int32_t* pidx = prop_idx + (size_t)qi * n_cand;
-    float* ex = exact + (size_t)qi * n_cand;
+    const float* ps = prop_s + (size_t)qi * n_cand;
     const float inf = __int_as_float(0x7f800000);
     float cut = inf;
     for (int r = lane; r < n_ranges; r += 32) cut = fminf(cut, prop_cut[(size_t)qi * n_ranges + r]);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) cut = fminf(cut, __shfl_xor_sync(0xffffffffu, cut, off));
-    const float* ps = prop_s + (size_t)qi * n_cand;
-    for (int c = lane; c < n_cand; c += 32) {
-        const int id = pidx[c];
-        float d = inf;
-        /* A proposal scoring above the cut cannot be in a CERTIFIED top-K (its exact d2 exceeds cut + |q|^2 - eps,
-         * which the certificate requires to exceed the K-th distance); if the certificate fails the query is redone
-         * exactly anyway. Skipping them leaves a few dozen exact evaluations per query instead of >1000. */
-        if (id >= 0 && !(ps[c] > cut)) {
-            d = exact_d2<METRIC>(q, keys + (size_t)id * R, R);
-            if (METRIC == 1 && !(d > FLT_EPSILON)) d = inf;          /* libnabo self-match rule */
-            if (!(d < (METRIC == 0 ? FLT_MAX : inf))) d = inf;       /* never accepted by the trees */
-        }
-        ex[c] = d;
+    /* A proposal scoring above the cut cannot be in a CERTIFIED top-K (its exact d2 exceeds cut + |q|^2 - eps, which
+     * the certificate requires to exceed the K-th distance); if the certificate fails the query is redone exactly
+     * anyway. So only the survivors are evaluated exactly. */
+    int n_surv = 0; bool overflow = false;
+    for (int c0 = 0; c0 < n_cand; c0 += 32) {
+        const int c = c0 + lane;
+        const int id = c < n_cand ? pidx[c] : -1;
+        const bool keep = id >= 0 && !(ps[c] > cut);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        const int pos = n_surv + __popc(m & ((1u << lane) - 1u));
+        if (keep && pos < kMaxSurvivors) s_id[w][pos] = id;
+        n_surv += __popc(m);
+    }
+    if (n_surv > kMaxSurvivors) { overflow = true; n_surv = kMaxSurvivors; }
+    __syncwarp();
+    for (int c = lane; c < n_surv; c += 32) {
+        float d = exact_d2<METRIC>(q, keys + (size_t)s_id[w][c] * R, R);
+        if (METRIC == 1 && !(d > FLT_EPSILON)) d = inf;          /* libnabo self-match rule */
+        if (!(d < (METRIC == 0 ? FLT_MAX : inf))) d = inf;       /* never accepted by the trees */
+        s_d[w][c] = d;
     }
     __syncwarp();
     /* K rounds: smallest (d2, id) strictly after the previous pick */
     float pd = -1.0f; int pi = -1; float dK = 0.0f; int found = 0;
     for (int r = 0; r < K; r++) {
         float bd = inf; int bi = 0x7fffffff;
-        for (int c = lane; c < n_cand; c += 32) {
-            const float d = ex[c];
+        for (int c = lane; c < n_surv; c += 32) {
+            const float d = s_d[w][c];
             if (!(d < inf)) continue;
-            const int id = pidx[c] * id_mul + id_add;
+            const int id = s_id[w][c] * id_mul + id_add;
             if (d < pd || (d == pd && id <= pi)) continue;
             if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; }
         }
@@ -634,14 +656,14 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(const float* __restrict
     }
     if (lane == 0) {
         for (int r = found; r < K; r++) { out_ids[(size_t)qi * K + r] = -1; out_d2[(size_t)qi * K + r] = FLT_MAX; }
-        bool certified = true;
+        bool certified = !overflow;
         if (cut < inf) {
             /* dropped keys have S >= cut, i.e. exact d2 > cut + |q|^2 - eps */
             float qn = 0.0f;
             for (int d = 0; d < R; d++) qn = fmaf(q[d], q[d], qn);
-            const float s = sqrtf(qn) + sqrtf(__ldg(kn2max));
-            const float eps = 1.52587890625e-05f * s * s + 2.0e-6f * dK;       /* 2^-16 (|q|+|k|max)^2 + exact-side rounding */
-            certified = (found == K) && (dK + eps < cut + qn);
+            const float sn = sqrtf(qn) + sqrtf(__ldg(kn2max));
+            const float eps = 1.52587890625e-05f * sn * sn + 2.0e-6f * dK;       /* 2^-16 (|q|+|k|max)^2 + exact-side rounding */
+            certified = certified && (found == K) && (dK + eps < cut + qn);
         }
         if (!certified) fail_list[atomicAdd(fail_count, 1)] = qi;
     }
@@ -746,9 +768,9 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
     const int warps = 4;
     if (metric == 0)
         knn_rerank_kernel<0><<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(qkeys, Q, keys, R, K, n_sub_total, kprime, ws.prop_s, ws.prop_idx, ws.prop_cut,
-                                                                                kn2max, ws.exact, id_mul, id_add, out_ids, out_d2, fail_list, fail_count);
+                                                                                kn2max, id_mul, id_add, out_ids, out_d2, fail_list, fail_count);
     else
         knn_rerank_kernel<1><<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(qkeys, Q, keys, R, K, n_sub_total, kprime, ws.prop_s, ws.prop_idx, ws.prop_cut,
-                                                                                kn2max, ws.exact, id_mul, id_add, out_ids, out_d2, fail_list, fail_count);
+                                                                                kn2max, id_mul, id_add, out_ids, out_d2, fail_list, fail_count);
     return cudaGetLastError();
 }

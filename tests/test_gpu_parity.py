@@ -340,7 +340,7 @@ def test_sharded_equals_unsharded(eng_mod, world):
 
 # ---------------------------------------------------------------- K3 on tensor cores (tcgen05 prefilter + exact re-rank)
 @pytest.mark.parametrize("R,S,K,n,nq,metric", [(20, 60, 10, 60000, 300, 0), (20, 60, 3, 33000, 129, 1), (40, 120, 10, 40000, 140, 0),
-                                               (20, 60, 16, 50000, 64, 0)])
+                                               (20, 60, 14, 50000, 64, 0)])
 def test_tensor_core_knn_equals_oracle(eng_mod, R, S, K, n, nq, metric):
     """Forced tensor-core mode: candidates, distances, shifts and winners still bit-identical to the
     CPU oracle, with no query needing the exact fallback on well-separated data."""
