@@ -611,9 +611,34 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(const float* __restrict
     for (int r = lane; r < n_ranges; r += 32) cut = fminf(cut, prop_cut[(size_t)qi * n_ranges + r]);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) cut = fminf(cut, __shfl_xor_sync(0xffffffffu, cut, off));
-    /* A proposal scoring above the cut cannot be in a CERTIFIED top-K (its exact d2 exceeds cut + |q|^2 - eps, which
-     * the certificate requires to exceed the K-th distance); if the certificate fails the query is redone exactly
-     * anyway. So only the survivors are evaluated exactly. */
+    /* T = the K'-th smallest score among ALL proposals (a K'-step k-way merge over the sorted lists). Everything that
+     * is not evaluated exactly below — keys the prefilter dropped (score >= cut) and proposals scoring above T — has
+     * score >= min(cut, T), hence exact d2 > min(cut, T) + |q|^2 - eps; the certificate demands that this exceeds
+     * the K-th selected distance. If it fails, the query is redone exactly. So only ~K' survivors are evaluated. */
+    {
+        constexpr int kHeads = 10;                      /* up to 320 lists */
+        int head[kHeads]; float hv[kHeads];
+#pragma unroll
+        for (int h = 0; h < kHeads; h++) { const int l = lane + 32 * h; head[h] = 0; hv[h] = l < n_ranges ? ps[(size_t)l * kprime] : inf; }
+        float T = inf;
+        for (int r = 0; r < kprime; r++) {
+            float bv = inf; int bh = -1;
+#pragma unroll
+            for (int h = 0; h < kHeads; h++) if (hv[h] < bv) { bv = hv[h]; bh = h; }
+            float wv = bv;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) wv = fminf(wv, __shfl_xor_sync(0xffffffffu, wv, off));
+            if (!(wv < inf)) { T = inf; break; }        /* fewer than K' proposals in all: keep them all */
+            T = wv;
+            const unsigned who = __ballot_sync(0xffffffffu, bh >= 0 && bv == wv);
+            if (lane == __ffs(who) - 1) {
+#pragma unroll
+                for (int h = 0; h < kHeads; h++)
+                    if (h == bh) { head[h]++; hv[h] = head[h] < kprime ? ps[(size_t)(lane + 32 * h) * kprime + head[h]] : inf; }
+            }
+        }
+        cut = fminf(cut, T);
+    }
     int n_surv = 0; bool overflow = false;
     for (int c0 = 0; c0 < n_cand; c0 += 32) {
         const int c = c0 + lane;
