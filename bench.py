@@ -253,11 +253,21 @@ def run_ours(args):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("k3_knn_dram_bytes_per_launch")
-    roof = {"kernel": "k3_knn stage (knn_bootstrap + 2x knn_tc_kernel tcgen05 + knn_sample_thr + knn_rerank + fallback)", "bound": "hbm", "achieved": alg_bytes / (k3_avg * 1e-3) / 1e9 if k3_avg > 0 else None,
-            "peak": pk["hbm"], "unit": "GB/s", "peak_source": pk["src"], "traffic": traffic,
-            "avg_launch_ms": k3_avg, "launches_timed": k3_n,
-            "tensor_equiv_tflops": alg_flops / (k3_avg * 1e-3) / 1e12 if k3_avg > 0 else None, "tensor_peak_tflops": pk["tc_sustained"]}
-    roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
+    # t_min = max(B_alg / HBM, F_alg / tensor); the binding roof names "bound".
+    t_hbm = alg_bytes / (pk["hbm"] * 1e9)
+    t_tc = alg_flops / (pk["tc_sustained"] * 1e12)
+    t_meas = k3_avg * 1e-3
+    if t_tc >= t_hbm:
+        roof = {"bound": "tensor", "achieved": alg_flops / t_meas / 1e12 if t_meas > 0 else None, "peak": pk["tc_sustained"], "unit": "TFLOP/s"}
+    else:
+        roof = {"bound": "hbm", "achieved": alg_bytes / t_meas / 1e9 if t_meas > 0 else None, "peak": pk["hbm"], "unit": "GB/s"}
+    roof.update({"kernel": "k3_knn stage (knn_bootstrap + 2x knn_tc_kernel tcgen05 + knn_sample_thr + knn_rerank + fallback)",
+                 "frac": roof["achieved"] / roof["peak"] if roof["achieved"] else None, "traffic": traffic, "peak_source": pk["src"],
+                 "avg_launch_ms": k3_avg, "launches_timed": k3_n,
+                 "algorithmic": {"bytes": alg_bytes, "flops": alg_flops, "t_hbm_us": t_hbm * 1e6, "t_tensor_us": t_tc * 1e6},
+                 "hbm_view": {"achieved_gbs": alg_bytes / t_meas / 1e9 if t_meas > 0 else None, "peak_gbs": pk["hbm"]},
+                 "note": "flops are the algorithmic 2*R*Q*N against the measured bf16 peak; the kernel spends 3 tf32 products on 24 padded "
+                         "columns (3.6x the algorithmic flops at half the bf16 rate) to keep FP32-level accuracy"})
     line = {
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+f64",
