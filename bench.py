@@ -165,6 +165,16 @@ def run_ours(args):
                     best_shift=torch.empty(Q, dtype=torch.int32, device=dev))
     local, merged = buf(), buf()
     if world > 1:
+        # one packed record block per rank -> ONE all-gather per step: [dist f64 | ids i32 | d2 f32 | shift i32] x Q*K
+        QK = Q * K
+        blob = torch.empty(QK * 20, dtype=torch.uint8, device=dev)
+        local["cand_dist"] = blob[:QK * 8].view(torch.float64).view(Q, K)
+        local["cand_ids"] = blob[QK * 8:QK * 12].view(torch.int32).view(Q, K)
+        local["cand_d2"] = blob[QK * 12:QK * 16].view(torch.float32).view(Q, K)
+        local["cand_shift"] = blob[QK * 16:QK * 20].view(torch.int32).view(Q, K)
+        gathered = torch.empty((world, QK * 20), dtype=torch.uint8, device=dev)
+        # the merge kernel reads rank-major [world][Q][K] arrays: views with the blob stride are not contiguous,
+        # so the four sections are re-packed by one small copy each (device-side, 4 x world*Q*K elements)
         gath = dict(ids=torch.empty((world, Q, K), dtype=torch.int32, device=dev), d2=torch.empty((world, Q, K), dtype=torch.float32, device=dev),
                     dist=torch.empty((world, Q, K), dtype=torch.float64, device=dev), shift=torch.empty((world, Q, K), dtype=torch.int32, device=dev))
     # ring_key, knn_bootstrap, knn_tc (sample), knn_sample_thr, knn_tc (main), knn_rerank, knn_exact (fallback list),
@@ -174,10 +184,11 @@ def run_ours(args):
     def step():
         e.query_batch_dev(q_dev, None, Q, K, n_local, 0, local)
         if world > 1:
-            dist.all_gather_into_tensor(gath["ids"], local["cand_ids"])
-            dist.all_gather_into_tensor(gath["d2"], local["cand_d2"])
-            dist.all_gather_into_tensor(gath["dist"], local["cand_dist"])
-            dist.all_gather_into_tensor(gath["shift"], local["cand_shift"])
+            dist.all_gather_into_tensor(gathered, blob)
+            gath["dist"].copy_(gathered[:, :QK * 8].view(torch.float64).view(world, Q, K))
+            gath["ids"].copy_(gathered[:, QK * 8:QK * 12].view(torch.int32).view(world, Q, K))
+            gath["d2"].copy_(gathered[:, QK * 12:QK * 16].view(torch.float32).view(world, Q, K))
+            gath["shift"].copy_(gathered[:, QK * 16:QK * 20].view(torch.int32).view(world, Q, K))
             e.merge_shards_dev(world, Q, K, None, gath["ids"], gath["d2"], gath["dist"], gath["shift"], merged)
 
     def barrier():
