@@ -55,19 +55,37 @@ __host__ __device__ inline ScLayout sc_layout(int R, int S, int K, int warps)
 
 // sequential column statistics of a row-major R x S float tile: mean (sector key, :1477-1489)
 // and Euclidean norm (col.norm(), :1523) in double
-__device__ __forceinline__ void column_stats(const float* __restrict__ d, int R, int S, int j, double& mean, double& norm)
+// Columns j0, j0+stride, ... (up to kJC of them) are reduced side by side: each column's sums keep the reference's
+// sequential order (bit-exact), while the independent chains hide the FP64 add latency.
+constexpr int kJC = 4;
+__device__ __forceinline__ void column_stats_batch(const float* __restrict__ d, int R, int S, int j0, int stride,
+                                                   double* __restrict__ mean, double* __restrict__ norm)
 {
-    double s = 0.0, ss = 0.0;
-    for (int r = 0; r < R; r++) {
-        const double v = (double)d[r * S + j];
-        s = __dadd_rn(s, v);
-        ss = __dadd_rn(ss, __dmul_rn(v, v));
+    for (int jb = j0; jb < S; jb += kJC * stride) {
+        double s[kJC], ss[kJC];
+#pragma unroll
+        for (int c = 0; c < kJC; c++) { s[c] = 0.0; ss[c] = 0.0; }
+        for (int r = 0; r < R; r++) {
+#pragma unroll
+            for (int c = 0; c < kJC; c++) {
+                const int j = jb + c * stride;
+                if (j < S) {
+                    const double v = (double)d[r * S + j];
+                    s[c] = __dadd_rn(s[c], v);
+                    ss[c] = __dadd_rn(ss[c], __dmul_rn(v, v));
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < kJC; c++) {
+            const int j = jb + c * stride;
+            if (j < S) { mean[j] = __ddiv_rn(s[c], (double)R); norm[j] = __dsqrt_rn(ss[c]); }
+        }
     }
-    mean = __ddiv_rn(s, (double)R);
-    norm = __dsqrt_rn(ss);
 }
 
-__global__ void __launch_bounds__(512) scdist_kernel(
+template <int kMaxThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) scdist_kernel(
     const float* __restrict__ db_desc, const float* __restrict__ q_desc, const int32_t* __restrict__ q_local,
     const int32_t* __restrict__ q_ids, const int32_t* __restrict__ cand_local, const int32_t* __restrict__ cand_ids,
     int K, int R, int S, int search_radius, int use_bulk,
@@ -112,7 +130,7 @@ __global__ void __launch_bounds__(512) scdist_kernel(
     }
     if (use_bulk) scl_mbar_wait(&bars[0], 0);
     else __syncthreads();
-    for (int j = threadIdx.x; j < S; j += blockDim.x) column_stats(qd, R, S, j, vq[j], nq[j]);
+    column_stats_batch(qd, R, S, threadIdx.x, blockDim.x, vq, nq);
     __syncthreads();
 
     uint32_t parity = 0;
@@ -123,21 +141,31 @@ __global__ void __launch_bounds__(512) scdist_kernel(
             if (use_bulk) { scl_mbar_wait(&bars[1 + warp], parity); parity ^= 1u; }
             else { for (int i = lane; i < RS; i += 32) cd[i] = __ldg(db_desc + (size_t)c_local * RS + i); __syncwarp(); }
             /* a. candidate sector key and column norms */
-            for (int j = lane; j < S; j += 32) column_stats(cd, R, S, j, vc[j], nc[j]);
+            column_stats_batch(cd, R, S, lane, 32, vc, nc);
             __syncwarp();
             /* b. fastAlignUsingVkey: lane <-> shift, sequential over columns (:1496-1508) */
             double bestn = 10000000.0; int bests = 0x7fffffff;
-            for (int s = lane; s < S; s += 32) {
-                double ss = 0.0;
-                int idx = S - s;                       /* (0 - s + S) % S, walks forward with j */
-                if (idx == S) idx = 0;
+            for (int sb = lane; sb < S; sb += kJC * 32) {       /* kJC shifts of this lane side by side */
+                double ss[kJC]; int idx[kJC];
+#pragma unroll
+                for (int c = 0; c < kJC; c++) { ss[c] = 0.0; const int sh = sb + 32 * c; idx[c] = sh < S ? (sh == 0 ? 0 : S - sh) : 0; }
                 for (int j = 0; j < S; j++) {
-                    const double d = __dsub_rn(vq[j], vc[idx]);
-                    ss = __dadd_rn(ss, __dmul_rn(d, d));
-                    if (++idx == S) idx = 0;
+                    const double a = vq[j];
+#pragma unroll
+                    for (int c = 0; c < kJC; c++) {
+                        const double d = __dsub_rn(a, vc[idx[c]]);
+                        ss[c] = __dadd_rn(ss[c], __dmul_rn(d, d));
+                        if (++idx[c] == S) idx[c] = 0;
+                    }
                 }
-                const double nrm = __dsqrt_rn(ss);
-                if (nrm < bestn) { bestn = nrm; bests = s; }   /* ascending s per lane: first minimum wins */
+#pragma unroll
+                for (int c = 0; c < kJC; c++) {
+                    const int sh = sb + 32 * c;
+                    if (sh < S) {
+                        const double nrm = __dsqrt_rn(ss[c]);
+                        if (nrm < bestn) { bestn = nrm; bests = sh; }   /* ascending shift per lane: first minimum wins */
+                    }
+                }
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
@@ -156,22 +184,28 @@ __global__ void __launch_bounds__(512) scdist_kernel(
                     if (cdist <= search_radius) shifts[ns++] = s_next;
                 }
                 if (ns == 0) break;
+                for (int j = lane; j < S; j += 32) {                   /* the chunk's shifts of column j side by side */
+                    const double na = nq[j];
+                    int cb[kShiftChunk]; double dot[kShiftChunk];
 #pragma unroll
-                for (int w = 0; w < kShiftChunk; w++) {
-                    if (w < ns) {
-                        const int s = shifts[w];
-                        for (int j = lane; j < S; j += 32) {
-                            int cb = j - s; if (cb < 0) cb += S;      /* circshift: shifted.col(j) = sc2.col(j - s) */
-                            const double na = nq[j], nb = nc[cb];
-                            double v = 0.0;
-                            if (!((na == 0.0) | (nb == 0.0))) {
-                                double dot = 0.0;
-                                for (int r = 0; r < R; r++) dot = __dadd_rn(dot, __dmul_rn((double)qd[r * S + j], (double)cd[r * S + cb]));
-                                v = __ddiv_rn(dot, __dmul_rn(na, nb));
-                            }
-                            sim[w * S + j] = v;
+                    for (int w = 0; w < kShiftChunk; w++) {
+                        int c = j - (w < ns ? shifts[w] : 0); if (c < 0) c += S;   /* circshift: shifted.col(j) = sc2.col(j - s) */
+                        cb[w] = c; dot[w] = 0.0;
+                    }
+                    if (na != 0.0) {
+                        for (int r = 0; r < R; r++) {
+                            const double a = (double)qd[r * S + j];
+#pragma unroll
+                            for (int w = 0; w < kShiftChunk; w++)
+                                if (w < ns) dot[w] = __dadd_rn(dot[w], __dmul_rn(a, (double)cd[r * S + cb[w]]));
                         }
                     }
+#pragma unroll
+                    for (int w = 0; w < kShiftChunk; w++)
+                        if (w < ns) {
+                            const double nb = nc[cb[w]];
+                            sim[w * S + j] = ((na == 0.0) | (nb == 0.0)) ? 0.0 : __ddiv_rn(dot[w], __dmul_rn(na, nb));
+                        }
                 }
                 __syncwarp();
                 double dist = 0.0;
@@ -280,16 +314,23 @@ cudaError_t scl_launch_scdist(const float* db_desc, const float* q_desc, const i
     while (warps > 1 && sc_layout(R, S, K, warps).total > budget) warps--;
     const ScLayout L = sc_layout(R, S, K, warps);
     if (L.total > 227 * 1024) return cudaErrorNotSupported;
-    static size_t attr_set = 0;
-    if (L.total > attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(scdist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-        if (e != cudaSuccess) return e;
-        attr_set = 227 * 1024;
-    }
     const int use_bulk = ((R * S) % 4 == 0) && ((reinterpret_cast<uintptr_t>(db_desc) & 15) == 0) &&
                          (q_desc == nullptr || (reinterpret_cast<uintptr_t>(q_desc) & 15) == 0);
-    scdist_kernel<<<Q, warps * 32, L.total, stream>>>(db_desc, q_desc, q_local, q_ids, cand_local, cand_ids, K, R, S, search_radius,
-                                                      use_bulk, cand_dist, cand_shift, best_id, best_dist, best_shift);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e1 = cudaFuncSetAttribute(scdist_kernel<320, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(113 * 1024));
+        cudaError_t e2 = cudaFuncSetAttribute(scdist_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+        if (e1 != cudaSuccess) return e1;
+        if (e2 != cudaSuccess) return e2;
+        attr_done = true;
+    }
+    /* up to 10 warps and <= 113 KB: two CTAs per SM (20 warps hide the FP64 latencies); otherwise one big CTA */
+    if (warps <= 10 && L.total <= 113 * 1024)
+        scdist_kernel<320, 2><<<Q, warps * 32, L.total, stream>>>(db_desc, q_desc, q_local, q_ids, cand_local, cand_ids, K, R, S, search_radius,
+                                                                use_bulk, cand_dist, cand_shift, best_id, best_dist, best_shift);
+    else
+        scdist_kernel<512, 1><<<Q, warps * 32, L.total, stream>>>(db_desc, q_desc, q_local, q_ids, cand_local, cand_ids, K, R, S, search_radius,
+                                                                use_bulk, cand_dist, cand_shift, best_id, best_dist, best_shift);
     return cudaGetLastError();
 }
 
