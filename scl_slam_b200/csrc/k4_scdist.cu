@@ -32,7 +32,7 @@ constexpr int kShiftChunk = 8;
 
 struct ScLayout {
     int RS, S, warps;
-    size_t off_q, off_c, off_vq, off_nq, off_warp, warp_stride, off_res, total;
+    size_t off_q, off_c, off_qdd, off_vq, off_nq, off_warp, warp_stride, off_res, total;
 };
 
 __host__ __device__ inline ScLayout sc_layout(int R, int S, int K, int warps)
@@ -43,6 +43,7 @@ __host__ __device__ inline ScLayout sc_layout(int R, int S, int K, int warps)
     L.off_q = o; o += (size_t)L.RS * 4;
     L.off_c = o; o += (size_t)warps * L.RS * 4;
     o = (o + 15) / 16 * 16;
+    L.off_qdd = o; o += (size_t)L.RS * 8;                       /* the query tile widened to double once per CTA */
     L.off_vq = o; o += (size_t)S * 8;
     L.off_nq = o; o += (size_t)S * 8;
     L.off_warp = o;
@@ -84,17 +85,20 @@ __device__ __forceinline__ void column_stats_batch(const float* __restrict__ d, 
     }
 }
 
-template <int kMaxThreads, int kMinBlocks>
+// RT/ST: compile-time rings/sectors (20x60, 40x120) so the row loops unroll and the index arithmetic folds; 0 = run time.
+template <int kMaxThreads, int kMinBlocks, int RT, int ST>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) scdist_kernel(
     const float* __restrict__ db_desc, const float* __restrict__ q_desc, const int32_t* __restrict__ q_local,
     const int32_t* __restrict__ q_ids, const int32_t* __restrict__ cand_local, const int32_t* __restrict__ cand_ids,
-    int K, int R, int S, int search_radius, int use_bulk,
+    int K, int R_arg, int S_arg, int search_radius, int use_bulk,
     double* __restrict__ cand_dist, int32_t* __restrict__ cand_shift,
     int32_t* __restrict__ best_id, double* __restrict__ best_dist, int32_t* __restrict__ best_shift)
 {
     extern __shared__ __align__(128) unsigned char smem[];
+    const int R = RT ? RT : R_arg, S = ST ? ST : S_arg;
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const ScLayout L = sc_layout(R, S, K, warps);
+    double* qdd = reinterpret_cast<double*>(smem + L.off_qdd);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     float* qd = reinterpret_cast<float*>(smem + L.off_q);
     float* cd = reinterpret_cast<float*>(smem + L.off_c) + (size_t)warp * L.RS;
@@ -131,6 +135,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) scdist_kernel(
     if (use_bulk) scl_mbar_wait(&bars[0], 0);
     else __syncthreads();
     column_stats_batch(qd, R, S, threadIdx.x, blockDim.x, vq, nq);
+    for (int i = threadIdx.x; i < RS; i += blockDim.x) qdd[i] = (double)qd[i];
     __syncthreads();
 
     uint32_t parity = 0;
@@ -184,27 +189,31 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) scdist_kernel(
                     if (cdist <= search_radius) shifts[ns++] = s_next;
                 }
                 if (ns == 0) break;
-                for (int j = lane; j < S; j += 32) {                   /* the chunk's shifts of column j side by side */
-                    const double na = nq[j];
-                    int cb[kShiftChunk]; double dot[kShiftChunk];
+                /* lane <-> CANDIDATE column cb: each candidate element is widened to double once and meets the
+                 * query columns j_w = cb + s_w of all the chunk's shifts (read as doubles from qdd). Every (j, s)
+                 * dot product still accumulates over the rows in order, so the result is unchanged bit for bit. */
+                for (int cb = lane; cb < S; cb += 32) {
+                    const double nb = nc[cb];
+                    int jw[kShiftChunk]; double dot[kShiftChunk];
 #pragma unroll
                     for (int w = 0; w < kShiftChunk; w++) {
-                        int c = j - (w < ns ? shifts[w] : 0); if (c < 0) c += S;   /* circshift: shifted.col(j) = sc2.col(j - s) */
-                        cb[w] = c; dot[w] = 0.0;
+                        int j = cb + (w < ns ? shifts[w] : 0); if (j >= S) j -= S;   /* circshift: shifted.col(j) = sc2.col(j - s) */
+                        jw[w] = j; dot[w] = 0.0;
                     }
-                    if (na != 0.0) {
+                    if (nb != 0.0) {
+#pragma unroll 4
                         for (int r = 0; r < R; r++) {
-                            const double a = (double)qd[r * S + j];
+                            const double b = (double)cd[r * S + cb];
 #pragma unroll
                             for (int w = 0; w < kShiftChunk; w++)
-                                if (w < ns) dot[w] = __dadd_rn(dot[w], __dmul_rn(a, (double)cd[r * S + cb[w]]));
+                                if (w < ns) dot[w] = __dadd_rn(dot[w], __dmul_rn(qdd[r * S + jw[w]], b));
                         }
                     }
 #pragma unroll
                     for (int w = 0; w < kShiftChunk; w++)
                         if (w < ns) {
-                            const double nb = nc[cb[w]];
-                            sim[w * S + j] = ((na == 0.0) | (nb == 0.0)) ? 0.0 : __ddiv_rn(dot[w], __dmul_rn(na, nb));
+                            const double na = nq[jw[w]];
+                            sim[w * S + jw[w]] = ((na == 0.0) | (nb == 0.0)) ? 0.0 : __ddiv_rn(dot[w], __dmul_rn(na, nb));
                         }
                 }
                 __syncwarp();
@@ -316,21 +325,19 @@ cudaError_t scl_launch_scdist(const float* db_desc, const float* q_desc, const i
     if (L.total > 227 * 1024) return cudaErrorNotSupported;
     const int use_bulk = ((R * S) % 4 == 0) && ((reinterpret_cast<uintptr_t>(db_desc) & 15) == 0) &&
                          (q_desc == nullptr || (reinterpret_cast<uintptr_t>(q_desc) & 15) == 0);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e1 = cudaFuncSetAttribute(scdist_kernel<320, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(113 * 1024));
-        cudaError_t e2 = cudaFuncSetAttribute(scdist_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-        if (e1 != cudaSuccess) return e1;
-        if (e2 != cudaSuccess) return e2;
-        attr_done = true;
-    }
+#define SCL_SCDIST_LAUNCH(MT, MB, RT, ST)                                                                                         \
+    do {                                                                                                                       \
+        cudaError_t ea = cudaFuncSetAttribute(scdist_kernel<MT, MB, RT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total); \
+        if (ea != cudaSuccess) return ea;                                                                                      \
+        scdist_kernel<MT, MB, RT, ST><<<Q, warps * 32, L.total, stream>>>(db_desc, q_desc, q_local, q_ids, cand_local, cand_ids, K, R, S, \
+                                                                          search_radius, use_bulk, cand_dist, cand_shift, best_id, best_dist, best_shift); \
+    } while (0)
     /* up to 10 warps and <= 113 KB: two CTAs per SM (20 warps hide the FP64 latencies); otherwise one big CTA */
-    if (warps <= 10 && L.total <= 113 * 1024)
-        scdist_kernel<320, 2><<<Q, warps * 32, L.total, stream>>>(db_desc, q_desc, q_local, q_ids, cand_local, cand_ids, K, R, S, search_radius,
-                                                                use_bulk, cand_dist, cand_shift, best_id, best_dist, best_shift);
-    else
-        scdist_kernel<512, 1><<<Q, warps * 32, L.total, stream>>>(db_desc, q_desc, q_local, q_ids, cand_local, cand_ids, K, R, S, search_radius,
-                                                                use_bulk, cand_dist, cand_shift, best_id, best_dist, best_shift);
+    const bool two = warps <= 10 && L.total <= 113 * 1024;
+    if (R == 20 && S == 60) { if (two) SCL_SCDIST_LAUNCH(320, 2, 20, 60); else SCL_SCDIST_LAUNCH(512, 1, 20, 60); }
+    else if (R == 40 && S == 120) { if (two) SCL_SCDIST_LAUNCH(320, 2, 40, 120); else SCL_SCDIST_LAUNCH(512, 1, 40, 120); }
+    else { if (two) SCL_SCDIST_LAUNCH(320, 2, 0, 0); else SCL_SCDIST_LAUNCH(512, 1, 0, 0); }
+#undef SCL_SCDIST_LAUNCH
     return cudaGetLastError();
 }
 
