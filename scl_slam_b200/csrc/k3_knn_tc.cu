@@ -458,17 +458,18 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
 }
 
 // Bootstrap: before any tensor-core work, every query gets a valid starting threshold from a strided sample of
-// kBootKeys keys scored on the CUDA cores. Each lane keeps the 4 smallest scores of its share; if b is the m-th
-// smallest of the lanes' 4th-smallest scores, at least 4m sample keys score <= b, so with 4m >= K' the K'-th
-// smallest score of the whole database is <= b. b (+ the prefilter's error bound, so that the bound also holds for
-// the tensor-core scores) removes most of the start-up transient of the streaming top-K' in the sample pass.
+// kBootKeys keys scored on the CUDA cores. Each lane keeps the 4 smallest scores of its share; the K'-th smallest of
+// those 128 scores is >= the K'-th smallest of the sample, hence of the whole database. That bound (+ the
+// prefilter's error bound, so that it also holds for the tensor-core scores) removes most of the start-up
+// transient of the streaming top-K' in the sample pass.
 constexpr int kBootKeys = 4096;
 template <int R>
 __global__ void __launch_bounds__(256) knn_bootstrap_kernel(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys,
                                                             const float* __restrict__ knorm, const float* __restrict__ kn2max, int n_db,
                                                             int kprime, int* __restrict__ g_thr)
 {
-    __shared__ float sk[256][R + 1];
+    __shared__ __align__(16) float sk[256 * R];          /* rows of R floats: LDS.128 reads at an 80-byte lane stride are conflict free */
+    __shared__ float sn[256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qi = blockIdx.x * 8 + warp;
     float q[R];
@@ -484,11 +485,9 @@ __global__ void __launch_bounds__(256) knn_bootstrap_kernel(const float* __restr
             if (j < n_s) {
                 const size_t key = (size_t)j * stride;
 #pragma unroll
-                for (int g = 0; g < R / 4; g++) {
-                    const float4 x = __ldg(reinterpret_cast<const float4*>(keys + key * R) + g);
-                    sk[threadIdx.x][4 * g] = x.x; sk[threadIdx.x][4 * g + 1] = x.y; sk[threadIdx.x][4 * g + 2] = x.z; sk[threadIdx.x][4 * g + 3] = x.w;
-                }
-                sk[threadIdx.x][R] = __ldg(knorm + key);
+                for (int g = 0; g < R / 4; g++)
+                    reinterpret_cast<float4*>(sk + threadIdx.x * R)[g] = __ldg(reinterpret_cast<const float4*>(keys + key * R) + g);
+                sn[threadIdx.x] = __ldg(knorm + key);
             }
         }
         __syncthreads();
@@ -496,8 +495,12 @@ __global__ void __launch_bounds__(256) knn_bootstrap_kernel(const float* __restr
         for (int j = lane; j < nk; j += 32) {
             float dot = 0.0f;
 #pragma unroll
-            for (int d = 0; d < R; d++) dot = fmaf(q[d], sk[j][d], dot);
-            float x = fmaf(-2.0f, dot, sk[j][R]);
+            for (int g = 0; g < R / 4; g++) {
+                const float4 k4 = reinterpret_cast<const float4*>(sk + j * R)[g];
+                dot = fmaf(q[4 * g], k4.x, dot); dot = fmaf(q[4 * g + 1], k4.y, dot);
+                dot = fmaf(q[4 * g + 2], k4.z, dot); dot = fmaf(q[4 * g + 3], k4.w, dot);
+            }
+            float x = fmaf(-2.0f, dot, sn[j]);
             float y;
             y = fminf(b0, x); x = fmaxf(b0, x); b0 = y;
             y = fminf(b1, x); x = fmaxf(b1, x); b1 = y;
@@ -505,23 +508,23 @@ __global__ void __launch_bounds__(256) knn_bootstrap_kernel(const float* __restr
             b3 = fminf(b3, x);
         }
     }
-    /* m-th smallest of the 32 lanes' 4th-smallest scores */
-    const int m = (kprime + 3) / 4;
-    float mine = b3, picked = kThrInit;
-    for (int r = 0; r < m; r++) {
-        float w = mine;
+    /* K'-th smallest among the 32 x 4 kept scores (each lane's four are sorted): a K'-step k-way merge. If a lane
+     * held more than four of the true top-K', the value found is only larger, so it stays a valid upper bound. */
+    float picked = kThrInit;
+    for (int r = 0; r < kprime; r++) {
+        float w = b0;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) w = fminf(w, __shfl_xor_sync(0xffffffffu, w, off));
         picked = w;
-        const unsigned who = __ballot_sync(0xffffffffu, mine == w);
-        if (lane == __ffs(who) - 1) mine = kThrInit;       /* remove one instance of the minimum */
+        const unsigned who = __ballot_sync(0xffffffffu, b0 == w);
+        if (lane == __ffs(who) - 1) { b0 = b1; b1 = b2; b2 = b3; b3 = kThrInit; }   /* pop this lane's head */
     }
     if (lane == 0 && qi < Q && picked < kThrInit) {
         float qn = 0.0f;
 #pragma unroll
         for (int d = 0; d < R; d++) qn = fmaf(q[d], q[d], qn);
-        const float sn = sqrtf(qn) + sqrtf(__ldg(kn2max));
-        atomicMin(g_thr + qi, ordered_int(picked + 3.0517578125e-05f * sn * sn));   /* + 2^-15 (|q|+|k|max)^2 */
+        const float sn2 = sqrtf(qn) + sqrtf(__ldg(kn2max));
+        atomicMin(g_thr + qi, ordered_int(picked + 3.0517578125e-05f * sn2 * sn2));   /* + 2^-15 (|q|+|k|max)^2 */
     }
 }
 
@@ -639,16 +642,22 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(const float* __restrict
         }
         cut = fminf(cut, T);
     }
-    int n_surv = 0; bool overflow = false;
-    for (int c0 = 0; c0 < n_cand; c0 += 32) {
-        const int c = c0 + lane;
-        const int id = c < n_cand ? pidx[c] : -1;
-        const bool keep = id >= 0 && !(ps[c] > cut);
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        const int pos = n_surv + __popc(m & ((1u << lane) - 1u));
-        if (keep && pos < kMaxSurvivors) s_id[w][pos] = id;
-        n_surv += __popc(m);
+    /* the lists are sorted ascending: a list is read only while its entries are at or below the cut */
+    __shared__ int s_count[4];
+    if (lane == 0) s_count[w] = 0;
+    __syncwarp();
+    for (int l = lane; l < n_ranges; l += 32) {
+        for (int i = 0; i < kprime; i++) {
+            const float sc = ps[(size_t)l * kprime + i];
+            if (sc > cut || !(sc < inf)) break;
+            const int id = pidx[(size_t)l * kprime + i];
+            if (id < 0) break;
+            const int pos = atomicAdd(&s_count[w], 1);
+            if (pos < kMaxSurvivors) s_id[w][pos] = id;
+        }
     }
+    __syncwarp();
+    int n_surv = s_count[w]; bool overflow = false;
     if (n_surv > kMaxSurvivors) { overflow = true; n_surv = kMaxSurvivors; }
     __syncwarp();
     for (int c = lane; c < n_surv; c += 32) {
