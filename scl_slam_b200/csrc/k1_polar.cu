@@ -21,32 +21,149 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <vector>
+
 namespace {
 
 constexpr float kNoPoint = -1000.0f;   /* descriptor.h:1411 */
 
-struct PolarParams {
-    int R, S;
-    double lidar_height, max_radius;
+// ---- exact bin tables -------------------------------------------------------------------------
+// The reference computes ring = clamp(ceil(double(r)/max_radius*R), 1, R) and
+// sector = clamp(ceil(double(theta)/360*S), 1, S) with theta = float(180/pi * atanf(y/x)) folded by quadrant
+// (descriptor.h:1352-1374,1434-1435). Both are MONOTONE step functions of one float — r, and within a
+// quadrant the ratio t = |y|/|x| (libm's atanf is monotone on [0, inf]: checked exhaustively).
+// So the host evaluates the reference formula (same double arithmetic, same atanf algorithm) only to find,
+// by bisection over float bit patterns, the exact floats at which each function steps; the kernel then needs
+// one float division and two binary searches per point — no atanf, no FP64 division — and is bit-exact by
+// construction, including at the sector boundaries.
+struct BinTables {
+    int n_ring;            /* ring thresholds: ring = 1 + #(thr <= r) */
+    int n_sec[4];          /* per quadrant: sector = base + dir * #(thr <= t) */
+    int sec_base[4], sec_dir[4], sec_off[4];
+    float r_max;           /* largest float r with double(r) <= max_radius */
 };
 
-// Per-point bin computation, operation for operation what the oracle does (sc_oracle.cpp
-// makeScancontext), which in turn follows descriptor.h:1420-1435. Returns false if dropped.
-__device__ __forceinline__ bool polar_bin(const PolarParams& p, float x, float y, float z, int& ring, int& sector, float& zf)
+inline uint32_t h_f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+inline float h_u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+// libm's float atan restated (fdlibm s_atanf, bit-identical to glibc 2.39 on all 2^32 inputs — see oracle/sc_oracle.cpp)
+float h_atanf(float x)
+{
+    static const float atanhi[4] = {4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f};
+    static const float atanlo[4] = {5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f};
+    static const float aT[11] = {3.3333334327e-01f, -2.0000000298e-01f, 1.4285714924e-01f, -1.1111110449e-01f, 9.0908870101e-02f,
+                                 -7.6918758452e-02f, 6.6610731184e-02f, -5.8335702866e-02f, 4.9768779427e-02f, -3.6531571299e-02f,
+                                 1.6285819933e-02f};
+    const uint32_t hx = h_f2u(x), ix = hx & 0x7fffffffu;
+    int id;
+    volatile float t1, t2;   /* volatile temporaries: no host-side contraction or reassociation */
+    if (ix >= 0x4c000000u) { if (ix > 0x7f800000u) return x + x; const float r = atanhi[3] + atanlo[3]; return (hx >> 31) ? -r : r; }
+    if (ix < 0x3ee00000u) { if (ix < 0x31000000u) return x; id = -1; }
+    else {
+        x = fabsf(x);
+        if (ix < 0x3f980000u) {
+            if (ix < 0x3f300000u) { id = 0; t1 = 2.0f * x; t1 = t1 - 1.0f; t2 = 2.0f + x; x = t1 / t2; }
+            else { id = 1; t1 = x - 1.0f; t2 = x + 1.0f; x = t1 / t2; }
+        } else {
+            if (ix < 0x401c0000u) { id = 2; t1 = x - 1.5f; t2 = 1.5f * x; t2 = 1.0f + t2; x = t1 / t2; }
+            else { id = 3; x = -1.0f / x; }
+        }
+    }
+    volatile float z = x * x, w = z * z, p;
+    p = w * aT[10]; p = aT[8] + p; p = w * p; p = aT[6] + p; p = w * p; p = aT[4] + p; p = w * p; p = aT[2] + p; p = w * p; p = aT[0] + p;
+    volatile float s1 = z * p;
+    p = w * aT[9]; p = aT[7] + p; p = w * p; p = aT[5] + p; p = w * p; p = aT[3] + p; p = w * p; p = aT[1] + p;
+    volatile float s2 = w * p;
+    volatile float sum = s1 + s2, xs = x * sum;
+    if (id < 0) return x - xs;
+    volatile float u = xs - atanlo[id]; u = u - x;
+    const float zz = atanhi[id] - u;
+    return (hx >> 31) ? -zz : zz;
+}
+
+int h_ceil_to_int(double v) { const double c = std::ceil(v); if (!(c >= -2147483648.0 && c <= 2147483647.0)) return (int)0x80000000; return (int)c; }
+
+int h_ring_of(float r, int R, double max_radius)
+{
+    volatile double q = (double)r / max_radius; q = q * (double)R;
+    return std::max(std::min(R, h_ceil_to_int(q)), 1);
+}
+// sector for quadrant qd and ratio t = |y|/|x| (the argument xy2theta hands to atan)
+int h_sector_of(int qd, float t, int S)
+{
+    volatile double a = (180 / M_PI) * (double)h_atanf(t);
+    volatile double th = qd == 0 ? a : qd == 1 ? 180 - a : qd == 2 ? 180 + a : 360 - a;
+    const float theta = (float)th;
+    volatile double q = (double)theta / 360.0; q = q * (double)S;
+    return std::max(std::min(S, h_ceil_to_int(q)), 1);
+}
+// smallest non-negative float (by bit pattern, 0..+inf) at which pred becomes true; pred must be monotone false->true
+template <typename Pred> bool h_first_true(Pred pred, float* out)
+{
+    uint32_t lo = 0, hi = 0x7f800000u;
+    if (!pred(h_u2f(hi))) return false;
+    while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (pred(h_u2f(mid))) hi = mid; else lo = mid + 1; }
+    *out = h_u2f(lo);
+    return true;
+}
+
+void build_tables(int R, int S, double max_radius, BinTables& bt, std::vector<float>& tab)
+{
+    tab.clear();
+    for (int i = 1; i < R; i++) { float f; if (h_first_true([&](float r) { return h_ring_of(r, R, max_radius) > i; }, &f)) tab.push_back(f); }
+    bt.n_ring = (int)tab.size();
+    float rm = 0.0f;
+    h_first_true([&](float r) { return (double)r > max_radius; }, &rm);      /* smallest float beyond the radius ... */
+    bt.r_max = std::nextafterf(rm, 0.0f);                                     /* ... so this is the largest one inside */
+    if (!((double)std::numeric_limits<float>::infinity() > max_radius)) bt.r_max = std::numeric_limits<float>::infinity();
+    for (int qd = 0; qd < 4; qd++) {
+        const int v0 = h_sector_of(qd, 0.0f, S), vinf = h_sector_of(qd, std::numeric_limits<float>::infinity(), S);
+        bt.sec_base[qd] = v0; bt.sec_dir[qd] = vinf >= v0 ? 1 : -1; bt.sec_off[qd] = (int)tab.size();
+        if (vinf >= v0) {
+            for (int v = v0 + 1; v <= vinf; v++) { float f; if (h_first_true([&](float t) { return h_sector_of(qd, t, S) >= v; }, &f)) tab.push_back(f); }
+        } else {
+            for (int v = v0 - 1; v >= vinf; v--) { float f; if (h_first_true([&](float t) { return h_sector_of(qd, t, S) <= v; }, &f)) tab.push_back(f); }
+        }
+        bt.n_sec[qd] = (int)tab.size() - bt.sec_off[qd];
+    }
+}
+
+struct PolarParams {
+    int R, S;
+    double lidar_height;
+    BinTables bt;
+    const float* tab;      /* device copy of the threshold table */
+    int n_tab;
+};
+
+__device__ __forceinline__ int count_le(const float* __restrict__ t, int n, float v)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (t[mid] <= v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// Per-point bin: one float sqrt, one float division, two table searches. stab = shared-memory copy of the table.
+__device__ __forceinline__ bool polar_bin(const PolarParams& p, const float* __restrict__ stab, float x, float y, float z,
+                                          int& ring, int& sector, float& zf)
 {
     zf = __double2float_rn(__dadd_rn((double)z, p.lidar_height));                  /* :1422 */
     const float azim_range = __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))); /* :1425 */
-    const double k = 180.0 / 3.14159265358979323846;                                 /* (180/M_PI) */
-    double theta;
-    if ((x >= 0) & (y >= 0))      theta = __dmul_rn(k, (double)scl_atanf(__fdiv_rn(y, x)));
-    else if ((x < 0) & (y >= 0))  theta = __dsub_rn(180.0, __dmul_rn(k, (double)scl_atanf(__fdiv_rn(y, -x))));
-    else if ((x < 0) & (y < 0))   theta = __dadd_rn(180.0, __dmul_rn(k, (double)scl_atanf(__fdiv_rn(y, x))));
-    else if ((x >= 0) & (y < 0))  theta = __dsub_rn(360.0, __dmul_rn(k, (double)scl_atanf(__fdiv_rn(-y, x))));
+    int qd; float t;
+    if ((x >= 0) & (y >= 0))      { qd = 0; t = __fdiv_rn(y, x); }
+    else if ((x < 0) & (y >= 0))  { qd = 1; t = __fdiv_rn(y, -x); }
+    else if ((x < 0) & (y < 0))   { qd = 2; t = __fdiv_rn(y, x); }
+    else if ((x >= 0) & (y < 0))  { qd = 3; t = __fdiv_rn(-y, x); }
     else return false;                          /* NaN coordinate: UB in the reference, dropped (Q9) */
-    const float azim_angle = __double2float_rn(theta);                               /* returned as float */
-    if ((double)azim_range > p.max_radius) return false;                             /* :1429 */
-    ring = max(min(p.R, scl_ceil_to_int(__dmul_rn(__ddiv_rn((double)azim_range, p.max_radius), (double)p.R))), 1);
-    sector = max(min(p.S, scl_ceil_to_int(__dmul_rn(__ddiv_rn((double)azim_angle, 360.0), (double)p.S))), 1);
+    if (azim_range > p.bt.r_max) return false;  /* double(r) > max_radius (:1429) */
+    ring = 1 + count_le(stab, p.bt.n_ring, azim_range);
+    if (t != t) sector = 1;                     /* (0,0): theta = NaN -> int(ceil(NaN)) = INT_MIN -> clamped to 1 */
+    else sector = p.bt.sec_base[qd] + p.bt.sec_dir[qd] * count_le(stab + p.bt.sec_off[qd], p.bt.n_sec[qd], t);
     return true;
 }
 
@@ -71,9 +188,11 @@ __global__ void __launch_bounds__(256) polar_bin_kernel(
     float* __restrict__ out_desc /* [scans][R*S] */, float* __restrict__ out_keys /* [scans][R] */,
     float* __restrict__ out_knorm /* [scans] */, float* __restrict__ kn2max, int* __restrict__ out_ring, int* __restrict__ out_sector)
 {
-    extern __shared__ uint32_t sbins[];   /* R*S keys, then R*S floats for the epilogue */
+    extern __shared__ uint32_t sbins[];   /* R*S keys, R*S + R floats for the epilogue, then the bin tables */
     __shared__ int s_last;
     const int RS = p.R * p.S;
+    float* stab = reinterpret_cast<float*>(sbins + 2 * RS + p.R);
+    for (int i = threadIdx.x; i < p.n_tab; i += blockDim.x) stab[i] = __ldg(p.tab + i);
     const int scan = blockIdx.y;
     const int p0 = offsets[scan], p1 = offsets[scan + 1];
     const uint32_t key_none = scl_float_key(kNoPoint);
@@ -94,7 +213,7 @@ __global__ void __launch_bounds__(256) polar_bin_kernel(
         for (int j = 0; j < kPointsPerThread; j++) {
             const int i = base + j * blockDim.x + threadIdx.x;
             int ring = 0, sector = 0; float zf;
-            bool ok = (i < p1) && polar_bin(p, x[j], y[j], z[j], ring, sector, zf);
+            bool ok = (i < p1) && polar_bin(p, stab, x[j], y[j], z[j], ring, sector, zf);
             if (out_ring != nullptr && i < p1) { out_ring[i] = ok ? ring : 0; out_sector[i] = ok ? sector : 0; }
             ok = ok && !(zf != zf);                     /* desc < NaN is false: NaN heights never win (:1438) */
             const int bin = ok ? (ring - 1) * p.S + (sector - 1) : -1;
@@ -188,7 +307,30 @@ cudaError_t scl_launch_polar(const void* pts_dev, const int* offsets_dev, int n_
                              cudaStream_t stream)
 {
     if (n_scans <= 0) return cudaSuccess;
-    PolarParams p{R, S, lidar_height, max_radius};
+    /* bin tables: built once per geometry on the host, kept in device memory */
+    struct Cached { int R, S; double max_radius; int device; BinTables bt; float* dev; int n; };
+    static std::vector<Cached> cache;
+    static std::mutex cache_mu;
+    PolarParams p;
+    {
+        std::lock_guard<std::mutex> lk(cache_mu);
+        int device = 0; cudaGetDevice(&device);
+        const Cached* hit = nullptr;
+        for (const Cached& c : cache) if (c.R == R && c.S == S && c.max_radius == max_radius && c.device == device) { hit = &c; break; }
+        if (!hit) {
+            Cached c; c.R = R; c.S = S; c.max_radius = max_radius; c.device = device;
+            std::vector<float> tab;
+            build_tables(R, S, max_radius, c.bt, tab);
+            c.n = (int)tab.size();
+            cudaError_t e = cudaMalloc(&c.dev, (tab.size() + 1) * sizeof(float));
+            if (e != cudaSuccess) return e;
+            e = cudaMemcpy(c.dev, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) return e;
+            cache.push_back(c);
+            hit = &cache.back();
+        }
+        p.R = R; p.S = S; p.lidar_height = lidar_height; p.bt = hit->bt; p.tab = hit->dev; p.n_tab = hit->n;
+    }
     constexpr int kPPT = 8;
     const int chunk = 256 * kPPT;
     int chunks = (max_points + chunk - 1) / chunk;
@@ -197,7 +339,7 @@ cudaError_t scl_launch_polar(const void* pts_dev, const int* offsets_dev, int n_
     const int want = (4 * SCL_NUM_SMS + n_scans - 1) / n_scans;
     if (chunks > want) chunks = want;
     const int vec4 = (stride_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(pts_dev) & 15) == 0);
-    const size_t smem = (size_t)R * S * 8 + (size_t)R * 4;
+    const size_t smem = (size_t)R * S * 8 + (size_t)R * 4 + (size_t)p.n_tab * 4;
     dim3 grid(chunks, n_scans);
     polar_bin_kernel<kPPT><<<grid, 256, smem, stream>>>(static_cast<const unsigned char*>(pts_dev), offsets_dev, stride_bytes, vec4, p,
                                                        gbins, tickets, out_desc, out_keys, out_knorm, kn2max, out_ring, out_sector);
