@@ -103,9 +103,9 @@ int h_sector_of(int qd, float t, int S)
     return std::max(std::min(S, h_ceil_to_int(q)), 1);
 }
 // smallest non-negative float (by bit pattern, 0..+inf) at which pred becomes true; pred must be monotone false->true
-template <typename Pred> bool h_first_true(Pred pred, float* out)
+template <typename Pred> bool h_first_true(Pred pred, float* out, float upper = std::numeric_limits<float>::infinity())
 {
-    uint32_t lo = 0, hi = 0x7f800000u;
+    uint32_t lo = 0, hi = h_f2u(upper);
     if (!pred(h_u2f(hi))) return false;
     while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (pred(h_u2f(mid))) hi = mid; else lo = mid + 1; }
     *out = h_u2f(lo);
@@ -115,12 +115,12 @@ template <typename Pred> bool h_first_true(Pred pred, float* out)
 void build_tables(int R, int S, double max_radius, BinTables& bt, std::vector<float>& tab)
 {
     tab.clear();
-    for (int i = 1; i < R; i++) { float f; if (h_first_true([&](float r) { return h_ring_of(r, R, max_radius) > i; }, &f)) tab.push_back(f); }
-    bt.n_ring = (int)tab.size();
     float rm = 0.0f;
     h_first_true([&](float r) { return (double)r > max_radius; }, &rm);      /* smallest float beyond the radius ... */
     bt.r_max = std::nextafterf(rm, 0.0f);                                     /* ... so this is the largest one inside */
-    if (!((double)std::numeric_limits<float>::infinity() > max_radius)) bt.r_max = std::numeric_limits<float>::infinity();
+    /* ring thresholds are searched inside [0, r_max] only (beyond it int(ceil()) overflows, and the point is dropped anyway) */
+    for (int i = 1; i < R; i++) { float f; if (h_first_true([&](float r) { return h_ring_of(r, R, max_radius) > i; }, &f, bt.r_max)) tab.push_back(f); }
+    bt.n_ring = (int)tab.size();
     for (int qd = 0; qd < 4; qd++) {
         const int v0 = h_sector_of(qd, 0.0f, S), vinf = h_sector_of(qd, std::numeric_limits<float>::infinity(), S);
         bt.sec_base[qd] = v0; bt.sec_dir[qd] = vinf >= v0 ? 1 : -1; bt.sec_off[qd] = (int)tab.size();
