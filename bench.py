@@ -291,11 +291,53 @@ def run_ours(args):
         "parity_spot": {"source_recovered": recovered, "shift_recovered_given_source": shift_ok},
         "knn": e.knn_stats(),
     }
+    if world == 1:
+        line["descriptors"] = descriptor_bench(engine, dev, pk)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(e, n_local, q_dev, final, sample=args.cpu_sample)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def descriptor_bench(engine, dev, pk, batch=64, iters=10):
+    """Secondary metric of BASELINE.json ("descriptors/sec; % HBM roofline"): K1+K2 on a batch of HDL-64-shaped
+    scans (BASELINE configs[1] shape, ~113k returns of 120k rays, pcl::PointXYZI layout, 32 B/point)."""
+    from scl_slam_b200 import synth
+    world = synth.make_world(1, 300)
+    sc = synth.to_pcl_xyzi(synth.scan(world, (3.0, -2.0, 0.4), synth.lidar_dirs("hdl64"), seed=0))
+    P = sc.shape[0]
+    host = np.ascontiguousarray(np.concatenate([sc] * batch))
+    offs = np.arange(batch + 1, dtype=np.int32) * P
+    pts = torch.from_numpy(host).to(dev)
+    out = torch.empty((batch, R, S), dtype=torch.float32, device=dev)
+    e = engine.ScanContextB200()
+    e.set_stream(torch.cuda.current_stream().cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        e.build_batch_dev(pts, offs, 32, insert=False, out_dev=out)
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in evs:
+        flush.zero_()
+        a.record(); e.build_batch_dev(pts, offs, 32, insert=False, out_dev=out); b.record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs) / iters
+    host_pinned = torch.from_numpy(host).pin_memory().numpy()
+    out_h = np.empty((batch, R * S), np.float32)
+    for _ in range(2):
+        e._ck(e.lib.scl_build_batch(e.h, host_pinned.ctypes.data, offs.ctypes.data, batch, 32, 0, None, None, out_h.ctypes.data))
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        e._ck(e.lib.scl_build_batch(e.h, host_pinned.ctypes.data, offs.ctypes.data, batch, 32, 0, None, None, out_h.ctypes.data))
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / iters
+    read_bytes = batch * P * 32
+    alg_bytes = batch * (16 * P + 4 * R * S + 4 * R + 4 * S)          # SURVEY.md §8d per-scan figure (packed float4 points)
+    return {"value": batch / (ms * 1e-3), "unit": "descriptors/s", "points_per_scan": P, "scans_per_launch": batch, "ms_per_launch": ms,
+            "e2e": {"value": batch / (e2e_ms * 1e-3), "unit": "descriptors/s", "h2d_bytes_per_launch": int(host.nbytes), "d2h_bytes_per_launch": int(out_h.nbytes)},
+            "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                         "frac": alg_bytes / (ms * 1e-3) / 1e9 / pk["hbm"], "consumed_in_place_gbs": read_bytes / (ms * 1e-3) / 1e9,
+                         "note": "algorithmic bytes count 16 B/point; the kernel reads the 32 B/point PCL layout in place"}}
 
 
 def _oracle(kind_pref=("ref", "port")):
