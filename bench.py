@@ -165,31 +165,30 @@ def run_ours(args):
                     best_shift=torch.empty(Q, dtype=torch.int32, device=dev))
     local, merged = buf(), buf()
     if world > 1:
-        # one packed record block per rank -> ONE all-gather per step: [dist f64 | ids i32 | d2 f32 | shift i32] x Q*K
+        # two-phase exchange (include/scl_engine.h): (id, d2) blocks, then (dist, shift) blocks; one all-gather each
         QK = Q * K
-        blob = torch.empty(QK * 20, dtype=torch.uint8, device=dev)
-        local["cand_dist"] = blob[:QK * 8].view(torch.float64).view(Q, K)
-        local["cand_ids"] = blob[QK * 8:QK * 12].view(torch.int32).view(Q, K)
-        local["cand_d2"] = blob[QK * 12:QK * 16].view(torch.float32).view(Q, K)
-        local["cand_shift"] = blob[QK * 16:QK * 20].view(torch.int32).view(Q, K)
-        gathered = torch.empty((world, QK * 20), dtype=torch.uint8, device=dev)
-        # the merge kernel reads rank-major [world][Q][K] arrays: views with the blob stride are not contiguous,
-        # so the four sections are re-packed by one small copy each (device-side, 4 x world*Q*K elements)
-        gath = dict(ids=torch.empty((world, Q, K), dtype=torch.int32, device=dev), d2=torch.empty((world, Q, K), dtype=torch.float32, device=dev),
-                    dist=torch.empty((world, Q, K), dtype=torch.float64, device=dev), shift=torch.empty((world, Q, K), dtype=torch.int32, device=dev))
+        blob1 = torch.empty(QK * 8, dtype=torch.uint8, device=dev)          # [ids i32 | d2 f32]
+        loc_ids = blob1[:QK * 4].view(torch.int32).view(Q, K)
+        loc_d2 = blob1[QK * 4:].view(torch.float32).view(Q, K)
+        gath1 = torch.empty((world, QK * 8), dtype=torch.uint8, device=dev)
+        blob2 = torch.empty(QK * 12, dtype=torch.uint8, device=dev)         # [dist f64 | shift i32]
+        own_dist = blob2[:QK * 8].view(torch.float64).view(Q, K)
+        own_shift = blob2[QK * 8:].view(torch.int32).view(Q, K)
+        gath2 = torch.empty((world, QK * 12), dtype=torch.uint8, device=dev)
     # ring_key, knn_bootstrap, knn_tc (sample), knn_sample_thr, knn_tc (main), knn_rerank, knn_exact (fallback list),
-    # knn_merge, ids_to_local, scdist (+ merge_shards)
-    launches_per_step = 10 + (1 if world > 1 else 0)
+    # knn_merge, ids_to_local, scdist (+ merge_topk, combine_owned)
+    launches_per_step = 10 + (2 if world > 1 else 0)
 
     def step():
-        e.query_batch_dev(q_dev, None, Q, K, n_local, 0, local)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, blob)
-            gath["dist"].copy_(gathered[:, :QK * 8].view(torch.float64).view(world, Q, K))
-            gath["ids"].copy_(gathered[:, QK * 8:QK * 12].view(torch.int32).view(world, Q, K))
-            gath["d2"].copy_(gathered[:, QK * 12:QK * 16].view(torch.float32).view(world, Q, K))
-            gath["shift"].copy_(gathered[:, QK * 16:QK * 20].view(torch.int32).view(world, Q, K))
-            e.merge_shards_dev(world, Q, K, None, gath["ids"], gath["d2"], gath["dist"], gath["shift"], merged)
+        if world == 1:
+            e.query_batch_dev(q_dev, None, Q, K, n_local, 0, local)
+            return
+        e.knn_batch_dev(q_dev, Q, K, n_local, 0, loc_ids, loc_d2)                       # K2 + K3 on the shard
+        dist.all_gather_into_tensor(gath1, blob1)
+        e.merge_topk_dev(world, Q, K, gath1, gath1[:, QK * 4:], QK * 8, merged["cand_ids"], merged["cand_d2"])
+        e.scdist_owned_dev(q_dev, Q, K, merged["cand_ids"], own_dist, own_shift)        # K4 on the owned candidates only
+        dist.all_gather_into_tensor(gath2, blob2)
+        e.combine_owned_dev(world, Q, K, merged["cand_ids"], gath2, gath2[:, QK * 8:], QK * 12, merged)
 
     def barrier():
         if world > 1:

@@ -144,6 +144,22 @@ int scl_merge_shards_dev(scl_engine* e, int world, int Q, int K, const int32_t* 
                          const int32_t* all_ids, const float* all_d2, const double* all_dist, const int32_t* all_shift,
                          scl_batch_result* merged);
 
+/* Two-phase exchange (what bench.py uses for N > 1): the SC distance is computed once per GLOBAL
+ * candidate, by the rank that owns it, instead of K times per rank.
+ *   1. scl_knn_batch_dev      : K2 + K3 on the shard -> local (id, d2) lists (device pointers, asynchronous)
+ *      all-gather of the (id, d2) blocks, rank blocks rank_stride_bytes apart
+ *   2. scl_merge_topk_dev     : global top-K by (d2, id), identical on every rank
+ *   3. scl_scdist_owned_dev   : K4 for the candidates with id mod world == rank (others: NaN / 0)
+ *      all-gather of the (dist, shift) blocks
+ *   4. scl_combine_owned_dev  : take each candidate's result from its owner's block + the winner scan */
+int scl_knn_batch_dev(scl_engine* e, const scl_batch_query* q, int32_t* ids_dev, float* d2_dev);
+int scl_merge_topk_dev(scl_engine* e, int world, int Q, int K, const void* ids_base, const void* d2_base, uint64_t rank_stride_bytes,
+                       int32_t* out_ids, float* out_d2);
+int scl_scdist_owned_dev(scl_engine* e, const float* q_desc_dev, const int32_t* q_ids_dev, int Q, int K, const int32_t* cand_ids_dev,
+                         double* dist_dev, int32_t* shift_dev);
+int scl_combine_owned_dev(scl_engine* e, int world, int Q, int K, const int32_t* q_ids, const int32_t* cand_ids, const void* dist_base,
+                          const void* shift_base, uint64_t rank_stride_bytes, scl_batch_result* merged);
+
 /* ---- ring-key kNN variant ---------------------------------------------
  * mode 0 = automatic (tensor-core prefilter for batches >= 64 queries on >= 32768 keys, exact
  * CUDA-core kernel otherwise), 1 = always exact, 2 = always tensor core. Both produce identical

@@ -134,12 +134,12 @@ int build_host(scl_engine* e, const void* pts, const int32_t* offsets, int n_sca
     return SCL_OK;
 }
 
-// the batched query on device pointers; any result pointer may be null (scratch is used)
-int query_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int K, int n_db, int metric, int missing_to_zero,
-              int32_t* cand_ids, float* cand_d2, double* cand_dist, int32_t* cand_shift,
-              int32_t* best_id, double* best_dist, int32_t* best_shift)
+// K2 (query ring keys) + K3 (ring-key kNN) on device pointers; results: reported ids + float distances
+int knn_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int K, int n_db, int metric,
+            int32_t* cand_ids, float* cand_d2, int32_t** q_local_out)
 {
     const int R = e->p.num_ring, S = e->p.num_sector;
+    if (q_local_out) *q_local_out = nullptr;
     if (Q <= 0) return SCL_OK;
     if (K < 1 || K > 32) FAIL(SCL_ERR_INVALID, "K must be in 1..32");
     if (metric != 0 && metric != 1) FAIL(SCL_ERR_INVALID, "metric must be 0 or 1");
@@ -148,8 +148,7 @@ int query_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, i
     if (!q_desc && !q_ids) FAIL(SCL_ERR_INVALID, "q_desc and q_ids are both NULL");
     if (!q_desc && e->world != 1) FAIL(SCL_ERR_INVALID, "queries by key need q_desc on a sharded engine");
     const size_t QK = (size_t)Q * K;
-    if (!cand_ids) { CK(e->cand_ids.ensure(QK * 4)); cand_ids = e->cand_ids.as<int32_t>(); }
-    if (!cand_d2) { CK(e->cand_d2.ensure(QK * 4)); cand_d2 = e->cand_d2.as<float>(); }
+    (void)QK;
     CK(e->cand_local.ensure(QK * 4));
     CK(e->qkeys.ensure((size_t)Q * R * 4));
     int32_t* q_local = nullptr;
@@ -199,12 +198,40 @@ int query_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, i
         CK(cudaStreamSynchronize(e->stream));
         e->stat_fallback_queries += nfail;
     }
+    if (q_local_out) *q_local_out = q_local;
+    return SCL_OK;
+}
+
+// K4 on device pointers: SC distance of every (query, candidate) this engine owns (+ the winner scan)
+int scdist_dev(scl_engine* e, const float* q_desc, const int32_t* q_local, const int32_t* q_ids, int Q, int K, int32_t* cand_ids,
+               int missing_to_zero, double* cand_dist, int32_t* cand_shift, int32_t* best_id, double* best_dist, int32_t* best_shift)
+{
+    const int R = e->p.num_ring, S = e->p.num_sector;
+    if (Q <= 0) return SCL_OK;
+    const size_t QK = (size_t)Q * K;
+    CK(e->cand_local.ensure(QK * 4));
     CK(scl_launch_ids_to_local(cand_ids, (int)QK, e->world, e->rank, missing_to_zero ? 0 : -1, missing_to_zero ? cand_ids : nullptr,
                                e->cand_local.as<int32_t>(), e->stream));
     StageTimer st(e, 2);
     CK(scl_launch_scdist(e->d_desc, q_desc, q_local, q_ids, e->cand_local.as<int32_t>(), cand_ids, Q, K, R, S, e->search_radius,
                          cand_dist, cand_shift, best_id, best_dist, best_shift, e->stream));
     return SCL_OK;
+}
+
+// the batched query on device pointers; any result pointer may be null (scratch is used)
+int query_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int K, int n_db, int metric, int missing_to_zero,
+              int32_t* cand_ids, float* cand_d2, double* cand_dist, int32_t* cand_shift,
+              int32_t* best_id, double* best_dist, int32_t* best_shift)
+{
+    if (Q <= 0) return SCL_OK;
+    if (K < 1 || K > 32) FAIL(SCL_ERR_INVALID, "K must be in 1..32");
+    const size_t QK = (size_t)Q * K;
+    if (!cand_ids) { CK(e->cand_ids.ensure(QK * 4)); cand_ids = e->cand_ids.as<int32_t>(); }
+    if (!cand_d2) { CK(e->cand_d2.ensure(QK * 4)); cand_d2 = e->cand_d2.as<float>(); }
+    int32_t* q_local = nullptr;
+    int rc = knn_dev(e, q_desc, q_ids, Q, K, n_db, metric, cand_ids, cand_d2, &q_local);
+    if (rc) return rc;
+    return scdist_dev(e, q_desc, q_local, q_ids, Q, K, cand_ids, missing_to_zero, cand_dist, cand_shift, best_id, best_dist, best_shift);
 }
 
 int query_host(scl_engine* e, const scl_batch_query* q, scl_batch_result* r, int missing_to_zero)
@@ -468,6 +495,41 @@ int scl_merge_shards_dev(scl_engine* e, int world, int Q, int K, const int32_t* 
     if (!m) FAIL(SCL_ERR_INVALID, "null result");
     CK(scl_launch_merge_shards(world, Q, K, q_ids, all_ids, all_d2, all_dist, all_shift, m->cand_ids, m->cand_d2, m->cand_dist,
                                m->cand_shift, m->best_id, m->best_dist, m->best_shift, e->stream));
+    return SCL_OK;
+}
+
+int scl_knn_batch_dev(scl_engine* e, const scl_batch_query* q, int32_t* ids_dev, float* d2_dev)
+{
+    LOCK();
+    if (!q || !ids_dev || !d2_dev) FAIL(SCL_ERR_INVALID, "null argument");
+    return knn_dev(e, q->q_desc, q->q_ids, q->Q, q->K, q->n_db, q->metric, ids_dev, d2_dev, nullptr);
+}
+
+int scl_merge_topk_dev(scl_engine* e, int world, int Q, int K, const void* ids_base, const void* d2_base, uint64_t rank_stride_bytes,
+                       int32_t* out_ids, float* out_d2)
+{
+    LOCK();
+    if (!ids_base || !d2_base || !out_ids || !out_d2) FAIL(SCL_ERR_INVALID, "null argument");
+    CK(scl_launch_merge_topk(world, Q, K, ids_base, d2_base, (size_t)rank_stride_bytes, out_ids, out_d2, e->stream));
+    return SCL_OK;
+}
+
+int scl_scdist_owned_dev(scl_engine* e, const float* q_desc_dev, const int32_t* q_ids_dev, int Q, int K, const int32_t* cand_ids_dev,
+                         double* dist_dev, int32_t* shift_dev)
+{
+    LOCK();
+    if (!q_desc_dev || !cand_ids_dev || !dist_dev || !shift_dev) FAIL(SCL_ERR_INVALID, "null argument");
+    if (K < 1 || K > 32) FAIL(SCL_ERR_INVALID, "K must be in 1..32");
+    return scdist_dev(e, q_desc_dev, nullptr, q_ids_dev, Q, K, const_cast<int32_t*>(cand_ids_dev), 0, dist_dev, shift_dev, nullptr, nullptr, nullptr);
+}
+
+int scl_combine_owned_dev(scl_engine* e, int world, int Q, int K, const int32_t* q_ids, const int32_t* cand_ids, const void* dist_base,
+                          const void* shift_base, uint64_t rank_stride_bytes, scl_batch_result* m)
+{
+    LOCK();
+    if (!cand_ids || !dist_base || !shift_base || !m) FAIL(SCL_ERR_INVALID, "null argument");
+    CK(scl_launch_combine_owned(world, Q, K, q_ids, cand_ids, dist_base, shift_base, (size_t)rank_stride_bytes, m->cand_dist, m->cand_shift,
+                                m->best_id, m->best_dist, m->best_shift, e->stream));
     return SCL_OK;
 }
 

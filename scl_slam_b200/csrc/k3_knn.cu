@@ -175,7 +175,7 @@ __global__ void ids_to_local_kernel(const int32_t* __restrict__ ids, int n, int 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int id = ids[i];
-    local[i] = id < 0 ? missing_to : (id - id_add) / id_mul;
+    local[i] = id < 0 ? missing_to : ((id - id_add) % id_mul == 0 ? (id - id_add) / id_mul : -1);   /* -1: owned by another shard */
     if (ids_rewrite != nullptr && id < 0) ids_rewrite[i] = missing_to;
 }
 

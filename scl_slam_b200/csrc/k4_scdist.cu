@@ -310,6 +310,60 @@ __global__ void merge_shards_kernel(int world, int Q, int K, const int32_t* __re
     if (best_shift) best_shift[qi] = nn_align;
 }
 
+// Two-phase multi-GPU exchange, phase 1: per query, world x K (id, d2) records (each rank's list in its own kNN
+// order; rank blocks `stride` bytes apart) -> the global top-K by (d2, id). Every rank computes the same lists.
+__global__ void merge_topk_kernel(int world, int Q, int K, const unsigned char* __restrict__ ids_base, const unsigned char* __restrict__ d2_base,
+                                  size_t stride, int32_t* __restrict__ out_ids, float* __restrict__ out_d2)
+{
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= Q) return;
+    int head[16];
+    for (int w = 0; w < world; w++) head[w] = 0;
+    for (int r = 0; r < K; r++) {
+        int bw = -1; float bd = 0.f; int bi = 0;
+        for (int w = 0; w < world; w++) {
+            if (head[w] >= K) continue;
+            const size_t o = (size_t)qi * K + head[w];
+            const int id = reinterpret_cast<const int32_t*>(ids_base + w * stride)[o];
+            if (id < 0) { head[w] = K; continue; }
+            const float d = reinterpret_cast<const float*>(d2_base + w * stride)[o];
+            if (bw < 0 || d < bd || (d == bd && id < bi)) { bw = w; bd = d; bi = id; }
+        }
+        if (bw >= 0) head[bw]++;
+        out_ids[(size_t)qi * K + r] = bw >= 0 ? bi : -1;
+        out_d2[(size_t)qi * K + r] = bw >= 0 ? bd : 3.402823466e+38f;
+    }
+}
+
+// Phase 2: every candidate's SC distance was computed by the rank that owns it (id mod world); pick it from that
+// rank's block and run the winner scan in global kNN order (descriptor.h:1721-1737).
+__global__ void combine_owned_kernel(int world, int Q, int K, const int32_t* __restrict__ q_ids, const int32_t* __restrict__ cand_ids,
+                                     const unsigned char* __restrict__ dist_base, const unsigned char* __restrict__ shift_base, size_t stride,
+                                     double* __restrict__ out_dist, int32_t* __restrict__ out_shift, int32_t* __restrict__ best_id,
+                                     double* __restrict__ best_dist, int32_t* __restrict__ best_shift)
+{
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= Q) return;
+    double min_dist = 10000000.0; int nn_align = 0, nn_idx = -1;
+    const int self = q_ids ? q_ids[qi] : -1;
+    for (int r = 0; r < K; r++) {
+        const size_t o = (size_t)qi * K + r;
+        const int id = cand_ids[o];
+        double dist = __longlong_as_double(0x7ff8000000000000LL); int shift = 0;
+        if (id >= 0) {
+            const int owner = id % world;
+            dist = reinterpret_cast<const double*>(dist_base + owner * stride)[o];
+            shift = reinterpret_cast<const int32_t*>(shift_base + owner * stride)[o];
+            if (dist < min_dist && id != self) { min_dist = dist; nn_align = shift; nn_idx = id; }
+        }
+        if (out_dist) out_dist[o] = dist;
+        if (out_shift) out_shift[o] = shift;
+    }
+    if (best_id) best_id[qi] = nn_idx;
+    if (best_dist) best_dist[qi] = min_dist;
+    if (best_shift) best_shift[qi] = nn_align;
+}
+
 } // namespace
 
 cudaError_t scl_launch_scdist(const float* db_desc, const float* q_desc, const int32_t* q_local, const int32_t* q_ids,
@@ -350,5 +404,27 @@ cudaError_t scl_launch_merge_shards(int world, int Q, int K, const int32_t* q_id
     if (world < 1 || world > 16) return cudaErrorInvalidValue;
     merge_shards_kernel<<<(Q + 127) / 128, 128, 0, stream>>>(world, Q, K, q_ids, all_ids, all_d2, all_dist, all_shift,
                                                             out_ids, out_d2, out_dist, out_shift, best_id, best_dist, best_shift);
+    return cudaGetLastError();
+}
+
+cudaError_t scl_launch_merge_topk(int world, int Q, int K, const void* ids_base, const void* d2_base, size_t rank_stride_bytes,
+                                  int32_t* out_ids, float* out_d2, cudaStream_t stream)
+{
+    if (Q <= 0) return cudaSuccess;
+    if (world < 1 || world > 16) return cudaErrorInvalidValue;
+    merge_topk_kernel<<<(Q + 127) / 128, 128, 0, stream>>>(world, Q, K, static_cast<const unsigned char*>(ids_base),
+                                                          static_cast<const unsigned char*>(d2_base), rank_stride_bytes, out_ids, out_d2);
+    return cudaGetLastError();
+}
+
+cudaError_t scl_launch_combine_owned(int world, int Q, int K, const int32_t* q_ids, const int32_t* cand_ids, const void* dist_base,
+                                     const void* shift_base, size_t rank_stride_bytes, double* out_dist, int32_t* out_shift,
+                                     int32_t* best_id, double* best_dist, int32_t* best_shift, cudaStream_t stream)
+{
+    if (Q <= 0) return cudaSuccess;
+    if (world < 1 || world > 16) return cudaErrorInvalidValue;
+    combine_owned_kernel<<<(Q + 127) / 128, 128, 0, stream>>>(world, Q, K, q_ids, cand_ids, static_cast<const unsigned char*>(dist_base),
+                                                             static_cast<const unsigned char*>(shift_base), rank_stride_bytes, out_dist, out_shift,
+                                                             best_id, best_dist, best_shift);
     return cudaGetLastError();
 }

@@ -58,9 +58,16 @@ cudaError_t scl_launch_merge_shards(int world, int Q, int K, const int32_t* q_id
                                     double* out_dist, int32_t* out_shift, int32_t* best_id, double* best_dist, int32_t* best_shift,
                                     cudaStream_t stream);
 
+// Two-phase multi-GPU exchange: rank blocks are `rank_stride_bytes` apart (e.g. an all-gather buffer).
+cudaError_t scl_launch_merge_topk(int world, int Q, int K, const void* ids_base, const void* d2_base, size_t rank_stride_bytes,
+                                  int32_t* out_ids, float* out_d2, cudaStream_t stream);
+cudaError_t scl_launch_combine_owned(int world, int Q, int K, const int32_t* q_ids, const int32_t* cand_ids, const void* dist_base,
+                                     const void* shift_base, size_t rank_stride_bytes, double* out_dist, int32_t* out_shift,
+                                     int32_t* best_id, double* best_dist, int32_t* best_shift, cudaStream_t stream);
+
 // small helpers
 cudaError_t scl_launch_gather_rows(const float* src, const int32_t* rows, int n, int width, float* dst, cudaStream_t stream);
-// reported id -> local key ((id - id_add) / id_mul); missing (-1) entries become `missing_to`, and are
-// also rewritten in ids_rewrite when that is non-null
+// reported id -> local key ((id - id_add) / id_mul; -1 if the id belongs to another shard); missing (-1) entries
+// become `missing_to`, and are also rewritten in ids_rewrite when that is non-null
 cudaError_t scl_launch_ids_to_local(const int32_t* ids, int n, int id_mul, int id_add, int missing_to, int32_t* ids_rewrite,
                                     int32_t* local, cudaStream_t stream);

@@ -26,6 +26,7 @@ EXPORTS = [
     "scl_insert", "scl_insert_batch", "scl_insert_batch_dev", "scl_get_index", "scl_size", "scl_get_descriptor",
     "scl_get_ring_key", "scl_query_intra", "scl_query_inter", "scl_query_batch", "scl_query_batch_dev",
     "scl_merge_shards_dev", "scl_icp", "scl_set_profiling", "scl_stage_time", "scl_set_knn_mode", "scl_knn_stats",
+    "scl_knn_batch_dev", "scl_merge_topk_dev", "scl_scdist_owned_dev", "scl_combine_owned_dev",
 ]
 
 
@@ -87,6 +88,11 @@ def load_library():
     lib.scl_query_batch_dev.argtypes = lib.scl_query_batch.argtypes
     lib.scl_merge_shards_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.POINTER(SclBatchResult)]
+    lib.scl_knn_batch_dev.argtypes = [C.c_void_p, C.POINTER(SclBatchQuery), C.c_void_p, C.c_void_p]
+    lib.scl_merge_topk_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.scl_scdist_owned_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.scl_combine_owned_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_uint64, C.POINTER(SclBatchResult)]
     lib.scl_set_knn_mode.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.scl_knn_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     lib.scl_set_profiling.argtypes = [C.c_void_p, C.c_int]
@@ -278,6 +284,24 @@ class ScanContextB200:
         ms, n = C.c_double(), C.c_int()
         self._ck(self.lib.scl_stage_time(self.h, stage, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    # ---- two-phase multi-GPU exchange (include/scl_engine.h) -------------------------------
+    def knn_batch_dev(self, q_desc_dev, Q, K, n_db, metric, ids_dev, d2_dev):
+        q = SclBatchQuery(_ptr(q_desc_dev), None, Q, K, n_db, metric)
+        self._ck(self.lib.scl_knn_batch_dev(self.h, C.byref(q), _ptr(ids_dev), _ptr(d2_dev)))
+
+    def merge_topk_dev(self, world, Q, K, ids_base, d2_base, rank_stride_bytes, out_ids, out_d2):
+        self._ck(self.lib.scl_merge_topk_dev(self.h, world, Q, K, _ptr(ids_base), _ptr(d2_base), rank_stride_bytes,
+                                             _ptr(out_ids), _ptr(out_d2)))
+
+    def scdist_owned_dev(self, q_desc_dev, Q, K, cand_ids_dev, dist_dev, shift_dev):
+        self._ck(self.lib.scl_scdist_owned_dev(self.h, _ptr(q_desc_dev), None, Q, K, _ptr(cand_ids_dev), _ptr(dist_dev), _ptr(shift_dev)))
+
+    def combine_owned_dev(self, world, Q, K, cand_ids, dist_base, shift_base, rank_stride_bytes, out):
+        r = SclBatchResult(*[_ptr(out.get(k)) for k in
+                             ("cand_ids", "cand_d2", "cand_dist", "cand_shift", "best_id", "best_dist", "best_shift")])
+        self._ck(self.lib.scl_combine_owned_dev(self.h, world, Q, K, None, _ptr(cand_ids), _ptr(dist_base), _ptr(shift_base),
+                                                rank_stride_bytes, C.byref(r)))
 
     # ---- geometric verification (distributedMapping.h:1108-1132) ---------------------------
     def icp(self, src, tgt, max_corr_dist=100.0, max_iterations=50, trans_eps=1e-6, fitness_eps=1e-6):

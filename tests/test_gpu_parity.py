@@ -392,3 +392,48 @@ def test_tensor_core_knn_fallback_on_ties(eng_mod):
         assert np.array_equal(_bits(got["cand_d2"]), _bits(exp["cand_d2"]))
         assert np.array_equal(got["best_id"], exp["best_id"]) and np.array_equal(got["best_shift"], exp["best_shift"])
     assert e.knn_stats()["fallback_queries"] > 0
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_two_phase_exchange_equals_unsharded(eng_mod, world):
+    """The N>1 path bench.py runs (kNN per shard -> gather (id,d2) -> global top-K -> SC distance on the owned
+    candidates only -> gather (dist,shift) -> combine), emulated with `world` engines on one GPU."""
+    from scl_slam_b200 import sharding
+    n, nq, K = 5003, 80, 10
+    db = synth.desc_db(n, seed=83)
+    q = synth.desc_queries(db, nq, seed=84)[0]
+    dbn = db.numpy()
+    dbn[21] = dbn[20]
+    full = eng_mod.ScanContextB200(numCandidates=K)
+    full.insert_batch(dbn)
+    exp = full.query_batch(q_desc=q.numpy(), K=K, n_db=n - 101)
+    dev = torch.device("cuda:0")
+    qd = q.to(dev).contiguous()
+    QK = nq * K
+    gath1 = torch.empty((world, QK * 8), dtype=torch.uint8, device=dev)
+    gath2 = torch.empty((world, QK * 12), dtype=torch.uint8, device=dev)
+    engines = []
+    for r in range(world):
+        e = eng_mod.ScanContextB200(numCandidates=K)
+        e.set_shard(r, world)
+        e.insert_batch(dbn[sharding.local_rows(n, r, world)])
+        e.knn_batch_dev(qd, nq, K, sharding.local_search_bound(n - 101, r, world), 0,
+                        gath1[r, :QK * 4].view(torch.int32), gath1[r, QK * 4:].view(torch.float32))
+        engines.append(e)
+    torch.cuda.synchronize()
+    m_ids = torch.empty((nq, K), dtype=torch.int32, device=dev)
+    m_d2 = torch.empty((nq, K), dtype=torch.float32, device=dev)
+    engines[0].merge_topk_dev(world, nq, K, gath1, gath1[:, QK * 4:], QK * 8, m_ids, m_d2)
+    torch.cuda.synchronize()
+    for r, e in enumerate(engines):
+        e.scdist_owned_dev(qd, nq, K, m_ids, gath2[r, :QK * 8].view(torch.float64), gath2[r, QK * 8:].view(torch.int32))
+    torch.cuda.synchronize()
+    out = dict(cand_dist=torch.empty((nq, K), dtype=torch.float64, device=dev), cand_shift=torch.empty((nq, K), dtype=torch.int32, device=dev),
+               best_id=torch.empty(nq, dtype=torch.int32, device=dev), best_dist=torch.empty(nq, dtype=torch.float64, device=dev),
+               best_shift=torch.empty(nq, dtype=torch.int32, device=dev))
+    engines[0].combine_owned_dev(world, nq, K, m_ids, gath2, gath2[:, QK * 8:], QK * 12, out)
+    torch.cuda.synchronize()
+    assert np.array_equal(m_ids.cpu().numpy(), exp["cand_ids"])
+    assert np.array_equal(_bits(m_d2.cpu().numpy()), _bits(exp["cand_d2"]))
+    for k in out:
+        assert np.array_equal(out[k].cpu().numpy(), exp[k], equal_nan=True), k
