@@ -191,6 +191,21 @@ void scl_default_icp_params(scl_icp_params* p);
 int scl_icp(scl_engine* e, const void* src, int n_src, const void* tgt, int n_tgt, int stride_bytes,
             const scl_icp_params* p, float* T_out, float* fitness, int* converged, int* iterations);
 
+/* replaces the RANSAC + SVD block of geometricVerificationService, distributedMapping.h:1211-1243 (the inter-robot
+ * verification): nearest-neighbour correspondences src -> tgt, max_iterations three-point hypotheses scored by the
+ * inlier threshold, closed-form fit on the inliers of the best one, success iff inliers >= min_inlier_ratio * corr.
+ * PCL's sampler is random (and stops early); here every hypothesis is evaluated and the seed makes the result
+ * reproducible. T_out: row-major 4x4. */
+typedef struct {
+    int max_iterations;       /* ransacMaxIter 1000, distributedMapping.h:187 */
+    double inlier_threshold;  /* ransacOutlierTreshold 0.25 m, :188 */
+    double min_inlier_ratio;  /* inlierTreshold 0.45, :189 */
+    unsigned seed;
+} scl_ransac_params;
+void scl_default_ransac_params(scl_ransac_params* p);
+int scl_verify_ransac(scl_engine* e, const void* src, int n_src, const void* tgt, int n_tgt, int stride_bytes,
+                      const scl_ransac_params* p, float* T_out, int* n_corr, int* n_inliers, int* success);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <random>
 #include <unordered_map>
 #include <vector>
 
@@ -194,6 +195,60 @@ int sco_icp(const float* src, int n_src, const float* tgt, int n_tgt, int stride
     for (int i = 0; i < 16; i++) T_out[i] = (float)final_T[i];
     *converged = conv ? 1 : 0;
     return iterations;
+}
+
+/* RANSAC + SVD verification as geometricVerificationService drives PCL (distributedMapping.h:1211-1243):
+ * CorrespondenceEstimation (nearest target of every source point), CorrespondenceRejectorSampleConsensus
+ * (pcl::RandomSampleConsensus over SampleConsensusModelRegistration: 3-point samples, inlier = residual <= threshold,
+ * adaptive stop k = log(1-0.99)/log(1-w^3), at most max_iter), TransformationEstimationSVD on the inliers,
+ * success iff inliers >= ratio * correspondences. PARITY UNPINNED (PCL not vendored; its sampler is random):
+ * the GPU result is compared statistically (same verdict, pose and inlier ratio within tolerance). */
+int sco_verify_ransac(const float* src, int n_src, const float* tgt, int n_tgt, int stride, int max_iter, double thr, double ratio,
+                      unsigned seed, float* T_out, int* n_corr, int* n_inliers, int* success)
+{
+    for (int i = 0; i < 16; i++) T_out[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+    *n_corr = 0; *n_inliers = 0; *success = 0;
+    if (n_src < 3 || n_tgt < 1) return 0;
+    std::vector<P3> s = load(src, n_src, stride), t = load(tgt, n_tgt, stride);
+    GridNN nn; nn.build(t, 1.0);
+    std::vector<P3> b(n_src);
+    for (int i = 0; i < n_src; i++) { double d2; b[i] = t[nn.nearest(s[i], &d2)]; }
+    std::mt19937 rng(seed);
+    std::uniform_int_distribution<int> pick(0, n_src - 1);
+    const double thr2 = thr * thr;
+    int best_cnt = 0; double bestT[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    double k = max_iter; int it = 0;
+    while (it < k && it < max_iter) {
+        int i0 = pick(rng), i1 = pick(rng), i2 = pick(rng);
+        ++it;
+        if (i0 == i1 || i0 == i2 || i1 == i2) continue;
+        std::vector<P3> pa{s[i0], s[i1], s[i2]}, pb{b[i0], b[i1], b[i2]};
+        double T[16];
+        rigid_fit(pa, pb, T);
+        int cnt = 0;
+        for (int i = 0; i < n_src; i++) {
+            const double x = T[0] * s[i].x + T[1] * s[i].y + T[2] * s[i].z + T[3] - b[i].x;
+            const double y = T[4] * s[i].x + T[5] * s[i].y + T[6] * s[i].z + T[7] - b[i].y;
+            const double z = T[8] * s[i].x + T[9] * s[i].y + T[10] * s[i].z + T[11] - b[i].z;
+            cnt += (x * x + y * y + z * z <= thr2);
+        }
+        if (cnt > best_cnt) {
+            best_cnt = cnt; std::memcpy(bestT, T, sizeof(T));
+            const double w = (double)cnt / n_src, p3 = std::max(1e-12, std::min(1.0 - 1e-12, w * w * w));
+            k = std::log(1.0 - 0.99) / std::log(1.0 - p3);
+        }
+    }
+    std::vector<P3> ia, ib;
+    for (int i = 0; i < n_src; i++) {
+        const double x = bestT[0] * s[i].x + bestT[1] * s[i].y + bestT[2] * s[i].z + bestT[3] - b[i].x;
+        const double y = bestT[4] * s[i].x + bestT[5] * s[i].y + bestT[6] * s[i].z + bestT[7] - b[i].y;
+        const double z = bestT[8] * s[i].x + bestT[9] * s[i].y + bestT[10] * s[i].z + bestT[11] - b[i].z;
+        if (x * x + y * y + z * z <= thr2) { ia.push_back(s[i]); ib.push_back(b[i]); }
+    }
+    *n_corr = n_src; *n_inliers = (int)ia.size();
+    if (ia.size() >= 3) { double T[16]; rigid_fit(ia, ib, T); for (int i = 0; i < 16; i++) T_out[i] = (float)T[i]; }
+    *success = ((double)ia.size() >= ratio * n_src) ? 1 : 0;
+    return it;
 }
 
 void sco_nn(const float* src, int n_src, const float* tgt, int n_tgt, int stride, int32_t* idx, float* d2)

@@ -94,6 +94,9 @@ float sco_atanf_port(float x);
 int sco_icp(const float* src, int n_src, const float* tgt, int n_tgt, int stride_floats,
             double max_corr_dist, int max_iter, double trans_eps, double fit_eps,
             float* T_out, float* fitness, int* converged);
+/* RANSAC + SVD verification restatement (distributedMapping.h:1211-1243). Returns hypotheses tried. */
+int sco_verify_ransac(const float* src, int n_src, const float* tgt, int n_tgt, int stride_floats, int max_iter, double inlier_thr,
+                      double min_inlier_ratio, unsigned seed, float* T_out, int* n_corr, int* n_inliers, int* success);
 /* exact nearest neighbour (brute force) — squared distances and indices */
 void sco_nn(const float* src, int n_src, const float* tgt, int n_tgt, int stride_floats,
             int32_t* idx, float* d2);

@@ -26,6 +26,7 @@
 #include "common.cuh"
 
 #include <cmath>
+#include <vector>
 
 namespace {
 
@@ -280,6 +281,134 @@ void mul4(const double A[16], const double B[16], double C[16])
     for (int i = 0; i < 16; i++) C[i] = t[i];
 }
 
+// ---- closed-form rigid fit (Horn 1987): rotation = eigenvector of the largest eigenvalue of a symmetric 4x4 built
+// from the cross-covariance S = sum (a - ca)(b - cb)^T; cyclic Jacobi. Used on the device for the 3-point RANSAC
+// hypotheses and on the host for the final fit on the inliers (pcl::registration::TransformationEstimationSVD,
+// distributedMapping.h:1228-1230, has the same optimum).
+__host__ __device__ inline void horn_fit(const double S[9], const double ca[3], const double cb[3], double T[12])
+{
+    double N[4][4] = {
+        {S[0] + S[4] + S[8], S[5] - S[7], S[6] - S[2], S[1] - S[3]},
+        {S[5] - S[7], S[0] - S[4] - S[8], S[1] + S[3], S[6] + S[2]},
+        {S[6] - S[2], S[1] + S[3], -S[0] + S[4] - S[8], S[5] + S[7]},
+        {S[1] - S[3], S[6] + S[2], S[5] + S[7], -S[0] - S[4] + S[8]}};
+    double V[4][4];
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) V[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 24; sweep++) {
+        double off = 0;
+        for (int i = 0; i < 4; i++) for (int j = i + 1; j < 4; j++) off += N[i][j] * N[i][j];
+        if (off < 1e-280) break;
+        for (int p = 0; p < 4; p++)
+            for (int q = p + 1; q < 4; q++) {
+                if (fabs(N[p][q]) < 1e-300) continue;
+                const double theta = (N[q][q] - N[p][p]) / (2 * N[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
+                const double c = 1 / sqrt(t * t + 1), sn = t * c;
+                for (int k = 0; k < 4; k++) { const double akp = N[k][p], akq = N[k][q]; N[k][p] = c * akp - sn * akq; N[k][q] = sn * akp + c * akq; }
+                for (int k = 0; k < 4; k++) { const double apk = N[p][k], aqk = N[q][k]; N[p][k] = c * apk - sn * aqk; N[q][k] = sn * apk + c * aqk; }
+                for (int k = 0; k < 4; k++) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - sn * vkq; V[k][q] = sn * vkp + c * vkq; }
+            }
+    }
+    int best = 0;
+    for (int i = 1; i < 4; i++) if (N[i][i] > N[best][best]) best = i;
+    double qw = V[0][best], qx = V[1][best], qy = V[2][best], qz = V[3][best];
+    const double nq = sqrt(qw * qw + qx * qx + qy * qy + qz * qz);
+    qw /= nq; qx /= nq; qy /= nq; qz /= nq;
+    const double R[9] = {1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw),
+                         2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw),
+                         2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)};
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) T[r * 4 + c] = R[r * 3 + c];
+        T[r * 4 + 3] = cb[r] - (R[r * 3] * ca[0] + R[r * 3 + 1] * ca[1] + R[r * 3 + 2] * ca[2]);
+    }
+}
+
+__device__ inline unsigned rng_hash(unsigned x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+// One RANSAC hypothesis per CTA (pcl::registration::CorrespondenceRejectorSampleConsensus, distributedMapping.h:1217-1225):
+// three distinct correspondences -> rigid transform -> inlier count over all correspondences.
+__global__ void __launch_bounds__(128) ransac_hyp_kernel(const float4* __restrict__ src, const float4* __restrict__ tgt, const int* __restrict__ nn,
+                                                         int n, unsigned seed, float thr2, float* __restrict__ hyp_T /* [H][12] */,
+                                                         int* __restrict__ hyp_inliers)
+{
+    __shared__ float sT[12];
+    __shared__ int s_cnt;
+    const int h = blockIdx.x;
+    if (threadIdx.x == 0) {
+        s_cnt = 0;
+        int pick[3];
+        unsigned st = rng_hash(seed ^ (0x9e3779b9u * (unsigned)(h + 1)));
+        for (int k = 0; k < 3; k++) {
+            while (true) {
+                st = rng_hash(st + 0x632be5abu);
+                const int c = (int)(st % (unsigned)n);
+                bool dup = false;
+                for (int j = 0; j < k; j++) dup |= pick[j] == c;
+                if (!dup) { pick[k] = c; break; }
+            }
+        }
+        double ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0}, a[3][3], b[3][3];
+        for (int k = 0; k < 3; k++) {
+            const float4 p = src[pick[k]], q = tgt[nn[pick[k]]];
+            a[k][0] = p.x; a[k][1] = p.y; a[k][2] = p.z; b[k][0] = q.x; b[k][1] = q.y; b[k][2] = q.z;
+            for (int d = 0; d < 3; d++) { ca[d] += a[k][d] / 3.0; cb[d] += b[k][d] / 3.0; }
+        }
+        double S[9] = {0};
+        for (int k = 0; k < 3; k++)
+            for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) S[r * 3 + c] += (a[k][r] - ca[r]) * (b[k][c] - cb[c]);
+        double T[12];
+        horn_fit(S, ca, cb, T);
+        for (int i = 0; i < 12; i++) { sT[i] = (float)T[i]; hyp_T[(size_t)h * 12 + i] = (float)T[i]; }
+    }
+    __syncthreads();
+    int cnt = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float4 p = src[i], q = __ldg(&tgt[nn[i]]);
+        const float x = fmaf(sT[0], p.x, fmaf(sT[1], p.y, fmaf(sT[2], p.z, sT[3]))) - q.x;
+        const float y = fmaf(sT[4], p.x, fmaf(sT[5], p.y, fmaf(sT[6], p.z, sT[7]))) - q.y;
+        const float z = fmaf(sT[8], p.x, fmaf(sT[9], p.y, fmaf(sT[10], p.z, sT[11]))) - q.z;
+        cnt += (fmaf(x, x, fmaf(y, y, z * z)) <= thr2) ? 1 : 0;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) hyp_inliers[h] = s_cnt;
+}
+
+// centroids + cross-covariance sums over the inliers of transform T (15 FP64 sums + count), warp-reduced
+__global__ void __launch_bounds__(256) inlier_stats_kernel(const float4* __restrict__ src, const float4* __restrict__ tgt, const int* __restrict__ nn,
+                                                           int n, const float* __restrict__ T, float thr2, double* __restrict__ acc /* [16] */)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[16];
+#pragma unroll
+    for (int a = 0; a < 16; a++) v[a] = 0.0;
+    if (i < n) {
+        const float4 p = src[i], q = __ldg(&tgt[nn[i]]);
+        const float x = fmaf(T[0], p.x, fmaf(T[1], p.y, fmaf(T[2], p.z, T[3]))) - q.x;
+        const float y = fmaf(T[4], p.x, fmaf(T[5], p.y, fmaf(T[6], p.z, T[7]))) - q.y;
+        const float z = fmaf(T[8], p.x, fmaf(T[9], p.y, fmaf(T[10], p.z, T[11]))) - q.z;
+        if (fmaf(x, x, fmaf(y, y, z * z)) <= thr2) {
+            const double a[3] = {p.x, p.y, p.z}, b[3] = {q.x, q.y, q.z};
+            for (int d = 0; d < 3; d++) { v[d] = a[d]; v[3 + d] = b[d]; }
+            for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) v[6 + r * 3 + c] = a[r] * b[c];
+            v[15] = 1.0;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 16; a++) {
+        double x = v[a];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        if ((threadIdx.x & 31) == 0 && x != 0.0) atomicAdd(&acc[a], x);
+    }
+}
+
 } // namespace
 
 extern "C" int scl_icp(scl_engine* e, const void* src, int n_src, const void* tgt, int n_tgt, int stride_bytes,
@@ -377,5 +506,84 @@ extern "C" int scl_icp(scl_engine* e, const void* src, int n_src, const void* tg
     for (int i = 0; i < 16; i++) T_out[i] = (float)Tf[i];
     *converged = conv ? 1 : 0;
     if (iterations) *iterations = it;
+    return SCL_OK;
+}
+
+extern "C" void scl_default_ransac_params(scl_ransac_params* p)
+{
+    p->max_iterations = 1000; p->inlier_threshold = 0.25; p->min_inlier_ratio = 0.45; p->seed = 1u;   /* distributedMapping.h:187-189 */
+}
+
+extern "C" int scl_verify_ransac(scl_engine* e, const void* src, int n_src, const void* tgt, int n_tgt, int stride_bytes,
+                                 const scl_ransac_params* prm, float* T_out, int* n_corr, int* n_inliers, int* success)
+{
+    LOCK();
+    if (!prm || !T_out || !n_corr || !n_inliers || !success) FAIL(SCL_ERR_INVALID, "null argument");
+    if (n_src < 0 || n_tgt < 0 || stride_bytes < 12 || (stride_bytes & 3) || prm->max_iterations < 1) FAIL(SCL_ERR_INVALID, "bad arguments");
+    for (int i = 0; i < 16; i++) T_out[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+    *n_corr = 0; *n_inliers = 0; *success = 0;
+    if (n_src < 3 || n_tgt < 1) return SCL_OK;
+    if (!src || !tgt) FAIL(SCL_ERR_INVALID, "null cloud");
+    const size_t sb = (size_t)(n_src - 1) * stride_bytes + 12, tb = (size_t)(n_tgt - 1) * stride_bytes + 12;
+    CK(e->icp_raw.ensure((sb > tb ? sb : tb) + 16));
+    CK(e->icp_src.ensure((size_t)n_src * 16));
+    CK(e->icp_tgt.ensure((size_t)n_tgt * 16));
+    CK(cudaMemcpyAsync(e->icp_raw.p, src, sb, cudaMemcpyHostToDevice, e->stream));
+    pack_xyz_kernel<<<(n_src + 255) / 256, 256, 0, e->stream>>>(e->icp_raw.as<unsigned char>(), n_src, stride_bytes, e->icp_src.as<float4>());
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpyAsync(e->icp_raw.p, tgt, tb, cudaMemcpyHostToDevice, e->stream));
+    pack_xyz_kernel<<<(n_tgt + 255) / 256, 256, 0, e->stream>>>(e->icp_raw.as<unsigned char>(), n_tgt, stride_bytes, e->icp_tgt.as<float4>());
+    CK(cudaGetLastError());
+    Grid fine, coarse;
+    int rc = build_grid(e, e->icp_tgt.as<float4>(), n_tgt, 1.0f,
+                        GridBufs{&e->icp_grid[0][0], &e->icp_grid[0][1], &e->icp_grid[0][2], &e->icp_grid[0][3], &e->icp_grid[0][4]}, &fine);
+    if (rc) return rc;
+    rc = build_grid(e, e->icp_tgt.as<float4>(), n_tgt, 8.0f,
+                    GridBufs{&e->icp_grid[1][0], &e->icp_grid[1][1], &e->icp_grid[1][2], &e->icp_grid[1][3], &e->icp_grid[1][4]}, &coarse);
+    if (rc) return rc;
+    /* initial matching (:1211-1215): nearest target point of every source point, no distance gate */
+    const int H = prm->max_iterations;
+    CK(e->icp_nn.ensure((size_t)n_src * 8 + (size_t)H * 13 * 4));
+    int* d_nn = e->icp_nn.as<int>();
+    float* d_nnd2 = reinterpret_cast<float*>(d_nn + n_src);
+    float* d_hypT = d_nnd2 + n_src;
+    int* d_hypI = reinterpret_cast<int*>(d_hypT + (size_t)H * 12);
+    CK(e->icp_acc.ensure(kAcc * 8 + 12 * 4));
+    double* d_acc = e->icp_acc.as<double>();
+    float* d_T = reinterpret_cast<float*>(d_acc + kAcc);
+    const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    CK(cudaMemcpyAsync(d_T, ident, sizeof(ident), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemsetAsync(d_acc, 0, kAcc * 8, e->stream));
+    icp_iter_kernel<<<(n_src + 255) / 256, 256, 0, e->stream>>>(e->icp_src.as<float4>(), n_src, e->icp_tgt.as<float4>(), n_tgt, fine, coarse, d_T,
+                                                                 3.0e38f, d_acc, d_nn, d_nnd2);
+    CK(cudaGetLastError());
+    /* RANSAC (:1217-1225): H three-point hypotheses, inlier threshold on the residual after the hypothesis */
+    const float thr2 = (float)(prm->inlier_threshold * prm->inlier_threshold);
+    ransac_hyp_kernel<<<H, 128, 0, e->stream>>>(e->icp_src.as<float4>(), e->icp_tgt.as<float4>(), d_nn, n_src, prm->seed, thr2, d_hypT, d_hypI);
+    CK(cudaGetLastError());
+    std::vector<int> inl(H);
+    CK(cudaMemcpyAsync(inl.data(), d_hypI, (size_t)H * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    int best = 0;
+    for (int h = 1; h < H; h++) if (inl[h] > inl[best]) best = h;
+    *n_corr = n_src; *n_inliers = inl[best];
+    /* SVD on the inliers of the best hypothesis (:1228-1230) */
+    CK(cudaMemcpyAsync(d_T, d_hypT + (size_t)best * 12, 12 * 4, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemsetAsync(d_acc, 0, kAcc * 8, e->stream));
+    inlier_stats_kernel<<<(n_src + 255) / 256, 256, 0, e->stream>>>(e->icp_src.as<float4>(), e->icp_tgt.as<float4>(), d_nn, n_src, d_T, thr2, d_acc);
+    CK(cudaGetLastError());
+    double acc[16];
+    CK(cudaMemcpyAsync(acc, d_acc, sizeof(acc), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (acc[15] >= 3.0) {
+        const double m = acc[15];
+        const double ca[3] = {acc[0] / m, acc[1] / m, acc[2] / m}, cb[3] = {acc[3] / m, acc[4] / m, acc[5] / m};
+        double S[9];
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) S[r * 3 + c] = acc[6 + r * 3 + c] - m * ca[r] * cb[c];
+        double T[12];
+        horn_fit(S, ca, cb, T);
+        for (int i = 0; i < 12; i++) T_out[i] = (float)T[i];
+    }
+    *success = ((double)*n_inliers >= prm->min_inlier_ratio * (double)*n_corr) ? 1 : 0;   /* :1238 */
     return SCL_OK;
 }

@@ -26,7 +26,7 @@ EXPORTS = [
     "scl_insert", "scl_insert_batch", "scl_insert_batch_dev", "scl_get_index", "scl_size", "scl_get_descriptor",
     "scl_get_ring_key", "scl_query_intra", "scl_query_inter", "scl_query_batch", "scl_query_batch_dev",
     "scl_merge_shards_dev", "scl_icp", "scl_set_profiling", "scl_stage_time", "scl_set_knn_mode", "scl_knn_stats",
-    "scl_knn_batch_dev", "scl_merge_topk_dev", "scl_scdist_owned_dev", "scl_combine_owned_dev",
+    "scl_default_ransac_params", "scl_verify_ransac", "scl_knn_batch_dev", "scl_merge_topk_dev", "scl_scdist_owned_dev", "scl_combine_owned_dev",
 ]
 
 
@@ -50,6 +50,10 @@ class SclBatchResult(C.Structure):
 class SclIcpParams(C.Structure):
     _fields_ = [("max_corr_dist", C.c_double), ("max_iterations", C.c_int), ("trans_eps", C.c_double),
                 ("fitness_eps", C.c_double)]
+
+
+class SclRansacParams(C.Structure):
+    _fields_ = [("max_iterations", C.c_int), ("inlier_threshold", C.c_double), ("min_inlier_ratio", C.c_double), ("seed", C.c_uint)]
 
 
 _lib = None
@@ -93,6 +97,8 @@ def load_library():
     lib.scl_scdist_owned_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.scl_combine_owned_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_uint64, C.POINTER(SclBatchResult)]
+    lib.scl_verify_ransac.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(SclRansacParams),
+                                      C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.scl_set_knn_mode.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.scl_knn_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     lib.scl_set_profiling.argtypes = [C.c_void_p, C.c_int]
@@ -315,3 +321,17 @@ class ScanContextB200:
         self._ck(self.lib.scl_icp(self.h, s.ctypes.data, ns, t.ctypes.data, nt, stride, C.byref(p), T.ctypes.data,
                                   C.byref(fit), C.byref(conv), C.byref(it)))
         return T.reshape(4, 4), fit.value, bool(conv.value), it.value
+
+    def verify_ransac(self, src, tgt, max_iterations=1000, inlier_threshold=0.25, min_inlier_ratio=0.45, seed=1):
+        """RANSAC + SVD verification (geometricVerificationService, distributedMapping.h:1211-1243).
+        Returns (T 4x4, n_correspondences, n_inliers, success)."""
+        s, ns, stride = _cloud(src)
+        t, nt, stride_t = _cloud(tgt)
+        if stride != stride_t:
+            raise ValueError("src and tgt must share a point stride")
+        p = SclRansacParams(max_iterations, inlier_threshold, min_inlier_ratio, seed)
+        T = np.empty(16, np.float32)
+        nc, ni, ok = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.lib.scl_verify_ransac(self.h, s.ctypes.data, ns, t.ctypes.data, nt, stride, C.byref(p), T.ctypes.data,
+                                            C.byref(nc), C.byref(ni), C.byref(ok)))
+        return T.reshape(4, 4), nc.value, ni.value, bool(ok.value)

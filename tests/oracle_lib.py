@@ -73,6 +73,9 @@ def _load(path):
         lib.sco_icp.restype = C.c_int
         lib.sco_icp.argtypes = [_f32p, C.c_int, _f32p, C.c_int, C.c_int, C.c_double, C.c_int,
                                 C.c_double, C.c_double, _f32p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        lib.sco_verify_ransac.restype = C.c_int
+        lib.sco_verify_ransac.argtypes = [_f32p, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_uint, _f32p,
+                                          C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         lib.sco_nn.argtypes = [_f32p, C.c_int, _f32p, C.c_int, C.c_int, _i32p, _f32p]
         lib.sco_voxel_grid.restype = C.c_int
         lib.sco_voxel_grid.argtypes = [_f32p, C.c_int, C.c_int, C.c_float, _f32p]
@@ -227,6 +230,19 @@ def icp(src, tgt, max_corr_dist=100.0, max_iter=50, trans_eps=1e-6, fit_eps=1e-6
     it = lib.sco_icp(src.reshape(-1), ns, tgt.reshape(-1), nt, st, max_corr_dist, max_iter, trans_eps, fit_eps,
                      T, C.byref(fit), C.byref(conv))
     return T.reshape(4, 4), fit.value, bool(conv.value), it
+
+
+def verify_ransac(src, tgt, max_iter=1000, inlier_thr=0.25, min_inlier_ratio=0.45, seed=1):
+    """RANSAC + SVD restatement (distributedMapping.h:1211-1243). Returns (T, n_corr, n_inliers, success)."""
+    lib = get_lib("port")
+    src, ns, st = _cloud(src)
+    tgt, nt, st2 = _cloud(tgt)
+    assert st == st2
+    T = np.empty(16, np.float32)
+    nc, ni, ok = C.c_int(), C.c_int(), C.c_int()
+    lib.sco_verify_ransac(src.reshape(-1), ns, tgt.reshape(-1), nt, st, max_iter, inlier_thr, min_inlier_ratio, seed, T,
+                          C.byref(nc), C.byref(ni), C.byref(ok))
+    return T.reshape(4, 4), nc.value, ni.value, bool(ok.value)
 
 
 def nn_bruteforce(src, tgt):

@@ -437,3 +437,29 @@ def test_two_phase_exchange_equals_unsharded(eng_mod, world):
     assert np.array_equal(_bits(m_d2.cpu().numpy()), _bits(exp["cand_d2"]))
     for k in out:
         assert np.array_equal(out[k].cpu().numpy(), exp[k], equal_nan=True), k
+
+
+# ---------------------------------------------------------------- a15: RANSAC + SVD verification (inter-robot)
+@pytest.mark.parametrize("seed", [2, 3])
+def test_ransac_verification_vs_oracle(eng_mod, seed):
+    """geometricVerificationService (distributedMapping.h:1211-1243). PCL's sampler is random, so parity is
+    statistical: same verdict, poses within 5 cm / 0.5 deg of each other and of the planted offset, inlier
+    ratios within 0.05; and a bad pair is rejected by both."""
+    import oracle_lib
+    src, tgt, yaw, t = _icp_pair(seed, yaw=0.02, t=(0.12, -0.08, 0.03))      # within the 0.25 m inlier threshold: a verifiable loop
+    e = eng_mod.ScanContextB200()
+    # nearest-neighbour correspondences of a displaced cloud are only ~50 % right, so the verdict is taken at a 0.3 ratio
+    T, nc, ni, ok = e.verify_ransac(src, tgt, min_inlier_ratio=0.3)
+    To, nco, nio, oko = oracle_lib.verify_ransac(src, tgt, min_inlier_ratio=0.3)
+    assert nc == nco == src.shape[0]
+    assert ok and oko
+    assert abs(ni / nc - nio / nco) < 0.08, (ni, nio, nc)
+    assert np.linalg.norm(T[:3, 3] - To[:3, 3]) < 0.08 and _rot_angle(T[:3, :3], To[:3, :3]) < 0.01
+    assert np.linalg.norm(T[:3, 3] - t) < 0.12 and abs(np.arctan2(T[1, 0], T[0, 0]) - yaw) < 0.02
+    T2, nc2, ni2, ok2 = e.verify_ransac(src, tgt, min_inlier_ratio=0.3, seed=1)                     # reproducible for a given seed
+    assert np.array_equal(T, T2) and ni == ni2
+    # a pair that does not match: the source pushed 30 m away -> few inliers, rejected by both
+    far = src.copy(); far[:, 0] += 30.0
+    _, _, ni_bad, ok_bad = e.verify_ransac(far, tgt, min_inlier_ratio=0.75)
+    _, _, nio_bad, oko_bad = oracle_lib.verify_ransac(far, tgt, min_inlier_ratio=0.75)
+    assert not ok_bad and not oko_bad
