@@ -130,6 +130,25 @@ public:
 		return rc == SCL_OK && converged != 0;
 	}
 
+	/* inter-robot verification for geometricVerificationService (distributedMapping.h:1211-1243): nearest-neighbour
+	 * correspondences, RANSAC over three-point hypotheses, SVD on the inliers. Returns the `success` of :1238;
+	 * T is the row-major 4x4 `transform` of :1228-1230. */
+	bool ransacVerify(const pcl::PointCloud<pcl::PointXYZI>& source, const pcl::PointCloud<pcl::PointXYZI>& target,
+		float T[16], int ransacMaxIter = 1000, double ransacOutlierTreshold = 0.25, double inlierTreshold = 0.45,
+		int* numCorrespondences = nullptr, int* numInliers = nullptr, unsigned seed = 1)
+	{
+		scl_ransac_params p;
+		p.max_iterations = ransacMaxIter; p.inlier_threshold = ransacOutlierTreshold; p.min_inlier_ratio = inlierTreshold; p.seed = seed;
+		int nc = 0, ni = 0, ok = 0;
+		const int rc = scl_verify_ransac(engine_, source.points.empty() ? nullptr : &source.points[0], (int)source.points.size(),
+			target.points.empty() ? nullptr : &target.points[0], (int)target.points.size(), (int)sizeof(pcl::PointXYZI),
+			&p, T, &nc, &ni, &ok);
+		check(rc, "ransacVerify");
+		if(numCorrespondences) *numCorrespondences = nc;
+		if(numInliers) *numInliers = ni;
+		return rc == SCL_OK && ok != 0;
+	}
+
 	scl_engine* engine() { return engine_; }
 
 private:
