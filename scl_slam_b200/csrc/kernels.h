@@ -44,6 +44,26 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
                               int metric, int id_mul, int id_add, KnnTcWorkspace ws, int32_t* out_ids, float* out_d2,
                               int32_t* fail_list, int* fail_count, cudaStream_t stream);
 
+// K3 on tcgen05, second generation (k3_knn_tc2.cu): BF16x3 prefilter fed by TMA from a pre-split key image
+// (scl_launch_key_image, 128-key tiles in the tcgen05 shared-memory layout), union-bound thresholds, exact re-rank.
+struct KnnTc2Workspace {
+    float* prop_s;       // [Qc][ranges][K']   (Qc = min(Q, scl_knn_tc2_max_batch()))
+    int32_t* prop_idx;   // [Qc][ranges][K']
+    float* prop_cut;     // [Qc][ranges]
+    int* g_thr;          // [Qc] union bounds, followed by [Qc][ranges] published range minima
+    float* err_probe;    // null, or one float raised to the largest |prefilter score error| / eps seen (tests)
+    size_t capacity;     // in proposal entries
+};
+bool scl_knn_tc2_supported(int R);
+int scl_knn_tc2_ranges(int Q);
+int scl_knn_tc2_max_batch();
+int scl_knn_tc2_kprime();
+size_t scl_knn_tc2_image_bytes(int R, int n_keys);
+cudaError_t scl_launch_key_image(const float* keys, const float* knorm, int k_lo, int k_hi, int R, unsigned char* img, cudaStream_t stream);
+cudaError_t scl_launch_knn_tc2(const float* qkeys, int Q, const float* keys, const unsigned char* img, const float* kn2max, int n_db, int R, int K,
+                               int metric, int id_mul, int id_add, KnnTc2Workspace ws, int32_t* out_ids, float* out_d2,
+                               int32_t* fail_list, int* fail_count, cudaStream_t stream);
+
 // K4: shift-aligned column-cosine distance for every (query, candidate) + winner scan. See k4_scdist.cu.
 //  q_desc [Q][R*S] or nullptr (then queries are db entries q_local[i]); cand_local [Q][K] local keys (-1 = none);
 //  cand_ids [Q][K] reported ids (for the self-skip rule against q_ids).
