@@ -197,17 +197,17 @@ int knn_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int
         StageTimer st(e, 1);
         if (use_tc2) {
             const int Qc = Q < scl_knn_tc2_max_batch() ? Q : scl_knn_tc2_max_batch();
-            const int ranges = scl_knn_tc2_ranges(Qc), kp = scl_knn_tc2_kprime();
-            const size_t ncand = (size_t)Qc * ranges * kp;
-            CK(e->tc_prop_s.ensure(ncand * 4)); CK(e->tc_prop_idx.ensure(ncand * 4)); CK(e->tc_prop_cut.ensure((size_t)Qc * ranges * 4));
+            const int ranges = scl_knn_tc2_ranges(Qc);
+            const size_t pairs = (size_t)Qc * ranges;
+            CK(e->tc_prop_s.ensure(pairs * scl_knn_tc2_queue_bytes())); CK(e->tc_prop_cut.ensure(pairs * 4));
             CK(e->tc_fail_list.ensure((size_t)Q * 4)); CK(e->tc_fail_count.ensure(64));
-            CK(e->tc_gthr.ensure(((size_t)Qc + (size_t)Qc * ranges) * 4));
+            CK(e->tc_gthr.ensure((size_t)Qc * scl_knn_tc2_kprime() * 4));
             float* probe = nullptr;
             if (e->count_fallbacks) {
                 if (!e->tc_err_probe.p) { CK(e->tc_err_probe.ensure(64)); CK(cudaMemsetAsync(e->tc_err_probe.p, 0, 64, e->stream)); }
                 probe = e->tc_err_probe.as<float>();
             }
-            KnnTc2Workspace tw{e->tc_prop_s.as<float>(), e->tc_prop_idx.as<int32_t>(), e->tc_prop_cut.as<float>(), e->tc_gthr.as<int>(), probe, ncand};
+            KnnTc2Workspace tw{e->tc_prop_s.as<uint32_t>(), e->tc_prop_cut.as<int>(), e->tc_gthr.as<int>(), probe, pairs};
             CK(scl_launch_knn_tc2(e->qkeys.as<float>(), Q, e->d_keys, e->d_kimg, e->d_kn2max, n_db, R, K, metric, e->world, e->rank, tw,
                                   cand_ids, cand_d2, e->tc_fail_list.as<int32_t>(), e->tc_fail_count.as<int>(), e->stream));
             CK(scl_launch_knn_exact(e->qkeys.as<float>(), Q, e->d_keys, n_db, R, K, metric, e->world, e->rank,

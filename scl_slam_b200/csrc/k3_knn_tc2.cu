@@ -53,15 +53,21 @@
 #include <cstdlib>
 #include <vector>
 
+#ifndef SCL_TC2_NH
+#define SCL_TC2_NH 128
+#endif
+
 namespace {
 
-constexpr int kKPrime = 16;        /* proposals kept per (query, range): a sorted list in REGISTERS */
-constexpr int kStageCap = 16;      /* staging entries per thread: one 8-column group can add 8 */
+constexpr int kKPrime = 16;        /* K': the number of distinct keys that back a query's threshold; K <= K' - 2 */
+constexpr int kQueueCap = 40;      /* hit queue per (query, range): groups of 12 words (first key, 3 pad, 8 scores); ~9 are used */
 constexpr int kEpiThreads = 256;   /* 8 epilogue warps: query tile = (warp-4)/4, TMEM lane quadrant = warp%4 */
 constexpr int kThreads = 384;
-constexpr int kNT = 128;           /* keys per tile */
+constexpr int kNT = 128;           /* keys per tile (one TMA copy) */
+constexpr int kNH = SCL_TC2_NH;    /* keys per accumulator slot (one MMA batch) */
+constexpr int kAccStages = 256 / kNH;   /* accumulator slots per query tile: stages x 2 query tiles x kNH columns = all 512 TMEM columns */
 constexpr int kQPerCta = 256;
-constexpr int kNoThr = 0x7f7f7f7f; /* memset pattern of g_thr / pub: 3.39e38 = "nothing yet" */
+constexpr int kNoThr = 0x7f7f7f7f; /* memset pattern of the slots: 3.39e38 = "nothing yet" */
 constexpr float kThrInit = 1.0e38f;
 
 // order-preserving float <-> signed int image
@@ -147,14 +153,14 @@ template <int R> struct Tc2Cfg {
     static constexpr int KSTEPS = KTOT / 16;                  /* tcgen05.mma instructions per 128x128 tile */
     static constexpr uint32_t LBO = 128 * 16, SBO = 128;      /* both operands are 128 rows tall */
     static constexpr uint32_t TILE_BYTES = 128 * KTOT * 2;    /* one operand tile: 16 KB / 32 KB */
-    static constexpr int NSTAGE = R <= 20 ? 6 : 3;            /* key tiles in flight in shared memory */
+    static constexpr int NSTAGE = R <= 20 ? 8 : 4;            /* key tiles in flight in shared memory */
     static constexpr uint32_t OFF_BAR = 0;                    /* mbarriers, tmem slot, flags */
-    static constexpr uint32_t OFF_A = 1024;                   /* two query tiles */
+    static constexpr uint32_t OFF_THR = 1024;                 /* [256] union bounds */
+    static constexpr uint32_t OFF_A = 2048;                   /* two query tiles */
     static constexpr uint32_t OFF_B = OFF_A + 2 * TILE_BYTES;
-    static constexpr uint32_t OFF_STG = OFF_B + NSTAGE * TILE_BYTES;          /* staging [cap][256] scores, keys */
-    static constexpr uint32_t TOTAL = OFF_STG + (2 * kStageCap + 8) * kEpiThreads * 4;          /* + bounce buffer [8][256] */
-    /* D = F32, A = B = BF16, both K-major, N = 128, M = 128 */
-    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kNT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    static constexpr uint32_t TOTAL = OFF_B + NSTAGE * TILE_BYTES;
+    /* D = F32, A = B = BF16, both K-major, N = kNH, M = 128 */
+    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kNH >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
 
 // value of GEMM column `idx` of the key row (B) / of the query row (A)
@@ -202,37 +208,59 @@ __global__ void __launch_bounds__(128) key_image_kernel(const float* __restrict_
     }
 }
 
+// A full hit queue is re-filtered with the threshold of the moment: groups queued under an earlier, looser bound whose
+// 8 scores have all risen to or above it can be dropped like any other key (they are >= the final cut). Rare, and kept
+// out of line so that the epilogue loop stays small.
+__device__ __noinline__ int compact_queue(uint4* q, int n, float thr)
+{
+    int w = 0;
+    for (int e = 0; e < n; e++) {
+        const uint4 k4 = __ldcg(q + 3 * e), a4 = __ldcg(q + 3 * e + 1), b4 = __ldcg(q + 3 * e + 2);
+        const float m = fminf(fminf(fminf(__uint_as_float(a4.x), __uint_as_float(a4.y)), fminf(__uint_as_float(a4.z), __uint_as_float(a4.w))),
+                              fminf(fminf(__uint_as_float(b4.x), __uint_as_float(b4.y)), fminf(__uint_as_float(b4.z), __uint_as_float(b4.w))));
+        if (m < thr) {
+            if (w != e) { __stcg(q + 3 * w, k4); __stcg(q + 3 * w + 1, a4); __stcg(q + 3 * w + 2, b4); }
+            w++;
+        }
+    }
+    return w;
+}
+
 // ---- the query kernel ---------------------------------------------------------------------------------
 template <int R>
 __global__ void __launch_bounds__(kThreads, 1) knn_tc2_kernel(
-    const float* __restrict__ qkeys, int Q, const unsigned char* __restrict__ img, int key_hi, int tiles_per_range, int n_ranges,
+    const float* __restrict__ qkeys, int Q, const unsigned char* __restrict__ img, int key_hi, int n_ranges,
     long long* __restrict__ times /* null, or [grid][16] developer counters (SCL_TC_TIMES=1) */,
-    int* __restrict__ g_thr /* [Q] union bounds (ordered-int image) */, float* __restrict__ pub /* [Q][n_ranges] range minima */,
-    float* __restrict__ prop_s /* [Q][n_ranges][K'] */, int32_t* __restrict__ prop_idx, float* __restrict__ prop_cut /* [Q][n_ranges] */)
+    int* __restrict__ slots /* [Q][K'] range minima by range % K' (ordered-int image) */,
+    uint32_t* __restrict__ hq /* [Q][n_ranges][kQueueCap][12] hit queues */, int* __restrict__ hq_cnt /* [Q][n_ranges] */,
+    int* __restrict__ dbg /* null, or developer counters */)
 {
     using C = Tc2Cfg<R>;
     constexpr int NS = C::NSTAGE;
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-    uint64_t *full = bars, *empty = bars + NS, *tfull = bars + 2 * NS, *tempty = bars + 2 * NS + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 8);
+    uint64_t *full = bars, *empty = bars + NS, *tfull = bars + 2 * NS, *tempty = bars + 2 * NS + 2 * kAccStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 4 * kAccStages);
     volatile int* epi_done = reinterpret_cast<volatile int*>(tmem_slot + 1);
+    volatile int* sthr = reinterpret_cast<volatile int*>(smem + C::OFF_THR);          /* [256] union bounds of the CTA's queries */
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_groups = gridDim.x / n_ranges;
     const int group = blockIdx.x % n_groups, range = blockIdx.x / n_groups;   /* neighbouring CTAs share a key range (L2 reuse) */
     const int q_base = group * kQPerCta;
+    /* Key tiles are dealt round-robin: this CTA owns tiles range, range + n_ranges, ... Every CTA then sees a sample of the
+     * WHOLE database, so the range minima that make up the union bound are alike even when the database is ordered
+     * (a trajectory: neighbouring keys are neighbouring places, and whole stretches of it are far from the query). */
     const int n_tiles_all = (key_hi + kNT - 1) / kNT;
-    const int tile_lo = range * tiles_per_range;
-    const int n_tiles = max(0, min(n_tiles_all, tile_lo + tiles_per_range) - tile_lo);
-    const int n_service = min(n_ranges, (n_tiles_all + tiles_per_range - 1) / tiles_per_range);   /* ranges that hold keys */
-
+    const int n_tiles = range < n_tiles_all ? (n_tiles_all - range + n_ranges - 1) / n_ranges : 0;
+    const int n_service = min(n_ranges, n_tiles_all);                         /* ranges that hold keys */
     // ---- one-time setup -----------------------------------------------------------------------
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; s++) { scl_mbar_init(&full[s], 1); scl_mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 4; s++) { scl_mbar_init(&tfull[s], 1); scl_mbar_init(&tempty[s], 4); }
+        for (int s = 0; s < 2 * kAccStages; s++) { scl_mbar_init(&tfull[s], 1); scl_mbar_init(&tempty[s], 4); }
         *epi_done = 0;
         scl_mbar_fence_init();
     }
+    if (threadIdx.x < kQPerCta) sthr[threadIdx.x] = kNoThr;
     if (warp == 0) {   /* TMEM: 2 stages x 2 query tiles x 128 fp32 columns */
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(scl_smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -270,56 +298,21 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc2_kernel(
 
     if (warp >= 4) {
         // ===== epilogue: thread = query = TMEM lane ====================================================
-        constexpr int E = kEpiThreads;
         const int qt = (warp - 4) >> 2;                 /* query tile of this warp */
         const int row = (warp & 3) * 32 + lane;         /* TMEM lane */
-        const int t = qt * 128 + row;                   /* slot of this thread in the shared-memory bounce buffer */
-        const int qi = q_base + t;
+        const int qi = q_base + qt * 128 + row;
         const bool live = qi < Q;
-        float* sv = reinterpret_cast<float*>(smem + C::OFF_STG);     /* staging [kStageCap][256] scores, then keys */
-        int* si = reinterpret_cast<int*>(sv + kStageCap * E);
-        float* sb = reinterpret_cast<float*>(si + kStageCap * E);   /* bounce buffer [8][256] */
-        // The thread's K' best (score, key) so far live in registers, sorted ascending.
-        float lv[kKPrime]; int li[kKPrime];
-#pragma unroll
-        for (int i = 0; i < kKPrime; i++) { lv[i] = kThrInit; li[i] = -1; }
-        int cnt = 0;                                    /* staged, not yet folded entries of this thread */
-        int n_slow = 0, n_push = 0, n_fold = 0;         /* developer counters (SCL_TC_TIMES) */
-        float thr = live ? kThrInit : -kThrInit;        /* rows beyond Q never keep anything */
+        int n_hit = 0;                                  /* 8-column groups queued by this thread */
+        int n_slow = 0;                                 /* developer counter (SCL_TC_TIMES) */
+        float thr = live ? kThrInit : -kThrInit;        /* rows beyond Q never queue anything */
         float published = kThrInit;
-        int* my_gthr = g_thr + (live ? qi : 0);
-        float* my_pub = pub + (size_t)(live ? qi : 0) * n_ranges + range;
-        // The epilogue is bound by the half-rate ALU pipe (FMNMX, FSETP, SEL all issue there), so instructions are what
-        // counts. A hit costs two predicated stores into the thread's staging column; the sorted lists are updated
-        // lazily, all 32 lanes at once, when some lane's column fills up (fold): one pass of the insert network then
-        // serves up to 32 pushes instead of one.
-        auto fold = [&]() {
-            n_fold++; n_push += cnt;
-            const int n_max = __reduce_max_sync(0xffffffffu, cnt);
-#pragma unroll 1
-            for (int s = 0; s < n_max; s++) {
-                float val = sv[s * E + t];
-                const int id = si[s * E + t];
-                val = (s < cnt && val < thr) ? val : __int_as_float(0x7f800000);   /* inserting +inf changes nothing */
-                /* all 16 comparisons are independent (the list is sorted, so the predicates are monotone); every entry
-                 * then picks its left neighbour, the new value or itself */
-                bool lt[kKPrime];
-#pragma unroll
-                for (int k = 0; k < kKPrime; k++) lt[k] = val < lv[k];
-#pragma unroll
-                for (int k = kKPrime - 1; k > 0; k--) {
-                    lv[k] = lt[k - 1] ? lv[k - 1] : (lt[k] ? val : lv[k]);
-                    li[k] = lt[k - 1] ? li[k - 1] : (lt[k] ? id : li[k]);
-                }
-                lv[0] = lt[0] ? val : lv[0];
-                li[0] = lt[0] ? id : li[0];
-                thr = fminf(thr, lv[kKPrime - 1]);
-            }
-            cnt = 0;
-            if (live && lv[0] < published) { published = lv[0]; __stcg(my_pub, published); }   /* feeds the union bound */
-        };
-        // 32 scores of one query: a FMNMX3 tree and one compare. Only when some lane's minimum beats its threshold are
-        // the 8-column groups looked at one by one (warp-uniform control flow: registers cannot be indexed dynamically).
+        int* my_slot = slots + (size_t)(live ? qi : 0) * kKPrime + (range % kKPrime);
+        volatile int* my_sthr = sthr + qt * 128 + row;
+        uint4* my_q = reinterpret_cast<uint4*>(hq + ((size_t)(live ? qi : 0) * n_ranges + range) * (size_t)(kQueueCap * 12));
+        // The epilogue warps are coupled through the accumulator hand-off (a slot is refilled only when all four warps of
+        // its query tile have drained it), so whatever a warp does on a hit sits on the critical path of the whole CTA.
+        // A hit therefore only APPENDS the 8-column group (its first key and its 8 scores: three 16-byte stores) to the
+        // (query, range) queue in global memory; the re-rank kernel sorts it out. 32 scores cost a FMNMX3 tree and a vote.
         auto examine = [&](uint32_t (&r)[32], int key_first) {
             float g[4];
 #pragma unroll
@@ -330,188 +323,166 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc2_kernel(
                 g[j] = fminf(fmin3(fmin3(x0, x1, x2), fmin3(x3, x4, x5), x6), x7);
             }
             const float m = fminf(fmin3(g[0], g[1], g[2]), g[3]);
-            if (!__any_sync(0xffffffffu, m < thr)) return;
-            unsigned mask = 0;
+            if (__any_sync(0xffffffffu, m < thr)) {     /* one chunk in ten */
+                n_slow++;
 #pragma unroll
-            for (int j = 0; j < 4; j++) mask |= (g[j] < thr ? 1u : 0u) << j;
-            unsigned wm = __reduce_or_sync(0xffffffffu, mask);
-            n_slow++;
-#pragma unroll 1
-            while (wm) {
-                const int j = __ffs(wm) - 1;             /* warp-uniform: the switch below does not diverge */
-                wm &= wm - 1;
-                const int kf = key_first + 8 * j;
-                /* bounce the group through shared memory so that ONE copy of the staging code serves all four groups
-                 * (code size: the whole kernel has to stay near the 32 KB instruction cache) */
-#define SCL_GROUP(J) case J: _Pragma("unroll") for (int i = 0; i < 8; i++) sb[i * E + t] = __uint_as_float(r[8 * J + i]); break;
-                switch (j) { SCL_GROUP(0) SCL_GROUP(1) SCL_GROUP(2) default: SCL_GROUP(3) }
-#undef SCL_GROUP
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const float x = sb[i * E + t];
-                    if (x < thr && kf + i < key_hi) { sv[cnt * E + t] = x; si[cnt * E + t] = kf + i; cnt++; }
+                for (int j = 0; j < 4; j++) {
+                    if (g[j] < thr) {                    /* divergent: usually one lane, one group */
+                        if (n_hit == kQueueCap) n_hit = compact_queue(my_q, kQueueCap, thr);
+                        if (n_hit < kQueueCap) {
+                            uint4* q = my_q + n_hit * 3;
+                            __stcg(q + 0, make_uint4((uint32_t)(key_first + 8 * j), 0u, 0u, 0u));
+                            __stcg(q + 1, make_uint4(r[8 * j + 0], r[8 * j + 1], r[8 * j + 2], r[8 * j + 3]));
+                            __stcg(q + 2, make_uint4(r[8 * j + 4], r[8 * j + 5], r[8 * j + 6], r[8 * j + 7]));
+                        }
+                        n_hit++;                         /* beyond the capacity: counted, the query is then redone exactly */
+                    }
                 }
-                if (__any_sync(0xffffffffu, cnt > kStageCap - 8)) fold();     /* all lanes fold together: amortised */
+                /* a new range minimum feeds the union bound at once */
+                if (live && m < published && key_first + 32 <= key_hi) { published = m; atomicMin(my_slot, ordered_int(m)); }
             }
-            /* a new range minimum feeds the union bound at once (the lists themselves are folded lazily) */
-            if (live && m < published && key_first + 32 <= key_hi) { published = m; __stcg(my_pub, m); }
         };
-        long long tw = 0, c0 = 0;
+        long long tw = 0, c0 = 0, t_ld = 0, t_ex = 0;
         if (times) c0 = clock64();
-        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(qt * kNT);
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(qt * kNH);
         uint32_t va[32], vb[32];
-        int shared_thr = live ? __ldcg(my_gthr) : kNoThr;   /* then fetched one tile ahead: its L2 latency is never exposed */
+        const int n_it = (kNT / kNH) * n_tiles;             /* accumulator slots to drain */
         if (n_tiles > 0) {
-            scl_mbar_wait(&tfull[qt], 0);
-            tc_fence_after();
-            /* Start-up: with no threshold yet, every score of the first tile would be pushed. Instead the tile is read
-             * twice: a first pass only finds the range minimum so far and publishes it; as soon as K' ranges have done
-             * so the service warps deliver a union bound (a few microseconds), and the normal pass below starts with it. */
-            if (n_service >= kKPrime && (tile_lo + 1) * kNT <= key_hi) {
+            /* Start-up: with no threshold yet, every score of the first tile would be a hit. Instead the first 128 keys are
+             * read twice: a first pass only finds the range minimum so far and publishes it; as soon as K' ranges have done
+             * so the service warps deliver a union bound (a few microseconds), and the normal pass starts with it. */
+            if (n_service >= kKPrime && (range + 1) * kNT <= key_hi) {
                 float m0 = kThrInit;
 #pragma unroll 1
-                for (int c = 0; c < 4; c++) {
-                    tmem_ld32_issue(lane_base + 32 * c, va);
+                for (int c = 0; c < kNT / 32; c++) {
+                    const int sl = (c * 32) / kNH, cc = (c * 32) % kNH;     /* slot, column within the slot */
+                    if (cc == 0) { scl_mbar_wait(&tfull[sl * 2 + qt], 0); tc_fence_after(); }
+                    tmem_ld32_issue(lane_base + (uint32_t)(sl * 2 * kNH + cc), va);
                     tmem_wait32(va);
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) m0 = fmin3(m0, __uint_as_float(va[j]), __uint_as_float(va[j + 1]));
                 }
-                if (live) { published = m0; __stcg(my_pub, m0); }
+                if (live) { published = m0; atomicMin(my_slot, ordered_int(m0)); }
                 const long long w0 = clock64();
                 while (true) {
-                    if (live) shared_thr = __ldcg(my_gthr);
-                    const bool ok = !live || shared_thr < 0x7f000000;
-                    if (__all_sync(0xffffffffu, ok) || clock64() - w0 > 20000) break;
+                    const bool ok = !live || *my_sthr < 0x7f000000;
+                    if (__all_sync(0xffffffffu, ok)) break;
+                    if (clock64() - w0 > 40000) { if (dbg && lane == 0) atomicAdd(dbg + 5, 1); break; }
                     __nanosleep(100);
                 }
+            } else {
+                scl_mbar_wait(&tfull[qt], 0);
+                tc_fence_after();
             }
             tmem_ld32_issue(lane_base, va);
         }
-        // Two 32-column chunks per iteration (va, vb), two iterations per key tile. The load of the next chunk is always in
-        // flight while the current one is examined; the accumulator is handed back as soon as its last chunk is in registers.
+        // One accumulator slot (kNH keys) per iteration, as pairs of 32-column chunks (va, vb). The load of the next chunk is
+        // always in flight while the current one is examined; the slot is handed back as soon as its last chunk is in registers.
 #pragma unroll 1
-        for (int it = 0; it < 2 * n_tiles; it++) {
-            const int tile = it >> 1, h = it & 1;
-            const int s = tile & 1;
-            const int key0 = (tile_lo + tile) * kNT + 64 * h;
-            const uint32_t col0 = lane_base + (uint32_t)(s * 2 * kNT + 64 * h);
-            if (h == 0 && live) { thr = fminf(thr, ordered_float(shared_thr)); shared_thr = __ldcg(my_gthr); }
-            tmem_wait32(va);
-            tmem_ld32_issue(col0 + 32, vb);
-            examine(va, key0);
-            tmem_wait32(vb);
-            bool pending = false;                        /* va still has to be loaded for the next iteration */
-            if (h == 0) {
-                tmem_ld32_issue(col0 + 64, va);
-            } else {
-                /* every score of this accumulator is in registers: hand it back to the MMA issuer now */
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[s * 2 + qt]);
-                if (tile + 1 < n_tiles) {
-                    const int s1 = (tile + 1) & 1; const uint32_t ph1 = ((tile + 1) >> 1) & 1;
-                    /* next accumulator already complete? then start its first load before examining the last 32 scores */
-                    if (__all_sync(0xffffffffu, mbar_test(&tfull[s1 * 2 + qt], ph1))) {
-                        tc_fence_after();
-                        tmem_ld32_issue(lane_base + (uint32_t)(s1 * 2 * kNT), va);
-                    } else {
-                        pending = true;
-                    }
+        for (int it = 0; it < n_it; it++) {
+            const int s = it % kAccStages;
+            const int key0 = (range + (it / (kNT / kNH)) * n_ranges) * kNT + (it % (kNT / kNH)) * kNH;
+            const uint32_t col0 = lane_base + (uint32_t)(s * 2 * kNH);
+            if (live) thr = fminf(thr, ordered_float(*my_sthr));
+            long long p0 = 0;
+#pragma unroll
+            for (int pr = 0; pr < kNH / 64; pr++) {
+                if (times) p0 = clock64();
+                tmem_wait32(va);
+                if (times) { const long long p1 = clock64(); t_ld += p1 - p0; p0 = p1; }
+                tmem_ld32_issue(col0 + 64 * pr + 32, vb);
+                examine(va, key0 + 64 * pr);
+                if (times) { const long long p1 = clock64(); t_ex += p1 - p0; p0 = p1; }
+                tmem_wait32(vb);
+                if (times) { const long long p1 = clock64(); t_ld += p1 - p0; p0 = p1; }
+                if (pr + 1 < kNH / 64) {
+                    tmem_ld32_issue(col0 + 64 * pr + 64, va);
+                    if (times) p0 = clock64();
+                    examine(vb, key0 + 64 * pr + 32);
+                    if (times) t_ex += clock64() - p0;
                 }
             }
-            examine(vb, key0 + 32);
+            /* every score of this slot is in registers: hand it back to the MMA issuer now */
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[s * 2 + qt]);
+            bool pending = false;                        /* va still has to be loaded for the next iteration */
+            const int s1 = (it + 1) % kAccStages; const uint32_t ph1 = ((it + 1) / kAccStages) & 1;
+            if (it + 1 < n_it) {
+                /* next slot already complete? then start its first load before examining the last 32 scores */
+                if (__all_sync(0xffffffffu, mbar_test(&tfull[s1 * 2 + qt], ph1))) {
+                    tc_fence_after();
+                    tmem_ld32_issue(lane_base + (uint32_t)(s1 * 2 * kNH), va);
+                } else {
+                    pending = true;
+                }
+            }
+            if (times) p0 = clock64();
+            examine(vb, key0 + kNH - 32);
+            if (times) t_ex += clock64() - p0;
             if (pending) {
-                const int s1 = (tile + 1) & 1; const uint32_t ph1 = ((tile + 1) >> 1) & 1;
                 long long w0 = 0;
                 if (times) w0 = clock64();
                 scl_mbar_wait(&tfull[s1 * 2 + qt], ph1);
                 if (times) tw += clock64() - w0;
                 tc_fence_after();
-                tmem_ld32_issue(lane_base + (uint32_t)(s1 * 2 * kNT), va);
+                tmem_ld32_issue(lane_base + (uint32_t)(s1 * 2 * kNH), va);
             }
         }
-        fold();
         if (times) {
-            const int wp = __reduce_add_sync(0xffffffffu, n_push);
+            const int wp = __reduce_add_sync(0xffffffffu, n_hit), wmax = __reduce_max_sync(0xffffffffu, n_hit);
             if (lane == 0) {
                 long long* o = times + (size_t)blockIdx.x * 16;
                 atomicAdd(reinterpret_cast<unsigned long long*>(o + 0), (unsigned long long)tw);
                 atomicAdd(reinterpret_cast<unsigned long long*>(o + 1), (unsigned long long)(clock64() - c0));
                 atomicAdd(reinterpret_cast<unsigned long long*>(o + 2), (unsigned long long)n_slow);
                 atomicAdd(reinterpret_cast<unsigned long long*>(o + 3), (unsigned long long)wp);
-                atomicAdd(reinterpret_cast<unsigned long long*>(o + 4), (unsigned long long)n_fold);
+                atomicMax(reinterpret_cast<unsigned long long*>(o + 4), (unsigned long long)wmax);
+                atomicAdd(reinterpret_cast<unsigned long long*>(o + 9), (unsigned long long)t_ld);
+                atomicAdd(reinterpret_cast<unsigned long long*>(o + 10), (unsigned long long)t_ex);
             }
         }
-        if (live) {
-            const size_t o = ((size_t)qi * n_ranges + range) * kKPrime;
-            const float inf = __int_as_float(0x7f800000);
-#pragma unroll
-            for (int i = 0; i < kKPrime; i += 4) {
-                float4 s4; int4 i4;
-                s4.x = li[i] >= 0 ? lv[i] : inf; s4.y = li[i + 1] >= 0 ? lv[i + 1] : inf;
-                s4.z = li[i + 2] >= 0 ? lv[i + 2] : inf; s4.w = li[i + 3] >= 0 ? lv[i + 3] : inf;
-                i4.x = li[i]; i4.y = li[i + 1]; i4.z = li[i + 2]; i4.w = li[i + 3];
-                *reinterpret_cast<float4*>(prop_s + o + i) = s4;
-                *reinterpret_cast<int4*>(prop_idx + o + i) = i4;
-            }
-            /* cut-off of this range: every key NOT proposed had a score >= the threshold in force when it was
-             * examined >= the final threshold (thresholds only fall); inf if nothing was ever dropped */
-            prop_cut[(size_t)qi * n_ranges + range] = thr < kThrInit ? thr : inf;
-        }
+        /* Everything this thread did NOT queue scored >= the threshold in force at the time >= the maximum the query's slots
+         * end at (slots only fall, and a thread only ever applies a bound computed from them): the re-rank takes that maximum
+         * as the query's cut. The count is written even when it is zero, so the queues need no clearing between batches. */
+        if (live) hq_cnt[(size_t)qi * n_ranges + range] = n_hit;
         __syncwarp();
         if (lane == 0) atomicAdd(const_cast<int*>(epi_done), 1);
     } else if (warp >= 2) {
-        // ===== threshold service: union bound = K'-th smallest of a query's published range minima ==========
-        // This CTA serves the queries j of its group with j % n_ranges == range (every query of the group has
-        // exactly one serving CTA among those that hold keys), split between the two service warps.
-        const int sw = warp - 2;
-        constexpr int LPL = 5;                          /* lists per lane: up to 160 ranges */
+        // ===== threshold service: union bound of the CTA's 256 queries ==================================
+        // Range r publishes its best score so far into slot r % K' of the query (atomicMin). The K' slots then hold the
+        // scores of K' DISTINCT keys (different ranges), so their maximum bounds the query's K'-th best score from above.
+        // Each lane refreshes four queries: 64 bytes from L2 and 15 max operations per query, a microsecond per sweep.
         int sweeps = 0;
-        const int n_active = n_service;
         while (n_tiles > 0) {
             const bool last = *epi_done >= 8;
-            for (int j = range + sw * n_active; j < kQPerCta; j += 2 * n_active) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int j = (warp - 2) * 128 + 32 * k + lane;
                 const int qi = q_base + j;
-                if (qi >= Q) break;
-                const float* p = pub + (size_t)qi * n_ranges;
-                int v[LPL];
-#pragma unroll
-                for (int l = 0; l < LPL; l++) {
-                    const int idx = lane + 32 * l;
-                    v[l] = idx < n_ranges ? ordered_int(__ldcg(p + idx)) : 0x7fffffff;
+                if (qi < Q) {
+                    const int4* p = reinterpret_cast<const int4*>(slots + (size_t)qi * kKPrime);
+                    const int4 a = __ldcg(p), b4 = __ldcg(p + 1), c = __ldcg(p + 2), d = __ldcg(p + 3);
+                    const int m = max(max(max(max(a.x, a.y), max(a.z, a.w)), max(max(b4.x, b4.y), max(b4.z, b4.w))),
+                                      max(max(max(c.x, c.y), max(c.z, c.w)), max(max(d.x, d.y), max(d.z, d.w))));
+                    if (m < 0x7f000000) sthr[j] = m;     /* all K' slots filled: a valid bound */
                 }
-                int kth = 0x7fffffff;
-#pragma unroll 1
-                for (int r = 0; r < kKPrime; r++) {
-                    int m = v[0];
-#pragma unroll
-                    for (int l = 1; l < LPL; l++) m = min(m, v[l]);
-                    const int wmin = __reduce_min_sync(0xffffffffu, m);
-                    kth = wmin;
-                    if (wmin >= 0x7f000000) break;      /* fewer than K' ranges have published: no bound yet */
-                    const unsigned who = __ballot_sync(0xffffffffu, m == wmin);
-                    if (lane == __ffs(who) - 1) {
-                        bool popped = false;
-#pragma unroll
-                        for (int l = 0; l < LPL; l++) { const bool hit = !popped && v[l] == wmin; v[l] = hit ? 0x7fffffff : v[l]; popped |= hit; }
-                    }
-                }
-                if (lane == 0 && kth < 0x7f000000) atomicMin(g_thr + qi, kth);
             }
             sweeps++;
             if (last) break;
-            __nanosleep(sweeps < 16 ? 250 * sweeps : 4000);
+            if (sweeps > 64) __nanosleep(1000);          /* the bound moves fast at the start: sweep back to back there */
         }
         if (times && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(times + (size_t)blockIdx.x * 16 + 5), (unsigned long long)sweeps);
     } else if (warp == 1) {
         // ===== TMA issuer: one thread, one bulk copy per key tile =======================================
         if (lane == 0) {
-            const unsigned char* src = img + (size_t)tile_lo * C::TILE_BYTES;
+            const unsigned char* src = img + (size_t)range * C::TILE_BYTES;
+            const size_t step = (size_t)n_ranges * C::TILE_BYTES;
             for (int tile = 0; tile < n_tiles; tile++) {
                 const int b = tile % NS; const uint32_t ph = (tile / NS) & 1;
                 scl_mbar_wait(&empty[b], ph ^ 1u);
                 scl_mbar_expect_tx(&full[b], C::TILE_BYTES);
-                scl_bulk_g2s(smem + C::OFF_B + (uint32_t)b * C::TILE_BYTES, src + (size_t)tile * C::TILE_BYTES, C::TILE_BYTES, &full[b]);
+                scl_bulk_g2s(smem + C::OFF_B + (uint32_t)b * C::TILE_BYTES, src + (size_t)tile * step, C::TILE_BYTES, &full[b]);
             }
         }
         __syncwarp();
@@ -520,25 +491,27 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc2_kernel(
         if (lane == 0) {
             const uint32_t a_base = scl_smem_u32(smem + C::OFF_A), b_base = scl_smem_u32(smem + C::OFF_B);
             long long t_te = 0, t_fu = 0, c0 = 0;
-            for (int tile = 0; tile < n_tiles; tile++) {
+            constexpr int SPT = kNT / kNH;                          /* accumulator slots per key tile */
+            for (int it = 0; it < SPT * n_tiles; it++) {
+                const int tile = it / SPT, hf = it % SPT;           /* kNH keys of a key tile -> one accumulator slot per query tile */
                 const int b = tile % NS; const uint32_t bph = (tile / NS) & 1;
-                const int s = tile & 1; const uint32_t ph = (tile >> 1) & 1;
+                const int s = it % kAccStages; const uint32_t ph = (it / kAccStages) & 1;
                 if (times) c0 = clock64();
-                scl_mbar_wait(&full[b], bph);                       /* key tile landed */
+                if (hf == 0) scl_mbar_wait(&full[b], bph);          /* key tile landed */
                 if (times) { const long long c1 = clock64(); t_fu += c1 - c0; c0 = c1; }
-                const uint32_t bs = b_base + (uint32_t)b * C::TILE_BYTES;
+                const uint32_t bs = b_base + (uint32_t)b * C::TILE_BYTES + (uint32_t)hf * (kNH / 8) * C::SBO;   /* rows 64*hf.. of the tile */
 #pragma unroll
                 for (int qt = 0; qt < 2; qt++) {
-                    scl_mbar_wait(&tempty[s * 2 + qt], ph ^ 1u);    /* accumulator drained by its four epilogue warps */
+                    scl_mbar_wait(&tempty[s * 2 + qt], ph ^ 1u);    /* slot drained by its four epilogue warps */
                     tc_fence_after();
-                    const uint32_t d = tmem_base + (uint32_t)((s * 2 + qt) * kNT);
+                    const uint32_t d = tmem_base + (uint32_t)((s * 2 + qt) * kNH);
                     const uint32_t as = a_base + (uint32_t)qt * C::TILE_BYTES;
 #pragma unroll
                     for (int k = 0; k < C::KSTEPS; k++)
                         tc_mma_bf16(d, make_desc(as + 2 * k * C::LBO, C::LBO, C::SBO), make_desc(bs + 2 * k * C::LBO, C::LBO, C::SBO), C::IDESC, k > 0 ? 1u : 0u);
-                    tc_commit(&tfull[s * 2 + qt]);                  /* accumulator ready for the epilogue */
+                    tc_commit(&tfull[s * 2 + qt]);                  /* slot ready for the epilogue */
                 }
-                tc_commit(&empty[b]);                               /* key tile reusable once these MMAs retire */
+                if (hf == SPT - 1) tc_commit(&empty[b]);                  /* key tile reusable once these MMAs retire */
                 if (times) { const long long c1 = clock64(); t_te += c1 - c0; }
             }
             if (times) { times[(size_t)blockIdx.x * 16 + 6] = t_fu; times[(size_t)blockIdx.x * 16 + 7] = t_te; times[(size_t)blockIdx.x * 16 + 8] = n_tiles; }
@@ -571,12 +544,12 @@ __device__ __forceinline__ float exact_d2(const float* __restrict__ q, const flo
     return result;
 }
 
-// Phase B: exact re-rank + certificate. One warp per query over its n_ranges * K' proposals.
+// Phase B: exact re-rank + certificate. One warp per query; a lane walks the hit queues of the ranges l, l+32, ...
 constexpr int kMaxSurvivors = 256;
 template <int METRIC>
 __global__ void __launch_bounds__(128) knn_rerank2_kernel(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys, int R, int K,
-                                                          int n_ranges, const float* __restrict__ prop_s, const int32_t* __restrict__ prop_idx,
-                                                          const float* __restrict__ prop_cut, const float* __restrict__ kn2max, int id_mul, int id_add,
+                                                          int n_ranges, int n_db, const uint32_t* __restrict__ hq, const int* __restrict__ hq_cnt,
+                                                          const int* __restrict__ slots, const float* __restrict__ kn2max, int id_mul, int id_add,
                                                           int32_t* __restrict__ out_ids, float* __restrict__ out_d2, int q_off,
                                                           int32_t* __restrict__ fail_list, int* __restrict__ fail_count, float* __restrict__ err_probe)
 {
@@ -587,62 +560,38 @@ __global__ void __launch_bounds__(128) knn_rerank2_kernel(const float* __restric
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int qi = blockIdx.x * (blockDim.x >> 5) + w;
     if (qi >= Q) return;
-    const int n_cand = n_ranges * kKPrime;
     const float* q = qkeys + (size_t)qi * R;
-    const int32_t* pidx = prop_idx + (size_t)qi * n_cand;
-    const float* ps = prop_s + (size_t)qi * n_cand;
     const float inf = __int_as_float(0x7f800000);
-    float cut = inf;
-    for (int r = lane; r < n_ranges; r += 32) cut = fminf(cut, prop_cut[(size_t)qi * n_ranges + r]);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) cut = fminf(cut, __shfl_xor_sync(0xffffffffu, cut, off));
-    /* The union bound once more, on the final lists: the K'-th smallest of the range minima (each list's head) is backed
-     * by K' distinct keys, so nothing above it can belong to the top-K' — it caps the cut even for a query whose
-     * serving CTA stopped early. */
-    {
-        constexpr int LPL = 5;                          /* up to 160 ranges */
-        int v[LPL];
-#pragma unroll
-        for (int l = 0; l < LPL; l++) {
-            const int r = lane + 32 * l;
-            const float h = r < n_ranges ? ps[(size_t)r * kKPrime] : inf;
-            v[l] = h < inf ? ordered_int(h) : 0x7fffffff;
-        }
-        int kth = 0x7fffffff;
-#pragma unroll 1
-        for (int r = 0; r < kKPrime; r++) {
-            int m = v[0];
-#pragma unroll
-            for (int l = 1; l < LPL; l++) m = min(m, v[l]);
-            const int wmin = __reduce_min_sync(0xffffffffu, m);
-            kth = wmin;
-            if (wmin == 0x7fffffff) break;              /* fewer than K' non-empty ranges: keep everything */
-            const unsigned who = __ballot_sync(0xffffffffu, m == wmin);
-            if (lane == __ffs(who) - 1) {
-                bool popped = false;
-#pragma unroll
-                for (int l = 0; l < LPL; l++) { const bool hit = !popped && v[l] == wmin; v[l] = hit ? 0x7fffffff : v[l]; popped |= hit; }
-            }
-        }
-        if (kth != 0x7fffffff) cut = fminf(cut, ordered_float(kth));
-    }
-    /* Every key scoring below the cut is among the proposals (a dropped key scored >= its range's final
-     * threshold >= cut). Proposals above the cut cannot be certified anyway, so only those at or below it are
-     * evaluated: about K' of them. */
+    /* The cut: the query's final union bound (the maximum of its K' slots). Everything that was not queued scored >= it, so every key scoring below it
+     * is in a queue; queued keys above it cannot be certified anyway and are skipped: about K' survive. */
+    int gt = lane < kKPrime ? __ldg(slots + (size_t)qi * kKPrime + lane) : (int)0x80000000;
+    gt = __reduce_max_sync(0xffffffffu, gt);
+    const float cut = gt < 0x7f000000 ? ordered_float(gt) : inf;
     if (lane == 0) s_count[w] = 0;
     __syncwarp();
-    for (int c = lane; c < n_cand; c += 32) {
-        const float sc = ps[c];
-        if (sc <= cut && sc < inf) {
-            const int id = pidx[c];
-            if (id >= 0) {
-                const int pos = atomicAdd(&s_count[w], 1);
-                if (pos < kMaxSurvivors) { s_id[w][pos] = id; s_s[w][pos] = sc; }
+    bool overflow = false;
+    for (int r = lane; r < n_ranges; r += 32) {
+        int cnt = __ldg(hq_cnt + (size_t)qi * n_ranges + r);
+        if (cnt > kQueueCap) { overflow = true; cnt = kQueueCap; }
+        const uint4* g = reinterpret_cast<const uint4*>(hq + ((size_t)qi * n_ranges + r) * (size_t)(kQueueCap * 12));
+#pragma unroll 2
+        for (int e = 0; e < cnt; e++) {
+            const uint4 k4 = __ldcg(g + 3 * e), a4 = __ldcg(g + 3 * e + 1), b4 = __ldcg(g + 3 * e + 2);
+            const float sc[8] = {__uint_as_float(a4.x), __uint_as_float(a4.y), __uint_as_float(a4.z), __uint_as_float(a4.w),
+                                 __uint_as_float(b4.x), __uint_as_float(b4.y), __uint_as_float(b4.z), __uint_as_float(b4.w)};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int id = (int)k4.x + i;
+                if (sc[i] <= cut && id < n_db) {
+                    const int pos = atomicAdd(&s_count[w], 1);
+                    if (pos < kMaxSurvivors) { s_id[w][pos] = id; s_s[w][pos] = sc[i]; }
+                }
             }
         }
     }
+    overflow = __any_sync(0xffffffffu, overflow);
     __syncwarp();
-    int n_surv = s_count[w]; bool overflow = false;
+    int n_surv = s_count[w];
     if (n_surv > kMaxSurvivors) { overflow = true; n_surv = kMaxSurvivors; }
     float qn = 0.0f;
     for (int d = 0; d < R; d++) qn = fmaf(q[d], q[d], qn);
@@ -692,6 +641,13 @@ __global__ void __launch_bounds__(128) knn_rerank2_kernel(const float* __restric
             certified = certified && (found == K) && (dK + eps < cut + qn);
         }
         if (!certified) fail_list[atomicAdd(fail_count, 1)] = q_off + qi;
+        if (!certified && err_probe) {                              /* developer counters: why */
+            int* why = reinterpret_cast<int*>(err_probe) + 1;
+            if (overflow) atomicAdd(why + 0, 1);
+            else if (found != K) atomicAdd(why + 1, 1);
+            else atomicAdd(why + 2, 1);
+            if (n_surv >= kMaxSurvivors) atomicAdd(why + 3, 1);
+        }
     }
 }
 
@@ -707,6 +663,7 @@ int scl_knn_tc2_ranges(int Q)
 }
 int scl_knn_tc2_max_batch() { return 1024; }          /* larger batches are cut into launches of this many queries */
 int scl_knn_tc2_kprime() { return kKPrime; }
+size_t scl_knn_tc2_queue_bytes() { return (size_t)kQueueCap * 12 * 4; }      /* per (query, range) */
 size_t scl_knn_tc2_image_bytes(int R, int n_keys)
 {
     const size_t tiles = ((size_t)n_keys + kNT - 1) / kNT;
@@ -724,8 +681,8 @@ cudaError_t scl_launch_key_image(const float* keys, const float* knorm, int k_lo
 }
 
 template <int R>
-static cudaError_t launch_tc2(const float* qkeys, int Q, const unsigned char* img, int n_db, int n_ranges, int* g_thr, float* pub,
-                              float* prop_s, int32_t* prop_idx, float* prop_cut, cudaStream_t stream)
+static cudaError_t launch_tc2(const float* qkeys, int Q, const unsigned char* img, int n_db, int n_ranges, int* slots,
+                              uint32_t* hq, int* hq_cnt, int* dbg, cudaStream_t stream)
 {
     using C = Tc2Cfg<R>;
     static bool attr = false;
@@ -735,22 +692,21 @@ static cudaError_t launch_tc2(const float* qkeys, int Q, const unsigned char* im
         attr = true;
     }
     const int groups = (Q + kQPerCta - 1) / kQPerCta;
-    const int n_tiles = (n_db + kNT - 1) / kNT;
-    const int tpr = (n_tiles + n_ranges - 1) / n_ranges;
     long long* times = nullptr;
     const bool want_times = getenv("SCL_TC_TIMES") != nullptr;       /* developer aid: per-role cycle counters on stderr */
     const int nb = groups * n_ranges;
     if (want_times) { cudaMalloc(&times, (size_t)nb * 16 * sizeof(long long)); cudaMemsetAsync(times, 0, (size_t)nb * 128, stream); }
-    knn_tc2_kernel<R><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, tpr, n_ranges, times, g_thr, pub, prop_s, prop_idx, prop_cut);
+    knn_tc2_kernel<R><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, times, slots, hq, hq_cnt, dbg);
     if (want_times) {
         std::vector<long long> h((size_t)nb * 16);
         cudaStreamSynchronize(stream);
         cudaMemcpy(h.data(), times, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-        double a[16] = {0};
+        double a[16] = {0}, amax4 = 0;
         for (int b = 0; b < nb; b++) for (int i = 0; i < 16; i++) a[i] += (double)h[(size_t)b * 16 + i] / nb;
-        fprintf(stderr, "[tc2 n_db %d] tiles/CTA %.0f | per tile, per epilogue warp: total %.0f cycles, waiting for the accumulator %.0f | slow 32-col chunks per warp %.0f of %.0f, "
-                        "pushes/lane %.1f, folds/warp %.1f | mma thread per tile: wait key tile %.0f, wait accumulators + issue %.0f | service sweeps %.0f\n",
-                n_db, a[8], a[1] / 8 / a[8], a[0] / 8 / a[8], a[2] / 8, a[8] * 4, a[3] / 8 / 32, a[4] / 8, a[6] / a[8], a[7] / a[8], a[5] / 2);
+        for (int b = 0; b < nb; b++) if ((double)h[(size_t)b * 16 + 4] > amax4) amax4 = (double)h[(size_t)b * 16 + 4];
+        fprintf(stderr, "[tc2 n_db %d] tiles/CTA %.0f | per tile, per epilogue warp: total %.0f cycles, waiting for the accumulator %.0f, in tcgen05.wait::ld %.0f, examining %.0f | slow 32-col chunks per warp %.0f of %.0f, "
+                        "groups queued per (query, range) %.1f (largest %.0f) | mma thread per tile: wait key tile %.0f, wait accumulators + issue %.0f | service sweeps %.0f\n",
+                n_db, a[8], a[1] / 8 / a[8], a[0] / 8 / a[8], a[9] / 8 / a[8], a[10] / 8 / a[8], a[2] / 8, a[8] * 4, a[3] / 8 / 32, amax4, a[6] / a[8], a[7] / a[8], a[5] / 2);
         cudaFree(times);
     }
     return cudaGetLastError();
@@ -769,26 +725,41 @@ cudaError_t scl_launch_knn_tc2(const float* qkeys, int Q, const float* keys, con
     for (int q0 = 0; q0 < Q; q0 += max_b) {
         const int Qc = Q - q0 < max_b ? Q - q0 : max_b;
         const int n_ranges = scl_knn_tc2_ranges(Qc);
-        if ((size_t)Qc * n_ranges * kKPrime > ws.capacity) return cudaErrorInvalidValue;
-        /* one memset: g_thr [Qc] and pub [Qc][n_ranges] are adjacent */
-        err = cudaMemsetAsync(ws.g_thr, 0x7f, ((size_t)Qc + (size_t)Qc * n_ranges) * 4, stream);
+        if ((size_t)Qc * n_ranges > ws.capacity) return cudaErrorInvalidValue;
+        err = cudaMemsetAsync(ws.slots, 0x7f, (size_t)Qc * kKPrime * 4, stream);     /* 3.39e38: "no key yet" */
         if (err != cudaSuccess) return err;
-        float* pub = reinterpret_cast<float*>(ws.g_thr + Qc);
         const float* qk = qkeys + (size_t)q0 * R;
-        if (R == 20) err = launch_tc2<20>(qk, Qc, img, n_db, n_ranges, ws.g_thr, pub, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
-        else err = launch_tc2<40>(qk, Qc, img, n_db, n_ranges, ws.g_thr, pub, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
+        if (R == 20) err = launch_tc2<20>(qk, Qc, img, n_db, n_ranges, ws.slots, ws.hq, ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), stream);
+        else err = launch_tc2<40>(qk, Qc, img, n_db, n_ranges, ws.slots, ws.hq, ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), stream);
         if (err != cudaSuccess) return err;
         const int warps = 4;
         if (metric == 0)
-            knn_rerank2_kernel<0><<<(Qc + warps - 1) / warps, warps * 32, 0, stream>>>(qk, Qc, keys, R, K, n_ranges, ws.prop_s, ws.prop_idx, ws.prop_cut,
+            knn_rerank2_kernel<0><<<(Qc + warps - 1) / warps, warps * 32, 0, stream>>>(qk, Qc, keys, R, K, n_ranges, n_db, ws.hq, ws.hq_cnt, ws.slots,
                                                                                       kn2max, id_mul, id_add, out_ids + (size_t)q0 * K, out_d2 + (size_t)q0 * K, q0,
                                                                                       fail_list, fail_count, ws.err_probe);
         else
-            knn_rerank2_kernel<1><<<(Qc + warps - 1) / warps, warps * 32, 0, stream>>>(qk, Qc, keys, R, K, n_ranges, ws.prop_s, ws.prop_idx, ws.prop_cut,
+            knn_rerank2_kernel<1><<<(Qc + warps - 1) / warps, warps * 32, 0, stream>>>(qk, Qc, keys, R, K, n_ranges, n_db, ws.hq, ws.hq_cnt, ws.slots,
                                                                                       kn2max, id_mul, id_add, out_ids + (size_t)q0 * K, out_d2 + (size_t)q0 * K, q0,
                                                                                       fail_list, fail_count, ws.err_probe);
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;
+    }
+    if (ws.err_probe && getenv("SCL_TC_DEBUG")) {                   /* developer aid */
+        int h[6];
+        cudaStreamSynchronize(stream);
+        {
+            const int Qc = Q < max_b ? Q : max_b;
+            std::vector<int> sl((size_t)Qc * kKPrime);
+            cudaMemcpy(sl.data(), ws.slots, sl.size() * 4, cudaMemcpyDeviceToHost);
+            int per_slot[kKPrime] = {0};
+            for (int q = 0; q < Qc; q++) for (int k = 0; k < kKPrime; k++) if (sl[(size_t)q * kKPrime + k] >= 0x7f000000) per_slot[k]++;
+            fprintf(stderr, "[tc2 slots of the last launch, unfilled per slot]");
+            for (int k = 0; k < kKPrime; k++) fprintf(stderr, " %d", per_slot[k]);
+            fprintf(stderr, "\n");
+        }
+        cudaMemcpy(h, ws.err_probe, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[tc2 Q %d n_db %d] worst |score error| / eps %.3f | uncertified so far: queue overflow %d, fewer than K survivors %d, certificate %d (survivor list full %d) | start-up waits timed out (warps) %d\n",
+                Q, n_db, *reinterpret_cast<float*>(&h[0]), h[1], h[2], h[3], h[4], h[5]);
     }
     return cudaSuccess;
 }

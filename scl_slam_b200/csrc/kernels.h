@@ -47,17 +47,17 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
 // K3 on tcgen05, second generation (k3_knn_tc2.cu): BF16x3 prefilter fed by TMA from a pre-split key image
 // (scl_launch_key_image, 128-key tiles in the tcgen05 shared-memory layout), union-bound thresholds, exact re-rank.
 struct KnnTc2Workspace {
-    float* prop_s;       // [Qc][ranges][K']   (Qc = min(Q, scl_knn_tc2_max_batch()))
-    int32_t* prop_idx;   // [Qc][ranges][K']
-    float* prop_cut;     // [Qc][ranges]
-    int* g_thr;          // [Qc] union bounds, followed by [Qc][ranges] published range minima
+    uint32_t* hq;        // [Qc][ranges] hit queues of scl_knn_tc2_queue_bytes() each (Qc = min(Q, scl_knn_tc2_max_batch()))
+    int* hq_cnt;         // [Qc][ranges] groups queued
+    int* slots;          // [Qc][K'] range minima by range % K' (K' = scl_knn_tc2_kprime())
     float* err_probe;    // null, or one float raised to the largest |prefilter score error| / eps seen (tests)
-    size_t capacity;     // in proposal entries
+    size_t capacity;     // in (query, range) pairs
 };
 bool scl_knn_tc2_supported(int R);
 int scl_knn_tc2_ranges(int Q);
 int scl_knn_tc2_max_batch();
 int scl_knn_tc2_kprime();
+size_t scl_knn_tc2_queue_bytes();
 size_t scl_knn_tc2_image_bytes(int R, int n_keys);
 cudaError_t scl_launch_key_image(const float* keys, const float* knorm, int k_lo, int k_hi, int R, unsigned char* img, cudaStream_t stream);
 cudaError_t scl_launch_knn_tc2(const float* qkeys, int Q, const float* keys, const unsigned char* img, const float* kn2max, int n_db, int R, int K,

@@ -6,11 +6,14 @@ from scl_slam_b200 import synth, engine
 
 MODE = int(os.environ.get("TC_MODE", "3"))
 
-def run(R, S, n, Q, K, metric=0, n_db=None):
+def run(R, S, n, Q, K, metric=0, n_db=None, ordered=False):
     dev = torch.device("cuda:0")
     db = synth.desc_db(n, R, S, seed=3, device=dev)
+    if ordered:   # a database ordered like a trajectory: neighbouring keys are alike, whole stretches are far from any one query
+        db = db[torch.argsort(db.reshape(n, -1).mean(1))].contiguous()
     q, src, shift = synth.desc_queries(db[: min(n, 1 << 16)], Q, seed=4)
     e = engine.ScanContextB200(numRing=R, numSector=S, numCandidates=K)
+    torch.cuda.synchronize()      # the engine runs on its own stream: the generated data must be complete before it reads it
     e.insert_batch_dev(db)
     torch.cuda.synchronize()
     qh = q.cpu().numpy()
@@ -22,7 +25,7 @@ def run(R, S, n, Q, K, metric=0, n_db=None):
     b = e.query_batch(q_desc=qh, K=K, n_db=n_db, metric=metric)
     st = e.knn_stats()
     same = {k: bool(np.array_equal(a[k], b[k], equal_nan=True)) for k in a}
-    print(f"R={R} S={S} n={n} n_db={n_db} Q={Q} K={K} metric={metric}: {same} stats={st} t={time.time()-t:.3f}s", flush=True)
+    print(f"R={R} S={S} n={n} n_db={n_db} Q={Q} K={K} metric={metric} ordered={ordered}: {same} stats={st} t={time.time()-t:.3f}s", flush=True)
     if not all(same.values()):
         bad = np.where((a["cand_ids"] != b["cand_ids"]).any(1))[0]
         print("  mismatching queries", len(bad), bad[:5])
@@ -61,5 +64,6 @@ if __name__ == "__main__":
         ok &= run(20, 60, 70001, 300, 10, n_db=69901)
         ok &= run(40, 120, 50000, 200, 10)
         ok &= run(20, 60, 200000, 2500, 10)
+        ok &= run(20, 60, 300000, 1024, 10, ordered=True)
         print("TC_CHECK", "OK" if ok else "FAIL", flush=True)
     timing()
