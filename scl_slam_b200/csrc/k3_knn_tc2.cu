@@ -227,7 +227,7 @@ __device__ __noinline__ int compact_queue(uint4* q, int n, float thr)
 }
 
 // ---- the query kernel ---------------------------------------------------------------------------------
-template <int R>
+template <int R, bool TIMES>
 __global__ void __launch_bounds__(kThreads, 1) knn_tc2_kernel(
     const float* __restrict__ qkeys, int Q, const unsigned char* __restrict__ img, int key_hi, int n_ranges,
     long long* __restrict__ times /* null, or [grid][16] developer counters (SCL_TC_TIMES=1) */,
@@ -343,10 +343,11 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc2_kernel(
             }
         };
         long long tw = 0, c0 = 0, t_ld = 0, t_ex = 0;
-        if (times) c0 = clock64();
+        if (TIMES) c0 = clock64();
         const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(qt * kNH);
         uint32_t va[32], vb[32];
         const int n_it = (kNT / kNH) * n_tiles;             /* accumulator slots to drain */
+        float next_thr = thr;                               /* the service warps' bound, read one slot ahead of its use */
         if (n_tiles > 0) {
             /* Start-up: with no threshold yet, every score of the first tile would be a hit. Instead the first 128 keys are
              * read twice: a first pass only finds the range minimum so far and publishes it; as soon as K' ranges have done
@@ -374,6 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc2_kernel(
                 scl_mbar_wait(&tfull[qt], 0);
                 tc_fence_after();
             }
+            if (live) next_thr = fminf(next_thr, ordered_float(*my_sthr));
             tmem_ld32_issue(lane_base, va);
         }
         // One accumulator slot (kNH keys) per iteration, as pairs of 32-column chunks (va, vb). The load of the next chunk is
@@ -383,25 +385,26 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc2_kernel(
             const int s = it % kAccStages;
             const int key0 = (range + (it / (kNT / kNH)) * n_ranges) * kNT + (it % (kNT / kNH)) * kNH;
             const uint32_t col0 = lane_base + (uint32_t)(s * 2 * kNH);
-            if (live) thr = fminf(thr, ordered_float(*my_sthr));
+            thr = fminf(thr, next_thr);
             long long p0 = 0;
 #pragma unroll
             for (int pr = 0; pr < kNH / 64; pr++) {
-                if (times) p0 = clock64();
+                if (TIMES) p0 = clock64();
                 tmem_wait32(va);
-                if (times) { const long long p1 = clock64(); t_ld += p1 - p0; p0 = p1; }
+                if (TIMES) { const long long p1 = clock64(); t_ld += p1 - p0; p0 = p1; }
                 tmem_ld32_issue(col0 + 64 * pr + 32, vb);
                 examine(va, key0 + 64 * pr);
-                if (times) { const long long p1 = clock64(); t_ex += p1 - p0; p0 = p1; }
+                if (TIMES) { const long long p1 = clock64(); t_ex += p1 - p0; p0 = p1; }
                 tmem_wait32(vb);
-                if (times) { const long long p1 = clock64(); t_ld += p1 - p0; p0 = p1; }
+                if (TIMES) { const long long p1 = clock64(); t_ld += p1 - p0; p0 = p1; }
                 if (pr + 1 < kNH / 64) {
                     tmem_ld32_issue(col0 + 64 * pr + 64, va);
-                    if (times) p0 = clock64();
+                    if (TIMES) p0 = clock64();
                     examine(vb, key0 + 64 * pr + 32);
-                    if (times) t_ex += clock64() - p0;
+                    if (TIMES) t_ex += clock64() - p0;
                 }
             }
+            if (live) next_thr = ordered_float(*my_sthr);
             /* every score of this slot is in registers: hand it back to the MMA issuer now */
             tc_fence_before();
             __syncwarp();
@@ -417,19 +420,19 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc2_kernel(
                     pending = true;
                 }
             }
-            if (times) p0 = clock64();
+            if (TIMES) p0 = clock64();
             examine(vb, key0 + kNH - 32);
-            if (times) t_ex += clock64() - p0;
+            if (TIMES) t_ex += clock64() - p0;
             if (pending) {
                 long long w0 = 0;
-                if (times) w0 = clock64();
+                if (TIMES) w0 = clock64();
                 scl_mbar_wait(&tfull[s1 * 2 + qt], ph1);
-                if (times) tw += clock64() - w0;
+                if (TIMES) tw += clock64() - w0;
                 tc_fence_after();
                 tmem_ld32_issue(lane_base + (uint32_t)(s1 * 2 * kNH), va);
             }
         }
-        if (times) {
+        if (TIMES) {
             const int wp = __reduce_add_sync(0xffffffffu, n_hit), wmax = __reduce_max_sync(0xffffffffu, n_hit);
             if (lane == 0) {
                 long long* o = times + (size_t)blockIdx.x * 16;
@@ -472,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc2_kernel(
             if (last) break;
             if (sweeps > 64) __nanosleep(1000);          /* the bound moves fast at the start: sweep back to back there */
         }
-        if (times && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(times + (size_t)blockIdx.x * 16 + 5), (unsigned long long)sweeps);
+        if (TIMES && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(times + (size_t)blockIdx.x * 16 + 5), (unsigned long long)sweeps);
     } else if (warp == 1) {
         // ===== TMA issuer: one thread, one bulk copy per key tile =======================================
         if (lane == 0) {
@@ -496,9 +499,9 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc2_kernel(
                 const int tile = it / SPT, hf = it % SPT;           /* kNH keys of a key tile -> one accumulator slot per query tile */
                 const int b = tile % NS; const uint32_t bph = (tile / NS) & 1;
                 const int s = it % kAccStages; const uint32_t ph = (it / kAccStages) & 1;
-                if (times) c0 = clock64();
+                if (TIMES) c0 = clock64();
                 if (hf == 0) scl_mbar_wait(&full[b], bph);          /* key tile landed */
-                if (times) { const long long c1 = clock64(); t_fu += c1 - c0; c0 = c1; }
+                if (TIMES) { const long long c1 = clock64(); t_fu += c1 - c0; c0 = c1; }
                 const uint32_t bs = b_base + (uint32_t)b * C::TILE_BYTES + (uint32_t)hf * (kNH / 8) * C::SBO;   /* rows 64*hf.. of the tile */
 #pragma unroll
                 for (int qt = 0; qt < 2; qt++) {
@@ -512,9 +515,9 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc2_kernel(
                     tc_commit(&tfull[s * 2 + qt]);                  /* slot ready for the epilogue */
                 }
                 if (hf == SPT - 1) tc_commit(&empty[b]);                  /* key tile reusable once these MMAs retire */
-                if (times) { const long long c1 = clock64(); t_te += c1 - c0; }
+                if (TIMES) { const long long c1 = clock64(); t_te += c1 - c0; }
             }
-            if (times) { times[(size_t)blockIdx.x * 16 + 6] = t_fu; times[(size_t)blockIdx.x * 16 + 7] = t_te; times[(size_t)blockIdx.x * 16 + 8] = n_tiles; }
+            if (TIMES) { times[(size_t)blockIdx.x * 16 + 6] = t_fu; times[(size_t)blockIdx.x * 16 + 7] = t_te; times[(size_t)blockIdx.x * 16 + 8] = n_tiles; }
         }
         __syncwarp();
     }
@@ -544,8 +547,11 @@ __device__ __forceinline__ float exact_d2(const float* __restrict__ q, const flo
     return result;
 }
 
-// Phase B: exact re-rank + certificate. One warp per query; a lane walks the hit queues of the ranges l, l+32, ...
+// Phase B: exact re-rank + certificate. One CTA of 128 threads per query: the hit queues of all ranges are flattened
+// (counts -> prefix sums in shared memory) so that every thread reads a few independent groups, the survivors (scores at
+// or below the cut) are re-scored exactly, and warp 0 selects the top-K and certifies it.
 constexpr int kMaxSurvivors = 256;
+constexpr int kMaxRanges = 160;
 template <int METRIC>
 __global__ void __launch_bounds__(128) knn_rerank2_kernel(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys, int R, int K,
                                                           int n_ranges, int n_db, const uint32_t* __restrict__ hq, const int* __restrict__ hq_cnt,
@@ -553,72 +559,91 @@ __global__ void __launch_bounds__(128) knn_rerank2_kernel(const float* __restric
                                                           int32_t* __restrict__ out_ids, float* __restrict__ out_d2, int q_off,
                                                           int32_t* __restrict__ fail_list, int* __restrict__ fail_count, float* __restrict__ err_probe)
 {
-    __shared__ int s_id[4][kMaxSurvivors];
-    __shared__ float s_d[4][kMaxSurvivors];
-    __shared__ float s_s[4][kMaxSurvivors];
-    __shared__ int s_count[4];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int qi = blockIdx.x * (blockDim.x >> 5) + w;
-    if (qi >= Q) return;
+    __shared__ int s_id[kMaxSurvivors];
+    __shared__ float s_d[kMaxSurvivors];
+    __shared__ float s_s[kMaxSurvivors];
+    __shared__ int s_pre[kMaxRanges + 1];
+    __shared__ float s_q[64];
+    __shared__ int s_count, s_overflow;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int qi = blockIdx.x;
     const float* q = qkeys + (size_t)qi * R;
     const float inf = __int_as_float(0x7f800000);
-    /* The cut: the query's final union bound (the maximum of its K' slots). Everything that was not queued scored >= it, so every key scoring below it
-     * is in a queue; queued keys above it cannot be certified anyway and are skipped: about K' survive. */
+    /* The cut: the query's final union bound (the maximum of its K' slots). Everything that was not queued scored >= it,
+     * so every key scoring below it is in a queue; queued keys above it cannot be certified anyway and are skipped:
+     * about K' survive. */
     int gt = lane < kKPrime ? __ldg(slots + (size_t)qi * kKPrime + lane) : (int)0x80000000;
     gt = __reduce_max_sync(0xffffffffu, gt);
     const float cut = gt < 0x7f000000 ? ordered_float(gt) : inf;
-    if (lane == 0) s_count[w] = 0;
-    __syncwarp();
-    bool overflow = false;
-    for (int r = lane; r < n_ranges; r += 32) {
-        int cnt = __ldg(hq_cnt + (size_t)qi * n_ranges + r);
-        if (cnt > kQueueCap) { overflow = true; cnt = kQueueCap; }
-        const uint4* g = reinterpret_cast<const uint4*>(hq + ((size_t)qi * n_ranges + r) * (size_t)(kQueueCap * 12));
-#pragma unroll 2
-        for (int e = 0; e < cnt; e++) {
-            const uint4 k4 = __ldcg(g + 3 * e), a4 = __ldcg(g + 3 * e + 1), b4 = __ldcg(g + 3 * e + 2);
-            const float sc[8] = {__uint_as_float(a4.x), __uint_as_float(a4.y), __uint_as_float(a4.z), __uint_as_float(a4.w),
-                                 __uint_as_float(b4.x), __uint_as_float(b4.y), __uint_as_float(b4.z), __uint_as_float(b4.w)};
+    if (t == 0) { s_count = 0; s_overflow = 0; }
+    if (t < R) s_q[t] = __ldg(q + t);
+    for (int r = t; r < n_ranges; r += 128) {
+        int c = __ldg(hq_cnt + (size_t)qi * n_ranges + r);
+        if (c > kQueueCap) { s_overflow = 1; c = kQueueCap; }
+        s_pre[r + 1] = c;
+    }
+    __syncthreads();
+    if (warp == 0) {                                    /* exclusive prefix sums of the counts, 32 ranges at a time */
+        int carry = 0;
+        for (int base = 0; base < n_ranges; base += 32) {
+            const int r = base + lane;
+            int v = r < n_ranges ? s_pre[r + 1] : 0;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int id = (int)k4.x + i;
-                if (sc[i] <= cut && id < n_db) {
-                    const int pos = atomicAdd(&s_count[w], 1);
-                    if (pos < kMaxSurvivors) { s_id[w][pos] = id; s_s[w][pos] = sc[i]; }
-                }
+            for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, v, off); if (lane >= off) v += o; }
+            if (r < n_ranges) s_pre[r + 1] = carry + v;
+            carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+        if (lane == 0) s_pre[0] = 0;
+    }
+    __syncthreads();
+    const int total = s_pre[n_ranges];
+    for (int g = t; g < total; g += 128) {
+        int lo = 0, hi = n_ranges;                      /* the range that holds group g: last r with s_pre[r] <= g */
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_pre[mid] <= g) lo = mid; else hi = mid; }
+        const uint4* gp = reinterpret_cast<const uint4*>(hq + ((size_t)qi * n_ranges + lo) * (size_t)(kQueueCap * 12)) + 3 * (g - s_pre[lo]);
+        const uint4 k4 = __ldcg(gp), a4 = __ldcg(gp + 1), b4 = __ldcg(gp + 2);
+        const float sc[8] = {__uint_as_float(a4.x), __uint_as_float(a4.y), __uint_as_float(a4.z), __uint_as_float(a4.w),
+                             __uint_as_float(b4.x), __uint_as_float(b4.y), __uint_as_float(b4.z), __uint_as_float(b4.w)};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int id = (int)k4.x + i;
+            if (sc[i] <= cut && id < n_db) {
+                const int pos = atomicAdd(&s_count, 1);
+                if (pos < kMaxSurvivors) { s_id[pos] = id; s_s[pos] = sc[i]; }
             }
         }
     }
-    overflow = __any_sync(0xffffffffu, overflow);
-    __syncwarp();
-    int n_surv = s_count[w];
+    __syncthreads();
+    bool overflow = s_overflow != 0;
+    int n_surv = s_count;
     if (n_surv > kMaxSurvivors) { overflow = true; n_surv = kMaxSurvivors; }
     float qn = 0.0f;
-    for (int d = 0; d < R; d++) qn = fmaf(q[d], q[d], qn);
+    for (int d = 0; d < R; d++) qn = fmaf(s_q[d], s_q[d], qn);
     const float sn = sqrtf(qn) + sqrtf(__ldg(kn2max));
     const float eps0 = 3.0517578125e-05f * sn * sn;                 /* 2^-15 (|q| + |k|max)^2 */
     float worst_err = 0.0f;
-    for (int c = lane; c < n_surv; c += 32) {
-        float d = exact_d2<METRIC>(q, keys + (size_t)s_id[w][c] * R, R);
-        if (err_probe) worst_err = fmaxf(worst_err, fabsf((d - qn) - s_s[w][c]) / eps0);
+    for (int c = t; c < n_surv; c += 128) {
+        float d = exact_d2<METRIC>(s_q, keys + (size_t)s_id[c] * R, R);
+        if (err_probe) worst_err = fmaxf(worst_err, fabsf((d - qn) - s_s[c]) / eps0);
         if (METRIC == 1 && !(d > FLT_EPSILON)) d = inf;          /* libnabo self-match rule */
         if (!(d < (METRIC == 0 ? FLT_MAX : inf))) d = inf;       /* never accepted by the trees */
-        s_d[w][c] = d;
+        s_d[c] = d;
     }
     if (err_probe) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) worst_err = fmaxf(worst_err, __shfl_xor_sync(0xffffffffu, worst_err, off));
-        if (lane == 0) atomicMax(reinterpret_cast<int*>(err_probe), __float_as_int(worst_err));   /* non-negative floats order as ints */
+        if (lane == 0 && worst_err > 0.0f) atomicMax(reinterpret_cast<int*>(err_probe), __float_as_int(worst_err));   /* non-negative floats order as ints */
     }
-    __syncwarp();
+    __syncthreads();
+    if (warp != 0) return;
     /* K rounds: smallest (d2, id) strictly after the previous pick */
     float pd = -1.0f; int pi = -1; float dK = 0.0f; int found = 0;
     for (int r = 0; r < K; r++) {
         float bd = inf; int bi = 0x7fffffff;
         for (int c = lane; c < n_surv; c += 32) {
-            const float d = s_d[w][c];
+            const float d = s_d[c];
             if (!(d < inf)) continue;
-            const int id = s_id[w][c] * id_mul + id_add;
+            const int id = s_id[c] * id_mul + id_add;
             if (d < pd || (d == pd && id <= pi)) continue;
             if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; }
         }
@@ -687,7 +712,8 @@ static cudaError_t launch_tc2(const float* qkeys, int Q, const unsigned char* im
     using C = Tc2Cfg<R>;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(knn_tc2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(knn_tc2_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(knn_tc2_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::TOTAL);
         if (e != cudaSuccess) return e;
         attr = true;
     }
@@ -696,7 +722,8 @@ static cudaError_t launch_tc2(const float* qkeys, int Q, const unsigned char* im
     const bool want_times = getenv("SCL_TC_TIMES") != nullptr;       /* developer aid: per-role cycle counters on stderr */
     const int nb = groups * n_ranges;
     if (want_times) { cudaMalloc(&times, (size_t)nb * 16 * sizeof(long long)); cudaMemsetAsync(times, 0, (size_t)nb * 128, stream); }
-    knn_tc2_kernel<R><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, times, slots, hq, hq_cnt, dbg);
+    if (want_times) knn_tc2_kernel<R, true><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, times, slots, hq, hq_cnt, dbg);
+    else knn_tc2_kernel<R, false><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, nullptr, slots, hq, hq_cnt, dbg);
     if (want_times) {
         std::vector<long long> h((size_t)nb * 16);
         cudaStreamSynchronize(stream);
@@ -732,13 +759,12 @@ cudaError_t scl_launch_knn_tc2(const float* qkeys, int Q, const float* keys, con
         if (R == 20) err = launch_tc2<20>(qk, Qc, img, n_db, n_ranges, ws.slots, ws.hq, ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), stream);
         else err = launch_tc2<40>(qk, Qc, img, n_db, n_ranges, ws.slots, ws.hq, ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), stream);
         if (err != cudaSuccess) return err;
-        const int warps = 4;
         if (metric == 0)
-            knn_rerank2_kernel<0><<<(Qc + warps - 1) / warps, warps * 32, 0, stream>>>(qk, Qc, keys, R, K, n_ranges, n_db, ws.hq, ws.hq_cnt, ws.slots,
+            knn_rerank2_kernel<0><<<Qc, 128, 0, stream>>>(qk, Qc, keys, R, K, n_ranges, n_db, ws.hq, ws.hq_cnt, ws.slots,
                                                                                       kn2max, id_mul, id_add, out_ids + (size_t)q0 * K, out_d2 + (size_t)q0 * K, q0,
                                                                                       fail_list, fail_count, ws.err_probe);
         else
-            knn_rerank2_kernel<1><<<(Qc + warps - 1) / warps, warps * 32, 0, stream>>>(qk, Qc, keys, R, K, n_ranges, n_db, ws.hq, ws.hq_cnt, ws.slots,
+            knn_rerank2_kernel<1><<<Qc, 128, 0, stream>>>(qk, Qc, keys, R, K, n_ranges, n_db, ws.hq, ws.hq_cnt, ws.slots,
                                                                                       kn2max, id_mul, id_add, out_ids + (size_t)q0 * K, out_d2 + (size_t)q0 * K, q0,
                                                                                       fail_list, fail_count, ws.err_probe);
         err = cudaGetLastError();
