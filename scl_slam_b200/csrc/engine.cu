@@ -142,7 +142,7 @@ int sync_key_image(scl_engine* e)
     if (e->img_cap < e->cap) {
         /* derived data: on growth the image is simply rebuilt from the keys */
         if (e->d_kimg) { CK(cudaStreamSynchronize(e->stream)); cudaFree(e->d_kimg); e->d_kimg = nullptr; }
-        const size_t bytes = scl_knn_tc2_image_bytes(R, e->cap);
+        const size_t bytes = scl_knn_tc_image_bytes(R, e->cap);
         CK(cudaMalloc(&e->d_kimg, bytes));
         CK(cudaMemsetAsync(e->d_kimg, 0, bytes, e->stream));
         e->img_cap = e->cap; e->img_n = 0;
@@ -189,39 +189,25 @@ int knn_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int
     ws.part_ids = e->part_ids.as<int32_t>(); ws.part_d2 = e->part_d2.as<float>(); ws.capacity = (size_t)Q * splits * K;
     /* K3 variant: the tensor-core prefilter pays off once there is a batch to fill 128-row tiles and a
      * database worth streaming; single queries and small databases take the exact CUDA-core kernel. */
-    bool use_tc = scl_knn_tc_supported(R) && K <= scl_knn_tc_kprime(K) - 2 &&
-                  (e->knn_mode == 2 || (e->knn_mode == 0 && Q >= 64 && n_db >= 32768));
-    const bool use_tc2 = scl_knn_tc2_supported(R) && K <= scl_knn_tc2_kprime() - 2 && e->knn_mode == 3;
-    if (use_tc2) { use_tc = false; int rc = sync_key_image(e); if (rc) return rc; }
+    const bool use_tc = scl_knn_tc_supported(R) && K <= scl_knn_tc_kprime() - 2 &&
+                        (e->knn_mode == 2 || (e->knn_mode == 0 && Q >= 64 && n_db >= 32768));
+    if (use_tc) { int rc = sync_key_image(e); if (rc) return rc; }
     {
         StageTimer st(e, 1);
-        if (use_tc2) {
-            const int Qc = Q < scl_knn_tc2_max_batch() ? Q : scl_knn_tc2_max_batch();
-            const int ranges = scl_knn_tc2_ranges(Qc);
+        if (use_tc) {
+            const int Qc = Q < scl_knn_tc_max_batch() ? Q : scl_knn_tc_max_batch();
+            const int ranges = scl_knn_tc_ranges(Qc);
             const size_t pairs = (size_t)Qc * ranges;
-            CK(e->tc_prop_s.ensure(pairs * scl_knn_tc2_queue_bytes())); CK(e->tc_prop_cut.ensure(pairs * 4));
+            CK(e->tc_queues.ensure(pairs * scl_knn_tc_queue_bytes())); CK(e->tc_queue_cnt.ensure(pairs * 4));
             CK(e->tc_fail_list.ensure((size_t)Q * 4)); CK(e->tc_fail_count.ensure(64));
-            CK(e->tc_gthr.ensure((size_t)Qc * scl_knn_tc2_kprime() * 4));
+            CK(e->tc_slots.ensure((size_t)Qc * scl_knn_tc_kprime() * 4));
             float* probe = nullptr;
             if (e->count_fallbacks) {
                 if (!e->tc_err_probe.p) { CK(e->tc_err_probe.ensure(64)); CK(cudaMemsetAsync(e->tc_err_probe.p, 0, 64, e->stream)); }
                 probe = e->tc_err_probe.as<float>();
             }
-            KnnTc2Workspace tw{e->tc_prop_s.as<uint32_t>(), e->tc_prop_cut.as<int>(), e->tc_gthr.as<int>(), probe, pairs};
-            CK(scl_launch_knn_tc2(e->qkeys.as<float>(), Q, e->d_keys, e->d_kimg, e->d_kn2max, n_db, R, K, metric, e->world, e->rank, tw,
-                                  cand_ids, cand_d2, e->tc_fail_list.as<int32_t>(), e->tc_fail_count.as<int>(), e->stream));
-            CK(scl_launch_knn_exact(e->qkeys.as<float>(), Q, e->d_keys, n_db, R, K, metric, e->world, e->rank,
-                                    e->tc_fail_list.as<int32_t>(), e->tc_fail_count.as<int>(), ws, cand_ids, cand_d2, e->stream));
-            e->stat_tc_queries += Q;
-        } else if (use_tc) {
-            const int ranges = 4 * scl_knn_tc_ranges(Q), kp = scl_knn_tc_kprime(K);   /* two passes x two column halves per CTA */
-            const size_t ncand = (size_t)Q * ranges * kp;
-            CK(e->tc_prop_s.ensure(ncand * 4)); CK(e->tc_prop_idx.ensure(ncand * 4)); CK(e->tc_exact.ensure(ncand * 4));
-            CK(e->tc_prop_cut.ensure((size_t)Q * ranges * 4));
-            CK(e->tc_fail_list.ensure((size_t)Q * 4)); CK(e->tc_fail_count.ensure(64)); CK(e->tc_gthr.ensure((size_t)Q * 4));
-            KnnTcWorkspace tw{e->tc_prop_s.as<float>(), e->tc_prop_idx.as<int32_t>(), e->tc_prop_cut.as<float>(), e->tc_exact.as<float>(),
-                              e->tc_gthr.as<int>(), ncand};
-            CK(scl_launch_knn_tc(e->qkeys.as<float>(), Q, e->d_keys, e->d_knorm, e->d_kn2max, n_db, R, K, metric, e->world, e->rank, tw,
+            KnnTcWorkspace tw{e->tc_queues.as<uint32_t>(), e->tc_queue_cnt.as<int>(), e->tc_slots.as<int>(), probe, pairs};
+            CK(scl_launch_knn_tc(e->qkeys.as<float>(), Q, e->d_keys, e->d_kimg, e->d_kn2max, n_db, R, K, metric, e->world, e->rank, tw,
                                  cand_ids, cand_d2, e->tc_fail_list.as<int32_t>(), e->tc_fail_count.as<int>(), e->stream));
             /* uncertified queries (normally none) are redone exactly; CTAs beyond the list length exit at once */
             CK(scl_launch_knn_exact(e->qkeys.as<float>(), Q, e->d_keys, n_db, R, K, metric, e->world, e->rank,
@@ -232,7 +218,7 @@ int knn_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int
                                     cand_ids, cand_d2, e->stream));
         }
     }
-    if ((use_tc || use_tc2) && e->count_fallbacks) {
+    if (use_tc && e->count_fallbacks) {
         int nfail = 0;
         CK(cudaMemcpyAsync(&nfail, e->tc_fail_count.p, 4, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
@@ -358,8 +344,8 @@ int scl_destroy(scl_engine* e)
         DevBuf* bufs[] = {&e->pts, &e->offsets, &e->gbins, &e->tickets, &e->stage_desc, &e->stage_keys, &e->stage_knorm,
                           &e->bins_ring, &e->bins_sector, &e->qdesc, &e->qids, &e->qlocal, &e->qkeys, &e->qknorm, &e->part_ids,
                           &e->part_d2, &e->cand_ids, &e->cand_d2, &e->cand_local, &e->cand_dist, &e->cand_shift, &e->best_id,
-                          &e->best_dist, &e->best_shift, &e->tc_prop_s, &e->tc_prop_idx, &e->tc_prop_cut, &e->tc_exact,
-                          &e->tc_fail_list, &e->tc_fail_count, &e->tc_gthr, &e->tc_err_probe, &e->icp_src, &e->icp_tgt, &e->icp_raw, &e->icp_acc, &e->icp_nn,
+                          &e->best_dist, &e->best_shift, &e->tc_queues, &e->tc_queue_cnt, &e->tc_slots,
+                          &e->tc_fail_list, &e->tc_fail_count, &e->tc_err_probe, &e->icp_src, &e->icp_tgt, &e->icp_raw, &e->icp_acc, &e->icp_nn,
                           &e->icp_grid[0][0], &e->icp_grid[0][1], &e->icp_grid[0][2], &e->icp_grid[0][3], &e->icp_grid[0][4],
                           &e->icp_grid[1][0], &e->icp_grid[1][1], &e->icp_grid[1][2], &e->icp_grid[1][3], &e->icp_grid[1][4]};
         for (DevBuf* b : bufs) b->release();
@@ -385,8 +371,8 @@ int scl_set_stream(scl_engine* e, void* s)
 int scl_set_knn_mode(scl_engine* e, int mode, int count_fallbacks)
 {
     LOCK();
-    if (mode < 0 || mode > 3) FAIL(SCL_ERR_INVALID, "mode must be 0 (auto), 1 (exact), 2 (TF32 prefilter) or 3 (BF16x3 prefilter)");
-    if (mode >= 2 && !scl_knn_tc_supported(e->p.num_ring)) FAIL(SCL_ERR_UNSUPPORTED, "tensor-core kNN is built for 20 and 40 rings");
+    if (mode < 0 || mode > 2) FAIL(SCL_ERR_INVALID, "mode must be 0 (auto), 1 (exact) or 2 (tensor core)");
+    if (mode == 2 && !scl_knn_tc_supported(e->p.num_ring)) FAIL(SCL_ERR_UNSUPPORTED, "tensor-core kNN is built for 20 and 40 rings");
     e->knn_mode = mode; e->count_fallbacks = count_fallbacks != 0;
     return SCL_OK;
 }

@@ -38,9 +38,9 @@ struct scl_engine {
     int n = 0, cap = 0;
     float *d_desc = nullptr, *d_keys = nullptr, *d_knorm = nullptr;
     float* d_kn2max = nullptr;             /* device scalar: largest squared ring-key norm in the database */
-    unsigned char* d_kimg = nullptr;       /* tensor-core key image: 128-key tiles in the tcgen05 operand layout (k3_knn_tc2.cu) */
+    unsigned char* d_kimg = nullptr;       /* tensor-core key image: 128-key tiles in the tcgen05 operand layout (k3_knn_tc.cu) */
     int img_n = 0, img_cap = 0;            /* keys [0, img_n) have an image; capacity in keys */
-    int knn_mode = 0;                      /* 0 auto, 1 exact CUDA-core kernel, 2 TF32 prefilter (first generation), 3 BF16x3 prefilter */
+    int knn_mode = 0;                      /* 0 auto, 1 exact CUDA-core kernel, 2 tensor-core prefilter */
     long long stat_tc_queries = 0, stat_fallback_queries = 0;
     bool count_fallbacks = false;
     std::vector<std::pair<int8_t, int>> index;
@@ -51,7 +51,7 @@ struct scl_engine {
     DevBuf pts, offsets, gbins, tickets, stage_desc, stage_keys, stage_knorm, bins_ring, bins_sector;
     DevBuf qdesc, qids, qlocal, qkeys, qknorm, part_ids, part_d2, cand_ids, cand_d2, cand_local, cand_dist, cand_shift,
         best_id, best_dist, best_shift;
-    DevBuf tc_prop_s, tc_prop_idx, tc_prop_cut, tc_exact, tc_fail_list, tc_fail_count, tc_gthr, tc_err_probe;
+    DevBuf tc_queues, tc_queue_cnt, tc_slots, tc_fail_list, tc_fail_count, tc_err_probe;
     DevBuf icp_src, icp_tgt, icp_raw, icp_grid[2][5], icp_acc, icp_nn;
     size_t gbins_scans = 0;
     /* per-stage event timing */

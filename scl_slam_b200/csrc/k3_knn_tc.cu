@@ -1,62 +1,90 @@
-// k3_knn_tc.cu — K3 on the 5th-generation tensor cores: a tcgen05 prefilter for the ring-key kNN,
-// followed by an exact re-rank that keeps the result bit-identical to k3_knn.cu.
+// k3_knn_tc.cu — K3 on the 5th-generation tensor cores, second generation: a BF16x3 tcgen05 prefilter fed by
+// TMA from a pre-split key image, followed by an exact re-rank that keeps the result bit-identical to k3_knn.cu.
 //
 // Replaces (together with k3_knn.cu) nanoflann findNeighbors, /root/reference/include/descriptor.h:1714-1716,
 // and libnabo knn, descriptor.h:1642.
 //
-// Phase A (knn_tc_kernel): the score S(q,k) = |k|^2 - 2 q.k of every (query, key) pair is one
-// augmented GEMM on tcgen05.mma kind::tf32 with FP32 accumulators in TMEM. To get ~FP32 accuracy out
-// of TF32 inputs every value is split x = hi + lo (hi = top 11 significant bits, lo = next 11):
-//      S = [-2q_hi | 1 1 1] . [k_hi | n_hi n_mid n_lo]   (A1 x B_hi)
-//        + [-2q_lo | 0 0 0] . [k_hi | ...]               (A2 x B_hi)
-//        + [-2q_hi | 1 1 1] . [k_lo | 0 0 0]             (A1 x B_lo)
-//   with |k|^2 = n_hi + n_mid + n_lo carried through the same contraction (three more columns).
-//   One CTA per SM: it owns a 128-query tile (M = 128 = TMEM lanes) and one contiguous range of the
-//   key matrix, and is warp-specialised:
-//     warps 4-11 epilogue  : tcgen05.ld 32 columns at a time (thread = query = TMEM lane), compare
-//                            against the thread's running threshold, push hits to a staging buffer,
-//                            fold the staging buffers into per-thread sorted top-K' lists
-//     warps 1-3  producers : stream raw keys (80 B each) from HBM, split hi/lo in registers, write
-//                            the UMMA K-major no-swizzle core-matrix layout into shared memory
-//     warp  0    MMA issuer: one thread issues the 9 tcgen05.mma per key tile and commits to
-//                            mbarriers (smem stage free / accumulator ready)
-//   Shared-memory stages and the two TMEM accumulator stages are handed around with mbarriers only.
+// Score. S(q,k) = |k|^2 - 2 q.k orders the keys of one query exactly like the squared distance. Every float is
+// split into bfloat16 pieces x = x0 + x1 + (rest), and the three largest cross products are contracted in ONE
+// K-concatenated GEMM on tcgen05.mma kind::f16 (BF16 inputs, FP32 accumulators in TMEM):
+//      A row (query) = [ -2 q0 | -2 q0 | -2 q1 | 1 1 1 0.. ]      (3R + 3 columns, padded to a multiple of 16)
+//      B row (key)   = [   k0  |   k1  |   k0  | n0 n1 n2 0.. ]   with |k|^2 = n0 + n1 + n2 exactly
+//   The dropped products (q0.k2, q1.k1, q2.k0) are bounded by 1.5 * 2^-16 |q||k|; the certificate below uses
+//   eps = 2^-15 (|q| + |k|max)^2, which leaves more than 5x room for the accumulation error of the tensor core.
+//   R = 20: 64 columns = 4 MMAs of K = 16 per 128x128 tile (the TF32x3 kernel this replaces needed 9 at half the rate).
 //
-// Phase B (knn_rerank_kernel): one warp per query recomputes the EXACT float distance (the
-//   reference's accumulation order, k3_knn.cu) of every proposed key, selects the top-K by
-//   (d2, id), and CERTIFIES the result: with T the smallest per-range cut-off score and eps the
-//   prefilter's error bound, every key the prefilter dropped has exact d2 > T + |q|^2 - eps; if the
-//   K-th selected distance is below that, no dropped key can belong to (or tie with) the top-K.
-//   Queries that fail the certificate are appended to a list and redone by the exact kernel.
+// Key image (key_image_kernel). The B operand is computed ONCE per inserted key and kept in HBM in exactly the
+// shared-memory layout tcgen05 reads (K-major, no swizzle, 8x16-byte core matrices): one 128-key tile is one
+// contiguous block (16 KB at R = 20), so a tile is moved by a single cp.async.bulk (TMA) and no thread of the
+// query kernel ever touches a key.
 //
-// Roofline: 2*R*Q*N flops against the tensor pipe, 4*R*N bytes against HBM; in practice bound by
-// the TMEM read-out + compare of Q*N accumulators in the epilogue warps.
+// Query kernel (knn_tc_kernel). One CTA per SM owns 256 queries (two M = 128 accumulator sets) and one contiguous
+// range of key tiles, so every key tile fetched from L2 is used for 256 queries. Warp roles:
+//     warp 0      MMA issuer : one thread; per key tile 2 x KSTEPS tcgen05.mma, committed per query tile
+//     warp 1      TMA issuer : one thread; ring of NSTAGE key tiles in shared memory
+//     warps 2-3   threshold service (below)
+//     warps 4-11  epilogue   : thread = query = TMEM lane. tcgen05.ld 32 columns at a time, double buffered
+//                              (the next load is in flight while the current 32 scores are examined); the common
+//                              case is a FMNMX3 min-tree and one compare against the query's threshold
+//   TMEM: 2 stages x 2 query tiles x 128 FP32 columns = all 512 columns, handed around with mbarriers.
+//
+// Thresholds. A thread keeps the K' = 16 best (score, key) of its (query, range) in registers and drops everything
+// at or above its threshold. The threshold is min(own K'-th best, union bound): every thread publishes the best
+// score of its range; for a query, the K'-th smallest of the C published range minima is backed by K' distinct keys,
+// so it bounds the global K'-th best score from above (pass fraction ~ 1.3 K'/n_seen_by_all_CTAs instead of
+// K'/n_seen_by_one). The service warps recompute that bound continuously for the CTA's share of the queries and
+// publish it in g_thr; epilogue threads read it once per tile. No bootstrap or sample pass is needed.
+//
+// Re-rank + certificate (knn_rerank_kernel). One warp per query: the proposals scoring at or below the query's cut
+// (the smallest final threshold of its ranges) are re-scored with the reference's exact float order (k3_knn.cu),
+// the top-K by (d2, id) is selected, and the result is CERTIFIED: every key the prefilter dropped has score >= cut,
+// i.e. exact d2 > cut + |q|^2 - eps; if the K-th selected distance is below that, no dropped key can belong to (or
+// tie with) the top-K. Queries that fail are appended to a list and redone by the exact kernel.
+//
+// Roofline: 2*R*Q*N algorithmic flops against the tensor pipe (the kernel issues 3.2x that in BF16), 4*R*N
+// algorithmic bytes against HBM (the image is 128 B/key at R = 20, read once per 256 queries from L2).
 #include "common.cuh"
 #include "kernels.h"
+
+#include <cuda_bf16.h>
 
 #include <cfloat>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
 
+#ifndef SCL_TC_NH
+#define SCL_TC_NH 128
+#endif
+
 namespace {
 
-constexpr int kKPrime = 16;        /* proposals kept per (query, sub-range): a sorted list in REGISTERS */
-constexpr int kStageCap = 16;      /* staging entries per thread: one 8-column group can add 8 */
-constexpr int kEpiThreads = 256, kProdThreads = 96;   /* 8 epilogue warps (two per TMEM lane quadrant, half of the columns each); 384 threads: 168 registers each */
-constexpr int kThreads = 32 + kProdThreads + kEpiThreads;
-constexpr float kPadNorm = 1.0e30f, kThrInit = 1.0e29f;
+constexpr int kKPrime = 16;        /* K': the number of distinct keys that back a query's threshold; K <= K' - 2 */
+constexpr int kQueueCap = 40;      /* hit queue per (query, range): groups of 12 words (first key, 3 pad, 8 scores); ~9 are used */
+constexpr int kEpiThreads = 256;   /* 8 epilogue warps: query tile = (warp-4)/4, TMEM lane quadrant = warp%4 */
+constexpr int kThreads = 384;
+constexpr int kNT = 128;           /* keys per tile (one TMA copy) */
+constexpr int kNH = SCL_TC_NH;    /* keys per accumulator slot (one MMA batch) */
+constexpr int kAccStages = 256 / kNH;   /* accumulator slots per query tile: stages x 2 query tiles x kNH columns = all 512 TMEM columns */
+constexpr int kQPerCta = 256;
+constexpr int kNoThr = 0x7f7f7f7f; /* memset pattern of the slots: 3.39e38 = "nothing yet" */
+constexpr float kThrInit = 1.0e38f;
 
-// order-preserving float <-> signed int image (for atomicMin on scores that may be negative)
+// order-preserving float <-> signed int image
 __device__ __forceinline__ int ordered_int(float f) { const int b = __float_as_int(f); return b ^ ((b >> 31) & 0x7fffffff); }
 __device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
-
-__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 // ---- tcgen05 / mbarrier PTX wrappers ---------------------------------------------------------
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(scl_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(scl_smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -65,11 +93,11 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(scl_smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // K-major, no swizzle: core matrix = 8 rows x 16 B stored contiguously; SBO = distance between 8-row
@@ -83,9 +111,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
     d |= (uint64_t)1 << 46;                      /* descriptor version for sm_100 */
     return d;                                    /* base offset 0, layout type 0 = SWIZZLE_NONE */
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+// 32 consecutive fp32 columns of this warp's 32 TMEM lanes; asynchronous until tmem_wait32 on the same registers
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32])
 {
-    uint32_t r[32];
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -95,55 +123,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
           "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
-}
-
-
-// 64 consecutive fp32 columns of this warp's 32 TMEM lanes; asynchronous until tmem_wait64 on the same registers
-#define SCL_R8(b) "%" #b
-__device__ __forceinline__ void tmem_ld64_issue(uint32_t taddr, uint32_t (&r)[64])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
-        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
-          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
-          "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
-          "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]),
-          "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]),
-          "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
-        : "r"(taddr));
 }
 // wait for the outstanding tcgen05.ld; the registers are in/out operands so no use can be scheduled above the wait
-__device__ __forceinline__ void tmem_wait64(uint32_t (&r)[64])
+__device__ __forceinline__ void tmem_wait32(uint32_t (&r)[32])
 {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
         : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
           "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]),
           "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
-          "+r"(r[30]), "+r"(r[31]), "+r"(r[32]), "+r"(r[33]), "+r"(r[34]), "+r"(r[35]), "+r"(r[36]), "+r"(r[37]), "+r"(r[38]), "+r"(r[39]),
-          "+r"(r[40]), "+r"(r[41]), "+r"(r[42]), "+r"(r[43]), "+r"(r[44]), "+r"(r[45]), "+r"(r[46]), "+r"(r[47]), "+r"(r[48]), "+r"(r[49]),
-          "+r"(r[50]), "+r"(r[51]), "+r"(r[52]), "+r"(r[53]), "+r"(r[54]), "+r"(r[55]), "+r"(r[56]), "+r"(r[57]), "+r"(r[58]), "+r"(r[59]),
-          "+r"(r[60]), "+r"(r[61]), "+r"(r[62]), "+r"(r[63])
+          "+r"(r[30]), "+r"(r[31])
         :: "memory");
-}
-#undef SCL_R8
-// 8 columns, synchronous (used only on the rare "some score beats the threshold" path)
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8])
-{
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]) :: "memory");
-#pragma unroll
-    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ float fmin3(float a, float b, float c)
 {
@@ -151,74 +140,154 @@ __device__ __forceinline__ float fmin3(float a, float b, float c)
     asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));   /* FMNMX3 */
     return r;
 }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
+{
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-template <int R, int NT> struct TcCfg {
-    static constexpr int G = ((R / 4 + 1) + 1) / 2 * 2;       /* 16-byte K chunks per row (incl. the norm chunk), even */
-    static constexpr int KSTEPS = G / 2;                      /* tcgen05.mma instructions per product (K = 8 tf32 each) */
-    static constexpr uint32_t A_LBO = 128 * 16, B_LBO = NT * 16, SBO = 128;
-    static constexpr uint32_t A_BLOCK = 128 * G * 16, B_BLOCK = NT * G * 16;
-    static constexpr uint32_t OFF_BAR = 0;                                    /* 8 mbarriers + tmem slot */
-    static constexpr uint32_t OFF_A = 128;                                    /* A1, A2 */
-    static constexpr uint32_t OFF_B = OFF_A + 2 * A_BLOCK;                    /* 2 stages x (B_hi, B_lo) */
-    static constexpr uint32_t OFF_STG = OFF_B + 4 * B_BLOCK;                  /* staging [cap][256] val, idx */
-    static constexpr uint32_t TOTAL = OFF_STG + 2 * kStageCap * kEpiThreads * 4;
-    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+template <int R> struct TcCfg {
+    static constexpr int KTOT = (3 * R + 3 + 15) / 16 * 16;   /* GEMM K: 64 at R = 20, 128 at R = 40 */
+    static constexpr int CHUNKS = KTOT / 8;                   /* 16-byte K chunks per row */
+    static constexpr int KSTEPS = KTOT / 16;                  /* tcgen05.mma instructions per 128x128 tile */
+    static constexpr uint32_t LBO = 128 * 16, SBO = 128;      /* both operands are 128 rows tall */
+    static constexpr uint32_t TILE_BYTES = 128 * KTOT * 2;    /* one operand tile: 16 KB / 32 KB */
+    static constexpr int NSTAGE = R <= 20 ? 8 : 4;            /* key tiles in flight in shared memory */
+    static constexpr uint32_t OFF_BAR = 0;                    /* mbarriers, tmem slot, flags */
+    static constexpr uint32_t OFF_THR = 1024;                 /* [256] union bounds */
+    static constexpr uint32_t OFF_A = 2048;                   /* two query tiles */
+    static constexpr uint32_t OFF_B = OFF_A + 2 * TILE_BYTES;
+    static constexpr uint32_t TOTAL = OFF_B + NSTAGE * TILE_BYTES;
+    /* D = F32, A = B = BF16, both K-major, N = kNH, M = 128 */
+    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kNH >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
 
-template <int R, int NT>
-__global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
-    const float* __restrict__ qkeys, int Q, const float* __restrict__ keys, const float* __restrict__ knorm, int key_lo, int key_hi,
-    int range_len, int n_ranges, int kprime, int sub_base, int n_sub_total, long long* __restrict__ times /* null, or [grid][8] role timers (SCL_TC_TIMES=1) */,
-    int* __restrict__ g_thr /* [Q] shared thresholds (ordered-int image) */,
-    float* __restrict__ prop_s /* [Q][n_ranges][K'] */, int32_t* __restrict__ prop_idx, float* __restrict__ prop_cut /* [Q][n_ranges] */)
+// value of GEMM column `idx` of the key row (B) / of the query row (A)
+template <int R>
+__device__ __forceinline__ float b_column(const float (&k0)[R], const float (&k1)[R], const float (&nn)[3], int idx)
 {
-    using C = TcCfg<R, NT>;
+    if (idx < R) return k0[idx];
+    if (idx < 2 * R) return k1[idx - R];
+    if (idx < 3 * R) return k0[idx - 2 * R];
+    if (idx < 3 * R + 3) return nn[idx - 3 * R];
+    return 0.0f;
+}
+
+// ---- key image: keys [n][R] fp32 -> B-operand tiles ------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(128) key_image_kernel(const float* __restrict__ keys, const float* __restrict__ knorm, int k_lo, int k_hi,
+                                                        unsigned char* __restrict__ img)
+{
+    using C = TcCfg<R>;
+    const int key = k_lo + blockIdx.x * 128 + threadIdx.x;
+    if (key >= k_hi) return;
+    float k0[R], k1[R], nn[3];
+#pragma unroll
+    for (int g = 0; g < R / 4; g++) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(keys + (size_t)key * R) + g);
+        const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            k0[4 * g + i] = bf16_round(xs[i]);
+            k1[4 * g + i] = bf16_round(xs[i] - k0[4 * g + i]);
+        }
+    }
+    const float n = __ldg(knorm + key);
+    nn[0] = bf16_round(n); nn[1] = bf16_round(n - nn[0]); nn[2] = bf16_round(n - nn[0] - nn[1]);
+    const int row = key & 127;
+    unsigned char* dst = img + (size_t)(key >> 7) * C::TILE_BYTES + (uint32_t)(row >> 3) * C::SBO + (uint32_t)(row & 7) * 16;
+#pragma unroll
+    for (int c = 0; c < C::CHUNKS; c++) {
+        uint4 v;
+        v.x = pack_bf16x2(b_column<R>(k0, k1, nn, 8 * c + 0), b_column<R>(k0, k1, nn, 8 * c + 1));
+        v.y = pack_bf16x2(b_column<R>(k0, k1, nn, 8 * c + 2), b_column<R>(k0, k1, nn, 8 * c + 3));
+        v.z = pack_bf16x2(b_column<R>(k0, k1, nn, 8 * c + 4), b_column<R>(k0, k1, nn, 8 * c + 5));
+        v.w = pack_bf16x2(b_column<R>(k0, k1, nn, 8 * c + 6), b_column<R>(k0, k1, nn, 8 * c + 7));
+        *reinterpret_cast<uint4*>(dst + (uint32_t)c * C::LBO) = v;
+    }
+}
+
+// A full hit queue is re-filtered with the threshold of the moment: groups queued under an earlier, looser bound whose
+// 8 scores have all risen to or above it can be dropped like any other key (they are >= the final cut). Rare, and kept
+// out of line so that the epilogue loop stays small.
+__device__ __noinline__ int compact_queue(uint4* q, int n, float thr)
+{
+    int w = 0;
+    for (int e = 0; e < n; e++) {
+        const uint4 k4 = __ldcg(q + 3 * e), a4 = __ldcg(q + 3 * e + 1), b4 = __ldcg(q + 3 * e + 2);
+        const float m = fminf(fminf(fminf(__uint_as_float(a4.x), __uint_as_float(a4.y)), fminf(__uint_as_float(a4.z), __uint_as_float(a4.w))),
+                              fminf(fminf(__uint_as_float(b4.x), __uint_as_float(b4.y)), fminf(__uint_as_float(b4.z), __uint_as_float(b4.w))));
+        if (m < thr) {
+            if (w != e) { __stcg(q + 3 * w, k4); __stcg(q + 3 * w + 1, a4); __stcg(q + 3 * w + 2, b4); }
+            w++;
+        }
+    }
+    return w;
+}
+
+// ---- the query kernel ---------------------------------------------------------------------------------
+template <int R, bool TIMES>
+__global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
+    const float* __restrict__ qkeys, int Q, const unsigned char* __restrict__ img, int key_hi, int n_ranges,
+    long long* __restrict__ times /* null, or [grid][16] developer counters (SCL_TC_TIMES=1) */,
+    int* __restrict__ slots /* [Q][K'] range minima by range % K' (ordered-int image) */,
+    uint32_t* __restrict__ hq /* [Q][n_ranges][kQueueCap][12] hit queues */, int* __restrict__ hq_cnt /* [Q][n_ranges] */,
+    int* __restrict__ dbg /* null, or developer counters */)
+{
+    using C = TcCfg<R>;
+    constexpr int NS = C::NSTAGE;
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-    uint64_t *full = bars, *empty = bars + 2, *tfull = bars + 4, *tempty = bars + 6;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t *full = bars, *empty = bars + NS, *tfull = bars + 2 * NS, *tempty = bars + 2 * NS + 2 * kAccStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 4 * kAccStages);
+    volatile int* epi_done = reinterpret_cast<volatile int*>(tmem_slot + 1);
+    volatile int* sthr = reinterpret_cast<volatile int*>(smem + C::OFF_THR);          /* [256] union bounds of the CTA's queries */
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qtile = blockIdx.x / n_ranges, range = blockIdx.x % n_ranges;
-    const int k_begin = key_lo + range * range_len;       /* this launch covers keys [key_lo, key_hi) */
-    const int k_end = min(key_hi, k_begin + range_len);
-    const int n_tiles = k_end > k_begin ? (k_end - k_begin + NT - 1) / NT : 0;
-
+    const int n_groups = gridDim.x / n_ranges;
+    const int group = blockIdx.x % n_groups, range = blockIdx.x / n_groups;   /* neighbouring CTAs share a key range (L2 reuse) */
+    const int q_base = group * kQPerCta;
+    /* Key tiles are dealt round-robin: this CTA owns tiles range, range + n_ranges, ... Every CTA then sees a sample of the
+     * WHOLE database, so the range minima that make up the union bound are alike even when the database is ordered
+     * (a trajectory: neighbouring keys are neighbouring places, and whole stretches of it are far from the query). */
+    const int n_tiles_all = (key_hi + kNT - 1) / kNT;
+    const int n_tiles = range < n_tiles_all ? (n_tiles_all - range + n_ranges - 1) / n_ranges : 0;
+    const int n_service = min(n_ranges, n_tiles_all);                         /* ranges that hold keys */
     // ---- one-time setup -----------------------------------------------------------------------
     if (threadIdx.x == 0) {
-        scl_mbar_init(&full[0], kProdThreads / 32); scl_mbar_init(&full[1], kProdThreads / 32);
-        scl_mbar_init(&empty[0], 1); scl_mbar_init(&empty[1], 1);
-        scl_mbar_init(&tfull[0], 1); scl_mbar_init(&tfull[1], 1);
-        scl_mbar_init(&tempty[0], kEpiThreads / 32); scl_mbar_init(&tempty[1], kEpiThreads / 32);
+        for (int s = 0; s < NS; s++) { scl_mbar_init(&full[s], 1); scl_mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2 * kAccStages; s++) { scl_mbar_init(&tfull[s], 1); scl_mbar_init(&tempty[s], 4); }
+        *epi_done = 0;
         scl_mbar_fence_init();
     }
-    if (warp == 0) {   /* TMEM: 2 accumulator stages of NT fp32 columns */
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(scl_smem_u32(tmem_slot)), "r"(2 * NT) : "memory");
+    if (threadIdx.x < kQPerCta) sthr[threadIdx.x] = kNoThr;
+    if (warp == 0) {   /* TMEM: 2 stages x 2 query tiles x 128 fp32 columns */
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(scl_smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    {   /* zero both B stages once (the norm chunk of B_lo and the padding chunk stay zero for ever) */
-        uint4* z = reinterpret_cast<uint4*>(smem + C::OFF_B);
-        for (uint32_t i = threadIdx.x; i < 4 * C::B_BLOCK / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
-    }
-    {   /* A operand: A1 = [-2 q_hi | 1 1 1 0 ...], A2 = [-2 q_lo | 0 ...], rows = the tile's 128 queries */
-        float* A1 = reinterpret_cast<float*>(smem + C::OFF_A);
-        float* A2 = reinterpret_cast<float*>(smem + C::OFF_A + C::A_BLOCK);
-        for (int i = threadIdx.x; i < 128 * C::G; i += kThreads) {
-            const int m = i % 128, g = i / 128;
-            const int qi = qtile * 128 + m;
-            float4 h = make_float4(0, 0, 0, 0), l = make_float4(0, 0, 0, 0);
-            if (g < R / 4) {
+    {   /* A operand: rows = the CTA's 256 queries, columns [-2 q0 | -2 q0 | -2 q1 | 1 1 1 0..] */
+        for (int i = threadIdx.x; i < kQPerCta * C::CHUNKS; i += kThreads) {
+            const int m = i % kQPerCta, c = i / kQPerCta;
+            const int qi = q_base + m;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int idx = 8 * c + j;
+                float x = 0.0f;
                 if (qi < Q) {
-                    const float4 x = __ldg(reinterpret_cast<const float4*>(qkeys + (size_t)qi * R + 4 * g));
-                    const float hx = tf32_trunc(x.x), hy = tf32_trunc(x.y), hz = tf32_trunc(x.z), hw = tf32_trunc(x.w);
-                    h = make_float4(-2.0f * hx, -2.0f * hy, -2.0f * hz, -2.0f * hw);
-                    l = make_float4(-2.0f * tf32_trunc(x.x - hx), -2.0f * tf32_trunc(x.y - hy), -2.0f * tf32_trunc(x.z - hz), -2.0f * tf32_trunc(x.w - hw));
+                    if (idx < 3 * R) {
+                        const float q = __ldg(qkeys + (size_t)qi * R + idx % R);
+                        const float q0 = bf16_round(q);
+                        x = idx < 2 * R ? -2.0f * q0 : -2.0f * bf16_round(q - q0);
+                    } else if (idx < 3 * R + 3) {
+                        x = 1.0f;
+                    }
                 }
-            } else if (g == R / 4) {
-                h = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+                v[j] = x;
             }
-            const uint32_t off = (uint32_t)g * C::A_LBO + (uint32_t)(m >> 3) * C::SBO + (uint32_t)(m & 7) * 16;
-            *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(A1) + off) = h;
-            *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(A2) + off) = l;
+            const int r = m & 127;
+            unsigned char* dst = smem + C::OFF_A + (uint32_t)(m >> 7) * C::TILE_BYTES + (uint32_t)c * C::LBO + (uint32_t)(r >> 3) * C::SBO + (uint32_t)(r & 7) * 16;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
     }
     fence_async_smem();
@@ -227,225 +296,228 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // Role -> warp mapping: the scheduler favours higher warp ids, so the epilogue (the busiest role) gets
-    // the highest warps (4-11), the producers 1-3 and the single MMA-issuing thread warp 0. tcgen05.ld lets warp w touch
-    // TMEM lanes 32*(w%4).., so epilogue warp w serves queries 32*(w%4)..32*(w%4)+31 of the tile.
     if (warp >= 4) {
-        // ===== epilogue: thread = (query = TMEM lane, half of the columns) ================================================
-        // A key is kept only if its score is below the thread's threshold. The threshold is the K'-th
-        // smallest score seen so far for this query — by this CTA, or (through g_thr) by ANY CTA working
-        // on the same query tile: each published value is backed by K' keys at or below it, so it bounds
-        // the global K'-th smallest score from above and nothing in the true top-K' is ever dropped.
-        constexpr int E = kEpiThreads;
-        const int half = (warp - 4) >> 2;          /* which half of every tile's columns this warp examines */
-        const int row = (warp & 3) * 32 + lane;    /* row of the tile = TMEM lane, 0..127 */
-        const int t = half * 128 + row;            /* slot of this thread in the shared-memory lists */
-        const int qi = qtile * 128 + row;
-        const int sub = sub_base + 2 * range + half;       /* slot of this thread's proposal list among all sub-ranges */
-        float* sv = reinterpret_cast<float*>(smem + C::OFF_STG);
-        int* si = reinterpret_cast<int*>(sv + kStageCap * E);
-        // The thread's K' best (score, key) so far live in registers, kept sorted by a branch-free bubble-through
-        // insert (the shared-memory insertion sort this replaces cost ~10x more: a chain of dependent LDS/STS).
-        float lv[kKPrime]; int li[kKPrime];
+        // ===== epilogue: thread = query = TMEM lane ====================================================
+        const int qt = (warp - 4) >> 2;                 /* query tile of this warp */
+        const int row = (warp & 3) * 32 + lane;         /* TMEM lane */
+        const int qi = q_base + qt * 128 + row;
+        const bool live = qi < Q;
+        int n_hit = 0;                                  /* 8-column groups queued by this thread */
+        int n_slow = 0;                                 /* developer counter (SCL_TC_TIMES) */
+        float thr = live ? kThrInit : -kThrInit;        /* rows beyond Q never queue anything */
+        float published = kThrInit;
+        int* my_slot = slots + (size_t)(live ? qi : 0) * kKPrime + (range % kKPrime);
+        volatile int* my_sthr = sthr + qt * 128 + row;
+        uint4* my_q = reinterpret_cast<uint4*>(hq + ((size_t)(live ? qi : 0) * n_ranges + range) * (size_t)(kQueueCap * 12));
+        // The epilogue warps are coupled through the accumulator hand-off (a slot is refilled only when all four warps of
+        // its query tile have drained it), so whatever a warp does on a hit sits on the critical path of the whole CTA.
+        // A hit therefore only APPENDS the 8-column group (its first key and its 8 scores: three 16-byte stores) to the
+        // (query, range) queue in global memory; the re-rank kernel sorts it out. 32 scores cost a FMNMX3 tree and a vote.
+        auto examine = [&](uint32_t (&r)[32], int key_first) {
+            float g[4];
 #pragma unroll
-        for (int i = 0; i < kKPrime; i++) { lv[i] = kThrInit; li[i] = -1; }
-        int cnt = 0;
-        int n_slow = 0, n_push = 0, n_fold = 0;      /* developer counters (SCL_TC_TIMES) */
-        float thr = kThrInit;
-        int* my_gthr = g_thr + (qi < Q ? qi : 0);
-        long long t_fold = 0;
-        auto fold = [&]() {
-            n_fold++; n_push += cnt;
-            long long f0 = 0;
-            if (times) f0 = clock64();
-            const float before = thr;
-            for (int s = 0; s < cnt; s++) {
-                float val = sv[s * E + t];
-                int id = si[s * E + t];
-                if (!(val < thr)) continue;
-#pragma unroll
-                for (int i = 0; i < kKPrime; i++) {
-                    const bool lt = val < lv[i];
-                    const float tv = lt ? lv[i] : val; const int ti = lt ? li[i] : id;
-                    lv[i] = lt ? val : lv[i]; li[i] = lt ? id : li[i];
-                    val = tv; id = ti;
-                }
-                thr = fminf(thr, lv[kKPrime - 1]);     /* never loosen a threshold learned from other CTAs */
-            }
-            cnt = 0;
-            if (thr < before && qi < Q) atomicMin(my_gthr, ordered_int(thr));
-            if (times) t_fold += clock64() - f0;
-        };
-        // One 64-column TMEM load is always in flight while the previous 64 columns are examined. The common
-        // case is "nothing below the threshold": a min-tree (FMNMX3) over the 64 scores and one compare. Only
-        // the 8-column groups whose minimum beats the threshold are examined element by element.
-        uint32_t va[64];
-        long long t_ld = 0, t_slow = 0;                      /* developer probes (SCL_TC_TIMES) */
-        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        auto examine = [&](uint32_t (&r)[64], uint32_t col_first, int key_first) {
-            unsigned mask = 0;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
+            for (int j = 0; j < 4; j++) {
                 const float x0 = __uint_as_float(r[8 * j]), x1 = __uint_as_float(r[8 * j + 1]), x2 = __uint_as_float(r[8 * j + 2]),
                             x3 = __uint_as_float(r[8 * j + 3]), x4 = __uint_as_float(r[8 * j + 4]), x5 = __uint_as_float(r[8 * j + 5]),
                             x6 = __uint_as_float(r[8 * j + 6]), x7 = __uint_as_float(r[8 * j + 7]);
-                const float gj = fminf(fmin3(fmin3(x0, x1, x2), fmin3(x3, x4, x5), x6), x7);
-                mask |= (gj < thr ? 1u : 0u) << j;
+                g[j] = fminf(fmin3(fmin3(x0, x1, x2), fmin3(x3, x4, x5), x6), x7);
             }
-            unsigned wm = __reduce_or_sync(0xffffffffu, mask);
-            if (wm) n_slow++;
-            long long e0 = 0;
-            if (times && wm) e0 = clock64();
-            const bool was_slow = wm != 0;
-#pragma unroll 1
-            while (wm) {
-                const int j = __ffs(wm) - 1;                 /* warp-uniform: the switch below does not diverge */
-                wm &= wm - 1;
-                float v[8];
-#define SCL_GROUP(J) case J: _Pragma("unroll") for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[8 * J + i]); break;
-                switch (j) { SCL_GROUP(0) SCL_GROUP(1) SCL_GROUP(2) SCL_GROUP(3) SCL_GROUP(4) SCL_GROUP(5) SCL_GROUP(6) default: SCL_GROUP(7) }
-#undef SCL_GROUP
+            const float m = fminf(fmin3(g[0], g[1], g[2]), g[3]);
+            if (__any_sync(0xffffffffu, m < thr)) {     /* one chunk in ten */
+                n_slow++;
 #pragma unroll
-                for (int i = 0; i < 8; i++)
-                    if (v[i] < thr) { sv[cnt * E + t] = v[i]; si[cnt * E + t] = key_first + 8 * j + i; cnt++; }
-                if (__any_sync(0xffffffffu, cnt > kStageCap - 8)) fold();     /* all lanes fold together: amortised */
+                for (int j = 0; j < 4; j++) {
+                    if (g[j] < thr) {                    /* divergent: usually one lane, one group */
+                        if (n_hit == kQueueCap) n_hit = compact_queue(my_q, kQueueCap, thr);
+                        if (n_hit < kQueueCap) {
+                            uint4* q = my_q + n_hit * 3;
+                            __stcg(q + 0, make_uint4((uint32_t)(key_first + 8 * j), 0u, 0u, 0u));
+                            __stcg(q + 1, make_uint4(r[8 * j + 0], r[8 * j + 1], r[8 * j + 2], r[8 * j + 3]));
+                            __stcg(q + 2, make_uint4(r[8 * j + 4], r[8 * j + 5], r[8 * j + 6], r[8 * j + 7]));
+                        }
+                        n_hit++;                         /* beyond the capacity: counted, the query is then redone exactly */
+                    }
+                }
+                /* a new range minimum feeds the union bound at once */
+                if (live && m < published && key_first + 32 <= key_hi) { published = m; atomicMin(my_slot, ordered_int(m)); }
             }
-            if (times && was_slow) t_slow += clock64() - e0;
         };
-        long long tw = 0, tp = 0, c0 = clock64();
-        int shared_thr = __ldcg(my_gthr);                      /* then fetched one tile ahead: its L2 latency is never exposed */
-        for (int tile = 0; tile < n_tiles; tile++) {
-            const int a = tile & 1; const uint32_t ph = (tile >> 1) & 1;
-            scl_mbar_wait(&tfull[a], ph);
-            tc_fence_after();
-            if (times) { const long long c1 = clock64(); tw += c1 - c0; c0 = c1; }
-            thr = fminf(thr, ordered_float(shared_thr));
-            shared_thr = __ldcg(my_gthr);
-            const int key0 = k_begin + tile * NT;
-            const uint32_t col0 = lane_base + (uint32_t)(a * NT);
+        long long tw = 0, c0 = 0, t_ld = 0, t_ex = 0;
+        if (TIMES) c0 = clock64();
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(qt * kNH);
+        uint32_t va[32], vb[32];
+        const int n_it = (kNT / kNH) * n_tiles;             /* accumulator slots to drain */
+        float next_thr = thr;                               /* the service warps' bound, read one slot ahead of its use */
+        if (n_tiles > 0) {
+            /* Start-up: with no threshold yet, every score of the first tile would be a hit. Instead the first 128 keys are
+             * read twice: a first pass only finds the range minimum so far and publishes it; as soon as K' ranges have done
+             * so the service warps deliver a union bound (a few microseconds), and the normal pass starts with it. */
+            if (n_service >= kKPrime && (range + 1) * kNT <= key_hi) {
+                float m0 = kThrInit;
 #pragma unroll 1
-            for (int c = 0; c < NT / 128; c++) {               /* this warp's half of the tile, 64 columns at a time */
-                const int cc = half * (NT / 128) + c;
-                long long d0 = 0;
-                if (times) d0 = clock64();
-                tmem_ld64_issue(col0 + cc * 64, va);
-                tmem_wait64(va);
-                if (times) { const long long d1 = clock64(); t_ld += d1 - d0; }
-                examine(va, col0 + cc * 64, key0 + cc * 64);
+                for (int c = 0; c < kNT / 32; c++) {
+                    const int sl = (c * 32) / kNH, cc = (c * 32) % kNH;     /* slot, column within the slot */
+                    if (cc == 0) { scl_mbar_wait(&tfull[sl * 2 + qt], 0); tc_fence_after(); }
+                    tmem_ld32_issue(lane_base + (uint32_t)(sl * 2 * kNH + cc), va);
+                    tmem_wait32(va);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) m0 = fmin3(m0, __uint_as_float(va[j]), __uint_as_float(va[j + 1]));
+                }
+                if (live) { published = m0; atomicMin(my_slot, ordered_int(m0)); }
+                const long long w0 = clock64();
+                while (true) {
+                    const bool ok = !live || *my_sthr < 0x7f000000;
+                    if (__all_sync(0xffffffffu, ok)) break;
+                    if (clock64() - w0 > 40000) { if (dbg && lane == 0) atomicAdd(dbg + 5, 1); break; }
+                    __nanosleep(100);
+                }
+            } else {
+                scl_mbar_wait(&tfull[qt], 0);
+                tc_fence_after();
             }
+            if (live) next_thr = fminf(next_thr, ordered_float(*my_sthr));
+            tmem_ld32_issue(lane_base, va);
+        }
+        // One accumulator slot (kNH keys) per iteration, as pairs of 32-column chunks (va, vb). The load of the next chunk is
+        // always in flight while the current one is examined; the slot is handed back as soon as its last chunk is in registers.
+#pragma unroll 1
+        for (int it = 0; it < n_it; it++) {
+            const int s = it % kAccStages;
+            const int key0 = (range + (it / (kNT / kNH)) * n_ranges) * kNT + (it % (kNT / kNH)) * kNH;
+            const uint32_t col0 = lane_base + (uint32_t)(s * 2 * kNH);
+            thr = fminf(thr, next_thr);
+            long long p0 = 0;
+#pragma unroll
+            for (int pr = 0; pr < kNH / 64; pr++) {
+                if (TIMES) p0 = clock64();
+                tmem_wait32(va);
+                if (TIMES) { const long long p1 = clock64(); t_ld += p1 - p0; p0 = p1; }
+                tmem_ld32_issue(col0 + 64 * pr + 32, vb);
+                examine(va, key0 + 64 * pr);
+                if (TIMES) { const long long p1 = clock64(); t_ex += p1 - p0; p0 = p1; }
+                tmem_wait32(vb);
+                if (TIMES) { const long long p1 = clock64(); t_ld += p1 - p0; p0 = p1; }
+                if (pr + 1 < kNH / 64) {
+                    tmem_ld32_issue(col0 + 64 * pr + 64, va);
+                    if (TIMES) p0 = clock64();
+                    examine(vb, key0 + 64 * pr + 32);
+                    if (TIMES) t_ex += clock64() - p0;
+                }
+            }
+            if (live) next_thr = ordered_float(*my_sthr);
+            /* every score of this slot is in registers: hand it back to the MMA issuer now */
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[a]);
-            if (times) { const long long c1 = clock64(); tp += c1 - c0; c0 = c1; }
-        }
-        if (times) {
-            const int ws = __reduce_add_sync(0xffffffffu, n_slow), wp = __reduce_add_sync(0xffffffffu, n_push + cnt);
-            const unsigned any_slow_chunks = 0;
-            (void)any_slow_chunks;
-            if (t == 0) { times[blockIdx.x * 16 + 0] = tw; times[blockIdx.x * 16 + 1] = tp; times[blockIdx.x * 16 + 8] = ws; times[blockIdx.x * 16 + 9] = wp; times[blockIdx.x * 16 + 10] = n_fold; times[blockIdx.x * 16 + 11] = t_ld; times[blockIdx.x * 16 + 12] = t_slow; times[blockIdx.x * 16 + 13] = t_fold; }
-        }
-        fold();
-        if (qi < Q) {
-            const size_t o = ((size_t)qi * n_sub_total + sub) * kKPrime;
-#pragma unroll
-            for (int i = 0; i < kKPrime; i++) {
-                prop_s[o + i] = li[i] >= 0 ? lv[i] : __int_as_float(0x7f800000);
-                prop_idx[o + i] = li[i];
-            }
-            /* cut-off of this sub-range: every key NOT proposed had S >= the threshold in force when it was
-             * examined >= the final threshold (thresholds only fall); inf if nothing was ever dropped */
-            prop_cut[(size_t)qi * n_sub_total + sub] = thr < kThrInit ? thr : __int_as_float(0x7f800000);
-        }
-    } else if (warp >= 1) {
-        // ===== producers: raw keys -> hi/lo split -> UMMA core-matrix layout =======================
-        // The raw keys of tile t+1 are already in flight (registers) while tile t is split and stored.
-        const int p = threadIdx.x - 32;            /* 0..95 */
-        constexpr int KPT = (NT + kProdThreads - 1) / kProdThreads;     /* keys per thread per tile */
-        float4 xa[KPT][R / 4];
-        float na[KPT];
-        auto load_tile = [&](int tile, float4 (&x)[KPT][R / 4], float (&n)[KPT]) {
-#pragma unroll
-            for (int mm = 0; mm < KPT; mm++) {
-                const int key = k_begin + tile * NT + p + mm * kProdThreads;
-                if (tile < n_tiles && key < k_end && p + mm * kProdThreads < NT) {
-                    const float4* src = reinterpret_cast<const float4*>(keys + (size_t)key * R);
-#pragma unroll
-                    for (int g = 0; g < R / 4; g++) x[mm][g] = __ldg(src + g);
-                    n[mm] = __ldg(knorm + key);
+            if (lane == 0) mbar_arrive(&tempty[s * 2 + qt]);
+            bool pending = false;                        /* va still has to be loaded for the next iteration */
+            const int s1 = (it + 1) % kAccStages; const uint32_t ph1 = ((it + 1) / kAccStages) & 1;
+            if (it + 1 < n_it) {
+                /* next slot already complete? then start its first load before examining the last 32 scores */
+                if (__all_sync(0xffffffffu, mbar_test(&tfull[s1 * 2 + qt], ph1))) {
+                    tc_fence_after();
+                    tmem_ld32_issue(lane_base + (uint32_t)(s1 * 2 * kNH), va);
                 } else {
-#pragma unroll
-                    for (int g = 0; g < R / 4; g++) x[mm][g] = make_float4(0, 0, 0, 0);
-                    n[mm] = kPadNorm;                     /* padded rows can never be proposed */
+                    pending = true;
                 }
             }
-        };
-        auto store_tile = [&](int s, const float4 (&x)[KPT][R / 4], const float (&n)[KPT]) {
-            unsigned char* Bhi = smem + C::OFF_B + (uint32_t)s * 2 * C::B_BLOCK;
-            unsigned char* Blo = Bhi + C::B_BLOCK;
-#pragma unroll
-            for (int mm = 0; mm < KPT; mm++) {
-                const int m = p + mm * kProdThreads;
-                if (m >= NT) continue;
-                const uint32_t row_off = (uint32_t)(m >> 3) * C::SBO + (uint32_t)(m & 7) * 16;
-#pragma unroll
-                for (int g = 0; g < R / 4; g++) {
-                    const float hx = tf32_trunc(x[mm][g].x), hy = tf32_trunc(x[mm][g].y), hz = tf32_trunc(x[mm][g].z), hw = tf32_trunc(x[mm][g].w);
-                    *reinterpret_cast<float4*>(Bhi + (uint32_t)g * C::B_LBO + row_off) = make_float4(hx, hy, hz, hw);
-                    *reinterpret_cast<float4*>(Blo + (uint32_t)g * C::B_LBO + row_off) =
-                        make_float4(tf32_trunc(x[mm][g].x - hx), tf32_trunc(x[mm][g].y - hy), tf32_trunc(x[mm][g].z - hz), tf32_trunc(x[mm][g].w - hw));
-                }
-                const float n_hi = tf32_trunc(n[mm]), r1 = n[mm] - n_hi, n_mid = tf32_trunc(r1), n_lo = tf32_trunc(r1 - n_mid);
-                *reinterpret_cast<float4*>(Bhi + (uint32_t)(R / 4) * C::B_LBO + row_off) = make_float4(n_hi, n_mid, n_lo, 0.0f);
+            if (TIMES) p0 = clock64();
+            examine(vb, key0 + kNH - 32);
+            if (TIMES) t_ex += clock64() - p0;
+            if (pending) {
+                long long w0 = 0;
+                if (TIMES) w0 = clock64();
+                scl_mbar_wait(&tfull[s1 * 2 + qt], ph1);
+                if (TIMES) tw += clock64() - w0;
+                tc_fence_after();
+                tmem_ld32_issue(lane_base + (uint32_t)(s1 * 2 * kNH), va);
             }
-        };
-        long long tw = 0, tp = 0, c0 = clock64();
-        load_tile(0, xa, na);
-#pragma unroll 1
-        for (int tile = 0; tile < n_tiles; tile++) {
-            const int s = tile & 1; const uint32_t ph = (tile >> 1) & 1;
-            scl_mbar_wait(&empty[s], ph ^ 1u);
-            if (times) { const long long c1 = clock64(); tw += c1 - c0; c0 = c1; }
-            store_tile(s, xa, na);
-            fence_async_smem();                    /* generic-proxy writes -> visible to the tensor core (async proxy) */
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[s]);
-            load_tile(tile + 1, xa, na);           /* in flight while we wait for the next free stage */
-            if (times) { const long long c1 = clock64(); tp += c1 - c0; c0 = c1; }
         }
-        if (times && p == 0) { times[blockIdx.x * 16 + 2] = tw; times[blockIdx.x * 16 + 3] = tp; }
+        if (TIMES) {
+            const int wp = __reduce_add_sync(0xffffffffu, n_hit), wmax = __reduce_max_sync(0xffffffffu, n_hit);
+            if (lane == 0) {
+                long long* o = times + (size_t)blockIdx.x * 16;
+                atomicAdd(reinterpret_cast<unsigned long long*>(o + 0), (unsigned long long)tw);
+                atomicAdd(reinterpret_cast<unsigned long long*>(o + 1), (unsigned long long)(clock64() - c0));
+                atomicAdd(reinterpret_cast<unsigned long long*>(o + 2), (unsigned long long)n_slow);
+                atomicAdd(reinterpret_cast<unsigned long long*>(o + 3), (unsigned long long)wp);
+                atomicMax(reinterpret_cast<unsigned long long*>(o + 4), (unsigned long long)wmax);
+                atomicAdd(reinterpret_cast<unsigned long long*>(o + 9), (unsigned long long)t_ld);
+                atomicAdd(reinterpret_cast<unsigned long long*>(o + 10), (unsigned long long)t_ex);
+            }
+        }
+        /* Everything this thread did NOT queue scored >= the threshold in force at the time >= the maximum the query's slots
+         * end at (slots only fall, and a thread only ever applies a bound computed from them): the re-rank takes that maximum
+         * as the query's cut. The count is written even when it is zero, so the queues need no clearing between batches. */
+        if (live) hq_cnt[(size_t)qi * n_ranges + range] = n_hit;
+        __syncwarp();
+        if (lane == 0) atomicAdd(const_cast<int*>(epi_done), 1);
+    } else if (warp >= 2) {
+        // ===== threshold service: union bound of the CTA's 256 queries ==================================
+        // Range r publishes its best score so far into slot r % K' of the query (atomicMin). The K' slots then hold the
+        // scores of K' DISTINCT keys (different ranges), so their maximum bounds the query's K'-th best score from above.
+        // Each lane refreshes four queries: 64 bytes from L2 and 15 max operations per query, a microsecond per sweep.
+        int sweeps = 0;
+        while (n_tiles > 0) {
+            const bool last = *epi_done >= 8;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int j = (warp - 2) * 128 + 32 * k + lane;
+                const int qi = q_base + j;
+                if (qi < Q) {
+                    const int4* p = reinterpret_cast<const int4*>(slots + (size_t)qi * kKPrime);
+                    const int4 a = __ldcg(p), b4 = __ldcg(p + 1), c = __ldcg(p + 2), d = __ldcg(p + 3);
+                    const int m = max(max(max(max(a.x, a.y), max(a.z, a.w)), max(max(b4.x, b4.y), max(b4.z, b4.w))),
+                                      max(max(max(c.x, c.y), max(c.z, c.w)), max(max(d.x, d.y), max(d.z, d.w))));
+                    if (m < 0x7f000000) sthr[j] = m;     /* all K' slots filled: a valid bound */
+                }
+            }
+            sweeps++;
+            if (last) break;
+            if (sweeps > 64) __nanosleep(1000);          /* the bound moves fast at the start: sweep back to back there */
+        }
+        if (TIMES && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(times + (size_t)blockIdx.x * 16 + 5), (unsigned long long)sweeps);
+    } else if (warp == 1) {
+        // ===== TMA issuer: one thread, one bulk copy per key tile =======================================
+        if (lane == 0) {
+            const unsigned char* src = img + (size_t)range * C::TILE_BYTES;
+            const size_t step = (size_t)n_ranges * C::TILE_BYTES;
+            for (int tile = 0; tile < n_tiles; tile++) {
+                const int b = tile % NS; const uint32_t ph = (tile / NS) & 1;
+                scl_mbar_wait(&empty[b], ph ^ 1u);
+                scl_mbar_expect_tx(&full[b], C::TILE_BYTES);
+                scl_bulk_g2s(smem + C::OFF_B + (uint32_t)b * C::TILE_BYTES, src + (size_t)tile * step, C::TILE_BYTES, &full[b]);
+            }
+        }
+        __syncwarp();
     } else {
         // ===== MMA issuer: one thread ==============================================================
         if (lane == 0) {
-            const uint32_t a1 = scl_smem_u32(smem + C::OFF_A), a2 = a1 + C::A_BLOCK;
-            long long t_te = 0, t_fu = 0, t_is = 0, c0 = clock64();
-            for (int tile = 0; tile < n_tiles; tile++) {
-                const int s = tile & 1; const uint32_t ph = (tile >> 1) & 1;
-                scl_mbar_wait(&tempty[s], ph ^ 1u);        /* accumulator stage drained by the epilogue */
-                if (times) { const long long c1 = clock64(); t_te += c1 - c0; c0 = c1; }
-                scl_mbar_wait(&full[s], ph);               /* operands written */
-                if (times) { const long long c1 = clock64(); t_fu += c1 - c0; c0 = c1; }
-                tc_fence_after();
-                const uint32_t bhi = scl_smem_u32(smem + C::OFF_B) + (uint32_t)s * 2 * C::B_BLOCK, blo = bhi + C::B_BLOCK;
-                const uint32_t d = tmem_base + (uint32_t)(s * NT);
-                uint32_t acc = 0;
-                {
+            const uint32_t a_base = scl_smem_u32(smem + C::OFF_A), b_base = scl_smem_u32(smem + C::OFF_B);
+            long long t_te = 0, t_fu = 0, c0 = 0;
+            constexpr int SPT = kNT / kNH;                          /* accumulator slots per key tile */
+            for (int it = 0; it < SPT * n_tiles; it++) {
+                const int tile = it / SPT, hf = it % SPT;           /* kNH keys of a key tile -> one accumulator slot per query tile */
+                const int b = tile % NS; const uint32_t bph = (tile / NS) & 1;
+                const int s = it % kAccStages; const uint32_t ph = (it / kAccStages) & 1;
+                if (TIMES) c0 = clock64();
+                if (hf == 0) scl_mbar_wait(&full[b], bph);          /* key tile landed */
+                if (TIMES) { const long long c1 = clock64(); t_fu += c1 - c0; c0 = c1; }
+                const uint32_t bs = b_base + (uint32_t)b * C::TILE_BYTES + (uint32_t)hf * (kNH / 8) * C::SBO;   /* rows 64*hf.. of the tile */
 #pragma unroll
-                for (int k = 0; k < C::KSTEPS; k++) {
-                    tc_mma_tf32(d, make_desc(a1 + 2 * k * C::A_LBO, C::A_LBO, C::SBO), make_desc(bhi + 2 * k * C::B_LBO, C::B_LBO, C::SBO), C::IDESC, acc);
-                    acc = 1;
+                for (int qt = 0; qt < 2; qt++) {
+                    scl_mbar_wait(&tempty[s * 2 + qt], ph ^ 1u);    /* slot drained by its four epilogue warps */
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + (uint32_t)((s * 2 + qt) * kNH);
+                    const uint32_t as = a_base + (uint32_t)qt * C::TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < C::KSTEPS; k++)
+                        tc_mma_bf16(d, make_desc(as + 2 * k * C::LBO, C::LBO, C::SBO), make_desc(bs + 2 * k * C::LBO, C::LBO, C::SBO), C::IDESC, k > 0 ? 1u : 0u);
+                    tc_commit(&tfull[s * 2 + qt]);                  /* slot ready for the epilogue */
                 }
-#pragma unroll
-                for (int k = 0; k < C::KSTEPS; k++)
-                    tc_mma_tf32(d, make_desc(a2 + 2 * k * C::A_LBO, C::A_LBO, C::SBO), make_desc(bhi + 2 * k * C::B_LBO, C::B_LBO, C::SBO), C::IDESC, 1);
-#pragma unroll
-                for (int k = 0; k < C::KSTEPS; k++)
-                    tc_mma_tf32(d, make_desc(a1 + 2 * k * C::A_LBO, C::A_LBO, C::SBO), make_desc(blo + 2 * k * C::B_LBO, C::B_LBO, C::SBO), C::IDESC, 1);
-                }
-                tc_commit(&empty[s]);                      /* smem stage reusable once these MMAs retire */
-                tc_commit(&tfull[s]);                      /* accumulator ready for the epilogue */
-                if (times) { const long long c1 = clock64(); t_is += c1 - c0; c0 = c1; }
+                if (hf == SPT - 1) tc_commit(&empty[b]);                  /* key tile reusable once these MMAs retire */
+                if (TIMES) { const long long c1 = clock64(); t_te += c1 - c0; }
             }
-            if (times) { times[blockIdx.x * 16 + 4] = t_te; times[blockIdx.x * 16 + 5] = t_fu; times[blockIdx.x * 16 + 6] = t_is; times[blockIdx.x * 16 + 7] = n_tiles; }
+            if (TIMES) { times[(size_t)blockIdx.x * 16 + 6] = t_fu; times[(size_t)blockIdx.x * 16 + 7] = t_te; times[(size_t)blockIdx.x * 16 + 8] = n_tiles; }
         }
         __syncwarp();
     }
@@ -453,122 +525,8 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * NT) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
-}
-
-// Bootstrap: before any tensor-core work, every query gets a valid starting threshold from a strided sample of
-// kBootKeys keys scored on the CUDA cores. Each lane keeps the 4 smallest scores of its share; the K'-th smallest of
-// those 128 scores is >= the K'-th smallest of the sample, hence of the whole database. That bound (+ the
-// prefilter's error bound, so that it also holds for the tensor-core scores) removes most of the start-up
-// transient of the streaming top-K' in the sample pass.
-constexpr int kBootKeys = 4096;
-template <int R>
-__global__ void __launch_bounds__(256) knn_bootstrap_kernel(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys,
-                                                            const float* __restrict__ knorm, const float* __restrict__ kn2max, int n_db,
-                                                            int kprime, int* __restrict__ g_thr)
-{
-    __shared__ __align__(16) float sk[256 * R];          /* rows of R floats: LDS.128 reads at an 80-byte lane stride are conflict free */
-    __shared__ float sn[256];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qi = blockIdx.x * 8 + warp;
-    float q[R];
-#pragma unroll
-    for (int d = 0; d < R; d++) q[d] = qi < Q ? __ldg(qkeys + (size_t)qi * R + d) : 0.0f;
-    const int n_s = n_db < kBootKeys ? n_db : kBootKeys;
-    const long long stride = n_db / n_s;                 /* sample key j is database key j*stride */
-    float b0 = kThrInit, b1 = kThrInit, b2 = kThrInit, b3 = kThrInit;
-    for (int base = 0; base < n_s; base += 256) {
-        __syncthreads();
-        {
-            const int j = base + threadIdx.x;
-            if (j < n_s) {
-                const size_t key = (size_t)j * stride;
-#pragma unroll
-                for (int g = 0; g < R / 4; g++)
-                    reinterpret_cast<float4*>(sk + threadIdx.x * R)[g] = __ldg(reinterpret_cast<const float4*>(keys + key * R) + g);
-                sn[threadIdx.x] = __ldg(knorm + key);
-            }
-        }
-        __syncthreads();
-        const int nk = min(256, n_s - base);
-        for (int j = lane; j < nk; j += 32) {
-            float dot = 0.0f;
-#pragma unroll
-            for (int g = 0; g < R / 4; g++) {
-                const float4 k4 = reinterpret_cast<const float4*>(sk + j * R)[g];
-                dot = fmaf(q[4 * g], k4.x, dot); dot = fmaf(q[4 * g + 1], k4.y, dot);
-                dot = fmaf(q[4 * g + 2], k4.z, dot); dot = fmaf(q[4 * g + 3], k4.w, dot);
-            }
-            float x = fmaf(-2.0f, dot, sn[j]);
-            float y;
-            y = fminf(b0, x); x = fmaxf(b0, x); b0 = y;
-            y = fminf(b1, x); x = fmaxf(b1, x); b1 = y;
-            y = fminf(b2, x); x = fmaxf(b2, x); b2 = y;
-            b3 = fminf(b3, x);
-        }
-    }
-    /* K'-th smallest among the 32 x 4 kept scores (each lane's four are sorted): a K'-step k-way merge. If a lane
-     * held more than four of the true top-K', the value found is only larger, so it stays a valid upper bound. */
-    float picked = kThrInit;
-    for (int r = 0; r < kprime; r++) {
-        float w = b0;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) w = fminf(w, __shfl_xor_sync(0xffffffffu, w, off));
-        picked = w;
-        const unsigned who = __ballot_sync(0xffffffffu, b0 == w);
-        if (lane == __ffs(who) - 1) { b0 = b1; b1 = b2; b2 = b3; b3 = kThrInit; }   /* pop this lane's head */
-    }
-    if (lane == 0 && qi < Q && picked < kThrInit) {
-        float qn = 0.0f;
-#pragma unroll
-        for (int d = 0; d < R; d++) qn = fmaf(q[d], q[d], qn);
-        const float sn2 = sqrtf(qn) + sqrtf(__ldg(kn2max));
-        atomicMin(g_thr + qi, ordered_int(picked + 3.0517578125e-05f * sn2 * sn2));   /* + 2^-15 (|q|+|k|max)^2 */
-    }
-}
-
-// Between the sample pass and the main pass: the K'-th smallest score over the sample keys (= over the union of
-// the sample pass' proposal lists) becomes every CTA's starting threshold for that query. One warp per query.
-__global__ void __launch_bounds__(128) knn_sample_thr_kernel(const float* __restrict__ prop_s, int Q, int n_sub_total, int n_sub_sample,
-                                                             int kprime, int* __restrict__ g_thr)
-{
-    /* every proposal list is sorted ascending: a K'-step k-way merge, each lane holding the heads of its lists */
-    const int lane = threadIdx.x & 31;
-    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (qi >= Q) return;
-    const float* ps = prop_s + (size_t)qi * n_sub_total * kprime;
-    const float inf = __int_as_float(0x7f800000);
-    constexpr int kHeads = 10;                          /* up to 320 lists (148 ranges x 2 halves) */
-    int head[kHeads];
-    float hv[kHeads];
-#pragma unroll
-    for (int h = 0; h < kHeads; h++) {
-        const int l = lane + 32 * h;
-        head[h] = 0;
-        hv[h] = l < n_sub_sample ? ps[(size_t)l * kprime] : inf;
-    }
-    float kth = inf;
-    for (int r = 0; r < kprime; r++) {
-        float bv = inf; int bh = -1;
-#pragma unroll
-        for (int h = 0; h < kHeads; h++) if (hv[h] < bv) { bv = hv[h]; bh = h; }
-        float wv = bv;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) wv = fminf(wv, __shfl_xor_sync(0xffffffffu, wv, off));
-        if (!(wv < inf)) { kth = inf; break; }          /* fewer than K' sample keys: no threshold */
-        kth = wv;
-        const unsigned who = __ballot_sync(0xffffffffu, bh >= 0 && bv == wv);
-        if (lane == __ffs(who) - 1) {
-#pragma unroll
-            for (int h = 0; h < kHeads; h++)
-                if (h == bh) {
-                    head[h]++;
-                    hv[h] = head[h] < kprime ? ps[(size_t)(lane + 32 * h) * kprime + head[h]] : inf;
-                }
-        }
-    }
-    if (lane == 0 && kth < inf) atomicMin(g_thr + qi, ordered_int(kth));
 }
 
 template <int METRIC>
@@ -589,92 +547,103 @@ __device__ __forceinline__ float exact_d2(const float* __restrict__ q, const flo
     return result;
 }
 
-// Phase B: exact re-rank + certificate. One warp per query; n_cand = n_ranges * K' proposals, of which only those
-// scoring at or below the cut (a few dozen) can matter — see below — and are compacted into shared memory.
+// Phase B: exact re-rank + certificate. One CTA of 128 threads per query: the hit queues of all ranges are flattened
+// (counts -> prefix sums in shared memory) so that every thread reads a few independent groups, the survivors (scores at
+// or below the cut) are re-scored exactly, and warp 0 selects the top-K and certifies it.
 constexpr int kMaxSurvivors = 256;
+constexpr int kMaxRanges = 160;
 template <int METRIC>
 __global__ void __launch_bounds__(128) knn_rerank_kernel(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys, int R, int K,
-                                                         int n_ranges, int kprime, const float* __restrict__ prop_s,
-                                                         const int32_t* __restrict__ prop_idx, const float* __restrict__ prop_cut,
-                                                         const float* __restrict__ kn2max, int id_mul, int id_add,
-                                                         int32_t* __restrict__ out_ids, float* __restrict__ out_d2,
-                                                         int32_t* __restrict__ fail_list, int* __restrict__ fail_count)
+                                                          int n_ranges, int n_db, const uint32_t* __restrict__ hq, const int* __restrict__ hq_cnt,
+                                                          const int* __restrict__ slots, const float* __restrict__ kn2max, int id_mul, int id_add,
+                                                          int32_t* __restrict__ out_ids, float* __restrict__ out_d2, int q_off,
+                                                          int32_t* __restrict__ fail_list, int* __restrict__ fail_count, float* __restrict__ err_probe)
 {
-    __shared__ int s_id[4][kMaxSurvivors];
-    __shared__ float s_d[4][kMaxSurvivors];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int qi = blockIdx.x * (blockDim.x >> 5) + w;
-    if (qi >= Q) return;
-    const int n_cand = n_ranges * kprime;
+    __shared__ int s_id[kMaxSurvivors];
+    __shared__ float s_d[kMaxSurvivors];
+    __shared__ float s_s[kMaxSurvivors];
+    __shared__ int s_pre[kMaxRanges + 1];
+    __shared__ float s_q[64];
+    __shared__ int s_count, s_overflow;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int qi = blockIdx.x;
     const float* q = qkeys + (size_t)qi * R;
-    const int32_t* pidx = prop_idx + (size_t)qi * n_cand;
-    const float* ps = prop_s + (size_t)qi * n_cand;
     const float inf = __int_as_float(0x7f800000);
-    float cut = inf;
-    for (int r = lane; r < n_ranges; r += 32) cut = fminf(cut, prop_cut[(size_t)qi * n_ranges + r]);
+    /* The cut: the query's final union bound (the maximum of its K' slots). Everything that was not queued scored >= it,
+     * so every key scoring below it is in a queue; queued keys above it cannot be certified anyway and are skipped:
+     * about K' survive. */
+    int gt = lane < kKPrime ? __ldg(slots + (size_t)qi * kKPrime + lane) : (int)0x80000000;
+    gt = __reduce_max_sync(0xffffffffu, gt);
+    const float cut = gt < 0x7f000000 ? ordered_float(gt) : inf;
+    if (t == 0) { s_count = 0; s_overflow = 0; }
+    if (t < R) s_q[t] = __ldg(q + t);
+    for (int r = t; r < n_ranges; r += 128) {
+        int c = __ldg(hq_cnt + (size_t)qi * n_ranges + r);
+        if (c > kQueueCap) { s_overflow = 1; c = kQueueCap; }
+        s_pre[r + 1] = c;
+    }
+    __syncthreads();
+    if (warp == 0) {                                    /* exclusive prefix sums of the counts, 32 ranges at a time */
+        int carry = 0;
+        for (int base = 0; base < n_ranges; base += 32) {
+            const int r = base + lane;
+            int v = r < n_ranges ? s_pre[r + 1] : 0;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) cut = fminf(cut, __shfl_xor_sync(0xffffffffu, cut, off));
-    /* T = the K'-th smallest score among ALL proposals (a K'-step k-way merge over the sorted lists). Everything that
-     * is not evaluated exactly below — keys the prefilter dropped (score >= cut) and proposals scoring above T — has
-     * score >= min(cut, T), hence exact d2 > min(cut, T) + |q|^2 - eps; the certificate demands that this exceeds
-     * the K-th selected distance. If it fails, the query is redone exactly. So only ~K' survivors are evaluated. */
-    {
-        constexpr int kHeads = 10;                      /* up to 320 lists */
-        int head[kHeads]; float hv[kHeads];
+            for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, v, off); if (lane >= off) v += o; }
+            if (r < n_ranges) s_pre[r + 1] = carry + v;
+            carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+        if (lane == 0) s_pre[0] = 0;
+    }
+    __syncthreads();
+    const int total = s_pre[n_ranges];
+    for (int g = t; g < total; g += 128) {
+        int lo = 0, hi = n_ranges;                      /* the range that holds group g: last r with s_pre[r] <= g */
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_pre[mid] <= g) lo = mid; else hi = mid; }
+        const uint4* gp = reinterpret_cast<const uint4*>(hq + ((size_t)qi * n_ranges + lo) * (size_t)(kQueueCap * 12)) + 3 * (g - s_pre[lo]);
+        const uint4 k4 = __ldcg(gp), a4 = __ldcg(gp + 1), b4 = __ldcg(gp + 2);
+        const float sc[8] = {__uint_as_float(a4.x), __uint_as_float(a4.y), __uint_as_float(a4.z), __uint_as_float(a4.w),
+                             __uint_as_float(b4.x), __uint_as_float(b4.y), __uint_as_float(b4.z), __uint_as_float(b4.w)};
 #pragma unroll
-        for (int h = 0; h < kHeads; h++) { const int l = lane + 32 * h; head[h] = 0; hv[h] = l < n_ranges ? ps[(size_t)l * kprime] : inf; }
-        float T = inf;
-        for (int r = 0; r < kprime; r++) {
-            float bv = inf; int bh = -1;
-#pragma unroll
-            for (int h = 0; h < kHeads; h++) if (hv[h] < bv) { bv = hv[h]; bh = h; }
-            float wv = bv;
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) wv = fminf(wv, __shfl_xor_sync(0xffffffffu, wv, off));
-            if (!(wv < inf)) { T = inf; break; }        /* fewer than K' proposals in all: keep them all */
-            T = wv;
-            const unsigned who = __ballot_sync(0xffffffffu, bh >= 0 && bv == wv);
-            if (lane == __ffs(who) - 1) {
-#pragma unroll
-                for (int h = 0; h < kHeads; h++)
-                    if (h == bh) { head[h]++; hv[h] = head[h] < kprime ? ps[(size_t)(lane + 32 * h) * kprime + head[h]] : inf; }
+        for (int i = 0; i < 8; i++) {
+            const int id = (int)k4.x + i;
+            if (sc[i] <= cut && id < n_db) {
+                const int pos = atomicAdd(&s_count, 1);
+                if (pos < kMaxSurvivors) { s_id[pos] = id; s_s[pos] = sc[i]; }
             }
         }
-        cut = fminf(cut, T);
     }
-    /* the lists are sorted ascending: a list is read only while its entries are at or below the cut */
-    __shared__ int s_count[4];
-    if (lane == 0) s_count[w] = 0;
-    __syncwarp();
-    for (int l = lane; l < n_ranges; l += 32) {
-        for (int i = 0; i < kprime; i++) {
-            const float sc = ps[(size_t)l * kprime + i];
-            if (sc > cut || !(sc < inf)) break;
-            const int id = pidx[(size_t)l * kprime + i];
-            if (id < 0) break;
-            const int pos = atomicAdd(&s_count[w], 1);
-            if (pos < kMaxSurvivors) s_id[w][pos] = id;
-        }
-    }
-    __syncwarp();
-    int n_surv = s_count[w]; bool overflow = false;
+    __syncthreads();
+    bool overflow = s_overflow != 0;
+    int n_surv = s_count;
     if (n_surv > kMaxSurvivors) { overflow = true; n_surv = kMaxSurvivors; }
-    __syncwarp();
-    for (int c = lane; c < n_surv; c += 32) {
-        float d = exact_d2<METRIC>(q, keys + (size_t)s_id[w][c] * R, R);
+    float qn = 0.0f;
+    for (int d = 0; d < R; d++) qn = fmaf(s_q[d], s_q[d], qn);
+    const float sn = sqrtf(qn) + sqrtf(__ldg(kn2max));
+    const float eps0 = 3.0517578125e-05f * sn * sn;                 /* 2^-15 (|q| + |k|max)^2 */
+    float worst_err = 0.0f;
+    for (int c = t; c < n_surv; c += 128) {
+        float d = exact_d2<METRIC>(s_q, keys + (size_t)s_id[c] * R, R);
+        if (err_probe) worst_err = fmaxf(worst_err, fabsf((d - qn) - s_s[c]) / eps0);
         if (METRIC == 1 && !(d > FLT_EPSILON)) d = inf;          /* libnabo self-match rule */
         if (!(d < (METRIC == 0 ? FLT_MAX : inf))) d = inf;       /* never accepted by the trees */
-        s_d[w][c] = d;
+        s_d[c] = d;
     }
-    __syncwarp();
+    if (err_probe) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) worst_err = fmaxf(worst_err, __shfl_xor_sync(0xffffffffu, worst_err, off));
+        if (lane == 0 && worst_err > 0.0f) atomicMax(reinterpret_cast<int*>(err_probe), __float_as_int(worst_err));   /* non-negative floats order as ints */
+    }
+    __syncthreads();
+    if (warp != 0) return;
     /* K rounds: smallest (d2, id) strictly after the previous pick */
     float pd = -1.0f; int pi = -1; float dK = 0.0f; int found = 0;
     for (int r = 0; r < K; r++) {
         float bd = inf; int bi = 0x7fffffff;
         for (int c = lane; c < n_surv; c += 32) {
-            const float d = s_d[w][c];
+            const float d = s_d[c];
             if (!(d < inf)) continue;
-            const int id = s_id[w][c] * id_mul + id_add;
+            const int id = s_id[c] * id_mul + id_add;
             if (d < pd || (d == pd && id <= pi)) continue;
             if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; }
         }
@@ -693,13 +662,17 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(const float* __restrict
         bool certified = !overflow;
         if (cut < inf) {
             /* dropped keys have S >= cut, i.e. exact d2 > cut + |q|^2 - eps */
-            float qn = 0.0f;
-            for (int d = 0; d < R; d++) qn = fmaf(q[d], q[d], qn);
-            const float sn = sqrtf(qn) + sqrtf(__ldg(kn2max));
-            const float eps = 1.52587890625e-05f * sn * sn + 2.0e-6f * dK;       /* 2^-16 (|q|+|k|max)^2 + exact-side rounding */
+            const float eps = eps0 + 2.0e-6f * dK;                  /* + exact-side rounding */
             certified = certified && (found == K) && (dK + eps < cut + qn);
         }
-        if (!certified) fail_list[atomicAdd(fail_count, 1)] = qi;
+        if (!certified) fail_list[atomicAdd(fail_count, 1)] = q_off + qi;
+        if (!certified && err_probe) {                              /* developer counters: why */
+            int* why = reinterpret_cast<int*>(err_probe) + 1;
+            if (overflow) atomicAdd(why + 0, 1);
+            else if (found != K) atomicAdd(why + 1, 1);
+            else atomicAdd(why + 2, 1);
+            if (n_surv >= kMaxSurvivors) atomicAdd(why + 3, 1);
+        }
     }
 }
 
@@ -709,102 +682,110 @@ bool scl_knn_tc_supported(int R) { return R == 20 || R == 40; }
 
 int scl_knn_tc_ranges(int Q)
 {
-    const int tiles = (Q + 127) / 128;
-    int r = SCL_NUM_SMS / tiles;
+    const int groups = (Q + kQPerCta - 1) / kQPerCta;
+    int r = SCL_NUM_SMS / groups;
     return r < 1 ? 1 : r;
 }
-
-int scl_knn_tc_kprime(int K) { (void)K; return kKPrime; }   /* fixed: the list is a register array */
-
-template <int R, int NT>
-static cudaError_t launch_tc(const float* qkeys, int Q, const float* keys, const float* knorm, int key_lo, int key_hi, int n_ranges,
-                             int kprime, int sub_base, int n_sub_total, int* g_thr, float* prop_s, int32_t* prop_idx, float* prop_cut,
-                             cudaStream_t stream)
+int scl_knn_tc_max_batch() { return 1024; }          /* larger batches are cut into launches of this many queries */
+int scl_knn_tc_kprime() { return kKPrime; }
+size_t scl_knn_tc_queue_bytes() { return (size_t)kQueueCap * 12 * 4; }      /* per (query, range) */
+size_t scl_knn_tc_image_bytes(int R, int n_keys)
 {
-    using C = TcCfg<R, NT>;
+    const size_t tiles = ((size_t)n_keys + kNT - 1) / kNT;
+    return tiles * (R == 20 ? TcCfg<20>::TILE_BYTES : TcCfg<40>::TILE_BYTES);
+}
+
+cudaError_t scl_launch_key_image(const float* keys, const float* knorm, int k_lo, int k_hi, int R, unsigned char* img, cudaStream_t stream)
+{
+    if (k_hi <= k_lo) return cudaSuccess;
+    const int blocks = (k_hi - k_lo + 127) / 128;
+    if (R == 20) key_image_kernel<20><<<blocks, 128, 0, stream>>>(keys, knorm, k_lo, k_hi, img);
+    else if (R == 40) key_image_kernel<40><<<blocks, 128, 0, stream>>>(keys, knorm, k_lo, k_hi, img);
+    else return cudaErrorNotSupported;
+    return cudaGetLastError();
+}
+
+template <int R>
+static cudaError_t launch_tc(const float* qkeys, int Q, const unsigned char* img, int n_db, int n_ranges, int* slots,
+                              uint32_t* hq, int* hq_cnt, int* dbg, cudaStream_t stream)
+{
+    using C = TcCfg<R>;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<R, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(knn_tc_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::TOTAL);
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    int range_len = (key_hi - key_lo + n_ranges - 1) / n_ranges;
-    range_len = (range_len + NT - 1) / NT * NT;
-    if (range_len < NT) range_len = NT;
-    const int tiles = (Q + 127) / 128;
+    const int groups = (Q + kQPerCta - 1) / kQPerCta;
     long long* times = nullptr;
     const bool want_times = getenv("SCL_TC_TIMES") != nullptr;       /* developer aid: per-role cycle counters on stderr */
-    if (want_times) { cudaMalloc(&times, (size_t)tiles * n_ranges * 16 * sizeof(long long)); cudaMemset(times, 0, (size_t)tiles * n_ranges * 128); }
-    knn_tc_kernel<R, NT><<<tiles * n_ranges, kThreads, C::TOTAL, stream>>>(qkeys, Q, keys, knorm, key_lo, key_hi, range_len, n_ranges, kprime,
-                                                                          sub_base, n_sub_total, times, g_thr, prop_s, prop_idx, prop_cut);
+    const int nb = groups * n_ranges;
+    if (want_times) { cudaMalloc(&times, (size_t)nb * 16 * sizeof(long long)); cudaMemsetAsync(times, 0, (size_t)nb * 128, stream); }
+    if (want_times) knn_tc_kernel<R, true><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, times, slots, hq, hq_cnt, dbg);
+    else knn_tc_kernel<R, false><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, nullptr, slots, hq, hq_cnt, dbg);
     if (want_times) {
-        const int nb = tiles * n_ranges;
         std::vector<long long> h((size_t)nb * 16);
         cudaStreamSynchronize(stream);
         cudaMemcpy(h.data(), times, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-        double a[16] = {0};
+        double a[16] = {0}, amax4 = 0;
         for (int b = 0; b < nb; b++) for (int i = 0; i < 16; i++) a[i] += (double)h[(size_t)b * 16 + i] / nb;
-        fprintf(stderr, "[tc keys %d..%d] tiles/CTA %.0f | cycles per tile: epilogue wait %.0f work %.0f (tmem %.0f, slow path %.0f of which folds %.0f) | producer wait %.0f work %.0f | "
-                        "mma wait_tmem %.0f wait_operands %.0f issue %.0f | per warp: slow chunks %.0f, pushes/lane %.1f, folds %.0f\n",
-                key_lo, key_hi, a[7], a[0] / a[7], a[1] / a[7], a[11] / a[7], a[12] / a[7], a[13] / a[7], a[2] / a[7], a[3] / a[7], a[4] / a[7], a[5] / a[7], a[6] / a[7],
-                a[8] / 32, a[9] / 32, a[10]);
+        for (int b = 0; b < nb; b++) if ((double)h[(size_t)b * 16 + 4] > amax4) amax4 = (double)h[(size_t)b * 16 + 4];
+        fprintf(stderr, "[tc n_db %d] tiles/CTA %.0f | per tile, per epilogue warp: total %.0f cycles, waiting for the accumulator %.0f, in tcgen05.wait::ld %.0f, examining %.0f | slow 32-col chunks per warp %.0f of %.0f, "
+                        "groups queued per (query, range) %.1f (largest %.0f) | mma thread per tile: wait key tile %.0f, wait accumulators + issue %.0f | service sweeps %.0f\n",
+                n_db, a[8], a[1] / 8 / a[8], a[0] / 8 / a[8], a[9] / 8 / a[8], a[10] / 8 / a[8], a[2] / 8, a[8] * 4, a[3] / 8 / 32, amax4, a[6] / a[8], a[7] / a[8], a[5] / 2);
         cudaFree(times);
     }
     return cudaGetLastError();
 }
 
-// The sample pass covers the first keys of the database (1/16 of it, at most 65,536): its only purpose is to hand the
-// main pass a tight starting threshold per query, which removes the start-up transient of the streaming top-K'
-// (~K' ln(n/K') hits per thread) from 15/16 of the stream.
-int scl_knn_tc_sample(int n_db)
-{
-    int n_s = n_db / 16;
-    if (n_s > 65536) n_s = 65536;
-    n_s &= ~255;
-    return n_s < 4096 ? 0 : n_s;
-}
-
-cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, const float* knorm, const float* kn2max, int n_db, int R, int K,
-                              int metric, int id_mul, int id_add, KnnTcWorkspace ws, int32_t* out_ids, float* out_d2,
-                              int32_t* fail_list, int* fail_count, cudaStream_t stream)
+cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, const unsigned char* img, const float* kn2max, int n_db, int R, int K,
+                               int metric, int id_mul, int id_add, KnnTcWorkspace ws, int32_t* out_ids, float* out_d2,
+                               int32_t* fail_list, int* fail_count, cudaStream_t stream)
 {
     if (Q <= 0) return cudaSuccess;
-    const int n_ranges = scl_knn_tc_ranges(Q);
-    const int kprime = scl_knn_tc_kprime(K);
-    if (K > kprime - 2) return cudaErrorInvalidValue;
-    const int n_sub = 2 * n_ranges;                       /* proposal lists per launch: two column halves per CTA */
-    const int n_s = scl_knn_tc_sample(n_db);
-    const int n_sub_total = n_s > 0 ? 2 * n_sub : n_sub;
-    if ((size_t)Q * n_sub_total * kprime > ws.capacity) return cudaErrorInvalidValue;
+    if (R != 20 && R != 40) return cudaErrorNotSupported;
+    if (K > kKPrime - 2) return cudaErrorInvalidValue;
     cudaError_t err = cudaMemsetAsync(fail_count, 0, sizeof(int), stream);
     if (err != cudaSuccess) return err;
-    err = cudaMemsetAsync(ws.g_thr, 0x7f, (size_t)Q * sizeof(int), stream);   /* 0x7f7f7f7f = 3.4e38: "no threshold yet" */
-    if (err != cudaSuccess) return err;
-    if (R != 20 && R != 40) return cudaErrorNotSupported;
-    if (n_db >= 4 * kBootKeys) {
-        if (R == 20) knn_bootstrap_kernel<20><<<(Q + 7) / 8, 256, 0, stream>>>(qkeys, Q, keys, knorm, kn2max, n_db, kprime, ws.g_thr);
-        else knn_bootstrap_kernel<40><<<(Q + 7) / 8, 256, 0, stream>>>(qkeys, Q, keys, knorm, kn2max, n_db, kprime, ws.g_thr);
+    const int max_b = scl_knn_tc_max_batch();
+    for (int q0 = 0; q0 < Q; q0 += max_b) {
+        const int Qc = Q - q0 < max_b ? Q - q0 : max_b;
+        const int n_ranges = scl_knn_tc_ranges(Qc);
+        if ((size_t)Qc * n_ranges > ws.capacity) return cudaErrorInvalidValue;
+        err = cudaMemsetAsync(ws.slots, 0x7f, (size_t)Qc * kKPrime * 4, stream);     /* 3.39e38: "no key yet" */
+        if (err != cudaSuccess) return err;
+        const float* qk = qkeys + (size_t)q0 * R;
+        if (R == 20) err = launch_tc<20>(qk, Qc, img, n_db, n_ranges, ws.slots, ws.hq, ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), stream);
+        else err = launch_tc<40>(qk, Qc, img, n_db, n_ranges, ws.slots, ws.hq, ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), stream);
+        if (err != cudaSuccess) return err;
+        if (metric == 0)
+            knn_rerank_kernel<0><<<Qc, 128, 0, stream>>>(qk, Qc, keys, R, K, n_ranges, n_db, ws.hq, ws.hq_cnt, ws.slots,
+                                                                                      kn2max, id_mul, id_add, out_ids + (size_t)q0 * K, out_d2 + (size_t)q0 * K, q0,
+                                                                                      fail_list, fail_count, ws.err_probe);
+        else
+            knn_rerank_kernel<1><<<Qc, 128, 0, stream>>>(qk, Qc, keys, R, K, n_ranges, n_db, ws.hq, ws.hq_cnt, ws.slots,
+                                                                                      kn2max, id_mul, id_add, out_ids + (size_t)q0 * K, out_d2 + (size_t)q0 * K, q0,
+                                                                                      fail_list, fail_count, ws.err_probe);
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;
     }
-    for (int pass = (n_s > 0 ? 0 : 1); pass < 2; pass++) {
-        const int lo = pass == 0 ? 0 : n_s, hi = pass == 0 ? n_s : n_db;
-        const int sub_base = (pass == 1 && n_s > 0) ? n_sub : 0;
-        if (R == 20) err = launch_tc<20, 256>(qkeys, Q, keys, knorm, lo, hi, n_ranges, kprime, sub_base, n_sub_total, ws.g_thr, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
-        else err = launch_tc<40, 128>(qkeys, Q, keys, knorm, lo, hi, n_ranges, kprime, sub_base, n_sub_total, ws.g_thr, ws.prop_s, ws.prop_idx, ws.prop_cut, stream);
-        if (err != cudaSuccess) return err;
-        if (pass == 0) {
-            knn_sample_thr_kernel<<<(Q + 3) / 4, 128, 0, stream>>>(ws.prop_s, Q, n_sub_total, n_sub, kprime, ws.g_thr);
-            err = cudaGetLastError();
-            if (err != cudaSuccess) return err;
+    if (ws.err_probe && getenv("SCL_TC_DEBUG")) {                   /* developer aid */
+        int h[6];
+        cudaStreamSynchronize(stream);
+        {
+            const int Qc = Q < max_b ? Q : max_b;
+            std::vector<int> sl((size_t)Qc * kKPrime);
+            cudaMemcpy(sl.data(), ws.slots, sl.size() * 4, cudaMemcpyDeviceToHost);
+            int per_slot[kKPrime] = {0};
+            for (int q = 0; q < Qc; q++) for (int k = 0; k < kKPrime; k++) if (sl[(size_t)q * kKPrime + k] >= 0x7f000000) per_slot[k]++;
+            fprintf(stderr, "[tc slots of the last launch, unfilled per slot]");
+            for (int k = 0; k < kKPrime; k++) fprintf(stderr, " %d", per_slot[k]);
+            fprintf(stderr, "\n");
         }
+        cudaMemcpy(h, ws.err_probe, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[tc Q %d n_db %d] worst |score error| / eps %.3f | uncertified so far: queue overflow %d, fewer than K survivors %d, certificate %d (survivor list full %d) | start-up waits timed out (warps) %d\n",
+                Q, n_db, *reinterpret_cast<float*>(&h[0]), h[1], h[2], h[3], h[4], h[5]);
     }
-    const int warps = 4;
-    if (metric == 0)
-        knn_rerank_kernel<0><<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(qkeys, Q, keys, R, K, n_sub_total, kprime, ws.prop_s, ws.prop_idx, ws.prop_cut,
-                                                                                kn2max, id_mul, id_add, out_ids, out_d2, fail_list, fail_count);
-    else
-        knn_rerank_kernel<1><<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(qkeys, Q, keys, R, K, n_sub_total, kprime, ws.prop_s, ws.prop_idx, ws.prop_cut,
-                                                                                kn2max, id_mul, id_add, out_ids, out_d2, fail_list, fail_count);
-    return cudaGetLastError();
+    return cudaSuccess;
 }

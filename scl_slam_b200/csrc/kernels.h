@@ -27,41 +27,25 @@ cudaError_t scl_launch_knn_exact(const float* qkeys, int Q, const float* keys, i
                                  int id_mul, int id_add, const int32_t* qlist, const int* qcount, KnnWorkspace ws,
                                  int32_t* out_ids, float* out_d2, cudaStream_t stream);
 
-// K3 on tcgen05 (k3_knn_tc.cu): tensor-core prefilter + exact re-rank + certificate. Queries whose top-K could not
-// be certified are appended to fail_list (count in *fail_count) for scl_launch_knn_exact.
+// K3 on tcgen05 (k3_knn_tc.cu): BF16x3 prefilter fed by TMA from a pre-split key image (scl_launch_key_image, 128-key
+// tiles in the tcgen05 shared-memory layout), union-bound thresholds, hit queues, exact re-rank + certificate. Queries whose
+// top-K could not be certified are appended to fail_list (count in *fail_count) for scl_launch_knn_exact.
 struct KnnTcWorkspace {
-    float* prop_s;       // [Q][ranges][K']
-    int32_t* prop_idx;   // [Q][ranges][K']
-    float* prop_cut;     // [Q][ranges]
-    float* exact;        // [Q][ranges*K']
-    int* g_thr;          // [Q] thresholds shared between the CTAs of a query tile
-    size_t capacity;     // in proposal entries
-};
-bool scl_knn_tc_supported(int R);
-int scl_knn_tc_ranges(int Q);
-int scl_knn_tc_kprime(int K);
-cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, const float* knorm, const float* kn2max, int n_db, int R, int K,
-                              int metric, int id_mul, int id_add, KnnTcWorkspace ws, int32_t* out_ids, float* out_d2,
-                              int32_t* fail_list, int* fail_count, cudaStream_t stream);
-
-// K3 on tcgen05, second generation (k3_knn_tc2.cu): BF16x3 prefilter fed by TMA from a pre-split key image
-// (scl_launch_key_image, 128-key tiles in the tcgen05 shared-memory layout), union-bound thresholds, exact re-rank.
-struct KnnTc2Workspace {
-    uint32_t* hq;        // [Qc][ranges] hit queues of scl_knn_tc2_queue_bytes() each (Qc = min(Q, scl_knn_tc2_max_batch()))
+    uint32_t* hq;        // [Qc][ranges] hit queues of scl_knn_tc_queue_bytes() each (Qc = min(Q, scl_knn_tc_max_batch()))
     int* hq_cnt;         // [Qc][ranges] groups queued
-    int* slots;          // [Qc][K'] range minima by range % K' (K' = scl_knn_tc2_kprime())
+    int* slots;          // [Qc][K'] range minima by range % K' (K' = scl_knn_tc_kprime())
     float* err_probe;    // null, or one float raised to the largest |prefilter score error| / eps seen (tests)
     size_t capacity;     // in (query, range) pairs
 };
-bool scl_knn_tc2_supported(int R);
-int scl_knn_tc2_ranges(int Q);
-int scl_knn_tc2_max_batch();
-int scl_knn_tc2_kprime();
-size_t scl_knn_tc2_queue_bytes();
-size_t scl_knn_tc2_image_bytes(int R, int n_keys);
+bool scl_knn_tc_supported(int R);
+int scl_knn_tc_ranges(int Q);
+int scl_knn_tc_max_batch();
+int scl_knn_tc_kprime();
+size_t scl_knn_tc_queue_bytes();
+size_t scl_knn_tc_image_bytes(int R, int n_keys);
 cudaError_t scl_launch_key_image(const float* keys, const float* knorm, int k_lo, int k_hi, int R, unsigned char* img, cudaStream_t stream);
-cudaError_t scl_launch_knn_tc2(const float* qkeys, int Q, const float* keys, const unsigned char* img, const float* kn2max, int n_db, int R, int K,
-                               int metric, int id_mul, int id_add, KnnTc2Workspace ws, int32_t* out_ids, float* out_d2,
+cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, const unsigned char* img, const float* kn2max, int n_db, int R, int K,
+                               int metric, int id_mul, int id_add, KnnTcWorkspace ws, int32_t* out_ids, float* out_d2,
                                int32_t* fail_list, int* fail_count, cudaStream_t stream);
 
 // K4: shift-aligned column-cosine distance for every (query, candidate) + winner scan. See k4_scdist.cu.

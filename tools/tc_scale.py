@@ -6,7 +6,7 @@ from scl_slam_b200 import synth, engine
 dev = torch.device("cuda:0"); N, K = 1 << 20, 10
 e = engine.ScanContextB200(numCandidates=K); e.set_stream(torch.cuda.current_stream().cuda_stream); e.reserve(N)
 for c0 in range(0, N, 1 << 17): e.insert_batch_dev(synth.desc_db(1 << 17, device=dev, start=c0))
-e.set_knn_mode(int(os.environ.get("TC_MODE", "3")), False)
+e.set_knn_mode(int(os.environ.get("TC_MODE", "2")), False)
 for Q in (1024, 256):
     q = synth.desc_queries(synth.desc_db(1 << 16, device=dev), Q)[0]
     ids = torch.empty((Q, K), dtype=torch.int32, device=dev); d2 = torch.empty((Q, K), device=dev)
