@@ -136,6 +136,14 @@ typedef struct {
 int scl_query_batch(scl_engine* e, const scl_batch_query* q, scl_batch_result* r);
 /* all pointers in q and r are device pointers; asynchronous on the engine's stream */
 int scl_query_batch_dev(scl_engine* e, const scl_batch_query* q, scl_batch_result* r);
+/* Pipelined host-buffer form, for a caller that streams batches (loopClosureThread draining a backlog,
+ * distributedMapping.h:1450-1473): submit returns as soon as the batch is enqueued, so the next batch can be
+ * submitted at once and its host-to-device copy (a second stream, double-buffered staging) overlaps the kernels
+ * of this one. scl_query_batch_wait(ticket) blocks until that batch's results are in the host arrays of r.
+ * At most two batches may be in flight; q_desc and the result arrays should be page-locked host memory (pageable
+ * memory works but serialises the copies) and must stay valid until the wait returns. */
+int scl_query_batch_submit(scl_engine* e, const scl_batch_query* q, scl_batch_result* r, int* ticket);
+int scl_query_batch_wait(scl_engine* e, int ticket);
 
 /* Multi-GPU merge: `world` per-rank result blocks of Q*K records, gathered
  * rank-major in device memory, are reduced to the global top-K by (d2, id) and then to the winner

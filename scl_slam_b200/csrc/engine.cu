@@ -260,26 +260,11 @@ int query_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, i
     return scdist_dev(e, q_desc, q_local, q_ids, Q, K, cand_ids, missing_to_zero, cand_dist, cand_shift, best_id, best_dist, best_shift);
 }
 
-int query_host(scl_engine* e, const scl_batch_query* q, scl_batch_result* r, int missing_to_zero)
+// device-side part of a host-buffer query: kernels + the device-to-host copies of whatever r asks for (no sync)
+int query_host_enqueue(scl_engine* e, const float* dq, const int32_t* di, const scl_batch_query* q, scl_batch_result* r, int missing_to_zero)
 {
-    if (!q || !r) FAIL(SCL_ERR_INVALID, "null query/result");
     const int Q = q->Q, K = q->K;
-    if (Q <= 0) return SCL_OK;
-    if (K < 1 || K > 32) FAIL(SCL_ERR_INVALID, "K must be in 1..32");
-    const size_t QK = (size_t)Q * K, RS = e->RS();
-    const float* dq = nullptr; const int32_t* di = nullptr;
-    if (q->q_desc) {
-        CK(e->qdesc.ensure((size_t)Q * RS * 4));
-        CK(cudaMemcpyAsync(e->qdesc.p, q->q_desc, (size_t)Q * RS * 4, cudaMemcpyHostToDevice, e->stream));
-        dq = e->qdesc.as<float>();
-    }
-    if (q->q_ids) {
-        for (int i = 0; i < Q && !q->q_desc; i++)
-            if (q->q_ids[i] < 0 || q->q_ids[i] >= e->n) FAIL(SCL_ERR_RANGE, "query key out of range");
-        CK(e->qids.ensure((size_t)Q * 4));
-        CK(cudaMemcpyAsync(e->qids.p, q->q_ids, (size_t)Q * 4, cudaMemcpyHostToDevice, e->stream));
-        di = e->qids.as<int32_t>();
-    }
+    const size_t QK = (size_t)Q * K;
     CK(e->cand_ids.ensure(QK * 4)); CK(e->cand_d2.ensure(QK * 4)); CK(e->cand_dist.ensure(QK * 8)); CK(e->cand_shift.ensure(QK * 4));
     CK(e->best_id.ensure((size_t)Q * 4)); CK(e->best_dist.ensure((size_t)Q * 8)); CK(e->best_shift.ensure((size_t)Q * 4));
     int rc = query_dev(e, dq, di, Q, K, q->n_db, q->metric, missing_to_zero, e->cand_ids.as<int32_t>(), e->cand_d2.as<float>(),
@@ -293,6 +278,38 @@ int query_host(scl_engine* e, const scl_batch_query* q, scl_batch_result* r, int
     if (r->best_id) CK(cudaMemcpyAsync(r->best_id, e->best_id.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, e->stream));
     if (r->best_dist) CK(cudaMemcpyAsync(r->best_dist, e->best_dist.p, (size_t)Q * 8, cudaMemcpyDeviceToHost, e->stream));
     if (r->best_shift) CK(cudaMemcpyAsync(r->best_shift, e->best_shift.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, e->stream));
+    return SCL_OK;
+}
+
+int check_host_query(scl_engine* e, const scl_batch_query* q, scl_batch_result* r)
+{
+    if (!q || !r) FAIL(SCL_ERR_INVALID, "null query/result");
+    if (q->Q <= 0) return SCL_OK;
+    if (q->K < 1 || q->K > 32) FAIL(SCL_ERR_INVALID, "K must be in 1..32");
+    if (q->q_ids && !q->q_desc)
+        for (int i = 0; i < q->Q; i++)
+            if (q->q_ids[i] < 0 || q->q_ids[i] >= e->n) FAIL(SCL_ERR_RANGE, "query key out of range");
+    return SCL_OK;
+}
+
+int query_host(scl_engine* e, const scl_batch_query* q, scl_batch_result* r, int missing_to_zero)
+{
+    int rc = check_host_query(e, q, r); if (rc) return rc;
+    const int Q = q->Q;
+    if (Q <= 0) return SCL_OK;
+    const size_t RS = e->RS();
+    const float* dq = nullptr; const int32_t* di = nullptr;
+    if (q->q_desc) {
+        CK(e->qdesc.ensure((size_t)Q * RS * 4));
+        CK(cudaMemcpyAsync(e->qdesc.p, q->q_desc, (size_t)Q * RS * 4, cudaMemcpyHostToDevice, e->stream));
+        dq = e->qdesc.as<float>();
+    }
+    if (q->q_ids) {
+        CK(e->qids.ensure((size_t)Q * 4));
+        CK(cudaMemcpyAsync(e->qids.p, q->q_ids, (size_t)Q * 4, cudaMemcpyHostToDevice, e->stream));
+        di = e->qids.as<int32_t>();
+    }
+    rc = query_host_enqueue(e, dq, di, q, r, missing_to_zero); if (rc) return rc;
     CK(cudaStreamSynchronize(e->stream));
     return SCL_OK;
 }
@@ -351,6 +368,8 @@ int scl_destroy(scl_engine* e)
         for (DevBuf* b : bufs) b->release();
         for (auto& v : e->ev) for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         for (cudaEvent_t x : e->ev_pool) cudaEventDestroy(x);
+        for (int i = 0; i < 2; i++) { e->pipe_qdesc[i].release(); e->pipe_qids[i].release(); if (e->pipe_copied[i]) cudaEventDestroy(e->pipe_copied[i]); if (e->pipe_done[i]) cudaEventDestroy(e->pipe_done[i]); }
+        if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
         if (e->own_stream) cudaStreamDestroy(e->stream);
     }
     delete e;
@@ -512,6 +531,64 @@ int scl_query_batch_dev(scl_engine* e, const scl_batch_query* q, scl_batch_resul
     if (!q || !r) FAIL(SCL_ERR_INVALID, "null query/result");
     return query_dev(e, q->q_desc, q->q_ids, q->Q, q->K, q->n_db, q->metric, 0, r->cand_ids, r->cand_d2, r->cand_dist, r->cand_shift,
                      r->best_id, r->best_dist, r->best_shift);
+}
+
+int scl_query_batch_submit(scl_engine* e, const scl_batch_query* q, scl_batch_result* r, int* ticket)
+{
+    LOCK();
+    if (!ticket) FAIL(SCL_ERR_INVALID, "null ticket");
+    int rc = check_host_query(e, q, r); if (rc) return rc;
+    const int b = (int)(e->pipe_next & 1);
+    if (e->pipe_busy[b]) FAIL(SCL_ERR_INVALID, "two batches are already in flight: wait for the older one first");
+    if (!e->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CK(cudaEventCreateWithFlags(&e->pipe_copied[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&e->pipe_done[i], cudaEventDisableTiming));
+        }
+    }
+    const int Q = q->Q;
+    const size_t RS = e->RS();
+    const float* dq = nullptr; const int32_t* di = nullptr;
+    if (Q > 0) {
+        /* staging buffer b was last read by the batch submitted two calls ago, whose wait has returned (pipe_busy) */
+        if (q->q_desc) {
+            CK(e->pipe_qdesc[b].ensure((size_t)Q * RS * 4));
+            CK(cudaMemcpyAsync(e->pipe_qdesc[b].p, q->q_desc, (size_t)Q * RS * 4, cudaMemcpyHostToDevice, e->copy_stream));
+            dq = e->pipe_qdesc[b].as<float>();
+        }
+        if (q->q_ids) {
+            CK(e->pipe_qids[b].ensure((size_t)Q * 4));
+            CK(cudaMemcpyAsync(e->pipe_qids[b].p, q->q_ids, (size_t)Q * 4, cudaMemcpyHostToDevice, e->copy_stream));
+            di = e->pipe_qids[b].as<int32_t>();
+        }
+        CK(cudaEventRecord(e->pipe_copied[b], e->copy_stream));
+        CK(cudaStreamWaitEvent(e->stream, e->pipe_copied[b], 0));
+        rc = query_host_enqueue(e, dq, di, q, r, 0); if (rc) return rc;
+    }
+    CK(cudaEventRecord(e->pipe_done[b], e->stream));
+    e->pipe_busy[b] = true;
+    *ticket = (int)(e->pipe_next & 0x7fffffff);
+    e->pipe_next++;
+    return SCL_OK;
+}
+
+int scl_query_batch_wait(scl_engine* e, int ticket)
+{
+    if (!e) return SCL_ERR_INVALID;
+    cudaEvent_t ev;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        const int b = ticket & 1;
+        if (!e->pipe_busy[b]) FAIL(SCL_ERR_INVALID, "no batch in flight for this ticket");
+        ev = e->pipe_done[b];
+    }
+    cudaSetDevice(e->device);
+    cudaError_t err = cudaEventSynchronize(ev);              /* outside the lock: inserts and submits may proceed meanwhile */
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->pipe_busy[ticket & 1] = false;
+    if (err != cudaSuccess) { e->err = std::string("cudaEventSynchronize: ") + cudaGetErrorString(err); return SCL_ERR_CUDA; }
+    return SCL_OK;
 }
 
 int scl_merge_shards_dev(scl_engine* e, int world, int Q, int K, const int32_t* q_ids, const int32_t* all_ids, const float* all_d2,

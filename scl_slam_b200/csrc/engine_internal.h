@@ -54,6 +54,12 @@ struct scl_engine {
     DevBuf tc_queues, tc_queue_cnt, tc_slots, tc_fail_list, tc_fail_count, tc_err_probe;
     DevBuf icp_src, icp_tgt, icp_raw, icp_grid[2][5], icp_acc, icp_nn;
     size_t gbins_scans = 0;
+    /* pipelined host-buffer queries (scl_query_batch_submit / _wait) */
+    cudaStream_t copy_stream = nullptr;
+    DevBuf pipe_qdesc[2], pipe_qids[2];
+    cudaEvent_t pipe_copied[2] = {nullptr, nullptr}, pipe_done[2] = {nullptr, nullptr};
+    bool pipe_busy[2] = {false, false};
+    long long pipe_next = 0;
     /* per-stage event timing */
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[4];

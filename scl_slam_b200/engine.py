@@ -27,6 +27,7 @@ EXPORTS = [
     "scl_get_ring_key", "scl_query_intra", "scl_query_inter", "scl_query_batch", "scl_query_batch_dev",
     "scl_merge_shards_dev", "scl_icp", "scl_set_profiling", "scl_stage_time", "scl_set_knn_mode", "scl_knn_stats",
     "scl_default_ransac_params", "scl_verify_ransac", "scl_knn_batch_dev", "scl_merge_topk_dev", "scl_scdist_owned_dev", "scl_combine_owned_dev",
+    "scl_query_batch_submit", "scl_query_batch_wait",
 ]
 
 
@@ -90,6 +91,8 @@ def load_library():
     lib.scl_query_inter.argtypes = lib.scl_query_intra.argtypes
     lib.scl_query_batch.argtypes = [C.c_void_p, C.POINTER(SclBatchQuery), C.POINTER(SclBatchResult)]
     lib.scl_query_batch_dev.argtypes = lib.scl_query_batch.argtypes
+    lib.scl_query_batch_submit.argtypes = [C.c_void_p, C.POINTER(SclBatchQuery), C.POINTER(SclBatchResult), C.POINTER(C.c_int)]
+    lib.scl_query_batch_wait.argtypes = [C.c_void_p, C.c_int]
     lib.scl_merge_shards_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.POINTER(SclBatchResult)]
     lib.scl_knn_batch_dev.argtypes = [C.c_void_p, C.POINTER(SclBatchQuery), C.c_void_p, C.c_void_p]
@@ -258,6 +261,22 @@ class ScanContextB200:
                              ("cand_ids", "cand_d2", "cand_dist", "cand_shift", "best_id", "best_dist", "best_shift")])
         self._ck(self.lib.scl_query_batch(self.h, C.byref(q), C.byref(r)))
         return out
+
+    def query_batch_submit(self, q_desc, out, K=None, n_db=None, metric=0):
+        """Pipelined host-buffer query (scl_query_batch_submit): q_desc and the arrays of `out` (scl_batch_result field
+        names -> numpy arrays, ideally page-locked) must stay alive until query_batch_wait(ticket) returns."""
+        K = K or self.K
+        Q = q_desc.shape[0]
+        n_db = self.getSize() if n_db is None else n_db
+        q = SclBatchQuery(q_desc.ctypes.data, None, Q, K, n_db, metric)
+        r = SclBatchResult(*[out[k].ctypes.data if out.get(k) is not None else None for k in
+                             ("cand_ids", "cand_d2", "cand_dist", "cand_shift", "best_id", "best_dist", "best_shift")])
+        t = C.c_int()
+        self._ck(self.lib.scl_query_batch_submit(self.h, C.byref(q), C.byref(r), C.byref(t)))
+        return t.value
+
+    def query_batch_wait(self, ticket):
+        self._ck(self.lib.scl_query_batch_wait(self.h, ticket))
 
     def query_batch_dev(self, q_desc_dev, q_ids_dev, Q, K, n_db, metric, out):
         """Device-pointer batch query, asynchronous on the engine's stream. `out` maps the

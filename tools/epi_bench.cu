@@ -30,10 +30,20 @@ template <int MODE> __device__ __forceinline__ bool examine(uint32_t (&r)[32], f
     const float m = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
     return __any_sync(0xffffffffu, m < thr);
 }
-template <int MODE>
-__global__ void __launch_bounds__(384, 1) bench(int iters, int warps, float thr, long long* out, int* sink)
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo)
 {
+    return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) | ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | ((uint64_t)1 << 46);
+}
+template <int MODE>
+__global__ void __launch_bounds__(416, 1) bench(int iters, int warps, float thr, int mma_n, long long* out, int* sink)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint32_t tmem_slot;
+    __shared__ uint64_t bar;
+    __shared__ volatile int stop;
+    if (mma_n > 0) for (int i = threadIdx.x; i < 48 * 1024 / 4; i += 416) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    if (threadIdx.x == 0) { stop = 0; asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar))); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (threadIdx.x < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -59,25 +69,47 @@ __global__ void __launch_bounds__(384, 1) bench(int iters, int warps, float thr,
         wait32(va);
         const long long t1 = clock64();
         if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+        __syncwarp();
+        if (threadIdx.x == 0) stop = 1;
+    } else if (mma_n > 0 && threadIdx.x == 384) {
+        /* a stream of bf16 MMAs (M = 128, N = mma_n, K = 16) into the upper TMEM columns, 4 per accumulator like the kNN kernel */
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(mma_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t a0 = smem_u32(smem), b0 = a0 + 16 * 1024;
+        int n = 0;
+        while (!stop && n < 400000) {
+            for (int k = 0; k < 4; k++)
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                             ::"r"(tmem + 256 + (uint32_t)((n & 4) ? 128 : 0)), "l"(make_desc(a0 + k * 2 * 2048, 2048, 128)), "l"(make_desc(b0 + k * 2 * 2048, 2048, 128)), "r"(idesc), "r"(k > 0 ? 1u : 0u) : "memory");
+            n += 4;
+            if ((n & 31) == 0) {   /* bound the queue depth */
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+                uint32_t done = 0; const uint32_t par = ((n >> 5) - 1) & 1;
+                while (!done) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(&bar)), "r"(par) : "memory");
+            }
+        }
+        if (blockIdx.x == 0) out[1] = n;
     }
-    sink[blockIdx.x * 384 + threadIdx.x] = hits;
+    if (threadIdx.x < 384) sink[blockIdx.x * 384 + threadIdx.x] = hits;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
-template <int MODE> void run(const char* name, int warps)
+template <int MODE> void run(const char* name, int warps, int mma_n, int dyn_smem = 48 * 1024)
 {
     long long* d; int* sink; cudaMalloc(&d, 16); cudaMalloc(&sink, 148 * 384 * 4); cudaMemset(d, 0, 16);
     const int iters = 2000;
-    for (int rep = 0; rep < 2; rep++) bench<MODE><<<148, 384>>>(iters, warps, -1.0e30f, d, sink);
+    cudaFuncSetAttribute(bench<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int rep = 0; rep < 2; rep++) bench<MODE><<<148, 416, dyn_smem>>>(iters, warps, -1.0e30f, mma_n, d, sink);
     cudaError_t e = cudaDeviceSynchronize();
-    long long h = 0; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
-    printf("%-10s %2d warps/SM: %6.1f cycles per 32-column chunk per warp -> %6.1f cycles per 128x256 tile-equivalent (%s)\n", name, warps,
-           (double)h / iters / 4, (double)h / iters / 4 * (1024.0 / warps), cudaGetErrorString(e));
+    long long h[2] = {0, 0}; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    const double per_chunk = (double)h[0] / iters / 4;
+    printf("%-8s smem %3d KB %2d warps/SM, concurrent MMA N=%3d: %6.1f cycles per 32-column chunk per warp = %6.1f cycles per 256x128 scores per SM; %6.1f cycles per MMA (%s)\n", name, dyn_smem / 1024, warps, mma_n,
+           per_chunk, per_chunk * 32.0 / warps, h[1] ? (double)h[0] / h[1] : 0.0, cudaGetErrorString(e));
     cudaFree(d); cudaFree(sink);
 }
 int main()
 {
-    for (int w : {4, 8, 12}) { run<0>("FMNMX3", w); run<1>("FMNMX", w); }
+    for (int sm : {0, 48 * 1024, 190 * 1024}) for (int w : {4, 8}) run<0>("FMNMX3", w, 0, sm);
+    for (int w : {4, 8}) run<0>("FMNMX3", w, 128, 48 * 1024);
     return 0;
 }
