@@ -299,6 +299,52 @@ __global__ void __launch_bounds__(256) ring_key_kernel(const float* __restrict__
     }
 }
 
+// The same with compile-time geometry (20x60, 40x120): the descriptor is fetched with 16-byte loads that are ALL in
+// flight before the first one is used (one DRAM round trip per descriptor instead of ten), the index arithmetic folds,
+// and two warps share a descriptor's rows when R > 32. The sums keep the reference's order (sequential, FP64).
+template <int R, int S, int kWarps>
+__global__ void __launch_bounds__(32 * kWarps) ring_key_fixed_kernel(const float* __restrict__ desc, int n, float* __restrict__ keys,
+                                                             float* __restrict__ knorm, float* __restrict__ kn2max)
+{
+    constexpr int kPitch = S | 1, kV4 = R * S / 4, kPerLane = (kV4 + 31) / 32;
+    static_assert((R * S) % 4 == 0 && S % 4 == 0, "rows are whole float4s");
+    __shared__ float tile[kWarps][R * kPitch];
+    __shared__ float skey[kWarps][R];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = blockIdx.x * kWarps + warp;
+    if (d >= n) return;
+    const float4* src = reinterpret_cast<const float4*>(desc + (size_t)d * R * S);
+    float4 v[kPerLane];
+#pragma unroll
+    for (int i = 0; i < kPerLane; i++) { const int k = lane + 32 * i; v[i] = k < kV4 ? __ldg(src + k) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+    for (int i = 0; i < kPerLane; i++) {
+        const int k = lane + 32 * i;
+        if (k < kV4) {
+            const int e = 4 * k, r = e / S, c = e % S;       /* a float4 never straddles a row: S % 4 == 0 */
+            float* t = &tile[warp][r * kPitch + c];
+            t[0] = v[i].x; t[1] = v[i].y; t[2] = v[i].z; t[3] = v[i].w;
+        }
+    }
+    __syncwarp();
+    for (int r = lane; r < R; r += 32) {
+        double s = 0.0;
+#pragma unroll 4
+        for (int c = 0; c < S; c++) s = __dadd_rn(s, (double)tile[warp][r * kPitch + c]);
+        const float kf = __double2float_rn(__ddiv_rn(s, (double)S));
+        keys[(size_t)d * R + r] = kf;
+        skey[warp][r] = kf;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        float n2 = 0.0f;
+#pragma unroll
+        for (int r = 0; r < R; r++) n2 = fmaf(skey[warp][r], skey[warp][r], n2);
+        knorm[d] = n2;
+        if (kn2max) atomicMax(reinterpret_cast<int*>(kn2max), __float_as_int(n2));
+    }
+}
+
 } // namespace
 
 cudaError_t scl_launch_polar(const void* pts_dev, const int* offsets_dev, int n_scans, int max_points, int stride_bytes,
@@ -349,6 +395,10 @@ cudaError_t scl_launch_polar(const void* pts_dev, const int* offsets_dev, int n_
 cudaError_t scl_launch_ring_keys(const float* desc_dev, int n, int R, int S, float* keys, float* knorm, float* kn2max, cudaStream_t stream)
 {
     if (n <= 0) return cudaSuccess;
+    if ((reinterpret_cast<uintptr_t>(desc_dev) & 15) == 0) {
+        if (R == 20 && S == 60) { ring_key_fixed_kernel<20, 60, 4><<<(n + 3) / 4, 128, 0, stream>>>(desc_dev, n, keys, knorm, kn2max); return cudaGetLastError(); }
+        if (R == 40 && S == 120) { ring_key_fixed_kernel<40, 120, 2><<<(n + 1) / 2, 64, 0, stream>>>(desc_dev, n, keys, knorm, kn2max); return cudaGetLastError(); }
+    }
     const int warps = 8;
     const size_t smem = (size_t)warps * (R * (S | 1) + R) * sizeof(float);
     static bool attr_done = false;

@@ -265,29 +265,37 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(scl_smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    {   /* A operand: rows = the CTA's 256 queries, columns [-2 q0 | -2 q0 | -2 q1 | 1 1 1 0..] */
-        for (int i = threadIdx.x; i < kQPerCta * C::CHUNKS; i += kThreads) {
-            const int m = i % kQPerCta, c = i / kQPerCta;
-            const int qi = q_base + m;
+    if (threadIdx.x < kQPerCta) {
+        /* A operand: rows = the CTA's 256 queries, columns [-2 q0 | -2 q0 | -2 q1 | 1 1 1 0..]. One thread per row: its key
+         * is fetched with R/4 independent 16-byte loads (one L2 round trip), split, and written as CHUNKS 16-byte stores. */
+        const int m = threadIdx.x, qi = q_base + m;
+        float a0[R], a1[R];                             /* -2 q0, -2 q1 */
+#pragma unroll
+        for (int g = 0; g < R / 4; g++) {
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (qi < Q) x = __ldg(reinterpret_cast<const float4*>(qkeys + (size_t)qi * R) + g);
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float q0 = bf16_round(xs[i]);
+                a0[4 * g + i] = -2.0f * q0;
+                a1[4 * g + i] = -2.0f * bf16_round(xs[i] - q0);
+            }
+        }
+        const float one = qi < Q ? 1.0f : 0.0f;
+        const int r = m & 127;
+        unsigned char* dst = smem + C::OFF_A + (uint32_t)(m >> 7) * C::TILE_BYTES + (uint32_t)(r >> 3) * C::SBO + (uint32_t)(r & 7) * 16;
+#pragma unroll
+        for (int c = 0; c < C::CHUNKS; c++) {
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const int idx = 8 * c + j;
-                float x = 0.0f;
-                if (qi < Q) {
-                    if (idx < 3 * R) {
-                        const float q = __ldg(qkeys + (size_t)qi * R + idx % R);
-                        const float q0 = bf16_round(q);
-                        x = idx < 2 * R ? -2.0f * q0 : -2.0f * bf16_round(q - q0);
-                    } else if (idx < 3 * R + 3) {
-                        x = 1.0f;
-                    }
-                }
-                v[j] = x;
+                const int idx = 8 * c + j;              /* compile-time after unrolling */
+                v[j] = idx < R ? a0[idx < R ? idx : 0] : idx < 2 * R ? a0[idx < 2 * R && idx >= R ? idx - R : 0]
+                     : idx < 3 * R ? a1[idx < 3 * R && idx >= 2 * R ? idx - 2 * R : 0] : idx < 3 * R + 3 ? one : 0.0f;
             }
-            const int r = m & 127;
-            unsigned char* dst = smem + C::OFF_A + (uint32_t)(m >> 7) * C::TILE_BYTES + (uint32_t)c * C::LBO + (uint32_t)(r >> 3) * C::SBO + (uint32_t)(r & 7) * 16;
-            *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            *reinterpret_cast<uint4*>(dst + (uint32_t)c * C::LBO) =
+                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
     }
     fence_async_smem();
