@@ -17,6 +17,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
     return d;
 }
 
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
 template <int KIND>  // 0 tf32, 1 f16(bf16)
 __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc)
 {
@@ -27,7 +31,7 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t
 }
 
 // variant: KIND, swizzle (0 none, 1 = 128B), N
-template <int KIND, int SW, int N>
+template <int KIND, int SW, int N, int TS = 0>
 __global__ void __launch_bounds__(128, 1) bench(int iters, int ksteps, long long* out)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -63,7 +67,8 @@ __global__ void __launch_bounds__(128, 1) bench(int iters, int ksteps, long long
                     da = make_desc(a0 + k * 32, 16, 1024, 2);
                     db = make_desc(b0 + k * 32, 16, 1024, 2);
                 }
-                mma<KIND>(tmem + (it & 1) * 256, da, db, idesc, (k > 0) ? 1u : 0u);
+                if (TS) mma_ts((N <= 128 ? tmem + (it % 3) * 128 : tmem + (it & 1) * 256 * 0), tmem + 448 + k * 8, db, idesc, (k > 0) ? 1u : 0u);
+                else mma<KIND>((N <= 128 ? tmem + (it & 3) * 128 : tmem + (it & 1) * 256), da, db, idesc, (k > 0) ? 1u : 0u);
             }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
@@ -78,13 +83,13 @@ __global__ void __launch_bounds__(128, 1) bench(int iters, int ksteps, long long
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
-template <int KIND, int SW, int N>
+template <int KIND, int SW, int N, int TS = 0>
 void run(const char* name, int ksteps)
 {
     long long* d; cudaMalloc(&d, 8);
     const int iters = 512;
-    cudaFuncSetAttribute(bench<KIND, SW, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    for (int rep = 0; rep < 2; rep++) bench<KIND, SW, N><<<148, 128, 96 * 1024>>>(iters, ksteps, d);
+    cudaFuncSetAttribute(bench<KIND, SW, N, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    for (int rep = 0; rep < 2; rep++) bench<KIND, SW, N, TS><<<148, 128, 96 * 1024>>>(iters, ksteps, d);
     cudaError_t e = cudaDeviceSynchronize();
     long long h = 0; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
     printf("%-34s ksteps=%d : %8.1f cycles / mma   (%s)\n", name, ksteps, (double)h / (iters * ksteps), cudaGetErrorString(e));
@@ -93,13 +98,14 @@ void run(const char* name, int ksteps)
 
 int main()
 {
-    run<0, 0, 256>("tf32  no-swizzle N=256", 3);
-    run<0, 1, 256>("tf32  128B-swizzle N=256", 3);
-    run<0, 0, 128>("tf32  no-swizzle N=128", 3);
-    run<0, 1, 128>("tf32  128B-swizzle N=128", 3);
-    run<1, 0, 256>("bf16  no-swizzle N=256", 3);
-    run<1, 1, 256>("bf16  128B-swizzle N=256", 3);
-    run<0, 0, 256>("tf32  no-swizzle N=256", 9);
-    run<0, 1, 256>("tf32  128B-swizzle N=256 (4 ksteps)", 4);
+    run<1, 0, 128>("bf16 SS no-swizzle N=128", 4);
+    run<1, 1, 128>("bf16 SS 128B-swizzle N=128", 4);
+    run<1, 0, 256>("bf16 SS no-swizzle N=256", 4);
+    run<1, 1, 256>("bf16 SS 128B-swizzle N=256", 4);
+    run<1, 0, 128, 1>("bf16 TS no-swizzle(B) N=128", 4);
+    run<1, 1, 128, 1>("bf16 TS 128B-swizzle(B) N=128", 4);
+    run<1, 0, 256, 1>("bf16 TS no-swizzle(B) N=256", 4);
+    run<1, 0, 64>("bf16 SS no-swizzle N=64", 4);
+    run<0, 0, 128>("tf32 SS no-swizzle N=128", 3);
     return 0;
 }
