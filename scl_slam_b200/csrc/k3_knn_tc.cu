@@ -11,11 +11,13 @@
 //      B row (key)   = [   k0  |   k1  |   k0  | n0 n1 n2 0.. ]   with |k|^2 = n0 + n1 + n2 exactly
 //   The dropped products (q0.k2, q1.k1, q2.k0) are bounded by 1.5 * 2^-16 |q||k|; the certificate below uses
 //   eps = 2^-15 (|q| + |k|max)^2, which leaves more than 5x room for the accumulation error of the tensor core.
-//   R = 20: 64 columns = 4 MMAs of K = 16 per 128x128 tile (the TF32x3 kernel this replaces needed 9 at half the rate).
+//   R = 20: 64 columns = 4 MMAs of K = 16 per 128x256 tile (the TF32x3 kernel this replaces needed 9 at half the rate).
+//   The MMA shape is M = 128, N = 256: measured (tools/mma_bench.cu) one cta_group::1 tcgen05.mma costs 93 cycles at any
+//   N <= 128 but 128 cycles at N = 256, i.e. only N = 256 runs the tensor pipe at its floor (M*N/256 cycles per K = 16).
 //
 // Key image (key_image_kernel). The B operand is computed ONCE per inserted key and kept in HBM in exactly the
-// shared-memory layout tcgen05 reads (K-major, no swizzle, 8x16-byte core matrices): one 128-key tile is one
-// contiguous block (16 KB at R = 20), so a tile is moved by a single cp.async.bulk (TMA) and no thread of the
+// shared-memory layout tcgen05 reads (K-major, no swizzle, 8x16-byte core matrices): one 256-key tile is one
+// contiguous block (32 KB at R = 20), so a tile is moved by a single cp.async.bulk (TMA) and no thread of the
 // query kernel ever touches a key.
 //
 // Query kernel (knn_tc_kernel). One CTA per SM owns 256 queries (two M = 128 accumulator sets) and one contiguous
@@ -26,17 +28,18 @@
 //     warps 4-11  epilogue   : thread = query = TMEM lane. tcgen05.ld 32 columns at a time, double buffered
 //                              (the next load is in flight while the current 32 scores are examined); the common
 //                              case is a FMNMX3 min-tree and one compare against the query's threshold
-//   TMEM: 2 stages x 2 query tiles x 128 FP32 columns = all 512 columns, handed around with mbarriers.
+//   TMEM: 2 query tiles x 256 FP32 columns = all 512 columns. The two query tiles are each other's double buffer:
+//   while the four epilogue warps of one drain its accumulator, the tensor pipe fills the other's.
 //
-// Thresholds. A thread keeps the K' = 16 best (score, key) of its (query, range) in registers and drops everything
-// at or above its threshold. The threshold is min(own K'-th best, union bound): every thread publishes the best
-// score of its range; for a query, the K'-th smallest of the C published range minima is backed by K' distinct keys,
-// so it bounds the global K'-th best score from above (pass fraction ~ 1.3 K'/n_seen_by_all_CTAs instead of
-// K'/n_seen_by_one). The service warps recompute that bound continuously for the CTA's share of the queries and
-// publish it in g_thr; epilogue threads read it once per tile. No bootstrap or sample pass is needed.
+// Thresholds. A thread drops every 8-key group whose best score is at or above its threshold and appends the others
+// (first key, group minimum: 8 bytes) to the hit queue of its (query, range) in global memory. The threshold is a union
+// bound: every thread publishes the best score of its range; for a query, the K'-th smallest of the published range
+// minima is backed by K' distinct keys, so it bounds the global K'-th best score from above. The service warps recompute
+// that bound continuously for the CTA's share of the queries; epilogue threads read it once per tile. No bootstrap or
+// sample pass is needed.
 //
-// Re-rank + certificate (knn_rerank_kernel). One warp per query: the proposals scoring at or below the query's cut
-// (the smallest final threshold of its ranges) are re-scored with the reference's exact float order (k3_knn.cu),
+// Re-rank + certificate (knn_rerank_kernel). One CTA per query: the keys of every queued group whose minimum is at or
+// below the query's cut (its final union bound) are re-scored with the reference's exact float order (k3_knn.cu),
 // the top-K by (d2, id) is selected, and the result is CERTIFIED: every key the prefilter dropped has score >= cut,
 // i.e. exact d2 > cut + |q|^2 - eps; if the K-th selected distance is below that, no dropped key can belong to (or
 // tie with) the top-K. Queries that fail are appended to a list and redone by the exact kernel.
@@ -53,19 +56,13 @@
 #include <cstdlib>
 #include <vector>
 
-#ifndef SCL_TC_NH
-#define SCL_TC_NH 128
-#endif
-
 namespace {
 
 constexpr int kKPrime = 16;        /* K': the number of distinct keys that back a query's threshold; K <= K' - 2 */
-constexpr int kQueueCap = 40;      /* hit queue per (query, range): groups of 12 words (first key, 3 pad, 8 scores); ~9 are used */
+constexpr int kQueueCap = 128;               /* hit queue per (query, range): entries of 2 words (first key of an 8-key group, its best score); ~12 are used; a tile adds at most 32 */
 constexpr int kEpiThreads = 256;   /* 8 epilogue warps: query tile = (warp-4)/4, TMEM lane quadrant = warp%4 */
 constexpr int kThreads = 384;
-constexpr int kNT = 128;           /* keys per tile (one TMA copy) */
-constexpr int kNH = SCL_TC_NH;    /* keys per accumulator slot (one MMA batch) */
-constexpr int kAccStages = 256 / kNH;   /* accumulator slots per query tile: stages x 2 query tiles x kNH columns = all 512 TMEM columns */
+constexpr int kNT = 256;           /* keys per tile: one TMA copy, one N = 256 accumulator per query tile */
 constexpr int kQPerCta = 256;
 constexpr int kNoThr = 0x7f7f7f7f; /* memset pattern of the slots: 3.39e38 = "nothing yet" */
 constexpr float kThrInit = 1.0e38f;
@@ -151,16 +148,19 @@ template <int R> struct TcCfg {
     static constexpr int KTOT = (3 * R + 3 + 15) / 16 * 16;   /* GEMM K: 64 at R = 20, 128 at R = 40 */
     static constexpr int CHUNKS = KTOT / 8;                   /* 16-byte K chunks per row */
     static constexpr int KSTEPS = KTOT / 16;                  /* tcgen05.mma instructions per 128x128 tile */
-    static constexpr uint32_t LBO = 128 * 16, SBO = 128;      /* both operands are 128 rows tall */
-    static constexpr uint32_t TILE_BYTES = 128 * KTOT * 2;    /* one operand tile: 16 KB / 32 KB */
-    static constexpr int NSTAGE = R <= 20 ? 8 : 4;            /* key tiles in flight in shared memory */
+    static constexpr uint32_t SBO = 128;                      /* 8-row core-matrix groups follow each other */
+    static constexpr uint32_t LBO_A = 128 * 16;               /* distance between 16-byte K chunks: rows x 16 B */
+    static constexpr uint32_t LBO_B = kNT * 16;
+    static constexpr uint32_t TILE_A = 128 * KTOT * 2;        /* one query tile: 16 KB / 32 KB */
+    static constexpr uint32_t TILE_B = kNT * KTOT * 2;        /* one key tile: 32 KB / 64 KB */
+    static constexpr int NSTAGE = R <= 20 ? 5 : 2;            /* key tiles in flight in shared memory */
     static constexpr uint32_t OFF_BAR = 0;                    /* mbarriers, tmem slot, flags */
     static constexpr uint32_t OFF_THR = 1024;                 /* [256] union bounds */
     static constexpr uint32_t OFF_A = 2048;                   /* two query tiles */
-    static constexpr uint32_t OFF_B = OFF_A + 2 * TILE_BYTES;
-    static constexpr uint32_t TOTAL = OFF_B + NSTAGE * TILE_BYTES;
-    /* D = F32, A = B = BF16, both K-major, N = kNH, M = 128 */
-    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kNH >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    static constexpr uint32_t OFF_B = OFF_A + 2 * TILE_A;
+    static constexpr uint32_t TOTAL = OFF_B + NSTAGE * TILE_B;
+    /* D = F32, A = B = BF16, both K-major, N = kNT, M = 128 */
+    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kNT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
 
 // value of GEMM column `idx` of the key row (B) / of the query row (A)
@@ -195,8 +195,8 @@ __global__ void __launch_bounds__(128) key_image_kernel(const float* __restrict_
     }
     const float n = __ldg(knorm + key);
     nn[0] = bf16_round(n); nn[1] = bf16_round(n - nn[0]); nn[2] = bf16_round(n - nn[0] - nn[1]);
-    const int row = key & 127;
-    unsigned char* dst = img + (size_t)(key >> 7) * C::TILE_BYTES + (uint32_t)(row >> 3) * C::SBO + (uint32_t)(row & 7) * 16;
+    const int row = key % kNT;
+    unsigned char* dst = img + (size_t)(key / kNT) * C::TILE_B + (uint32_t)(row >> 3) * C::SBO + (uint32_t)(row & 7) * 16;
 #pragma unroll
     for (int c = 0; c < C::CHUNKS; c++) {
         uint4 v;
@@ -204,22 +204,20 @@ __global__ void __launch_bounds__(128) key_image_kernel(const float* __restrict_
         v.y = pack_bf16x2(b_column<R>(k0, k1, nn, 8 * c + 2), b_column<R>(k0, k1, nn, 8 * c + 3));
         v.z = pack_bf16x2(b_column<R>(k0, k1, nn, 8 * c + 4), b_column<R>(k0, k1, nn, 8 * c + 5));
         v.w = pack_bf16x2(b_column<R>(k0, k1, nn, 8 * c + 6), b_column<R>(k0, k1, nn, 8 * c + 7));
-        *reinterpret_cast<uint4*>(dst + (uint32_t)c * C::LBO) = v;
+        *reinterpret_cast<uint4*>(dst + (uint32_t)c * C::LBO_B) = v;
     }
 }
 
 // A full hit queue is re-filtered with the threshold of the moment: groups queued under an earlier, looser bound whose
-// 8 scores have all risen to or above it can be dropped like any other key (they are >= the final cut). Rare, and kept
+// best score has risen to or above it can be dropped like any other key (they are >= the final cut). Rare, and kept
 // out of line so that the epilogue loop stays small.
-__device__ __noinline__ int compact_queue(uint4* q, int n, float thr)
+__device__ __noinline__ int compact_queue(uint2* q, int n, float thr)
 {
     int w = 0;
     for (int e = 0; e < n; e++) {
-        const uint4 k4 = __ldcg(q + 3 * e), a4 = __ldcg(q + 3 * e + 1), b4 = __ldcg(q + 3 * e + 2);
-        const float m = fminf(fminf(fminf(__uint_as_float(a4.x), __uint_as_float(a4.y)), fminf(__uint_as_float(a4.z), __uint_as_float(a4.w))),
-                              fminf(fminf(__uint_as_float(b4.x), __uint_as_float(b4.y)), fminf(__uint_as_float(b4.z), __uint_as_float(b4.w))));
-        if (m < thr) {
-            if (w != e) { __stcg(q + 3 * w, k4); __stcg(q + 3 * w + 1, a4); __stcg(q + 3 * w + 2, b4); }
+        const uint2 v = __ldcg(q + e);
+        if (__uint_as_float(v.y) < thr) {
+            if (w != e) __stcg(q + w, v);
             w++;
         }
     }
@@ -232,15 +230,15 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     const float* __restrict__ qkeys, int Q, const unsigned char* __restrict__ img, int key_hi, int n_ranges,
     long long* __restrict__ times /* null, or [grid][16] developer counters (SCL_TC_TIMES=1) */,
     int* __restrict__ slots /* [Q][K'] range minima by range % K' (ordered-int image) */,
-    uint32_t* __restrict__ hq /* [Q][n_ranges][kQueueCap][12] hit queues */, int* __restrict__ hq_cnt /* [Q][n_ranges] */,
-    int* __restrict__ dbg /* null, or developer counters */)
+    uint2* __restrict__ hq /* [Q][n_ranges][kQueueCap] hit queues: (first key of the group, its best score) */, int* __restrict__ hq_cnt /* [Q][n_ranges] */,
+    int* __restrict__ dbg /* null, or developer counters */, int dev_flags /* SCL_TC_FLAGS: timing experiments, results are then wrong */)
 {
     using C = TcCfg<R>;
     constexpr int NS = C::NSTAGE;
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-    uint64_t *full = bars, *empty = bars + NS, *tfull = bars + 2 * NS, *tempty = bars + 2 * NS + 2 * kAccStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 4 * kAccStages);
+    uint64_t *full = bars, *empty = bars + NS, *tfull = bars + 2 * NS, *tempty = bars + 2 * NS + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 4);
     volatile int* epi_done = reinterpret_cast<volatile int*>(tmem_slot + 1);
     volatile int* sthr = reinterpret_cast<volatile int*>(smem + C::OFF_THR);          /* [256] union bounds of the CTA's queries */
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -256,12 +254,12 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     // ---- one-time setup -----------------------------------------------------------------------
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; s++) { scl_mbar_init(&full[s], 1); scl_mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2 * kAccStages; s++) { scl_mbar_init(&tfull[s], 1); scl_mbar_init(&tempty[s], 4); }
+        for (int s = 0; s < 2; s++) { scl_mbar_init(&tfull[s], 1); scl_mbar_init(&tempty[s], 4); }
         *epi_done = 0;
         scl_mbar_fence_init();
     }
     if (threadIdx.x < kQPerCta) sthr[threadIdx.x] = kNoThr;
-    if (warp == 0) {   /* TMEM: 2 stages x 2 query tiles x 128 fp32 columns */
+    if (warp == 0) {   /* TMEM: 2 query tiles x 256 fp32 columns */
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(scl_smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -284,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         }
         const float one = qi < Q ? 1.0f : 0.0f;
         const int r = m & 127;
-        unsigned char* dst = smem + C::OFF_A + (uint32_t)(m >> 7) * C::TILE_BYTES + (uint32_t)(r >> 3) * C::SBO + (uint32_t)(r & 7) * 16;
+        unsigned char* dst = smem + C::OFF_A + (uint32_t)(m >> 7) * C::TILE_A + (uint32_t)(r >> 3) * C::SBO + (uint32_t)(r & 7) * 16;
 #pragma unroll
         for (int c = 0; c < C::CHUNKS; c++) {
             float v[8];
@@ -294,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                 v[j] = idx < R ? a0[idx < R ? idx : 0] : idx < 2 * R ? a0[idx < 2 * R && idx >= R ? idx - R : 0]
                      : idx < 3 * R ? a1[idx < 3 * R && idx >= 2 * R ? idx - 2 * R : 0] : idx < 3 * R + 3 ? one : 0.0f;
             }
-            *reinterpret_cast<uint4*>(dst + (uint32_t)c * C::LBO) =
+            *reinterpret_cast<uint4*>(dst + (uint32_t)c * C::LBO_A) =
                 make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
     }
@@ -310,18 +308,23 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         const int row = (warp & 3) * 32 + lane;         /* TMEM lane */
         const int qi = q_base + qt * 128 + row;
         const bool live = qi < Q;
-        int n_hit = 0;                                  /* 8-column groups queued by this thread */
+        int n_hit = 0;                                  /* 8-key groups queued by this thread */
         int n_slow = 0;                                 /* developer counter (SCL_TC_TIMES) */
-        float thr = live ? kThrInit : -kThrInit;        /* rows beyond Q never queue anything */
+        float thr = (live && !(dev_flags & 1)) ? kThrInit : -kThrInit;        /* rows beyond Q never queue anything */
         float published = kThrInit;
         int* my_slot = slots + (size_t)(live ? qi : 0) * kKPrime + (range % kKPrime);
         volatile int* my_sthr = sthr + qt * 128 + row;
-        uint4* my_q = reinterpret_cast<uint4*>(hq + ((size_t)(live ? qi : 0) * n_ranges + range) * (size_t)(kQueueCap * 12));
-        // The epilogue warps are coupled through the accumulator hand-off (a slot is refilled only when all four warps of
-        // its query tile have drained it), so whatever a warp does on a hit sits on the critical path of the whole CTA.
-        // A hit therefore only APPENDS the 8-column group (its first key and its 8 scores: three 16-byte stores) to the
-        // (query, range) queue in global memory; the re-rank kernel sorts it out. 32 scores cost a FMNMX3 tree and a vote.
-        auto examine = [&](uint32_t (&r)[32], int key_first) {
+        uint2* my_q = hq + ((size_t)(live ? qi : 0) * n_ranges + range) * (size_t)kQueueCap;
+        // The four epilogue warps of a query tile are coupled through the accumulator hand-off (it is refilled only when all
+        // four have drained it), so the per-chunk code sits on the critical path of the whole CTA. It is BRANCH-FREE on purpose:
+        // ptxas only hoists a tcgen05.ld above the min-tree of the previous chunk when both are in one basic block (with a
+        // branch per chunk it sank every load to the end of its block, right in front of its consumers: 220 cycles per chunk
+        // instead of 60). 18 FMNMX(3) per 32 scores; a hit APPENDS (first key, group minimum) of the 8-key groups below the
+        // threshold to the (query, range) queue in global memory with predicated stores; the re-rank kernel re-scores those
+        // keys exactly. The queue has room for two tiles' worth of groups and is compacted between tiles when half full.
+        float tile_min = kThrInit;
+        bool overflowed = false;
+        auto examine = [&](const uint32_t (&r)[32], int key_first) {
             float g[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -331,42 +334,31 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                 g[j] = fminf(fmin3(fmin3(x0, x1, x2), fmin3(x3, x4, x5), x6), x7);
             }
             const float m = fminf(fmin3(g[0], g[1], g[2]), g[3]);
-            if (__any_sync(0xffffffffu, m < thr)) {     /* one chunk in ten */
-                n_slow++;
+            if (TIMES && __any_sync(0xffffffffu, m < thr)) n_slow++;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (g[j] < thr) {                    /* divergent: usually one lane, one group */
-                        if (n_hit == kQueueCap) n_hit = compact_queue(my_q, kQueueCap, thr);
-                        if (n_hit < kQueueCap) {
-                            uint4* q = my_q + n_hit * 3;
-                            __stcg(q + 0, make_uint4((uint32_t)(key_first + 8 * j), 0u, 0u, 0u));
-                            __stcg(q + 1, make_uint4(r[8 * j + 0], r[8 * j + 1], r[8 * j + 2], r[8 * j + 3]));
-                            __stcg(q + 2, make_uint4(r[8 * j + 4], r[8 * j + 5], r[8 * j + 6], r[8 * j + 7]));
-                        }
-                        n_hit++;                         /* beyond the capacity: counted, the query is then redone exactly */
-                    }
-                }
-                /* a new range minimum feeds the union bound at once */
-                if (live && m < published && key_first + 32 <= key_hi) { published = m; atomicMin(my_slot, ordered_int(m)); }
+            for (int j = 0; j < 4; j++) {
+                const bool hj = g[j] < thr;
+                if (hj) __stcg(my_q + n_hit, make_uint2((uint32_t)(key_first + 8 * j), __float_as_uint(g[j])));
+                n_hit += hj ? 1 : 0;
             }
+            tile_min = fminf(tile_min, m);
         };
-        long long tw = 0, c0 = 0, t_ld = 0, t_ex = 0;
+        long long tw = 0, c0 = 0, t_first = 0, t_body = 0, t_tail = 0, q0 = 0;
         if (TIMES) c0 = clock64();
-        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(qt * kNH);
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(qt * kNT);
         uint32_t va[32], vb[32];
-        const int n_it = (kNT / kNH) * n_tiles;             /* accumulator slots to drain */
-        float next_thr = thr;                               /* the service warps' bound, read one slot ahead of its use */
+        float next_thr = thr;                               /* the service warps' bound, read one tile ahead of its use */
         if (n_tiles > 0) {
-            /* Start-up: with no threshold yet, every score of the first tile would be a hit. Instead the first 128 keys are
+            /* Start-up: with no threshold yet, every score of the first tile would be a hit. Instead the first tile is
              * read twice: a first pass only finds the range minimum so far and publishes it; as soon as K' ranges have done
              * so the service warps deliver a union bound (a few microseconds), and the normal pass starts with it. */
-            if (n_service >= kKPrime && (range + 1) * kNT <= key_hi) {
+            scl_mbar_wait(&tfull[qt], 0);
+            tc_fence_after();
+            if (n_service >= kKPrime && (range + 1) * kNT <= key_hi && !(dev_flags & 2)) {
                 float m0 = kThrInit;
 #pragma unroll 1
                 for (int c = 0; c < kNT / 32; c++) {
-                    const int sl = (c * 32) / kNH, cc = (c * 32) % kNH;     /* slot, column within the slot */
-                    if (cc == 0) { scl_mbar_wait(&tfull[sl * 2 + qt], 0); tc_fence_after(); }
-                    tmem_ld32_issue(lane_base + (uint32_t)(sl * 2 * kNH + cc), va);
+                    tmem_ld32_issue(lane_base + (uint32_t)(c * 32), va);
                     tmem_wait32(va);
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) m0 = fmin3(m0, __uint_as_float(va[j]), __uint_as_float(va[j + 1]));
@@ -379,69 +371,55 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                     if (clock64() - w0 > 40000) { if (dbg && lane == 0) atomicAdd(dbg + 5, 1); break; }
                     __nanosleep(100);
                 }
-            } else {
-                scl_mbar_wait(&tfull[qt], 0);
-                tc_fence_after();
             }
             if (live) next_thr = fminf(next_thr, ordered_float(*my_sthr));
-            tmem_ld32_issue(lane_base, va);
         }
-        // One accumulator slot (kNH keys) per iteration, as pairs of 32-column chunks (va, vb). The load of the next chunk is
-        // always in flight while the current one is examined; the slot is handed back as soon as its last chunk is in registers.
+        // One accumulator (kNT keys of this query tile) per iteration, as eight 32-column chunks alternating between va and vb:
+        // the load of the next chunk is in flight while the current one is examined, and the accumulator is handed back to the
+        // MMA issuer as soon as its last chunk is in registers.
 #pragma unroll 1
-        for (int it = 0; it < n_it; it++) {
-            const int s = it % kAccStages;
-            const int key0 = (range + (it / (kNT / kNH)) * n_ranges) * kNT + (it % (kNT / kNH)) * kNH;
-            const uint32_t col0 = lane_base + (uint32_t)(s * 2 * kNH);
-            thr = fminf(thr, next_thr);
-            long long p0 = 0;
-#pragma unroll
-            for (int pr = 0; pr < kNH / 64; pr++) {
+        for (int it = 0; it < n_tiles; it++) {
+            const int key0 = (range + it * n_ranges) * kNT;
+            if (it > 0) {
+                long long p0 = 0;
                 if (TIMES) p0 = clock64();
+                scl_mbar_wait(&tfull[qt], (uint32_t)(it & 1));
+                if (TIMES) tw += clock64() - p0;
+                tc_fence_after();
+            }
+            thr = fminf(thr, next_thr);
+            tile_min = kThrInit;
+            if (TIMES) q0 = clock64();
+            tmem_ld32_issue(lane_base, va);
+#pragma unroll
+            for (int c = 0; c < kNT / 32; c += 2) {
                 tmem_wait32(va);
-                if (TIMES) { const long long p1 = clock64(); t_ld += p1 - p0; p0 = p1; }
-                tmem_ld32_issue(col0 + 64 * pr + 32, vb);
-                examine(va, key0 + 64 * pr);
-                if (TIMES) { const long long p1 = clock64(); t_ex += p1 - p0; p0 = p1; }
+                if (TIMES && c == 0) { const long long q1 = clock64(); t_first += q1 - q0; q0 = q1; }
+                tmem_ld32_issue(lane_base + (uint32_t)(32 * c + 32), vb);
+                examine(va, key0 + 32 * c);
                 tmem_wait32(vb);
-                if (TIMES) { const long long p1 = clock64(); t_ld += p1 - p0; p0 = p1; }
-                if (pr + 1 < kNH / 64) {
-                    tmem_ld32_issue(col0 + 64 * pr + 64, va);
-                    if (TIMES) p0 = clock64();
-                    examine(vb, key0 + 64 * pr + 32);
-                    if (TIMES) t_ex += clock64() - p0;
+                if (c + 2 < kNT / 32) tmem_ld32_issue(lane_base + (uint32_t)(32 * c + 64), va);
+                else {
+                    /* every score of this accumulator is in registers: hand it back to the MMA issuer */
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[qt]);
                 }
+                examine(vb, key0 + 32 * c + 32);
+            }
+            if (TIMES) { const long long q1 = clock64(); t_body += q1 - q0; q0 = q1; }
+            /* a new range minimum feeds the union bound (tiles wholly below key_hi only; thr is -inf for rows beyond Q) */
+            if (key0 + kNT <= key_hi && tile_min < fminf(thr, published)) { published = tile_min; atomicMin(my_slot, ordered_int(tile_min)); }
+            if (n_hit > kQueueCap - kNT / 8) {           /* no room for another tile's worth of groups: compact (rare) */
+                n_hit = compact_queue(my_q, n_hit, thr);
+                if (n_hit > kQueueCap - kNT / 8) { overflowed = true; n_hit = 0; thr = -kThrInit; }   /* sticky: nothing more is queued, the query is redone exactly */
             }
             if (live) next_thr = ordered_float(*my_sthr);
-            /* every score of this slot is in registers: hand it back to the MMA issuer now */
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[s * 2 + qt]);
-            bool pending = false;                        /* va still has to be loaded for the next iteration */
-            const int s1 = (it + 1) % kAccStages; const uint32_t ph1 = ((it + 1) / kAccStages) & 1;
-            if (it + 1 < n_it) {
-                /* next slot already complete? then start its first load before examining the last 32 scores */
-                if (__all_sync(0xffffffffu, mbar_test(&tfull[s1 * 2 + qt], ph1))) {
-                    tc_fence_after();
-                    tmem_ld32_issue(lane_base + (uint32_t)(s1 * 2 * kNH), va);
-                } else {
-                    pending = true;
-                }
-            }
-            if (TIMES) p0 = clock64();
-            examine(vb, key0 + kNH - 32);
-            if (TIMES) t_ex += clock64() - p0;
-            if (pending) {
-                long long w0 = 0;
-                if (TIMES) w0 = clock64();
-                scl_mbar_wait(&tfull[s1 * 2 + qt], ph1);
-                if (TIMES) tw += clock64() - w0;
-                tc_fence_after();
-                tmem_ld32_issue(lane_base + (uint32_t)(s1 * 2 * kNH), va);
-            }
+            if (TIMES) t_tail += clock64() - q0;
         }
+        if (overflowed) n_hit = kQueueCap + 1;
         if (TIMES) {
-            const int wp = __reduce_add_sync(0xffffffffu, n_hit), wmax = __reduce_max_sync(0xffffffffu, n_hit);
+            const int wp = __reduce_add_sync(0xffffffffu, min(n_hit, kQueueCap)), wmax = __reduce_max_sync(0xffffffffu, n_hit);
             if (lane == 0) {
                 long long* o = times + (size_t)blockIdx.x * 16;
                 atomicAdd(reinterpret_cast<unsigned long long*>(o + 0), (unsigned long long)tw);
@@ -449,8 +427,9 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                 atomicAdd(reinterpret_cast<unsigned long long*>(o + 2), (unsigned long long)n_slow);
                 atomicAdd(reinterpret_cast<unsigned long long*>(o + 3), (unsigned long long)wp);
                 atomicMax(reinterpret_cast<unsigned long long*>(o + 4), (unsigned long long)wmax);
-                atomicAdd(reinterpret_cast<unsigned long long*>(o + 9), (unsigned long long)t_ld);
-                atomicAdd(reinterpret_cast<unsigned long long*>(o + 10), (unsigned long long)t_ex);
+                atomicAdd(reinterpret_cast<unsigned long long*>(o + 9), (unsigned long long)t_first);
+                atomicAdd(reinterpret_cast<unsigned long long*>(o + 10), (unsigned long long)t_body);
+                atomicAdd(reinterpret_cast<unsigned long long*>(o + 11), (unsigned long long)t_tail);
             }
         }
         /* Everything this thread did NOT queue scored >= the threshold in force at the time >= the maximum the query's slots
@@ -465,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         // scores of K' DISTINCT keys (different ranges), so their maximum bounds the query's K'-th best score from above.
         // Each lane refreshes four queries: 64 bytes from L2 and 15 max operations per query, a microsecond per sweep.
         int sweeps = 0;
-        while (n_tiles > 0) {
+        while (n_tiles > 0 && !(dev_flags & 2)) {
             const bool last = *epi_done >= 8;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
@@ -487,13 +466,13 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     } else if (warp == 1) {
         // ===== TMA issuer: one thread, one bulk copy per key tile =======================================
         if (lane == 0) {
-            const unsigned char* src = img + (size_t)range * C::TILE_BYTES;
-            const size_t step = (size_t)n_ranges * C::TILE_BYTES;
+            const unsigned char* src = img + (size_t)range * C::TILE_B;
+            const size_t step = (size_t)n_ranges * C::TILE_B;
             for (int tile = 0; tile < n_tiles; tile++) {
                 const int b = tile % NS; const uint32_t ph = (tile / NS) & 1;
                 scl_mbar_wait(&empty[b], ph ^ 1u);
-                scl_mbar_expect_tx(&full[b], C::TILE_BYTES);
-                scl_bulk_g2s(smem + C::OFF_B + (uint32_t)b * C::TILE_BYTES, src + (size_t)tile * step, C::TILE_BYTES, &full[b]);
+                scl_mbar_expect_tx(&full[b], C::TILE_B);
+                scl_bulk_g2s(smem + C::OFF_B + (uint32_t)b * C::TILE_B, src + (size_t)tile * step, C::TILE_B, &full[b]);
             }
         }
         __syncwarp();
@@ -502,27 +481,24 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         if (lane == 0) {
             const uint32_t a_base = scl_smem_u32(smem + C::OFF_A), b_base = scl_smem_u32(smem + C::OFF_B);
             long long t_te = 0, t_fu = 0, c0 = 0;
-            constexpr int SPT = kNT / kNH;                          /* accumulator slots per key tile */
-            for (int it = 0; it < SPT * n_tiles; it++) {
-                const int tile = it / SPT, hf = it % SPT;           /* kNH keys of a key tile -> one accumulator slot per query tile */
-                const int b = tile % NS; const uint32_t bph = (tile / NS) & 1;
-                const int s = it % kAccStages; const uint32_t ph = (it / kAccStages) & 1;
+            for (int it = 0; it < n_tiles; it++) {
+                const int b = it % NS; const uint32_t bph = (it / NS) & 1;
                 if (TIMES) c0 = clock64();
-                if (hf == 0) scl_mbar_wait(&full[b], bph);          /* key tile landed */
+                scl_mbar_wait(&full[b], bph);                       /* key tile landed */
                 if (TIMES) { const long long c1 = clock64(); t_fu += c1 - c0; c0 = c1; }
-                const uint32_t bs = b_base + (uint32_t)b * C::TILE_BYTES + (uint32_t)hf * (kNH / 8) * C::SBO;   /* rows 64*hf.. of the tile */
+                const uint32_t bs = b_base + (uint32_t)b * C::TILE_B;
 #pragma unroll
                 for (int qt = 0; qt < 2; qt++) {
-                    scl_mbar_wait(&tempty[s * 2 + qt], ph ^ 1u);    /* slot drained by its four epilogue warps */
+                    scl_mbar_wait(&tempty[qt], (uint32_t)((it & 1) ^ 1));      /* accumulator drained by its four epilogue warps */
                     tc_fence_after();
-                    const uint32_t d = tmem_base + (uint32_t)((s * 2 + qt) * kNH);
-                    const uint32_t as = a_base + (uint32_t)qt * C::TILE_BYTES;
+                    const uint32_t d = tmem_base + (uint32_t)(qt * kNT);
+                    const uint32_t as = a_base + (uint32_t)qt * C::TILE_A;
 #pragma unroll
                     for (int k = 0; k < C::KSTEPS; k++)
-                        tc_mma_bf16(d, make_desc(as + 2 * k * C::LBO, C::LBO, C::SBO), make_desc(bs + 2 * k * C::LBO, C::LBO, C::SBO), C::IDESC, k > 0 ? 1u : 0u);
-                    tc_commit(&tfull[s * 2 + qt]);                  /* slot ready for the epilogue */
+                        if (!(dev_flags & 4)) tc_mma_bf16(d, make_desc(as + 2 * k * C::LBO_A, C::LBO_A, C::SBO), make_desc(bs + 2 * k * C::LBO_B, C::LBO_B, C::SBO), C::IDESC, k > 0 ? 1u : 0u);
+                    tc_commit(&tfull[qt]);                          /* accumulator ready for the epilogue */
                 }
-                if (hf == SPT - 1) tc_commit(&empty[b]);                  /* key tile reusable once these MMAs retire */
+                tc_commit(&empty[b]);                               /* key tile reusable once these MMAs retire */
                 if (TIMES) { const long long c1 = clock64(); t_te += c1 - c0; }
             }
             if (TIMES) { times[(size_t)blockIdx.x * 16 + 6] = t_fu; times[(size_t)blockIdx.x * 16 + 7] = t_te; times[(size_t)blockIdx.x * 16 + 8] = n_tiles; }
@@ -556,34 +532,36 @@ __device__ __forceinline__ float exact_d2(const float* __restrict__ q, const flo
 }
 
 // Phase B: exact re-rank + certificate. One CTA of 128 threads per query: the hit queues of all ranges are flattened
-// (counts -> prefix sums in shared memory) so that every thread reads a few independent groups, the survivors (scores at
-// or below the cut) are re-scored exactly, and warp 0 selects the top-K and certifies it.
-constexpr int kMaxSurvivors = 256;
+// (counts -> prefix sums in shared memory) so that every thread reads a few independent entries; the 8 keys of every
+// surviving group (best score at or below the cut) are re-scored exactly, and warp 0 selects the top-K and certifies it.
+constexpr int kMaxGroups = 256;                         /* surviving groups per query (about 3 K' are expected: the cut is the LARGEST of K' slot minima) */
 constexpr int kMaxRanges = 160;
+constexpr int kMaxSel = 512;                            /* keys entering the top-K selection */
 template <int METRIC>
 __global__ void __launch_bounds__(128) knn_rerank_kernel(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys, int R, int K,
-                                                          int n_ranges, int n_db, const uint32_t* __restrict__ hq, const int* __restrict__ hq_cnt,
+                                                          int n_ranges, int n_db, const uint2* __restrict__ hq, const int* __restrict__ hq_cnt,
                                                           const int* __restrict__ slots, const float* __restrict__ kn2max, int id_mul, int id_add,
                                                           int32_t* __restrict__ out_ids, float* __restrict__ out_d2, int q_off,
                                                           int32_t* __restrict__ fail_list, int* __restrict__ fail_count, float* __restrict__ err_probe)
 {
-    __shared__ int s_id[kMaxSurvivors];
-    __shared__ float s_d[kMaxSurvivors];
-    __shared__ float s_s[kMaxSurvivors];
+    __shared__ int s_key[kMaxGroups];                   /* first key of the group */
+    __shared__ float s_g[kMaxGroups];                   /* its best prefilter score */
+    __shared__ float s_d[kMaxSel];                      /* exact distances / ids of the keys that can still make the top-K */
+    __shared__ int s_id[kMaxSel];
     __shared__ int s_pre[kMaxRanges + 1];
     __shared__ float s_q[64];
-    __shared__ int s_count, s_overflow;
+    __shared__ int s_count, s_overflow, s_nsel;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int qi = blockIdx.x;
     const float* q = qkeys + (size_t)qi * R;
     const float inf = __int_as_float(0x7f800000);
-    /* The cut: the query's final union bound (the maximum of its K' slots). Everything that was not queued scored >= it,
-     * so every key scoring below it is in a queue; queued keys above it cannot be certified anyway and are skipped:
-     * about K' survive. */
+    /* The cut: the query's final union bound (the maximum of its K' slots). Every group that was not queued had all its
+     * scores >= it, so every key scoring below it sits in a queued group; queued groups whose best score is above it
+     * cannot be certified anyway and are skipped: about K' groups survive. */
     int gt = lane < kKPrime ? __ldg(slots + (size_t)qi * kKPrime + lane) : (int)0x80000000;
     gt = __reduce_max_sync(0xffffffffu, gt);
     const float cut = gt < 0x7f000000 ? ordered_float(gt) : inf;
-    if (t == 0) { s_count = 0; s_overflow = 0; }
+    if (t == 0) { s_count = 0; s_overflow = 0; s_nsel = 0; }
     if (t < R) s_q[t] = __ldg(q + t);
     for (int r = t; r < n_ranges; r += 128) {
         int c = __ldg(hq_cnt + (size_t)qi * n_ranges + r);
@@ -606,36 +584,39 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(const float* __restrict
     __syncthreads();
     const int total = s_pre[n_ranges];
     for (int g = t; g < total; g += 128) {
-        int lo = 0, hi = n_ranges;                      /* the range that holds group g: last r with s_pre[r] <= g */
+        int lo = 0, hi = n_ranges;                      /* the range that holds entry g: last r with s_pre[r] <= g */
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_pre[mid] <= g) lo = mid; else hi = mid; }
-        const uint4* gp = reinterpret_cast<const uint4*>(hq + ((size_t)qi * n_ranges + lo) * (size_t)(kQueueCap * 12)) + 3 * (g - s_pre[lo]);
-        const uint4 k4 = __ldcg(gp), a4 = __ldcg(gp + 1), b4 = __ldcg(gp + 2);
-        const float sc[8] = {__uint_as_float(a4.x), __uint_as_float(a4.y), __uint_as_float(a4.z), __uint_as_float(a4.w),
-                             __uint_as_float(b4.x), __uint_as_float(b4.y), __uint_as_float(b4.z), __uint_as_float(b4.w)};
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int id = (int)k4.x + i;
-            if (sc[i] <= cut && id < n_db) {
-                const int pos = atomicAdd(&s_count, 1);
-                if (pos < kMaxSurvivors) { s_id[pos] = id; s_s[pos] = sc[i]; }
-            }
+        const uint2 e = __ldcg(hq + ((size_t)qi * n_ranges + lo) * (size_t)kQueueCap + (g - s_pre[lo]));
+        const float gm = __uint_as_float(e.y);
+        if (gm <= cut && (int)e.x < n_db) {
+            const int pos = atomicAdd(&s_count, 1);
+            if (pos < kMaxGroups) { s_key[pos] = (int)e.x; s_g[pos] = gm; }
         }
     }
     __syncthreads();
     bool overflow = s_overflow != 0;
-    int n_surv = s_count;
-    if (n_surv > kMaxSurvivors) { overflow = true; n_surv = kMaxSurvivors; }
+    int n_grp = s_count;
+    if (n_grp > kMaxGroups) { overflow = true; n_grp = kMaxGroups; }
     float qn = 0.0f;
     for (int d = 0; d < R; d++) qn = fmaf(s_q[d], s_q[d], qn);
     const float sn = sqrtf(qn) + sqrtf(__ldg(kn2max));
     const float eps0 = 3.0517578125e-05f * sn * sn;                 /* 2^-15 (|q| + |k|max)^2 */
+    /* a certified top-K lies wholly below cut + |q|^2 (see below): keys at or above it need not enter the selection */
+    const float d_lim = cut < inf ? cut + qn : inf;
     float worst_err = 0.0f;
-    for (int c = t; c < n_surv; c += 128) {
-        float d = exact_d2<METRIC>(s_q, keys + (size_t)s_id[c] * R, R);
-        if (err_probe) worst_err = fmaxf(worst_err, fabsf((d - qn) - s_s[c]) / eps0);
-        if (METRIC == 1 && !(d > FLT_EPSILON)) d = inf;          /* libnabo self-match rule */
-        if (!(d < (METRIC == 0 ? FLT_MAX : inf))) d = inf;       /* never accepted by the trees */
-        s_d[c] = d;
+    for (int c = t; c < n_grp * 8; c += 128) {
+        const int id = s_key[c >> 3] + (c & 7);
+        if (id < n_db) {
+            float d = exact_d2<METRIC>(s_q, keys + (size_t)id * R, R);
+            /* the prefilter must not have OVER-estimated a key by more than eps (that is what the certificate relies on) */
+            if (err_probe) worst_err = fmaxf(worst_err, (s_g[c >> 3] - (d - qn)) / eps0);
+            if (METRIC == 1 && !(d > FLT_EPSILON)) d = inf;          /* libnabo self-match rule */
+            if (!(d < (METRIC == 0 ? FLT_MAX : inf))) d = inf;       /* never accepted by the trees */
+            if (d < d_lim) {
+                const int pos = atomicAdd(&s_nsel, 1);
+                if (pos < kMaxSel) { s_d[pos] = d; s_id[pos] = id * id_mul + id_add; }
+            }
+        }
     }
     if (err_probe) {
 #pragma unroll
@@ -644,14 +625,15 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(const float* __restrict
     }
     __syncthreads();
     if (warp != 0) return;
+    int n_surv = s_nsel;
+    if (n_surv > kMaxSel) { overflow = true; n_surv = kMaxSel; }
     /* K rounds: smallest (d2, id) strictly after the previous pick */
     float pd = -1.0f; int pi = -1; float dK = 0.0f; int found = 0;
     for (int r = 0; r < K; r++) {
         float bd = inf; int bi = 0x7fffffff;
         for (int c = lane; c < n_surv; c += 32) {
             const float d = s_d[c];
-            if (!(d < inf)) continue;
-            const int id = s_id[c] * id_mul + id_add;
+            const int id = s_id[c];
             if (d < pd || (d == pd && id <= pi)) continue;
             if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; }
         }
@@ -679,7 +661,7 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(const float* __restrict
             if (overflow) atomicAdd(why + 0, 1);
             else if (found != K) atomicAdd(why + 1, 1);
             else atomicAdd(why + 2, 1);
-            if (n_surv >= kMaxSurvivors) atomicAdd(why + 3, 1);
+            if (n_grp >= kMaxGroups) atomicAdd(why + 3, 1);
         }
     }
 }
@@ -696,11 +678,11 @@ int scl_knn_tc_ranges(int Q)
 }
 int scl_knn_tc_max_batch() { return 1024; }          /* larger batches are cut into launches of this many queries */
 int scl_knn_tc_kprime() { return kKPrime; }
-size_t scl_knn_tc_queue_bytes() { return (size_t)kQueueCap * 12 * 4; }      /* per (query, range) */
+size_t scl_knn_tc_queue_bytes() { return (size_t)kQueueCap * 8; }           /* per (query, range) */
 size_t scl_knn_tc_image_bytes(int R, int n_keys)
 {
     const size_t tiles = ((size_t)n_keys + kNT - 1) / kNT;
-    return tiles * (R == 20 ? TcCfg<20>::TILE_BYTES : TcCfg<40>::TILE_BYTES);
+    return tiles * (R == 20 ? TcCfg<20>::TILE_B : TcCfg<40>::TILE_B);
 }
 
 cudaError_t scl_launch_key_image(const float* keys, const float* knorm, int k_lo, int k_hi, int R, unsigned char* img, cudaStream_t stream)
@@ -715,7 +697,7 @@ cudaError_t scl_launch_key_image(const float* keys, const float* knorm, int k_lo
 
 template <int R>
 static cudaError_t launch_tc(const float* qkeys, int Q, const unsigned char* img, int n_db, int n_ranges, int* slots,
-                              uint32_t* hq, int* hq_cnt, int* dbg, cudaStream_t stream)
+                              uint2* hq, int* hq_cnt, int* dbg, cudaStream_t stream)
 {
     using C = TcCfg<R>;
     static bool attr = false;
@@ -728,10 +710,11 @@ static cudaError_t launch_tc(const float* qkeys, int Q, const unsigned char* img
     const int groups = (Q + kQPerCta - 1) / kQPerCta;
     long long* times = nullptr;
     const bool want_times = getenv("SCL_TC_TIMES") != nullptr;       /* developer aid: per-role cycle counters on stderr */
+    const int dev_flags = getenv("SCL_TC_FLAGS") ? atoi(getenv("SCL_TC_FLAGS")) : 0;
     const int nb = groups * n_ranges;
     if (want_times) { cudaMalloc(&times, (size_t)nb * 16 * sizeof(long long)); cudaMemsetAsync(times, 0, (size_t)nb * 128, stream); }
-    if (want_times) knn_tc_kernel<R, true><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, times, slots, hq, hq_cnt, dbg);
-    else knn_tc_kernel<R, false><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, nullptr, slots, hq, hq_cnt, dbg);
+    if (want_times) knn_tc_kernel<R, true><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, times, slots, hq, hq_cnt, dbg, dev_flags);
+    else knn_tc_kernel<R, false><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, nullptr, slots, hq, hq_cnt, dbg, dev_flags);
     if (want_times) {
         std::vector<long long> h((size_t)nb * 16);
         cudaStreamSynchronize(stream);
@@ -739,9 +722,9 @@ static cudaError_t launch_tc(const float* qkeys, int Q, const unsigned char* img
         double a[16] = {0}, amax4 = 0;
         for (int b = 0; b < nb; b++) for (int i = 0; i < 16; i++) a[i] += (double)h[(size_t)b * 16 + i] / nb;
         for (int b = 0; b < nb; b++) if ((double)h[(size_t)b * 16 + 4] > amax4) amax4 = (double)h[(size_t)b * 16 + 4];
-        fprintf(stderr, "[tc n_db %d] tiles/CTA %.0f | per tile, per epilogue warp: total %.0f cycles, waiting for the accumulator %.0f, in tcgen05.wait::ld %.0f, examining %.0f | slow 32-col chunks per warp %.0f of %.0f, "
+        fprintf(stderr, "[tc n_db %d] tiles/CTA %.0f | per tile, per epilogue warp: total %.0f cycles, waiting for the accumulator %.0f, first chunk %.0f, other seven %.0f, tail %.0f | chunks with a hit per warp %.0f of %.0f, "
                         "groups queued per (query, range) %.1f (largest %.0f) | mma thread per tile: wait key tile %.0f, wait accumulators + issue %.0f | service sweeps %.0f\n",
-                n_db, a[8], a[1] / 8 / a[8], a[0] / 8 / a[8], a[9] / 8 / a[8], a[10] / 8 / a[8], a[2] / 8, a[8] * 4, a[3] / 8 / 32, amax4, a[6] / a[8], a[7] / a[8], a[5] / 2);
+                n_db, a[8], a[1] / 8 / a[8], a[0] / 8 / a[8], a[9] / 8 / a[8], a[10] / 8 / a[8], a[11] / 8 / a[8], a[2] / 8, a[8] * 8, a[3] / 8 / 32, amax4, a[6] / a[8], a[7] / a[8], a[5] / 2);
         cudaFree(times);
     }
     return cudaGetLastError();
@@ -764,15 +747,15 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
         err = cudaMemsetAsync(ws.slots, 0x7f, (size_t)Qc * kKPrime * 4, stream);     /* 3.39e38: "no key yet" */
         if (err != cudaSuccess) return err;
         const float* qk = qkeys + (size_t)q0 * R;
-        if (R == 20) err = launch_tc<20>(qk, Qc, img, n_db, n_ranges, ws.slots, ws.hq, ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), stream);
-        else err = launch_tc<40>(qk, Qc, img, n_db, n_ranges, ws.slots, ws.hq, ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), stream);
+        if (R == 20) err = launch_tc<20>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint2*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), stream);
+        else err = launch_tc<40>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint2*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), stream);
         if (err != cudaSuccess) return err;
         if (metric == 0)
-            knn_rerank_kernel<0><<<Qc, 128, 0, stream>>>(qk, Qc, keys, R, K, n_ranges, n_db, ws.hq, ws.hq_cnt, ws.slots,
+            knn_rerank_kernel<0><<<Qc, 128, 0, stream>>>(qk, Qc, keys, R, K, n_ranges, n_db, reinterpret_cast<const uint2*>(ws.hq), ws.hq_cnt, ws.slots,
                                                                                       kn2max, id_mul, id_add, out_ids + (size_t)q0 * K, out_d2 + (size_t)q0 * K, q0,
                                                                                       fail_list, fail_count, ws.err_probe);
         else
-            knn_rerank_kernel<1><<<Qc, 128, 0, stream>>>(qk, Qc, keys, R, K, n_ranges, n_db, ws.hq, ws.hq_cnt, ws.slots,
+            knn_rerank_kernel<1><<<Qc, 128, 0, stream>>>(qk, Qc, keys, R, K, n_ranges, n_db, reinterpret_cast<const uint2*>(ws.hq), ws.hq_cnt, ws.slots,
                                                                                       kn2max, id_mul, id_add, out_ids + (size_t)q0 * K, out_d2 + (size_t)q0 * K, q0,
                                                                                       fail_list, fail_count, ws.err_probe);
         err = cudaGetLastError();
