@@ -513,32 +513,37 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     }
 }
 
-template <int METRIC>
-__device__ __forceinline__ float exact_d2(const float* __restrict__ q, const float* __restrict__ k, int R)
+// the reference's float distance (the operation order of k3_knn.cu: nanoflann adds four squares at a time, libnabo one)
+// on a key row held in registers
+template <int METRIC, int R>
+__device__ __forceinline__ float exact_d2(const float* __restrict__ q, const float4 (&kv)[R / 4])
 {
     float result = 0.0f;
-    if (METRIC == 0) {
-        int d = 0;
-        for (; d + 3 < R; d += 4) {
-            const float d0 = __fsub_rn(q[d], k[d]), d1 = __fsub_rn(q[d + 1], k[d + 1]), d2 = __fsub_rn(q[d + 2], k[d + 2]), d3 = __fsub_rn(q[d + 3], k[d + 3]);
-            const float g = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)), __fmul_rn(d3, d3));
-            result = __fadd_rn(result, g);
+#pragma unroll
+    for (int g = 0; g < R / 4; g++) {
+        const float d0 = __fsub_rn(q[4 * g], kv[g].x), d1 = __fsub_rn(q[4 * g + 1], kv[g].y), d2 = __fsub_rn(q[4 * g + 2], kv[g].z), d3 = __fsub_rn(q[4 * g + 3], kv[g].w);
+        if (METRIC == 0) {
+            const float s = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)), __fmul_rn(d3, d3));
+            result = __fadd_rn(result, s);
+        } else {
+            result = __fadd_rn(result, __fmul_rn(d0, d0)); result = __fadd_rn(result, __fmul_rn(d1, d1));
+            result = __fadd_rn(result, __fmul_rn(d2, d2)); result = __fadd_rn(result, __fmul_rn(d3, d3));
         }
-        for (; d < R; d++) { const float d0 = __fsub_rn(q[d], k[d]); result = __fadd_rn(result, __fmul_rn(d0, d0)); }
-    } else {
-        for (int d = 0; d < R; d++) { const float d0 = __fsub_rn(q[d], k[d]); result = __fadd_rn(result, __fmul_rn(d0, d0)); }
     }
     return result;
 }
 
-// Phase B: exact re-rank + certificate. One CTA of 128 threads per query: the hit queues of all ranges are flattened
+// Phase B: exact re-rank + certificate. One CTA of 256 threads per query: the hit queues of all ranges are flattened
 // (counts -> prefix sums in shared memory) so that every thread reads a few independent entries; the 8 keys of every
 // surviving group (best score at or below the cut) are re-scored exactly, and warp 0 selects the top-K and certifies it.
+// The kernel is a chain of dependent memory round trips (counts -> entries -> key rows), so every phase issues all of a
+// thread's loads before it uses any of them.
 constexpr int kMaxGroups = 256;                         /* surviving groups per query (about 3 K' are expected: the cut is the LARGEST of K' slot minima) */
 constexpr int kMaxRanges = 160;
 constexpr int kMaxSel = 512;                            /* keys entering the top-K selection */
-template <int METRIC>
-__global__ void __launch_bounds__(128) knn_rerank_kernel(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys, int R, int K,
+constexpr int kRrThreads = 256;
+template <int METRIC, int R>
+__global__ void __launch_bounds__(kRrThreads, 4) knn_rerank_kernel(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys, int K,
                                                           int n_ranges, int n_db, const uint2* __restrict__ hq, const int* __restrict__ hq_cnt,
                                                           const int* __restrict__ slots, const float* __restrict__ kn2max, int id_mul, int id_add,
                                                           int32_t* __restrict__ out_ids, float* __restrict__ out_d2, int q_off,
@@ -563,7 +568,7 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(const float* __restrict
     const float cut = gt < 0x7f000000 ? ordered_float(gt) : inf;
     if (t == 0) { s_count = 0; s_overflow = 0; s_nsel = 0; }
     if (t < R) s_q[t] = __ldg(q + t);
-    for (int r = t; r < n_ranges; r += 128) {
+    for (int r = t; r < n_ranges; r += kRrThreads) {
         int c = __ldg(hq_cnt + (size_t)qi * n_ranges + r);
         if (c > kQueueCap) { s_overflow = 1; c = kQueueCap; }
         s_pre[r + 1] = c;
@@ -583,14 +588,26 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(const float* __restrict
     }
     __syncthreads();
     const int total = s_pre[n_ranges];
-    for (int g = t; g < total; g += 128) {
-        int lo = 0, hi = n_ranges;                      /* the range that holds entry g: last r with s_pre[r] <= g */
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_pre[mid] <= g) lo = mid; else hi = mid; }
-        const uint2 e = __ldcg(hq + ((size_t)qi * n_ranges + lo) * (size_t)kQueueCap + (g - s_pre[lo]));
-        const float gm = __uint_as_float(e.y);
-        if (gm <= cut && (int)e.x < n_db) {
-            const int pos = atomicAdd(&s_count, 1);
-            if (pos < kMaxGroups) { s_key[pos] = (int)e.x; s_g[pos] = gm; }
+    constexpr int UE = 4;                               /* queue entries in flight per thread */
+    for (int base = 0; base < total; base += kRrThreads * UE) {
+        uint2 e[UE];
+#pragma unroll
+        for (int u = 0; u < UE; u++) {
+            const int g = base + u * kRrThreads + t;
+            e[u] = make_uint2(0x7fffffffu, 0x7f800000u);
+            if (g < total) {
+                int lo = 0, hi = n_ranges;              /* the range that holds entry g: last r with s_pre[r] <= g */
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_pre[mid] <= g) lo = mid; else hi = mid; }
+                e[u] = __ldcg(hq + ((size_t)qi * n_ranges + lo) * (size_t)kQueueCap + (g - s_pre[lo]));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UE; u++) {
+            const float gm = __uint_as_float(e[u].y);
+            if (gm <= cut && (int)e[u].x < n_db) {
+                const int pos = atomicAdd(&s_count, 1);
+                if (pos < kMaxGroups) { s_key[pos] = (int)e[u].x; s_g[pos] = gm; }
+            }
         }
     }
     __syncthreads();
@@ -604,17 +621,32 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(const float* __restrict
     /* a certified top-K lies wholly below cut + |q|^2 (see below): keys at or above it need not enter the selection */
     const float d_lim = cut < inf ? cut + qn : inf;
     float worst_err = 0.0f;
-    for (int c = t; c < n_grp * 8; c += 128) {
-        const int id = s_key[c >> 3] + (c & 7);
-        if (id < n_db) {
-            float d = exact_d2<METRIC>(s_q, keys + (size_t)id * R, R);
-            /* the prefilter must not have OVER-estimated a key by more than eps (that is what the certificate relies on) */
-            if (err_probe) worst_err = fmaxf(worst_err, (s_g[c >> 3] - (d - qn)) / eps0);
-            if (METRIC == 1 && !(d > FLT_EPSILON)) d = inf;          /* libnabo self-match rule */
-            if (!(d < (METRIC == 0 ? FLT_MAX : inf))) d = inf;       /* never accepted by the trees */
-            if (d < d_lim) {
-                const int pos = atomicAdd(&s_nsel, 1);
-                if (pos < kMaxSel) { s_d[pos] = d; s_id[pos] = id * id_mul + id_add; }
+    constexpr int UK = R <= 20 ? 2 : 1;                 /* key rows in flight per thread (64 registers: four CTAs per SM) */
+    for (int base = 0; base < n_grp * 8; base += kRrThreads * UK) {
+        float4 kv[UK][R / 4];
+        int id[UK];
+#pragma unroll
+        for (int u = 0; u < UK; u++) {
+            const int c = base + u * kRrThreads + t;
+            id[u] = c < n_grp * 8 ? s_key[c >> 3] + (c & 7) : n_db;
+            if (id[u] < n_db) {
+#pragma unroll
+                for (int g = 0; g < R / 4; g++) kv[u][g] = __ldg(reinterpret_cast<const float4*>(keys + (size_t)id[u] * R) + g);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UK; u++) {
+            if (id[u] < n_db) {
+                const int c = base + u * kRrThreads + t;
+                float d = exact_d2<METRIC, R>(s_q, kv[u]);
+                /* the prefilter must not have OVER-estimated a key by more than eps (that is what the certificate relies on) */
+                if (err_probe) worst_err = fmaxf(worst_err, (s_g[c >> 3] - (d - qn)) / eps0);
+                if (METRIC == 1 && !(d > FLT_EPSILON)) d = inf;          /* libnabo self-match rule */
+                if (!(d < (METRIC == 0 ? FLT_MAX : inf))) d = inf;       /* never accepted by the trees */
+                if (d < d_lim) {
+                    const int pos = atomicAdd(&s_nsel, 1);
+                    if (pos < kMaxSel) { s_d[pos] = d; s_id[pos] = id[u] * id_mul + id_add; }
+                }
             }
         }
     }
@@ -750,14 +782,13 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
         if (R == 20) err = launch_tc<20>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint2*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), stream);
         else err = launch_tc<40>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint2*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), stream);
         if (err != cudaSuccess) return err;
-        if (metric == 0)
-            knn_rerank_kernel<0><<<Qc, 128, 0, stream>>>(qk, Qc, keys, R, K, n_ranges, n_db, reinterpret_cast<const uint2*>(ws.hq), ws.hq_cnt, ws.slots,
-                                                                                      kn2max, id_mul, id_add, out_ids + (size_t)q0 * K, out_d2 + (size_t)q0 * K, q0,
-                                                                                      fail_list, fail_count, ws.err_probe);
-        else
-            knn_rerank_kernel<1><<<Qc, 128, 0, stream>>>(qk, Qc, keys, R, K, n_ranges, n_db, reinterpret_cast<const uint2*>(ws.hq), ws.hq_cnt, ws.slots,
-                                                                                      kn2max, id_mul, id_add, out_ids + (size_t)q0 * K, out_d2 + (size_t)q0 * K, q0,
-                                                                                      fail_list, fail_count, ws.err_probe);
+#define SCL_RERANK(M, RR)                                                                                                              \
+    knn_rerank_kernel<M, RR><<<Qc, kRrThreads, 0, stream>>>(qk, Qc, keys, K, n_ranges, n_db, reinterpret_cast<const uint2*>(ws.hq), ws.hq_cnt,   \
+                                                            ws.slots, kn2max, id_mul, id_add, out_ids + (size_t)q0 * K, out_d2 + (size_t)q0 * K, \
+                                                            q0, fail_list, fail_count, ws.err_probe)
+        if (R == 20) { if (metric == 0) SCL_RERANK(0, 20); else SCL_RERANK(1, 20); }
+        else { if (metric == 0) SCL_RERANK(0, 40); else SCL_RERANK(1, 40); }
+#undef SCL_RERANK
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;
     }

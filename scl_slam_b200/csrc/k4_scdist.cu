@@ -28,7 +28,7 @@
 
 namespace {
 
-constexpr int kShiftChunk = 8;
+constexpr int kShiftChunk = 7;          /* the default window (radius 3) in one chunk; keeps two CTAs per SM at 20x60 */
 
 struct ScLayout {
     int RS, S, warps;
@@ -47,7 +47,7 @@ __host__ __device__ inline ScLayout sc_layout(int R, int S, int K, int warps)
     L.off_vq = o; o += (size_t)S * 8;
     L.off_nq = o; o += (size_t)S * 8;
     L.off_warp = o;
-    L.warp_stride = (size_t)(2 + kShiftChunk) * S * 8;          /* vc, nc, sim[kShiftChunk][S] */
+    L.warp_stride = (size_t)(3 + kShiftChunk) * S * 8;          /* vc (twice in a row: circular reads need no wrap), nc, sim[kShiftChunk][S] */
     o += (size_t)warps * L.warp_stride;
     L.off_res = o; o += (size_t)K * 16;                         /* dist[K] doubles, shift[K] ints */
     L.total = o;
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) scdist_kernel(
     double* vq = reinterpret_cast<double*>(smem + L.off_vq);
     double* nq = reinterpret_cast<double*>(smem + L.off_nq);
     double* vc = reinterpret_cast<double*>(smem + L.off_warp + (size_t)warp * L.warp_stride);
-    double* nc = vc + S;
+    double* nc = vc + 2 * S;
     double* sim = nc + S;
     double* res_dist = reinterpret_cast<double*>(smem + L.off_res);
     int* res_shift = reinterpret_cast<int*>(res_dist + K);
@@ -148,23 +148,27 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) scdist_kernel(
             /* a. candidate sector key and column norms */
             column_stats_batch(cd, R, S, lane, 32, vc, nc);
             __syncwarp();
-            /* b. fastAlignUsingVkey: lane <-> shift, sequential over columns (:1496-1508) */
+            for (int j = lane; j < S; j += 32) vc[S + j] = vc[j];
+            __syncwarp();
+            /* b. fastAlignUsingVkey: lane <-> shift, sequential over columns (:1496-1508). Shifted key element j of shift sh is
+             * vc[(j - sh) mod S] = vc2[S - sh + j]: two shifts of this lane (sh, sh + 32) run side by side. */
             double bestn = 10000000.0; int bests = 0x7fffffff;
-            for (int sb = lane; sb < S; sb += kJC * 32) {       /* kJC shifts of this lane side by side */
-                double ss[kJC]; int idx[kJC];
+            constexpr int kSC = 2;
+            for (int sb = lane; sb < S; sb += kSC * 32) {
+                double ss[kSC]; const double* vs[kSC];
 #pragma unroll
-                for (int c = 0; c < kJC; c++) { ss[c] = 0.0; const int sh = sb + 32 * c; idx[c] = sh < S ? (sh == 0 ? 0 : S - sh) : 0; }
+                for (int c = 0; c < kSC; c++) { ss[c] = 0.0; const int sh = sb + 32 * c; vs[c] = vc + (sh < S ? S - sh : 0); }
+#pragma unroll 4
                 for (int j = 0; j < S; j++) {
                     const double a = vq[j];
 #pragma unroll
-                    for (int c = 0; c < kJC; c++) {
-                        const double d = __dsub_rn(a, vc[idx[c]]);
+                    for (int c = 0; c < kSC; c++) {
+                        const double d = __dsub_rn(a, vs[c][j]);
                         ss[c] = __dadd_rn(ss[c], __dmul_rn(d, d));
-                        if (++idx[c] == S) idx[c] = 0;
                     }
                 }
 #pragma unroll
-                for (int c = 0; c < kJC; c++) {
+                for (int c = 0; c < kSC; c++) {
                     const int sh = sb + 32 * c;
                     if (sh < S) {
                         const double nrm = __dsqrt_rn(ss[c]);

@@ -367,19 +367,19 @@ def test_tensor_core_knn_equals_oracle(eng_mod, R, S, K, n, nq, metric):
 
 
 def test_tensor_core_knn_fallback_on_ties(eng_mod):
-    """Adversarial database: hundreds of exact duplicates and near-duplicates around every query — more than the
-    re-rank's survivor list holds — so the prefilter cannot certify a top-K; those queries must be redone exactly
-    and still match."""
+    """Adversarial database: 1400 exact duplicates and near-duplicates around every query — more than the
+    re-rank's selection list holds (512 keys) — so the prefilter cannot certify a top-K; those queries must be
+    redone exactly and still match."""
     n, nq, K = 40000, 70, 10
     db = synth.desc_db(n, seed=93).numpy()
     rng = np.random.default_rng(5)
-    for b in range(20):                                      # 20 clusters of 400 copies, some perturbed in the last float bits
+    for b in range(20):                                      # 20 clusters of 1400 copies, some perturbed in the last float bits
         base = db[1000 + b].copy()
-        for j in range(400):
+        for j in range(1400):
             d = base.copy()
             if j % 3 == 1:
                 d[rng.integers(0, 20), rng.integers(0, 60)] += np.float32(1e-5)
-            db[2000 + b * 1500 + j * 3] = d
+            db[2000 + b * 1500 + j] = d
     q = np.stack([db[1000 + (i % 20)] for i in range(nq)])   # queries = the cluster centres
     o = Oracle(num_candidates=K)
     o.bulk_load(np.concatenate([db.reshape(n, -1), q.reshape(nq, -1)]))
