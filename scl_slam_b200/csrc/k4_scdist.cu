@@ -28,6 +28,7 @@
 
 namespace {
 
+constexpr int kQExt = 8;                /* query rows are stored S + kQExt wide (the first columns repeated): circular windows read straight */
 constexpr int kShiftChunk = 7;          /* the default window (radius 3) in one chunk; keeps two CTAs per SM at 20x60 */
 
 struct ScLayout {
@@ -43,7 +44,7 @@ __host__ __device__ inline ScLayout sc_layout(int R, int S, int K, int warps)
     L.off_q = o; o += (size_t)L.RS * 4;
     L.off_c = o; o += (size_t)warps * L.RS * 4;
     o = (o + 15) / 16 * 16;
-    L.off_qdd = o; o += (size_t)L.RS * 8;                       /* the query tile widened to double once per CTA */
+    L.off_qdd = o; o += (size_t)R * (S + kQExt) * 8;            /* the query tile widened to double once per CTA, rows S + kQExt wide */
     L.off_vq = o; o += (size_t)S * 8;
     L.off_nq = o; o += (size_t)S * 8;
     L.off_warp = o;
@@ -135,7 +136,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) scdist_kernel(
     if (use_bulk) scl_mbar_wait(&bars[0], 0);
     else __syncthreads();
     column_stats_batch(qd, R, S, threadIdx.x, blockDim.x, vq, nq);
-    for (int i = threadIdx.x; i < RS; i += blockDim.x) qdd[i] = (double)qd[i];
+    for (int i = threadIdx.x; i < R * (S + kQExt); i += blockDim.x) {
+        const int r = i / (S + kQExt), j = i - r * (S + kQExt);
+        qdd[i] = (double)qd[r * S + (j < S ? j : j - S)];
+    }
     __syncthreads();
 
     uint32_t parity = 0;
@@ -182,62 +186,86 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) scdist_kernel(
                 if (on < bestn || (on == bestn && os < bests)) { bestn = on; bests = os; }
             }
             const int align = (bests == 0x7fffffff) ? 0 : bests;   /* no norm below 1e7: argmin stays 0 (:1493) */
-            /* c. window of shifts around the alignment, ascending, strict < (:1545-1566) */
-            double min_sc = 10000000.0; int argmin_shift = 0;
-            int s_next = 0;
-            while (s_next < S) {
-                int shifts[kShiftChunk]; int ns = 0;
-                for (; s_next < S && ns < kShiftChunk; s_next++) {
-                    int diff = s_next - align; if (diff < 0) diff += S;
-                    const int cdist = min(diff, S - diff);
-                    if (cdist <= search_radius) shifts[ns++] = s_next;
-                }
-                if (ns == 0) break;
-                /* lane <-> CANDIDATE column cb: each candidate element is widened to double once and meets the
-                 * query columns j_w = cb + s_w of all the chunk's shifts (read as doubles from qdd). Every (j, s)
-                 * dot product still accumulates over the rows in order, so the result is unchanged bit for bit. */
-                for (int cb = lane; cb < S; cb += 32) {
-                    const double nb = nc[cb];
-                    int jw[kShiftChunk]; double dot[kShiftChunk];
+            /* c. window of shifts around the alignment (:1545-1566). The reference visits the shifts within search_radius of
+             * the alignment in ascending order and keeps the first strict minimum, i.e. the smallest distance and, among equal
+             * distances, the smallest shift. Here the window is walked in circular order from align - radius (consecutive
+             * shifts read consecutive query columns) and that rule is applied to (distance, shift) pairs. */
+            double min_sc = 10000000.0; int argmin_shift = 0; bool found = false;
+            const int win = min(2 * search_radius + 1, S);
+            int s_first = win == S ? 0 : align - search_radius; if (s_first < 0) s_first += S;
+            for (int p0 = 0; p0 < win; p0 += kShiftChunk) {
+                const int ns = min(kShiftChunk, win - p0);
+                int s0 = s_first + p0; if (s0 >= S) s0 -= S;               /* shift of window position p0; position w has s0 + w (mod S) */
+                int cnt[kShiftChunk];                                       /* columns that count, per shift (warp-uniform) */
+#pragma unroll
+                for (int w = 0; w < kShiftChunk; w++) cnt[w] = 0;
+                /* lane <-> CANDIDATE column cb: each candidate element is widened to double once and meets the query columns
+                 * cb + s0 + w of all the chunk's shifts (consecutive doubles of the widened query row). Every (j, s) dot
+                 * product still accumulates over the rows in order, so the result is unchanged bit for bit. */
+                for (int cb0 = 0; cb0 < S; cb0 += 32) {
+                    const int cb = cb0 + lane;
+                    const bool on = cb < S;
+                    const double nb = on ? nc[cb] : 0.0;
+                    int jb = (on ? cb : 0) + s0; if (jb >= S) jb -= S;      /* query column of window position 0 */
+                    double dot[kShiftChunk];
+#pragma unroll
+                    for (int w = 0; w < kShiftChunk; w++) dot[w] = 0.0;
+                    if (nb != 0.0) {
+                        const double* qrow = qdd + jb;
+                        const float* crow = cd + cb;
+                        if (ns == kShiftChunk) {
+#pragma unroll 4
+                            for (int r = 0; r < R; r++) {
+                                const double b = (double)crow[r * S];
+#pragma unroll
+                                for (int w = 0; w < kShiftChunk; w++) dot[w] = __dadd_rn(dot[w], __dmul_rn(qrow[r * (S + kQExt) + w], b));
+                            }
+                        } else {
+#pragma unroll 2
+                            for (int r = 0; r < R; r++) {
+                                const double b = (double)crow[r * S];
+#pragma unroll
+                                for (int w = 0; w < kShiftChunk; w++)
+                                    if (w < ns) dot[w] = __dadd_rn(dot[w], __dmul_rn(qrow[r * (S + kQExt) + w], b));
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int w = 0; w < kShiftChunk; w++) {
-                        int j = cb + (w < ns ? shifts[w] : 0); if (j >= S) j -= S;   /* circshift: shifted.col(j) = sc2.col(j - s) */
-                        jw[w] = j; dot[w] = 0.0;
-                    }
-                    if (nb != 0.0) {
-#pragma unroll 4
-                        for (int r = 0; r < R; r++) {
-                            const double b = (double)cd[r * S + cb];
-#pragma unroll
-                            for (int w = 0; w < kShiftChunk; w++)
-                                if (w < ns) dot[w] = __dadd_rn(dot[w], __dmul_rn(qdd[r * S + jw[w]], b));
+                        if (w < ns) {                                      /* warp-uniform */
+                            int j = jb + w; if (j >= S) j -= S;
+                            const double na = nq[j];
+                            const bool counts = on && !((na == 0.0) | (nb == 0.0));
+                            if (on) sim[w * S + j] = counts ? __ddiv_rn(dot[w], __dmul_rn(na, nb)) : 0.0;
+                            cnt[w] += __popc(__ballot_sync(0xffffffffu, counts));
                         }
                     }
-#pragma unroll
-                    for (int w = 0; w < kShiftChunk; w++)
-                        if (w < ns) {
-                            const double na = nq[jw[w]];
-                            sim[w * S + jw[w]] = ((na == 0.0) | (nb == 0.0)) ? 0.0 : __ddiv_rn(dot[w], __dmul_rn(na, nb));
-                        }
                 }
                 __syncwarp();
-                double dist = 0.0;
-                if (lane < ns) {                                       /* one lane per shift: in-order sum over columns */
-                    int my_s = 0;                                      /* shifts[] is warp-uniform; select by lane */
+                /* one lane per shift: in-order sum over the columns. Columns that do not count hold +0.0, and adding +0.0 never
+                 * changes the running sum (it starts at +0.0 and a dot product that starts at +0.0 is never -0.0). */
+                double dist = 0.0; int my_s = 0x7fffffff;
+                if (lane < ns) {
+                    int my_cnt = 0;
 #pragma unroll
-                    for (int w = 0; w < kShiftChunk; w++) if (w == lane) my_s = shifts[w];
-                    double sum = 0.0; int cnt = 0;
-                    for (int j = 0; j < S; j++) {
-                        int cb = j - my_s; if (cb < 0) cb += S;
-                        if (!((nq[j] == 0.0) | (nc[cb] == 0.0))) { sum = __dadd_rn(sum, sim[lane * S + j]); cnt++; }
-                    }
-                    dist = __dsub_rn(1.0, __ddiv_rn(sum, (double)cnt));   /* 0/0 = NaN when no column counts (:1534) */
+                    for (int w = 0; w < kShiftChunk; w++) if (w == lane) my_cnt = cnt[w];
+                    const double* sp = sim + lane * S;
+                    double sum = 0.0;
+#pragma unroll 4
+                    for (int j = 0; j < S; j++) sum = __dadd_rn(sum, sp[j]);
+                    dist = __dsub_rn(1.0, __ddiv_rn(sum, (double)my_cnt));  /* 0/0 = NaN when no column counts (:1534) */
+                    my_s = s0 + lane; if (my_s >= S) my_s -= S;
                 }
+                /* smallest (distance, shift) of the chunk; NaN and anything not below the running minimum never wins */
+                bool cand = lane < ns && dist < 10000000.0;
+                double bd = cand ? dist : 10000000.0; int bs = cand ? my_s : 0x7fffffff;
 #pragma unroll
-                for (int w = 0; w < kShiftChunk; w++) {
-                    const double d = __shfl_sync(0xffffffffu, dist, w);
-                    if (w < ns && d < min_sc) { min_sc = d; argmin_shift = shifts[w]; }
+                for (int off = 4; off > 0; off >>= 1) {                    /* kShiftChunk <= 8 lanes hold values */
+                    const double od = __shfl_xor_sync(0xffffffffu, bd, off); const int os = __shfl_xor_sync(0xffffffffu, bs, off);
+                    if (od < bd || (od == bd && os < bs)) { bd = od; bs = os; }
                 }
+                bd = __shfl_sync(0xffffffffu, bd, 0); bs = __shfl_sync(0xffffffffu, bs, 0);
+                if (bs != 0x7fffffff && (bd < min_sc || (found && bd == min_sc && bs < argmin_shift))) { min_sc = bd; argmin_shift = bs; found = true; }
                 __syncwarp();
             }
             out_dist = min_sc; out_shift = argmin_shift;
