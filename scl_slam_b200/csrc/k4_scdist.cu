@@ -199,6 +199,48 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) scdist_kernel(
                 int cnt[kShiftChunk];                                       /* columns that count, per shift (warp-uniform) */
 #pragma unroll
                 for (int w = 0; w < kShiftChunk; w++) cnt[w] = 0;
+                if (ns == kShiftChunk && (S & 1) == 0) {
+                    /* Full chunk: lane <-> a PAIR of adjacent candidate columns (cb, cb + 1). Window position w of column cb
+                     * meets query column jb + w, and of column cb + 1 query column jb + w + 1: the pair shares kShiftChunk + 1
+                     * consecutive doubles of the widened query row, read once (shared memory is the binding resource of this
+                     * kernel). Every (column, shift) dot product still accumulates over the rows in order: unchanged bit for bit. */
+                    for (int cb0 = 0; cb0 < S; cb0 += 64) {
+                        const int cb = cb0 + 2 * lane;
+                        const bool on = cb < S;                            /* S is even: cb + 1 < S as well */
+                        const double nba = on ? nc[cb] : 0.0, nbb = on ? nc[cb + 1] : 0.0;
+                        int jb = (on ? cb : 0) + s0; if (jb >= S) jb -= S;
+                        double da[kShiftChunk], db[kShiftChunk];
+#pragma unroll
+                        for (int w = 0; w < kShiftChunk; w++) { da[w] = 0.0; db[w] = 0.0; }
+                        if (on && ((nba != 0.0) | (nbb != 0.0))) {
+                            const double* qrow = qdd + jb;
+                            const float2* crow = reinterpret_cast<const float2*>(cd + cb);
+#pragma unroll 2
+                            for (int r = 0; r < R; r++) {
+                                const float2 c2 = crow[r * (S / 2)];
+                                const double a = (double)c2.x, b = (double)c2.y;
+#pragma unroll
+                                for (int w = 0; w <= kShiftChunk; w++) {
+                                    const double qv = qrow[r * (S + kQExt) + w];
+                                    if (w < kShiftChunk) da[w] = __dadd_rn(da[w], __dmul_rn(qv, a));
+                                    if (w > 0) db[w - 1] = __dadd_rn(db[w - 1], __dmul_rn(qv, b));
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int w = 0; w < kShiftChunk; w++) {
+                            int ja = jb + w; if (ja >= S) ja -= S;
+                            int jn = ja + 1; if (jn >= S) jn -= S;
+                            const double naa = nq[ja], nab = nq[jn];
+                            const bool ca = on && !((naa == 0.0) | (nba == 0.0)), cbn = on && !((nab == 0.0) | (nbb == 0.0));
+                            if (on) {
+                                sim[w * S + ja] = ca ? __ddiv_rn(da[w], __dmul_rn(naa, nba)) : 0.0;
+                                sim[w * S + jn] = cbn ? __ddiv_rn(db[w], __dmul_rn(nab, nbb)) : 0.0;
+                            }
+                            cnt[w] += __popc(__ballot_sync(0xffffffffu, ca)) + __popc(__ballot_sync(0xffffffffu, cbn));
+                        }
+                    }
+                } else
                 /* lane <-> CANDIDATE column cb: each candidate element is widened to double once and meets the query columns
                  * cb + s0 + w of all the chunk's shifts (consecutive doubles of the widened query row). Every (j, s) dot
                  * product still accumulates over the rows in order, so the result is unchanged bit for bit. */
@@ -213,21 +255,12 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) scdist_kernel(
                     if (nb != 0.0) {
                         const double* qrow = qdd + jb;
                         const float* crow = cd + cb;
-                        if (ns == kShiftChunk) {
-#pragma unroll 4
-                            for (int r = 0; r < R; r++) {
-                                const double b = (double)crow[r * S];
-#pragma unroll
-                                for (int w = 0; w < kShiftChunk; w++) dot[w] = __dadd_rn(dot[w], __dmul_rn(qrow[r * (S + kQExt) + w], b));
-                            }
-                        } else {
 #pragma unroll 2
-                            for (int r = 0; r < R; r++) {
-                                const double b = (double)crow[r * S];
+                        for (int r = 0; r < R; r++) {
+                            const double b = (double)crow[r * S];
 #pragma unroll
-                                for (int w = 0; w < kShiftChunk; w++)
-                                    if (w < ns) dot[w] = __dadd_rn(dot[w], __dmul_rn(qrow[r * (S + kQExt) + w], b));
-                            }
+                            for (int w = 0; w < kShiftChunk; w++)
+                                if (w < ns) dot[w] = __dadd_rn(dot[w], __dmul_rn(qrow[r * (S + kQExt) + w], b));
                         }
                     }
 #pragma unroll
