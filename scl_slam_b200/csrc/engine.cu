@@ -210,6 +210,7 @@ int knn_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int
             CK(scl_launch_knn_tc(e->qkeys.as<float>(), Q, e->d_keys, e->d_kimg, e->d_kn2max, n_db, R, K, metric, e->world, e->rank, tw,
                                  cand_ids, cand_d2, e->tc_fail_list.as<int32_t>(), e->tc_fail_count.as<int>(), e->stream));
             /* uncertified queries (normally none) are redone exactly; CTAs beyond the list length exit at once */
+            if (!(getenv("SCL_TC_FLAGS") && (atoi(getenv("SCL_TC_FLAGS")) & 32)))
             CK(scl_launch_knn_exact(e->qkeys.as<float>(), Q, e->d_keys, n_db, R, K, metric, e->world, e->rank,
                                     e->tc_fail_list.as<int32_t>(), e->tc_fail_count.as<int>(), ws, cand_ids, cand_d2, e->stream));
             e->stat_tc_queries += Q;

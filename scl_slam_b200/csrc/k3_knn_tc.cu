@@ -58,7 +58,8 @@
 
 namespace {
 
-constexpr int kKPrime = 16;        /* K': the number of distinct keys that back a query's threshold; K <= K' - 2 */
+constexpr int kKPrime = 12;        /* K': the number of distinct keys that back a query's threshold; K <= K' - 2. The bound is the LARGEST of K'
+                                    * slot minima, which about K' H(K') keys undercut (37 at K' = 12, 54 at 16): smaller is tighter. Multiple of 4. */
 constexpr int kQueueCap = 128;               /* hit queue per (query, range): entries of 2 words (first key of an 8-key group, its best score); ~12 are used; a tile adds at most 32 */
 constexpr int kEpiThreads = 256;   /* 8 epilogue warps: query tile = (warp-4)/4, TMEM lane quadrant = warp%4 */
 constexpr int kThreads = 384;
@@ -442,7 +443,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         // ===== threshold service: union bound of the CTA's 256 queries ==================================
         // Range r publishes its best score so far into slot r % K' of the query (atomicMin). The K' slots then hold the
         // scores of K' DISTINCT keys (different ranges), so their maximum bounds the query's K'-th best score from above.
-        // Each lane refreshes four queries: 64 bytes from L2 and 15 max operations per query, a microsecond per sweep.
+        // Each lane refreshes four queries: 4 K' bytes from L2 and K' - 1 max operations per query, a microsecond per sweep.
         int sweeps = 0;
         while (n_tiles > 0 && !(dev_flags & 2)) {
             const bool last = *epi_done >= 8;
@@ -452,9 +453,12 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                 const int qi = q_base + j;
                 if (qi < Q) {
                     const int4* p = reinterpret_cast<const int4*>(slots + (size_t)qi * kKPrime);
-                    const int4 a = __ldcg(p), b4 = __ldcg(p + 1), c = __ldcg(p + 2), d = __ldcg(p + 3);
-                    const int m = max(max(max(max(a.x, a.y), max(a.z, a.w)), max(max(b4.x, b4.y), max(b4.z, b4.w))),
-                                      max(max(max(c.x, c.y), max(c.z, c.w)), max(max(d.x, d.y), max(d.z, d.w))));
+                    int4 v[kKPrime / 4];
+#pragma unroll
+                    for (int i = 0; i < kKPrime / 4; i++) v[i] = __ldcg(p + i);
+                    int m = (int)0x80000000;
+#pragma unroll
+                    for (int i = 0; i < kKPrime / 4; i++) m = max(m, max(max(v[i].x, v[i].y), max(v[i].z, v[i].w)));
                     if (m < 0x7f000000) sthr[j] = m;     /* all K' slots filled: a valid bound */
                 }
             }
@@ -533,101 +537,116 @@ __device__ __forceinline__ float exact_d2(const float* __restrict__ q, const flo
     return result;
 }
 
-// Phase B: exact re-rank + certificate. One CTA of 256 threads per query: the hit queues of all ranges are flattened
-// (counts -> prefix sums in shared memory) so that every thread reads a few independent entries; the 8 keys of every
-// surviving group (best score at or below the cut) are re-scored exactly, and warp 0 selects the top-K and certifies it.
-// The kernel is a chain of dependent memory round trips (counts -> entries -> key rows), so every phase issues all of a
-// thread's loads before it uses any of them.
+// Phase B: exact re-rank + certificate. One WARP per query (four queries per CTA, no block-wide barriers): the kernel is
+// a chain of dependent memory round trips (counts -> queue entries -> key rows), so what matters is how many loads a lane
+// has in flight per trip, not how many threads share a query. The hit queues of all ranges are flattened (counts ->
+// prefix sums in the warp's shared memory), every lane reads a few independent entries per trip, the 8 keys of every
+// surviving group (best score at or below the cut) are re-scored exactly, four rows per lane in flight, and the warp
+// selects the top-K and certifies it.
 constexpr int kMaxGroups = 256;                         /* surviving groups per query (about 3 K' are expected: the cut is the LARGEST of K' slot minima) */
 constexpr int kMaxRanges = 160;
 constexpr int kMaxSel = 512;                            /* keys entering the top-K selection */
-constexpr int kRrThreads = 256;
+constexpr int kRrWarps = 4;                             /* queries per CTA */
 template <int METRIC, int R>
-__global__ void __launch_bounds__(kRrThreads, 4) knn_rerank_kernel(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys, int K,
+__global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys, int K,
                                                           int n_ranges, int n_db, const uint2* __restrict__ hq, const int* __restrict__ hq_cnt,
                                                           const int* __restrict__ slots, const float* __restrict__ kn2max, int id_mul, int id_add,
                                                           int32_t* __restrict__ out_ids, float* __restrict__ out_d2, int q_off,
-                                                          int32_t* __restrict__ fail_list, int* __restrict__ fail_count, float* __restrict__ err_probe)
+                                                          int32_t* __restrict__ fail_list, int* __restrict__ fail_count, float* __restrict__ err_probe, int dev_flags)
 {
-    __shared__ int s_key[kMaxGroups];                   /* first key of the group */
-    __shared__ float s_g[kMaxGroups];                   /* its best prefilter score */
-    __shared__ float s_d[kMaxSel];                      /* exact distances / ids of the keys that can still make the top-K */
-    __shared__ int s_id[kMaxSel];
-    __shared__ int s_pre[kMaxRanges + 1];
-    __shared__ float s_q[64];
-    __shared__ int s_count, s_overflow, s_nsel;
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int qi = blockIdx.x;
-    const float* q = qkeys + (size_t)qi * R;
+    __shared__ int sh_key[kRrWarps][kMaxGroups];        /* first key of the group */
+    __shared__ float sh_g[kRrWarps][kMaxGroups];        /* its best prefilter score */
+    __shared__ float sh_d[kRrWarps][kMaxSel];           /* exact distances / ids of the keys that can still make the top-K */
+    __shared__ int sh_id[kRrWarps][kMaxSel];
+    __shared__ int sh_pre[kRrWarps][kMaxRanges + 1];
+    __shared__ float sh_q[kRrWarps][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int qi = blockIdx.x * kRrWarps + warp;
+    if (qi >= Q) return;                                /* whole warp */
+    int* s_key = sh_key[warp]; float* s_g = sh_g[warp]; float* s_d = sh_d[warp]; int* s_id = sh_id[warp]; int* s_pre = sh_pre[warp];
+    float* s_q = sh_q[warp];
+    const unsigned lt_mask = (1u << lane) - 1u;
     const float inf = __int_as_float(0x7f800000);
+    /* first trip: slots, the query's key, the queue counts, the largest key norm: all independent */
+    int gt = lane < kKPrime ? __ldg(slots + (size_t)qi * kKPrime + lane) : (int)0x80000000;
+    const float qv = lane < R ? __ldg(qkeys + (size_t)qi * R + lane) : 0.0f;
+    const float qv2 = (R > 32 && lane + 32 < R) ? __ldg(qkeys + (size_t)qi * R + lane + 32) : 0.0f;
+    const float knmax = __ldg(kn2max);
+    constexpr int kCntPerLane = (kMaxRanges + 31) / 32;
+    int cnt[kCntPerLane];
+#pragma unroll
+    for (int u = 0; u < kCntPerLane; u++) {
+        const int r = u * 32 + lane;
+        cnt[u] = r < n_ranges ? __ldg(hq_cnt + (size_t)qi * n_ranges + r) : 0;
+    }
     /* The cut: the query's final union bound (the maximum of its K' slots). Every group that was not queued had all its
      * scores >= it, so every key scoring below it sits in a queued group; queued groups whose best score is above it
      * cannot be certified anyway and are skipped: about K' groups survive. */
-    int gt = lane < kKPrime ? __ldg(slots + (size_t)qi * kKPrime + lane) : (int)0x80000000;
     gt = __reduce_max_sync(0xffffffffu, gt);
     const float cut = gt < 0x7f000000 ? ordered_float(gt) : inf;
-    if (t == 0) { s_count = 0; s_overflow = 0; s_nsel = 0; }
-    if (t < R) s_q[t] = __ldg(q + t);
-    for (int r = t; r < n_ranges; r += kRrThreads) {
-        int c = __ldg(hq_cnt + (size_t)qi * n_ranges + r);
-        if (c > kQueueCap) { s_overflow = 1; c = kQueueCap; }
-        s_pre[r + 1] = c;
-    }
-    __syncthreads();
-    if (warp == 0) {                                    /* exclusive prefix sums of the counts, 32 ranges at a time */
-        int carry = 0;
-        for (int base = 0; base < n_ranges; base += 32) {
-            const int r = base + lane;
-            int v = r < n_ranges ? s_pre[r + 1] : 0;
+    if (lane < R) s_q[lane] = qv;
+    if (R > 32 && lane + 32 < R) s_q[lane + 32] = qv2;
+    bool overflow = false;
+    int carry = 0;                                      /* exclusive prefix sums of the counts, 32 ranges at a time */
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, v, off); if (lane >= off) v += o; }
-            if (r < n_ranges) s_pre[r + 1] = carry + v;
-            carry += __shfl_sync(0xffffffffu, v, 31);
-        }
-        if (lane == 0) s_pre[0] = 0;
+    for (int u = 0; u < kCntPerLane; u++) {
+        int v = cnt[u];
+        if (v > kQueueCap) { overflow = true; v = kQueueCap; }
+        int incl = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
+        const int r = u * 32 + lane;
+        if (r < n_ranges) s_pre[r + 1] = carry + incl;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    __syncthreads();
-    const int total = s_pre[n_ranges];
-    constexpr int UE = 4;                               /* queue entries in flight per thread */
-    for (int base = 0; base < total; base += kRrThreads * UE) {
+    if (lane == 0) s_pre[0] = 0;
+    overflow = __any_sync(0xffffffffu, overflow);
+    __syncwarp();
+    const int total = carry;
+    if (dev_flags & 128) { if (lane == 0) out_ids[(size_t)qi * K] = total; return; }
+    /* second trip(s): the queue entries, UE per lane in flight; survivors are compacted with a ballot */
+    int n_grp = 0;
+    constexpr int UE = 8;
+    int lo = 0;                                         /* the range that holds this lane's entry: advances monotonically */
+    for (int base = 0; base < total; base += 32 * UE) {
         uint2 e[UE];
 #pragma unroll
         for (int u = 0; u < UE; u++) {
-            const int g = base + u * kRrThreads + t;
+            const int g = base + u * 32 + lane;
             e[u] = make_uint2(0x7fffffffu, 0x7f800000u);
             if (g < total) {
-                int lo = 0, hi = n_ranges;              /* the range that holds entry g: last r with s_pre[r] <= g */
-                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_pre[mid] <= g) lo = mid; else hi = mid; }
+                while (s_pre[lo + 1] <= g) lo++;
                 e[u] = __ldcg(hq + ((size_t)qi * n_ranges + lo) * (size_t)kQueueCap + (g - s_pre[lo]));
             }
         }
 #pragma unroll
         for (int u = 0; u < UE; u++) {
             const float gm = __uint_as_float(e[u].y);
-            if (gm <= cut && (int)e[u].x < n_db) {
-                const int pos = atomicAdd(&s_count, 1);
-                if (pos < kMaxGroups) { s_key[pos] = (int)e[u].x; s_g[pos] = gm; }
-            }
+            const bool keep = gm <= cut && (int)e[u].x < n_db;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            const int pos = n_grp + __popc(m & lt_mask);
+            if (keep && pos < kMaxGroups) { s_key[pos] = (int)e[u].x; s_g[pos] = gm; }
+            n_grp += __popc(m);
         }
     }
-    __syncthreads();
-    bool overflow = s_overflow != 0;
-    int n_grp = s_count;
     if (n_grp > kMaxGroups) { overflow = true; n_grp = kMaxGroups; }
+    __syncwarp();
+    if (dev_flags & 256) { if (lane == 0) out_ids[(size_t)qi * K] = n_grp; return; }
     float qn = 0.0f;
     for (int d = 0; d < R; d++) qn = fmaf(s_q[d], s_q[d], qn);
-    const float sn = sqrtf(qn) + sqrtf(__ldg(kn2max));
+    const float sn = sqrtf(qn) + sqrtf(knmax);
     const float eps0 = 3.0517578125e-05f * sn * sn;                 /* 2^-15 (|q| + |k|max)^2 */
     /* a certified top-K lies wholly below cut + |q|^2 (see below): keys at or above it need not enter the selection */
     const float d_lim = cut < inf ? cut + qn : inf;
     float worst_err = 0.0f;
-    constexpr int UK = R <= 20 ? 2 : 1;                 /* key rows in flight per thread (64 registers: four CTAs per SM) */
-    for (int base = 0; base < n_grp * 8; base += kRrThreads * UK) {
+    int n_sel = 0;
+    constexpr int UK = R <= 20 ? 4 : 2;                 /* key rows in flight per lane */
+    for (int base = 0; base < n_grp * 8; base += 32 * UK) {
         float4 kv[UK][R / 4];
         int id[UK];
 #pragma unroll
         for (int u = 0; u < UK; u++) {
-            const int c = base + u * kRrThreads + t;
+            const int c = base + u * 32 + lane;
             id[u] = c < n_grp * 8 ? s_key[c >> 3] + (c & 7) : n_db;
             if (id[u] < n_db) {
 #pragma unroll
@@ -636,18 +655,20 @@ __global__ void __launch_bounds__(kRrThreads, 4) knn_rerank_kernel(const float* 
         }
 #pragma unroll
         for (int u = 0; u < UK; u++) {
+            float d = inf;
             if (id[u] < n_db) {
-                const int c = base + u * kRrThreads + t;
-                float d = exact_d2<METRIC, R>(s_q, kv[u]);
+                const int c = base + u * 32 + lane;
+                d = exact_d2<METRIC, R>(s_q, kv[u]);
                 /* the prefilter must not have OVER-estimated a key by more than eps (that is what the certificate relies on) */
                 if (err_probe) worst_err = fmaxf(worst_err, (s_g[c >> 3] - (d - qn)) / eps0);
                 if (METRIC == 1 && !(d > FLT_EPSILON)) d = inf;          /* libnabo self-match rule */
                 if (!(d < (METRIC == 0 ? FLT_MAX : inf))) d = inf;       /* never accepted by the trees */
-                if (d < d_lim) {
-                    const int pos = atomicAdd(&s_nsel, 1);
-                    if (pos < kMaxSel) { s_d[pos] = d; s_id[pos] = id[u] * id_mul + id_add; }
-                }
             }
+            const bool keep = d < d_lim;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            const int pos = n_sel + __popc(m & lt_mask);
+            if (keep && pos < kMaxSel) { s_d[pos] = d; s_id[pos] = id[u] * id_mul + id_add; }
+            n_sel += __popc(m);
         }
     }
     if (err_probe) {
@@ -655,30 +676,25 @@ __global__ void __launch_bounds__(kRrThreads, 4) knn_rerank_kernel(const float* 
         for (int off = 16; off > 0; off >>= 1) worst_err = fmaxf(worst_err, __shfl_xor_sync(0xffffffffu, worst_err, off));
         if (lane == 0 && worst_err > 0.0f) atomicMax(reinterpret_cast<int*>(err_probe), __float_as_int(worst_err));   /* non-negative floats order as ints */
     }
-    __syncthreads();
-    if (warp != 0) return;
-    int n_surv = s_nsel;
+    int n_surv = n_sel;
     if (n_surv > kMaxSel) { overflow = true; n_surv = kMaxSel; }
-    /* K rounds: smallest (d2, id) strictly after the previous pick */
-    float pd = -1.0f; int pi = -1; float dK = 0.0f; int found = 0;
-    for (int r = 0; r < K; r++) {
-        float bd = inf; int bi = 0x7fffffff;
-        for (int c = lane; c < n_surv; c += 32) {
-            const float d = s_d[c];
-            const int id = s_id[c];
-            if (d < pd || (d == pd && id <= pi)) continue;
-            if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; }
+    __syncwarp();
+    if (dev_flags & 512) { if (lane == 0) out_ids[(size_t)qi * K] = n_surv; return; }
+    /* Selection by rank: (d2, id) pairs are distinct, so the number of pairs below a pair is its place in the result. Every
+     * lane ranks its own entries against all of them (broadcast reads); no round depends on the one before. */
+    float dK = 0.0f;
+    const int found = min(K, n_surv);
+    for (int mine = lane; mine < n_surv; mine += 32) {
+        const float d = s_d[mine]; const int id = s_id[mine];
+        int rank = 0;
+        for (int c = 0; c < n_surv; c++) {
+            const float od = s_d[c]; const int oi = s_id[c];
+            rank += (od < d || (od == d && oi < id)) ? 1 : 0;
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const float od = __shfl_xor_sync(0xffffffffu, bd, off); const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-        }
-        const bool ok = bi != 0x7fffffff;
-        if (lane == 0) { out_ids[(size_t)qi * K + r] = ok ? bi : -1; out_d2[(size_t)qi * K + r] = ok ? bd : FLT_MAX; }
-        if (ok) { pd = bd; pi = bi; dK = bd; found++; }
-        else break;
+        if (rank < K) { out_ids[(size_t)qi * K + rank] = id; out_d2[(size_t)qi * K + rank] = d; }
+        if (rank == found - 1) dK = d;
     }
+    dK = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(dK)));       /* distances are >= 0: their bit patterns order as ints */
     if (lane == 0) {
         for (int r = found; r < K; r++) { out_ids[(size_t)qi * K + r] = -1; out_d2[(size_t)qi * K + r] = FLT_MAX; }
         bool certified = !overflow;
@@ -688,6 +704,10 @@ __global__ void __launch_bounds__(kRrThreads, 4) knn_rerank_kernel(const float* 
             certified = certified && (found == K) && (dK + eps < cut + qn);
         }
         if (!certified) fail_list[atomicAdd(fail_count, 1)] = q_off + qi;
+        if (err_probe) {                                            /* developer counters: list sizes */
+            int* sz = reinterpret_cast<int*>(err_probe) + 6;
+            atomicAdd(sz + 0, total); atomicAdd(sz + 1, n_grp); atomicAdd(sz + 2, n_sel); atomicAdd(sz + 3, 1); atomicMax(sz + 4, n_grp); atomicMax(sz + 5, total);
+        }
         if (!certified && err_probe) {                              /* developer counters: why */
             int* why = reinterpret_cast<int*>(err_probe) + 1;
             if (overflow) atomicAdd(why + 0, 1);
@@ -745,7 +765,8 @@ static cudaError_t launch_tc(const float* qkeys, int Q, const unsigned char* img
     const int dev_flags = getenv("SCL_TC_FLAGS") ? atoi(getenv("SCL_TC_FLAGS")) : 0;
     const int nb = groups * n_ranges;
     if (want_times) { cudaMalloc(&times, (size_t)nb * 16 * sizeof(long long)); cudaMemsetAsync(times, 0, (size_t)nb * 128, stream); }
-    if (want_times) knn_tc_kernel<R, true><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, times, slots, hq, hq_cnt, dbg, dev_flags);
+    if (dev_flags & 64) {}
+    else if (want_times) knn_tc_kernel<R, true><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, times, slots, hq, hq_cnt, dbg, dev_flags);
     else knn_tc_kernel<R, false><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, nullptr, slots, hq, hq_cnt, dbg, dev_flags);
     if (want_times) {
         std::vector<long long> h((size_t)nb * 16);
@@ -783,17 +804,19 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
         else err = launch_tc<40>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint2*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), stream);
         if (err != cudaSuccess) return err;
 #define SCL_RERANK(M, RR)                                                                                                              \
-    knn_rerank_kernel<M, RR><<<Qc, kRrThreads, 0, stream>>>(qk, Qc, keys, K, n_ranges, n_db, reinterpret_cast<const uint2*>(ws.hq), ws.hq_cnt,   \
+    knn_rerank_kernel<M, RR><<<(Qc + kRrWarps - 1) / kRrWarps, 32 * kRrWarps, 0, stream>>>(qk, Qc, keys, K, n_ranges, n_db, reinterpret_cast<const uint2*>(ws.hq), ws.hq_cnt,   \
                                                             ws.slots, kn2max, id_mul, id_add, out_ids + (size_t)q0 * K, out_d2 + (size_t)q0 * K, \
-                                                            q0, fail_list, fail_count, ws.err_probe)
-        if (R == 20) { if (metric == 0) SCL_RERANK(0, 20); else SCL_RERANK(1, 20); }
+                                                            q0, fail_list, fail_count, ws.err_probe, dev_flags)
+        const int dev_flags = getenv("SCL_TC_FLAGS") ? atoi(getenv("SCL_TC_FLAGS")) : 0;     /* developer aid: timing experiments */
+        if (dev_flags & 16) {}
+        else if (R == 20) { if (metric == 0) SCL_RERANK(0, 20); else SCL_RERANK(1, 20); }
         else { if (metric == 0) SCL_RERANK(0, 40); else SCL_RERANK(1, 40); }
 #undef SCL_RERANK
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;
     }
     if (ws.err_probe && getenv("SCL_TC_DEBUG")) {                   /* developer aid */
-        int h[6];
+        int h[12];
         cudaStreamSynchronize(stream);
         {
             const int Qc = Q < max_b ? Q : max_b;
@@ -808,6 +831,8 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
         cudaMemcpy(h, ws.err_probe, sizeof(h), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[tc Q %d n_db %d] worst |score error| / eps %.3f | uncertified so far: queue overflow %d, fewer than K survivors %d, certificate %d (survivor list full %d) | start-up waits timed out (warps) %d\n",
                 Q, n_db, *reinterpret_cast<float*>(&h[0]), h[1], h[2], h[3], h[4], h[5]);
+        if (h[9] > 0) fprintf(stderr, "[tc re-rank, averages over %d queries] queue entries %.0f (largest %d), surviving groups %.1f (largest %d), keys in the selection %.1f\n",
+                              h[9], (double)h[6] / h[9], h[11], (double)h[7] / h[9], h[10], (double)h[8] / h[9]);
     }
     return cudaSuccess;
 }
