@@ -493,7 +493,12 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                 const uint32_t bs = b_base + (uint32_t)b * C::TILE_B;
 #pragma unroll
                 for (int qt = 0; qt < 2; qt++) {
-                    scl_mbar_wait(&tempty[qt], (uint32_t)((it & 1) ^ 1));      /* accumulator drained by its four epilogue warps */
+                    /* accumulator drained by its four epilogue warps? This one thread SPINS (a sleeping try_wait wakes up late:
+                     * measured 5 us per batch); a bound turns a protocol bug into a trap instead of a hung GPU */
+                    if (!mbar_test(&tempty[qt], (uint32_t)((it & 1) ^ 1))) {
+                        const long long w0 = clock64();
+                        while (!mbar_test(&tempty[qt], (uint32_t)((it & 1) ^ 1))) { if (clock64() - w0 > (4ll << 30)) __trap(); }
+                    }
                     tc_fence_after();
                     const uint32_t d = tmem_base + (uint32_t)(qt * kNT);
                     const uint32_t as = a_base + (uint32_t)qt * C::TILE_A;
@@ -680,21 +685,27 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
     if (n_surv > kMaxSel) { overflow = true; n_surv = kMaxSel; }
     __syncwarp();
     if (dev_flags & 512) { if (lane == 0) out_ids[(size_t)qi * K] = n_surv; return; }
-    /* Selection by rank: (d2, id) pairs are distinct, so the number of pairs below a pair is its place in the result. Every
-     * lane ranks its own entries against all of them (broadcast reads); no round depends on the one before. */
-    float dK = 0.0f;
-    const int found = min(K, n_surv);
-    for (int mine = lane; mine < n_surv; mine += 32) {
-        const float d = s_d[mine]; const int id = s_id[mine];
-        int rank = 0;
-        for (int c = 0; c < n_surv; c++) {
-            const float od = s_d[c]; const int oi = s_id[c];
-            rank += (od < d || (od == d && oi < id)) ? 1 : 0;
+    /* K rounds: smallest (d2, id) strictly after the previous pick (a rank-by-counting selection measured slower: its cost
+     * grows with the square of the list length, and the longest list of the batch sets the kernel's duration) */
+    float pd = -1.0f; int pi = -1; float dK = 0.0f; int found = 0;
+    for (int r = 0; r < K; r++) {
+        float bd = inf; int bi = 0x7fffffff;
+        for (int c = lane; c < n_surv; c += 32) {
+            const float d = s_d[c];
+            const int id = s_id[c];
+            if (d < pd || (d == pd && id <= pi)) continue;
+            if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; }
         }
-        if (rank < K) { out_ids[(size_t)qi * K + rank] = id; out_d2[(size_t)qi * K + rank] = d; }
-        if (rank == found - 1) dK = d;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, bd, off); const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        const bool ok = bi != 0x7fffffff;
+        if (lane == 0) { out_ids[(size_t)qi * K + r] = ok ? bi : -1; out_d2[(size_t)qi * K + r] = ok ? bd : FLT_MAX; }
+        if (ok) { pd = bd; pi = bi; dK = bd; found++; }
+        else break;
     }
-    dK = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(dK)));       /* distances are >= 0: their bit patterns order as ints */
     if (lane == 0) {
         for (int r = found; r < K; r++) { out_ids[(size_t)qi * K + r] = -1; out_d2[(size_t)qi * K + r] = FLT_MAX; }
         bool certified = !overflow;
