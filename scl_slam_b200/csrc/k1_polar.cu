@@ -141,30 +141,41 @@ struct PolarParams {
     int n_tab;
 };
 
-__device__ __forceinline__ int count_le(const float* __restrict__ t, int n, float v)
+// Shared-memory image of the tables: every table is padded with NaN (never <= anything) to a power of two minus one, so
+// that the search is a fixed number of steps without a branch.
+constexpr int kRingPad = 64, kSecPad = 32;
+struct PolarSmem {
+    float ring[kRingPad];
+    float sec[4][kSecPad];
+    int4 qd[4];            /* per quadrant: sector base, direction, -, - */
+};
+
+template <int TOP>       /* TOP = half the padded size: 32 -> 63 entries, 16 -> 31 entries */
+__device__ __forceinline__ int count_le_fixed(const float* __restrict__ t, float v)
 {
-    int lo = 0, hi = n;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (t[mid] <= v) lo = mid + 1; else hi = mid; }
-    return lo;
+    int pos = 0;
+#pragma unroll
+    for (int step = TOP; step > 0; step >>= 1) pos += (t[pos + step - 1] <= v) ? step : 0;
+    return pos;
 }
 
-// Per-point bin: one float sqrt, one float division, two table searches. stab = shared-memory copy of the table.
-__device__ __forceinline__ bool polar_bin(const PolarParams& p, const float* __restrict__ stab, float x, float y, float z,
+// Per-point bin: one float sqrt, one float division, two fixed-depth table searches, no divergent branch.
+// The ratio handed to the sector table is the one xy2theta hands to atan in each quadrant (y/x, y/-x, y/x, -y/x).
+__device__ __forceinline__ bool polar_bin(const PolarParams& p, const PolarSmem& ps, float x, float y, float z, double lidar_height,
                                           int& ring, int& sector, float& zf)
 {
-    zf = __double2float_rn(__dadd_rn((double)z, p.lidar_height));                  /* :1422 */
+    zf = __double2float_rn(__dadd_rn((double)z, lidar_height));                    /* :1422 */
     const float azim_range = __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))); /* :1425 */
-    int qd; float t;
-    if ((x >= 0) & (y >= 0))      { qd = 0; t = __fdiv_rn(y, x); }
-    else if ((x < 0) & (y >= 0))  { qd = 1; t = __fdiv_rn(y, -x); }
-    else if ((x < 0) & (y < 0))   { qd = 2; t = __fdiv_rn(y, x); }
-    else if ((x >= 0) & (y < 0))  { qd = 3; t = __fdiv_rn(-y, x); }
-    else return false;                          /* NaN coordinate: UB in the reference, dropped (Q9) */
-    if (azim_range > p.bt.r_max) return false;  /* double(r) > max_radius (:1429) */
-    ring = 1 + count_le(stab, p.bt.n_ring, azim_range);
-    if (t != t) sector = 1;                     /* (0,0): theta = NaN -> int(ceil(NaN)) = INT_MIN -> clamped to 1 */
-    else sector = p.bt.sec_base[qd] + p.bt.sec_dir[qd] * count_le(stab + p.bt.sec_off[qd], p.bt.n_sec[qd], t);
-    return true;
+    const bool xn = x < 0, yn = y < 0;
+    const bool valid = (xn | (x >= 0)) & (yn | (y >= 0));      /* a NaN coordinate is UB in the reference: dropped (Q9) */
+    const int qd = xn ? (yn ? 2 : 1) : (yn ? 3 : 0);
+    const float num = qd == 3 ? -y : y, den = qd == 1 ? -x : x;
+    const float t = __fdiv_rn(num, den);
+    ring = 1 + count_le_fixed<kRingPad / 2>(ps.ring, azim_range);
+    const int4 q = ps.qd[qd];
+    const int cnt = count_le_fixed<kSecPad / 2>(ps.sec[qd], t);
+    sector = (t != t) ? 1 : q.x + q.y * cnt;    /* (0,0): theta = NaN -> int(ceil(NaN)) = INT_MIN -> clamped to 1 */
+    return valid & !(azim_range > p.bt.r_max);  /* double(r) > max_radius (:1429) */
 }
 
 __device__ __forceinline__ void load_xyz(const unsigned char* base, size_t i, int stride, bool vec4, float& x, float& y, float& z)
@@ -188,11 +199,27 @@ __global__ void __launch_bounds__(256) polar_bin_kernel(
     float* __restrict__ out_desc /* [scans][R*S] */, float* __restrict__ out_keys /* [scans][R] */,
     float* __restrict__ out_knorm /* [scans] */, float* __restrict__ kn2max, int* __restrict__ out_ring, int* __restrict__ out_sector)
 {
-    extern __shared__ uint32_t sbins[];   /* R*S keys, R*S + R floats for the epilogue, then the bin tables */
+    extern __shared__ uint32_t sbins[];   /* R*S keys, then R*S + R floats for the epilogue */
     __shared__ int s_last;
+    __shared__ PolarSmem ps;
     const int RS = p.R * p.S;
-    float* stab = reinterpret_cast<float*>(sbins + 2 * RS + p.R);
-    for (int i = threadIdx.x; i < p.n_tab; i += blockDim.x) stab[i] = __ldg(p.tab + i);
+    {
+        const float nan = __int_as_float(0x7fc00000);
+        for (int i = threadIdx.x; i < kRingPad; i += blockDim.x) ps.ring[i] = i < p.bt.n_ring ? __ldg(p.tab + i) : nan;
+        for (int i = threadIdx.x; i < 4 * kSecPad; i += blockDim.x) {
+            const int qd = i / kSecPad, k = i % kSecPad;
+            const int n = qd == 0 ? p.bt.n_sec[0] : qd == 1 ? p.bt.n_sec[1] : qd == 2 ? p.bt.n_sec[2] : p.bt.n_sec[3];
+            const int off = qd == 0 ? p.bt.sec_off[0] : qd == 1 ? p.bt.sec_off[1] : qd == 2 ? p.bt.sec_off[2] : p.bt.sec_off[3];
+            ps.sec[qd][k] = k < n ? __ldg(p.tab + off + k) : nan;
+        }
+        if (threadIdx.x < 4) {
+            const int qd = threadIdx.x;
+            const int base = qd == 0 ? p.bt.sec_base[0] : qd == 1 ? p.bt.sec_base[1] : qd == 2 ? p.bt.sec_base[2] : p.bt.sec_base[3];
+            const int dir = qd == 0 ? p.bt.sec_dir[0] : qd == 1 ? p.bt.sec_dir[1] : qd == 2 ? p.bt.sec_dir[2] : p.bt.sec_dir[3];
+            ps.qd[qd] = make_int4(base, dir, 0, 0);
+        }
+    }
+    const double lidar_height = p.lidar_height;
     const int scan = blockIdx.y;
     const int p0 = offsets[scan], p1 = offsets[scan + 1];
     const uint32_t key_none = scl_float_key(kNoPoint);
@@ -213,7 +240,7 @@ __global__ void __launch_bounds__(256) polar_bin_kernel(
         for (int j = 0; j < kPointsPerThread; j++) {
             const int i = base + j * blockDim.x + threadIdx.x;
             int ring = 0, sector = 0; float zf;
-            bool ok = (i < p1) && polar_bin(p, stab, x[j], y[j], z[j], ring, sector, zf);
+            bool ok = polar_bin(p, ps, x[j], y[j], z[j], lidar_height, ring, sector, zf) && (i < p1);
             if (out_ring != nullptr && i < p1) { out_ring[i] = ok ? ring : 0; out_sector[i] = ok ? sector : 0; }
             ok = ok && !(zf != zf);                     /* desc < NaN is false: NaN heights never win (:1438) */
             const int bin = ok ? (ring - 1) * p.S + (sector - 1) : -1;
@@ -385,7 +412,9 @@ cudaError_t scl_launch_polar(const void* pts_dev, const int* offsets_dev, int n_
     const int want = (4 * SCL_NUM_SMS + n_scans - 1) / n_scans;
     if (chunks > want) chunks = want;
     const int vec4 = (stride_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(pts_dev) & 15) == 0);
-    const size_t smem = (size_t)R * S * 8 + (size_t)R * 4 + (size_t)p.n_tab * 4;
+    if (p.bt.n_ring > kRingPad - 1 || p.bt.n_sec[0] > kSecPad - 1 || p.bt.n_sec[1] > kSecPad - 1 || p.bt.n_sec[2] > kSecPad - 1 ||
+        p.bt.n_sec[3] > kSecPad - 1) return cudaErrorNotSupported;       /* up to 64 rings x 124 sectors */
+    const size_t smem = (size_t)R * S * 8 + (size_t)R * 4;
     dim3 grid(chunks, n_scans);
     polar_bin_kernel<kPPT><<<grid, 256, smem, stream>>>(static_cast<const unsigned char*>(pts_dev), offsets_dev, stride_bytes, vec4, p,
                                                        gbins, tickets, out_desc, out_keys, out_knorm, kn2max, out_ring, out_sector);

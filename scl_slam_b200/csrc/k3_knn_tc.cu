@@ -58,8 +58,10 @@
 
 namespace {
 
-constexpr int kKPrime = 12;        /* K': the number of distinct keys that back a query's threshold; K <= K' - 2. The bound is the LARGEST of K'
-                                    * slot minima, which about K' H(K') keys undercut (37 at K' = 12, 54 at 16): smaller is tighter. Multiple of 4. */
+constexpr int kKPrime = 16;        /* slots per query (stride). K', the number of distinct keys that back a query's threshold, is chosen per
+                                    * launch: K <= K' - 2. The bound is the LARGEST of K' slot minima, which about K' H(K') keys undercut
+                                    * (37 at K' = 12, 54 at 16): smaller is tighter, so K <= 10 (the reference's default) runs with K' = 12. */
+__host__ __device__ constexpr int kprime_for(int K) { return K <= 10 ? 12 : 16; }
 constexpr int kQueueCap = 128;               /* hit queue per (query, range): entries of 2 words (first key of an 8-key group, its best score); ~12 are used; a tile adds at most 32 */
 constexpr int kEpiThreads = 256;   /* 8 epilogue warps: query tile = (warp-4)/4, TMEM lane quadrant = warp%4 */
 constexpr int kThreads = 384;
@@ -232,7 +234,8 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     long long* __restrict__ times /* null, or [grid][16] developer counters (SCL_TC_TIMES=1) */,
     int* __restrict__ slots /* [Q][K'] range minima by range % K' (ordered-int image) */,
     uint2* __restrict__ hq /* [Q][n_ranges][kQueueCap] hit queues: (first key of the group, its best score) */, int* __restrict__ hq_cnt /* [Q][n_ranges] */,
-    int* __restrict__ dbg /* null, or developer counters */, int dev_flags /* SCL_TC_FLAGS: timing experiments, results are then wrong */)
+    int* __restrict__ dbg /* null, or developer counters */, int dev_flags /* SCL_TC_FLAGS: timing experiments, results are then wrong */,
+    int kp /* K' of this launch: 12 or 16 */)
 {
     using C = TcCfg<R>;
     constexpr int NS = C::NSTAGE;
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         int n_slow = 0;                                 /* developer counter (SCL_TC_TIMES) */
         float thr = (live && !(dev_flags & 1)) ? kThrInit : -kThrInit;        /* rows beyond Q never queue anything */
         float published = kThrInit;
-        int* my_slot = slots + (size_t)(live ? qi : 0) * kKPrime + (range % kKPrime);
+        int* my_slot = slots + (size_t)(live ? qi : 0) * kKPrime + (range % kp);
         volatile int* my_sthr = sthr + qt * 128 + row;
         uint2* my_q = hq + ((size_t)(live ? qi : 0) * n_ranges + range) * (size_t)kQueueCap;
         // The four epilogue warps of a query tile are coupled through the accumulator hand-off (it is refilled only when all
@@ -355,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
              * so the service warps deliver a union bound (a few microseconds), and the normal pass starts with it. */
             scl_mbar_wait(&tfull[qt], 0);
             tc_fence_after();
-            if (n_service >= kKPrime && (range + 1) * kNT <= key_hi && !(dev_flags & 2)) {
+            if (n_service >= kp && (range + 1) * kNT <= key_hi && !(dev_flags & 2)) {
                 float m0 = kThrInit;
 #pragma unroll 1
                 for (int c = 0; c < kNT / 32; c++) {
@@ -458,7 +461,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                     for (int i = 0; i < kKPrime / 4; i++) v[i] = __ldcg(p + i);
                     int m = (int)0x80000000;
 #pragma unroll
-                    for (int i = 0; i < kKPrime / 4; i++) m = max(m, max(max(v[i].x, v[i].y), max(v[i].z, v[i].w)));
+                    for (int i = 0; i < kKPrime / 4; i++) if (4 * i < kp) m = max(m, max(max(v[i].x, v[i].y), max(v[i].z, v[i].w)));
                     if (m < 0x7f000000) sthr[j] = m;     /* all K' slots filled: a valid bound */
                 }
             }
@@ -557,7 +560,7 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
                                                           int n_ranges, int n_db, const uint2* __restrict__ hq, const int* __restrict__ hq_cnt,
                                                           const int* __restrict__ slots, const float* __restrict__ kn2max, int id_mul, int id_add,
                                                           int32_t* __restrict__ out_ids, float* __restrict__ out_d2, int q_off,
-                                                          int32_t* __restrict__ fail_list, int* __restrict__ fail_count, float* __restrict__ err_probe, int dev_flags)
+                                                          int32_t* __restrict__ fail_list, int* __restrict__ fail_count, float* __restrict__ err_probe, int dev_flags, int kp)
 {
     __shared__ int sh_key[kRrWarps][kMaxGroups];        /* first key of the group */
     __shared__ float sh_g[kRrWarps][kMaxGroups];        /* its best prefilter score */
@@ -573,7 +576,7 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
     const unsigned lt_mask = (1u << lane) - 1u;
     const float inf = __int_as_float(0x7f800000);
     /* first trip: slots, the query's key, the queue counts, the largest key norm: all independent */
-    int gt = lane < kKPrime ? __ldg(slots + (size_t)qi * kKPrime + lane) : (int)0x80000000;
+    int gt = lane < kp ? __ldg(slots + (size_t)qi * kKPrime + lane) : (int)0x80000000;
     const float qv = lane < R ? __ldg(qkeys + (size_t)qi * R + lane) : 0.0f;
     const float qv2 = (R > 32 && lane + 32 < R) ? __ldg(qkeys + (size_t)qi * R + lane + 32) : 0.0f;
     const float knmax = __ldg(kn2max);
@@ -760,7 +763,7 @@ cudaError_t scl_launch_key_image(const float* keys, const float* knorm, int k_lo
 
 template <int R>
 static cudaError_t launch_tc(const float* qkeys, int Q, const unsigned char* img, int n_db, int n_ranges, int* slots,
-                              uint2* hq, int* hq_cnt, int* dbg, cudaStream_t stream)
+                              uint2* hq, int* hq_cnt, int* dbg, int kp, cudaStream_t stream)
 {
     using C = TcCfg<R>;
     static bool attr = false;
@@ -777,8 +780,8 @@ static cudaError_t launch_tc(const float* qkeys, int Q, const unsigned char* img
     const int nb = groups * n_ranges;
     if (want_times) { cudaMalloc(&times, (size_t)nb * 16 * sizeof(long long)); cudaMemsetAsync(times, 0, (size_t)nb * 128, stream); }
     if (dev_flags & 64) {}
-    else if (want_times) knn_tc_kernel<R, true><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, times, slots, hq, hq_cnt, dbg, dev_flags);
-    else knn_tc_kernel<R, false><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, nullptr, slots, hq, hq_cnt, dbg, dev_flags);
+    else if (want_times) knn_tc_kernel<R, true><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, times, slots, hq, hq_cnt, dbg, dev_flags, kp);
+    else knn_tc_kernel<R, false><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, nullptr, slots, hq, hq_cnt, dbg, dev_flags, kp);
     if (want_times) {
         std::vector<long long> h((size_t)nb * 16);
         cudaStreamSynchronize(stream);
@@ -811,13 +814,13 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
         err = cudaMemsetAsync(ws.slots, 0x7f, (size_t)Qc * kKPrime * 4, stream);     /* 3.39e38: "no key yet" */
         if (err != cudaSuccess) return err;
         const float* qk = qkeys + (size_t)q0 * R;
-        if (R == 20) err = launch_tc<20>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint2*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), stream);
-        else err = launch_tc<40>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint2*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), stream);
+        if (R == 20) err = launch_tc<20>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint2*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), kprime_for(K), stream);
+        else err = launch_tc<40>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint2*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), kprime_for(K), stream);
         if (err != cudaSuccess) return err;
 #define SCL_RERANK(M, RR)                                                                                                              \
     knn_rerank_kernel<M, RR><<<(Qc + kRrWarps - 1) / kRrWarps, 32 * kRrWarps, 0, stream>>>(qk, Qc, keys, K, n_ranges, n_db, reinterpret_cast<const uint2*>(ws.hq), ws.hq_cnt,   \
                                                             ws.slots, kn2max, id_mul, id_add, out_ids + (size_t)q0 * K, out_d2 + (size_t)q0 * K, \
-                                                            q0, fail_list, fail_count, ws.err_probe, dev_flags)
+                                                            q0, fail_list, fail_count, ws.err_probe, dev_flags, kprime_for(K))
         const int dev_flags = getenv("SCL_TC_FLAGS") ? atoi(getenv("SCL_TC_FLAGS")) : 0;     /* developer aid: timing experiments */
         if (dev_flags & 16) {}
         else if (R == 20) { if (metric == 0) SCL_RERANK(0, 20); else SCL_RERANK(1, 20); }
