@@ -300,8 +300,11 @@ def run_ours(args):
                  "algorithmic": {"bytes": alg_bytes, "flops": alg_flops, "t_hbm_us": t_hbm * 1e6, "t_tensor_us": t_tc * 1e6},
                  "hbm_view": {"achieved_gbs": alg_bytes / t_meas / 1e9 if t_meas > 0 else None, "peak_gbs": pk["hbm"]},
                  "note": "flops are the algorithmic 2*R*Q*N against the measured bf16 peak; the kernel issues 3.2x that (three bf16 "
-                         "products per pair, K = 64 columns for R = 20) to keep FP32-level accuracy, and is bound by the epilogue "
-                         "(TMEM read-out + min tree of Q*N scores), not by the tensor pipe"})
+                         "products per pair, K = 64 columns for R = 20) to keep FP32-level accuracy. Per 256x256 score tile an SM needs "
+                         "1024 cycles of tensor pipe (M=128,N=256 tcgen05.mma at its floor) and >= 768 cycles of TMEM read-out "
+                         "(every score is read once: 256 KB at 64-85 B/clk per quadrant); ncu: tensor pipe 56 % active in knn_tc_kernel. "
+                         "traffic = dram read+write of knn_tc_kernel (the pre-split BF16 key image is 128 B/key, 1.6x the 80 B/key of "
+                         "the algorithmic count) + knn_rerank_kernel"})
     line = {
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+f64",
