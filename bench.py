@@ -142,6 +142,8 @@ def run_ours(args):
     if rank == 0:
         sampler.start()                      # nvidia-smi needs ~1 s to produce its first line: start it early
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # the version banner goes to stdout, where the one JSON line belongs
         dist.init_process_group("nccl", device_id=dev)
     build.build()
     n_db = args.n_db
@@ -178,7 +180,7 @@ def run_ours(args):
     # ring_key, knn_tc, knn_rerank, knn_exact (fallback list), knn_merge, ids_to_local, scdist (+ merge_topk, combine_owned)
     launches_per_step = 7 + (2 if world > 1 else 0)
 
-    def step():
+    def step(q_dev=q_dev):
         if world == 1:
             e.query_batch_dev(q_dev, None, Q, K, n_local, 0, local)
             return
@@ -226,7 +228,8 @@ def run_ours(args):
     # The pipelined form (scl_query_batch_submit / _wait, at most two batches in flight) is what a caller draining a
     # backlog of loop queries uses: the H2D copy of step i+1 overlaps the kernels of step i. The one-call synchronous
     # form (scl_query_batch) is timed too and reported beside it.
-    q_host = q_dev.cpu().pin_memory().numpy()
+    q_pin = q_dev.cpu().pin_memory()
+    q_host = q_pin.numpy()
     pinned = [dict(best_id=torch.empty(Q, dtype=torch.int32).pin_memory(), best_dist=torch.empty(Q, dtype=torch.float64).pin_memory(),
                    best_shift=torch.empty(Q, dtype=torch.int32).pin_memory()) for _ in range(2)]
     res2 = [{k: v.numpy() for k, v in p.items()} for p in pinned]
@@ -266,6 +269,33 @@ def run_ours(args):
                "h2d_bytes_per_step": int(q_host.nbytes), "d2h_bytes_per_step": int(sum(v.nbytes for v in res.values())),
                "api": "scl_query_batch_submit / scl_query_batch_wait, two batches in flight",
                "one_call_synchronous": {"value": Q / (sync_ms * 1e-3), "ms_per_step": sync_ms, "api": "scl_query_batch"}}
+    if world > 1:
+        # N > 1: every rank copies the step's queries from pinned host memory, runs the sharded step with its two
+        # exchanges, and reads the merged winners back; wall clock between barriers, max over ranks.
+        q_in = torch.empty_like(q_dev)
+        outp = pinned[0]
+
+        def e2e_sharded():
+            q_in.copy_(q_pin, non_blocking=True)
+            step(q_in)
+            for k in ("best_id", "best_dist", "best_shift"):
+                outp[k].copy_(merged[k], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        for _ in range(3):
+            e2e_sharded()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_sharded()
+        barrier()
+        t = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        assert np.array_equal(outp["best_id"].numpy(), merged["best_id"].cpu().numpy())
+        e2e = {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(q_host.nbytes), "d2h_bytes_per_step": int(sum(v.nbytes for v in res.values())),
+               "api": "per rank: pinned host queries -> scl_knn_batch_dev, all-gather, scl_merge_topk_dev, scl_scdist_owned_dev, "
+                      "all-gather, scl_combine_owned_dev -> winners to pinned host memory; synchronous steps"}
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- parity spot check on what was just measured (size-independent property of D3) ----
@@ -318,7 +348,7 @@ def run_ours(args):
         "knn": e.knn_stats(),
     }
     if world == 1:
-        line["descriptors"] = descriptor_bench(engine, dev, pk)
+        line["descriptors"] = descriptor_bench(engine, dev, pk, cpu=not args.no_cpu_baseline)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(e, n_local, q_dev, final, sample=args.cpu_sample)
     print(json.dumps(line))
@@ -326,7 +356,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def descriptor_bench(engine, dev, pk, batch=64, iters=10):
+def descriptor_bench(engine, dev, pk, batch=64, iters=10, cpu=True):
     """Secondary metric of BASELINE.json ("descriptors/sec; % HBM roofline"): K1+K2 on a batch of HDL-64-shaped
     scans (BASELINE configs[1] shape, ~113k returns of 120k rays, pcl::PointXYZI layout, 32 B/point)."""
     from scl_slam_b200 import synth
@@ -359,7 +389,25 @@ def descriptor_bench(engine, dev, pk, batch=64, iters=10):
     e2e_ms = (time.perf_counter() - t0) * 1e3 / iters
     read_bytes = batch * P * 32
     alg_bytes = batch * (16 * P + 4 * R * S + 4 * R + 4 * S)          # SURVEY.md §8d per-scan figure (packed float4 points)
-    return {"value": batch / (ms * 1e-3), "unit": "descriptors/s", "points_per_scan": P, "scans_per_launch": batch, "ms_per_launch": ms,
+    # K6: pcl::VoxelGrid of one scan at the reference's 0.4 m leaf, through the host-buffer call
+    # (H2D + kernels + D2H inside), beside the oracle restatement on one host core and checked against it bit for bit
+    for _ in range(2):
+        vg = e.voxel_grid(sc, 0.4)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        vg = e.voxel_grid(sc, 0.4)
+    vg_ms = (time.perf_counter() - t0) * 1e3 / iters
+    voxel = {"value": P / (vg_ms * 1e-3), "unit": "points/s", "api": "scl_voxel_grid (host buffers in and out)", "points": P, "leaves": int(len(vg)),
+             "ms_per_scan": vg_ms}
+    if cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+        xyzi = np.ascontiguousarray(np.concatenate([sc[:, :3], sc[:, 4:5]], 1))
+        t0 = time.perf_counter()
+        vg_cpu = oracle_lib.voxel_grid_pcl(xyzi, 0.4)
+        voxel["cpu_baseline"] = {"ms_per_scan": (time.perf_counter() - t0) * 1e3, "cores": 1, "kind": "port"}
+        voxel["identical_to_oracle"] = bool(np.array_equal(vg.view(np.uint32), vg_cpu.view(np.uint32)))
+    return {"voxel_grid": voxel, "value": batch / (ms * 1e-3), "unit": "descriptors/s", "points_per_scan": P, "scans_per_launch": batch, "ms_per_launch": ms,
             "e2e": {"value": batch / (e2e_ms * 1e-3), "unit": "descriptors/s", "h2d_bytes_per_launch": int(host.nbytes), "d2h_bytes_per_launch": int(out_h.nbytes)},
             "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                          "frac": alg_bytes / (ms * 1e-3) / 1e9 / pk["hbm"], "consumed_in_place_gbs": read_bytes / (ms * 1e-3) / 1e9,

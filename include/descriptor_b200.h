@@ -149,9 +149,54 @@ public:
 		return rc == SCL_OK && ok != 0;
 	}
 
+	/* downSizeFilterDes / downSizeFilterICP (distributedMapping.h:996-998, 1181-1185): pcl::VoxelGrid with a cubic leaf.
+	 * `out` receives the centroids (x, y, z, intensity; the padding fields are zeroed). */
+	bool voxelGrid(const pcl::PointCloud<pcl::PointXYZI>& cloud, float leaf, pcl::PointCloud<pcl::PointXYZI>& out)
+	{
+		std::vector<float> buf(cloud.points.size() * 4 + 4);
+		int m = 0;
+		const int rc = scl_voxel_grid(engine_, cloud.points.empty() ? nullptr : &cloud.points[0], (int)cloud.points.size(),
+			(int)sizeof(pcl::PointXYZI), leaf, buf.data(), &m);
+		check(rc, "voxelGrid");
+		unpack(buf, rc == SCL_OK ? m : 0, out);
+		return rc == SCL_OK;
+	}
+
+	/* loopFindNearKeyframes (distributedMapping.h:1163-1186): the keyframe clouds moved by their 6-DoF poses
+	 * (x, y, z, roll, pitch, yaw: PointPose6D), concatenated and down-sampled (leaf <= 0: not down-sampled). */
+	bool assembleSubmap(const std::vector<const pcl::PointCloud<pcl::PointXYZI>*>& clouds, const std::vector<float>& poses6,
+		float leaf, pcl::PointCloud<pcl::PointXYZI>& out)
+	{
+		std::vector<pcl::PointXYZI> all;
+		std::vector<int> offsets(1, 0);
+		for(size_t c = 0; c < clouds.size(); c++)
+		{
+			all.insert(all.end(), clouds[c]->points.begin(), clouds[c]->points.end());
+			offsets.push_back((int)all.size());
+		}
+		std::vector<float> buf(all.size() * 4 + 4);
+		int m = 0;
+		const int rc = scl_assemble_submap(engine_, all.empty() ? nullptr : &all[0], offsets.data(), (int)clouds.size(),
+			(int)sizeof(pcl::PointXYZI), poses6.data(), leaf, buf.data(), &m);
+		check(rc, "assembleSubmap");
+		unpack(buf, rc == SCL_OK ? m : 0, out);
+		return rc == SCL_OK;
+	}
+
 	scl_engine* engine() { return engine_; }
 
 private:
+	static void unpack(const std::vector<float>& buf, int m, pcl::PointCloud<pcl::PointXYZI>& out)
+	{
+		out.points.resize(m);
+		for(int i = 0; i < m; i++)
+		{
+			pcl::PointXYZI p = pcl::PointXYZI();
+			p.x = buf[4 * i]; p.y = buf[4 * i + 1]; p.z = buf[4 * i + 2]; p.intensity = buf[4 * i + 3];
+			out.points[i] = p;
+		}
+	}
+
 	void check(int rc, const char* what)
 	{
 		if(rc != SCL_OK)

@@ -214,6 +214,21 @@ void scl_default_ransac_params(scl_ransac_params* p);
 int scl_verify_ransac(scl_engine* e, const void* src, int n_src, const void* tgt, int n_tgt, int stride_bytes,
                       const scl_ransac_params* p, float* T_out, int* n_corr, int* n_inliers, int* success);
 
+/* ---- cloud preparation --------------------------------------------------
+ * Points are 16-byte aligned records stride_bytes apart with x, y, z in the first 12 bytes: stride 16 = packed
+ * (x, y, z, intensity); stride >= 32 = pcl::PointXYZI (intensity at byte 16).
+ * Outputs are packed: 4 floats (x, y, z, intensity) per point; the caller provides room for every input point.
+ *
+ * scl_voxel_grid replaces pcl::VoxelGrid<PointXYZI>::filter with setLeafSize(leaf, leaf, leaf) — downSizeFilterDes in
+ * front of the descriptor (distributedMapping.h:996-998) and downSizeFilterICP (:1181-1185, :1200-1201): one centroid
+ * per occupied leaf, ordered by the linear leaf index; non-finite points are skipped. */
+int scl_voxel_grid(scl_engine* e, const void* pts, int n, int stride_bytes, float leaf, float* out_xyzi, int* n_out);
+/* scl_assemble_submap replaces loopFindNearKeyframes (distributedMapping.h:1163-1186): cloud c (points
+ * offsets[c]..offsets[c+1]) is moved by pose c = (x, y, z, roll, pitch, yaw) as transformPointCloud does (:234-253),
+ * the clouds are concatenated in order and down-sampled with scl_voxel_grid(leaf); leaf <= 0 skips the down-sampling. */
+int scl_assemble_submap(scl_engine* e, const void* pts, const int* offsets, int n_clouds, int stride_bytes, const float* poses6,
+                        float leaf, float* out_xyzi, int* n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,6 +104,14 @@ void sco_nn(const float* src, int n_src, const float* tgt, int n_tgt, int stride
  * Returns the number of output points written to out (xyz packed, 3 floats). */
 int sco_voxel_grid(const float* pts, int n, int stride_floats, float leaf, float* out);
 
+/* ---- cloud preparation (cloud_oracle.cpp) -------------------------------------------------
+ * pcl::VoxelGrid<PointXYZI> restated in PCL's float arithmetic (distributedMapping.h:996-998,1181-1185): out holds
+ * 4 floats (x, y, z, intensity) per leaf, room for n points; returns the number written. */
+int sco_voxel_grid_pcl(const float* pts, int n, int stride_floats, float leaf, float* out);
+/* loopFindNearKeyframes (distributedMapping.h:1163-1186): transformPointCloud (:234-253) per cloud, concatenation,
+ * VoxelGrid (leaf <= 0: none). poses6 = (x, y, z, roll, pitch, yaw) per cloud. */
+int sco_assemble_submap(const float* pts, const int* offsets, int n_clouds, int stride_floats, const float* poses6, float leaf, float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -681,4 +681,105 @@ int scl_query_inter(scl_engine* e, int cur, int* id, float* second)
     return SCL_OK;
 }
 
+// ---- cloud preparation (K6) -------------------------------------------------------------------------------------
+namespace {
+inline float ordered_to_float(int i) { const int b = i ^ ((i >> 31) & 0x7fffffff); float f; memcpy(&f, &b, 4); return f; }
+
+// pcl::VoxelGrid on a device cloud (16-byte aligned records); result: packed float4 in e->vg_out, count in *n_out (host)
+int voxel_grid_dev(scl_engine* e, const void* d_pts, int n, int stride, float leaf, int* n_out)
+{
+    *n_out = 0;
+    if (n <= 0) return SCL_OK;
+    if (!(leaf > 0.0f)) FAIL(SCL_ERR_INVALID, "leaf size must be positive");
+    CK(e->vg_misc.ensure(64));
+    int* d_bounds = e->vg_misc.as<int>();
+    int* d_nout = d_bounds + 8;
+    CK(scl_launch_cloud_bounds(d_pts, n, stride, d_bounds, e->stream));
+    int hb[6];
+    CK(cudaMemcpyAsync(hb, d_bounds, sizeof(hb), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(e->vg_out.ensure((size_t)n * 16));
+    if (hb[0] == 0x7fffffff) return SCL_OK;                          /* no finite point */
+    float mn[3], mx[3];
+    for (int k = 0; k < 3; k++) { mn[k] = ordered_to_float(hb[k]); mx[k] = ordered_to_float(hb[3 + k]); }
+    const float inv = 1.0f / leaf;                                   /* voxel_grid.h: inverse_leaf_size_ = 1 / leaf_size_ */
+    /* voxel_grid.hpp: refuse grids whose linear index would overflow an int (PCL then returns the input unchanged) */
+    const long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1, dz = (long long)((mx[2] - mn[2]) * inv) + 1;
+    if (dx * dy * dz > 2147483647LL) {
+        CK(scl_launch_pack_xyzi(d_pts, n, stride, e->vg_out.p, e->stream));
+        *n_out = n;
+        return SCL_OK;
+    }
+    int min_b[3], max_b[3];
+    for (int k = 0; k < 3; k++) { min_b[k] = (int)floorf(mn[k] * inv); max_b[k] = (int)floorf(mx[k] * inv); }
+    const int div0 = max_b[0] - min_b[0] + 1, div1 = max_b[1] - min_b[1] + 1;
+    const size_t tb = scl_voxel_temp_bytes(n);
+    CK(e->vg_temp.ensure(tb));
+    for (int k = 0; k < 2; k++) { CK(e->vg_keys[k].ensure((size_t)n * 4)); CK(e->vg_vals[k].ensure((size_t)n * 4)); }
+    CK(e->vg_head.ensure((size_t)n * 4)); CK(e->vg_ord.ensure((size_t)n * 4));
+    CK(scl_launch_voxel_grid(d_pts, n, stride, inv, min_b, div0, div0 * div1, 32, e->vg_keys[0].as<uint32_t>(), e->vg_keys[1].as<uint32_t>(),
+                             e->vg_vals[0].as<int>(), e->vg_vals[1].as<int>(), e->vg_head.as<int>(), e->vg_ord.as<int>(), e->vg_temp.p, tb,
+                             e->vg_out.p, d_nout, e->stream));
+    CK(cudaMemcpyAsync(n_out, d_nout, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SCL_OK;
+}
+} // namespace
+
+int scl_voxel_grid(scl_engine* e, const void* pts, int n, int stride_bytes, float leaf, float* out_xyzi, int* n_out)
+{
+    LOCK();
+    if (!n_out || (n > 0 && (!pts || !out_xyzi))) FAIL(SCL_ERR_INVALID, "null argument");
+    if (stride_bytes < 16 || stride_bytes % 16) FAIL(SCL_ERR_UNSUPPORTED, "points must be 16-byte aligned x,y,z,intensity records");
+    *n_out = 0;
+    if (n <= 0) return SCL_OK;
+    CK(e->vg_in.ensure((size_t)n * stride_bytes));
+    CK(cudaMemcpyAsync(e->vg_in.p, pts, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, e->stream));
+    int rc = voxel_grid_dev(e, e->vg_in.p, n, stride_bytes, leaf, n_out); if (rc) return rc;
+    if (*n_out > 0) {
+        CK(cudaMemcpyAsync(out_xyzi, e->vg_out.p, (size_t)*n_out * 16, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    return SCL_OK;
+}
+
+int scl_assemble_submap(scl_engine* e, const void* pts, const int* offsets, int n_clouds, int stride_bytes, const float* poses6,
+                        float leaf, float* out_xyzi, int* n_out)
+{
+    LOCK();
+    if (!n_out || !offsets || n_clouds < 0 || (n_clouds > 0 && (!poses6 || !pts))) FAIL(SCL_ERR_INVALID, "null argument");
+    if (stride_bytes < 16 || stride_bytes % 16) FAIL(SCL_ERR_UNSUPPORTED, "points must be 16-byte aligned x,y,z,intensity records");
+    *n_out = 0;
+    const int total = n_clouds > 0 ? offsets[n_clouds] : 0;
+    if (total <= 0) return SCL_OK;
+    if (!out_xyzi) FAIL(SCL_ERR_INVALID, "null output");
+    /* pcl::getTransformation(x, y, z, roll, pitch, yaw) in float with libm, as the reference calls it (:241) */
+    std::vector<float> T((size_t)n_clouds * 12);
+    int max_points = 0;
+    for (int c = 0; c < n_clouds; c++) {
+        const float* p = poses6 + (size_t)c * 6;
+        const float A = cosf(p[5]), B = sinf(p[5]), C = cosf(p[4]), D = sinf(p[4]), E = cosf(p[3]), F = sinf(p[3]), DE = D * E, DF = D * F;
+        float* t = &T[(size_t)c * 12];
+        t[0] = A * C; t[1] = A * DF - B * E; t[2] = B * F + A * DE; t[3] = p[0];
+        t[4] = B * C; t[5] = A * E + B * DF; t[6] = B * DE - A * F; t[7] = p[1];
+        t[8] = -D;    t[9] = C * F;          t[10] = C * E;         t[11] = p[2];
+        max_points = std::max(max_points, offsets[c + 1] - offsets[c]);
+    }
+    CK(e->vg_in.ensure((size_t)total * stride_bytes)); CK(e->vg_world.ensure((size_t)total * 16));
+    CK(e->vg_T.ensure(T.size() * 4)); CK(e->vg_off.ensure((size_t)(n_clouds + 1) * 4));
+    CK(cudaMemcpyAsync(e->vg_in.p, pts, (size_t)total * stride_bytes, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->vg_T.p, T.data(), T.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->vg_off.p, offsets, (size_t)(n_clouds + 1) * 4, cudaMemcpyHostToDevice, e->stream));
+    CK(scl_launch_transform_concat(e->vg_in.p, e->vg_off.as<int>(), n_clouds, max_points, stride_bytes, e->vg_T.as<float>(), e->vg_world.p, e->stream));
+    if (leaf > 0.0f) {
+        int rc = voxel_grid_dev(e, e->vg_world.p, total, 16, leaf, n_out); if (rc) return rc;   /* T is consumed before voxel_grid_dev synchronises */
+        if (*n_out > 0) CK(cudaMemcpyAsync(out_xyzi, e->vg_out.p, (size_t)*n_out * 16, cudaMemcpyDeviceToHost, e->stream));
+    } else {
+        *n_out = total;
+        CK(cudaMemcpyAsync(out_xyzi, e->vg_world.p, (size_t)total * 16, cudaMemcpyDeviceToHost, e->stream));
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    return SCL_OK;
+}
+
 } // extern "C"

@@ -53,6 +53,7 @@ struct scl_engine {
         best_id, best_dist, best_shift;
     DevBuf tc_queues, tc_queue_cnt, tc_slots, tc_fail_list, tc_fail_count, tc_err_probe;
     DevBuf icp_src, icp_tgt, icp_raw, icp_grid[2][5], icp_acc, icp_nn;
+    DevBuf vg_in, vg_world, vg_out, vg_keys[2], vg_vals[2], vg_head, vg_ord, vg_temp, vg_misc, vg_T, vg_off;
     size_t gbins_scans = 0;
     /* pipelined host-buffer queries (scl_query_batch_submit / _wait) */
     cudaStream_t copy_stream = nullptr;

@@ -75,3 +75,15 @@ cudaError_t scl_launch_gather_rows(const float* src, const int32_t* rows, int n,
 // become `missing_to`, and are also rewritten in ids_rewrite when that is non-null
 cudaError_t scl_launch_ids_to_local(const int32_t* ids, int n, int id_mul, int id_add, int missing_to, int32_t* ids_rewrite,
                                     int32_t* local, cudaStream_t stream);
+
+// K6 (k6_cloud.cu): cloud preparation — transformPointCloud + concat (distributedMapping.h:234-253,1163-1175) and
+// pcl::VoxelGrid (:996-998,1181-1185). Points are 16-byte aligned x,y,z,intensity records `stride_bytes` apart; outputs
+// are packed float4 (x, y, z, intensity).
+cudaError_t scl_launch_transform_concat(const void* pts, const int* offsets_dev, int n_clouds, int max_points, int stride_bytes,
+                                        const float* T_dev /* [n_clouds][12] */, void* out_xyzi, cudaStream_t stream);
+cudaError_t scl_launch_cloud_bounds(const void* pts, int n, int stride_bytes, int* bounds6 /* order-preserving int images */, cudaStream_t stream);
+size_t scl_voxel_temp_bytes(int n);
+cudaError_t scl_launch_voxel_grid(const void* pts, int n, int stride_bytes, float inv_leaf, const int* min_b, int div0, int div01, int key_bits,
+                                  uint32_t* keys_a, uint32_t* keys_b, int* vals_a, int* vals_b, int* head, int* ord,
+                                  void* temp, size_t temp_bytes, void* out_xyzi, int* n_out, cudaStream_t stream);
+cudaError_t scl_launch_pack_xyzi(const void* pts, int n, int stride_bytes, void* out_xyzi, cudaStream_t stream);

@@ -27,7 +27,7 @@ EXPORTS = [
     "scl_get_ring_key", "scl_query_intra", "scl_query_inter", "scl_query_batch", "scl_query_batch_dev",
     "scl_merge_shards_dev", "scl_icp", "scl_set_profiling", "scl_stage_time", "scl_set_knn_mode", "scl_knn_stats",
     "scl_default_ransac_params", "scl_verify_ransac", "scl_knn_batch_dev", "scl_merge_topk_dev", "scl_scdist_owned_dev", "scl_combine_owned_dev",
-    "scl_query_batch_submit", "scl_query_batch_wait",
+    "scl_query_batch_submit", "scl_query_batch_wait", "scl_voxel_grid", "scl_assemble_submap",
 ]
 
 
@@ -354,3 +354,27 @@ class ScanContextB200:
         self._ck(self.lib.scl_verify_ransac(self.h, s.ctypes.data, ns, t.ctypes.data, nt, stride, C.byref(p), T.ctypes.data,
                                             C.byref(nc), C.byref(ni), C.byref(ok)))
         return T.reshape(4, 4), nc.value, ni.value, bool(ok.value)
+
+    def voxel_grid(self, pts, leaf):
+        """pcl::VoxelGrid<PointXYZI> (distributedMapping.h:996-998, 1181-1185): (m, 4) float32 centroids x, y, z, intensity."""
+        p, n, stride = _cloud(pts)
+        out = np.empty((max(n, 1), 4), np.float32)
+        m = C.c_int()
+        self._ck(self.lib.scl_voxel_grid(self.h, p.ctypes.data, n, stride, C.c_float(leaf), out.ctypes.data, C.byref(m)))
+        return out[:m.value].copy()
+
+    def assemble_submap(self, clouds, poses6, leaf):
+        """loopFindNearKeyframes (distributedMapping.h:1163-1186): clouds moved by their (x, y, z, roll, pitch, yaw) poses,
+        concatenated and voxel-filtered (leaf <= 0: not filtered). Returns (m, 4) float32."""
+        parts = [_cloud(c) for c in clouds]
+        stride = parts[0][2]
+        if any(s != stride for _, _, s in parts):
+            raise ValueError("clouds must share a point stride")
+        pts = np.ascontiguousarray(np.concatenate([p for p, _, _ in parts]))
+        offs = np.concatenate([[0], np.cumsum([n for _, n, _ in parts])]).astype(np.int32)
+        poses = np.ascontiguousarray(poses6, dtype=np.float32).reshape(len(clouds), 6)
+        out = np.empty((max(pts.shape[0], 1), 4), np.float32)
+        m = C.c_int()
+        self._ck(self.lib.scl_assemble_submap(self.h, pts.ctypes.data, offs.ctypes.data, len(clouds), stride, poses.ctypes.data,
+                                              C.c_float(leaf), out.ctypes.data, C.byref(m)))
+        return out[:m.value].copy()

@@ -79,6 +79,11 @@ def _load(path):
         lib.sco_nn.argtypes = [_f32p, C.c_int, _f32p, C.c_int, C.c_int, _i32p, _f32p]
         lib.sco_voxel_grid.restype = C.c_int
         lib.sco_voxel_grid.argtypes = [_f32p, C.c_int, C.c_int, C.c_float, _f32p]
+    if hasattr(lib, "sco_voxel_grid_pcl"):
+        lib.sco_voxel_grid_pcl.restype = C.c_int
+        lib.sco_voxel_grid_pcl.argtypes = [_f32p, C.c_int, C.c_int, C.c_float, _f32p]
+        lib.sco_assemble_submap.restype = C.c_int
+        lib.sco_assemble_submap.argtypes = [_f32p, _i32p, C.c_int, C.c_int, _f32p, C.c_float, _f32p]
     return lib
 
 
@@ -260,4 +265,27 @@ def voxel_grid(pts, leaf):
     pts, n, st = _cloud(pts)
     out = np.empty((max(n, 1), 3), np.float32)
     m = lib.sco_voxel_grid(pts.reshape(-1), n, st, leaf, out.reshape(-1))
+    return out[:m].copy()
+
+
+def voxel_grid_pcl(pts, leaf):
+    """pcl::VoxelGrid<PointXYZI> restatement: (m, 4) float32 centroids (x, y, z, intensity) in leaf-index order."""
+    lib = get_lib("port")
+    pts = np.ascontiguousarray(pts, dtype=np.float32)
+    assert pts.ndim == 2 and pts.shape[1] >= 4
+    n, st = pts.shape
+    out = np.empty((max(n, 1), 4), np.float32)
+    m = lib.sco_voxel_grid_pcl(pts.reshape(-1), n, st, leaf, out.reshape(-1))
+    return out[:m].copy()
+
+
+def assemble_submap(clouds, poses6, leaf):
+    """loopFindNearKeyframes restatement: clouds = list of (n_i, >=4) arrays sharing a stride, poses6 = (len, 6)."""
+    lib = get_lib("port")
+    st = clouds[0].shape[1]
+    pts = np.ascontiguousarray(np.concatenate(clouds), dtype=np.float32)
+    offs = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int32)
+    poses = np.ascontiguousarray(poses6, dtype=np.float32)
+    out = np.empty((max(pts.shape[0], 1), 4), np.float32)
+    m = lib.sco_assemble_submap(pts.reshape(-1), offs, len(clouds), st, poses.reshape(-1), leaf, out.reshape(-1))
     return out[:m].copy()

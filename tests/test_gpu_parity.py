@@ -499,3 +499,65 @@ def test_ransac_verification_vs_oracle(eng_mod, seed):
     _, _, ni_bad, ok_bad = e.verify_ransac(far, tgt, min_inlier_ratio=0.75)
     _, _, nio_bad, oko_bad = oracle_lib.verify_ransac(far, tgt, min_inlier_ratio=0.75)
     assert not ok_bad and not oko_bad
+
+
+# ---- K6: cloud preparation ---------------------------------------------------------------------
+import oracle_lib as _ol
+
+
+def _scan_xyzi(kind="hdl64", seed=0, n_az=None):
+    world = synth.make_world(1, 200)
+    dirs = synth.lidar_dirs(kind) if n_az is None else synth.lidar_dirs(kind, n_az=n_az)
+    pts = synth.scan(world, (0.0, 0.0, 0.3), dirs, seed=seed).astype(np.float32)
+    if pts.shape[1] < 4:
+        pts = np.concatenate([pts, np.zeros((len(pts), 4 - pts.shape[1]), np.float32)], 1)
+    pts = pts[:, :4].copy()
+    pts[:, 3] = np.random.default_rng(seed).uniform(0, 255, len(pts)).astype(np.float32)
+    return pts
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", ["packed16", "pcl32"])
+@pytest.mark.parametrize("leaf", [0.4, 1.0])
+def test_voxel_grid_bit_exact(eng_mod, layout, leaf):
+    """pcl::VoxelGrid<PointXYZI> on a full HDL-64 scan with non-finite points sprinkled in: centroids, intensities,
+    count and order identical to the oracle, for both input layouts."""
+    pts = _scan_xyzi("hdl64", seed=3)
+    pts[::501, 0] = np.nan
+    pts[7::733, 2] = np.inf
+    e = eng_mod.ScanContextB200()
+    exp = _ol.voxel_grid_pcl(pts, leaf)
+    got = e.voxel_grid(pts if layout == "packed16" else synth.to_pcl_xyzi(pts), leaf)
+    assert got.shape == exp.shape and len(exp) > 1000
+    assert np.array_equal(_bits(got), _bits(exp))
+
+
+@pytest.mark.gpu
+def test_voxel_grid_edges(eng_mod):
+    e = eng_mod.ScanContextB200()
+    assert e.voxel_grid(np.empty((0, 4), np.float32), 0.4).shape == (0, 4)
+    assert e.voxel_grid(np.full((9, 4), np.nan, np.float32), 0.4).shape == (0, 4)
+    one = np.tile(np.array([[3.1, -2.2, 0.3, 8.0]], np.float32), (9, 1))
+    assert np.array_equal(_bits(e.voxel_grid(one, 0.4)), _bits(_ol.voxel_grid_pcl(one, 0.4)))
+    far = np.array([[0, 0, 0, 1], [1e6, 1e6, 1e6, 2]], np.float32)          # leaf grid too large for an int index: input returned
+    assert np.array_equal(e.voxel_grid(far, 0.01), far)
+    neg = np.array([[-0.0, -0.5, 0.2, 1], [0.0, -0.4, 0.1, 3], [-7.3, 2.0, -1.0, 5]], np.float32)
+    assert np.array_equal(_bits(e.voxel_grid(neg, 0.4)), _bits(_ol.voxel_grid_pcl(neg, 0.4)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("leaf", [0.0, 0.4])
+def test_assemble_submap_bit_exact(eng_mod, leaf):
+    """loopFindNearKeyframes: 7 keyframe clouds (2n+1 with n = 3, config/dlc_lio_livox_horizon_config.yaml:34), one of them
+    empty, moved by 6-DoF poses, concatenated and voxel-filtered: identical to the oracle."""
+    rng = np.random.default_rng(21)
+    clouds = [_scan_xyzi("vlp16", seed=30 + i, n_az=600) for i in range(7)]
+    clouds[4] = clouds[4][:0]
+    poses = np.concatenate([rng.normal(0, 3, (7, 3)), rng.normal(0, 0.2, (7, 3))], 1).astype(np.float32)
+    e = eng_mod.ScanContextB200()
+    exp = _ol.assemble_submap(clouds, poses, leaf)
+    got = e.assemble_submap(clouds, poses, leaf)
+    assert got.shape == exp.shape and len(exp) > 1000
+    assert np.array_equal(_bits(got), _bits(exp))
+    got32 = e.assemble_submap([synth.to_pcl_xyzi(c) for c in clouds], poses, leaf)
+    assert np.array_equal(_bits(got32), _bits(exp))
