@@ -142,9 +142,19 @@ def run_ours(args):
     if rank == 0:
         sampler.start()                      # nvidia-smi needs ~1 s to produce its first line: start it early
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # the version banner goes to stdout, where the one JSON line belongs
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL writes its version banner to stdout when the first communicator is created; stdout is for the one JSON
+        # line, so file descriptor 1 points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     build.build()
     n_db = args.n_db
     e = engine.ScanContextB200(numCandidates=K, device=local_rank)
