@@ -227,14 +227,27 @@ __global__ void __launch_bounds__(256) polar_bin_kernel(
     for (int i = threadIdx.x; i < RS; i += blockDim.x) sbins[i] = 0u;
     __syncthreads();
 
+    /* Software pipeline: the loads of the next batch of kPointsPerThread points per thread are in flight while the current
+     * batch is binned (40 % of the stall samples of the unpipelined loop were the first use of a freshly loaded point). */
     const int chunk = blockDim.x * kPointsPerThread;
-    for (int base = p0 + blockIdx.x * chunk; base < p1; base += gridDim.x * chunk) {
-        float x[kPointsPerThread], y[kPointsPerThread], z[kPointsPerThread];
+    const int step = gridDim.x * chunk;
+    const float qnan = __int_as_float(0x7fc00000);
+    float x[kPointsPerThread], y[kPointsPerThread], z[kPointsPerThread];
+    float nx[kPointsPerThread], ny[kPointsPerThread], nz[kPointsPerThread];
+    int base = p0 + blockIdx.x * chunk;
 #pragma unroll
-        for (int j = 0; j < kPointsPerThread; j++) {   /* all loads first: kPointsPerThread LDG.128 in flight */
-            const int i = base + j * blockDim.x + threadIdx.x;
-            if (i < p1) load_xyz(pts, (size_t)i, stride, vec4 != 0, x[j], y[j], z[j]);
-            else { x[j] = y[j] = z[j] = __int_as_float(0x7fc00000); }
+    for (int j = 0; j < kPointsPerThread; j++) {
+        const int i = base + j * blockDim.x + threadIdx.x;
+        if (i < p1) load_xyz(pts, (size_t)i, stride, vec4 != 0, x[j], y[j], z[j]);
+        else { x[j] = y[j] = z[j] = qnan; }
+    }
+    for (; base < p1; base += step) {
+        const int nbase = base + step;
+#pragma unroll
+        for (int j = 0; j < kPointsPerThread; j++) {
+            const int i = nbase + j * blockDim.x + threadIdx.x;
+            if (i < p1) load_xyz(pts, (size_t)i, stride, vec4 != 0, nx[j], ny[j], nz[j]);
+            else { nx[j] = ny[j] = nz[j] = qnan; }
         }
 #pragma unroll
         for (int j = 0; j < kPointsPerThread; j++) {
@@ -250,6 +263,8 @@ __global__ void __launch_bounds__(256) polar_bin_kernel(
             const uint32_t m = __reduce_max_sync(peers, key);
             if (ok && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicMax(&sbins[bin], m);
         }
+#pragma unroll
+        for (int j = 0; j < kPointsPerThread; j++) { x[j] = nx[j]; y[j] = ny[j]; z[j] = nz[j]; }
     }
     __syncthreads();
     uint32_t* g = gbins + (size_t)scan * RS;
@@ -404,12 +419,12 @@ cudaError_t scl_launch_polar(const void* pts_dev, const int* offsets_dev, int n_
         }
         p.R = R; p.S = S; p.lidar_height = lidar_height; p.bt = hit->bt; p.tab = hit->dev; p.n_tab = hit->n;
     }
-    constexpr int kPPT = 8;
+    constexpr int kPPT = 4;        /* per batch; two batches per thread are live (software pipeline) */
     const int chunk = 256 * kPPT;
     int chunks = (max_points + chunk - 1) / chunk;
     if (chunks < 1) chunks = 1;
-    /* enough CTAs to cover the machine about 4x, but never more chunks than a scan has */
-    const int want = (4 * SCL_NUM_SMS + n_scans - 1) / n_scans;
+    /* enough CTAs to cover the machine about 8x (measured: 4x 86 us, 8x 76 us, 16x 75 us per 64 scans), but never more chunks than a scan has */
+    const int want = (8 * SCL_NUM_SMS + n_scans - 1) / n_scans;
     if (chunks > want) chunks = want;
     const int vec4 = (stride_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(pts_dev) & 15) == 0);
     if (p.bt.n_ring > kRingPad - 1 || p.bt.n_sec[0] > kSecPad - 1 || p.bt.n_sec[1] > kSecPad - 1 || p.bt.n_sec[2] > kSecPad - 1 ||
