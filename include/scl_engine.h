@@ -223,6 +223,11 @@ int scl_verify_ransac(scl_engine* e, const void* src, int n_src, const void* tgt
  * front of the descriptor (distributedMapping.h:996-998) and downSizeFilterICP (:1181-1185, :1200-1201): one centroid
  * per occupied leaf, ordered by the linear leaf index; non-finite points are skipped. */
 int scl_voxel_grid(scl_engine* e, const void* pts, int n, int stride_bytes, float leaf, float* out_xyzi, int* n_out);
+/* scl_build_insert_filtered = the producer step of distributedMapping.h:996-1003 in one call: downSizeFilterDes.filter(cloud)
+ * followed by makeAndSaveDescriptorAndKey(filtered, robot, index); the filtered cloud stays on the device. out_desc (R*S
+ * floats) and n_filtered may be NULL. */
+int scl_build_insert_filtered(scl_engine* e, const void* pts, int n, int stride_bytes, float leaf, int8_t robot, int index,
+                              float* out_desc, int* n_filtered);
 /* scl_assemble_submap replaces loopFindNearKeyframes (distributedMapping.h:1163-1186): cloud c (points
  * offsets[c]..offsets[c+1]) is moved by pose c = (x, y, z, roll, pitch, yaw) as transformPointCloud does (:234-253),
  * the clouds are concatenated in order and down-sampled with scl_voxel_grid(leaf); leaf <= 0 skips the down-sampling. */

@@ -743,6 +743,32 @@ int scl_voxel_grid(scl_engine* e, const void* pts, int n, int stride_bytes, floa
     return SCL_OK;
 }
 
+// The reference's producer step as one call (distributedMapping.h:996-1003): downSizeFilterDes.filter(keyFrame) and then
+// makeAndSaveDescriptorAndKey(filtered, robot, index). The filtered cloud never leaves the device.
+int scl_build_insert_filtered(scl_engine* e, const void* pts, int n, int stride_bytes, float leaf, int8_t robot, int index,
+                              float* out_desc, int* n_filtered)
+{
+    LOCK();
+    if (n < 0) FAIL(SCL_ERR_INVALID, "n < 0");
+    if (n > 0 && !pts) FAIL(SCL_ERR_INVALID, "null cloud");
+    if (stride_bytes < 16 || stride_bytes % 16) FAIL(SCL_ERR_UNSUPPORTED, "points must be 16-byte aligned x,y,z,intensity records");
+    int m = 0;
+    if (n > 0) {
+        CK(e->vg_in.ensure((size_t)n * stride_bytes));
+        CK(cudaMemcpyAsync(e->vg_in.p, pts, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, e->stream));
+        int rc = voxel_grid_dev(e, e->vg_in.p, n, stride_bytes, leaf, &m); if (rc) return rc;
+    } else {
+        CK(e->vg_out.ensure(16));
+    }
+    if (n_filtered) *n_filtered = m;
+    const int32_t off[2] = {0, m};
+    float* where = nullptr;
+    int rc = build_dev(e, e->vg_out.p, off, 1, 16, 1, &robot, &index, nullptr, nullptr, nullptr, &where); if (rc) return rc;
+    if (out_desc) CK(cudaMemcpyAsync(out_desc, where, (size_t)e->RS() * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SCL_OK;
+}
+
 int scl_assemble_submap(scl_engine* e, const void* pts, const int* offsets, int n_clouds, int stride_bytes, const float* poses6,
                         float leaf, float* out_xyzi, int* n_out)
 {

@@ -27,7 +27,7 @@ EXPORTS = [
     "scl_get_ring_key", "scl_query_intra", "scl_query_inter", "scl_query_batch", "scl_query_batch_dev",
     "scl_merge_shards_dev", "scl_icp", "scl_set_profiling", "scl_stage_time", "scl_set_knn_mode", "scl_knn_stats",
     "scl_default_ransac_params", "scl_verify_ransac", "scl_knn_batch_dev", "scl_merge_topk_dev", "scl_scdist_owned_dev", "scl_combine_owned_dev",
-    "scl_query_batch_submit", "scl_query_batch_wait", "scl_voxel_grid", "scl_assemble_submap",
+    "scl_query_batch_submit", "scl_query_batch_wait", "scl_voxel_grid", "scl_assemble_submap", "scl_build_insert_filtered",
 ]
 
 
@@ -378,3 +378,13 @@ class ScanContextB200:
         self._ck(self.lib.scl_assemble_submap(self.h, pts.ctypes.data, offs.ctypes.data, len(clouds), stride, poses.ctypes.data,
                                               C.c_float(leaf), out.ctypes.data, C.byref(m)))
         return out[:m.value].copy()
+
+    def makeAndSaveDescriptorAndKeyFiltered(self, scan, leaf, robot, index):
+        """distributedMapping.h:996-1003 in one call: VoxelGrid(leaf) then makeAndSaveDescriptorAndKey on the device-resident
+        filtered cloud. Returns (wire vector of R*S floats, number of filtered points)."""
+        p, n, stride = _cloud(scan)
+        out = np.empty(self.params.num_ring * self.params.num_sector, np.float32)
+        m = C.c_int()
+        self._ck(self.lib.scl_build_insert_filtered(self.h, p.ctypes.data, n, stride, C.c_float(leaf), C.c_int8(robot), index,
+                                                    out.ctypes.data, C.byref(m)))
+        return out, m.value

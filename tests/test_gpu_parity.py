@@ -561,3 +561,17 @@ def test_assemble_submap_bit_exact(eng_mod, leaf):
     assert np.array_equal(_bits(got), _bits(exp))
     got32 = e.assemble_submap([synth.to_pcl_xyzi(c) for c in clouds], poses, leaf)
     assert np.array_equal(_bits(got32), _bits(exp))
+
+
+@pytest.mark.gpu
+def test_filtered_build_equals_filter_then_build(eng_mod):
+    """scl_build_insert_filtered (VoxelGrid on the device feeding K1) = oracle VoxelGrid followed by the oracle's
+    makeAndSaveDescriptorAndKey, bit for bit, and the entry lands in the database like any other insert."""
+    pts = _scan_xyzi("hdl64", seed=5)
+    e, o = eng_mod.ScanContextB200(), Oracle()
+    filt = _ol.voxel_grid_pcl(pts, 0.4)
+    exp = o.makeAndSaveDescriptorAndKey(synth.to_pcl_xyzi(filt), 2, 17)
+    got, m = e.makeAndSaveDescriptorAndKeyFiltered(synth.to_pcl_xyzi(pts), 0.4, 2, 17)
+    assert m == len(filt)
+    assert np.array_equal(_bits(got), _bits(exp))
+    assert e.getSize() == 1 and e.getIndex(0) == (2, 17)
