@@ -199,8 +199,14 @@ int knn_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int
             const int ranges = scl_knn_tc_ranges(Qc);
             const size_t pairs = (size_t)Qc * ranges;
             CK(e->tc_queues.ensure(pairs * scl_knn_tc_queue_bytes())); CK(e->tc_queue_cnt.ensure(pairs * 4));
+            const void* old_slots = e->tc_slots.p; const void* old_cnt = e->tc_fail_count.p;
             CK(e->tc_fail_list.ensure((size_t)Q * 4)); CK(e->tc_fail_count.ensure(64));
             CK(e->tc_slots.ensure((size_t)Qc * scl_knn_tc_kprime() * 4));
+            const bool init_state = !e->tc_state_clean || old_slots != e->tc_slots.p || old_cnt != e->tc_fail_count.p || Qc > e->tc_slots_rows;
+            int* fail_cur = e->tc_fail_count.as<int>() + 8 * (e->tc_calls & 1);
+            int* fail_next = e->tc_fail_count.as<int>() + 8 * ((e->tc_calls + 1) & 1);
+            e->tc_calls++;
+            e->tc_state_clean = false;
             float* probe = nullptr;
             if (e->count_fallbacks) {
                 if (!e->tc_err_probe.p) { CK(e->tc_err_probe.ensure(64)); CK(cudaMemsetAsync(e->tc_err_probe.p, 0, 64, e->stream)); }
@@ -208,11 +214,13 @@ int knn_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int
             }
             KnnTcWorkspace tw{e->tc_queues.as<uint32_t>(), e->tc_queue_cnt.as<int>(), e->tc_slots.as<int>(), probe, pairs};
             CK(scl_launch_knn_tc(e->qkeys.as<float>(), Q, e->d_keys, e->d_kimg, e->d_kn2max, n_db, R, K, metric, e->world, e->rank, tw,
-                                 cand_ids, cand_d2, e->tc_fail_list.as<int32_t>(), e->tc_fail_count.as<int>(), e->stream));
+                                 cand_ids, cand_d2, e->tc_fail_list.as<int32_t>(), fail_cur, fail_next, init_state, e->stream));
+            e->tc_state_clean = true; e->tc_slots_rows = Qc;
             /* uncertified queries (normally none) are redone exactly; CTAs beyond the list length exit at once */
             if (!(getenv("SCL_TC_FLAGS") && (atoi(getenv("SCL_TC_FLAGS")) & 32)))
             CK(scl_launch_knn_exact(e->qkeys.as<float>(), Q, e->d_keys, n_db, R, K, metric, e->world, e->rank,
-                                    e->tc_fail_list.as<int32_t>(), e->tc_fail_count.as<int>(), ws, cand_ids, cand_d2, e->stream));
+                                    e->tc_fail_list.as<int32_t>(), fail_cur, ws, cand_ids, cand_d2, e->stream));
+            e->tc_last_fail = fail_cur;
             e->stat_tc_queries += Q;
         } else {
             CK(scl_launch_knn_exact(e->qkeys.as<float>(), Q, e->d_keys, n_db, R, K, metric, e->world, e->rank, nullptr, nullptr, ws,
@@ -221,7 +229,7 @@ int knn_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int
     }
     if (use_tc && e->count_fallbacks) {
         int nfail = 0;
-        CK(cudaMemcpyAsync(&nfail, e->tc_fail_count.p, 4, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(&nfail, e->tc_last_fail, 4, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
         e->stat_fallback_queries += nfail;
     }
@@ -236,11 +244,16 @@ int scdist_dev(scl_engine* e, const float* q_desc, const int32_t* q_local, const
     const int R = e->p.num_ring, S = e->p.num_sector;
     if (Q <= 0) return SCL_OK;
     const size_t QK = (size_t)Q * K;
-    CK(e->cand_local.ensure(QK * 4));
-    CK(scl_launch_ids_to_local(cand_ids, (int)QK, e->world, e->rank, missing_to_zero ? 0 : -1, missing_to_zero ? cand_ids : nullptr,
-                               e->cand_local.as<int32_t>(), e->stream));
+    /* reported id -> row of this engine's descriptor array; on an unsharded engine the two are the same (missing = -1) */
+    const int32_t* cand_local = cand_ids;
+    if (e->world != 1 || missing_to_zero) {
+        CK(e->cand_local.ensure(QK * 4));
+        CK(scl_launch_ids_to_local(cand_ids, (int)QK, e->world, e->rank, missing_to_zero ? 0 : -1, missing_to_zero ? cand_ids : nullptr,
+                                   e->cand_local.as<int32_t>(), e->stream));
+        cand_local = e->cand_local.as<int32_t>();
+    }
     StageTimer st(e, 2);
-    CK(scl_launch_scdist(e->d_desc, q_desc, q_local, q_ids, e->cand_local.as<int32_t>(), cand_ids, Q, K, R, S, e->search_radius,
+    CK(scl_launch_scdist(e->d_desc, q_desc, q_local, q_ids, cand_local, cand_ids, Q, K, R, S, e->search_radius,
                          cand_dist, cand_shift, best_id, best_dist, best_shift, e->stream));
     return SCL_OK;
 }

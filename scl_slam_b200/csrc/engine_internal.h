@@ -52,6 +52,10 @@ struct scl_engine {
     DevBuf qdesc, qids, qlocal, qkeys, qknorm, part_ids, part_d2, cand_ids, cand_d2, cand_local, cand_dist, cand_shift,
         best_id, best_dist, best_shift;
     DevBuf tc_queues, tc_queue_cnt, tc_slots, tc_fail_list, tc_fail_count, tc_err_probe;
+    long long tc_calls = 0;                /* tensor-core batches so far: they alternate between two fail counters */
+    bool tc_state_clean = false;           /* slots and the next fail counter were reset by the last re-rank kernel */
+    int tc_slots_rows = 0;                 /* rows of tc_slots known to be clean */
+    int* tc_last_fail = nullptr;           /* the counter the last batch used */
     DevBuf icp_src, icp_tgt, icp_raw, icp_grid[2][5], icp_acc, icp_nn;
     DevBuf vg_in, vg_world, vg_out, vg_keys[2], vg_vals[2], vg_head, vg_ord, vg_temp, vg_misc, vg_T, vg_off;
     size_t gbins_scans = 0;

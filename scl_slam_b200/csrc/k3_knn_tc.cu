@@ -560,7 +560,9 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
                                                           int n_ranges, int n_db, const uint2* __restrict__ hq, const int* __restrict__ hq_cnt,
                                                           const int* __restrict__ slots, const float* __restrict__ kn2max, int id_mul, int id_add,
                                                           int32_t* __restrict__ out_ids, float* __restrict__ out_d2, int q_off,
-                                                          int32_t* __restrict__ fail_list, int* __restrict__ fail_count, float* __restrict__ err_probe, int dev_flags, int kp)
+                                                          int32_t* __restrict__ fail_list, int* __restrict__ fail_count, float* __restrict__ err_probe, int dev_flags, int kp,
+                                                          int* __restrict__ slots_rw /* the same slots, to be reset for the next launch */,
+                                                          int* __restrict__ next_fail_count /* the other call parity's counter: zeroed here */)
 {
     __shared__ int sh_key[kRrWarps][kMaxGroups];        /* first key of the group */
     __shared__ float sh_g[kRrWarps][kMaxGroups];        /* its best prefilter score */
@@ -592,6 +594,10 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
      * cannot be certified anyway and are skipped: about K' groups survive. */
     gt = __reduce_max_sync(0xffffffffu, gt);
     const float cut = gt < 0x7f000000 ? ordered_float(gt) : inf;
+    /* housekeeping that used to be two memsets per batch: this query's slots go back to "no key yet" for the next launch
+     * (nobody else reads them), and the fail counter of the NEXT call is zeroed (calls alternate between two counters) */
+    if (lane < kKPrime) slots_rw[(size_t)qi * kKPrime + lane] = kNoThr;
+    if (qi == 0 && lane == 0) *next_fail_count = 0;
     if (lane < R) s_q[lane] = qv;
     if (R > 32 && lane + 32 < R) s_q[lane + 32] = qv2;
     bool overflow = false;
@@ -799,20 +805,23 @@ static cudaError_t launch_tc(const float* qkeys, int Q, const unsigned char* img
 
 cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, const unsigned char* img, const float* kn2max, int n_db, int R, int K,
                                int metric, int id_mul, int id_add, KnnTcWorkspace ws, int32_t* out_ids, float* out_d2,
-                               int32_t* fail_list, int* fail_count, cudaStream_t stream)
+                               int32_t* fail_list, int* fail_count, int* next_fail_count, bool init_state, cudaStream_t stream)
 {
     if (Q <= 0) return cudaSuccess;
     if (R != 20 && R != 40) return cudaErrorNotSupported;
     if (K > kKPrime - 2) return cudaErrorInvalidValue;
-    cudaError_t err = cudaMemsetAsync(fail_count, 0, sizeof(int), stream);
-    if (err != cudaSuccess) return err;
+    cudaError_t err = cudaSuccess;
     const int max_b = scl_knn_tc_max_batch();
+    if (init_state) {
+        /* first use of these buffers (or a call that was cut short): afterwards the re-rank kernel keeps them clean */
+        err = cudaMemsetAsync(fail_count, 0, sizeof(int), stream);
+        if (err == cudaSuccess) err = cudaMemsetAsync(ws.slots, 0x7f, (size_t)(Q < max_b ? Q : max_b) * kKPrime * 4, stream);     /* 3.39e38: "no key yet" */
+        if (err != cudaSuccess) return err;
+    }
     for (int q0 = 0; q0 < Q; q0 += max_b) {
         const int Qc = Q - q0 < max_b ? Q - q0 : max_b;
         const int n_ranges = scl_knn_tc_ranges(Qc);
         if ((size_t)Qc * n_ranges > ws.capacity) return cudaErrorInvalidValue;
-        err = cudaMemsetAsync(ws.slots, 0x7f, (size_t)Qc * kKPrime * 4, stream);     /* 3.39e38: "no key yet" */
-        if (err != cudaSuccess) return err;
         const float* qk = qkeys + (size_t)q0 * R;
         if (R == 20) err = launch_tc<20>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint2*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), kprime_for(K), stream);
         else err = launch_tc<40>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint2*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), kprime_for(K), stream);
@@ -820,7 +829,7 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
 #define SCL_RERANK(M, RR)                                                                                                              \
     knn_rerank_kernel<M, RR><<<(Qc + kRrWarps - 1) / kRrWarps, 32 * kRrWarps, 0, stream>>>(qk, Qc, keys, K, n_ranges, n_db, reinterpret_cast<const uint2*>(ws.hq), ws.hq_cnt,   \
                                                             ws.slots, kn2max, id_mul, id_add, out_ids + (size_t)q0 * K, out_d2 + (size_t)q0 * K, \
-                                                            q0, fail_list, fail_count, ws.err_probe, dev_flags, kprime_for(K))
+                                                            q0, fail_list, fail_count, ws.err_probe, dev_flags, kprime_for(K), ws.slots, next_fail_count)
         const int dev_flags = getenv("SCL_TC_FLAGS") ? atoi(getenv("SCL_TC_FLAGS")) : 0;     /* developer aid: timing experiments */
         if (dev_flags & 16) {}
         else if (R == 20) { if (metric == 0) SCL_RERANK(0, 20); else SCL_RERANK(1, 20); }

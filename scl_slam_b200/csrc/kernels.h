@@ -46,7 +46,8 @@ size_t scl_knn_tc_image_bytes(int R, int n_keys);
 cudaError_t scl_launch_key_image(const float* keys, const float* knorm, int k_lo, int k_hi, int R, unsigned char* img, cudaStream_t stream);
 cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, const unsigned char* img, const float* kn2max, int n_db, int R, int K,
                                int metric, int id_mul, int id_add, KnnTcWorkspace ws, int32_t* out_ids, float* out_d2,
-                               int32_t* fail_list, int* fail_count, cudaStream_t stream);
+                               int32_t* fail_list, int* fail_count, int* next_fail_count /* zeroed by the re-rank for the next call */,
+                               bool init_state /* slots and fail_count are not known to be clean */, cudaStream_t stream);
 
 // K4: shift-aligned column-cosine distance for every (query, candidate) + winner scan. See k4_scdist.cu.
 //  q_desc [Q][R*S] or nullptr (then queries are db entries q_local[i]); cand_local [Q][K] local keys (-1 = none);
