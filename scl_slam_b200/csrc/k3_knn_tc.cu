@@ -62,7 +62,7 @@ constexpr int kKPrime = 16;        /* slots per query (stride). K', the number o
                                     * launch: K <= K' - 2. The bound is the LARGEST of K' slot minima, which about K' H(K') keys undercut
                                     * (37 at K' = 12, 54 at 16): smaller is tighter, so K <= 10 (the reference's default) runs with K' = 12. */
 __host__ __device__ constexpr int kprime_for(int K) { return K <= 10 ? 12 : 16; }
-constexpr int kQueueCap = 128;               /* hit queue per (query, range): entries of 2 words (first key of an 8-key group, its best score); ~12 are used; a tile adds at most 32 */
+constexpr int kQueueCap = 64;                /* hit queue per (query, range): entries of 8 words (first key of a 32-key chunk, the best scores of its four 8-key groups, 3 pad); ~10 are used; a tile adds at most 8 */
 constexpr int kEpiThreads = 256;   /* 8 epilogue warps: query tile = (warp-4)/4, TMEM lane quadrant = warp%4 */
 constexpr int kThreads = 384;
 constexpr int kNT = 256;           /* keys per tile: one TMA copy, one N = 256 accumulator per query tile */
@@ -214,13 +214,14 @@ __global__ void __launch_bounds__(128) key_image_kernel(const float* __restrict_
 // A full hit queue is re-filtered with the threshold of the moment: groups queued under an earlier, looser bound whose
 // best score has risen to or above it can be dropped like any other key (they are >= the final cut). Rare, and kept
 // out of line so that the epilogue loop stays small.
-__device__ __noinline__ int compact_queue(uint2* q, int n, float thr)
+__device__ __noinline__ int compact_queue(uint4* q, int n, float thr)
 {
     int w = 0;
     for (int e = 0; e < n; e++) {
-        const uint2 v = __ldcg(q + e);
-        if (__uint_as_float(v.y) < thr) {
-            if (w != e) __stcg(q + w, v);
+        const uint4 a = __ldcg(q + 2 * e), b4 = __ldcg(q + 2 * e + 1);
+        const float m = fminf(fminf(__uint_as_float(a.y), __uint_as_float(a.z)), fminf(__uint_as_float(a.w), __uint_as_float(b4.x)));
+        if (m < thr) {
+            if (w != e) { __stcg(q + 2 * w, a); __stcg(q + 2 * w + 1, b4); }
             w++;
         }
     }
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     const float* __restrict__ qkeys, int Q, const unsigned char* __restrict__ img, int key_hi, int n_ranges,
     long long* __restrict__ times /* null, or [grid][16] developer counters (SCL_TC_TIMES=1) */,
     int* __restrict__ slots /* [Q][K'] range minima by range % K' (ordered-int image) */,
-    uint2* __restrict__ hq /* [Q][n_ranges][kQueueCap] hit queues: (first key of the group, its best score) */, int* __restrict__ hq_cnt /* [Q][n_ranges] */,
+    uint4* __restrict__ hq /* [Q][n_ranges][kQueueCap][2] hit queues: (first key of the chunk, best scores of its four groups) */, int* __restrict__ hq_cnt /* [Q][n_ranges] */,
     int* __restrict__ dbg /* null, or developer counters */, int dev_flags /* SCL_TC_FLAGS: timing experiments, results are then wrong */,
     int kp /* K' of this launch: 12 or 16 */)
 {
@@ -318,14 +319,14 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         float published = kThrInit;
         int* my_slot = slots + (size_t)(live ? qi : 0) * kKPrime + (range % kp);
         volatile int* my_sthr = sthr + qt * 128 + row;
-        uint2* my_q = hq + ((size_t)(live ? qi : 0) * n_ranges + range) * (size_t)kQueueCap;
+        uint4* my_q = hq + ((size_t)(live ? qi : 0) * n_ranges + range) * (size_t)(2 * kQueueCap);
         // The four epilogue warps of a query tile are coupled through the accumulator hand-off (it is refilled only when all
         // four have drained it), so the per-chunk code sits on the critical path of the whole CTA. It is BRANCH-FREE on purpose:
         // ptxas only hoists a tcgen05.ld above the min-tree of the previous chunk when both are in one basic block (with a
         // branch per chunk it sank every load to the end of its block, right in front of its consumers: 220 cycles per chunk
-        // instead of 60). 18 FMNMX(3) per 32 scores; a hit APPENDS (first key, group minimum) of the 8-key groups below the
-        // threshold to the (query, range) queue in global memory with predicated stores; the re-rank kernel re-scores those
-        // keys exactly. The queue has room for two tiles' worth of groups and is compacted between tiles when half full.
+        // instead of 60). 18 FMNMX(3) per 32 scores; a hit APPENDS (first key, the four group minima) of the chunk to the
+        // (query, range) queue in global memory with predicated stores; the re-rank kernel re-scores the keys of the groups at
+        // or below the cut exactly. The queue has room for four tiles' worth of chunks and is compacted between tiles when nearly full.
         float tile_min = kThrInit;
         bool overflowed = false;
         auto examine = [&](const uint32_t (&r)[32], int key_first) {
@@ -339,12 +340,14 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             }
             const float m = fminf(fmin3(g[0], g[1], g[2]), g[3]);
             if (TIMES && __any_sync(0xffffffffu, m < thr)) n_slow++;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const bool hj = g[j] < thr;
-                if (hj) __stcg(my_q + n_hit, make_uint2((uint32_t)(key_first + 8 * j), __float_as_uint(g[j])));
-                n_hit += hj ? 1 : 0;
+            /* one compare and two predicated 16-byte stores per chunk: the four group minima travel together and the re-rank
+             * decides per group (per-group compares and stores here cost a quarter of the chunk's issue slots) */
+            const bool hit = m < thr;
+            if (hit) {
+                __stcg(my_q + 2 * n_hit, make_uint4((uint32_t)key_first, __float_as_uint(g[0]), __float_as_uint(g[1]), __float_as_uint(g[2])));
+                __stcg(my_q + 2 * n_hit + 1, make_uint4(__float_as_uint(g[3]), 0u, 0u, 0u));
             }
+            n_hit += hit ? 1 : 0;
             tile_min = fminf(tile_min, m);
         };
         long long tw = 0, c0 = 0, t_first = 0, t_body = 0, t_tail = 0, q0 = 0;
@@ -414,9 +417,9 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             if (TIMES) { const long long q1 = clock64(); t_body += q1 - q0; q0 = q1; }
             /* a new range minimum feeds the union bound (tiles wholly below key_hi only; thr is -inf for rows beyond Q) */
             if (key0 + kNT <= key_hi && tile_min < fminf(thr, published)) { published = tile_min; atomicMin(my_slot, ordered_int(tile_min)); }
-            if (n_hit > kQueueCap - kNT / 8) {           /* no room for another tile's worth of groups: compact (rare) */
+            if (n_hit > kQueueCap - kNT / 32) {          /* no room for another tile's worth of chunks: compact (rare) */
                 n_hit = compact_queue(my_q, n_hit, thr);
-                if (n_hit > kQueueCap - kNT / 8) { overflowed = true; n_hit = 0; thr = -kThrInit; }   /* sticky: nothing more is queued, the query is redone exactly */
+                if (n_hit > kQueueCap - kNT / 32) { overflowed = true; n_hit = 0; thr = -kThrInit; }   /* sticky: nothing more is queued, the query is redone exactly */
             }
             if (live) next_thr = ordered_float(*my_sthr);
             if (TIMES) t_tail += clock64() - q0;
@@ -557,7 +560,7 @@ constexpr int kMaxSel = 512;                            /* keys entering the top
 constexpr int kRrWarps = 4;                             /* queries per CTA */
 template <int METRIC, int R>
 __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys, int K,
-                                                          int n_ranges, int n_db, const uint2* __restrict__ hq, const int* __restrict__ hq_cnt,
+                                                          int n_ranges, int n_db, const uint4* __restrict__ hq, const int* __restrict__ hq_cnt,
                                                           const int* __restrict__ slots, const float* __restrict__ kn2max, int id_mul, int id_add,
                                                           int32_t* __restrict__ out_ids, float* __restrict__ out_d2, int q_off,
                                                           int32_t* __restrict__ fail_list, int* __restrict__ fail_count, float* __restrict__ err_probe, int dev_flags, int kp,
@@ -620,27 +623,33 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
     if (dev_flags & 128) { if (lane == 0) out_ids[(size_t)qi * K] = total; return; }
     /* second trip(s): the queue entries, UE per lane in flight; survivors are compacted with a ballot */
     int n_grp = 0;
-    constexpr int UE = 8;
+    constexpr int UE = 4;
     int lo = 0;                                         /* the range that holds this lane's entry: advances monotonically */
     for (int base = 0; base < total; base += 32 * UE) {
-        uint2 e[UE];
+        uint4 ea[UE]; uint32_t eb[UE];
 #pragma unroll
         for (int u = 0; u < UE; u++) {
             const int g = base + u * 32 + lane;
-            e[u] = make_uint2(0x7fffffffu, 0x7f800000u);
+            ea[u] = make_uint4(0x7fffffffu, 0x7f800000u, 0x7f800000u, 0x7f800000u); eb[u] = 0x7f800000u;
             if (g < total) {
                 while (s_pre[lo + 1] <= g) lo++;
-                e[u] = __ldcg(hq + ((size_t)qi * n_ranges + lo) * (size_t)kQueueCap + (g - s_pre[lo]));
+                const uint4* ep = hq + ((size_t)qi * n_ranges + lo) * (size_t)(2 * kQueueCap) + 2 * (g - s_pre[lo]);
+                ea[u] = __ldcg(ep);
+                eb[u] = __ldcg(reinterpret_cast<const uint32_t*>(ep + 1));
             }
         }
 #pragma unroll
         for (int u = 0; u < UE; u++) {
-            const float gm = __uint_as_float(e[u].y);
-            const bool keep = gm <= cut && (int)e[u].x < n_db;
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            const int pos = n_grp + __popc(m & lt_mask);
-            if (keep && pos < kMaxGroups) { s_key[pos] = (int)e[u].x; s_g[pos] = gm; }
-            n_grp += __popc(m);
+            const float gm[4] = {__uint_as_float(ea[u].y), __uint_as_float(ea[u].z), __uint_as_float(ea[u].w), __uint_as_float(eb[u])};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {               /* the four 8-key groups of the chunk */
+                const int key = (int)ea[u].x + 8 * j;
+                const bool keep = gm[j] <= cut && key < n_db && ea[u].x != 0x7fffffffu;
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                const int pos = n_grp + __popc(m & lt_mask);
+                if (keep && pos < kMaxGroups) { s_key[pos] = key; s_g[pos] = gm[j]; }
+                n_grp += __popc(m);
+            }
         }
     }
     if (n_grp > kMaxGroups) { overflow = true; n_grp = kMaxGroups; }
@@ -750,7 +759,7 @@ int scl_knn_tc_ranges(int Q)
 }
 int scl_knn_tc_max_batch() { return 1024; }          /* larger batches are cut into launches of this many queries */
 int scl_knn_tc_kprime() { return kKPrime; }
-size_t scl_knn_tc_queue_bytes() { return (size_t)kQueueCap * 8; }           /* per (query, range) */
+size_t scl_knn_tc_queue_bytes() { return (size_t)kQueueCap * 32; }          /* per (query, range) */
 size_t scl_knn_tc_image_bytes(int R, int n_keys)
 {
     const size_t tiles = ((size_t)n_keys + kNT - 1) / kNT;
@@ -769,7 +778,7 @@ cudaError_t scl_launch_key_image(const float* keys, const float* knorm, int k_lo
 
 template <int R>
 static cudaError_t launch_tc(const float* qkeys, int Q, const unsigned char* img, int n_db, int n_ranges, int* slots,
-                              uint2* hq, int* hq_cnt, int* dbg, int kp, cudaStream_t stream)
+                              uint4* hq, int* hq_cnt, int* dbg, int kp, cudaStream_t stream)
 {
     using C = TcCfg<R>;
     static bool attr = false;
@@ -796,7 +805,7 @@ static cudaError_t launch_tc(const float* qkeys, int Q, const unsigned char* img
         for (int b = 0; b < nb; b++) for (int i = 0; i < 16; i++) a[i] += (double)h[(size_t)b * 16 + i] / nb;
         for (int b = 0; b < nb; b++) if ((double)h[(size_t)b * 16 + 4] > amax4) amax4 = (double)h[(size_t)b * 16 + 4];
         fprintf(stderr, "[tc n_db %d] tiles/CTA %.0f | per tile, per epilogue warp: total %.0f cycles, waiting for the accumulator %.0f, first chunk %.0f, other seven %.0f, tail %.0f | chunks with a hit per warp %.0f of %.0f, "
-                        "groups queued per (query, range) %.1f (largest %.0f) | mma thread per tile: wait key tile %.0f, wait accumulators + issue %.0f | service sweeps %.0f\n",
+                        "chunks queued per (query, range) %.1f (largest %.0f) | mma thread per tile: wait key tile %.0f, wait accumulators + issue %.0f | service sweeps %.0f\n",
                 n_db, a[8], a[1] / 8 / a[8], a[0] / 8 / a[8], a[9] / 8 / a[8], a[10] / 8 / a[8], a[11] / 8 / a[8], a[2] / 8, a[8] * 8, a[3] / 8 / 32, amax4, a[6] / a[8], a[7] / a[8], a[5] / 2);
         cudaFree(times);
     }
@@ -823,11 +832,11 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
         const int n_ranges = scl_knn_tc_ranges(Qc);
         if ((size_t)Qc * n_ranges > ws.capacity) return cudaErrorInvalidValue;
         const float* qk = qkeys + (size_t)q0 * R;
-        if (R == 20) err = launch_tc<20>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint2*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), kprime_for(K), stream);
-        else err = launch_tc<40>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint2*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), kprime_for(K), stream);
+        if (R == 20) err = launch_tc<20>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint4*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), kprime_for(K), stream);
+        else err = launch_tc<40>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint4*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), kprime_for(K), stream);
         if (err != cudaSuccess) return err;
 #define SCL_RERANK(M, RR)                                                                                                              \
-    knn_rerank_kernel<M, RR><<<(Qc + kRrWarps - 1) / kRrWarps, 32 * kRrWarps, 0, stream>>>(qk, Qc, keys, K, n_ranges, n_db, reinterpret_cast<const uint2*>(ws.hq), ws.hq_cnt,   \
+    knn_rerank_kernel<M, RR><<<(Qc + kRrWarps - 1) / kRrWarps, 32 * kRrWarps, 0, stream>>>(qk, Qc, keys, K, n_ranges, n_db, reinterpret_cast<const uint4*>(ws.hq), ws.hq_cnt,   \
                                                             ws.slots, kn2max, id_mul, id_add, out_ids + (size_t)q0 * K, out_d2 + (size_t)q0 * K, \
                                                             q0, fail_list, fail_count, ws.err_probe, dev_flags, kprime_for(K), ws.slots, next_fail_count)
         const int dev_flags = getenv("SCL_TC_FLAGS") ? atoi(getenv("SCL_TC_FLAGS")) : 0;     /* developer aid: timing experiments */
