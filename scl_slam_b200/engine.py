@@ -28,7 +28,46 @@ EXPORTS = [
     "scl_merge_shards_dev", "scl_icp", "scl_set_profiling", "scl_stage_time", "scl_set_knn_mode", "scl_knn_stats",
     "scl_default_ransac_params", "scl_verify_ransac", "scl_knn_batch_dev", "scl_merge_topk_dev", "scl_scdist_owned_dev", "scl_combine_owned_dev",
     "scl_query_batch_submit", "scl_query_batch_wait", "scl_voxel_grid", "scl_assemble_submap", "scl_build_insert_filtered",
+    "scl_wire_pose6_to_transform", "scl_wire_loop_between", "scl_wire_make_loop_info", "scl_wire_make_global_descriptor",
+    "scl_wire_encode_global_descriptor", "scl_wire_decode_global_descriptor", "scl_wire_encode_loop_info", "scl_wire_decode_loop_info",
 ]
+
+
+class SclTransform(C.Structure):
+    """geometry_msgs/Transform (include/scl_wire.h)"""
+    _fields_ = [("tx", C.c_double), ("ty", C.c_double), ("tz", C.c_double), ("qx", C.c_double), ("qy", C.c_double), ("qz", C.c_double), ("qw", C.c_double)]
+
+    def as_tuple(self):
+        return (self.tx, self.ty, self.tz, self.qx, self.qy, self.qz, self.qw)
+
+
+class SclGlobalDescriptor(C.Structure):
+    """global_descriptor.msg"""
+    _fields_ = [("index", C.c_int32), ("pre_pose", SclTransform), ("cur_pose", SclTransform), ("values", C.POINTER(C.c_float)), ("n_values", C.c_int32)]
+
+
+class SclLoopInfo(C.Structure):
+    """loop_info.msg"""
+    _fields_ = [("robot0", C.c_int32), ("robot1", C.c_int32), ("index0", C.c_int32), ("index1", C.c_int32), ("noise", C.c_float), ("bet_pose", SclTransform)]
+
+
+def wire_loop_between(T_align, pose_cur6, pose_pre6, quat_from_rpy=False):
+    """distributedMapping.h:1129-1141 / 1249-1256: the pose between two keyframes of a verified loop (tx, ty, tz, qx, qy, qz, qw)."""
+    lib = load_library()
+    T = np.ascontiguousarray(T_align, np.float32).reshape(16)
+    a = np.ascontiguousarray(pose_cur6, np.float32).reshape(6)
+    b = np.ascontiguousarray(pose_pre6, np.float32).reshape(6)
+    out = SclTransform()
+    lib.scl_wire_loop_between(C.c_void_p(T.ctypes.data), C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data), int(bool(quat_from_rpy)), C.byref(out))
+    return out.as_tuple()
+
+
+def wire_pose6_to_transform(pose6):
+    lib = load_library()
+    a = np.ascontiguousarray(pose6, np.float32).reshape(6)
+    out = SclTransform()
+    lib.scl_wire_pose6_to_transform(C.c_void_p(a.ctypes.data), C.byref(out))
+    return out.as_tuple()
 
 
 class SclParams(C.Structure):

@@ -1,5 +1,5 @@
 """CPU-side checks of the drop-in boundary: the C-ABI library builds for sm_100a, loads, and
-exports every symbol include/scl_engine.h declares; without a GPU the engine refuses to come up
+exports every symbol include/scl_engine.h and include/scl_wire.h declare; without a GPU the engine refuses to come up
 (no CPU fallback). No compute calls here."""
 import ctypes as C
 import os
@@ -20,7 +20,7 @@ def lib():
 
 def test_header_symbols_all_exported(lib):
     from scl_slam_b200 import engine
-    hdr = open(os.path.join(ROOT, "include", "scl_engine.h")).read()
+    hdr = open(os.path.join(ROOT, "include", "scl_engine.h")).read() + open(os.path.join(ROOT, "include", "scl_wire.h")).read()
     declared = set(re.findall(r"\b(scl_[a-z_0-9]+)\s*\(", hdr))
     assert declared == set(engine.EXPORTS), declared ^ set(engine.EXPORTS)
     for name in declared:

@@ -14,6 +14,7 @@ template <int OP> __device__ __forceinline__ void step(float (&a)[8], int (&ia)[
         if (OP == 3) { ia[i] = min(min(ia[i], ib), ic); OPAQUE_I(ia[i]); }                             /* VIMNMX3 if fused */
         if (OP == 4) { asm volatile("min.u32 %0, %0, %1;" : "+r"(ia[i]) : "r"(ib)); }
         if (OP == 5) { asm volatile("{.reg .pred p; setp.lt.f32 p, %0, %1; @p add.s32 %2, %2, 1;}" : "+f"(a[i]), "+f"(b), "+r"(ia[i])); }   /* FSETP + predicated IADD */
+        if (OP == 7) { asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b), "f"(c)); ia[i] = min(min(ia[i], ib), ic); OPAQUE_I(ia[i]); }   /* FMNMX3 + VIMNMX3 interleaved */
         if (OP == 6) { asm volatile("{.reg .pred p; setp.lt.s32 p, %0, %1; @p add.s32 %0, %0, 1;}" : "+r"(ia[i]) : "r"(ib)); }         /* ISETP + predicated IADD */
     }
 }
@@ -44,8 +45,8 @@ template <int OP> void run(const char* name, int threads, int per_step)
 int main()
 {
     for (int threads : {128, 512}) {
-        if (threads == 128) { run<0>("min.f32 (2 in)", 128, 1); run<1>("min.f32 (3 in)", 128, 1); run<2>("min.s32 (2 in)", 128, 1); run<3>("min(min()) s32 (3 in)", 128, 1); run<4>("min.u32 (2 in)", 128, 1); run<5>("setp.f32 + @p add", 128, 2); run<6>("setp.s32 + @p add", 128, 2); }
-        else { run<0>("min.f32 (2 in)", 512, 1); run<1>("min.f32 (3 in)", 512, 1); run<2>("min.s32 (2 in)", 512, 1); run<3>("min(min()) s32 (3 in)", 512, 1); run<4>("min.u32 (2 in)", 512, 1); run<5>("setp.f32 + @p add", 512, 2); run<6>("setp.s32 + @p add", 512, 2); }
+        if (threads == 128) { run<0>("min.f32 (2 in)", 128, 1); run<1>("min.f32 (3 in)", 128, 1); run<2>("min.s32 (2 in)", 128, 1); run<3>("min(min()) s32 (3 in)", 128, 1); run<4>("min.u32 (2 in)", 128, 1); run<5>("setp.f32 + @p add", 128, 2); run<6>("setp.s32 + @p add", 128, 2); run<7>("min3.f32 + min3.s32 mixed", 128, 2); }
+        else { run<0>("min.f32 (2 in)", 512, 1); run<1>("min.f32 (3 in)", 512, 1); run<2>("min.s32 (2 in)", 512, 1); run<3>("min(min()) s32 (3 in)", 512, 1); run<4>("min.u32 (2 in)", 512, 1); run<5>("setp.f32 + @p add", 512, 2); run<6>("setp.s32 + @p add", 512, 2); run<7>("min3.f32 + min3.s32 mixed", 512, 2); }
     }
     return 0;
 }
