@@ -703,26 +703,52 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
     if (n_surv > kMaxSel) { overflow = true; n_surv = kMaxSel; }
     __syncwarp();
     if (dev_flags & 512) { if (lane == 0) out_ids[(size_t)qi * K] = n_surv; return; }
-    /* K rounds: smallest (d2, id) strictly after the previous pick (a rank-by-counting selection measured slower: its cost
-     * grows with the square of the list length, and the longest list of the batch sets the kernel's duration) */
-    float pd = -1.0f; int pi = -1; float dK = 0.0f; int found = 0;
-    for (int r = 0; r < K; r++) {
-        float bd = inf; int bi = 0x7fffffff;
-        for (int c = lane; c < n_surv; c += 32) {
-            const float d = s_d[c];
-            const int id = s_id[c];
-            if (d < pd || (d == pd && id <= pi)) continue;
-            if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; }
-        }
+    /* K rounds of "smallest (d2, id) not picked yet" (a rank-by-counting selection measured slower: its cost grows with
+     * the square of the list length, and the longest list of the batch sets the kernel's duration). Distances are
+     * non-negative floats, whose bit patterns order like unsigned integers, so (d2, id) is ONE 64-bit key; lists of up
+     * to 128 keys (the rule) live in registers, four per lane, and a round is a local minimum plus two warp reductions. */
+    float dK = 0.0f; int found = 0;
+    if (n_surv <= 128) {
+        unsigned long long e[4];
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const float od = __shfl_xor_sync(0xffffffffu, bd, off); const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        for (int j = 0; j < 4; j++) {
+            const int c = lane + 32 * j;
+            e[j] = c < n_surv ? (((unsigned long long)__float_as_uint(s_d[c]) << 32) | (unsigned)s_id[c]) : ~0ull;
         }
-        const bool ok = bi != 0x7fffffff;
-        if (lane == 0) { out_ids[(size_t)qi * K + r] = ok ? bi : -1; out_d2[(size_t)qi * K + r] = ok ? bd : FLT_MAX; }
-        if (ok) { pd = bd; pi = bi; dK = bd; found++; }
-        else break;
+        for (int r = 0; r < K; r++) {
+            unsigned long long loc = e[0] < e[1] ? e[0] : e[1];
+            const unsigned long long loc2 = e[2] < e[3] ? e[2] : e[3];
+            loc = loc < loc2 ? loc : loc2;
+            const unsigned hi = (unsigned)(loc >> 32);
+            const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+            const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? (unsigned)loc : 0xffffffffu);
+            const unsigned long long win = ((unsigned long long)mhi << 32) | mlo;
+            if (win == ~0ull) break;
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (e[j] == win) e[j] = ~0ull;     /* keys are distinct: exactly one owner */
+            if (lane == 0) { out_ids[(size_t)qi * K + r] = (int)mlo; out_d2[(size_t)qi * K + r] = __uint_as_float(mhi); }
+            dK = __uint_as_float(mhi); found++;
+        }
+    } else {
+        float pd = -1.0f; int pi = -1;
+        for (int r = 0; r < K; r++) {
+            float bd = inf; int bi = 0x7fffffff;
+            for (int c = lane; c < n_surv; c += 32) {
+                const float d = s_d[c];
+                const int id = s_id[c];
+                if (d < pd || (d == pd && id <= pi)) continue;
+                if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, bd, off); const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+            }
+            const bool ok = bi != 0x7fffffff;
+            if (lane == 0) { out_ids[(size_t)qi * K + r] = ok ? bi : -1; out_d2[(size_t)qi * K + r] = ok ? bd : FLT_MAX; }
+            if (ok) { pd = bd; pi = bi; dK = bd; found++; }
+            else break;
+        }
     }
     if (lane == 0) {
         for (int r = found; r < K; r++) { out_ids[(size_t)qi * K + r] = -1; out_d2[(size_t)qi * K + r] = FLT_MAX; }
