@@ -270,14 +270,20 @@ def run_ours(args):
         sync_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         e2e_pipelined(3)
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        e2e_pipelined(args.steps)
-        torch.cuda.synchronize()
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        # K steps take a few milliseconds of wall clock on a shared host: the region is repeated five times and the MEDIAN
+        # repetition is reported (all five are listed)
+        reps = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            e2e_pipelined(args.steps)
+            torch.cuda.synchronize()
+            reps.append((time.perf_counter() - t0) * 1e3 / args.steps)
+        e2e_ms = sorted(reps)[len(reps) // 2]
         assert np.array_equal(res2[0]["best_id"], res2[1]["best_id"]) and np.array_equal(res2[0]["best_id"], local["best_id"].cpu().numpy())
         e2e = {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(q_host.nbytes), "d2h_bytes_per_step": int(sum(v.nbytes for v in res.values())),
                "api": "scl_query_batch_submit / scl_query_batch_wait, two batches in flight",
+               "repetitions_ms_per_step": reps, "reported": "median of five repetitions of --steps steps",
                "one_call_synchronous": {"value": Q / (sync_ms * 1e-3), "ms_per_step": sync_ms, "api": "scl_query_batch"}}
     if world > 1:
         # N > 1: every rank copies the step's queries from pinned host memory, runs the sharded step with its two

@@ -200,11 +200,14 @@ int knn_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int
             const size_t pairs = (size_t)Qc * ranges;
             CK(e->tc_queues.ensure(pairs * scl_knn_tc_queue_bytes())); CK(e->tc_queue_cnt.ensure(pairs * 4));
             const void* old_slots = e->tc_slots.p; const void* old_cnt = e->tc_fail_count.p;
-            CK(e->tc_fail_list.ensure((size_t)Q * 4)); CK(e->tc_fail_count.ensure(64));
+            CK(e->tc_fail_list.ensure((size_t)Q * 4)); CK(e->tc_fail_count.ensure(128));
             CK(e->tc_slots.ensure((size_t)Qc * scl_knn_tc_kprime() * 4));
             const bool init_state = !e->tc_state_clean || old_slots != e->tc_slots.p || old_cnt != e->tc_fail_count.p || Qc > e->tc_slots_rows;
-            int* fail_cur = e->tc_fail_count.as<int>() + 8 * (e->tc_calls & 1);
-            int* fail_next = e->tc_fail_count.as<int>() + 8 * ((e->tc_calls + 1) & 1);
+            if (old_cnt != e->tc_fail_count.p) CK(cudaMemsetAsync(e->tc_fail_count.p, 0, 128, e->stream));   /* two call counters + the running total */
+            /* counter block (ints): [0] / [16] = the fail counters of even / odd calls; [8] + [24] = uncertified queries since
+             * creation (the re-rank kernel adds to the int 8 places after the counter it is told to zero) */
+            int* fail_cur = e->tc_fail_count.as<int>() + 16 * (e->tc_calls & 1);
+            int* fail_next = e->tc_fail_count.as<int>() + 16 * ((e->tc_calls + 1) & 1);
             e->tc_calls++;
             e->tc_state_clean = false;
             float* probe = nullptr;
@@ -230,8 +233,8 @@ int knn_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int
     if (use_tc && e->count_fallbacks) {
         int nfail = 0;
         CK(cudaMemcpyAsync(&nfail, e->tc_last_fail, 4, cudaMemcpyDeviceToHost, e->stream));
-        CK(cudaStreamSynchronize(e->stream));
-        e->stat_fallback_queries += nfail;
+        CK(cudaStreamSynchronize(e->stream));            /* developer mode: surfaces kernel faults at the call that caused them */
+        (void)nfail;
     }
     if (q_local_out) *q_local_out = q_local;
     return SCL_OK;
@@ -414,7 +417,15 @@ int scl_knn_stats(scl_engine* e, long long* tc_queries, long long* fallback_quer
 {
     LOCK();
     if (tc_queries) *tc_queries = e->stat_tc_queries;
-    if (fallback_queries) *fallback_queries = e->stat_fallback_queries;
+    if (fallback_queries) {
+        /* counted on the device by the re-rank kernel (ints [8] and [24] of the counter block, one per call parity) */
+        int h[32] = {0};
+        if (e->tc_fail_count.p) {
+            CK(cudaStreamSynchronize(e->stream));
+            CK(cudaMemcpy(h, e->tc_fail_count.p, sizeof(h), cudaMemcpyDeviceToHost));
+        }
+        *fallback_queries = (long long)h[8] + (long long)h[24];
+    }
     return SCL_OK;
 }
 

@@ -758,7 +758,7 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
             const float eps = eps0 + 2.0e-6f * dK;                  /* + exact-side rounding */
             certified = certified && (found == K) && (dK + eps < cut + qn);
         }
-        if (!certified) fail_list[atomicAdd(fail_count, 1)] = q_off + qi;
+        if (!certified) { fail_list[atomicAdd(fail_count, 1)] = q_off + qi; atomicAdd(next_fail_count + 8, 1); }   /* + the engine's running total (third counter of the block) */
         if (err_probe) {                                            /* developer counters: list sizes */
             int* sz = reinterpret_cast<int*>(err_probe) + 6;
             atomicAdd(sz + 0, total); atomicAdd(sz + 1, n_grp); atomicAdd(sz + 2, n_sel); atomicAdd(sz + 3, 1); atomicMax(sz + 4, n_grp); atomicMax(sz + 5, total);
