@@ -257,7 +257,7 @@ int scdist_dev(scl_engine* e, const float* q_desc, const int32_t* q_local, const
     }
     StageTimer st(e, 2);
     CK(scl_launch_scdist(e->d_desc, q_desc, q_local, q_ids, cand_local, cand_ids, Q, K, R, S, e->search_radius,
-                         cand_dist, cand_shift, best_id, best_dist, best_shift, e->stream));
+                         cand_dist, cand_shift, best_id, best_dist, best_shift, e->scdist_owned_hint, e->stream));
     return SCL_OK;
 }
 
@@ -648,7 +648,11 @@ int scl_scdist_owned_dev(scl_engine* e, const float* q_desc_dev, const int32_t* 
     LOCK();
     if (!q_desc_dev || !cand_ids_dev || !dist_dev || !shift_dev) FAIL(SCL_ERR_INVALID, "null argument");
     if (K < 1 || K > 32) FAIL(SCL_ERR_INVALID, "K must be in 1..32");
-    return scdist_dev(e, q_desc_dev, nullptr, q_ids_dev, Q, K, const_cast<int32_t*>(cand_ids_dev), 0, dist_dev, shift_dev, nullptr, nullptr, nullptr);
+    /* the global candidate lists are spread over the shards: about K / world of a query's candidates live here */
+    e->scdist_owned_hint = e->world > 1 ? (K + e->world - 1) / e->world + 1 : 0;
+    const int rc = scdist_dev(e, q_desc_dev, nullptr, q_ids_dev, Q, K, const_cast<int32_t*>(cand_ids_dev), 0, dist_dev, shift_dev, nullptr, nullptr, nullptr);
+    e->scdist_owned_hint = 0;
+    return rc;
 }
 
 int scl_combine_owned_dev(scl_engine* e, int world, int Q, int K, const int32_t* q_ids, const int32_t* cand_ids, const void* dist_base,

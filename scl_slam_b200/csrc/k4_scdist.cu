@@ -126,8 +126,26 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) scdist_kernel(
     } else {
         for (int i = threadIdx.x; i < RS; i += blockDim.x) qd[i] = __ldg(qsrc + i);
     }
+    /* The candidates this engine holds (all of them on an unsharded engine, about K / world on a shard) are listed first, so
+     * that the warps share the work evenly whatever the ownership pattern; slots of other shards report NaN at once. */
+    __shared__ int s_owned[32];
+    __shared__ int s_n_owned;
+    if (warp == 0) {
+        const int cl = lane < K ? cand_local[(size_t)qi * K + lane] : -1;
+        const unsigned m = __ballot_sync(0xffffffffu, cl >= 0);
+        if (cl >= 0) s_owned[__popc(m & ((1u << lane) - 1u))] = lane;
+        if (lane == 0) s_n_owned = __popc(m);
+        if (lane < K && cl < 0) {
+            res_dist[lane] = __longlong_as_double(0x7ff8000000000000LL); res_shift[lane] = 0;
+            if (cand_dist) cand_dist[(size_t)qi * K + lane] = __longlong_as_double(0x7ff8000000000000LL);
+            if (cand_shift) cand_shift[(size_t)qi * K + lane] = 0;
+        }
+    }
+    __syncthreads();
+    const int n_owned = s_n_owned;
     /* first candidate of every warp goes in flight before anyone waits */
-    int it = warp;
+    int oi = warp;                                    /* position in the owned list */
+    int it = oi < n_owned ? s_owned[oi] : K;
     int c_local = it < K ? cand_local[(size_t)qi * K + it] : -1;
     if (use_bulk && lane == 0 && c_local >= 0) {
         scl_mbar_expect_tx(&bars[1 + warp], bytes);
@@ -143,7 +161,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) scdist_kernel(
     __syncthreads();
 
     uint32_t parity = 0;
-    for (; it < K; it += warps) {
+    for (; oi < n_owned; oi += warps) {
         double out_dist = __longlong_as_double(0x7ff8000000000000LL); /* NaN: candidate missing */
         int out_shift = 0;
         if (c_local >= 0) {
@@ -309,8 +327,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) scdist_kernel(
             if (cand_shift) cand_shift[(size_t)qi * K + it] = out_shift;
         }
         /* next candidate of this warp into the same tile */
-        const int nxt = it + warps;
+        const int nxt = oi + warps < n_owned ? s_owned[oi + warps] : K;
         c_local = nxt < K ? cand_local[(size_t)qi * K + nxt] : -1;
+        it = nxt;
         __syncwarp();
         if (use_bulk && lane == 0 && c_local >= 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -434,11 +453,13 @@ __global__ void combine_owned_kernel(int world, int Q, int K, const int32_t* __r
 cudaError_t scl_launch_scdist(const float* db_desc, const float* q_desc, const int32_t* q_local, const int32_t* q_ids,
                               const int32_t* cand_local, const int32_t* cand_ids, int Q, int K, int R, int S, int search_radius,
                               double* cand_dist, int32_t* cand_shift, int32_t* best_id, double* best_dist, int32_t* best_shift,
-                              cudaStream_t stream)
+                              int owned_per_query /* expected candidates per query held here; <= 0: all K */, cudaStream_t stream)
 {
     if (Q <= 0) return cudaSuccess;
     const size_t budget = 200 * 1024;
     int warps = K < 16 ? K : 16;
+    /* a shard holds about K / world of a query's candidates: fewer warps per CTA then, so that more CTAs (queries) share an SM */
+    if (owned_per_query > 0 && owned_per_query < warps) warps = owned_per_query < 2 ? 2 : owned_per_query;
     while (warps > 1 && sc_layout(R, S, K, warps).total > budget) warps--;
     const ScLayout L = sc_layout(R, S, K, warps);
     if (L.total > 227 * 1024) return cudaErrorNotSupported;

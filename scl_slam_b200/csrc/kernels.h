@@ -55,7 +55,7 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
 cudaError_t scl_launch_scdist(const float* db_desc, const float* q_desc, const int32_t* q_local, const int32_t* q_ids,
                               const int32_t* cand_local, const int32_t* cand_ids, int Q, int K, int R, int S, int search_radius,
                               double* cand_dist, int32_t* cand_shift, int32_t* best_id, double* best_dist, int32_t* best_shift,
-                              cudaStream_t stream);
+                              int owned_per_query, cudaStream_t stream);
 
 // Shard merge (multi-GPU): world blocks of [Q][K] records -> global top-K by (d2,id) + winner scan.
 cudaError_t scl_launch_merge_shards(int world, int Q, int K, const int32_t* q_ids, const int32_t* all_ids, const float* all_d2,
