@@ -383,6 +383,9 @@ int scl_destroy(scl_engine* e)
                           &e->icp_grid[0][0], &e->icp_grid[0][1], &e->icp_grid[0][2], &e->icp_grid[0][3], &e->icp_grid[0][4],
                           &e->icp_grid[1][0], &e->icp_grid[1][1], &e->icp_grid[1][2], &e->icp_grid[1][3], &e->icp_grid[1][4]};
         for (DevBuf* b : bufs) b->release();
+        DevBuf* cloud_bufs[] = {&e->vg_in, &e->vg_world, &e->vg_out, &e->vg_keys[0], &e->vg_keys[1], &e->vg_vals[0], &e->vg_vals[1], &e->vg_head,
+                                &e->vg_ord, &e->vg_temp, &e->vg_misc, &e->vg_T, &e->vg_off};
+        for (DevBuf* b : cloud_bufs) b->release();
         for (auto& v : e->ev) for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         for (cudaEvent_t x : e->ev_pool) cudaEventDestroy(x);
         for (int i = 0; i < 2; i++) { e->pipe_qdesc[i].release(); e->pipe_qids[i].release(); if (e->pipe_copied[i]) cudaEventDestroy(e->pipe_copied[i]); if (e->pipe_done[i]) cudaEventDestroy(e->pipe_done[i]); }
