@@ -138,9 +138,9 @@ int scl_query_batch(scl_engine* e, const scl_batch_query* q, scl_batch_result* r
 int scl_query_batch_dev(scl_engine* e, const scl_batch_query* q, scl_batch_result* r);
 /* Pipelined host-buffer form, for a caller that streams batches (loopClosureThread draining a backlog,
  * distributedMapping.h:1450-1473): submit returns as soon as the batch is enqueued, so the next batch can be
- * submitted at once and its host-to-device copy (a second stream, double-buffered staging) overlaps the kernels
- * of this one. scl_query_batch_wait(ticket) blocks until that batch's results are in the host arrays of r.
- * At most two batches may be in flight; q_desc and the result arrays should be page-locked host memory (pageable
+* submitted at once and its host-to-device copy (a second stream, one staging buffer per batch in flight) overlaps
+ * the kernels of this one. scl_query_batch_wait(ticket) blocks until that batch's results are in the host arrays of r.
+ * At most four batches may be in flight (tickets are consecutive; wait for them in order); q_desc and the result arrays should be page-locked host memory (pageable
  * memory works but serialises the copies) and must stay valid until the wait returns. */
 int scl_query_batch_submit(scl_engine* e, const scl_batch_query* q, scl_batch_result* r, int* ticket);
 int scl_query_batch_wait(scl_engine* e, int ticket);

@@ -388,7 +388,7 @@ int scl_destroy(scl_engine* e)
         for (DevBuf* b : cloud_bufs) b->release();
         for (auto& v : e->ev) for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         for (cudaEvent_t x : e->ev_pool) cudaEventDestroy(x);
-        for (int i = 0; i < 2; i++) { e->pipe_qdesc[i].release(); e->pipe_qids[i].release(); if (e->pipe_copied[i]) cudaEventDestroy(e->pipe_copied[i]); if (e->pipe_done[i]) cudaEventDestroy(e->pipe_done[i]); }
+        for (int i = 0; i < scl_engine::kPipeDepth; i++) { e->pipe_qdesc[i].release(); e->pipe_qids[i].release(); if (e->pipe_copied[i]) cudaEventDestroy(e->pipe_copied[i]); if (e->pipe_done[i]) cudaEventDestroy(e->pipe_done[i]); }
         if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
         if (e->own_stream) cudaStreamDestroy(e->stream);
     }
@@ -566,11 +566,11 @@ int scl_query_batch_submit(scl_engine* e, const scl_batch_query* q, scl_batch_re
     LOCK();
     if (!ticket) FAIL(SCL_ERR_INVALID, "null ticket");
     int rc = check_host_query(e, q, r); if (rc) return rc;
-    const int b = (int)(e->pipe_next & 1);
-    if (e->pipe_busy[b]) FAIL(SCL_ERR_INVALID, "two batches are already in flight: wait for the older one first");
+    const int b = (int)(e->pipe_next % scl_engine::kPipeDepth);
+    if (e->pipe_busy[b]) FAIL(SCL_ERR_INVALID, "four batches are already in flight: wait for the oldest one first");
     if (!e->copy_stream) {
         CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < scl_engine::kPipeDepth; i++) {
             CK(cudaEventCreateWithFlags(&e->pipe_copied[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&e->pipe_done[i], cudaEventDisableTiming));
         }
@@ -579,7 +579,7 @@ int scl_query_batch_submit(scl_engine* e, const scl_batch_query* q, scl_batch_re
     const size_t RS = e->RS();
     const float* dq = nullptr; const int32_t* di = nullptr;
     if (Q > 0) {
-        /* staging buffer b was last read by the batch submitted two calls ago, whose wait has returned (pipe_busy) */
+        /* staging buffer b was last read by the batch submitted kPipeDepth calls ago, whose wait has returned (pipe_busy) */
         if (q->q_desc) {
             CK(e->pipe_qdesc[b].ensure((size_t)Q * RS * 4));
             CK(cudaMemcpyAsync(e->pipe_qdesc[b].p, q->q_desc, (size_t)Q * RS * 4, cudaMemcpyHostToDevice, e->copy_stream));
@@ -607,14 +607,14 @@ int scl_query_batch_wait(scl_engine* e, int ticket)
     cudaEvent_t ev;
     {
         std::lock_guard<std::mutex> lk(e->mu);
-        const int b = ticket & 1;
-        if (!e->pipe_busy[b]) FAIL(SCL_ERR_INVALID, "no batch in flight for this ticket");
+        const int b = ticket % scl_engine::kPipeDepth;
+        if (ticket < 0 || !e->pipe_busy[b]) FAIL(SCL_ERR_INVALID, "no batch in flight for this ticket");
         ev = e->pipe_done[b];
     }
     cudaSetDevice(e->device);
     cudaError_t err = cudaEventSynchronize(ev);              /* outside the lock: inserts and submits may proceed meanwhile */
     std::lock_guard<std::mutex> lk(e->mu);
-    e->pipe_busy[ticket & 1] = false;
+    e->pipe_busy[ticket % scl_engine::kPipeDepth] = false;
     if (err != cudaSuccess) { e->err = std::string("cudaEventSynchronize: ") + cudaGetErrorString(err); return SCL_ERR_CUDA; }
     return SCL_OK;
 }

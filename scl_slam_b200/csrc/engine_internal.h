@@ -62,9 +62,10 @@ struct scl_engine {
     size_t gbins_scans = 0;
     /* pipelined host-buffer queries (scl_query_batch_submit / _wait) */
     cudaStream_t copy_stream = nullptr;
-    DevBuf pipe_qdesc[2], pipe_qids[2];
-    cudaEvent_t pipe_copied[2] = {nullptr, nullptr}, pipe_done[2] = {nullptr, nullptr};
-    bool pipe_busy[2] = {false, false};
+    static constexpr int kPipeDepth = 4;   /* batches in flight */
+    DevBuf pipe_qdesc[kPipeDepth], pipe_qids[kPipeDepth];
+    cudaEvent_t pipe_copied[kPipeDepth] = {}, pipe_done[kPipeDepth] = {};
+    bool pipe_busy[kPipeDepth] = {};
     long long pipe_next = 0;
     /* per-stage event timing */
     bool profiling = false;

@@ -301,13 +301,14 @@ class ScanContextB200:
         self._ck(self.lib.scl_query_batch(self.h, C.byref(q), C.byref(r)))
         return out
 
-    def query_batch_submit(self, q_desc, out, K=None, n_db=None, metric=0):
-        """Pipelined host-buffer query (scl_query_batch_submit): q_desc and the arrays of `out` (scl_batch_result field
-        names -> numpy arrays, ideally page-locked) must stay alive until query_batch_wait(ticket) returns."""
+    def query_batch_submit(self, q_desc, out, K=None, n_db=None, metric=0, q_ids=None):
+        """Pipelined host-buffer query (scl_query_batch_submit): q_desc (fresh descriptors) or q_ids (keys of stored entries,
+        what detectIntra/InterLoopClosureID take) and the arrays of `out` (scl_batch_result field names -> numpy arrays,
+        ideally page-locked) must stay alive until query_batch_wait(ticket) returns."""
         K = K or self.K
-        Q = q_desc.shape[0]
+        Q = q_desc.shape[0] if q_desc is not None else q_ids.shape[0]
         n_db = self.getSize() if n_db is None else n_db
-        q = SclBatchQuery(q_desc.ctypes.data, None, Q, K, n_db, metric)
+        q = SclBatchQuery(q_desc.ctypes.data if q_desc is not None else None, q_ids.ctypes.data if q_ids is not None else None, Q, K, n_db, metric)
         r = SclBatchResult(*[out[k].ctypes.data if out.get(k) is not None else None for k in
                              ("cand_ids", "cand_d2", "cand_dist", "cand_shift", "best_id", "best_dist", "best_shift")])
         t = C.c_int()
