@@ -187,19 +187,45 @@ def run_ours(args):
         own_dist = blob2[:QK * 8].view(torch.float64).view(Q, K)
         own_shift = blob2[QK * 8:].view(torch.int32).view(Q, K)
         gath2 = torch.empty((world, QK * 12), dtype=torch.uint8, device=dev)
-    # ring_key, knn_tc, knn_rerank, knn_exact (fallback list), knn_merge, ids_to_local, scdist (+ merge_topk, combine_owned)
-    launches_per_step = 7 + (2 if world > 1 else 0)
+    # ring_key, knn_tc, knn_rerank, knn_exact (fallback list), knn_merge, scdist (+ merge_topk / combine_owned, or the two
+    # exchange kernels of k7_exchange.cu)
+    launches_per_step = 6 + (2 if world > 1 else 0)
+    # N > 1: the two exchange points run over NVLink peer memory (one kernel each: store to every peer, flag, wait, merge);
+    # the NCCL all-gather form is kept for --nccl-exchange and as the fallback when the peers' buffers cannot be mapped
+    use_p2p = False
+    p2p_note = None
+    if world > 1 and not args.nccl_exchange:
+        try:
+            handle = e.xchg_create(world, Q * K)
+            handles = [None] * world
+            dist.all_gather_object(handles, handle)
+            e.xchg_open(world, rank, handles)
+            use_p2p = True
+        except Exception as ex:                                   # noqa: BLE001 - any failure means "use NCCL"
+            p2p_note = str(ex)[:200]
+        ok = torch.tensor([1 if use_p2p else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        use_p2p = bool(ok.item())
+    seq = [0]
 
-    def step(q_dev=q_dev):
+    def step(q_dev=q_dev, p2p=None):
+        p2p = use_p2p if p2p is None else p2p
         if world == 1:
             e.query_batch_dev(q_dev, None, Q, K, n_local, 0, local)
             return
         e.knn_batch_dev(q_dev, Q, K, n_local, 0, loc_ids, loc_d2)                       # K2 + K3 on the shard
-        dist.all_gather_into_tensor(gath1, blob1)
-        e.merge_topk_dev(world, Q, K, gath1, gath1[:, QK * 4:], QK * 8, merged["cand_ids"], merged["cand_d2"])
+        if p2p:
+            seq[0] += 1
+            e.xchg_merge_topk_dev(seq[0], Q, K, blob1, merged["cand_ids"], merged["cand_d2"])
+        else:
+            dist.all_gather_into_tensor(gath1, blob1)
+            e.merge_topk_dev(world, Q, K, gath1, gath1[:, QK * 4:], QK * 8, merged["cand_ids"], merged["cand_d2"])
         e.scdist_owned_dev(q_dev, Q, K, merged["cand_ids"], own_dist, own_shift)        # K4 on the owned candidates only
-        dist.all_gather_into_tensor(gath2, blob2)
-        e.combine_owned_dev(world, Q, K, merged["cand_ids"], gath2, gath2[:, QK * 8:], QK * 12, merged)
+        if p2p:
+            e.xchg_combine_dev(seq[0], Q, K, blob2, merged["cand_ids"], merged)
+        else:
+            dist.all_gather_into_tensor(gath2, blob2)
+            e.combine_owned_dev(world, Q, K, merged["cand_ids"], gath2, gath2[:, QK * 8:], QK * 12, merged)
 
     def barrier():
         if world > 1:
@@ -209,6 +235,19 @@ def run_ours(args):
     # L2 hygiene: the 84 MB key matrix alone would fit the 126 MB L2, so a 512 MB buffer is
     # rewritten between steps, OUTSIDE the per-step event pairs (B200_PROFILING.md timing rules).
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    if use_p2p:
+        # one step each way: the peer-memory exchange must reproduce the NCCL form exactly, on every rank
+        step(p2p=False)
+        torch.cuda.synchronize()
+        ref_out = {k: merged[k].clone() for k in ("cand_ids", "cand_d2", "cand_dist", "cand_shift", "best_id", "best_dist", "best_shift")}
+        step(p2p=True)
+        torch.cuda.synchronize()
+        same = all(bool(torch.equal(merged[k].view(torch.uint8), ref_out[k].view(torch.uint8))) for k in ref_out)
+        ok = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not bool(ok.item()):
+            use_p2p = False
+            p2p_note = "peer-memory exchange disagreed with the NCCL form: disabled"
     for _ in range(max(args.warmup, 3)):
         step()
         flush.zero_()
@@ -338,8 +377,8 @@ def run_ours(args):
         assert np.array_equal(outp["best_id"].numpy(), merged["best_id"].cpu().numpy())
         e2e = {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(q_host.nbytes), "d2h_bytes_per_step": int(sum(v.nbytes for v in res.values())),
-               "api": "per rank: pinned host queries -> scl_knn_batch_dev, all-gather, scl_merge_topk_dev, scl_scdist_owned_dev, "
-                      "all-gather, scl_combine_owned_dev -> winners to pinned host memory; synchronous steps"}
+               "api": "per rank: pinned host queries -> scl_knn_batch_dev, exchange + global top-K, scl_scdist_owned_dev, "
+                      "exchange + combine -> winners to pinned host memory; synchronous steps"}
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- parity spot check on what was just measured (size-independent property of D3) ----
@@ -384,7 +423,8 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+f64",
         "data": "synthetic", "impl": "ours",
         "config": {"workload": WORKLOAD, "db_keyframes": n_db, "queries_per_step": Q, "top_k": K, "rings": R, "sectors": S,
-                   "sharding": f"key mod {world}" if world > 1 else "none", "l2": "512 MB buffer rewritten between timed steps (outside the per-step CUDA-event pairs)"},
+                   "sharding": f"key mod {world}" if world > 1 else "none",
+                   "exchange": ("nvlink peer memory, fused with the merge kernels (k7_exchange.cu)" if use_p2p else "nccl all-gather x2" + (f" ({p2p_note})" if p2p_note else "")) if world > 1 else "none", "l2": "512 MB buffer rewritten between timed steps (outside the per-step CUDA-event pairs)"},
         "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
         "stage_ms_per_step": {k: v[0] / max(v[1], 1) for k, v in stage.items()},
         "roofline": roof, "clocks": clocks,
@@ -553,6 +593,7 @@ def main():
     ap.add_argument("--n-db", type=int, default=N_DB, help="database size (default: the 1M workload)")
     ap.add_argument("--cpu-sample", type=int, default=256, help="queries per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: exchange with NCCL all-gathers instead of NVLink peer memory")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -168,6 +168,19 @@ int scl_scdist_owned_dev(scl_engine* e, const float* q_desc_dev, const int32_t* 
 int scl_combine_owned_dev(scl_engine* e, int world, int Q, int K, const int32_t* q_ids, const int32_t* cand_ids, const void* dist_base,
                           const void* shift_base, uint64_t rank_stride_bytes, scl_batch_result* merged);
 
+/* The same two exchange points over NVLink peer memory instead of NCCL (csrc/k7_exchange.cu): every rank creates an exchange
+ * buffer and hands its 64-byte IPC handle to the others (any side channel: torch.distributed, MPI, a file); after
+ * scl_xchg_open, scl_xchg_merge_topk_dev replaces {all-gather, scl_merge_topk_dev} and scl_xchg_combine_dev replaces
+ * {all-gather, scl_combine_owned_dev}: one kernel each stores this rank's block into every peer's buffer, raises a flag,
+ * waits for all ranks' flags and merges. seq = 1, 2, 3, ... must advance by one per query step, identically on all ranks;
+ * my_block_dev = [ids i32 Q*K | d2 f32 Q*K] resp. [dist f64 Q*K | shift i32 Q*K], 16-byte aligned; Q*K a multiple of 4. */
+int scl_xchg_create(scl_engine* e, int world, int max_qk, unsigned char* handle64);
+int scl_xchg_open(scl_engine* e, int world, int rank, const unsigned char* handles /* world x 64 bytes, rank-major */);
+int scl_xchg_merge_topk_dev(scl_engine* e, int seq, int Q, int K, const void* my_block_dev, int32_t* out_ids, float* out_d2);
+int scl_xchg_combine_dev(scl_engine* e, int seq, int Q, int K, const void* my_block_dev, const int32_t* q_ids, const int32_t* cand_ids,
+                         scl_batch_result* merged);
+int scl_xchg_close(scl_engine* e);
+
 /* ---- ring-key kNN variant ---------------------------------------------
  * mode 0 = automatic (tensor-core prefilter for batches >= 64 queries on >= 32768 keys, exact
  * CUDA-core kernel otherwise), 1 = always exact, 2 = always tensor core. Both produce identical

@@ -374,6 +374,8 @@ int scl_destroy(scl_engine* e)
         std::lock_guard<std::mutex> lk(e->mu);
         cudaSetDevice(e->device);
         cudaStreamSynchronize(e->stream);
+        for (int r = 0; r < 16; r++) if (e->xchg_peer_map[r]) cudaIpcCloseMemHandle(e->xchg_peer_map[r]);
+        if (e->xchg_buf) cudaFree(e->xchg_buf);
         cudaFree(e->d_desc); cudaFree(e->d_keys); cudaFree(e->d_knorm); cudaFree(e->d_kn2max); cudaFree(e->d_kimg);
         DevBuf* bufs[] = {&e->pts, &e->offsets, &e->gbins, &e->tickets, &e->stage_desc, &e->stage_keys, &e->stage_knorm,
                           &e->bins_ring, &e->bins_sector, &e->qdesc, &e->qids, &e->qlocal, &e->qkeys, &e->qknorm, &e->part_ids,
@@ -665,6 +667,80 @@ int scl_combine_owned_dev(scl_engine* e, int world, int Q, int K, const int32_t*
     if (!cand_ids || !dist_base || !shift_base || !m) FAIL(SCL_ERR_INVALID, "null argument");
     CK(scl_launch_combine_owned(world, Q, K, q_ids, cand_ids, dist_base, shift_base, (size_t)rank_stride_bytes, m->cand_dist, m->cand_shift,
                                 m->best_id, m->best_dist, m->best_shift, e->stream));
+    return SCL_OK;
+}
+
+// ---- peer-memory exchange (k7_exchange.cu) ------------------------------------------------------------------------
+int scl_xchg_create(scl_engine* e, int world, int max_qk, unsigned char* handle64)
+{
+    LOCK();
+    if (world < 2 || world > 16 || max_qk < 1 || !handle64) FAIL(SCL_ERR_INVALID, "bad arguments");
+    if (e->xchg_buf) FAIL(SCL_ERR_INVALID, "exchange buffer exists already");
+    XchgView& x = e->xchg;
+    x.world = world; x.rank = -1;
+    x.flag_off = 0; x.ticket_off = 128;
+    x.slot_bytes[0] = ((size_t)max_qk * 8 + 15) / 16 * 16;
+    x.slot_bytes[1] = ((size_t)max_qk * 12 + 15) / 16 * 16;
+    x.data_off[0] = 256;
+    x.data_off[1] = x.data_off[0] + 2 * (size_t)world * x.slot_bytes[0];
+    e->xchg_bytes = x.data_off[1] + 2 * (size_t)world * x.slot_bytes[1];
+    e->xchg_qk = max_qk;
+    CK(cudaMalloc(&e->xchg_buf, e->xchg_bytes));
+    CK(cudaMemset(e->xchg_buf, 0, e->xchg_bytes));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, e->xchg_buf));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    return SCL_OK;
+}
+
+int scl_xchg_open(scl_engine* e, int world, int rank, const unsigned char* handles)
+{
+    LOCK();
+    if (!e->xchg_buf || world != e->xchg.world || rank < 0 || rank >= world || !handles) FAIL(SCL_ERR_INVALID, "bad arguments");
+    for (int r = 0; r < world; r++) {
+        if (r == rank) { e->xchg.peer[r] = static_cast<unsigned char*>(e->xchg_buf); continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * 64, 64);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        e->xchg_peer_map[r] = p;
+        e->xchg.peer[r] = static_cast<unsigned char*>(p);
+    }
+    e->xchg.rank = rank;
+    e->xchg_open = true;
+    return SCL_OK;
+}
+
+int scl_xchg_close(scl_engine* e)
+{
+    LOCK();
+    cudaStreamSynchronize(e->stream);
+    for (int r = 0; r < 16; r++) if (e->xchg_peer_map[r]) { cudaIpcCloseMemHandle(e->xchg_peer_map[r]); e->xchg_peer_map[r] = nullptr; }
+    if (e->xchg_buf) { cudaFree(e->xchg_buf); e->xchg_buf = nullptr; }
+    e->xchg_open = false;
+    return SCL_OK;
+}
+
+int scl_xchg_merge_topk_dev(scl_engine* e, int seq, int Q, int K, const void* my_block_dev, int32_t* out_ids, float* out_d2)
+{
+    LOCK();
+    if (!e->xchg_open) FAIL(SCL_ERR_INVALID, "exchange not open");
+    if (seq < 1 || Q < 0 || K < 1 || (long long)Q * K > e->xchg_qk || ((long long)Q * K) % 4 || !my_block_dev || !out_ids || !out_d2)
+        FAIL(SCL_ERR_INVALID, "bad arguments (Q*K must be a multiple of 4 within the size given to scl_xchg_create)");
+    CK(scl_launch_xchg_merge_topk(e->xchg, seq, Q, K, my_block_dev, out_ids, out_d2, e->stream));
+    return SCL_OK;
+}
+
+int scl_xchg_combine_dev(scl_engine* e, int seq, int Q, int K, const void* my_block_dev, const int32_t* q_ids, const int32_t* cand_ids,
+                         scl_batch_result* m)
+{
+    LOCK();
+    if (!e->xchg_open) FAIL(SCL_ERR_INVALID, "exchange not open");
+    if (seq < 1 || Q < 0 || K < 1 || (long long)Q * K > e->xchg_qk || ((long long)Q * K) % 4 || !my_block_dev || !cand_ids || !m)
+        FAIL(SCL_ERR_INVALID, "bad arguments (Q*K must be a multiple of 4 within the size given to scl_xchg_create)");
+    CK(scl_launch_xchg_combine(e->xchg, seq, Q, K, my_block_dev, q_ids, cand_ids, m->cand_dist, m->cand_shift, m->best_id, m->best_dist,
+                               m->best_shift, e->stream));
     return SCL_OK;
 }
 

@@ -56,6 +56,9 @@ struct scl_engine {
     bool tc_state_clean = false;           /* slots and the next fail counter were reset by the last re-rank kernel */
     int tc_slots_rows = 0;                 /* rows of tc_slots known to be clean */
     int* tc_last_fail = nullptr;           /* the counter the last batch used */
+    /* peer-memory exchange (k7_exchange.cu) */
+    void* xchg_buf = nullptr; size_t xchg_bytes = 0; int xchg_qk = 0;
+    XchgView xchg{}; bool xchg_open = false; void* xchg_peer_map[16] = {};
     int scdist_owned_hint = 0;             /* K4 launch: expected candidates per query held by this shard (0 = all K) */
     DevBuf icp_src, icp_tgt, icp_raw, icp_grid[2][5], icp_acc, icp_nn;
     DevBuf vg_in, vg_world, vg_out, vg_keys[2], vg_vals[2], vg_head, vg_ord, vg_temp, vg_misc, vg_T, vg_off;

@@ -88,3 +88,16 @@ cudaError_t scl_launch_voxel_grid(const void* pts, int n, int stride_bytes, floa
                                   uint32_t* keys_a, uint32_t* keys_b, int* vals_a, int* vals_b, int* head, int* ord,
                                   void* temp, size_t temp_bytes, void* out_xyzi, int* n_out, cudaStream_t stream);
 cudaError_t scl_launch_pack_xyzi(const void* pts, int n, int stride_bytes, void* out_xyzi, cudaStream_t stream);
+
+// K7 (k7_exchange.cu): the sharded query's two exchange points over NVLink peer memory, fused with their merge kernels.
+// Every rank's exchange buffer has the same layout; peer[r] is rank r's buffer as mapped into this process.
+struct XchgView {
+    unsigned char* peer[16];
+    int world, rank;
+    size_t data_off[2], slot_bytes[2];    /* per exchange point: [2 parities][world] slots */
+    size_t flag_off;                      /* int flags[2 points][16 ranks] */
+    size_t ticket_off;                    /* int tickets[2] */
+};
+cudaError_t scl_launch_xchg_merge_topk(const XchgView& x, int seq, int Q, int K, const void* my_block, int32_t* out_ids, float* out_d2, cudaStream_t stream);
+cudaError_t scl_launch_xchg_combine(const XchgView& x, int seq, int Q, int K, const void* my_block, const int32_t* q_ids, const int32_t* cand_ids,
+                                    double* out_dist, int32_t* out_shift, int32_t* best_id, double* best_dist, int32_t* best_shift, cudaStream_t stream);

@@ -28,6 +28,7 @@ EXPORTS = [
     "scl_merge_shards_dev", "scl_icp", "scl_set_profiling", "scl_stage_time", "scl_set_knn_mode", "scl_knn_stats",
     "scl_default_ransac_params", "scl_verify_ransac", "scl_knn_batch_dev", "scl_merge_topk_dev", "scl_scdist_owned_dev", "scl_combine_owned_dev",
     "scl_query_batch_submit", "scl_query_batch_wait", "scl_voxel_grid", "scl_assemble_submap", "scl_build_insert_filtered",
+    "scl_xchg_create", "scl_xchg_open", "scl_xchg_merge_topk_dev", "scl_xchg_combine_dev", "scl_xchg_close",
     "scl_wire_pose6_to_transform", "scl_wire_loop_between", "scl_wire_make_loop_info", "scl_wire_make_global_descriptor",
     "scl_wire_encode_global_descriptor", "scl_wire_decode_global_descriptor", "scl_wire_encode_loop_info", "scl_wire_decode_loop_info",
 ]
@@ -58,7 +59,7 @@ def wire_loop_between(T_align, pose_cur6, pose_pre6, quat_from_rpy=False):
     a = np.ascontiguousarray(pose_cur6, np.float32).reshape(6)
     b = np.ascontiguousarray(pose_pre6, np.float32).reshape(6)
     out = SclTransform()
-    lib.scl_wire_loop_between(C.c_void_p(T.ctypes.data), C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data), int(bool(quat_from_rpy)), C.byref(out))
+    lib.scl_wire_loop_between(T.ctypes.data, a.ctypes.data, b.ctypes.data, int(bool(quat_from_rpy)), C.byref(out))
     return out.as_tuple()
 
 
@@ -66,7 +67,7 @@ def wire_pose6_to_transform(pose6):
     lib = load_library()
     a = np.ascontiguousarray(pose6, np.float32).reshape(6)
     out = SclTransform()
-    lib.scl_wire_pose6_to_transform(C.c_void_p(a.ctypes.data), C.byref(out))
+    lib.scl_wire_pose6_to_transform(a.ctypes.data, C.byref(out))
     return out.as_tuple()
 
 
@@ -135,6 +136,22 @@ def load_library():
     lib.scl_merge_shards_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.POINTER(SclBatchResult)]
     lib.scl_knn_batch_dev.argtypes = [C.c_void_p, C.POINTER(SclBatchQuery), C.c_void_p, C.c_void_p]
+    lib.scl_voxel_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.POINTER(C.c_int)]
+    lib.scl_assemble_submap.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.POINTER(C.c_int)]
+    lib.scl_build_insert_filtered.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int8, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    lib.scl_xchg_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.scl_xchg_open.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.scl_xchg_close.argtypes = [C.c_void_p]
+    lib.scl_xchg_merge_topk_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.scl_xchg_combine_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SclBatchResult)]
+    lib.scl_wire_pose6_to_transform.argtypes = [C.c_void_p, C.POINTER(SclTransform)]
+    lib.scl_wire_loop_between.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(SclTransform)]
+    lib.scl_wire_make_loop_info.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SclLoopInfo)]
+    lib.scl_wire_make_global_descriptor.argtypes = [C.c_int, C.c_void_p, C.c_int, C.POINTER(SclTransform), C.c_int, C.c_void_p, C.POINTER(SclGlobalDescriptor)]
+    lib.scl_wire_encode_global_descriptor.argtypes = [C.POINTER(SclGlobalDescriptor), C.c_void_p, C.c_int]
+    lib.scl_wire_decode_global_descriptor.argtypes = [C.c_void_p, C.c_int, C.POINTER(SclGlobalDescriptor)]
+    lib.scl_wire_encode_loop_info.argtypes = [C.POINTER(SclLoopInfo), C.c_void_p, C.c_int]
+    lib.scl_wire_decode_loop_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(SclLoopInfo)]
     lib.scl_merge_topk_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.scl_scdist_owned_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.scl_combine_owned_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -368,6 +385,27 @@ class ScanContextB200:
         self._ck(self.lib.scl_combine_owned_dev(self.h, world, Q, K, None, _ptr(cand_ids), _ptr(dist_base), _ptr(shift_base),
                                                 rank_stride_bytes, C.byref(r)))
 
+    # ---- peer-memory exchange (csrc/k7_exchange.cu) ----------------------------------------
+    def xchg_create(self, world, max_qk):
+        h = (C.c_ubyte * 64)()
+        self._ck(self.lib.scl_xchg_create(self.h, world, max_qk, h))
+        return bytes(h)
+
+    def xchg_open(self, world, rank, handles):
+        buf = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+        self._ck(self.lib.scl_xchg_open(self.h, world, rank, buf))
+
+    def xchg_close(self):
+        self._ck(self.lib.scl_xchg_close(self.h))
+
+    def xchg_merge_topk_dev(self, seq, Q, K, my_block, out_ids, out_d2):
+        self._ck(self.lib.scl_xchg_merge_topk_dev(self.h, seq, Q, K, _ptr(my_block), _ptr(out_ids), _ptr(out_d2)))
+
+    def xchg_combine_dev(self, seq, Q, K, my_block, cand_ids, out):
+        r = SclBatchResult(*[_ptr(out.get(k)) for k in
+                             ("cand_ids", "cand_d2", "cand_dist", "cand_shift", "best_id", "best_dist", "best_shift")])
+        self._ck(self.lib.scl_xchg_combine_dev(self.h, seq, Q, K, _ptr(my_block), None, _ptr(cand_ids), C.byref(r)))
+
     # ---- geometric verification (distributedMapping.h:1108-1132) ---------------------------
     def icp(self, src, tgt, max_corr_dist=100.0, max_iterations=50, trans_eps=1e-6, fitness_eps=1e-6):
         s, ns, stride = _cloud(src)
@@ -400,7 +438,7 @@ class ScanContextB200:
         p, n, stride = _cloud(pts)
         out = np.empty((max(n, 1), 4), np.float32)
         m = C.c_int()
-        self._ck(self.lib.scl_voxel_grid(self.h, p.ctypes.data, n, stride, C.c_float(leaf), out.ctypes.data, C.byref(m)))
+        self._ck(self.lib.scl_voxel_grid(self.h, p.ctypes.data, n, stride, leaf, out.ctypes.data, C.byref(m)))
         return out[:m.value].copy()
 
     def assemble_submap(self, clouds, poses6, leaf):
@@ -416,7 +454,7 @@ class ScanContextB200:
         out = np.empty((max(pts.shape[0], 1), 4), np.float32)
         m = C.c_int()
         self._ck(self.lib.scl_assemble_submap(self.h, pts.ctypes.data, offs.ctypes.data, len(clouds), stride, poses.ctypes.data,
-                                              C.c_float(leaf), out.ctypes.data, C.byref(m)))
+                                              leaf, out.ctypes.data, C.byref(m)))
         return out[:m.value].copy()
 
     def makeAndSaveDescriptorAndKeyFiltered(self, scan, leaf, robot, index):
@@ -425,6 +463,6 @@ class ScanContextB200:
         p, n, stride = _cloud(scan)
         out = np.empty(self.params.num_ring * self.params.num_sector, np.float32)
         m = C.c_int()
-        self._ck(self.lib.scl_build_insert_filtered(self.h, p.ctypes.data, n, stride, C.c_float(leaf), C.c_int8(robot), index,
+        self._ck(self.lib.scl_build_insert_filtered(self.h, p.ctypes.data, n, stride, leaf, robot, index,
                                                     out.ctypes.data, C.byref(m)))
         return out, m.value

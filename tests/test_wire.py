@@ -65,7 +65,7 @@ def test_message_round_trips():
     cur = engine.SclTransform(1, 2, 3, 0, 0, 0, 1)
     pre6 = np.array([0.5, 0.25, 0.0, 0.0, 0.0, 0.3], np.float32)
     m = engine.SclGlobalDescriptor()
-    lib.scl_wire_make_global_descriptor(42, C.c_void_p(vals.ctypes.data), 1200, C.byref(cur), 1, C.c_void_p(pre6.ctypes.data), C.byref(m))
+    lib.scl_wire_make_global_descriptor(42, vals.ctypes.data, 1200, C.byref(cur), 1, pre6.ctypes.data, C.byref(m))
     assert m.index == 42 and m.n_values == 1200 and m.cur_pose.as_tuple() == cur.as_tuple()
     assert np.allclose(m.pre_pose.as_tuple(), engine.wire_pose6_to_transform(pre6))
     need = lib.scl_wire_encode_global_descriptor(C.byref(m), None, 0)
@@ -83,7 +83,7 @@ def test_message_round_trips():
     a = np.array([1, 2, 3, 0, 0, 0.5], np.float32)
     b = np.array([2, 2, 3, 0, 0, 0.4], np.float32)
     li = engine.SclLoopInfo()
-    lib.scl_wire_make_loop_info(1, 300, 12, C.c_float(0.17), C.c_void_p(T.ctypes.data), C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data), C.byref(li))
+    lib.scl_wire_make_loop_info(1, 300, 12, 0.17, T.ctypes.data, a.ctypes.data, b.ctypes.data, C.byref(li))
     assert (li.robot0, li.robot1, li.index0, li.index1) == (1, 1, 300, 12) and abs(li.noise - 0.17) < 1e-7
     assert np.allclose(li.bet_pose.as_tuple(), engine.wire_loop_between(T, a, b, False))
     buf2 = (C.c_ubyte * 76)()
