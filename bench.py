@@ -256,8 +256,11 @@ def run_ours(args):
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t_region0 = time.time()
+    align = torch.zeros(1, dtype=torch.int32, device=dev)
     for a, b in evs:
-        a.record()
+        if world > 1:
+            dist.all_reduce(align)           # stream-ordered: every rank enters the timed step together (the L2 flush of the
+        a.record()                           # previous step, outside the event pair, finishes at different times per rank)
         step()
         b.record()
         flush.zero_()

@@ -58,11 +58,10 @@ __device__ void publish_and_wait(const XchgView& x, int phase, int seq, const un
         const long long t0 = clock64();
         while (ld_acquire_sys(f) < seq) {
             if (clock64() - t0 > (8ll << 30)) __trap();          /* ~4 s: a peer is gone */
-            __nanosleep(200);
+            __nanosleep(40);
         }
     }
-    __syncthreads();
-    __threadfence_system();
+    __syncthreads();     /* the polling threads' acquire loads + this barrier order every thread's (volatile) reads of the slots after the flags */
 }
 
 // exchange point 1 + global top-K by (d2, id): block = [ids i32 Q*K | d2 f32 Q*K]
