@@ -661,6 +661,55 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
     const float eps0 = 3.0517578125e-05f * sn * sn;                 /* 2^-15 (|q| + |k|max)^2 */
     /* a certified top-K lies wholly below cut + |q|^2 (see below): keys at or above it need not enter the selection */
     const float d_lim = cut < inf ? cut + qn : inf;
+    /* Second, tighter filter before the key rows are fetched (nanoflann flavour only: libnabo's self-match rule can remove
+     * keys from the result). Every surviving group's minimum is the score of a distinct key, so the K-th smallest minimum
+     * m_K is undercut by K keys: the K-th nearest neighbour has exact d2 <= m_K + |q|^2 + eps, and a group whose minimum
+     * exceeds m_K + 2 eps holds no key that can beat it. About K of the ~3 K' groups remain. Groups that straddle the
+     * search bound may owe their minimum to a key outside it: they do not vote for m_K and are always kept. */
+    if (METRIC == 0 && n_grp > K && n_grp <= 128) {
+        unsigned v[4]; bool whole[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int c = lane + 32 * j;
+            whole[j] = c < n_grp && s_key[c] + 7 < n_db;
+            /* scores can be negative: order-preserving unsigned image of the float */
+            const unsigned b = c < n_grp ? __float_as_uint(s_g[c]) : 0u;
+            v[j] = whole[j] ? (b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u)) : 0xffffffffu;
+        }
+        unsigned mk = 0xffffffffu; int have = 0;
+        for (int r = 0; r < K; r++) {
+            const unsigned loc = min(min(v[0], v[1]), min(v[2], v[3]));
+            const unsigned w = __reduce_min_sync(0xffffffffu, loc);
+            if (w == 0xffffffffu) break;
+            /* remove ONE holder of the minimum (equal minima are distinct keys and count separately) */
+            const unsigned holders = __ballot_sync(0xffffffffu, loc == w);
+            if (lane == __ffs(holders) - 1) {
+                bool done = false;
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (!done && v[j] == w) { v[j] = 0xffffffffu; done = true; }
+            }
+            mk = w; have++;
+        }
+        if (have == K) {
+            const unsigned mb = mk ^ ((mk >> 31) ? 0x80000000u : 0xffffffffu);          /* back to float bits */
+            const float lim = __uint_as_float(mb) + 2.0f * eps0;
+            /* compact the list in place: positions only move down, lanes work in index order */
+            int n_new = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int c = lane + 32 * j;
+                const int key = c < n_grp ? s_key[c] : 0; const float g = c < n_grp ? s_g[c] : 0.0f;
+                const bool keep = c < n_grp && (!whole[j] || g <= lim);
+                __syncwarp();
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                const int pos = n_new + __popc(m & lt_mask);
+                if (keep) { s_key[pos] = key; s_g[pos] = g; }
+                n_new += __popc(m);
+                __syncwarp();
+            }
+            n_grp = n_new;
+        }
+    }
     float worst_err = 0.0f;
     int n_sel = 0;
     constexpr int UK = R <= 20 ? 4 : 2;                 /* key rows in flight per lane */
