@@ -186,7 +186,12 @@ int knn_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int
     KnnWorkspace ws;
     CK(e->part_ids.ensure((size_t)Q * splits * K * 4));
     CK(e->part_d2.ensure((size_t)Q * splits * K * 4));
-    ws.part_ids = e->part_ids.as<int32_t>(); ws.part_d2 = e->part_d2.as<float>(); ws.capacity = (size_t)Q * splits * K;
+    {
+        const void* old = e->knn_tickets.p;
+        CK(e->knn_tickets.ensure(((size_t)Q / 128 + 2) * 4));
+        if (old != e->knn_tickets.p) CK(cudaMemsetAsync(e->knn_tickets.p, 0, e->knn_tickets.cap, e->stream));   /* the kernel leaves them zero */
+    }
+    ws.part_ids = e->part_ids.as<int32_t>(); ws.part_d2 = e->part_d2.as<float>(); ws.tickets = e->knn_tickets.as<int>(); ws.capacity = (size_t)Q * splits * K;
     /* K3 variant: the tensor-core prefilter pays off once there is a batch to fill 128-row tiles and a
      * database worth streaming; single queries and small databases take the exact CUDA-core kernel. */
     const bool use_tc = scl_knn_tc_supported(R) && K <= scl_knn_tc_kprime() - 2 &&
@@ -378,7 +383,7 @@ int scl_destroy(scl_engine* e)
         if (e->xchg_buf) cudaFree(e->xchg_buf);
         cudaFree(e->d_desc); cudaFree(e->d_keys); cudaFree(e->d_knorm); cudaFree(e->d_kn2max); cudaFree(e->d_kimg);
         DevBuf* bufs[] = {&e->pts, &e->offsets, &e->gbins, &e->tickets, &e->stage_desc, &e->stage_keys, &e->stage_knorm,
-                          &e->bins_ring, &e->bins_sector, &e->qdesc, &e->qids, &e->qlocal, &e->qkeys, &e->qknorm, &e->part_ids,
+                          &e->bins_ring, &e->bins_sector, &e->knn_tickets, &e->qdesc, &e->qids, &e->qlocal, &e->qkeys, &e->qknorm, &e->part_ids,
                           &e->part_d2, &e->cand_ids, &e->cand_d2, &e->cand_local, &e->cand_dist, &e->cand_shift, &e->best_id,
                           &e->best_dist, &e->best_shift, &e->tc_queues, &e->tc_queue_cnt, &e->tc_slots,
                           &e->tc_fail_list, &e->tc_fail_count, &e->tc_err_probe, &e->icp_src, &e->icp_tgt, &e->icp_raw, &e->icp_acc, &e->icp_nn,

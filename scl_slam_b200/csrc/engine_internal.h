@@ -49,6 +49,7 @@ struct scl_engine {
     int search_radius = 0;                 /* round(0.5*SEARCH_RATIO*S), descriptor.h:1545 */
     /* scratch */
     DevBuf pts, offsets, gbins, tickets, stage_desc, stage_keys, stage_knorm, bins_ring, bins_sector;
+    DevBuf knn_tickets;
     DevBuf qdesc, qids, qlocal, qkeys, qknorm, part_ids, part_d2, cand_ids, cand_d2, cand_local, cand_dist, cand_shift,
         best_id, best_dist, best_shift;
     DevBuf tc_queues, tc_queue_cnt, tc_slots, tc_fail_list, tc_fail_count, tc_err_probe;

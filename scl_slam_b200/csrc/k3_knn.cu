@@ -54,11 +54,51 @@ __device__ __forceinline__ float key_d2(const float (&q)[R], const float* __rest
     return result;
 }
 
+// k-way merge of the per-split sorted lists of one query by one warp; order = (d2, id). The lists were written by other
+// CTAs of the same launch: they are read through L2 (__ldcg).
+__device__ void merge_splits_warp(const int32_t* __restrict__ pi, const float* __restrict__ pd, int splits, int K, int lane,
+                                  int32_t* __restrict__ out_ids, float* __restrict__ out_d2)
+{
+    constexpr int kPer = kMaxSplits / 32;
+    int head[kPer];
+#pragma unroll
+    for (int s = 0; s < kPer; s++) head[s] = 0;
+    for (int r = 0; r < K; r++) {
+        float bd = __int_as_float(0x7f800000); int bi = 0x7fffffff; int bs = -1;
+#pragma unroll
+        for (int s = 0; s < kPer; s++) {
+            const int sp = lane + 32 * s;
+            if (sp < splits && head[s] < K) {
+                const float d = __ldcg(pd + (size_t)sp * K + head[s]); const int id = __ldcg(pi + (size_t)sp * K + head[s]);
+                if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; bs = s; }
+            }
+        }
+        /* warp argmin on (d2, id) */
+        float wd = bd; int wi = bi;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, wd, off); const int oi = __shfl_xor_sync(0xffffffffu, wi, off);
+            if (od < wd || (od == wd && oi < wi)) { wd = od; wi = oi; }
+        }
+        const bool found = wi != 0x7fffffff;
+        if (bs >= 0 && bi == wi && bd == wd && found) {
+#pragma unroll
+            for (int s = 0; s < kPer; s++) if (s == bs) head[s]++;
+        }
+        if (lane == 0) {
+            out_ids[r] = found ? wi : -1;
+            out_d2[r] = found ? wd : FLT_MAX;
+        }
+    }
+}
+
 template <int R, int METRIC>
 __global__ void __launch_bounds__(kTQ) knn_exact_kernel(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys,
                                                         int n_db, int K, int split_len, int id_mul, int id_add,
                                                         const int32_t* __restrict__ qlist, const int* __restrict__ qcount,
-                                                        int32_t* __restrict__ part_ids, float* __restrict__ part_d2)
+                                                        int32_t* __restrict__ part_ids, float* __restrict__ part_d2,
+                                                        int* __restrict__ tickets /* [query tiles], zero between launches */,
+                                                        int32_t* __restrict__ out_ids, float* __restrict__ out_d2)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* sk = reinterpret_cast<float*>(smem_raw);                 /* [kTK][R] */
@@ -108,55 +148,30 @@ __global__ void __launch_bounds__(kTQ) knn_exact_kernel(const float* __restrict_
             if (count == K) worst = ld[(K - 1) * kTQ + t];
         }
     }
-    if (!active) return;
-    const size_t o = ((size_t)slot * gridDim.x + blockIdx.x) * K;
-    for (int i = 0; i < K; i++) {
-        part_d2[o + i] = i < count ? ld[i * kTQ + t] : __int_as_float(0x7f800000);
-        part_ids[o + i] = i < count ? li[i * kTQ + t] : 0x7fffffff;
+    if (active) {
+        const size_t o = ((size_t)slot * gridDim.x + blockIdx.x) * K;
+        for (int i = 0; i < K; i++) {
+            part_d2[o + i] = i < count ? ld[i * kTQ + t] : __int_as_float(0x7f800000);
+            part_ids[o + i] = i < count ? li[i * kTQ + t] : 0x7fffffff;
+        }
     }
-}
-
-// k-way merge of the per-split sorted lists of one query by one warp; order = (d2, id).
-__global__ void __launch_bounds__(128) knn_merge_kernel(const int32_t* __restrict__ part_ids, const float* __restrict__ part_d2,
-                                                        int Q, int splits, int K, const int32_t* __restrict__ qlist,
-                                                        const int* __restrict__ qcount, int32_t* __restrict__ out_ids, float* __restrict__ out_d2)
-{
-    const int lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (slot >= (qlist ? *qcount : Q)) return;
-    const int qi = qlist ? qlist[slot] : slot;
-    constexpr int kPer = kMaxSplits / 32;
-    int head[kPer];
-#pragma unroll
-    for (int s = 0; s < kPer; s++) head[s] = 0;
-    const int32_t* pi = part_ids + (size_t)slot * splits * K;
-    const float* pd = part_d2 + (size_t)slot * splits * K;
-    for (int r = 0; r < K; r++) {
-        float bd = __int_as_float(0x7f800000); int bi = 0x7fffffff; int bs = -1;
-#pragma unroll
-        for (int s = 0; s < kPer; s++) {
-            const int sp = lane + 32 * s;
-            if (sp < splits && head[s] < K) {
-                const float d = pd[(size_t)sp * K + head[s]]; const int id = pi[(size_t)sp * K + head[s]];
-                if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; bs = s; }
-            }
-        }
-        /* warp argmin on (d2, id) */
-        float wd = bd; int wi = bi;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const float od = __shfl_xor_sync(0xffffffffu, wd, off); const int oi = __shfl_xor_sync(0xffffffffu, wi, off);
-            if (od < wd || (od == wd && oi < wi)) { wd = od; wi = oi; }
-        }
-        const bool found = wi != 0x7fffffff;
-        if (bs >= 0 && bi == wi && bd == wd && found) {
-#pragma unroll
-            for (int s = 0; s < kPer; s++) if (s == bs) head[s]++;
-        }
-        if (lane == 0) {
-            out_ids[(size_t)qi * K + r] = found ? wi : -1;
-            out_d2[(size_t)qi * K + r] = found ? wd : FLT_MAX;
-        }
+    /* The last CTA of this query tile to get here (ticket) merges the tile's per-split lists: one launch instead of two,
+     * and a launch that has nothing to do (the tensor-core path's empty fallback list) ends at the early return above. */
+    __threadfence();
+    __syncthreads();
+    __shared__ int s_last;
+    if (t == 0) s_last = (atomicAdd(&tickets[blockIdx.y], 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (t == 0) tickets[blockIdx.y] = 0;
+    const int warp = t >> 5, lane = t & 31;
+    for (int s = warp; s < kTQ; s += kTQ / 32) {
+        const int sl = blockIdx.y * kTQ + s;
+        if (sl >= nq) break;
+        const int qq = qlist ? qlist[sl] : sl;
+        merge_splits_warp(part_ids + (size_t)sl * gridDim.x * K, part_d2 + (size_t)sl * gridDim.x * K, (int)gridDim.x, K, lane,
+                          out_ids + (size_t)qq * K, out_d2 + (size_t)qq * K);
     }
 }
 
@@ -181,14 +196,17 @@ __global__ void ids_to_local_kernel(const int32_t* __restrict__ ids, int n, int 
 
 template <int R>
 cudaError_t launch_exact(const float* qkeys, int Q, const float* keys, int n_db, int K, int metric, int splits, int split_len,
-                         int id_mul, int id_add, const int32_t* qlist, const int* qcount, KnnWorkspace ws, cudaStream_t stream)
+                         int id_mul, int id_add, const int32_t* qlist, const int* qcount, KnnWorkspace ws, int32_t* out_ids, float* out_d2,
+                         cudaStream_t stream)
 {
     const size_t smem = (size_t)kTK * R * 4 + (size_t)K * kTQ * 8;
     dim3 grid(splits, (Q + kTQ - 1) / kTQ);
     if (metric == 0)
-        knn_exact_kernel<R, 0><<<grid, kTQ, smem, stream>>>(qkeys, Q, keys, n_db, K, split_len, id_mul, id_add, qlist, qcount, ws.part_ids, ws.part_d2);
+        knn_exact_kernel<R, 0><<<grid, kTQ, smem, stream>>>(qkeys, Q, keys, n_db, K, split_len, id_mul, id_add, qlist, qcount, ws.part_ids, ws.part_d2,
+                                                            ws.tickets, out_ids, out_d2);
     else
-        knn_exact_kernel<R, 1><<<grid, kTQ, smem, stream>>>(qkeys, Q, keys, n_db, K, split_len, id_mul, id_add, qlist, qcount, ws.part_ids, ws.part_d2);
+        knn_exact_kernel<R, 1><<<grid, kTQ, smem, stream>>>(qkeys, Q, keys, n_db, K, split_len, id_mul, id_add, qlist, qcount, ws.part_ids, ws.part_d2,
+                                                            ws.tickets, out_ids, out_d2);
     return cudaGetLastError();
 }
 
@@ -215,17 +233,14 @@ cudaError_t scl_launch_knn_exact(const float* qkeys, int Q, const float* keys, i
     int split_len = (n_db + splits - 1) / splits;
     split_len = (split_len + kTK - 1) / kTK * kTK;
     if (split_len < kTK) split_len = kTK;
-    if ((size_t)Q * splits * K > ws.capacity) return cudaErrorInvalidValue;
+    if ((size_t)Q * splits * K > ws.capacity || !ws.tickets) return cudaErrorInvalidValue;
     cudaError_t err;
-    if (R == 20) err = launch_exact<20>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, stream);
-    else if (R == 40) err = launch_exact<40>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, stream);
-    else if (R == 10) err = launch_exact<10>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, stream);
-    else if (R == 80) err = launch_exact<80>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, stream);
+    if (R == 20) err = launch_exact<20>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, out_ids, out_d2, stream);
+    else if (R == 40) err = launch_exact<40>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, out_ids, out_d2, stream);
+    else if (R == 10) err = launch_exact<10>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, out_ids, out_d2, stream);
+    else if (R == 80) err = launch_exact<80>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, out_ids, out_d2, stream);
     else return cudaErrorNotSupported;
-    if (err != cudaSuccess) return err;
-    const int warps = 4;
-    knn_merge_kernel<<<(Q + warps - 1) / warps, warps * 32, 0, stream>>>(ws.part_ids, ws.part_d2, Q, splits, K, qlist, qcount, out_ids, out_d2);
-    return cudaGetLastError();
+    return err;
 }
 
 cudaError_t scl_launch_gather_rows(const float* src, const int32_t* rows, int n, int width, float* dst, cudaStream_t stream)

@@ -19,6 +19,7 @@ cudaError_t scl_launch_ring_keys(const float* desc_dev, int n, int R, int S, flo
 struct KnnWorkspace {
     int32_t* part_ids;   // [Q][splits][K]
     float* part_d2;      // [Q][splits][K]
+    int* tickets;        // [ceil(Q / 128)] zero between launches (the last CTA of a query tile merges its splits)
     size_t capacity;     // in entries
 };
 int scl_knn_splits(int Q, int n_db);
