@@ -573,3 +573,25 @@ def test_filtered_build_equals_filter_then_build(eng_mod):
     assert m == len(filt)
     assert np.array_equal(_bits(got), _bits(exp))
     assert e.getSize() == 1 and e.getIndex(0) == (2, 17)
+
+
+@pytest.mark.gpu
+def test_tensor_core_knn_sub_batches_equal_exact_kernel(eng_mod):
+    """A batch larger than one tensor-core launch (1024 queries) is cut into sub-batches that share the slots, the fail
+    counters and the hit queues: the result must still be bit-identical to the exact CUDA-core kernel, call after call."""
+    n, nq, K = 50000, 2100, 10
+    db = synth.desc_db(n, seed=61)
+    q = synth.desc_queries(db, nq, seed=62)[0].numpy()
+    e = eng_mod.ScanContextB200(numCandidates=K)
+    e.insert_batch(db.numpy())
+    e.set_knn_mode(1)
+    exp = e.query_batch(q_desc=q, K=K, n_db=n - 13, metric=0)
+    e.set_knn_mode(2)
+    for _ in range(3):                                   # repeated calls: the state the re-rank kernel leaves behind is reused
+        got = e.query_batch(q_desc=q, K=K, n_db=n - 13, metric=0)
+        for k in ("cand_ids", "cand_shift", "best_id", "best_shift"):
+            assert np.array_equal(got[k], exp[k]), k
+        assert np.array_equal(_bits(got["cand_d2"]), _bits(exp["cand_d2"]))
+        assert np.array_equal(_bits(got["cand_dist"]), _bits(exp["cand_dist"]))
+    st = e.knn_stats()
+    assert st["tc_queries"] == 3 * nq and st["fallback_queries"] == 0, st
