@@ -453,6 +453,16 @@ def run_ours(args):
         "knn": e.knn_stats(),
     }
     if world == 1:
+        # the reference's own call pattern: ONE detectInterLoopClosureID per keyframe against the whole database (host call:
+        # key in, id and yaw out, synchronous), descriptor.h:1676
+        last = e.getSize() - 1
+        for _ in range(3):
+            e.detectInterLoopClosureID(last)
+        t0 = time.perf_counter()
+        for i in range(50):
+            e.detectInterLoopClosureID(last - i)
+        line["single_query"] = {"us_per_call": (time.perf_counter() - t0) / 50 * 1e6, "api": "scl_query_inter (one key per call, synchronous)",
+                                "db_keyframes": e.getSize()}
         line["descriptors"] = descriptor_bench(engine, dev, pk, cpu=not args.no_cpu_baseline)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(e, n_local, q_dev, final, sample=args.cpu_sample)

@@ -188,7 +188,7 @@ int knn_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int
     CK(e->part_d2.ensure((size_t)Q * splits * K * 4));
     {
         const void* old = e->knn_tickets.p;
-        CK(e->knn_tickets.ensure(((size_t)Q / 128 + 2) * 4));
+        CK(e->knn_tickets.ensure(((size_t)Q / 128 + 16) * 4));          /* per 128-query tile, or per query of a handful */
         if (old != e->knn_tickets.p) CK(cudaMemsetAsync(e->knn_tickets.p, 0, e->knn_tickets.cap, e->stream));   /* the kernel leaves them zero */
     }
     ws.part_ids = e->part_ids.as<int32_t>(); ws.part_d2 = e->part_d2.as<float>(); ws.tickets = e->knn_tickets.as<int>(); ws.capacity = (size_t)Q * splits * K;

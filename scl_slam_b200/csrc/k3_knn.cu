@@ -175,6 +175,103 @@ __global__ void __launch_bounds__(kTQ) knn_exact_kernel(const float* __restrict_
     }
 }
 
+// The same search for a HANDFUL of queries (the reference's own call pattern: one detect*LoopClosureID per keyframe).
+// With thread = query a single query would leave 127 of 128 threads idle, so here thread = key: a CTA of 256 threads scores
+// KPT * 256 keys of one query (rows read straight from global memory, 80 contiguous bytes per thread), then picks its K
+// smallest (d2, id) in K rounds of block-wide argmin, and the last CTA of the query (ticket) merges the splits.
+// grid = (key splits, queries).
+constexpr int kSmallThreads = 256;
+template <int R, int METRIC, int KPT>
+__global__ void __launch_bounds__(kSmallThreads) knn_exact_small_kernel(const float* __restrict__ qkeys, const float* __restrict__ keys, int n_db,
+                                                                        int K, int split_len, int id_mul, int id_add, int32_t* __restrict__ part_ids,
+                                                                        float* __restrict__ part_d2, int* __restrict__ tickets,
+                                                                        int32_t* __restrict__ out_ids, float* __restrict__ out_d2)
+{
+    __shared__ float s_d[kSmallThreads / 32];
+    __shared__ int s_i[kSmallThreads / 32];
+    __shared__ int s_last;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int qi = blockIdx.y;
+    const float inf = __int_as_float(0x7f800000);
+    float q[R];
+#pragma unroll
+    for (int d = 0; d < R; d++) q[d] = __ldg(qkeys + (size_t)qi * R + d);
+    const int k0 = blockIdx.x * split_len;
+    const int k1 = min(n_db, k0 + split_len);
+    const float limit = (METRIC == 0) ? FLT_MAX : inf;
+    float d[KPT];
+#pragma unroll
+    for (int i = 0; i < KPT; i++) {
+        const int j = k0 + i * kSmallThreads + t;
+        float dd = inf;
+        if (j < k1) {
+            dd = key_d2<R, METRIC>(q, keys + (size_t)j * R);
+            if (METRIC == 1 && !(dd > FLT_EPSILON)) dd = inf;       /* libnabo self-match rule */
+            if (!(dd < limit)) dd = inf;                             /* never accepted by the trees (NaN included) */
+        }
+        d[i] = dd;
+    }
+    const size_t o = ((size_t)qi * gridDim.x + blockIdx.x) * K;
+    int r = 0;
+    for (; r < K; r++) {
+        float bd = inf; int bi = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < KPT; i++) if (d[i] < bd) { bd = d[i]; bi = k0 + i * kSmallThreads + t; }   /* ascending keys: first minimum = lowest id */
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, bd, off); const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        if (lane == 0) { s_d[warp] = bd; s_i[warp] = bi; }
+        __syncthreads();
+        float wd = s_d[0]; int wi = s_i[0];
+#pragma unroll
+        for (int w = 1; w < kSmallThreads / 32; w++) { const float od = s_d[w]; const int oi = s_i[w]; if (od < wd || (od == wd && oi < wi)) { wd = od; wi = oi; } }
+        __syncthreads();
+        if (wi == 0x7fffffff) break;                                 /* fewer than K acceptable keys in this split */
+        if ((wi - k0) % kSmallThreads == t) {
+            const int slot = (wi - k0) / kSmallThreads;
+#pragma unroll
+            for (int i = 0; i < KPT; i++) if (i == slot) d[i] = inf;
+        }
+        if (t == 0) { part_d2[o + r] = wd; part_ids[o + r] = wi * id_mul + id_add; }
+    }
+    if (t == 0) {
+        for (; r < K; r++) { part_d2[o + r] = inf; part_ids[o + r] = 0x7fffffff; }
+        __threadfence();
+        s_last = (atomicAdd(&tickets[qi], 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (t == 0) tickets[qi] = 0;
+    if (warp == 0)
+        merge_splits_warp(part_ids + (size_t)qi * gridDim.x * K, part_d2 + (size_t)qi * gridDim.x * K, (int)gridDim.x, K, lane,
+                          out_ids + (size_t)qi * K, out_d2 + (size_t)qi * K);
+}
+
+template <int R>
+cudaError_t launch_exact_small(const float* qkeys, int Q, const float* keys, int n_db, int K, int metric, int id_mul, int id_add,
+                               KnnWorkspace ws, int32_t* out_ids, float* out_d2, cudaStream_t stream, bool* done)
+{
+    *done = false;
+    int splits = (n_db + 1023) / 1024;
+    if (splits > kMaxSplits) splits = kMaxSplits;
+    if (splits < 1) splits = 1;
+    int split_len = (n_db + splits - 1) / splits;
+    split_len = (split_len + kSmallThreads - 1) / kSmallThreads * kSmallThreads;
+    const int kpt = split_len / kSmallThreads;
+    if (kpt > 32 || (size_t)Q * splits * K > ws.capacity) return cudaSuccess;        /* the general kernel takes it */
+    dim3 grid(splits, Q);
+#define SCL_SMALL(M, P) knn_exact_small_kernel<R, M, P><<<grid, kSmallThreads, 0, stream>>>(qkeys, keys, n_db, K, split_len, id_mul, id_add, ws.part_ids, \
+                                                                                          ws.part_d2, ws.tickets, out_ids, out_d2)
+    if (kpt <= 16) { if (metric == 0) SCL_SMALL(0, 16); else SCL_SMALL(1, 16); }
+    else { if (metric == 0) SCL_SMALL(0, 32); else SCL_SMALL(1, 32); }
+#undef SCL_SMALL
+    *done = true;
+    return cudaGetLastError();
+}
+
 __global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ rows, int n, int width, float* __restrict__ dst)
 {
     const size_t total = (size_t)n * width;
@@ -229,6 +326,12 @@ cudaError_t scl_launch_knn_exact(const float* qkeys, int Q, const float* keys, i
 {
     if (Q <= 0) return cudaSuccess;
     if (K < 1 || K > kMaxK) return cudaErrorInvalidValue;
+    if (!qlist && Q <= 8 && ws.tickets && (R == 20 || R == 40)) {       /* a handful of queries: thread = key */
+        bool done = false;
+        const cudaError_t e = R == 20 ? launch_exact_small<20>(qkeys, Q, keys, n_db, K, metric, id_mul, id_add, ws, out_ids, out_d2, stream, &done)
+                                      : launch_exact_small<40>(qkeys, Q, keys, n_db, K, metric, id_mul, id_add, ws, out_ids, out_d2, stream, &done);
+        if (e != cudaSuccess || done) return e;
+    }
     const int splits = scl_knn_splits(Q, n_db);
     int split_len = (n_db + splits - 1) / splits;
     split_len = (split_len + kTK - 1) / kTK * kTK;
