@@ -182,7 +182,7 @@ int scl_xchg_combine_dev(scl_engine* e, int seq, int Q, int K, const void* my_bl
 int scl_xchg_close(scl_engine* e);
 
 /* ---- ring-key kNN variant ---------------------------------------------
- * mode 0 = automatic (tensor-core prefilter for batches >= 64 queries on >= 32768 keys, exact
+ * mode 0 = automatic (tensor-core prefilter for batches of more than 3 queries on >= 32768 keys, exact
  * CUDA-core kernel otherwise), 1 = always exact, 2 = always tensor core. Both produce identical
  * results: the prefilter's proposals are re-ranked exactly and certified, uncertified queries are
  * redone by the exact kernel. With count_fallbacks != 0 every batch reads back how many queries

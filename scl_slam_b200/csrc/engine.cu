@@ -192,10 +192,11 @@ int knn_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int
         if (old != e->knn_tickets.p) CK(cudaMemsetAsync(e->knn_tickets.p, 0, e->knn_tickets.cap, e->stream));   /* the kernel leaves them zero */
     }
     ws.part_ids = e->part_ids.as<int32_t>(); ws.part_d2 = e->part_d2.as<float>(); ws.tickets = e->knn_tickets.as<int>(); ws.capacity = (size_t)Q * splits * K;
-    /* K3 variant: the tensor-core prefilter pays off once there is a batch to fill 128-row tiles and a
-     * database worth streaming; single queries and small databases take the exact CUDA-core kernel. */
+    /* K3 variant: on a database worth streaming the tensor-core prefilter wins from four queries up (measured on 1 M keys:
+     * 182 us per call at Q = 9..128 against 800..1800 us for the exact kernel, and against 199 / 234 us for the thread-per-key
+     * kernel at Q = 4 / 8); up to three queries and small databases take the exact CUDA-core kernels. */
     const bool use_tc = scl_knn_tc_supported(R) && K <= scl_knn_tc_kprime() - 2 &&
-                        (e->knn_mode == 2 || (e->knn_mode == 0 && Q >= 64 && n_db >= 32768));
+                        (e->knn_mode == 2 || (e->knn_mode == 0 && Q > 3 && n_db >= 32768));
     if (use_tc) { int rc = sync_key_image(e); if (rc) return rc; }
     {
         StageTimer st(e, 1);
