@@ -46,6 +46,62 @@ def _worker(rank, world, port, n, nq, K, ret):
     dist.destroy_process_group()
 
 
+def _worker_two_phase(rank, world, port, n, nq, K, ret):
+    """The protocol bench.py runs at N > 1: kNN per shard -> exchange (id, d2) -> global top-K -> SC distance for the owned
+    candidates only -> exchange (dist, shift) -> owner pick + winner scan."""
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle_lib import Oracle
+    from scl_slam_b200 import sharding, synth
+    db = synth.desc_db(n, seed=73).numpy().reshape(n, -1)
+    q = synth.desc_queries(torch.from_numpy(db.reshape(n, 20, 60)), nq, seed=74)[0].numpy().reshape(nq, -1)
+    rows = sharding.local_rows(n, rank, world)
+    n_local = sharding.local_count(n, rank, world)
+    o = Oracle(num_candidates=K)
+    o.bulk_load(np.concatenate([db[rows], q]))
+    n_search = sharding.local_search_bound(n - 57, rank, world)
+    loc = o.query_batch(np.arange(n_local, n_local + nq), n_search, K, 0)
+    ids = np.where(loc["cand_ids"] >= 0, loc["cand_ids"].astype(np.int64) * world + rank, -1).astype(np.int32)
+
+    def gather(arr):
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        return np.stack([x.numpy() for x in outs])
+    g_ids, g_d2 = sharding.merge_topk_numpy(gather(ids), gather(loc["cand_d2"]))
+    own_dist = np.full((nq, K), np.nan); own_shift = np.zeros((nq, K), np.int32)
+    for qi in range(nq):
+        for k in range(K):
+            i = int(g_ids[qi, k])
+            if i >= 0 and i % world == rank:
+                own_dist[qi, k], own_shift[qi, k] = o.distance(n_local + qi, i // world)
+    fin = sharding.combine_owned_numpy(g_ids, gather(own_dist), gather(own_shift))
+    if rank == 0:
+        full = Oracle(num_candidates=K)
+        full.bulk_load(np.concatenate([db, q]))
+        exp = full.query_batch(np.arange(n, n + nq), n - 57, K, 0)
+        ok = np.array_equal(g_ids, exp["cand_ids"]) and np.array_equal(g_d2, exp["cand_d2"]) and \
+            all(np.array_equal(fin[k], exp[k], equal_nan=True) for k in fin)
+        ret.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_two_phase_exchange_equals_unsharded_gloo(world):
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker_two_phase, args=(r, world, port, 1203, 48, 10, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) is True
+
+
 def test_two_rank_merge_equals_unsharded():
     world = 2
     ctx = mp.get_context("spawn")
