@@ -42,9 +42,12 @@ int grow(scl_engine* e, int need)
     while (ncap < need) ncap = ncap < (1 << 28) ? ncap * 2 : ncap + (1 << 26);
     const size_t RS = e->RS(), R = e->p.num_ring;
     float *nd = nullptr, *nk = nullptr, *nn = nullptr;
-    CK(cudaMalloc(&nd, (size_t)ncap * RS * 4));
-    CK(cudaMalloc(&nk, (size_t)ncap * R * 4));
-    CK(cudaMalloc(&nn, (size_t)ncap * 4));
+    if (cudaMalloc(&nd, (size_t)ncap * RS * 4) != cudaSuccess || cudaMalloc(&nk, (size_t)ncap * R * 4) != cudaSuccess ||
+        cudaMalloc(&nn, (size_t)ncap * 4) != cudaSuccess) {
+        cudaFree(nd); cudaFree(nk); cudaFree(nn);          /* the database stays as it was */
+        (void)cudaGetLastError();
+        FAIL(SCL_ERR_CUDA, "out of device memory growing the keyframe database");
+    }
     if (e->n > 0) {
         CK(cudaMemcpyAsync(nd, e->d_desc, (size_t)e->n * RS * 4, cudaMemcpyDeviceToDevice, e->stream));
         CK(cudaMemcpyAsync(nk, e->d_keys, (size_t)e->n * R * 4, cudaMemcpyDeviceToDevice, e->stream));
@@ -168,7 +171,6 @@ int knn_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int
     if (!q_desc && !q_ids) FAIL(SCL_ERR_INVALID, "q_desc and q_ids are both NULL");
     if (!q_desc && e->world != 1) FAIL(SCL_ERR_INVALID, "queries by key need q_desc on a sharded engine");
     const size_t QK = (size_t)Q * K;
-    (void)QK;
     CK(e->cand_local.ensure(QK * 4));
     CK(e->qkeys.ensure((size_t)Q * R * 4));
     int32_t* q_local = nullptr;
@@ -226,9 +228,10 @@ int knn_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int
                                  cand_ids, cand_d2, e->tc_fail_list.as<int32_t>(), fail_cur, fail_next, init_state, e->stream));
             e->tc_state_clean = true; e->tc_slots_rows = Qc;
             /* uncertified queries (normally none) are redone exactly; CTAs beyond the list length exit at once */
-            if (!(getenv("SCL_TC_FLAGS") && (atoi(getenv("SCL_TC_FLAGS")) & 32)))
-            CK(scl_launch_knn_exact(e->qkeys.as<float>(), Q, e->d_keys, n_db, R, K, metric, e->world, e->rank,
-                                    e->tc_fail_list.as<int32_t>(), fail_cur, ws, cand_ids, cand_d2, e->stream));
+            static const bool skip_fallback = getenv("SCL_TC_FLAGS") && (atoi(getenv("SCL_TC_FLAGS")) & 32);   /* bring-up switch */
+            if (!skip_fallback)
+                CK(scl_launch_knn_exact(e->qkeys.as<float>(), Q, e->d_keys, n_db, R, K, metric, e->world, e->rank,
+                                        e->tc_fail_list.as<int32_t>(), fail_cur, ws, cand_ids, cand_d2, e->stream));
             e->tc_last_fail = fail_cur;
             e->stat_tc_queries += Q;
         } else {
@@ -890,6 +893,8 @@ int scl_assemble_submap(scl_engine* e, const void* pts, const int* offsets, int 
     if (stride_bytes < 16 || stride_bytes % 16) FAIL(SCL_ERR_UNSUPPORTED, "points must be 16-byte aligned x,y,z,intensity records");
     *n_out = 0;
     const int total = n_clouds > 0 ? offsets[n_clouds] : 0;
+    for (int c = 0; c < n_clouds; c++)
+        if (offsets[c] < 0 || offsets[c + 1] < offsets[c]) FAIL(SCL_ERR_INVALID, "offsets must start at >= 0 and be non-decreasing");
     if (total <= 0) return SCL_OK;
     if (!out_xyzi) FAIL(SCL_ERR_INVALID, "null output");
     /* pcl::getTransformation(x, y, z, roll, pitch, yaw) in float with libm, as the reference calls it (:241) */
