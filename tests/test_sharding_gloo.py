@@ -123,3 +123,47 @@ def test_local_rows_partition():
             rows = [sharding.local_rows(n, r, world) for r in range(world)]
             assert sorted(np.concatenate(rows).tolist()) == list(range(n))
             assert [len(x) for x in rows] == [sharding.local_count(n, r, world) for r in range(world)]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_merge_rules_equal_unsharded_with_ties(world):
+    """Host-side rules only (no processes): heavy d2 ties, short shards and NaN distances. The one-phase merge and the two-phase
+    (global top-K, owner's distance, winner scan) rules give the same answer as ranking the whole database at once."""
+    from scl_slam_b200 import sharding
+    rng = np.random.default_rng(100 + world)
+    Q, K, n = 37, 10, 23                                           # n < world * K: some ranks hold fewer than K keys
+    d2 = rng.integers(0, 6, size=(Q, n)).astype(np.float32)        # few distinct values: ties decided by the lower id
+    dist = rng.uniform(0, 1, size=(Q, n))
+    dist[rng.uniform(size=(Q, n)) < 0.1] = np.nan                  # empty overlap: never selected (descriptor.h:1534,1561)
+    dist[:, ::5] = np.round(dist[:, ::5], 1)                       # SC-distance ties: nearest ring key wins (strict <)
+    shift = rng.integers(0, 60, size=(Q, n)).astype(np.int32)
+    q_ids = rng.integers(0, n, size=Q).astype(np.int32)            # a query that is itself in the database is skipped as winner
+    all_ids = np.full((world, Q, K), -1, np.int32); all_d2 = np.full((world, Q, K), np.finfo(np.float32).max, np.float32)
+    all_dist = np.full((world, Q, K), np.nan); all_shift = np.zeros((world, Q, K), np.int32)
+    for w in range(world):
+        own = sharding.local_rows(n, w, world)
+        for q in range(Q):
+            order = sorted(own, key=lambda i: (d2[q, i], i))[:K]
+            for k, i in enumerate(order):
+                all_ids[w, q, k], all_d2[w, q, k], all_dist[w, q, k], all_shift[w, q, k] = i, d2[q, i], dist[q, i], shift[q, i]
+    one = sharding.merge_shards_numpy(all_ids, all_d2, all_dist, all_shift, q_ids)
+    g_ids, g_d2 = sharding.merge_topk_numpy(all_ids, all_d2)
+    own_dist = np.full((world, Q, K), np.nan); own_shift = np.zeros((world, Q, K), np.int32)
+    for q in range(Q):
+        for k in range(K):
+            i = int(g_ids[q, k])
+            if i >= 0:
+                own_dist[i % world, q, k], own_shift[i % world, q, k] = dist[q, i], shift[q, i]
+    two = sharding.combine_owned_numpy(g_ids, own_dist, own_shift, q_ids)
+    for q in range(Q):                                             # the unsharded ranking
+        order = sorted(range(n), key=lambda i: (d2[q, i], i))[:K]
+        assert g_ids[q].tolist() == order and one["cand_ids"][q].tolist() == order
+        best, best_i, best_s = 1e7, -1, 0
+        for i in order:
+            if dist[q, i] < best and i != q_ids[q]:
+                best, best_i, best_s = dist[q, i], i, shift[q, i]
+        for res in (one, two):
+            assert res["best_id"][q] == best_i and res["best_shift"][q] == best_s and res["best_dist"][q] == best
+    assert np.array_equal(g_d2, one["cand_d2"])
+    for k in ("cand_dist", "cand_shift", "best_id", "best_dist", "best_shift"):
+        assert np.array_equal(one[k], two[k], equal_nan=True), k
