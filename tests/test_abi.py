@@ -27,6 +27,14 @@ def test_header_symbols_all_exported(lib):
         assert hasattr(lib, name), name
 
 
+def test_every_entry_point_is_in_the_integration_map():
+    """INTEGRATION.md §2 maps each C-ABI entry point to the reference member it stands in for."""
+    hdr = open(os.path.join(ROOT, "include", "scl_engine.h")).read() + open(os.path.join(ROOT, "include", "scl_wire.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = sorted(n for n in set(re.findall(r"\b(scl_[a-z_0-9]+)\s*\(", hdr)) if n not in doc)
+    assert not missing, missing
+
+
 def test_default_params_match_reference_ctor(lib):
     """descriptor.h:1307-1316"""
     from scl_slam_b200.engine import SclParams
