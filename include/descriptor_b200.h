@@ -76,6 +76,20 @@ public:
 		return vT;
 	}
 
+	/* distributedMapping.h:996-1003 as one call — downSizeFilterDes (a pcl::VoxelGrid with a cubic leaf) followed by
+	 * makeAndSaveDescriptorAndKey; the filtered cloud stays on the device. *filteredSize = points after the filter. */
+	std::vector<float> makeAndSaveDescriptorAndKeyFiltered(const pcl::PointCloud<pcl::PointXYZI>& scan, const float leaf,
+		const int8_t robot, const int index, int* filteredSize = nullptr)
+	{
+		std::vector<float> vT(rs_, 0.0f);
+		const void* pts = scan.points.empty() ? nullptr : static_cast<const void*>(&scan.points[0]);
+		int m = 0;
+		check(scl_build_insert_filtered(engine_, pts, (int)scan.points.size(), (int)sizeof(pcl::PointXYZI), leaf, robot, index, vT.data(), &m),
+			"makeAndSaveDescriptorAndKeyFiltered");
+		if(filteredSize) *filteredSize = m;
+		return vT;
+	}
+
 	/* descriptor.h:1572-1585 — descriptorMat is msg->values.data(), borrowed for the call */
 	void saveDescriptorAndKey(const float* descriptorMat, const int8_t robot, const int index)
 	{
