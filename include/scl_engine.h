@@ -17,7 +17,7 @@
  *  - descriptors cross the boundary as R*S row-major float32 — the layout of
  *    global_descriptor.msg `values` (descriptor.h:1446-1455 writer, :1575-1582 reader);
  *  - keys are dense global insertion indices 0..N-1 as in the reference (descriptor.h:1593-1599);
- *  - an engine handle is internally serialised (one mutex, one CUDA stream), so the reference's
+ *  - an engine handle is internally serialised (one mutex; inserts on one CUDA stream, query batches on lanes), so the reference's
  *    {insert on the ROS/LIO threads || query on loopClosureThread} pattern
  *    (distributedMapping.h:625-628,1001-1003 vs :1078,1280) is safe;
  *  - there is no CPU fallback: without a CUDA device scl_create fails with SCL_ERR_CUDA.
@@ -145,6 +145,20 @@ int scl_query_batch_dev(scl_engine* e, const scl_batch_query* q, scl_batch_resul
 int scl_query_batch_submit(scl_engine* e, const scl_batch_query* q, scl_batch_result* r, int* ticket);
 int scl_query_batch_wait(scl_engine* e, int ticket);
 
+/* Query lanes. An engine keeps scl_num_lanes() independent sets of query scratch, each with its own CUDA stream, so that
+ * several batches are in flight at once: the kernels of one batch leave SMs idle (start-up, the exact re-rank, exchange
+ * waits) that the next batch fills. scl_query_batch_submit rotates over the lanes by itself; for device-resident queries
+ * scl_query_batch_dev_lane enqueues a batch on lane `lane` (lane 0 is the engine's own stream, what scl_query_batch_dev
+ * uses). scl_lanes_fork makes every lane wait for the work enqueued so far on `cuda_stream` (the stream the caller filled
+ * the query buffers on), scl_lanes_join makes `cuda_stream` wait for everything enqueued so far on every lane, so a caller
+ * can bracket a group of batches with events on its own stream; scl_lane_sync blocks the host until lane `lane` is idle.
+ * Results of a lane are valid once its stream has passed them; a lane's scratch is reused by its next batch. */
+int scl_num_lanes(void);
+int scl_query_batch_dev_lane(scl_engine* e, int lane, const scl_batch_query* q, scl_batch_result* r);
+int scl_lanes_fork(scl_engine* e, void* cuda_stream);
+int scl_lanes_join(scl_engine* e, void* cuda_stream);
+int scl_lane_sync(scl_engine* e, int lane);
+
 /* Multi-GPU merge: `world` per-rank result blocks of Q*K records, gathered
  * rank-major in device memory, are reduced to the global top-K by (d2, id) and then to the winner
  * by the same strict-< scan as the unsharded query. */
@@ -169,17 +183,35 @@ int scl_combine_owned_dev(scl_engine* e, int world, int Q, int K, const int32_t*
                           const void* shift_base, uint64_t rank_stride_bytes, scl_batch_result* merged);
 
 /* The same two exchange points over NVLink peer memory instead of NCCL (csrc/k7_exchange.cu): every rank creates an exchange
- * buffer and hands its 64-byte IPC handle to the others (any side channel: torch.distributed, MPI, a file); after
- * scl_xchg_open, scl_xchg_merge_topk_dev replaces {all-gather, scl_merge_topk_dev} and scl_xchg_combine_dev replaces
+ * buffer (room for batches of max_q queries with up to max_k candidates, one region per query lane) and hands its 64-byte
+ * IPC handle to the others (any side channel: torch.distributed, MPI, a file); after scl_xchg_open,
+ * scl_xchg_merge_topk_dev replaces {all-gather, scl_merge_topk_dev} and scl_xchg_combine_dev replaces
  * {all-gather, scl_combine_owned_dev}: one kernel each stores this rank's block into every peer's buffer, raises a flag,
  * waits for all ranks' flags and merges. seq = 1, 2, 3, ... must advance by one per query step, identically on all ranks;
- * my_block_dev = [ids i32 Q*K | d2 f32 Q*K] resp. [dist f64 Q*K | shift i32 Q*K], 16-byte aligned; Q*K a multiple of 4. */
-int scl_xchg_create(scl_engine* e, int world, int max_qk, unsigned char* handle64);
+ * my_block_dev = [ids i32 Q*K | d2 f32 Q*K] resp. [dist f64 Q*K | shift i32 Q*K], 16-byte aligned; Q*K a multiple of 4.
+ * (These two run on lane 0 with the caller's step counter; scl_shard_query_dev below keeps the counters itself.)
+ * scl_xchg_open_local is scl_xchg_open for engines of ONE process (one per device, peer access enabled): peer_bufs[r] =
+ * scl_xchg_buffer(engine of rank r). */
+int scl_xchg_create(scl_engine* e, int world, int max_q, int max_k, unsigned char* handle64);
 int scl_xchg_open(scl_engine* e, int world, int rank, const unsigned char* handles /* world x 64 bytes, rank-major */);
+int scl_xchg_open_local(scl_engine* e, int world, int rank, void* const* peer_bufs);
+void* scl_xchg_buffer(scl_engine* e);
+int scl_xchg_bytes(scl_engine* e, int world, int max_q, int max_k, uint64_t* bytes);
 int scl_xchg_merge_topk_dev(scl_engine* e, int seq, int Q, int K, const void* my_block_dev, int32_t* out_ids, float* out_d2);
 int scl_xchg_combine_dev(scl_engine* e, int seq, int Q, int K, const void* my_block_dev, const int32_t* q_ids, const int32_t* cand_ids,
                          scl_batch_result* merged);
 int scl_xchg_close(scl_engine* e);
+
+/* The sharded query as ONE call per batch (every rank makes the same calls in the same order, with the same lane):
+ *   scl_shard_query_dev   : q->q_desc = the whole batch in device memory (every rank holds it); K2 + K3 on the shard,
+ *                           exchange + global top-K, K4 on the candidates this rank owns, exchange + winner scan, all on
+ *                           lane `lane`; r holds device pointers (any may be NULL), identical on all ranks afterwards.
+ *   scl_shard_query_submit: host buffers, pipelined like scl_query_batch_submit (wait with scl_query_batch_wait). Every
+ *                           rank passes the same whole batch in q->q_desc but uploads only its 1/world of the rows; a
+ *                           gather kernel stores them into every peer's query area over NVLink, so the host link carries each
+ *                           descriptor once. q->Q must be a multiple of the world size. */
+int scl_shard_query_dev(scl_engine* e, int lane, const scl_batch_query* q, scl_batch_result* r);
+int scl_shard_query_submit(scl_engine* e, const scl_batch_query* q, scl_batch_result* r, int* ticket);
 
 /* ---- ring-key kNN variant ---------------------------------------------
  * mode 0 = automatic (tensor-core prefilter for batches of more than 3 queries on >= 32768 keys, exact
@@ -188,6 +220,11 @@ int scl_xchg_close(scl_engine* e);
  * redone by the exact kernel. With count_fallbacks != 0 every batch reads back how many queries
  * needed that (a host sync; for tests and reports). */
 int scl_set_knn_mode(scl_engine* e, int mode, int count_fallbacks);
+/* ---- SC distance variant ------------------------------------------------
+ * mode 0 (default): FP32 estimates of every alignment / window shift, then the shifts that can win (within a proven error
+ * bound of the best estimate) in FP64 with the operation order of distanceBtnScanContext (descriptor.h:1538-1569);
+ * mode 1: every shift in FP64. Both give bit-identical distances and shifts; mode 1 exists for the tests. */
+int scl_set_scdist_mode(scl_engine* e, int mode);
 int scl_knn_stats(scl_engine* e, long long* tc_queries, long long* fallback_queries);
 
 /* ---- per-stage device timing (for roofline reports) ----------------------------------------

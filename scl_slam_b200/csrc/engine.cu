@@ -14,18 +14,20 @@
 
 namespace {
 
+typedef scl_engine::Lane Lane;
+
 struct StageTimer {
-    scl_engine* e; int stage; cudaEvent_t a = nullptr, b = nullptr;
-    StageTimer(scl_engine* e_, int stage_) : e(e_), stage(stage_)
+    scl_engine* e; int stage; cudaStream_t s; cudaEvent_t a = nullptr, b = nullptr;
+    StageTimer(scl_engine* e_, int stage_, cudaStream_t s_) : e(e_), stage(stage_), s(s_)
     {
         if (!e->profiling) return;
         a = take(); b = take();
-        cudaEventRecord(a, e->stream);
+        cudaEventRecord(a, s);
     }
     ~StageTimer()
     {
         if (!a) return;
-        cudaEventRecord(b, e->stream);
+        cudaEventRecord(b, s);
         e->ev[stage].emplace_back(a, b);
     }
     cudaEvent_t take()
@@ -41,10 +43,11 @@ int grow(scl_engine* e, int need)
     int ncap = e->cap ? e->cap : 1024;
     while (ncap < need) ncap = ncap < (1 << 28) ? ncap * 2 : ncap + (1 << 26);
     const size_t RS = e->RS(), R = e->p.num_ring;
-    float *nd = nullptr, *nk = nullptr, *nn = nullptr;
+    const size_t S2 = 2 * (size_t)e->p.num_sector;
+    float *nd = nullptr, *nk = nullptr, *nn = nullptr; double* nc = nullptr;
     if (cudaMalloc(&nd, (size_t)ncap * RS * 4) != cudaSuccess || cudaMalloc(&nk, (size_t)ncap * R * 4) != cudaSuccess ||
-        cudaMalloc(&nn, (size_t)ncap * 4) != cudaSuccess) {
-        cudaFree(nd); cudaFree(nk); cudaFree(nn);          /* the database stays as it was */
+        cudaMalloc(&nn, (size_t)ncap * 4) != cudaSuccess || cudaMalloc(&nc, (size_t)ncap * S2 * 8) != cudaSuccess) {
+        cudaFree(nd); cudaFree(nk); cudaFree(nn); cudaFree(nc);          /* the database stays as it was */
         (void)cudaGetLastError();
         FAIL(SCL_ERR_CUDA, "out of device memory growing the keyframe database");
     }
@@ -52,10 +55,12 @@ int grow(scl_engine* e, int need)
         CK(cudaMemcpyAsync(nd, e->d_desc, (size_t)e->n * RS * 4, cudaMemcpyDeviceToDevice, e->stream));
         CK(cudaMemcpyAsync(nk, e->d_keys, (size_t)e->n * R * 4, cudaMemcpyDeviceToDevice, e->stream));
         CK(cudaMemcpyAsync(nn, e->d_knorm, (size_t)e->n * 4, cudaMemcpyDeviceToDevice, e->stream));
+        CK(cudaMemcpyAsync(nc, e->d_cstat, (size_t)e->n * S2 * 8, cudaMemcpyDeviceToDevice, e->stream));
     }
     CK(cudaStreamSynchronize(e->stream));
-    cudaFree(e->d_desc); cudaFree(e->d_keys); cudaFree(e->d_knorm);
-    e->d_desc = nd; e->d_keys = nk; e->d_knorm = nn; e->cap = ncap;
+    for (int l = 1; l < scl_engine::kLanes; l++) if (e->lanes[l].stream) CK(cudaStreamSynchronize(e->lanes[l].stream));   /* queries in flight read the old arrays */
+    cudaFree(e->d_desc); cudaFree(e->d_keys); cudaFree(e->d_knorm); cudaFree(e->d_cstat);
+    e->d_desc = nd; e->d_keys = nk; e->d_knorm = nn; e->d_cstat = nc; e->cap = ncap;
     return SCL_OK;
 }
 
@@ -90,18 +95,22 @@ int build_dev(scl_engine* e, const void* pts_dev, const int32_t* offsets_host, i
         e->gbins_scans = e->gbins.cap / (RS * 4);
         if (e->tickets.cap / 4 < e->gbins_scans) e->gbins_scans = e->tickets.cap / 4;
     }
-    float *od, *ok, *on;
+    float *od, *ok, *on; double* oc = nullptr;
     if (insert) {
         od = e->d_desc + (size_t)e->n * RS; ok = e->d_keys + (size_t)e->n * R; on = e->d_knorm + e->n;
+        oc = e->d_cstat + (size_t)e->n * 2 * S;
     } else {
         CK(e->stage_desc.ensure((size_t)n_scans * RS * 4));
         CK(e->stage_keys.ensure((size_t)n_scans * R * 4));
         CK(e->stage_knorm.ensure((size_t)n_scans * 4));
         od = e->stage_desc.as<float>(); ok = e->stage_keys.as<float>(); on = e->stage_knorm.as<float>();
     }
-    StageTimer st(e, 3);
+    StageTimer st(e, 3, e->stream);
+    e->db_dirty = e->db_dirty || insert;
     CK(scl_launch_polar(pts_dev, e->offsets.as<int>(), n_scans, max_points, stride_bytes, R, S, e->p.lidar_height, e->p.max_radius,
                         e->gbins.as<uint32_t>(), e->tickets.as<int>(), od, ok, on, insert ? e->d_kn2max : nullptr, ring_dev, sector_dev, e->stream));
+    /* the per-entry cache K4 reads: sector key + column norms of the new entries (descriptor.h:1541-1542 recomputes them per pair) */
+    if (oc) CK(scl_launch_ring_keys(od, n_scans, R, S, nullptr, nullptr, nullptr, oc, e->stream));
     if (out_desc_dev) CK(cudaMemcpyAsync(out_desc_dev, od, (size_t)n_scans * RS * 4, cudaMemcpyDeviceToDevice, e->stream));
     if (where_desc) *where_desc = od;
     if (insert) { append_index(e, n_scans, robots, indices); e->n += n_scans; }
@@ -144,7 +153,11 @@ int sync_key_image(scl_engine* e)
     const int R = e->p.num_ring;
     if (e->img_cap < e->cap) {
         /* derived data: on growth the image is simply rebuilt from the keys */
-        if (e->d_kimg) { CK(cudaStreamSynchronize(e->stream)); cudaFree(e->d_kimg); e->d_kimg = nullptr; }
+        if (e->d_kimg) {
+            CK(cudaStreamSynchronize(e->stream));
+            for (int l = 1; l < scl_engine::kLanes; l++) if (e->lanes[l].stream) CK(cudaStreamSynchronize(e->lanes[l].stream));
+            cudaFree(e->d_kimg); e->d_kimg = nullptr;
+        }
         const size_t bytes = scl_knn_tc_image_bytes(R, e->cap);
         CK(cudaMalloc(&e->d_kimg, bytes));
         CK(cudaMemsetAsync(e->d_kimg, 0, bytes, e->stream));
@@ -153,12 +166,28 @@ int sync_key_image(scl_engine* e)
     if (e->img_n < e->n) {
         CK(scl_launch_key_image(e->d_keys, e->d_knorm, e->img_n, e->n, R, e->d_kimg, e->stream));
         e->img_n = e->n;
+        e->db_dirty = true;
     }
     return SCL_OK;
 }
 
+// A lane other than lane 0 runs on its own stream: it must see every insert (and key-image update) enqueued on the engine
+// stream so far. One event, re-recorded only when the database changed since it was last recorded.
+int lane_begin(scl_engine* e, Lane& ln)
+{
+    if (!ln.stream) {
+        if (&ln == &e->lanes[0]) ln.stream = e->stream;
+        else CK(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+    }
+    if (&ln == &e->lanes[0]) { ln.stream = e->stream; return SCL_OK; }
+    if (!e->db_ready) { CK(cudaEventCreateWithFlags(&e->db_ready, cudaEventDisableTiming)); e->db_dirty = true; }
+    if (e->db_dirty) { CK(cudaEventRecord(e->db_ready, e->stream)); e->db_dirty = false; }
+    CK(cudaStreamWaitEvent(ln.stream, e->db_ready, 0));
+    return SCL_OK;
+}
+
 // K2 (query ring keys) + K3 (ring-key kNN) on device pointers; results: reported ids + float distances
-int knn_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int K, int n_db, int metric,
+int knn_dev(scl_engine* e, Lane& ln, const float* q_desc, const int32_t* q_ids, int Q, int K, int n_db, int metric,
             int32_t* cand_ids, float* cand_d2, int32_t** q_local_out)
 {
     const int R = e->p.num_ring, S = e->p.num_sector;
@@ -170,79 +199,83 @@ int knn_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int
     if (n_db > e->n) n_db = e->n;
     if (!q_desc && !q_ids) FAIL(SCL_ERR_INVALID, "q_desc and q_ids are both NULL");
     if (!q_desc && e->world != 1) FAIL(SCL_ERR_INVALID, "queries by key need q_desc on a sharded engine");
-    const size_t QK = (size_t)Q * K;
-    CK(e->cand_local.ensure(QK * 4));
-    CK(e->qkeys.ensure((size_t)Q * R * 4));
-    int32_t* q_local = nullptr;
-    if (q_desc) {
-        CK(e->qknorm.ensure((size_t)Q * 4));
-        StageTimer st(e, 0);
-        CK(scl_launch_ring_keys(q_desc, Q, R, S, e->qkeys.as<float>(), e->qknorm.as<float>(), nullptr, e->stream));
-    } else {
-        CK(e->qlocal.ensure((size_t)Q * 4));
-        q_local = e->qlocal.as<int32_t>();
-        CK(scl_launch_ids_to_local(q_ids, Q, e->world, e->rank, -1, nullptr, q_local, e->stream));
-        CK(scl_launch_gather_rows(e->d_keys, q_local, Q, R, e->qkeys.as<float>(), e->stream));
-    }
-    const int splits = scl_knn_splits(Q, n_db);
-    KnnWorkspace ws;
-    CK(e->part_ids.ensure((size_t)Q * splits * K * 4));
-    CK(e->part_d2.ensure((size_t)Q * splits * K * 4));
-    {
-        const void* old = e->knn_tickets.p;
-        CK(e->knn_tickets.ensure(((size_t)Q / 128 + 16) * 4));          /* per 128-query tile, or per query of a handful */
-        if (old != e->knn_tickets.p) CK(cudaMemsetAsync(e->knn_tickets.p, 0, e->knn_tickets.cap, e->stream));   /* the kernel leaves them zero */
-    }
-    ws.part_ids = e->part_ids.as<int32_t>(); ws.part_d2 = e->part_d2.as<float>(); ws.tickets = e->knn_tickets.as<int>(); ws.capacity = (size_t)Q * splits * K;
     /* K3 variant: on a database worth streaming the tensor-core prefilter wins from four queries up (measured on 1 M keys:
      * 182 us per call at Q = 9..128 against 800..1800 us for the exact kernel, and against 199 / 234 us for the thread-per-key
      * kernel at Q = 4 / 8); up to three queries and small databases take the exact CUDA-core kernels. */
     const bool use_tc = scl_knn_tc_supported(R) && K <= scl_knn_tc_kprime() - 2 &&
                         (e->knn_mode == 2 || (e->knn_mode == 0 && Q > 3 && n_db >= 32768));
-    if (use_tc) { int rc = sync_key_image(e); if (rc) return rc; }
+    if (use_tc) { int rc = sync_key_image(e); if (rc) return rc; }            /* on the engine stream */
+    { int rc = lane_begin(e, ln); if (rc) return rc; }
+    const size_t QK = (size_t)Q * K;
+    CK(ln.cand_local.ensure(QK * 4));
+    CK(ln.qkeys.ensure((size_t)Q * R * 4));
+    int32_t* q_local = nullptr;
+    if (q_desc) {
+        CK(ln.qknorm.ensure((size_t)Q * 4));
+        CK(ln.qstat.ensure((size_t)Q * 2 * S * 8));
+    } else {
+        CK(ln.qlocal.ensure((size_t)Q * 4));
+        q_local = ln.qlocal.as<int32_t>();
+    }
+    const int splits = scl_knn_splits(Q, n_db);
+    KnnWorkspace ws;
+    CK(ln.part_ids.ensure((size_t)Q * splits * K * 4));
+    CK(ln.part_d2.ensure((size_t)Q * splits * K * 4));
     {
-        StageTimer st(e, 1);
+        const void* old = ln.knn_tickets.p;
+        CK(ln.knn_tickets.ensure(((size_t)Q / 128 + 16) * 4));          /* per 128-query tile, or per query of a handful */
+        if (old != ln.knn_tickets.p) CK(cudaMemsetAsync(ln.knn_tickets.p, 0, ln.knn_tickets.cap, ln.stream));   /* the kernel leaves them zero */
+    }
+    ws.part_ids = ln.part_ids.as<int32_t>(); ws.part_d2 = ln.part_d2.as<float>(); ws.tickets = ln.knn_tickets.as<int>(); ws.capacity = (size_t)Q * splits * K;
+    if (q_desc) {
+        StageTimer st(e, 0, ln.stream);
+        CK(scl_launch_ring_keys(q_desc, Q, R, S, ln.qkeys.as<float>(), ln.qknorm.as<float>(), nullptr, ln.qstat.as<double>(), ln.stream));
+        ln.qstat_of = q_desc; ln.qstat_rows = Q;
+    } else {
+        CK(scl_launch_ids_to_local(q_ids, Q, e->world, e->rank, -1, nullptr, q_local, ln.stream));
+        CK(scl_launch_gather_rows(e->d_keys, q_local, Q, R, ln.qkeys.as<float>(), ln.stream));
+    }
+    {
+        StageTimer st(e, 1, ln.stream);
         if (use_tc) {
             const int Qc = Q < scl_knn_tc_max_batch() ? Q : scl_knn_tc_max_batch();
             const int ranges = scl_knn_tc_ranges(Qc);
             const size_t pairs = (size_t)Qc * ranges;
-            CK(e->tc_queues.ensure(pairs * scl_knn_tc_queue_bytes())); CK(e->tc_queue_cnt.ensure(pairs * 4));
-            const void* old_slots = e->tc_slots.p; const void* old_cnt = e->tc_fail_count.p;
-            CK(e->tc_fail_list.ensure((size_t)Q * 4)); CK(e->tc_fail_count.ensure(128));
-            CK(e->tc_slots.ensure((size_t)Qc * scl_knn_tc_kprime() * 4));
-            const bool init_state = !e->tc_state_clean || old_slots != e->tc_slots.p || old_cnt != e->tc_fail_count.p || Qc > e->tc_slots_rows;
-            if (old_cnt != e->tc_fail_count.p) CK(cudaMemsetAsync(e->tc_fail_count.p, 0, 128, e->stream));   /* two call counters + the running total */
+            CK(ln.tc_queues.ensure(pairs * scl_knn_tc_queue_bytes())); CK(ln.tc_queue_cnt.ensure(pairs * 4));
+            const void* old_slots = ln.tc_slots.p; const void* old_cnt = ln.tc_fail_count.p;
+            CK(ln.tc_fail_list.ensure((size_t)Q * 4)); CK(ln.tc_fail_count.ensure(128));
+            CK(ln.tc_slots.ensure((size_t)Qc * scl_knn_tc_kprime() * 4));
+            const bool init_state = !ln.tc_state_clean || old_slots != ln.tc_slots.p || old_cnt != ln.tc_fail_count.p || Qc > ln.tc_slots_rows;
+            if (old_cnt != ln.tc_fail_count.p) CK(cudaMemsetAsync(ln.tc_fail_count.p, 0, 128, ln.stream));   /* two call counters + the running total */
             /* counter block (ints): [0] / [16] = the fail counters of even / odd calls; [8] + [24] = uncertified queries since
              * creation (the re-rank kernel adds to the int 8 places after the counter it is told to zero) */
-            int* fail_cur = e->tc_fail_count.as<int>() + 16 * (e->tc_calls & 1);
-            int* fail_next = e->tc_fail_count.as<int>() + 16 * ((e->tc_calls + 1) & 1);
-            e->tc_calls++;
-            e->tc_state_clean = false;
+            int* fail_cur = ln.tc_fail_count.as<int>() + 16 * (ln.tc_calls & 1);
+            int* fail_next = ln.tc_fail_count.as<int>() + 16 * ((ln.tc_calls + 1) & 1);
+            ln.tc_calls++;
+            ln.tc_state_clean = false;
             float* probe = nullptr;
             if (e->count_fallbacks) {
-                if (!e->tc_err_probe.p) { CK(e->tc_err_probe.ensure(64)); CK(cudaMemsetAsync(e->tc_err_probe.p, 0, 64, e->stream)); }
-                probe = e->tc_err_probe.as<float>();
+                if (!ln.tc_err_probe.p) { CK(ln.tc_err_probe.ensure(64)); CK(cudaMemsetAsync(ln.tc_err_probe.p, 0, 64, ln.stream)); }
+                probe = ln.tc_err_probe.as<float>();
             }
-            KnnTcWorkspace tw{e->tc_queues.as<uint32_t>(), e->tc_queue_cnt.as<int>(), e->tc_slots.as<int>(), probe, pairs};
-            CK(scl_launch_knn_tc(e->qkeys.as<float>(), Q, e->d_keys, e->d_kimg, e->d_kn2max, n_db, R, K, metric, e->world, e->rank, tw,
-                                 cand_ids, cand_d2, e->tc_fail_list.as<int32_t>(), fail_cur, fail_next, init_state, e->stream));
-            e->tc_state_clean = true; e->tc_slots_rows = Qc;
+            KnnTcWorkspace tw{ln.tc_queues.as<uint32_t>(), ln.tc_queue_cnt.as<int>(), ln.tc_slots.as<int>(), probe, pairs};
+            CK(scl_launch_knn_tc(ln.qkeys.as<float>(), Q, e->d_keys, e->d_kimg, e->d_kn2max, n_db, R, K, metric, e->world, e->rank, tw,
+                                 cand_ids, cand_d2, ln.tc_fail_list.as<int32_t>(), fail_cur, fail_next, init_state, ln.stream));
+            ln.tc_state_clean = true; ln.tc_slots_rows = Qc;
             /* uncertified queries (normally none) are redone exactly; CTAs beyond the list length exit at once */
-            static const bool skip_fallback = getenv("SCL_TC_FLAGS") && (atoi(getenv("SCL_TC_FLAGS")) & 32);   /* bring-up switch */
-            if (!skip_fallback)
-                CK(scl_launch_knn_exact(e->qkeys.as<float>(), Q, e->d_keys, n_db, R, K, metric, e->world, e->rank,
-                                        e->tc_fail_list.as<int32_t>(), fail_cur, ws, cand_ids, cand_d2, e->stream));
-            e->tc_last_fail = fail_cur;
+            CK(scl_launch_knn_exact(ln.qkeys.as<float>(), Q, e->d_keys, n_db, R, K, metric, e->world, e->rank,
+                                    ln.tc_fail_list.as<int32_t>(), fail_cur, ws, cand_ids, cand_d2, ln.stream));
+            ln.tc_last_fail = fail_cur;
             e->stat_tc_queries += Q;
         } else {
-            CK(scl_launch_knn_exact(e->qkeys.as<float>(), Q, e->d_keys, n_db, R, K, metric, e->world, e->rank, nullptr, nullptr, ws,
-                                    cand_ids, cand_d2, e->stream));
+            CK(scl_launch_knn_exact(ln.qkeys.as<float>(), Q, e->d_keys, n_db, R, K, metric, e->world, e->rank, nullptr, nullptr, ws,
+                                    cand_ids, cand_d2, ln.stream));
         }
     }
     if (use_tc && e->count_fallbacks) {
         int nfail = 0;
-        CK(cudaMemcpyAsync(&nfail, e->tc_last_fail, 4, cudaMemcpyDeviceToHost, e->stream));
-        CK(cudaStreamSynchronize(e->stream));            /* developer mode: surfaces kernel faults at the call that caused them */
+        CK(cudaMemcpyAsync(&nfail, ln.tc_last_fail, 4, cudaMemcpyDeviceToHost, ln.stream));
+        CK(cudaStreamSynchronize(ln.stream));            /* developer mode: surfaces kernel faults at the call that caused them */
         (void)nfail;
     }
     if (q_local_out) *q_local_out = q_local;
@@ -250,60 +283,73 @@ int knn_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int
 }
 
 // K4 on device pointers: SC distance of every (query, candidate) this engine owns (+ the winner scan)
-int scdist_dev(scl_engine* e, const float* q_desc, const int32_t* q_local, const int32_t* q_ids, int Q, int K, int32_t* cand_ids,
-               int missing_to_zero, double* cand_dist, int32_t* cand_shift, int32_t* best_id, double* best_dist, int32_t* best_shift)
+int scdist_dev(scl_engine* e, Lane& ln, const float* q_desc, const int32_t* q_local, const int32_t* q_ids, int Q, int K, int32_t* cand_ids,
+               int missing_to_zero, double* cand_dist, int32_t* cand_shift, int32_t* best_id, double* best_dist, int32_t* best_shift,
+               bool q_stat_ready)
 {
     const int R = e->p.num_ring, S = e->p.num_sector;
     if (Q <= 0) return SCL_OK;
+    { int rc = lane_begin(e, ln); if (rc) return rc; }
     const size_t QK = (size_t)Q * K;
     /* reported id -> row of this engine's descriptor array; on an unsharded engine the two are the same (missing = -1) */
     const int32_t* cand_local = cand_ids;
     if (e->world != 1 || missing_to_zero) {
-        CK(e->cand_local.ensure(QK * 4));
+        CK(ln.cand_local.ensure(QK * 4));
         CK(scl_launch_ids_to_local(cand_ids, (int)QK, e->world, e->rank, missing_to_zero ? 0 : -1, missing_to_zero ? cand_ids : nullptr,
-                                   e->cand_local.as<int32_t>(), e->stream));
-        cand_local = e->cand_local.as<int32_t>();
+                                   ln.cand_local.as<int32_t>(), ln.stream));
+        cand_local = ln.cand_local.as<int32_t>();
     }
-    StageTimer st(e, 2);
-    CK(scl_launch_scdist(e->d_desc, q_desc, q_local, q_ids, cand_local, cand_ids, Q, K, R, S, e->search_radius,
-                         cand_dist, cand_shift, best_id, best_dist, best_shift, e->scdist_owned_hint, e->stream));
+    const double* q_stat = nullptr;
+    if (q_desc) {
+        if (!q_stat_ready) {
+            /* queries that did not come through knn_dev on this lane: their column statistics first */
+            CK(ln.qstat.ensure((size_t)Q * 2 * S * 8));
+            CK(scl_launch_ring_keys(q_desc, Q, R, S, nullptr, nullptr, nullptr, ln.qstat.as<double>(), ln.stream));
+            ln.qstat_of = q_desc; ln.qstat_rows = Q;
+        }
+        q_stat = ln.qstat.as<double>();
+    }
+    StageTimer st(e, 2, ln.stream);
+    CK(scl_launch_scdist(e->d_desc, e->d_cstat, q_desc, q_stat, q_local, q_ids, cand_local, cand_ids, Q, K, R, S, e->search_radius,
+                         cand_dist, cand_shift, best_id, best_dist, best_shift, ln.scdist_owned_hint, e->scdist_exact_all ? 1 : 0, ln.stream));
     return SCL_OK;
 }
 
 // the batched query on device pointers; any result pointer may be null (scratch is used)
-int query_dev(scl_engine* e, const float* q_desc, const int32_t* q_ids, int Q, int K, int n_db, int metric, int missing_to_zero,
+int query_dev(scl_engine* e, Lane& ln, const float* q_desc, const int32_t* q_ids, int Q, int K, int n_db, int metric, int missing_to_zero,
               int32_t* cand_ids, float* cand_d2, double* cand_dist, int32_t* cand_shift,
               int32_t* best_id, double* best_dist, int32_t* best_shift)
 {
     if (Q <= 0) return SCL_OK;
     if (K < 1 || K > 32) FAIL(SCL_ERR_INVALID, "K must be in 1..32");
     const size_t QK = (size_t)Q * K;
-    if (!cand_ids) { CK(e->cand_ids.ensure(QK * 4)); cand_ids = e->cand_ids.as<int32_t>(); }
-    if (!cand_d2) { CK(e->cand_d2.ensure(QK * 4)); cand_d2 = e->cand_d2.as<float>(); }
+    if (!cand_ids) { CK(ln.cand_ids.ensure(QK * 4)); cand_ids = ln.cand_ids.as<int32_t>(); }
+    if (!cand_d2) { CK(ln.cand_d2.ensure(QK * 4)); cand_d2 = ln.cand_d2.as<float>(); }
     int32_t* q_local = nullptr;
-    int rc = knn_dev(e, q_desc, q_ids, Q, K, n_db, metric, cand_ids, cand_d2, &q_local);
+    int rc = knn_dev(e, ln, q_desc, q_ids, Q, K, n_db, metric, cand_ids, cand_d2, &q_local);
     if (rc) return rc;
-    return scdist_dev(e, q_desc, q_local, q_ids, Q, K, cand_ids, missing_to_zero, cand_dist, cand_shift, best_id, best_dist, best_shift);
+    return scdist_dev(e, ln, q_desc, q_local, q_ids, Q, K, cand_ids, missing_to_zero, cand_dist, cand_shift, best_id, best_dist, best_shift,
+                      /* q_stat_ready = */ q_desc != nullptr);
 }
 
 // device-side part of a host-buffer query: kernels + the device-to-host copies of whatever r asks for (no sync)
-int query_host_enqueue(scl_engine* e, const float* dq, const int32_t* di, const scl_batch_query* q, scl_batch_result* r, int missing_to_zero)
+int query_host_enqueue(scl_engine* e, Lane& ln, const float* dq, const int32_t* di, const scl_batch_query* q, scl_batch_result* r, int missing_to_zero)
 {
     const int Q = q->Q, K = q->K;
     const size_t QK = (size_t)Q * K;
-    CK(e->cand_ids.ensure(QK * 4)); CK(e->cand_d2.ensure(QK * 4)); CK(e->cand_dist.ensure(QK * 8)); CK(e->cand_shift.ensure(QK * 4));
-    CK(e->best_id.ensure((size_t)Q * 4)); CK(e->best_dist.ensure((size_t)Q * 8)); CK(e->best_shift.ensure((size_t)Q * 4));
-    int rc = query_dev(e, dq, di, Q, K, q->n_db, q->metric, missing_to_zero, e->cand_ids.as<int32_t>(), e->cand_d2.as<float>(),
-                       e->cand_dist.as<double>(), e->cand_shift.as<int32_t>(), e->best_id.as<int32_t>(), e->best_dist.as<double>(),
-                       e->best_shift.as<int32_t>());
+    CK(ln.cand_ids.ensure(QK * 4)); CK(ln.cand_d2.ensure(QK * 4)); CK(ln.cand_dist.ensure(QK * 8)); CK(ln.cand_shift.ensure(QK * 4));
+    CK(ln.best_id.ensure((size_t)Q * 4)); CK(ln.best_dist.ensure((size_t)Q * 8)); CK(ln.best_shift.ensure((size_t)Q * 4));
+    int rc = query_dev(e, ln, dq, di, Q, K, q->n_db, q->metric, missing_to_zero, ln.cand_ids.as<int32_t>(), ln.cand_d2.as<float>(),
+                       ln.cand_dist.as<double>(), ln.cand_shift.as<int32_t>(), ln.best_id.as<int32_t>(), ln.best_dist.as<double>(),
+                       ln.best_shift.as<int32_t>());
     if (rc) return rc;
-    if (r->cand_ids) CK(cudaMemcpyAsync(r->cand_ids, e->cand_ids.p, QK * 4, cudaMemcpyDeviceToHost, e->stream));
-    if (r->cand_d2) CK(cudaMemcpyAsync(r->cand_d2, e->cand_d2.p, QK * 4, cudaMemcpyDeviceToHost, e->stream));
-    if (r->cand_dist) CK(cudaMemcpyAsync(r->cand_dist, e->cand_dist.p, QK * 8, cudaMemcpyDeviceToHost, e->stream));
-    if (r->cand_shift) CK(cudaMemcpyAsync(r->cand_shift, e->cand_shift.p, QK * 4, cudaMemcpyDeviceToHost, e->stream));
-    if (r->best_id) CK(cudaMemcpyAsync(r->best_id, e->best_id.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, e->stream));
-    if (r->best_dist) CK(cudaMemcpyAsync(r->best_dist, e->best_dist.p, (size_t)Q * 8, cudaMemcpyDeviceToHost, e->stream));
-    if (r->best_shift) CK(cudaMemcpyAsync(r->best_shift, e->best_shift.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (r->cand_ids) CK(cudaMemcpyAsync(r->cand_ids, ln.cand_ids.p, QK * 4, cudaMemcpyDeviceToHost, ln.stream));
+    if (r->cand_d2) CK(cudaMemcpyAsync(r->cand_d2, ln.cand_d2.p, QK * 4, cudaMemcpyDeviceToHost, ln.stream));
+    if (r->cand_dist) CK(cudaMemcpyAsync(r->cand_dist, ln.cand_dist.p, QK * 8, cudaMemcpyDeviceToHost, ln.stream));
+    if (r->cand_shift) CK(cudaMemcpyAsync(r->cand_shift, ln.cand_shift.p, QK * 4, cudaMemcpyDeviceToHost, ln.stream));
+    if (r->best_id) CK(cudaMemcpyAsync(r->best_id, ln.best_id.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, ln.stream));
+    if (r->best_dist) CK(cudaMemcpyAsync(r->best_dist, ln.best_dist.p, (size_t)Q * 8, cudaMemcpyDeviceToHost, ln.stream));
+    if (r->best_shift) CK(cudaMemcpyAsync(r->best_shift, ln.best_shift.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, ln.stream));
     return SCL_OK;
 }
 
@@ -318,25 +364,35 @@ int check_host_query(scl_engine* e, const scl_batch_query* q, scl_batch_result* 
     return SCL_OK;
 }
 
+// host queries -> the lane's staging buffers (on the lane's stream: the copy of one lane overlaps the kernels of the others)
+int stage_host_query(scl_engine* e, Lane& ln, const scl_batch_query* q, const float** dq, const int32_t** di)
+{
+    const int Q = q->Q;
+    const size_t RS = e->RS();
+    *dq = nullptr; *di = nullptr;
+    { int rc = lane_begin(e, ln); if (rc) return rc; }
+    if (q->q_desc) {
+        CK(ln.qdesc.ensure((size_t)Q * RS * 4));
+        CK(cudaMemcpyAsync(ln.qdesc.p, q->q_desc, (size_t)Q * RS * 4, cudaMemcpyHostToDevice, ln.stream));
+        *dq = ln.qdesc.as<float>();
+    }
+    if (q->q_ids) {
+        CK(ln.qids.ensure((size_t)Q * 4));
+        CK(cudaMemcpyAsync(ln.qids.p, q->q_ids, (size_t)Q * 4, cudaMemcpyHostToDevice, ln.stream));
+        *di = ln.qids.as<int32_t>();
+    }
+    return SCL_OK;
+}
+
 int query_host(scl_engine* e, const scl_batch_query* q, scl_batch_result* r, int missing_to_zero)
 {
     int rc = check_host_query(e, q, r); if (rc) return rc;
-    const int Q = q->Q;
-    if (Q <= 0) return SCL_OK;
-    const size_t RS = e->RS();
+    if (q->Q <= 0) return SCL_OK;
+    Lane& ln = e->lanes[0];                          /* behind any pipelined batch of lane 0 in stream order */
     const float* dq = nullptr; const int32_t* di = nullptr;
-    if (q->q_desc) {
-        CK(e->qdesc.ensure((size_t)Q * RS * 4));
-        CK(cudaMemcpyAsync(e->qdesc.p, q->q_desc, (size_t)Q * RS * 4, cudaMemcpyHostToDevice, e->stream));
-        dq = e->qdesc.as<float>();
-    }
-    if (q->q_ids) {
-        CK(e->qids.ensure((size_t)Q * 4));
-        CK(cudaMemcpyAsync(e->qids.p, q->q_ids, (size_t)Q * 4, cudaMemcpyHostToDevice, e->stream));
-        di = e->qids.as<int32_t>();
-    }
-    rc = query_host_enqueue(e, dq, di, q, r, missing_to_zero); if (rc) return rc;
-    CK(cudaStreamSynchronize(e->stream));
+    rc = stage_host_query(e, ln, q, &dq, &di); if (rc) return rc;
+    rc = query_host_enqueue(e, ln, dq, di, q, r, missing_to_zero); if (rc) return rc;
+    CK(cudaStreamSynchronize(ln.stream));
     return SCL_OK;
 }
 
@@ -383,14 +439,18 @@ int scl_destroy(scl_engine* e)
         std::lock_guard<std::mutex> lk(e->mu);
         cudaSetDevice(e->device);
         cudaStreamSynchronize(e->stream);
+        for (int l = 0; l < scl_engine::kLanes; l++) {
+            Lane& ln = e->lanes[l];
+            if (l > 0 && ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamDestroy(ln.stream); }
+            if (ln.done) cudaEventDestroy(ln.done);
+            for (DevBuf* b : ln.all) b->release();
+        }
+        if (e->db_ready) cudaEventDestroy(e->db_ready);
         for (int r = 0; r < 16; r++) if (e->xchg_peer_map[r]) cudaIpcCloseMemHandle(e->xchg_peer_map[r]);
         if (e->xchg_buf) cudaFree(e->xchg_buf);
-        cudaFree(e->d_desc); cudaFree(e->d_keys); cudaFree(e->d_knorm); cudaFree(e->d_kn2max); cudaFree(e->d_kimg);
+        cudaFree(e->d_desc); cudaFree(e->d_keys); cudaFree(e->d_knorm); cudaFree(e->d_cstat); cudaFree(e->d_kn2max); cudaFree(e->d_kimg);
         DevBuf* bufs[] = {&e->pts, &e->offsets, &e->gbins, &e->tickets, &e->stage_desc, &e->stage_keys, &e->stage_knorm,
-                          &e->bins_ring, &e->bins_sector, &e->knn_tickets, &e->qdesc, &e->qids, &e->qlocal, &e->qkeys, &e->qknorm, &e->part_ids,
-                          &e->part_d2, &e->cand_ids, &e->cand_d2, &e->cand_local, &e->cand_dist, &e->cand_shift, &e->best_id,
-                          &e->best_dist, &e->best_shift, &e->tc_queues, &e->tc_queue_cnt, &e->tc_slots,
-                          &e->tc_fail_list, &e->tc_fail_count, &e->tc_err_probe, &e->icp_src, &e->icp_tgt, &e->icp_raw, &e->icp_acc, &e->icp_nn,
+                          &e->bins_ring, &e->bins_sector, &e->icp_src, &e->icp_tgt, &e->icp_raw, &e->icp_acc, &e->icp_nn,
                           &e->icp_grid[0][0], &e->icp_grid[0][1], &e->icp_grid[0][2], &e->icp_grid[0][3], &e->icp_grid[0][4],
                           &e->icp_grid[1][0], &e->icp_grid[1][1], &e->icp_grid[1][2], &e->icp_grid[1][3], &e->icp_grid[1][4]};
         for (DevBuf* b : bufs) b->release();
@@ -399,8 +459,6 @@ int scl_destroy(scl_engine* e)
         for (DevBuf* b : cloud_bufs) b->release();
         for (auto& v : e->ev) for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         for (cudaEvent_t x : e->ev_pool) cudaEventDestroy(x);
-        for (int i = 0; i < scl_engine::kPipeDepth; i++) { e->pipe_qdesc[i].release(); e->pipe_qids[i].release(); if (e->pipe_copied[i]) cudaEventDestroy(e->pipe_copied[i]); if (e->pipe_done[i]) cudaEventDestroy(e->pipe_done[i]); }
-        if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
         if (e->own_stream) cudaStreamDestroy(e->stream);
     }
     delete e;
@@ -415,6 +473,8 @@ int scl_set_stream(scl_engine* e, void* s)
     CK(cudaStreamSynchronize(e->stream));
     if (e->own_stream) cudaStreamDestroy(e->stream);
     e->stream = static_cast<cudaStream_t>(s); e->own_stream = false;
+    e->lanes[0].stream = e->stream;
+    e->db_dirty = true;
     return SCL_OK;
 }
 
@@ -427,18 +487,30 @@ int scl_set_knn_mode(scl_engine* e, int mode, int count_fallbacks)
     return SCL_OK;
 }
 
+int scl_set_scdist_mode(scl_engine* e, int mode)
+{
+    LOCK();
+    if (mode != 0 && mode != 1) FAIL(SCL_ERR_INVALID, "mode must be 0 (FP32 prefilter + exact evaluation of the shifts that can win) or 1 (every shift exactly)");
+    e->scdist_exact_all = mode == 1;
+    return SCL_OK;
+}
+
 int scl_knn_stats(scl_engine* e, long long* tc_queries, long long* fallback_queries)
 {
     LOCK();
     if (tc_queries) *tc_queries = e->stat_tc_queries;
     if (fallback_queries) {
-        /* counted on the device by the re-rank kernel (ints [8] and [24] of the counter block, one per call parity) */
-        int h[32] = {0};
-        if (e->tc_fail_count.p) {
-            CK(cudaStreamSynchronize(e->stream));
-            CK(cudaMemcpy(h, e->tc_fail_count.p, sizeof(h), cudaMemcpyDeviceToHost));
+        /* counted on the device by the re-rank kernel (ints [8] and [24] of each lane's counter block, one per call parity) */
+        long long total = 0;
+        for (int l = 0; l < scl_engine::kLanes; l++) {
+            Lane& ln = e->lanes[l];
+            if (!ln.tc_fail_count.p) continue;
+            int h[32] = {0};
+            CK(cudaStreamSynchronize(ln.stream));
+            CK(cudaMemcpy(h, ln.tc_fail_count.p, sizeof(h), cudaMemcpyDeviceToHost));
+            total += (long long)h[8] + (long long)h[24];
         }
-        *fallback_queries = (long long)h[8] + (long long)h[24];
+        *fallback_queries = total;
     }
     return SCL_OK;
 }
@@ -450,6 +522,7 @@ int scl_stage_time(scl_engine* e, int stage, double* ms, int* launches)
     LOCK();
     if (stage < 0 || stage > 3 || !ms || !launches) FAIL(SCL_ERR_INVALID, "bad stage");
     CK(cudaStreamSynchronize(e->stream));
+    for (int l = 1; l < scl_engine::kLanes; l++) if (e->lanes[l].stream) CK(cudaStreamSynchronize(e->lanes[l].stream));
     double total = 0.0; int n = 0;
     for (auto& pr : e->ev[stage]) {
         float t = 0.f;
@@ -511,9 +584,11 @@ int scl_insert_batch(scl_engine* e, const float* descs, int n, const int8_t* rob
     const size_t RS = e->RS();
     float* dst = e->d_desc + (size_t)e->n * RS;
     CK(cudaMemcpyAsync(dst, descs, (size_t)n * RS * 4, cudaMemcpyHostToDevice, e->stream));   /* wire decode, descriptor.h:1575-1582 */
-    CK(scl_launch_ring_keys(dst, n, e->p.num_ring, e->p.num_sector, e->d_keys + (size_t)e->n * e->p.num_ring, e->d_knorm + e->n, e->d_kn2max, e->stream));
+    CK(scl_launch_ring_keys(dst, n, e->p.num_ring, e->p.num_sector, e->d_keys + (size_t)e->n * e->p.num_ring, e->d_knorm + e->n, e->d_kn2max,
+                            e->d_cstat + (size_t)e->n * 2 * e->p.num_sector, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     append_index(e, n, robots, indices); e->n += n;
+    e->db_dirty = true;
     return SCL_OK;
 }
 
@@ -528,8 +603,10 @@ int scl_insert_batch_dev(scl_engine* e, const float* descs_dev, int n, const int
     const size_t RS = e->RS();
     float* dst = e->d_desc + (size_t)e->n * RS;
     CK(cudaMemcpyAsync(dst, descs_dev, (size_t)n * RS * 4, cudaMemcpyDeviceToDevice, e->stream));
-    CK(scl_launch_ring_keys(dst, n, e->p.num_ring, e->p.num_sector, e->d_keys + (size_t)e->n * e->p.num_ring, e->d_knorm + e->n, e->d_kn2max, e->stream));
+    CK(scl_launch_ring_keys(dst, n, e->p.num_ring, e->p.num_sector, e->d_keys + (size_t)e->n * e->p.num_ring, e->d_knorm + e->n, e->d_kn2max,
+                            e->d_cstat + (size_t)e->n * 2 * e->p.num_sector, e->stream));
     append_index(e, n, robots, indices); e->n += n;
+    e->db_dirty = true;
     return SCL_OK;
 }
 
@@ -568,46 +645,95 @@ int scl_query_batch_dev(scl_engine* e, const scl_batch_query* q, scl_batch_resul
 {
     LOCK();
     if (!q || !r) FAIL(SCL_ERR_INVALID, "null query/result");
-    return query_dev(e, q->q_desc, q->q_ids, q->Q, q->K, q->n_db, q->metric, 0, r->cand_ids, r->cand_d2, r->cand_dist, r->cand_shift,
+    return query_dev(e, e->lanes[0], q->q_desc, q->q_ids, q->Q, q->K, q->n_db, q->metric, 0, r->cand_ids, r->cand_d2, r->cand_dist, r->cand_shift,
                      r->best_id, r->best_dist, r->best_shift);
 }
+
+int scl_num_lanes(void) { return scl_engine::kLanes; }
+
+int scl_query_batch_dev_lane(scl_engine* e, int lane, const scl_batch_query* q, scl_batch_result* r)
+{
+    LOCK();
+    if (!q || !r) FAIL(SCL_ERR_INVALID, "null query/result");
+    if (lane < 0 || lane >= scl_engine::kLanes) FAIL(SCL_ERR_INVALID, "no such lane");
+    return query_dev(e, e->lanes[lane], q->q_desc, q->q_ids, q->Q, q->K, q->n_db, q->metric, 0, r->cand_ids, r->cand_d2, r->cand_dist, r->cand_shift,
+                     r->best_id, r->best_dist, r->best_shift);
+}
+
+int scl_lanes_fork(scl_engine* e, void* stream)
+{
+    LOCK();
+    cudaEvent_t ev;
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(ev, static_cast<cudaStream_t>(stream)));
+    for (int l = 0; l < scl_engine::kLanes; l++) {
+        Lane& ln = e->lanes[l];
+        int rc = lane_begin(e, ln); if (rc) { cudaEventDestroy(ev); return rc; }
+        if (ln.stream != static_cast<cudaStream_t>(stream)) CK(cudaStreamWaitEvent(ln.stream, ev, 0));
+    }
+    CK(cudaEventDestroy(ev));                        /* released once the waits that captured it have passed */
+    return SCL_OK;
+}
+
+int scl_lanes_join(scl_engine* e, void* stream)
+{
+    LOCK();
+    for (int l = 0; l < scl_engine::kLanes; l++) {
+        Lane& ln = e->lanes[l];
+        if (!ln.stream || ln.stream == static_cast<cudaStream_t>(stream)) continue;
+        cudaEvent_t ev;
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CK(cudaEventRecord(ev, ln.stream));
+        CK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), ev, 0));
+        CK(cudaEventDestroy(ev));
+    }
+    return SCL_OK;
+}
+
+int scl_lane_sync(scl_engine* e, int lane)
+{
+    if (!e) return SCL_ERR_INVALID;
+    cudaStream_t s;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        if (lane < 0 || lane >= scl_engine::kLanes) FAIL(SCL_ERR_INVALID, "no such lane");
+        s = e->lanes[lane].stream;
+    }
+    cudaSetDevice(e->device);
+    if (s && cudaStreamSynchronize(s) != cudaSuccess) { std::lock_guard<std::mutex> lk(e->mu); FAIL(SCL_ERR_CUDA, "cudaStreamSynchronize failed"); }
+    return SCL_OK;
+}
+
+namespace {
+// ticket -> lane; at most kLanes batches in flight
+int pipe_take_lane(scl_engine* e, Lane** out, int* ticket)
+{
+    const int l = (int)(e->pipe_next % scl_engine::kLanes);
+    Lane& ln = e->lanes[l];
+    if (ln.busy) FAIL(SCL_ERR_INVALID, "every lane has a batch in flight: wait for the oldest one first");
+    if (!ln.done) CK(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+    *out = &ln;
+    *ticket = (int)(e->pipe_next & 0x7fffffff);
+    return SCL_OK;
+}
+} // namespace
 
 int scl_query_batch_submit(scl_engine* e, const scl_batch_query* q, scl_batch_result* r, int* ticket)
 {
     LOCK();
     if (!ticket) FAIL(SCL_ERR_INVALID, "null ticket");
     int rc = check_host_query(e, q, r); if (rc) return rc;
-    const int b = (int)(e->pipe_next % scl_engine::kPipeDepth);
-    if (e->pipe_busy[b]) FAIL(SCL_ERR_INVALID, "four batches are already in flight: wait for the oldest one first");
-    if (!e->copy_stream) {
-        CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < scl_engine::kPipeDepth; i++) {
-            CK(cudaEventCreateWithFlags(&e->pipe_copied[i], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&e->pipe_done[i], cudaEventDisableTiming));
-        }
-    }
-    const int Q = q->Q;
-    const size_t RS = e->RS();
-    const float* dq = nullptr; const int32_t* di = nullptr;
-    if (Q > 0) {
-        /* staging buffer b was last read by the batch submitted kPipeDepth calls ago, whose wait has returned (pipe_busy) */
-        if (q->q_desc) {
-            CK(e->pipe_qdesc[b].ensure((size_t)Q * RS * 4));
-            CK(cudaMemcpyAsync(e->pipe_qdesc[b].p, q->q_desc, (size_t)Q * RS * 4, cudaMemcpyHostToDevice, e->copy_stream));
-            dq = e->pipe_qdesc[b].as<float>();
-        }
-        if (q->q_ids) {
-            CK(e->pipe_qids[b].ensure((size_t)Q * 4));
-            CK(cudaMemcpyAsync(e->pipe_qids[b].p, q->q_ids, (size_t)Q * 4, cudaMemcpyHostToDevice, e->copy_stream));
-            di = e->pipe_qids[b].as<int32_t>();
-        }
-        CK(cudaEventRecord(e->pipe_copied[b], e->copy_stream));
-        CK(cudaStreamWaitEvent(e->stream, e->pipe_copied[b], 0));
-        rc = query_host_enqueue(e, dq, di, q, r, 0); if (rc) return rc;
-    }
-    CK(cudaEventRecord(e->pipe_done[b], e->stream));
-    e->pipe_busy[b] = true;
-    *ticket = (int)(e->pipe_next & 0x7fffffff);
+    Lane* lnp = nullptr; int t = 0;
+    rc = pipe_take_lane(e, &lnp, &t); if (rc) return rc;
+    Lane& ln = *lnp;
+    if (q->Q > 0) {
+        const float* dq = nullptr; const int32_t* di = nullptr;
+        rc = stage_host_query(e, ln, q, &dq, &di); if (rc) return rc;
+        rc = query_host_enqueue(e, ln, dq, di, q, r, 0); if (rc) return rc;
+    } else { rc = lane_begin(e, ln); if (rc) return rc; }
+    CK(cudaEventRecord(ln.done, ln.stream));
+    ln.busy = true;
+    *ticket = t;
     e->pipe_next++;
     return SCL_OK;
 }
@@ -618,14 +744,14 @@ int scl_query_batch_wait(scl_engine* e, int ticket)
     cudaEvent_t ev;
     {
         std::lock_guard<std::mutex> lk(e->mu);
-        const int b = ticket % scl_engine::kPipeDepth;
-        if (ticket < 0 || !e->pipe_busy[b]) FAIL(SCL_ERR_INVALID, "no batch in flight for this ticket");
-        ev = e->pipe_done[b];
+        const int l = ticket % scl_engine::kLanes;
+        if (ticket < 0 || !e->lanes[l].busy) FAIL(SCL_ERR_INVALID, "no batch in flight for this ticket");
+        ev = e->lanes[l].done;
     }
     cudaSetDevice(e->device);
     cudaError_t err = cudaEventSynchronize(ev);              /* outside the lock: inserts and submits may proceed meanwhile */
     std::lock_guard<std::mutex> lk(e->mu);
-    e->pipe_busy[ticket % scl_engine::kPipeDepth] = false;
+    e->lanes[ticket % scl_engine::kLanes].busy = false;
     if (err != cudaSuccess) { e->err = std::string("cudaEventSynchronize: ") + cudaGetErrorString(err); return SCL_ERR_CUDA; }
     return SCL_OK;
 }
@@ -644,7 +770,7 @@ int scl_knn_batch_dev(scl_engine* e, const scl_batch_query* q, int32_t* ids_dev,
 {
     LOCK();
     if (!q || !ids_dev || !d2_dev) FAIL(SCL_ERR_INVALID, "null argument");
-    return knn_dev(e, q->q_desc, q->q_ids, q->Q, q->K, q->n_db, q->metric, ids_dev, d2_dev, nullptr);
+    return knn_dev(e, e->lanes[0], q->q_desc, q->q_ids, q->Q, q->K, q->n_db, q->metric, ids_dev, d2_dev, nullptr);
 }
 
 int scl_merge_topk_dev(scl_engine* e, int world, int Q, int K, const void* ids_base, const void* d2_base, uint64_t rank_stride_bytes,
@@ -656,17 +782,26 @@ int scl_merge_topk_dev(scl_engine* e, int world, int Q, int K, const void* ids_b
     return SCL_OK;
 }
 
+namespace {
+int scdist_owned(scl_engine* e, Lane& ln, const float* q_desc_dev, const int32_t* q_ids_dev, int Q, int K, const int32_t* cand_ids_dev,
+                 double* dist_dev, int32_t* shift_dev, bool stats_ready /* knn_dev has just run on this lane for these very queries */)
+{
+    /* the global candidate lists are spread over the shards: about K / world of a query's candidates live here */
+    ln.scdist_owned_hint = e->world > 1 ? (K + e->world - 1) / e->world + 1 : 0;
+    const int rc = scdist_dev(e, ln, q_desc_dev, nullptr, q_ids_dev, Q, K, const_cast<int32_t*>(cand_ids_dev), 0, dist_dev, shift_dev, nullptr, nullptr, nullptr,
+                              stats_ready && ln.qstat_of == q_desc_dev && ln.qstat_rows >= Q);
+    ln.scdist_owned_hint = 0;
+    return rc;
+}
+} // namespace
+
 int scl_scdist_owned_dev(scl_engine* e, const float* q_desc_dev, const int32_t* q_ids_dev, int Q, int K, const int32_t* cand_ids_dev,
                          double* dist_dev, int32_t* shift_dev)
 {
     LOCK();
     if (!q_desc_dev || !cand_ids_dev || !dist_dev || !shift_dev) FAIL(SCL_ERR_INVALID, "null argument");
     if (K < 1 || K > 32) FAIL(SCL_ERR_INVALID, "K must be in 1..32");
-    /* the global candidate lists are spread over the shards: about K / world of a query's candidates live here */
-    e->scdist_owned_hint = e->world > 1 ? (K + e->world - 1) / e->world + 1 : 0;
-    const int rc = scdist_dev(e, q_desc_dev, nullptr, q_ids_dev, Q, K, const_cast<int32_t*>(cand_ids_dev), 0, dist_dev, shift_dev, nullptr, nullptr, nullptr);
-    e->scdist_owned_hint = 0;
-    return rc;
+    return scdist_owned(e, e->lanes[0], q_desc_dev, q_ids_dev, Q, K, cand_ids_dev, dist_dev, shift_dev, false);
 }
 
 int scl_combine_owned_dev(scl_engine* e, int world, int Q, int K, const int32_t* q_ids, const int32_t* cand_ids, const void* dist_base,
@@ -680,20 +815,45 @@ int scl_combine_owned_dev(scl_engine* e, int world, int Q, int K, const int32_t*
 }
 
 // ---- peer-memory exchange (k7_exchange.cu) ------------------------------------------------------------------------
-int scl_xchg_create(scl_engine* e, int world, int max_qk, unsigned char* handle64)
+namespace {
+size_t xchg_layout(scl_engine* e, int world, int max_q, int max_k)
+{
+    /* one region per lane: [flags 3 x 16 ints | tickets | point 0 slots | point 1 slots | query areas] */
+    const size_t qk = (size_t)max_q * max_k;
+    const size_t s0 = (qk * 8 + 15) / 16 * 16, s1 = (qk * 12 + 15) / 16 * 16;
+    const size_t s2 = ((size_t)max_q * e->RS() * 4 + 15) / 16 * 16;
+    size_t o = 0;
+    for (int l = 0; l < scl_engine::kLanes; l++) {
+        XchgView& x = e->xchg[l];
+        x.world = world; x.rank = -1;
+        x.flag_off = o; o += 256;
+        x.ticket_off = o; o += 256;
+        x.slot_bytes[0] = s0; x.data_off[0] = o; o += 2 * (size_t)world * s0;
+        x.slot_bytes[1] = s1; x.data_off[1] = o; o += 2 * (size_t)world * s1;
+        x.slot_bytes[2] = s2; x.data_off[2] = o; o += 2 * s2;
+    }
+    return o;
+}
+} // namespace
+
+int scl_xchg_bytes(scl_engine* e, int world, int max_q, int max_k, uint64_t* bytes)
 {
     LOCK();
-    if (world < 2 || world > 16 || max_qk < 1 || !handle64) FAIL(SCL_ERR_INVALID, "bad arguments");
+    if (world < 2 || world > 16 || max_q < 1 || max_k < 1 || !bytes) FAIL(SCL_ERR_INVALID, "bad arguments");
+    XchgView keep[scl_engine::kLanes];
+    memcpy(keep, e->xchg, sizeof(keep));
+    *bytes = xchg_layout(e, world, max_q, max_k);
+    memcpy(e->xchg, keep, sizeof(keep));
+    return SCL_OK;
+}
+
+int scl_xchg_create(scl_engine* e, int world, int max_q, int max_k, unsigned char* handle64)
+{
+    LOCK();
+    if (world < 2 || world > 16 || max_q < 1 || max_k < 1 || max_k > 32 || !handle64) FAIL(SCL_ERR_INVALID, "bad arguments");
     if (e->xchg_buf) FAIL(SCL_ERR_INVALID, "exchange buffer exists already");
-    XchgView& x = e->xchg;
-    x.world = world; x.rank = -1;
-    x.flag_off = 0; x.ticket_off = 128;
-    x.slot_bytes[0] = ((size_t)max_qk * 8 + 15) / 16 * 16;
-    x.slot_bytes[1] = ((size_t)max_qk * 12 + 15) / 16 * 16;
-    x.data_off[0] = 256;
-    x.data_off[1] = x.data_off[0] + 2 * (size_t)world * x.slot_bytes[0];
-    e->xchg_bytes = x.data_off[1] + 2 * (size_t)world * x.slot_bytes[1];
-    e->xchg_qk = max_qk;
+    e->xchg_bytes = xchg_layout(e, world, max_q, max_k);
+    e->xchg_qk = max_q * max_k; e->xchg_q = max_q;
     CK(cudaMalloc(&e->xchg_buf, e->xchg_bytes));
     CK(cudaMemset(e->xchg_buf, 0, e->xchg_bytes));
     cudaIpcMemHandle_t h;
@@ -706,25 +866,43 @@ int scl_xchg_create(scl_engine* e, int world, int max_qk, unsigned char* handle6
 int scl_xchg_open(scl_engine* e, int world, int rank, const unsigned char* handles)
 {
     LOCK();
-    if (!e->xchg_buf || world != e->xchg.world || rank < 0 || rank >= world || !handles) FAIL(SCL_ERR_INVALID, "bad arguments");
+    if (!e->xchg_buf || world != e->xchg[0].world || rank < 0 || rank >= world || !handles) FAIL(SCL_ERR_INVALID, "bad arguments");
+    unsigned char* peer[16] = {};
     for (int r = 0; r < world; r++) {
-        if (r == rank) { e->xchg.peer[r] = static_cast<unsigned char*>(e->xchg_buf); continue; }
+        if (r == rank) { peer[r] = static_cast<unsigned char*>(e->xchg_buf); continue; }
         cudaIpcMemHandle_t h;
         memcpy(&h, handles + (size_t)r * 64, 64);
         void* p = nullptr;
         CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
         e->xchg_peer_map[r] = p;
-        e->xchg.peer[r] = static_cast<unsigned char*>(p);
+        peer[r] = static_cast<unsigned char*>(p);
     }
-    e->xchg.rank = rank;
+    for (int l = 0; l < scl_engine::kLanes; l++) { memcpy(e->xchg[l].peer, peer, sizeof(peer)); e->xchg[l].rank = rank; }
     e->xchg_open = true;
     return SCL_OK;
 }
+
+/* the same within ONE process (scl_sharded.cu: one engine per device of a box): the peers' buffers are plain device
+ * pointers once peer access is enabled */
+int scl_xchg_open_local(scl_engine* e, int world, int rank, void* const* peer_bufs)
+{
+    LOCK();
+    if (!e->xchg_buf || world != e->xchg[0].world || rank < 0 || rank >= world || !peer_bufs) FAIL(SCL_ERR_INVALID, "bad arguments");
+    for (int l = 0; l < scl_engine::kLanes; l++) {
+        for (int r = 0; r < world; r++) e->xchg[l].peer[r] = static_cast<unsigned char*>(r == rank ? e->xchg_buf : peer_bufs[r]);
+        e->xchg[l].rank = rank;
+    }
+    e->xchg_open = true;
+    return SCL_OK;
+}
+
+void* scl_xchg_buffer(scl_engine* e) { return e ? e->xchg_buf : nullptr; }
 
 int scl_xchg_close(scl_engine* e)
 {
     LOCK();
     cudaStreamSynchronize(e->stream);
+    for (int l = 1; l < scl_engine::kLanes; l++) if (e->lanes[l].stream) cudaStreamSynchronize(e->lanes[l].stream);
     for (int r = 0; r < 16; r++) if (e->xchg_peer_map[r]) { cudaIpcCloseMemHandle(e->xchg_peer_map[r]); e->xchg_peer_map[r] = nullptr; }
     if (e->xchg_buf) { cudaFree(e->xchg_buf); e->xchg_buf = nullptr; }
     e->xchg_open = false;
@@ -737,7 +915,7 @@ int scl_xchg_merge_topk_dev(scl_engine* e, int seq, int Q, int K, const void* my
     if (!e->xchg_open) FAIL(SCL_ERR_INVALID, "exchange not open");
     if (seq < 1 || Q < 0 || K < 1 || (long long)Q * K > e->xchg_qk || ((long long)Q * K) % 4 || !my_block_dev || !out_ids || !out_d2)
         FAIL(SCL_ERR_INVALID, "bad arguments (Q*K must be a multiple of 4 within the size given to scl_xchg_create)");
-    CK(scl_launch_xchg_merge_topk(e->xchg, seq, Q, K, my_block_dev, out_ids, out_d2, e->stream));
+    CK(scl_launch_xchg_merge_topk(e->xchg[0], seq, Q, K, my_block_dev, out_ids, out_d2, e->stream));
     return SCL_OK;
 }
 
@@ -748,8 +926,84 @@ int scl_xchg_combine_dev(scl_engine* e, int seq, int Q, int K, const void* my_bl
     if (!e->xchg_open) FAIL(SCL_ERR_INVALID, "exchange not open");
     if (seq < 1 || Q < 0 || K < 1 || (long long)Q * K > e->xchg_qk || ((long long)Q * K) % 4 || !my_block_dev || !cand_ids || !m)
         FAIL(SCL_ERR_INVALID, "bad arguments (Q*K must be a multiple of 4 within the size given to scl_xchg_create)");
-    CK(scl_launch_xchg_combine(e->xchg, seq, Q, K, my_block_dev, q_ids, cand_ids, m->cand_dist, m->cand_shift, m->best_id, m->best_dist,
+    CK(scl_launch_xchg_combine(e->xchg[0], seq, Q, K, my_block_dev, q_ids, cand_ids, m->cand_dist, m->cand_shift, m->best_id, m->best_dist,
                                m->best_shift, e->stream));
+    return SCL_OK;
+}
+
+// ---- the sharded query as ONE call per batch and lane -----------------------------------------------------
+namespace {
+// device side of one sharded step on lane ln: K2 + K3 on the shard, exchange + global top-K, K4 on the owned candidates,
+// exchange + winner scan. q_desc: the full batch in device memory. Results: device pointers (scratch where null).
+int shard_step(scl_engine* e, Lane& ln, int lane, const float* q_desc, const int32_t* q_ids, int Q, int K, int n_db, int metric, scl_batch_result* r)
+{
+    if (!e->xchg_open) FAIL(SCL_ERR_INVALID, "exchange not open (scl_xchg_create / scl_xchg_open)");
+    if (Q < 1 || K < 1 || K > 32 || (long long)Q * K > e->xchg_qk || ((long long)Q * K) % 4) FAIL(SCL_ERR_INVALID, "Q*K must be a multiple of 4 within the size given to scl_xchg_create");
+    const size_t QK = (size_t)Q * K;
+    CK(ln.x_blob1.ensure(QK * 8)); CK(ln.x_blob2.ensure(QK * 12)); CK(ln.x_ids.ensure(QK * 4)); CK(ln.x_d2.ensure(QK * 4));
+    int32_t* loc_ids = ln.x_blob1.as<int32_t>(); float* loc_d2 = reinterpret_cast<float*>(ln.x_blob1.as<unsigned char>() + QK * 4);
+    double* own_dist = ln.x_blob2.as<double>(); int32_t* own_shift = reinterpret_cast<int32_t*>(ln.x_blob2.as<unsigned char>() + QK * 8);
+    int32_t* g_ids = r->cand_ids ? r->cand_ids : ln.x_ids.as<int32_t>();
+    float* g_d2 = r->cand_d2 ? r->cand_d2 : ln.x_d2.as<float>();
+    int rc = knn_dev(e, ln, q_desc, nullptr, Q, K, n_db, metric, loc_ids, loc_d2, nullptr); if (rc) return rc;
+    const int seq = ++ln.xseq;
+    CK(scl_launch_xchg_merge_topk(e->xchg[lane], seq, Q, K, ln.x_blob1.p, g_ids, g_d2, ln.stream));
+    rc = scdist_owned(e, ln, q_desc, q_ids, Q, K, g_ids, own_dist, own_shift, true); if (rc) return rc;
+    CK(scl_launch_xchg_combine(e->xchg[lane], seq, Q, K, ln.x_blob2.p, q_ids, g_ids, r->cand_dist, r->cand_shift, r->best_id, r->best_dist,
+                               r->best_shift, ln.stream));
+    return SCL_OK;
+}
+} // namespace
+
+int scl_shard_query_dev(scl_engine* e, int lane, const scl_batch_query* q, scl_batch_result* r)
+{
+    LOCK();
+    if (!q || !r || !q->q_desc) FAIL(SCL_ERR_INVALID, "a sharded query needs device descriptors and a result");
+    if (lane < 0 || lane >= scl_engine::kLanes) FAIL(SCL_ERR_INVALID, "no such lane");
+    return shard_step(e, e->lanes[lane], lane, q->q_desc, q->q_ids, q->Q, q->K, q->n_db, q->metric, r);
+}
+
+int scl_shard_query_submit(scl_engine* e, const scl_batch_query* q, scl_batch_result* r, int* ticket)
+{
+    LOCK();
+    if (!q || !r || !ticket || !q->q_desc) FAIL(SCL_ERR_INVALID, "a sharded query needs host descriptors, a result and a ticket");
+    if (!e->xchg_open) FAIL(SCL_ERR_INVALID, "exchange not open (scl_xchg_create / scl_xchg_open)");
+    const int Q = q->Q, K = q->K, world = e->world, rank = e->rank;
+    if (Q < 1 || Q > e->xchg_q || Q % world) FAIL(SCL_ERR_INVALID, "Q must be a multiple of the world size within the size given to scl_xchg_create");
+    Lane* lnp = nullptr; int t = 0;
+    int rc = pipe_take_lane(e, &lnp, &t); if (rc) return rc;
+    Lane& ln = *lnp;
+    const int lane = (int)(e->pipe_next % scl_engine::kLanes);
+    rc = lane_begin(e, ln); if (rc) return rc;
+    /* every rank uploads 1 / world of the batch (its rows) straight into its own query area and the gather kernel stores
+     * them into every peer's: the host link carries each descriptor once, NVLink the rest */
+    const size_t RS4 = (size_t)e->RS() * 4;
+    const XchgView& x = e->xchg[lane];
+    const int seq_next = ln.xseq + 1;
+    unsigned char* area = static_cast<unsigned char*>(e->xchg_buf) + x.data_off[2] + (size_t)(seq_next & 1) * x.slot_bytes[2];
+    const int rows = Q / world, row0 = rank * rows;
+    CK(cudaMemcpyAsync(area + (size_t)row0 * RS4, reinterpret_cast<const unsigned char*>(q->q_desc) + (size_t)row0 * RS4, (size_t)rows * RS4,
+                       cudaMemcpyHostToDevice, ln.stream));
+    /* the gather uses its own step counter space: exchange point 2 of step seq_next */
+    CK(scl_launch_xchg_gather_queries(x, seq_next, area + (size_t)row0 * RS4, (size_t)row0 * RS4, (size_t)rows * RS4, ln.stream));
+    const size_t QK = (size_t)Q * K;
+    CK(ln.cand_dist.ensure(QK * 8)); CK(ln.cand_shift.ensure(QK * 4));
+    CK(ln.best_id.ensure((size_t)Q * 4)); CK(ln.best_dist.ensure((size_t)Q * 8)); CK(ln.best_shift.ensure((size_t)Q * 4));
+    CK(ln.cand_ids.ensure(QK * 4)); CK(ln.cand_d2.ensure(QK * 4));
+    scl_batch_result d{ln.cand_ids.as<int32_t>(), ln.cand_d2.as<float>(), ln.cand_dist.as<double>(), ln.cand_shift.as<int32_t>(),
+                       ln.best_id.as<int32_t>(), ln.best_dist.as<double>(), ln.best_shift.as<int32_t>()};
+    rc = shard_step(e, ln, lane, reinterpret_cast<const float*>(area), nullptr, Q, K, q->n_db, q->metric, &d); if (rc) return rc;
+    if (r->cand_ids) CK(cudaMemcpyAsync(r->cand_ids, d.cand_ids, QK * 4, cudaMemcpyDeviceToHost, ln.stream));
+    if (r->cand_d2) CK(cudaMemcpyAsync(r->cand_d2, d.cand_d2, QK * 4, cudaMemcpyDeviceToHost, ln.stream));
+    if (r->cand_dist) CK(cudaMemcpyAsync(r->cand_dist, d.cand_dist, QK * 8, cudaMemcpyDeviceToHost, ln.stream));
+    if (r->cand_shift) CK(cudaMemcpyAsync(r->cand_shift, d.cand_shift, QK * 4, cudaMemcpyDeviceToHost, ln.stream));
+    if (r->best_id) CK(cudaMemcpyAsync(r->best_id, d.best_id, (size_t)Q * 4, cudaMemcpyDeviceToHost, ln.stream));
+    if (r->best_dist) CK(cudaMemcpyAsync(r->best_dist, d.best_dist, (size_t)Q * 8, cudaMemcpyDeviceToHost, ln.stream));
+    if (r->best_shift) CK(cudaMemcpyAsync(r->best_shift, d.best_shift, (size_t)Q * 4, cudaMemcpyDeviceToHost, ln.stream));
+    CK(cudaEventRecord(ln.done, ln.stream));
+    ln.busy = true;
+    *ticket = t;
+    e->pipe_next++;
     return SCL_OK;
 }
 

@@ -308,11 +308,30 @@ __global__ void __launch_bounds__(256) polar_bin_kernel(
     }
 }
 
+// Per-entry cache of what distanceBtnScanContext recomputes for both operands of every pair (descriptor.h:1541-1542 ->
+// makeSectorkeyFromScancontext :1477-1489; distDirectSC's column norms :1521-1522): cstat[0..S) = column means (the
+// sector key), cstat[S..2S) = column Euclidean norms, both in double and in the reference's order (sequential over the
+// rows). v * v is exact in double for a float v, so the fused multiply-add rounds exactly like mul-then-add.
+__device__ __forceinline__ void column_stats(const float* __restrict__ tile, int R, int S, int pitch, int lane, double* __restrict__ out)
+{
+    for (int c = lane; c < S; c += 32) {
+        double s = 0.0, ss = 0.0;
+        for (int r = 0; r < R; r++) {
+            const double v = (double)tile[r * pitch + c];
+            s = __dadd_rn(s, v);
+            ss = __fma_rn(v, v, ss);
+        }
+        out[c] = __ddiv_rn(s, (double)R);
+        out[S + c] = __dsqrt_rn(ss);
+    }
+}
+
 // K2 stand-alone: ring keys of n descriptors already in device memory (the insert path,
 // descriptor.h:1572-1599). One warp per descriptor; the descriptor is staged in shared memory
 // with a padded row pitch so the per-row sequential sums are bank-conflict free.
 __global__ void __launch_bounds__(256) ring_key_kernel(const float* __restrict__ desc, int n, int R, int S,
-                                                       float* __restrict__ keys, float* __restrict__ knorm, float* __restrict__ kn2max)
+                                                       float* __restrict__ keys, float* __restrict__ knorm, float* __restrict__ kn2max,
+                                                       double* __restrict__ cstat)
 {
     extern __shared__ float sm[];
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -323,20 +342,23 @@ __global__ void __launch_bounds__(256) ring_key_kernel(const float* __restrict__
         const float* src = desc + (size_t)d * R * S;
         for (int i = lane; i < R * S; i += 32) my[(i / S) * pitch + (i % S)] = __ldg(src + i);
         __syncwarp();
-        for (int r = lane; r < R; r += 32) {
-            double s = 0.0;
-            for (int c = 0; c < S; c++) s = __dadd_rn(s, (double)my[r * pitch + c]);
-            const float kf = __double2float_rn(__ddiv_rn(s, (double)S));
-            keys[(size_t)d * R + r] = kf;
-            mykey[r] = kf;
+        if (keys) {
+            for (int r = lane; r < R; r += 32) {
+                double s = 0.0;
+                for (int c = 0; c < S; c++) s = __dadd_rn(s, (double)my[r * pitch + c]);
+                const float kf = __double2float_rn(__ddiv_rn(s, (double)S));
+                keys[(size_t)d * R + r] = kf;
+                mykey[r] = kf;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                float n2 = 0.0f;
+                for (int r = 0; r < R; r++) n2 = fmaf(mykey[r], mykey[r], n2);
+                knorm[d] = n2;
+                if (kn2max) atomicMax(reinterpret_cast<int*>(kn2max), __float_as_int(n2));
+            }
         }
-        __syncwarp();
-        if (lane == 0) {
-            float n2 = 0.0f;
-            for (int r = 0; r < R; r++) n2 = fmaf(mykey[r], mykey[r], n2);
-            knorm[d] = n2;
-            if (kn2max) atomicMax(reinterpret_cast<int*>(kn2max), __float_as_int(n2));
-        }
+        if (cstat) column_stats(my, R, S, pitch, lane, cstat + (size_t)d * 2 * S);
         __syncwarp();
     }
 }
@@ -346,7 +368,7 @@ __global__ void __launch_bounds__(256) ring_key_kernel(const float* __restrict__
 // and two warps share a descriptor's rows when R > 32. The sums keep the reference's order (sequential, FP64).
 template <int R, int S, int kWarps>
 __global__ void __launch_bounds__(32 * kWarps) ring_key_fixed_kernel(const float* __restrict__ desc, int n, float* __restrict__ keys,
-                                                             float* __restrict__ knorm, float* __restrict__ kn2max)
+                                                             float* __restrict__ knorm, float* __restrict__ kn2max, double* __restrict__ cstat)
 {
     constexpr int kPitch = S | 1, kV4 = R * S / 4, kPerLane = (kV4 + 31) / 32;
     static_assert((R * S) % 4 == 0 && S % 4 == 0, "rows are whole float4s");
@@ -369,6 +391,8 @@ __global__ void __launch_bounds__(32 * kWarps) ring_key_fixed_kernel(const float
         }
     }
     __syncwarp();
+    if (cstat) column_stats(tile[warp], R, S, kPitch, lane, cstat + (size_t)d * 2 * S);
+    if (!keys) return;
     for (int r = lane; r < R; r += 32) {
         double s = 0.0;
 #pragma unroll 4
@@ -436,19 +460,22 @@ cudaError_t scl_launch_polar(const void* pts_dev, const int* offsets_dev, int n_
     return cudaGetLastError();
 }
 
-cudaError_t scl_launch_ring_keys(const float* desc_dev, int n, int R, int S, float* keys, float* knorm, float* kn2max, cudaStream_t stream)
+cudaError_t scl_launch_ring_keys(const float* desc_dev, int n, int R, int S, float* keys, float* knorm, float* kn2max, double* cstat,
+                                 cudaStream_t stream)
 {
     if (n <= 0) return cudaSuccess;
     if ((reinterpret_cast<uintptr_t>(desc_dev) & 15) == 0) {
-        if (R == 20 && S == 60) { ring_key_fixed_kernel<20, 60, 4><<<(n + 3) / 4, 128, 0, stream>>>(desc_dev, n, keys, knorm, kn2max); return cudaGetLastError(); }
-        if (R == 40 && S == 120) { ring_key_fixed_kernel<40, 120, 2><<<(n + 1) / 2, 64, 0, stream>>>(desc_dev, n, keys, knorm, kn2max); return cudaGetLastError(); }
+        if (R == 20 && S == 60) { ring_key_fixed_kernel<20, 60, 4><<<(n + 3) / 4, 128, 0, stream>>>(desc_dev, n, keys, knorm, kn2max, cstat); return cudaGetLastError(); }
+        if (R == 40 && S == 120) { ring_key_fixed_kernel<40, 120, 2><<<(n + 1) / 2, 64, 0, stream>>>(desc_dev, n, keys, knorm, kn2max, cstat); return cudaGetLastError(); }
     }
-    const int warps = 8;
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * (R * (S | 1) + R) * sizeof(float) > 200 * 1024) warps >>= 1;
     const size_t smem = (size_t)warps * (R * (S | 1) + R) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) { cudaFuncSetAttribute(ring_key_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_done = true; }
+    /* per device, not per process: a function attribute belongs to the current device's context */
+    cudaError_t ea = cudaFuncSetAttribute(ring_key_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (ea != cudaSuccess) return ea;
     int blocks = (n + warps - 1) / warps;
     if (blocks > 8 * SCL_NUM_SMS) blocks = 8 * SCL_NUM_SMS;
-    ring_key_kernel<<<blocks, warps * 32, smem, stream>>>(desc_dev, n, R, S, keys, knorm, kn2max);
+    ring_key_kernel<<<blocks, warps * 32, smem, stream>>>(desc_dev, n, R, S, keys, knorm, kn2max, cstat);
     return cudaGetLastError();
 }

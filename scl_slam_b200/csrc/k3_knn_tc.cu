@@ -54,6 +54,7 @@
 #include <cfloat>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 namespace {
@@ -851,23 +852,43 @@ cudaError_t scl_launch_key_image(const float* keys, const float* knorm, int k_lo
     return cudaGetLastError();
 }
 
+// Developer switches (per-role cycle counters, timing experiments that make results wrong) exist only in builds with
+// -DSCL_DEV_SWITCHES; a release build has no environment lookups on the launch path.
+#ifdef SCL_DEV_SWITCHES
+static int dev_flags_env() { const char* f = getenv("SCL_TC_FLAGS"); return f ? atoi(f) : 0; }
+static bool dev_times_env() { return getenv("SCL_TC_TIMES") != nullptr; }
+#else
+static constexpr int dev_flags_env() { return 0; }
+#endif
+
 template <int R>
 static cudaError_t launch_tc(const float* qkeys, int Q, const unsigned char* img, int n_db, int n_ranges, int* slots,
                               uint4* hq, int* hq_cnt, int* dbg, int kp, cudaStream_t stream)
 {
     using C = TcCfg<R>;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::TOTAL);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(knn_tc_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::TOTAL);
+    {
+        /* a function attribute belongs to the current device's context: once per device, not once per process */
+        static bool attr[64] = {false};
+        static std::mutex mu;
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
-        attr = true;
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev >= 64 || !attr[dev]) {
+            e = cudaFuncSetAttribute(knn_tc_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::TOTAL);
+#ifdef SCL_DEV_SWITCHES
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(knn_tc_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::TOTAL);
+#endif
+            if (e != cudaSuccess) return e;
+            if (dev < 64) attr[dev] = true;
+        }
     }
     const int groups = (Q + kQPerCta - 1) / kQPerCta;
-    long long* times = nullptr;
-    const bool want_times = getenv("SCL_TC_TIMES") != nullptr;       /* developer aid: per-role cycle counters on stderr */
-    const int dev_flags = getenv("SCL_TC_FLAGS") ? atoi(getenv("SCL_TC_FLAGS")) : 0;
     const int nb = groups * n_ranges;
+#ifdef SCL_DEV_SWITCHES
+    long long* times = nullptr;
+    const bool want_times = dev_times_env();
+    const int dev_flags = dev_flags_env();
     if (want_times) { cudaMalloc(&times, (size_t)nb * 16 * sizeof(long long)); cudaMemsetAsync(times, 0, (size_t)nb * 128, stream); }
     if (dev_flags & 64) {}
     else if (want_times) knn_tc_kernel<R, true><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, times, slots, hq, hq_cnt, dbg, dev_flags, kp);
@@ -884,6 +905,9 @@ static cudaError_t launch_tc(const float* qkeys, int Q, const unsigned char* img
                 n_db, a[8], a[1] / 8 / a[8], a[0] / 8 / a[8], a[9] / 8 / a[8], a[10] / 8 / a[8], a[11] / 8 / a[8], a[2] / 8, a[8] * 8, a[3] / 8 / 32, amax4, a[6] / a[8], a[7] / a[8], a[5] / 2);
         cudaFree(times);
     }
+#else
+    knn_tc_kernel<R, false><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, nullptr, slots, hq, hq_cnt, dbg, 0, kp);
+#endif
     return cudaGetLastError();
 }
 
@@ -914,7 +938,7 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
     knn_rerank_kernel<M, RR><<<(Qc + kRrWarps - 1) / kRrWarps, 32 * kRrWarps, 0, stream>>>(qk, Qc, keys, K, n_ranges, n_db, reinterpret_cast<const uint4*>(ws.hq), ws.hq_cnt,   \
                                                             ws.slots, kn2max, id_mul, id_add, out_ids + (size_t)q0 * K, out_d2 + (size_t)q0 * K, \
                                                             q0, fail_list, fail_count, ws.err_probe, dev_flags, kprime_for(K), ws.slots, next_fail_count)
-        const int dev_flags = getenv("SCL_TC_FLAGS") ? atoi(getenv("SCL_TC_FLAGS")) : 0;     /* developer aid: timing experiments */
+        const int dev_flags = dev_flags_env();     /* 0 in release builds */
         if (dev_flags & 16) {}
         else if (R == 20) { if (metric == 0) SCL_RERANK(0, 20); else SCL_RERANK(1, 20); }
         else { if (metric == 0) SCL_RERANK(0, 40); else SCL_RERANK(1, 40); }
@@ -922,6 +946,7 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;
     }
+#ifdef SCL_DEV_SWITCHES
     if (ws.err_probe && getenv("SCL_TC_DEBUG")) {                   /* developer aid */
         int h[12];
         cudaStreamSynchronize(stream);
@@ -941,5 +966,6 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
         if (h[9] > 0) fprintf(stderr, "[tc re-rank, averages over %d queries] queue entries %.0f (largest %d), surviving groups %.1f (largest %d), keys in the selection %.1f\n",
                               h[9], (double)h[6] / h[9], h[11], (double)h[7] / h[9], h[10], (double)h[8] / h[9]);
     }
+#endif
     return cudaSuccess;
 }

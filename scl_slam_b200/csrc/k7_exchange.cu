@@ -11,9 +11,10 @@
 //   3. waits until the flags of all ranks have reached the step number, and
 //   4. does the merge (global top-K by (d2, id) / owner pick + strict-< winner scan) on the now complete local buffer.
 // Data slots are double-buffered by step parity: a rank can run at most one exchange point ahead of a peer, because
-// it needs that peer's flag for the point in between (see the reuse argument in DESIGN.md §7). The grid is small
-// (Q / 128 CTAs) so all of its CTAs are resident while they wait; the wait is bounded (a lost peer becomes a trap,
-// not a hung GPU).
+// it needs that peer's flag for the point in between (see the reuse argument in DESIGN.md §7). The grids are small
+// (Q / 128 CTAs, at most 32) so all of their CTAs are resident while they wait; the wait is bounded (a lost peer becomes a
+// trap, not a hung GPU). Every query lane of an engine (engine_internal.h) has its own region of the buffer, flags and
+// step counter, so batches on different lanes exchange independently and their waits overlap other lanes' kernels.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -30,15 +31,16 @@ __device__ __forceinline__ void st_release_sys(int* p, int v)
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// common prologue: publish `bytes` from `src` into slot `rank` of every rank's data area, raise flags, wait for all
-__device__ void publish_and_wait(const XchgView& x, int phase, int seq, const unsigned char* src, size_t bytes)
+// common prologue: publish `bytes` from `src` at byte offset `dst_off` of every rank's buffer, raise this rank's flag of
+// exchange point `phase` in every rank's buffer, wait for the flags of all ranks
+__device__ void publish_and_wait(const XchgView& x, int phase, int seq, const unsigned char* src, size_t bytes, size_t dst_off)
 {
-    const size_t slot_off = x.data_off[phase] + ((size_t)(seq & 1) * x.world + x.rank) * x.slot_bytes[phase];
     const int nthreads = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
     const size_t n16 = bytes / 16;
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
     for (int r = 0; r < x.world; r++) {
-        uint4* d4 = reinterpret_cast<uint4*>(x.peer[r] + slot_off);
+        uint4* d4 = reinterpret_cast<uint4*>(x.peer[r] + dst_off);
+        if (reinterpret_cast<const unsigned char*>(d4) == src) continue;          /* already in place (own slice of a gather) */
         for (size_t i = tid; i < n16; i += nthreads) d4[i] = s4[i];
     }
     __threadfence_system();
@@ -57,11 +59,18 @@ __device__ void publish_and_wait(const XchgView& x, int phase, int seq, const un
         const int* f = reinterpret_cast<const int*>(x.peer[x.rank] + x.flag_off) + phase * 16 + threadIdx.x;
         const long long t0 = clock64();
         while (ld_acquire_sys(f) < seq) {
-            if (clock64() - t0 > (8ll << 30)) __trap();          /* ~4 s: a peer is gone */
+            if (clock64() - t0 > (40ll << 30)) __trap();         /* ~20 s: a peer is gone */
             __nanosleep(40);
         }
     }
     __syncthreads();     /* the polling threads' acquire loads + this barrier order every thread's (volatile) reads of the slots after the flags */
+}
+
+// exchange point 0: all-gather of the step's query descriptors. Every rank brings the rows [row0, row0 + rows) of the batch
+// (its share of the host upload) and stores them into the same rows of every rank's query area (parity seq & 1).
+__global__ void __launch_bounds__(256) xchg_gather_queries_kernel(XchgView x, int seq, const unsigned char* __restrict__ my_rows, size_t row0_bytes, size_t bytes)
+{
+    publish_and_wait(x, 2, seq, my_rows, bytes, x.data_off[2] + (size_t)(seq & 1) * x.slot_bytes[2] + row0_bytes);
 }
 
 // exchange point 1 + global top-K by (d2, id): block = [ids i32 Q*K | d2 f32 Q*K]
@@ -69,7 +78,7 @@ __global__ void __launch_bounds__(128) xchg_merge_topk_kernel(XchgView x, int se
                                                                int32_t* __restrict__ out_ids, float* __restrict__ out_d2)
 {
     const size_t QK = (size_t)Q * K;
-    publish_and_wait(x, 0, seq, my_block, QK * 8);
+    publish_and_wait(x, 0, seq, my_block, QK * 8, x.data_off[0] + ((size_t)(seq & 1) * x.world + x.rank) * x.slot_bytes[0]);
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= Q) return;
     const unsigned char* base = x.peer[x.rank] + x.data_off[0] + (size_t)(seq & 1) * x.world * x.slot_bytes[0];
@@ -99,7 +108,7 @@ __global__ void __launch_bounds__(128) xchg_combine_kernel(XchgView x, int seq, 
                                                             int32_t* __restrict__ best_id, double* __restrict__ best_dist, int32_t* __restrict__ best_shift)
 {
     const size_t QK = (size_t)Q * K;
-    publish_and_wait(x, 1, seq, my_block, QK * 12);
+    publish_and_wait(x, 1, seq, my_block, QK * 12, x.data_off[1] + ((size_t)(seq & 1) * x.world + x.rank) * x.slot_bytes[1]);
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= Q) return;
     const unsigned char* base = x.peer[x.rank] + x.data_off[1] + (size_t)(seq & 1) * x.world * x.slot_bytes[1];
@@ -138,5 +147,15 @@ cudaError_t scl_launch_xchg_combine(const XchgView& x, int seq, int Q, int K, co
     if (Q <= 0) return cudaSuccess;
     xchg_combine_kernel<<<(Q + 127) / 128, 128, 0, stream>>>(x, seq, Q, K, static_cast<const unsigned char*>(my_block), q_ids, cand_ids,
                                                            out_dist, out_shift, best_id, best_dist, best_shift);
+    return cudaGetLastError();
+}
+
+cudaError_t scl_launch_xchg_gather_queries(const XchgView& x, int seq, const void* my_rows, size_t row0_bytes, size_t bytes, cudaStream_t stream)
+{
+    if (bytes % 16 || row0_bytes % 16) return cudaErrorInvalidValue;
+    int blocks = (int)((bytes / 16 + 255) / 256);
+    if (blocks > 32) blocks = 32;                     /* every CTA must be resident while it waits: a handful */
+    if (blocks < 1) blocks = 1;
+    xchg_gather_queries_kernel<<<blocks, 256, 0, stream>>>(x, seq, static_cast<const unsigned char*>(my_rows), row0_bytes, bytes);
     return cudaGetLastError();
 }

@@ -11,7 +11,10 @@ cudaError_t scl_launch_polar(const void* pts_dev, const int* offsets_dev, int n_
                              cudaStream_t stream);
 // K2: ring keys (+ squared key norms) of descriptors already in device memory.
 //     kn2max (device scalar, may be null) is raised to the largest squared norm seen (atomicMax on the float bits).
-cudaError_t scl_launch_ring_keys(const float* desc_dev, int n, int R, int S, float* keys, float* knorm, float* kn2max, cudaStream_t stream);
+//     cstat (may be null): per descriptor 2*S doubles, the column means (sector key, descriptor.h:1477-1489) and the column
+//     norms (descriptor.h:1521-1522) that K4 would otherwise recompute for every pair. keys may be null (cstat only).
+cudaError_t scl_launch_ring_keys(const float* desc_dev, int n, int R, int S, float* keys, float* knorm, float* kn2max, double* cstat,
+                                 cudaStream_t stream);
 
 // K3: ring-key kNN. Exact variant (CUDA cores, reference accumulation order). See k3_knn.cu.
 //  qkeys [Q][R], keys [n_db][R]; out ids/d2 [Q][K] ascending by (d2, id); id_mul/id_add map local
@@ -51,12 +54,14 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
                                bool init_state /* slots and fail_count are not known to be clean */, cudaStream_t stream);
 
 // K4: shift-aligned column-cosine distance for every (query, candidate) + winner scan. See k4_scdist.cu.
-//  q_desc [Q][R*S] or nullptr (then queries are db entries q_local[i]); cand_local [Q][K] local keys (-1 = none);
-//  cand_ids [Q][K] reported ids (for the self-skip rule against q_ids).
-cudaError_t scl_launch_scdist(const float* db_desc, const float* q_desc, const int32_t* q_local, const int32_t* q_ids,
+//  q_desc [Q][R*S] with q_stat [Q][2*S] (scl_launch_ring_keys' cstat of the queries), or both nullptr (then queries are db
+//  entries q_local[i]); db_stat [n][2*S] the per-entry cache; cand_local [Q][K] local keys (-1 = none);
+//  cand_ids [Q][K] reported ids (for the self-skip rule against q_ids). exact_all != 0: every shift in FP64 (no FP32 prefilter).
+cudaError_t scl_launch_scdist(const float* db_desc, const double* db_stat, const float* q_desc, const double* q_stat,
+                              const int32_t* q_local, const int32_t* q_ids,
                               const int32_t* cand_local, const int32_t* cand_ids, int Q, int K, int R, int S, int search_radius,
                               double* cand_dist, int32_t* cand_shift, int32_t* best_id, double* best_dist, int32_t* best_shift,
-                              int owned_per_query, cudaStream_t stream);
+                              int owned_per_query, int exact_all, cudaStream_t stream);
 
 // Shard merge (multi-GPU): world blocks of [Q][K] records -> global top-K by (d2,id) + winner scan.
 cudaError_t scl_launch_merge_shards(int world, int Q, int K, const int32_t* q_ids, const int32_t* all_ids, const float* all_d2,
@@ -95,10 +100,11 @@ cudaError_t scl_launch_pack_xyzi(const void* pts, int n, int stride_bytes, void*
 struct XchgView {
     unsigned char* peer[16];
     int world, rank;
-    size_t data_off[2], slot_bytes[2];    /* per exchange point: [2 parities][world] slots */
-    size_t flag_off;                      /* int flags[2 points][16 ranks] */
-    size_t ticket_off;                    /* int tickets[2] */
+    size_t data_off[3], slot_bytes[3];    /* points 0, 1: [2 parities][world] slots; point 2 (query gather): [2 parities] areas */
+    size_t flag_off;                      /* int flags[3 points][16 ranks] */
+    size_t ticket_off;                    /* int tickets[3] */
 };
+cudaError_t scl_launch_xchg_gather_queries(const XchgView& x, int seq, const void* my_rows, size_t row0_bytes, size_t bytes, cudaStream_t stream);
 cudaError_t scl_launch_xchg_merge_topk(const XchgView& x, int seq, int Q, int K, const void* my_block, int32_t* out_ids, float* out_d2, cudaStream_t stream);
 cudaError_t scl_launch_xchg_combine(const XchgView& x, int seq, int Q, int K, const void* my_block, const int32_t* q_ids, const int32_t* cand_ids,
                                     double* out_dist, int32_t* out_shift, int32_t* best_id, double* best_dist, int32_t* best_shift, cudaStream_t stream);

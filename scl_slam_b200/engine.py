@@ -25,10 +25,12 @@ EXPORTS = [
     "scl_reserve", "scl_set_shard", "scl_build_insert", "scl_make_scancontext", "scl_build_batch", "scl_build_batch_dev",
     "scl_insert", "scl_insert_batch", "scl_insert_batch_dev", "scl_get_index", "scl_size", "scl_get_descriptor",
     "scl_get_ring_key", "scl_query_intra", "scl_query_inter", "scl_query_batch", "scl_query_batch_dev",
-    "scl_merge_shards_dev", "scl_icp", "scl_set_profiling", "scl_stage_time", "scl_set_knn_mode", "scl_knn_stats",
+    "scl_merge_shards_dev", "scl_icp", "scl_set_profiling", "scl_stage_time", "scl_set_knn_mode", "scl_set_scdist_mode", "scl_knn_stats",
     "scl_default_ransac_params", "scl_verify_ransac", "scl_knn_batch_dev", "scl_merge_topk_dev", "scl_scdist_owned_dev", "scl_combine_owned_dev",
     "scl_query_batch_submit", "scl_query_batch_wait", "scl_voxel_grid", "scl_assemble_submap", "scl_build_insert_filtered",
     "scl_xchg_create", "scl_xchg_open", "scl_xchg_merge_topk_dev", "scl_xchg_combine_dev", "scl_xchg_close",
+    "scl_xchg_open_local", "scl_xchg_buffer", "scl_xchg_bytes", "scl_num_lanes", "scl_query_batch_dev_lane", "scl_lanes_fork", "scl_lanes_join",
+    "scl_lane_sync", "scl_shard_query_dev", "scl_shard_query_submit",
     "scl_wire_pose6_to_transform", "scl_wire_loop_between", "scl_wire_make_loop_info", "scl_wire_make_global_descriptor",
     "scl_wire_encode_global_descriptor", "scl_wire_decode_global_descriptor", "scl_wire_encode_loop_info", "scl_wire_decode_loop_info",
 ]
@@ -139,7 +141,17 @@ def load_library():
     lib.scl_voxel_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.POINTER(C.c_int)]
     lib.scl_assemble_submap.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.POINTER(C.c_int)]
     lib.scl_build_insert_filtered.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int8, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
-    lib.scl_xchg_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.scl_xchg_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.scl_xchg_open_local.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.scl_xchg_buffer.argtypes = [C.c_void_p]
+    lib.scl_xchg_buffer.restype = C.c_void_p
+    lib.scl_xchg_bytes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    lib.scl_query_batch_dev_lane.argtypes = [C.c_void_p, C.c_int, C.POINTER(SclBatchQuery), C.POINTER(SclBatchResult)]
+    lib.scl_lanes_fork.argtypes = [C.c_void_p, C.c_void_p]
+    lib.scl_lanes_join.argtypes = [C.c_void_p, C.c_void_p]
+    lib.scl_lane_sync.argtypes = [C.c_void_p, C.c_int]
+    lib.scl_shard_query_dev.argtypes = [C.c_void_p, C.c_int, C.POINTER(SclBatchQuery), C.POINTER(SclBatchResult)]
+    lib.scl_shard_query_submit.argtypes = [C.c_void_p, C.POINTER(SclBatchQuery), C.POINTER(SclBatchResult), C.POINTER(C.c_int)]
     lib.scl_xchg_open.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.scl_xchg_close.argtypes = [C.c_void_p]
     lib.scl_xchg_merge_topk_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -159,6 +171,7 @@ def load_library():
     lib.scl_verify_ransac.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(SclRansacParams),
                                       C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.scl_set_knn_mode.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.scl_set_scdist_mode.argtypes = [C.c_void_p, C.c_int]
     lib.scl_knn_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     lib.scl_set_profiling.argtypes = [C.c_void_p, C.c_int]
     lib.scl_stage_time.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
@@ -353,6 +366,10 @@ class ScanContextB200:
         """0 auto, 1 exact CUDA-core kNN, 2 tensor-core prefilter + exact re-rank (same results)."""
         self._ck(self.lib.scl_set_knn_mode(self.h, mode, int(count_fallbacks)))
 
+    def set_scdist_mode(self, mode):
+        """0 FP32 prefilter + exact evaluation of the shifts that can win, 1 every shift exactly (same results)."""
+        self._ck(self.lib.scl_set_scdist_mode(self.h, mode))
+
     def knn_stats(self):
         a, b = C.c_longlong(), C.c_longlong()
         self._ck(self.lib.scl_knn_stats(self.h, C.byref(a), C.byref(b)))
@@ -386,10 +403,48 @@ class ScanContextB200:
                                                 rank_stride_bytes, C.byref(r)))
 
     # ---- peer-memory exchange (csrc/k7_exchange.cu) ----------------------------------------
-    def xchg_create(self, world, max_qk):
+    def xchg_create(self, world, max_q, max_k):
         h = (C.c_ubyte * 64)()
-        self._ck(self.lib.scl_xchg_create(self.h, world, max_qk, h))
+        self._ck(self.lib.scl_xchg_create(self.h, world, max_q, max_k, h))
         return bytes(h)
+
+    # ---- lanes: several batches in flight on one engine (include/scl_engine.h) -------------------
+    def num_lanes(self):
+        return self.lib.scl_num_lanes()
+
+    def _result(self, out):
+        return SclBatchResult(*[_ptr(out.get(k)) for k in
+                                ("cand_ids", "cand_d2", "cand_dist", "cand_shift", "best_id", "best_dist", "best_shift")])
+
+    def query_batch_dev_lane(self, lane, q_desc_dev, q_ids_dev, Q, K, n_db, metric, out):
+        q = SclBatchQuery(_ptr(q_desc_dev), _ptr(q_ids_dev), Q, K, n_db, metric)
+        r = self._result(out)
+        self._ck(self.lib.scl_query_batch_dev_lane(self.h, lane, C.byref(q), C.byref(r)))
+
+    def lanes_fork(self, cuda_stream_handle):
+        self._ck(self.lib.scl_lanes_fork(self.h, C.c_void_p(cuda_stream_handle)))
+
+    def lanes_join(self, cuda_stream_handle):
+        self._ck(self.lib.scl_lanes_join(self.h, C.c_void_p(cuda_stream_handle)))
+
+    def lane_sync(self, lane):
+        self._ck(self.lib.scl_lane_sync(self.h, lane))
+
+    def shard_query_dev(self, lane, q_desc_dev, Q, K, n_db, metric, out):
+        """One sharded query step on lane `lane` (every rank calls it with the same arguments)."""
+        q = SclBatchQuery(_ptr(q_desc_dev), None, Q, K, n_db, metric)
+        r = self._result(out)
+        self._ck(self.lib.scl_shard_query_dev(self.h, lane, C.byref(q), C.byref(r)))
+
+    def shard_query_submit(self, q_desc_host, out, K=None, n_db=None, metric=0):
+        K = K or self.K
+        n_db = self.getSize() if n_db is None else n_db
+        q = SclBatchQuery(q_desc_host.ctypes.data, None, q_desc_host.shape[0], K, n_db, metric)
+        r = SclBatchResult(*[out[k].ctypes.data if out.get(k) is not None else None for k in
+                             ("cand_ids", "cand_d2", "cand_dist", "cand_shift", "best_id", "best_dist", "best_shift")])
+        t = C.c_int()
+        self._ck(self.lib.scl_shard_query_submit(self.h, C.byref(q), C.byref(r), C.byref(t)))
+        return t.value
 
     def xchg_open(self, world, rank, handles):
         buf = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))

@@ -240,3 +240,87 @@ def to_pcl_xyzi(points):
     p[:, 3] = 1.0
     p[:, 4] = points[:, 3] if points.shape[1] > 3 else 0.0
     return p
+
+
+# --------------------------------------------------------------------------------------------
+# the same ray caster in torch (runs on the GPU box): batches of scans for the C1 / C4 / C5 benches
+# --------------------------------------------------------------------------------------------
+def scan_batch_torch(world, poses, dirs, seed=0, device="cuda", sensor_height=1.65, max_range=100.0, sigma=0.02, dropout=0.05,
+                     box_radius=120.0, pcl_layout=True, rays_per_chunk=1 << 15):
+    """Ray-casts len(poses) scans of the box world on `device`. Same geometry as scan() (ground plane + axis-aligned
+    boxes, range noise, dropout), noise from the integer hash (so CPU and CUDA give the same clouds for a seed).
+    Returns (points, offsets): points [sum P_i, 8] float32 in the pcl::PointXYZI layout (or [.., 4] x, y, z, intensity
+    with pcl_layout=False) in the SENSOR frame, offsets int32 [n + 1]."""
+    dev = torch.device(device)
+    lo = torch.as_tensor(world[0], device=dev)
+    hi = torch.as_tensor(world[1], device=dev)
+    d = torch.as_tensor(dirs, device=dev, dtype=torch.float32)
+    poses = np.asarray(poses, np.float64).reshape(-1, 3)
+    clouds, counts = [], []
+    P = d.shape[0]
+    for si, (x, y, yaw) in enumerate(poses):
+        cy, sy = math.cos(yaw), math.sin(yaw)
+        dw = torch.stack([cy * d[:, 0] - sy * d[:, 1], sy * d[:, 0] + cy * d[:, 1], d[:, 2]], dim=1)
+        o = torch.tensor([x, y, sensor_height], device=dev, dtype=torch.float32)
+        t = torch.full((P,), float("inf"), device=dev)
+        down = dw[:, 2] < -1e-6
+        t = torch.where(down, -sensor_height / dw[:, 2].clamp(max=-1e-6), t)
+        cx, cyb = (lo[:, 0] + hi[:, 0]) / 2, (lo[:, 1] + hi[:, 1]) / 2
+        near = ((cx - x).abs() < box_radius) & ((cyb - y).abs() < box_radius)
+        inside = (lo[:, 0] < x) & (x < hi[:, 0]) & (lo[:, 1] < y) & (y < hi[:, 1]) & (hi[:, 2] > sensor_height)
+        near &= ~inside
+        blo, bhi = lo[near], hi[near]
+        if blo.shape[0]:
+            inv = 1.0 / dw
+            for c0 in range(0, P, rays_per_chunk):
+                sl = slice(c0, min(P, c0 + rays_per_chunk))
+                t1 = (blo[None] - o[None, None]) * inv[sl, None]
+                t2 = (bhi[None] - o[None, None]) * inv[sl, None]
+                tmin = torch.nan_to_num(torch.minimum(t1, t2), nan=-float("inf")).amax(dim=2)
+                tmax = torch.nan_to_num(torch.maximum(t1, t2), nan=float("inf")).amin(dim=2)
+                hit = tmax >= tmin.clamp(min=0.0)
+                th = torch.where(hit, tmin.clamp(min=0.0), torch.full_like(tmin, float("inf"))).amin(dim=1)
+                t[sl] = torch.minimum(t[sl], th)
+        idx = torch.arange(P, device=dev, dtype=torch.int64) + (seed * 1000003 + si) * 0x10001
+        u1 = _uniform(idx, 41).clamp_min(1e-7)
+        u2 = _uniform(idx, 42)
+        t = t + sigma * torch.sqrt(-2.0 * torch.log(u1)) * torch.cos(2 * math.pi * u2)
+        keep = torch.isfinite(t) & (t < max_range) & (t > 0.5) & (_uniform(idx, 43) >= dropout)
+        p = d[keep] * t[keep, None]
+        inten = 255.0 * _uniform(idx[keep], 44)
+        if pcl_layout:
+            c = torch.zeros((p.shape[0], 8), device=dev, dtype=torch.float32)
+            c[:, 0:3] = p
+            c[:, 3] = 1.0
+            c[:, 4] = inten
+        else:
+            c = torch.cat([p, inten[:, None]], dim=1)
+        clouds.append(c)
+        counts.append(c.shape[0])
+    offsets = np.zeros(len(counts) + 1, np.int32)
+    offsets[1:] = np.cumsum(counts)
+    pts = torch.cat(clouds) if clouds else torch.zeros((0, 8 if pcl_layout else 4), device=dev)
+    return pts.contiguous(), offsets
+
+
+def desc_db_trajectory(n, num_ring=20, num_sector=60, seed=5, device="cpu", start=0, run=16):
+    """A database ordered like a trajectory (the robustness arm of the bench): every `run` consecutive entries are one place
+    seen from slightly different poses — the entry of desc_db at index i // run with fresh N(0, 0.1^2) noise on its
+    non-empty bins, 1 % bin dropout and a yaw drift of up to one sector — so neighbouring keys are near-duplicates
+    (what D1 / D2 look like to the ring-key search)."""
+    R, S = num_ring, num_sector
+    dev = torch.device(device)
+    g0, g1 = start // run, (start + n + run - 1) // run
+    places = desc_db(g1 - g0, R, S, seed=seed, device=dev, start=g0)
+    i = torch.arange(start, start + n, device=dev, dtype=torch.int64)
+    base = places[(i // run - g0)]
+    drift = ((_uniform(i, 51) * 3).to(torch.int64) - 1).view(-1, 1)                    # -1, 0, +1 sectors
+    cols = (torch.arange(S, device=dev).view(1, S) - drift) % S
+    rot = torch.gather(base, 2, cols.view(n, 1, S).expand(n, R, S))
+    bins = torch.arange(R * S, device=dev, dtype=torch.int64).view(1, R * S)
+    u1 = _uniform(i.view(-1, 1) * (R * S) + bins, 52).clamp_min_(1e-7)
+    u2 = _uniform(i.view(-1, 1) * (R * S) + bins, 53)
+    g = torch.sqrt(-2.0 * torch.log(u1)) * torch.cos(2 * math.pi * u2)
+    out = torch.where(rot != 0, rot + 0.1 * g.view(n, R, S), rot)
+    drop = _uniform(i.view(-1, 1) * (R * S) + bins, 54).view(n, R, S) < 0.01
+    return torch.where(drop, torch.zeros_like(out), out).contiguous()

@@ -595,3 +595,175 @@ def test_tensor_core_knn_sub_batches_equal_exact_kernel(eng_mod):
         assert np.array_equal(_bits(got["cand_dist"]), _bits(exp["cand_dist"]))
     st = e.knn_stats()
     assert st["tc_queries"] == 3 * nq and st["fallback_queries"] == 0, st
+
+
+# ---------------------------------------------------------------- K4: FP32 prefilter == every shift in FP64 == oracle
+def _adversarial_descriptors(R, S, seed):
+    """Descriptors built to produce exact and near ties among shifts, zero columns, and magnitudes at the
+    edge of / outside the range where K4's FP32 estimates are trusted."""
+    rng = np.random.default_rng(seed)
+    base = synth.desc_db(6, R, S, seed=seed).numpy()
+    out = [base[0], base[1]]
+    out.append(np.roll(base[0], 7, axis=1))                              # a pure rotation of entry 0
+    per = base[2].copy(); per[:, S // 2:] = per[:, :S // 2]; out.append(per)     # period S/2: two shifts tie exactly
+    per3 = base[3].copy(); w = S // 3
+    per3[:, w:2 * w] = per3[:, :w]; per3[:, 2 * w:3 * w] = per3[:, :w]; out.append(per3)   # period S/3
+    out.append(np.full((R, S), 3.25, np.float32))                       # constant: every shift ties
+    z = base[4].copy(); z[:, ::2] = 0; out.append(z)                     # every other column empty
+    z2 = base[5].copy(); z2[:, 5:] = 0; out.append(z2)                   # five columns only
+    out.append(np.zeros((R, S), np.float32))                             # empty
+    out.append(base[0] * np.float32(1e-22)); out.append(base[1] * np.float32(1e21))   # outside the FP32-safe range
+    out.append(base[0] * np.float32(1e-9)); out.append(base[1] * np.float32(1e9))     # inside it
+    n1 = base[0].copy(); n1[3, 4] = np.nan; out.append(n1)
+    n2 = base[1].copy(); n2[0, 0] = np.inf; out.append(n2)
+    near = base[0] + (rng.standard_normal((R, S)) * 1e-6).astype(np.float32) * (base[0] != 0); out.append(near.astype(np.float32))
+    sym = base[2].copy(); sym = np.concatenate([sym[:, :S // 2], sym[:, :S // 2][:, ::-1]], axis=1); out.append(sym)   # mirror symmetric
+    out.append(-base[3])                                                 # negative heights are kept by the reference
+    return np.stack(out).astype(np.float32)
+
+
+@pytest.mark.parametrize("R,S,ratio", [(20, 60, 0.1), (20, 60, 1.0), (40, 120, 0.1), (10, 34, 0.3)])
+def test_scdist_prefilter_equals_exact_and_oracle(eng_mod, R, S, ratio):
+    db = _adversarial_descriptors(R, S, seed=71)
+    n = db.shape[0]
+    K = n                                       # every entry is a candidate of every query: K4 sees all pairs
+    assert K <= 32
+    rot = np.stack([np.roll(db[i], (3 * i + 1) % S, axis=1) for i in range(n)])
+    q = np.concatenate([db, rot]).astype(np.float32)
+    o = Oracle(num_ring=R, num_sector=S, num_candidates=K, search_ratio=ratio)
+    o.bulk_load(np.concatenate([db.reshape(n, -1), q.reshape(q.shape[0], -1)]))
+    exp = o.query_batch(np.arange(n, n + q.shape[0]), n, K, 0)
+    res = []
+    for mode in (0, 1):
+        e = eng_mod.ScanContextB200(numRing=R, numSector=S, numCandidates=K, searchRatio=ratio)
+        e.set_scdist_mode(mode)
+        e.insert_batch(db)
+        res.append(e.query_batch(q_desc=q, K=K, n_db=n, metric=0))
+        # queries that are database entries take their statistics from the per-entry cache
+        got2 = e.query_batch(q_ids=np.arange(n, dtype=np.int32), K=K, n_db=n, metric=0)
+        exp2 = o.query_batch(np.arange(n), n, K, 0)
+        same_cand = np.array_equal(got2["cand_ids"], exp2["cand_ids"])
+        if same_cand:
+            assert np.array_equal(_bits(got2["cand_dist"]), _bits(exp2["cand_dist"])), mode
+            assert np.array_equal(got2["cand_shift"], exp2["cand_shift"]), mode
+    for k in ("cand_ids", "cand_shift", "best_id", "best_shift"):
+        assert np.array_equal(res[0][k], res[1][k]), k
+    assert np.array_equal(_bits(res[0]["cand_dist"]), _bits(res[1]["cand_dist"]))
+    # against the oracle wherever the candidate order agrees (NaN / inf ring keys make the kNN order itself undefined)
+    ok = (res[0]["cand_ids"] == exp["cand_ids"]).all(axis=1)
+    assert ok.sum() >= q.shape[0] - 8
+    assert np.array_equal(_bits(res[0]["cand_dist"][ok]), _bits(exp["cand_dist"][ok]))
+    assert np.array_equal(res[0]["cand_shift"][ok], exp["cand_shift"][ok])
+    assert np.array_equal(res[0]["best_id"][ok], exp["best_id"][ok])
+
+
+def test_scdist_modes_agree_on_random_batches(eng_mod):
+    """Larger seeded batches through both K4 variants: identical distances, shifts and winners."""
+    db = synth.desc_db(5000, seed=81)
+    q, _, _ = synth.desc_queries(db, 700, seed=82, noise_sigma=0.3, dropout=0.1)
+    out = []
+    for mode in (0, 1):
+        e = eng_mod.ScanContextB200(numCandidates=10)
+        e.set_scdist_mode(mode)
+        e.insert_batch(db.numpy())
+        out.append(e.query_batch(q_desc=q.numpy(), K=10, n_db=5000))
+    for k in ("cand_ids", "cand_shift", "best_id", "best_shift"):
+        assert np.array_equal(out[0][k], out[1][k]), k
+    assert np.array_equal(_bits(out[0]["cand_dist"]), _bits(out[1]["cand_dist"]))
+
+
+def _k4_pairs(e, q, cand):
+    """K4 alone on explicit (query descriptor, candidate key) lists: scl_scdist_owned_dev on an unsharded engine."""
+    dev = torch.device("cuda", 0)
+    nq, K = cand.shape
+    qd = torch.from_numpy(np.ascontiguousarray(q, np.float32)).to(dev)
+    ci = torch.from_numpy(np.ascontiguousarray(cand, np.int32)).to(dev)
+    dist = torch.empty((nq, K), dtype=torch.float64, device=dev)
+    shift = torch.empty((nq, K), dtype=torch.int32, device=dev)
+    e.scdist_owned_dev(qd, nq, K, ci, dist, shift)
+    torch.cuda.synchronize()
+    return dist.cpu().numpy(), shift.cpu().numpy()
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_golden_pairs_on_gpu(eng_mod, golden, tag):
+    """distanceBtnScanContext and fastAlignUsingVkey of the reference's own class text (tests/golden, generated from
+    oracle/_ref) replayed through K4: distance, shift, and (with a window of one shift) the alignment."""
+    R, S, K, excl = [int(v) for v in golden[tag + "_params"]]
+    db = golden[tag + "_db"]
+    pairs = golden[tag + "_pairs"]
+    for mode in (0, 1):
+        e = eng_mod.ScanContextB200(numRing=R, numSector=S)
+        e.set_scdist_mode(mode)
+        e.insert_batch(db)
+        dist, shift = _k4_pairs(e, db[pairs[:, 0]], pairs[:, 1:2])
+        assert np.array_equal(_bits(dist[:, 0]), _bits(golden[tag + "_pair_dist"])), mode
+        assert np.array_equal(shift[:, 0], golden[tag + "_pair_shift"]), mode
+        e0 = eng_mod.ScanContextB200(numRing=R, numSector=S, searchRatio=0.0)      # window = the alignment alone
+        e0.set_scdist_mode(mode)
+        e0.insert_batch(db)
+        d0, s0 = _k4_pairs(e0, db[pairs[:, 0]], pairs[:, 1:2])
+        ok = d0[:, 0] < 1e7                                                       # no column counts: the reference keeps shift 0
+        assert np.array_equal(s0[ok, 0], golden[tag + "_pair_align"][ok]), mode
+
+
+@pytest.mark.parametrize("R,S,ratio", [(20, 60, 0.1), (20, 60, 1.0), (40, 120, 0.1), (10, 34, 0.3), (20, 60, 0.0)])
+def test_scdist_all_pairs_adversarial(eng_mod, R, S, ratio):
+    """Every (query, entry) pair of the adversarial set straight through K4 (the kNN stage never proposes entries
+    with NaN / inf / 1e21 keys): both K4 variants against the oracle's distanceBtnScanContext, bit for bit."""
+    db = _adversarial_descriptors(R, S, seed=72)
+    n = db.shape[0]
+    rot = np.stack([np.roll(db[i], (5 * i + 2) % S, axis=1) for i in range(n)])
+    q = np.concatenate([db, rot]).astype(np.float32)
+    cand = np.tile(np.arange(n, dtype=np.int32), (q.shape[0], 1))
+    o = Oracle(num_ring=R, num_sector=S, search_ratio=ratio)
+    exp_d = np.empty((q.shape[0], n)); exp_s = np.empty((q.shape[0], n), np.int32)
+    for i in range(q.shape[0]):
+        for j in range(n):
+            exp_d[i, j], exp_s[i, j] = o.distance_raw(q[i], db[j])
+    for mode in (0, 1):
+        e = eng_mod.ScanContextB200(numRing=R, numSector=S, searchRatio=ratio)
+        e.set_scdist_mode(mode)
+        e.insert_batch(db)
+        dist, shift = _k4_pairs(e, q, cand)
+        bad = _bits(dist) != _bits(exp_d)
+        assert not bad.any(), (mode, np.argwhere(bad)[:5], dist[bad][:5], exp_d[bad][:5])
+        assert np.array_equal(shift, exp_s), (mode, np.argwhere(shift != exp_s)[:5])
+
+
+def test_lanes_concurrent_batches_equal_sequential(eng_mod):
+    """Four different batches in flight on the four query lanes of one engine (scl_query_batch_dev_lane between
+    scl_lanes_fork / scl_lanes_join) give exactly what the same batches give one after the other; inserts made in
+    between are visible to every lane."""
+    dev = torch.device("cuda", 0)
+    n, nq, K = 50000, 300, 10
+    db = synth.desc_db(n + 5000, seed=91, device=dev)
+    e = eng_mod.ScanContextB200(numCandidates=K)
+    e.set_stream(torch.cuda.current_stream().cuda_stream)
+    e.insert_batch_dev(db[:n].contiguous())
+    L = e.num_lanes()
+    assert L >= 2
+    qs = [synth.desc_queries(db[:n], nq, seed=92 + i)[0].contiguous() for i in range(L)]
+
+    def bufs():
+        return dict(cand_ids=torch.empty((nq, K), dtype=torch.int32, device=dev), cand_d2=torch.empty((nq, K), dtype=torch.float32, device=dev),
+                    cand_dist=torch.empty((nq, K), dtype=torch.float64, device=dev), cand_shift=torch.empty((nq, K), dtype=torch.int32, device=dev),
+                    best_id=torch.empty(nq, dtype=torch.int32, device=dev), best_dist=torch.empty(nq, dtype=torch.float64, device=dev),
+                    best_shift=torch.empty(nq, dtype=torch.int32, device=dev))
+    for n_db in (n, n + 5000):
+        seq = [bufs() for _ in range(L)]
+        for i in range(L):
+            e.query_batch_dev(qs[i], None, nq, K, n_db, 0, seq[i])
+        torch.cuda.synchronize()
+        par = [bufs() for _ in range(L)]
+        for rep in range(3):
+            e.lanes_fork(torch.cuda.current_stream().cuda_stream)
+            for i in range(L):
+                e.query_batch_dev_lane(i, qs[i], None, nq, K, n_db, 0, par[i])
+            e.lanes_join(torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        for i in range(L):
+            for k in seq[i]:
+                assert torch.equal(seq[i][k].view(torch.uint8), par[i][k].view(torch.uint8)), (n_db, i, k)
+        e.insert_batch_dev(db[n:].contiguous())          # grows the database between the two rounds
+    assert e.knn_stats()["tc_queries"] > 0
