@@ -7,9 +7,9 @@ Workload (BASELINE.json configs[2], the one the metric is quoted on; it fits one
   with the ring-key top-10 + the shift-aligned SC distance of every candidate and the winning
   (id, shift).
 
-  value : whole-job queries/s with the queries already in HBM. The engine keeps four query lanes
-          (stream + scratch each, include/scl_engine.h), so the K timed steps run as K / D groups of D
-          batches in flight (--in-flight D, default 4): CUDA events around every group on the launching
+  value : whole-job queries/s with the queries already in HBM. The engine keeps eight query lanes
+          (stream + scratch each, include/scl_engine.h), so the K timed steps run as groups of D
+          batches in flight (--in-flight D, default 8): CUDA events around every group on the launching
           stream, a 512 MB buffer rewritten between groups (L2 flush, outside the event pairs), max over
           ranks. The same steps are also run one at a time (`latency`), which is where the per-stage
           times and the roofline of the dominant kernel come from (a kernel timed alone).
@@ -174,13 +174,15 @@ class Timed:
             self.step(i % self.depth, first + i)
         self.e.lanes_join(self.stream)
 
-    def run(self, steps, warmup):
-        """-> (latency ms/step, throughput ms/step). Both are sums of CUDA-event pairs on the launching stream; the L2 flush
-        sits between the pairs."""
+    def run(self, steps, warmup, after_warmup=None):
+        """One step at a time -> latency in ms/step: the sum of CUDA-event pairs on the launching stream; the L2 flush sits
+        between the pairs."""
         for w in range(max(warmup, 3)):
             self.group(w * self.depth, self.depth)
             self.flush.zero_()
         self.barrier()
+        if after_warmup:
+            after_warmup()
         lat = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         for i, (a, b) in enumerate(lat):
             if self.align:
@@ -239,9 +241,11 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
     e.set_stream(stream.cuda_stream)
     e.set_shard(rank, world)
+    if args.tc_stages:
+        e.set_tc_stages(args.tc_stages)
     n_local = fill(e, dev, rank, world, n_db)
     D = max(1, min(args.in_flight, e.num_lanes()))
-    steps = max(D, args.steps - args.steps % D)            # whole groups
+    steps = args.steps                                     # the last group is smaller when D does not divide K
     # D different query batches (seeds 4, 5, ...), one per lane; every one made of perturbed + rotated database entries
     head = synth.desc_db(1 << 16, R, S, seed=3, device=dev)
     batches = [synth.desc_queries(head, Q, seed=4 + i) for i in range(D)]
@@ -275,10 +279,8 @@ def run_ours(args):
 
     timed = Timed(e, dev, step, D, barrier=barrier, align=align)
     launches_per_step = 5 + (2 if world > 1 else 0)       # ring_key(+stats), knn_tc, knn_rerank, knn_exact (fallback list), scdist (+ the two exchange kernels)
-    e.set_profiling(True)
-    e.stage_time(0); e.stage_time(1); e.stage_time(2)
     t_region0 = time.time()
-    lat_ms = timed.run(steps, args.warmup)
+    lat_ms = timed.run(steps, args.warmup, after_warmup=lambda: e.set_profiling(True))
     stage = {name: e.stage_time(i) for i, name in ((0, "k2_query_keys"), (1, "k3_knn"), (2, "k4_scdist"))}
     e.set_profiling(False)
     barrier()
@@ -488,9 +490,7 @@ def query_arm(engine, synth, dev, pk, n_db, gen, seed, depth, r=R, s=S, no_match
     def step(lane, i):
         e.query_batch_dev_lane(lane, qs[i % depth], None, Q, K, n_db, 0, outs[i % depth])
     timed = Timed(e, dev, step, depth, flush_mb=256)
-    e.set_profiling(True)
-    e.stage_time(0); e.stage_time(1); e.stage_time(2)
-    lat = timed.run(steps, 3)
+    lat = timed.run(steps, 3, after_warmup=lambda: e.set_profiling(True))
     stage = {name: (lambda v: v[0] / max(v[1], 1))(e.stage_time(i)) for i, name in ((0, "k2_query_keys"), (1, "k3_knn"), (2, "k4_scdist"))}
     e.set_profiling(False)
     thr = timed.run_groups(steps)
@@ -915,7 +915,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-db", type=int, default=N_DB, help="database size (default: the 1M workload)")
-    ap.add_argument("--in-flight", type=int, default=4, help="batches in flight (query lanes used), 1..4")
+    ap.add_argument("--in-flight", type=int, default=8, help="batches in flight (query lanes used), 1..8")
+    ap.add_argument("--tc-stages", type=int, default=0, help="key tiles the tensor-core kNN kernel keeps in flight (2..5; 0 = the engine's default)")
     ap.add_argument("--cpu-sample", type=int, default=256, help="queries per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the secondary arms (C1, C2, C4, C5, robustness)")

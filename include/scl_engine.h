@@ -138,9 +138,9 @@ int scl_query_batch(scl_engine* e, const scl_batch_query* q, scl_batch_result* r
 int scl_query_batch_dev(scl_engine* e, const scl_batch_query* q, scl_batch_result* r);
 /* Pipelined host-buffer form, for a caller that streams batches (loopClosureThread draining a backlog,
  * distributedMapping.h:1450-1473): submit returns as soon as the batch is enqueued, so the next batch can be
-* submitted at once and its host-to-device copy (a second stream, one staging buffer per batch in flight) overlaps
+* submitted at once and its host-to-device copy (every batch runs on its own query lane: stream + staging + scratch) overlaps
  * the kernels of this one. scl_query_batch_wait(ticket) blocks until that batch's results are in the host arrays of r.
- * At most four batches may be in flight (tickets are consecutive; wait for them in order); q_desc and the result arrays should be page-locked host memory (pageable
+ * At most scl_num_lanes() batches may be in flight (tickets are consecutive; wait for them in order); q_desc and the result arrays should be page-locked host memory (pageable
  * memory works but serialises the copies) and must stay valid until the wait returns. */
 int scl_query_batch_submit(scl_engine* e, const scl_batch_query* q, scl_batch_result* r, int* ticket);
 int scl_query_batch_wait(scl_engine* e, int ticket);
@@ -226,6 +226,10 @@ int scl_set_knn_mode(scl_engine* e, int mode, int count_fallbacks);
  * mode 1: every shift in FP64. Both give bit-identical distances and shifts; mode 1 exists for the tests. */
 int scl_set_scdist_mode(scl_engine* e, int mode);
 int scl_knn_stats(scl_engine* e, long long* tc_queries, long long* fallback_queries);
+/* Shared memory of the tensor-core kNN kernel: `stages` key tiles (32 KB each at 20 rings) are in flight per SM, 2..5
+ * (default 5). Fewer stages leave shared memory to the kernels of other query lanes (re-rank, SC distance), which then run
+ * on the same SMs at the same time; results do not depend on it. */
+int scl_set_tc_stages(scl_engine* e, int stages);
 
 /* ---- per-stage device timing (for roofline reports) ----------------------------------------
  * With profiling on, every batched query records CUDA events on the engine's stream around each

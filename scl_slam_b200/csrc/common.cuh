@@ -6,6 +6,26 @@
 
 #define SCL_NUM_SMS 148 /* B200: 2 dies x 74 SMs; grids are sized in multiples of this */
 
+// Kernels of different query lanes run on the same SM at the same time only if the SM's L1 / shared-memory split suits all of
+// them: every kernel of the query path asks for the largest shared-memory carveout once per device, so a small-footprint kernel
+// never forces the SM to drain and re-partition between lanes.
+#include <atomic>
+struct SclOncePerDevice {
+    std::atomic<unsigned long long> seen{0};
+    bool first()
+    {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess) return false;
+        const unsigned long long bit = 1ull << (d & 63);
+        return !(seen.fetch_or(bit) & bit);
+    }
+};
+#define SCL_PREFER_SMEM(kernel)                                                                                              \
+    do {                                                                                                                     \
+        static SclOncePerDevice _once;                                                                                       \
+        if (_once.first()) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+    } while (0)
+
 // ---- order-preserving float <-> uint key (for atomicMax on bins) ---------------------------
 // key(a) < key(b)  <=>  a < b for all non-NaN floats (with -0.0 < +0.0).
 __device__ __forceinline__ uint32_t scl_float_key(float f)

@@ -260,7 +260,7 @@ int knn_dev(scl_engine* e, Lane& ln, const float* q_desc, const int32_t* q_ids, 
             }
             KnnTcWorkspace tw{ln.tc_queues.as<uint32_t>(), ln.tc_queue_cnt.as<int>(), ln.tc_slots.as<int>(), probe, pairs};
             CK(scl_launch_knn_tc(ln.qkeys.as<float>(), Q, e->d_keys, e->d_kimg, e->d_kn2max, n_db, R, K, metric, e->world, e->rank, tw,
-                                 cand_ids, cand_d2, ln.tc_fail_list.as<int32_t>(), fail_cur, fail_next, init_state, ln.stream));
+                                 cand_ids, cand_d2, ln.tc_fail_list.as<int32_t>(), fail_cur, fail_next, init_state, e->tc_stages, ln.stream));
             ln.tc_state_clean = true; ln.tc_slots_rows = Qc;
             /* uncertified queries (normally none) are redone exactly; CTAs beyond the list length exit at once */
             CK(scl_launch_knn_exact(ln.qkeys.as<float>(), Q, e->d_keys, n_db, R, K, metric, e->world, e->rank,
@@ -292,8 +292,8 @@ int scdist_dev(scl_engine* e, Lane& ln, const float* q_desc, const int32_t* q_lo
     { int rc = lane_begin(e, ln); if (rc) return rc; }
     const size_t QK = (size_t)Q * K;
     /* reported id -> row of this engine's descriptor array; on an unsharded engine the two are the same (missing = -1) */
-    const int32_t* cand_local = cand_ids;
-    if (e->world != 1 || missing_to_zero) {
+    const int32_t* cand_local = e->world != 1 ? nullptr : cand_ids;     /* a shard derives the local keys inside K4 */
+    if (missing_to_zero) {
         CK(ln.cand_local.ensure(QK * 4));
         CK(scl_launch_ids_to_local(cand_ids, (int)QK, e->world, e->rank, missing_to_zero ? 0 : -1, missing_to_zero ? cand_ids : nullptr,
                                    ln.cand_local.as<int32_t>(), ln.stream));
@@ -310,7 +310,7 @@ int scdist_dev(scl_engine* e, Lane& ln, const float* q_desc, const int32_t* q_lo
         q_stat = ln.qstat.as<double>();
     }
     StageTimer st(e, 2, ln.stream);
-    CK(scl_launch_scdist(e->d_desc, e->d_cstat, q_desc, q_stat, q_local, q_ids, cand_local, cand_ids, Q, K, R, S, e->search_radius,
+    CK(scl_launch_scdist(e->d_desc, e->d_cstat, q_desc, q_stat, q_local, q_ids, cand_local, cand_ids, e->world, e->rank, Q, K, R, S, e->search_radius,
                          cand_dist, cand_shift, best_id, best_dist, best_shift, ln.scdist_owned_hint, e->scdist_exact_all ? 1 : 0, ln.stream));
     return SCL_OK;
 }
@@ -484,6 +484,14 @@ int scl_set_knn_mode(scl_engine* e, int mode, int count_fallbacks)
     if (mode < 0 || mode > 2) FAIL(SCL_ERR_INVALID, "mode must be 0 (auto), 1 (exact) or 2 (tensor core)");
     if (mode == 2 && !scl_knn_tc_supported(e->p.num_ring)) FAIL(SCL_ERR_UNSUPPORTED, "tensor-core kNN is built for 20 and 40 rings");
     e->knn_mode = mode; e->count_fallbacks = count_fallbacks != 0;
+    return SCL_OK;
+}
+
+int scl_set_tc_stages(scl_engine* e, int stages)
+{
+    LOCK();
+    if (stages < 2 || stages > 5) FAIL(SCL_ERR_INVALID, "2..5 key tiles in flight");
+    e->tc_stages = stages;
     return SCL_OK;
 }
 

@@ -43,6 +43,7 @@ struct scl_engine {
     unsigned char* d_kimg = nullptr;       /* tensor-core key image: 128-key tiles in the tcgen05 operand layout (k3_knn_tc.cu) */
     int img_n = 0, img_cap = 0;            /* keys [0, img_n) have an image; capacity in keys */
     int knn_mode = 0;                      /* 0 auto, 1 exact CUDA-core kernel, 2 tensor-core prefilter */
+    int tc_stages = 5;                     /* key tiles knn_tc_kernel keeps in flight in shared memory (scl_set_tc_stages) */
     long long stat_tc_queries = 0, stat_fallback_queries = 0;
     bool count_fallbacks = false;
     std::vector<std::pair<int8_t, int>> index;
@@ -54,7 +55,7 @@ struct scl_engine {
     /* Query lanes: a lane is a CUDA stream plus every scratch buffer one query batch needs, so batches on different lanes
      * run concurrently (the kernels of one batch leave SMs idle: start-up, re-rank, exchange waits). Lane 0 runs on the engine
      * stream and serves the synchronous calls; scl_query_batch_submit and the *_lane calls rotate over all of them. */
-    static constexpr int kLanes = 4;
+    static constexpr int kLanes = 8;
     struct Lane {
         cudaStream_t stream = nullptr;
         DevBuf knn_tickets;

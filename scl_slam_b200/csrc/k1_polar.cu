@@ -465,8 +465,8 @@ cudaError_t scl_launch_ring_keys(const float* desc_dev, int n, int R, int S, flo
 {
     if (n <= 0) return cudaSuccess;
     if ((reinterpret_cast<uintptr_t>(desc_dev) & 15) == 0) {
-        if (R == 20 && S == 60) { ring_key_fixed_kernel<20, 60, 4><<<(n + 3) / 4, 128, 0, stream>>>(desc_dev, n, keys, knorm, kn2max, cstat); return cudaGetLastError(); }
-        if (R == 40 && S == 120) { ring_key_fixed_kernel<40, 120, 2><<<(n + 1) / 2, 64, 0, stream>>>(desc_dev, n, keys, knorm, kn2max, cstat); return cudaGetLastError(); }
+        if (R == 20 && S == 60) { SCL_PREFER_SMEM((ring_key_fixed_kernel<20, 60, 4>)); ring_key_fixed_kernel<20, 60, 4><<<(n + 3) / 4, 128, 0, stream>>>(desc_dev, n, keys, knorm, kn2max, cstat); return cudaGetLastError(); }
+        if (R == 40 && S == 120) { SCL_PREFER_SMEM((ring_key_fixed_kernel<40, 120, 2>)); ring_key_fixed_kernel<40, 120, 2><<<(n + 1) / 2, 64, 0, stream>>>(desc_dev, n, keys, knorm, kn2max, cstat); return cudaGetLastError(); }
     }
     int warps = 8;
     while (warps > 1 && (size_t)warps * (R * (S | 1) + R) * sizeof(float) > 200 * 1024) warps >>= 1;

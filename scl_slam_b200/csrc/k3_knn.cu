@@ -263,10 +263,10 @@ cudaError_t launch_exact_small(const float* qkeys, int Q, const float* keys, int
     const int kpt = split_len / kSmallThreads;
     if (kpt > 32 || (size_t)Q * splits * K > ws.capacity) return cudaSuccess;        /* the general kernel takes it */
     dim3 grid(splits, Q);
-#define SCL_SMALL(M, P) knn_exact_small_kernel<R, M, P><<<grid, kSmallThreads, 0, stream>>>(qkeys, keys, n_db, K, split_len, id_mul, id_add, ws.part_ids, \
+#define SCL_SMALL(M, P) SCL_PREFER_SMEM((knn_exact_small_kernel<R, M, P>)); knn_exact_small_kernel<R, M, P><<<grid, kSmallThreads, 0, stream>>>(qkeys, keys, n_db, K, split_len, id_mul, id_add, ws.part_ids, \
                                                                                           ws.part_d2, ws.tickets, out_ids, out_d2)
-    if (kpt <= 16) { if (metric == 0) SCL_SMALL(0, 16); else SCL_SMALL(1, 16); }
-    else { if (metric == 0) SCL_SMALL(0, 32); else SCL_SMALL(1, 32); }
+    if (kpt <= 16) { if (metric == 0) { SCL_SMALL(0, 16); } else { SCL_SMALL(1, 16); } }
+    else { if (metric == 0) { SCL_SMALL(0, 32); } else { SCL_SMALL(1, 32); } }
 #undef SCL_SMALL
     *done = true;
     return cudaGetLastError();
@@ -298,12 +298,15 @@ cudaError_t launch_exact(const float* qkeys, int Q, const float* keys, int n_db,
 {
     const size_t smem = (size_t)kTK * R * 4 + (size_t)K * kTQ * 8;
     dim3 grid(splits, (Q + kTQ - 1) / kTQ);
-    if (metric == 0)
+    if (metric == 0) {
+        SCL_PREFER_SMEM((knn_exact_kernel<R, 0>));
         knn_exact_kernel<R, 0><<<grid, kTQ, smem, stream>>>(qkeys, Q, keys, n_db, K, split_len, id_mul, id_add, qlist, qcount, ws.part_ids, ws.part_d2,
                                                             ws.tickets, out_ids, out_d2);
-    else
+    } else {
+        SCL_PREFER_SMEM((knn_exact_kernel<R, 1>));
         knn_exact_kernel<R, 1><<<grid, kTQ, smem, stream>>>(qkeys, Q, keys, n_db, K, split_len, id_mul, id_add, qlist, qcount, ws.part_ids, ws.part_d2,
                                                             ws.tickets, out_ids, out_d2);
+    }
     return cudaGetLastError();
 }
 
@@ -352,6 +355,7 @@ cudaError_t scl_launch_gather_rows(const float* src, const int32_t* rows, int n,
     const size_t total = (size_t)n * width;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 16 * SCL_NUM_SMS) blocks = 16 * SCL_NUM_SMS;
+    SCL_PREFER_SMEM(gather_rows_kernel);
     gather_rows_kernel<<<blocks, 256, 0, stream>>>(src, rows, n, width, dst);
     return cudaGetLastError();
 }
@@ -360,6 +364,7 @@ cudaError_t scl_launch_ids_to_local(const int32_t* ids, int n, int id_mul, int i
                                     int32_t* local, cudaStream_t stream)
 {
     if (n <= 0) return cudaSuccess;
+    SCL_PREFER_SMEM(ids_to_local_kernel);
     ids_to_local_kernel<<<(n + 255) / 256, 256, 0, stream>>>(ids, n, id_mul, id_add, missing_to, ids_rewrite, local);
     return cudaGetLastError();
 }

@@ -157,12 +157,13 @@ template <int R> struct TcCfg {
     static constexpr uint32_t LBO_B = kNT * 16;
     static constexpr uint32_t TILE_A = 128 * KTOT * 2;        /* one query tile: 16 KB / 32 KB */
     static constexpr uint32_t TILE_B = kNT * KTOT * 2;        /* one key tile: 32 KB / 64 KB */
-    static constexpr int NSTAGE = R <= 20 ? 5 : 2;            /* key tiles in flight in shared memory */
+    static constexpr int NSTAGE = R <= 20 ? 5 : 2;            /* most key tiles in flight in shared memory (the launch may ask for fewer) */
     static constexpr uint32_t OFF_BAR = 0;                    /* mbarriers, tmem slot, flags */
     static constexpr uint32_t OFF_THR = 1024;                 /* [256] union bounds */
     static constexpr uint32_t OFF_A = 2048;                   /* two query tiles */
     static constexpr uint32_t OFF_B = OFF_A + 2 * TILE_A;
     static constexpr uint32_t TOTAL = OFF_B + NSTAGE * TILE_B;
+    static constexpr uint32_t total(int stages) { return OFF_B + (uint32_t)stages * TILE_B; }
     /* D = F32, A = B = BF16, both K-major, N = kNT, M = 128 */
     static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kNT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
@@ -237,14 +238,14 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     int* __restrict__ slots /* [Q][K'] range minima by range % K' (ordered-int image) */,
     uint4* __restrict__ hq /* [Q][n_ranges][kQueueCap][2] hit queues: (first key of the chunk, best scores of its four groups) */, int* __restrict__ hq_cnt /* [Q][n_ranges] */,
     int* __restrict__ dbg /* null, or developer counters */, int dev_flags /* SCL_TC_FLAGS: timing experiments, results are then wrong */,
-    int kp /* K' of this launch: 12 or 16 */)
+    int kp /* K' of this launch: 12 or 16 */, int NS /* key tiles in flight: 2 .. C::NSTAGE (fewer leave shared memory to kernels of other lanes) */)
 {
     using C = TcCfg<R>;
-    constexpr int NS = C::NSTAGE;
+    constexpr int NSMAX = C::NSTAGE;
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-    uint64_t *full = bars, *empty = bars + NS, *tfull = bars + 2 * NS, *tempty = bars + 2 * NS + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 4);
+    uint64_t *full = bars, *empty = bars + NSMAX, *tfull = bars + 2 * NSMAX, *tempty = bars + 2 * NSMAX + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSMAX + 4);
     volatile int* epi_done = reinterpret_cast<volatile int*>(tmem_slot + 1);
     volatile int* sthr = reinterpret_cast<volatile int*>(smem + C::OFF_THR);          /* [256] union bounds of the CTA's queries */
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -863,9 +864,12 @@ static constexpr int dev_flags_env() { return 0; }
 
 template <int R>
 static cudaError_t launch_tc(const float* qkeys, int Q, const unsigned char* img, int n_db, int n_ranges, int* slots,
-                              uint4* hq, int* hq_cnt, int* dbg, int kp, cudaStream_t stream)
+                              uint4* hq, int* hq_cnt, int* dbg, int kp, int stages, cudaStream_t stream)
 {
     using C = TcCfg<R>;
+    if (stages < 2) stages = 2;
+    if (stages > C::NSTAGE) stages = C::NSTAGE;
+    const uint32_t smem_bytes = C::total(stages);
     {
         /* a function attribute belongs to the current device's context: once per device, not once per process */
         static bool attr[64] = {false};
@@ -891,8 +895,8 @@ static cudaError_t launch_tc(const float* qkeys, int Q, const unsigned char* img
     const int dev_flags = dev_flags_env();
     if (want_times) { cudaMalloc(&times, (size_t)nb * 16 * sizeof(long long)); cudaMemsetAsync(times, 0, (size_t)nb * 128, stream); }
     if (dev_flags & 64) {}
-    else if (want_times) knn_tc_kernel<R, true><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, times, slots, hq, hq_cnt, dbg, dev_flags, kp);
-    else knn_tc_kernel<R, false><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, nullptr, slots, hq, hq_cnt, dbg, dev_flags, kp);
+    else if (want_times) knn_tc_kernel<R, true><<<nb, kThreads, smem_bytes, stream>>>(qkeys, Q, img, n_db, n_ranges, times, slots, hq, hq_cnt, dbg, dev_flags, kp, stages);
+    else knn_tc_kernel<R, false><<<nb, kThreads, smem_bytes, stream>>>(qkeys, Q, img, n_db, n_ranges, nullptr, slots, hq, hq_cnt, dbg, dev_flags, kp, stages);
     if (want_times) {
         std::vector<long long> h((size_t)nb * 16);
         cudaStreamSynchronize(stream);
@@ -906,14 +910,15 @@ static cudaError_t launch_tc(const float* qkeys, int Q, const unsigned char* img
         cudaFree(times);
     }
 #else
-    knn_tc_kernel<R, false><<<nb, kThreads, C::TOTAL, stream>>>(qkeys, Q, img, n_db, n_ranges, nullptr, slots, hq, hq_cnt, dbg, 0, kp);
+    SCL_PREFER_SMEM((knn_tc_kernel<R, false>));
+    knn_tc_kernel<R, false><<<nb, kThreads, smem_bytes, stream>>>(qkeys, Q, img, n_db, n_ranges, nullptr, slots, hq, hq_cnt, dbg, 0, kp, stages);
 #endif
     return cudaGetLastError();
 }
 
 cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, const unsigned char* img, const float* kn2max, int n_db, int R, int K,
                                int metric, int id_mul, int id_add, KnnTcWorkspace ws, int32_t* out_ids, float* out_d2,
-                               int32_t* fail_list, int* fail_count, int* next_fail_count, bool init_state, cudaStream_t stream)
+                               int32_t* fail_list, int* fail_count, int* next_fail_count, bool init_state, int stages, cudaStream_t stream)
 {
     if (Q <= 0) return cudaSuccess;
     if (R != 20 && R != 40) return cudaErrorNotSupported;
@@ -931,17 +936,18 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
         const int n_ranges = scl_knn_tc_ranges(Qc);
         if ((size_t)Qc * n_ranges > ws.capacity) return cudaErrorInvalidValue;
         const float* qk = qkeys + (size_t)q0 * R;
-        if (R == 20) err = launch_tc<20>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint4*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), kprime_for(K), stream);
-        else err = launch_tc<40>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint4*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), kprime_for(K), stream);
+        if (R == 20) err = launch_tc<20>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint4*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), kprime_for(K), stages, stream);
+        else err = launch_tc<40>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint4*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), kprime_for(K), stages, stream);
         if (err != cudaSuccess) return err;
 #define SCL_RERANK(M, RR)                                                                                                              \
+    SCL_PREFER_SMEM((knn_rerank_kernel<M, RR>));                                                                                          \
     knn_rerank_kernel<M, RR><<<(Qc + kRrWarps - 1) / kRrWarps, 32 * kRrWarps, 0, stream>>>(qk, Qc, keys, K, n_ranges, n_db, reinterpret_cast<const uint4*>(ws.hq), ws.hq_cnt,   \
                                                             ws.slots, kn2max, id_mul, id_add, out_ids + (size_t)q0 * K, out_d2 + (size_t)q0 * K, \
                                                             q0, fail_list, fail_count, ws.err_probe, dev_flags, kprime_for(K), ws.slots, next_fail_count)
         const int dev_flags = dev_flags_env();     /* 0 in release builds */
         if (dev_flags & 16) {}
-        else if (R == 20) { if (metric == 0) SCL_RERANK(0, 20); else SCL_RERANK(1, 20); }
-        else { if (metric == 0) SCL_RERANK(0, 40); else SCL_RERANK(1, 40); }
+        else if (R == 20) { if (metric == 0) { SCL_RERANK(0, 20); } else { SCL_RERANK(1, 20); } }
+        else { if (metric == 0) { SCL_RERANK(0, 40); } else { SCL_RERANK(1, 40); } }
 #undef SCL_RERANK
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;

@@ -82,7 +82,8 @@ struct ScArgs {
     const float* db_desc; const double* db_stat;
     const float* q_desc; const double* q_stat;          /* fresh queries (+ their stats from K2), or null: queries are entries q_local[i] */
     const int32_t* q_local; const int32_t* q_ids;
-    const int32_t* cand_local; const int32_t* cand_ids;
+    const int32_t* cand_local; const int32_t* cand_ids;  /* cand_local null: derived from the reported ids (id = local * id_mul + id_add) */
+    int id_mul, id_add;
     int K, R, S, search_radius, use_bulk, exact_all;
     double* cand_dist; int32_t* cand_shift; int32_t* best_id; double* best_dist; int32_t* best_shift;
 };
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) scdist_kernel(const S
     double* vq = reinterpret_cast<double*>(smem + L.off_qs);
     double* nq = vq + S;
     float* vq32 = reinterpret_cast<float*>(smem + L.off_vq32);
-    unsigned char* wbase = smem + L.off_warp + (size_t)warp * L.warp_stride;
+    unsigned char* wbase = smem + L.off_warp + (size_t)(warp < L.warps ? warp : 0) * L.warp_stride;   /* helper warps never touch it */
     float* cd = reinterpret_cast<float*>(wbase + L.w_cd);
     double* vc = reinterpret_cast<double*>(wbase + L.w_cs);
     double* nc = vc + S;
@@ -192,12 +193,45 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) scdist_kernel(const S
     const uint32_t bytes = (uint32_t)RS * 4u, sbytes = (uint32_t)S * 16u;
     const int TP = S + 1;                                       /* pitch of T */
 
+    const int slots = L.warps;                        /* candidate tiles in shared memory: warps 0 .. slots-1 score pairs, the others only help with the query side */
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 1 + warps; i++) scl_mbar_init(&bars[i], 1);
+        for (int i = 0; i < 1 + slots; i++) scl_mbar_init(&bars[i], 1);
         scl_mbar_fence_init();
     }
+    /* The candidates this engine holds (all of them on an unsharded engine, about K / world on a shard) are listed first, so
+     * that the warps share the work evenly whatever the ownership pattern; slots of other shards report NaN at once. */
+    __shared__ int s_owned[32];
+    __shared__ int s_local[32];                       /* local key of every candidate slot (-1: not held here) */
+    __shared__ int s_n_owned;
+    __shared__ float s_q[4];                          /* centre of the query sector key, its centred squared norm, FP32-safe flag */
+    __shared__ unsigned s_zq[4];                      /* bit j: query column j is not empty */
+    __shared__ float s_red[4][32];
+    if (warp == 0) {
+        int cl = -1;
+        if (lane < K) {
+            if (a.cand_local) cl = a.cand_local[(size_t)qi * K + lane];
+            else { const int id = a.cand_ids[(size_t)qi * K + lane]; cl = (id >= 0 && id % a.id_mul == a.id_add) ? id / a.id_mul : -1; }
+        }
+        s_local[lane] = cl;
+        const unsigned m = __ballot_sync(0xffffffffu, cl >= 0);
+        if (cl >= 0) s_owned[__popc(m & ((1u << lane) - 1u))] = lane;
+        if (lane == 0) s_n_owned = __popc(m);
+        if (lane < K && cl < 0) {
+            res_dist[lane] = __longlong_as_double(0x7ff8000000000000LL); res_shift[lane] = 0;
+            if (a.cand_dist) a.cand_dist[(size_t)qi * K + lane] = __longlong_as_double(0x7ff8000000000000LL);
+            if (a.cand_shift) a.cand_shift[(size_t)qi * K + lane] = 0;
+        }
+    }
     __syncthreads();
-
+    const int n_owned = s_n_owned;
+    if (n_owned == 0) {                               /* nothing to score here (a shard that owns none of this query's candidates): nothing was fetched */
+        if (threadIdx.x == 0) {
+            if (a.best_id) a.best_id[qi] = -1;
+            if (a.best_dist) a.best_dist[qi] = 10000000.0;
+            if (a.best_shift) a.best_shift[qi] = 0;
+        }
+        return;
+    }
     const float* qsrc = a.q_desc ? a.q_desc + (size_t)qi * RS : a.db_desc + (size_t)a.q_local[qi] * RS;
     const double* qssrc = a.q_desc ? a.q_stat + (size_t)qi * 2 * S : a.db_stat + (size_t)a.q_local[qi] * 2 * S;
     if (a.use_bulk) {
@@ -210,43 +244,14 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) scdist_kernel(const S
         for (int i = threadIdx.x; i < RS; i += blockDim.x) qd[i] = __ldg(qsrc + i);
         for (int i = threadIdx.x; i < 2 * S; i += blockDim.x) vq[i] = __ldg(qssrc + i);
     }
-    /* The candidates this engine holds (all of them on an unsharded engine, about K / world on a shard) are listed first, so
-     * that the warps share the work evenly whatever the ownership pattern; slots of other shards report NaN at once. */
-    __shared__ int s_owned[32];
-    __shared__ int s_n_owned;
-    __shared__ float s_q[4];                          /* centre of the query sector key, its centred squared norm, FP32-safe flag */
-    __shared__ unsigned s_zq[4];                      /* bit j: query column j is not empty */
-    __shared__ float s_red[4][32];
-    if (warp == 0) {
-        const int cl = lane < K ? a.cand_local[(size_t)qi * K + lane] : -1;
-        const unsigned m = __ballot_sync(0xffffffffu, cl >= 0);
-        if (cl >= 0) s_owned[__popc(m & ((1u << lane) - 1u))] = lane;
-        if (lane == 0) s_n_owned = __popc(m);
-        if (lane < K && cl < 0) {
-            res_dist[lane] = __longlong_as_double(0x7ff8000000000000LL); res_shift[lane] = 0;
-            if (a.cand_dist) a.cand_dist[(size_t)qi * K + lane] = __longlong_as_double(0x7ff8000000000000LL);
-            if (a.cand_shift) a.cand_shift[(size_t)qi * K + lane] = 0;
-        }
-    }
-    __syncthreads();
-    const int n_owned = s_n_owned;
-    /* first candidate of every warp goes in flight before anyone waits */
-    int oi = warp;                                    /* position in the owned list */
+    /* first candidate of every scoring warp goes in flight before anyone waits */
+    int oi = warp < slots ? warp : n_owned;           /* position in the owned list */
     int it = oi < n_owned ? s_owned[oi] : K;
-    int c_local = it < K ? a.cand_local[(size_t)qi * K + it] : -1;
+    int c_local = it < K ? s_local[it] : -1;
     if (a.use_bulk && lane == 0 && c_local >= 0) {
         scl_mbar_expect_tx(&bars[1 + warp], bytes + sbytes);
         scl_bulk_g2s(cd, a.db_desc + (size_t)c_local * RS, bytes, &bars[1 + warp]);
         scl_bulk_g2s(vc, a.db_stat + (size_t)c_local * 2 * S, sbytes, &bars[1 + warp]);
-    }
-    if (n_owned == 0) {                               /* nothing to score here (a shard that owns none of this query's candidates) */
-        if (threadIdx.x == 0) {
-            if (a.best_id) a.best_id[qi] = -1;
-            if (a.best_dist) a.best_dist[qi] = 10000000.0;
-            if (a.best_shift) a.best_shift[qi] = 0;
-        }
-        if (a.use_bulk) scl_mbar_wait(&bars[0], 0);    /* the query copies must land before the CTA's shared memory goes away */
-        return;
     }
     if (a.use_bulk) scl_mbar_wait(&bars[0], 0);
     else __syncthreads();
@@ -304,7 +309,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) scdist_kernel(const S
     const unsigned zq0 = s_zq[0], zq1 = S > 32 ? s_zq[1] : 0u, zq2 = S > 64 ? s_zq[2] : 0u, zq3 = S > 96 ? s_zq[3] : 0u;
 
     uint32_t parity = 0;
-    for (; oi < n_owned; oi += warps) {
+    for (; oi < n_owned; oi += slots) {
         double out_dist = __longlong_as_double(0x7ff8000000000000LL); /* NaN: candidate missing */
         int out_shift = 0;
         if (c_local >= 0) {
@@ -591,8 +596,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) scdist_kernel(const S
             if (a.cand_shift) a.cand_shift[(size_t)qi * K + it] = out_shift;
         }
         /* next candidate of this warp into the same tile */
-        const int nxt = oi + warps < n_owned ? s_owned[oi + warps] : K;
-        c_local = nxt < K ? a.cand_local[(size_t)qi * K + nxt] : -1;
+        const int nxt = oi + slots < n_owned ? s_owned[oi + slots] : K;
+        c_local = nxt < K ? s_local[nxt] : -1;
         it = nxt;
         __syncwarp();
         if (a.use_bulk && lane == 0 && c_local >= 0) {
@@ -736,30 +741,31 @@ cudaError_t set_smem(void (*kern)(const ScArgs), size_t bytes)
 
 cudaError_t scl_launch_scdist(const float* db_desc, const double* db_stat, const float* q_desc, const double* q_stat,
                               const int32_t* q_local, const int32_t* q_ids,
-                              const int32_t* cand_local, const int32_t* cand_ids, int Q, int K, int R, int S, int search_radius,
+                              const int32_t* cand_local, const int32_t* cand_ids, int id_mul, int id_add, int Q, int K, int R, int S, int search_radius,
                               double* cand_dist, int32_t* cand_shift, int32_t* best_id, double* best_dist, int32_t* best_shift,
                               int owned_per_query /* expected candidates per query held here; <= 0: all K */, int exact_all, cudaStream_t stream)
 {
     if (Q <= 0) return cudaSuccess;
     if (S > 128 || K > 32) return cudaErrorNotSupported;
     const size_t budget = 227 * 1024 - 2048;
-    int warps = K < 16 ? K : 16;
-    /* a shard holds about K / world of a query's candidates: fewer warps per CTA then, so that more CTAs (queries) share an SM */
-    if (owned_per_query > 0 && owned_per_query < warps) warps = owned_per_query < 2 ? 2 : owned_per_query;
-    /* two CTAs per SM when they fit */
-    while (warps > 1 && sc_layout(R, S, K, warps).total > budget) warps--;
-    const ScLayout L = sc_layout(R, S, K, warps);
+    int slots = K < 16 ? K : 16;
+    /* a shard holds about K / world of a query's candidates: fewer candidate tiles per CTA then, so that more CTAs (queries) share an SM */
+    if (owned_per_query > 0 && owned_per_query < slots) slots = owned_per_query < 2 ? 2 : owned_per_query;
+    while (slots > 1 && sc_layout(R, S, K, slots).total > budget) slots--;
+    const ScLayout L = sc_layout(R, S, K, slots);
     if (L.total > budget) return cudaErrorNotSupported;
+    const int warps = slots < 4 ? 4 : slots;           /* at least four warps prepare the query side */
     const int use_bulk = ((R * S) % 4 == 0) && ((reinterpret_cast<uintptr_t>(db_desc) & 15) == 0) &&
                          (q_desc == nullptr || ((reinterpret_cast<uintptr_t>(q_desc) & 15) == 0 && (reinterpret_cast<uintptr_t>(q_stat) & 15) == 0)) &&
                          ((reinterpret_cast<uintptr_t>(db_stat) & 15) == 0);
     if (S & 1) exact_all = 1;                                   /* the FP32 window pass pairs adjacent columns */
-    ScArgs a{L, db_desc, db_stat, q_desc, q_stat, q_local, q_ids, cand_local, cand_ids, K, R, S, search_radius, use_bulk, exact_all,
+    ScArgs a{L, db_desc, db_stat, q_desc, q_stat, q_local, q_ids, cand_local, cand_ids, id_mul < 1 ? 1 : id_mul, id_add, K, R, S, search_radius, use_bulk, exact_all,
              cand_dist, cand_shift, best_id, best_dist, best_shift};
 #define SCL_SCDIST_LAUNCH(MT, MB, RT, ST)                                                                                       \
     do {                                                                                                                       \
         cudaError_t ea = set_smem(scdist_kernel<MT, MB, RT, ST>, L.total);                                                       \
         if (ea != cudaSuccess) return ea;                                                                                      \
+        SCL_PREFER_SMEM((scdist_kernel<MT, MB, RT, ST>));                                                                       \
         scdist_kernel<MT, MB, RT, ST><<<Q, warps * 32, L.total, stream>>>(a);                                                   \
     } while (0)
     /* up to 10 warps and half an SM's shared memory: two CTAs per SM; otherwise one big CTA */

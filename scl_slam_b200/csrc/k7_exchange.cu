@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(128) xchg_combine_kernel(XchgView x, int seq, 
 cudaError_t scl_launch_xchg_merge_topk(const XchgView& x, int seq, int Q, int K, const void* my_block, int32_t* out_ids, float* out_d2, cudaStream_t stream)
 {
     if (Q <= 0) return cudaSuccess;
+    SCL_PREFER_SMEM(xchg_merge_topk_kernel);
     xchg_merge_topk_kernel<<<(Q + 127) / 128, 128, 0, stream>>>(x, seq, Q, K, static_cast<const unsigned char*>(my_block), out_ids, out_d2);
     return cudaGetLastError();
 }
@@ -145,6 +146,7 @@ cudaError_t scl_launch_xchg_combine(const XchgView& x, int seq, int Q, int K, co
                                     double* out_dist, int32_t* out_shift, int32_t* best_id, double* best_dist, int32_t* best_shift, cudaStream_t stream)
 {
     if (Q <= 0) return cudaSuccess;
+    SCL_PREFER_SMEM(xchg_combine_kernel);
     xchg_combine_kernel<<<(Q + 127) / 128, 128, 0, stream>>>(x, seq, Q, K, static_cast<const unsigned char*>(my_block), q_ids, cand_ids,
                                                            out_dist, out_shift, best_id, best_dist, best_shift);
     return cudaGetLastError();
@@ -156,6 +158,7 @@ cudaError_t scl_launch_xchg_gather_queries(const XchgView& x, int seq, const voi
     int blocks = (int)((bytes / 16 + 255) / 256);
     if (blocks > 32) blocks = 32;                     /* every CTA must be resident while it waits: a handful */
     if (blocks < 1) blocks = 1;
+    SCL_PREFER_SMEM(xchg_gather_queries_kernel);
     xchg_gather_queries_kernel<<<blocks, 256, 0, stream>>>(x, seq, static_cast<const unsigned char*>(my_rows), row0_bytes, bytes);
     return cudaGetLastError();
 }

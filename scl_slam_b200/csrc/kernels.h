@@ -51,7 +51,9 @@ cudaError_t scl_launch_key_image(const float* keys, const float* knorm, int k_lo
 cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, const unsigned char* img, const float* kn2max, int n_db, int R, int K,
                                int metric, int id_mul, int id_add, KnnTcWorkspace ws, int32_t* out_ids, float* out_d2,
                                int32_t* fail_list, int* fail_count, int* next_fail_count /* zeroed by the re-rank for the next call */,
-                               bool init_state /* slots and fail_count are not known to be clean */, cudaStream_t stream);
+                               bool init_state /* slots and fail_count are not known to be clean */,
+                               int stages /* key tiles in flight in shared memory, 2..5: fewer leave room for kernels of other lanes on the SM */,
+                               cudaStream_t stream);
 
 // K4: shift-aligned column-cosine distance for every (query, candidate) + winner scan. See k4_scdist.cu.
 //  q_desc [Q][R*S] with q_stat [Q][2*S] (scl_launch_ring_keys' cstat of the queries), or both nullptr (then queries are db
@@ -59,7 +61,8 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
 //  cand_ids [Q][K] reported ids (for the self-skip rule against q_ids). exact_all != 0: every shift in FP64 (no FP32 prefilter).
 cudaError_t scl_launch_scdist(const float* db_desc, const double* db_stat, const float* q_desc, const double* q_stat,
                               const int32_t* q_local, const int32_t* q_ids,
-                              const int32_t* cand_local, const int32_t* cand_ids, int Q, int K, int R, int S, int search_radius,
+                              const int32_t* cand_local /* null: derived from cand_ids with id = local * id_mul + id_add */, const int32_t* cand_ids,
+                              int id_mul, int id_add, int Q, int K, int R, int S, int search_radius,
                               double* cand_dist, int32_t* cand_shift, int32_t* best_id, double* best_dist, int32_t* best_shift,
                               int owned_per_query, int exact_all, cudaStream_t stream);
 

@@ -396,34 +396,36 @@ def test_tensor_core_knn_fallback_on_ties(eng_mod):
 
 
 def test_pipelined_host_queries_equal_synchronous(eng_mod):
-    """scl_query_batch_submit / _wait (up to four batches in flight, second copy stream) returns exactly what the
-    one-call scl_query_batch returns, batch after batch, and refuses a fifth batch in flight."""
+    """scl_query_batch_submit / _wait (one batch in flight per query lane) returns exactly what the one-call
+    scl_query_batch returns, batch after batch, and refuses one batch more than there are lanes."""
     import torch
     n, nq, K = 40000, 200, 10
     db = synth.desc_db(n, seed=71)
     e = eng_mod.ScanContextB200(numCandidates=K)
     e.insert_batch(db.numpy())
-    batches = [np.ascontiguousarray(synth.desc_queries(db, nq, seed=80 + i)[0].numpy().reshape(nq, -1)) for i in range(8)]
+    L = e.num_lanes()
+    nb = L + 4
+    batches = [np.ascontiguousarray(synth.desc_queries(db, nq, seed=80 + i)[0].numpy().reshape(nq, -1)) for i in range(nb)]
     exp = [e.query_batch(q_desc=b, K=K, n_db=n, metric=0) for b in batches]
     names = ("cand_ids", "cand_d2", "cand_dist", "cand_shift", "best_id", "best_dist", "best_shift")
     dt = dict(cand_ids=np.int32, cand_d2=np.float32, cand_dist=np.float64, cand_shift=np.int32, best_id=np.int32, best_dist=np.float64, best_shift=np.int32)
     outs = [{k: np.empty((nq, K) if k.startswith("cand") else nq, dt[k]) for k in names} for _ in batches]
     pinned_q = [torch.from_numpy(b).pin_memory().numpy() for b in batches]
-    tickets = [e.query_batch_submit(pinned_q[i], outs[i], K=K, n_db=n, metric=0) for i in range(4)]       # four in flight
+    tickets = [e.query_batch_submit(pinned_q[i], outs[i], K=K, n_db=n, metric=0) for i in range(L)]       # every lane busy
     with pytest.raises(RuntimeError):
-        e.query_batch_submit(pinned_q[4], outs[4], K=K, n_db=n, metric=0)                                 # a fifth is refused
+        e.query_batch_submit(pinned_q[L], outs[L], K=K, n_db=n, metric=0)                                 # one more is refused
     e.query_batch_wait(tickets[0])
-    tickets.append(e.query_batch_submit(pinned_q[4], outs[4], K=K, n_db=n, metric=0))                     # room again
+    tickets.append(e.query_batch_submit(pinned_q[L], outs[L], K=K, n_db=n, metric=0))                     # room again
     for t in tickets[1:]:
         e.query_batch_wait(t)
     prev = None
-    for i in range(5, 8):                                                                                 # the streaming pattern
+    for i in range(L + 1, nb):                                                                            # the streaming pattern
         t = e.query_batch_submit(pinned_q[i], outs[i], K=K, n_db=n, metric=0)
         if prev is not None:
             e.query_batch_wait(prev)
         prev = t
     e.query_batch_wait(prev)
-    for i in range(8):
+    for i in range(nb):
         for k in names:
             assert np.array_equal(outs[i][k], exp[i][k], equal_nan=True), (i, k)
 
