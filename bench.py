@@ -500,7 +500,7 @@ def query_arm(engine, synth, dev, pk, n_db, gen, seed, depth, r=R, s=S, no_match
     res = {"value": Q / (thr * 1e-3), "unit": "queries/s", "ms_per_step": thr, "in_flight": depth, "latency_ms_per_step": lat, "stage_ms_per_step": stage,
            "db_keyframes": n_db, "rings": r, "sectors": s, "knn": e.knn_stats(),
            "source_recovered": float((bid[has] == src[has]).mean()) if has.any() else None,
-           "no_match_answered_minus_one": float((bid[~has] == -1).mean()) if (~has).any() else None,
+           "no_match_best_distance_above_threshold": float((outs[0]["best_dist"].cpu().numpy()[~has] >= 0.14).mean()) if (~has).any() else None,
            "roofline": {"bound": "hbm", "algorithmic_bytes": alg, "achieved": alg / (thr * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                         "frac": alg / (thr * 1e-3) / 1e9 / pk["hbm"]}}
     return e, res, qs, outs
@@ -540,6 +540,7 @@ def arm_c5(engine, synth, dev, pk, cpu, depth):
     eng = {}
     for name, seed in (("b", 52), ("c", 53)):
         e = engine.ScanContextB200(numRing=r, numSector=s, numCandidates=K)
+        e.set_stream(torch.cuda.current_stream().cuda_stream)          # the fill below is generated on this stream
         fill(e, dev, 0, 1, n, seed=seed, r=r, s=s)
         eng[name] = e
     both = torch.cat([synth.desc_db(n, r, s, seed=52, device=dev), synth.desc_db(n, r, s, seed=53, device=dev)])
@@ -548,8 +549,6 @@ def arm_c5(engine, synth, dev, pk, cpu, depth):
     del both
     outs = {name: out_bufs(dev) for name in eng}
     cur = torch.cuda.current_stream().cuda_stream
-    for e in eng.values():
-        e.set_stream(cur)
     best = torch.empty(Q, dtype=torch.int64, device=dev)
 
     def step():
@@ -579,12 +578,12 @@ def arm_c5(engine, synth, dev, pk, cpu, depth):
     if cpu:
         oracle_lib, kind = _oracle()
         sample = 64
-        db_host = np.concatenate([synth.desc_db(n, r, s, seed=52).numpy().reshape(n, -1), q[:sample].cpu().numpy().reshape(sample, -1)])
+        db_host = np.concatenate([synth.desc_db(n, r, s, seed=52, device=dev).cpu().numpy().reshape(n, -1), q[:sample].cpu().numpy().reshape(sample, -1)])
         wins = []
         t_q = 0.0
         for name, seed in (("b", 52), ("c", 53)):
             if name == "c":
-                db_host[:n] = synth.desc_db(n, r, s, seed=53).numpy().reshape(n, -1)
+                db_host[:n] = synth.desc_db(n, r, s, seed=53, device=dev).cpu().numpy().reshape(n, -1)
             o = oracle_lib.Oracle(num_ring=r, num_sector=s, num_candidates=K, kind=kind)
             o.bulk_load(db_host, borrow=True)
             ids = np.arange(n, n + sample, dtype=np.int32)

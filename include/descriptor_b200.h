@@ -27,6 +27,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <utility>
+#include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "scl_engine.h"
@@ -72,7 +74,8 @@ public:
 	{
 		std::vector<float> vT(rs_, 0.0f);
 		const void* pts = scan.points.empty() ? nullptr : static_cast<const void*>(&scan.points[0]);
-		check(scl_build_insert(engine_, pts, (int)scan.points.size(), (int)sizeof(pcl::PointXYZI), robot, index, vT.data()), "makeAndSaveDescriptorAndKey");
+		if(!check(scl_build_insert(engine_, pts, (int)scan.points.size(), (int)sizeof(pcl::PointXYZI), robot, index, vT.data()), "makeAndSaveDescriptorAndKey"))
+			keep_keys_dense(vT, robot, index);
 		return vT;
 	}
 
@@ -84,8 +87,9 @@ public:
 		std::vector<float> vT(rs_, 0.0f);
 		const void* pts = scan.points.empty() ? nullptr : static_cast<const void*>(&scan.points[0]);
 		int m = 0;
-		check(scl_build_insert_filtered(engine_, pts, (int)scan.points.size(), (int)sizeof(pcl::PointXYZI), leaf, robot, index, vT.data(), &m),
-			"makeAndSaveDescriptorAndKeyFiltered");
+		if(!check(scl_build_insert_filtered(engine_, pts, (int)scan.points.size(), (int)sizeof(pcl::PointXYZI), leaf, robot, index, vT.data(), &m),
+			"makeAndSaveDescriptorAndKeyFiltered"))
+			keep_keys_dense(vT, robot, index);
 		if(filteredSize) *filteredSize = m;
 		return vT;
 	}
@@ -211,10 +215,24 @@ private:
 		}
 	}
 
-	void check(int rc, const char* what)
+	bool check(int rc, const char* what)
 	{
 		if(rc != SCL_OK)
 			std::fprintf(stderr, "[scan_context_descriptor_b200] %s failed (%d): %s\n", what, rc, engine_ ? scl_last_error(engine_) : "no engine");
+		return rc == SCL_OK;
+	}
+
+	/* The caller takes key = cloudKeyPoses6D->size() - 1 for granted (distributedMapping.h:1002,1072): a build that failed
+	 * must still occupy its key, or every later key drifts by one. An empty (all-zero) descriptor takes the slot: it matches
+	 * nothing (every SC distance against it is NaN, descriptor.h:1523,1534). If even that fails the process cannot continue. */
+	void keep_keys_dense(std::vector<float>& vT, const int8_t robot, const int index)
+	{
+		std::fill(vT.begin(), vT.end(), 0.0f);
+		if(!engine_ || scl_insert(engine_, vT.data(), robot, index) != SCL_OK)
+		{
+			std::fprintf(stderr, "[scan_context_descriptor_b200] cannot keep the key space dense after a failed build: aborting\n");
+			std::abort();
+		}
 	}
 
 	scl_engine* engine_;

@@ -154,7 +154,9 @@ int sco_icp(const float* src, int n_src, const float* tgt, int n_tgt, int stride
     std::vector<P3> s = load(src, n_src, stride), t = load(tgt, n_tgt, stride);
     GridNN nn; nn.build(t, 1.0);
     double final_T[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-    const double rotation_threshold = 0.99999, mse_rel = 0.00001;
+    /* icp.hpp (PCL 1.8 - 1.12): setRelativeMSE(euclidean_fitness_epsilon_), setTranslationThreshold(transformation_epsilon_),
+     * setRotationThreshold(1 - transformation_epsilon_); absolute-MSE threshold at its default 1e-12 */
+    const double rotation_threshold = 1.0 - trans_eps, mse_rel = fit_eps, mse_abs = 1e-12;
     const double max_d2 = max_corr_dist * max_corr_dist;
     double prev_mse = DBL_MAX;
     int iterations = 0; bool conv = false;
@@ -184,7 +186,7 @@ int sco_icp(const float* src, int n_src, const float* tgt, int n_tgt, int stride
         const double translation_sqr = T[3] * T[3] + T[7] * T[7] + T[11] * T[11];
         if (cos_angle >= rotation_threshold && translation_sqr <= trans_eps) { conv = true; break; }
         const double cur_mse = sum_d2 / (double)a.size();
-        if (std::fabs(cur_mse - prev_mse) < fit_eps) { conv = true; break; }
+        if (std::fabs(cur_mse - prev_mse) < mse_abs) { conv = true; break; }
         if (std::fabs(cur_mse - prev_mse) / prev_mse < mse_rel) { conv = true; break; }
         prev_mse = cur_mse;
     }

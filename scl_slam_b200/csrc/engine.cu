@@ -201,9 +201,10 @@ int knn_dev(scl_engine* e, Lane& ln, const float* q_desc, const int32_t* q_ids, 
     if (!q_desc && e->world != 1) FAIL(SCL_ERR_INVALID, "queries by key need q_desc on a sharded engine");
     /* K3 variant: on a database worth streaming the tensor-core prefilter wins from four queries up (measured on 1 M keys:
      * 182 us per call at Q = 9..128 against 800..1800 us for the exact kernel, and against 199 / 234 us for the thread-per-key
-     * kernel at Q = 4 / 8); up to three queries and small databases take the exact CUDA-core kernels. */
+     * kernel at Q = 4 / 8; on 20 k keys and batches of 1024: 15.1 M against 5.0 M queries/s for the whole query); up to three queries and
+     * databases under 16 384 keys (fewer key tiles than the union bound needs ranges) take the exact CUDA-core kernels. */
     const bool use_tc = scl_knn_tc_supported(R) && K <= scl_knn_tc_kprime() - 2 &&
-                        (e->knn_mode == 2 || (e->knn_mode == 0 && Q > 3 && n_db >= 32768));
+                        (e->knn_mode == 2 || (e->knn_mode == 0 && Q > 3 && n_db >= 16384));
     if (use_tc) { int rc = sync_key_image(e); if (rc) return rc; }            /* on the engine stream */
     { int rc = lane_begin(e, ln); if (rc) return rc; }
     const size_t QK = (size_t)Q * K;
@@ -244,7 +245,7 @@ int knn_dev(scl_engine* e, Lane& ln, const float* q_desc, const int32_t* q_ids, 
             CK(ln.tc_queues.ensure(pairs * scl_knn_tc_queue_bytes())); CK(ln.tc_queue_cnt.ensure(pairs * 4));
             const void* old_slots = ln.tc_slots.p; const void* old_cnt = ln.tc_fail_count.p;
             CK(ln.tc_fail_list.ensure((size_t)Q * 4)); CK(ln.tc_fail_count.ensure(128));
-            CK(ln.tc_slots.ensure((size_t)Qc * scl_knn_tc_kprime() * 4));
+            CK(ln.tc_slots.ensure((size_t)Qc * scl_knn_tc_slot_stride() * 4));
             const bool init_state = !ln.tc_state_clean || old_slots != ln.tc_slots.p || old_cnt != ln.tc_fail_count.p || Qc > ln.tc_slots_rows;
             if (old_cnt != ln.tc_fail_count.p) CK(cudaMemsetAsync(ln.tc_fail_count.p, 0, 128, ln.stream));   /* two call counters + the running total */
             /* counter block (ints): [0] / [16] = the fail counters of even / odd calls; [8] + [24] = uncertified queries since
@@ -418,8 +419,10 @@ int scl_create(const scl_params* p, int device, scl_engine** out)
     if (p->num_ring < 1 || p->num_sector < 1 || p->num_candidates < 1 || p->num_candidates > 32 || p->tree_making_period < 1 ||
         !(p->max_radius > 0))
         return SCL_ERR_INVALID;
-    if (p->num_ring != 10 && p->num_ring != 20 && p->num_ring != 40 && p->num_ring != 80) return SCL_ERR_UNSUPPORTED;
-    if (p->num_ring * p->num_sector > 8192) return SCL_ERR_UNSUPPORTED;
+    /* what EVERY kernel of the path can run, so that a build can never fail later for a geometry that was accepted here:
+     * the kNN kernels are built for 10 / 20 / 40 rings, K1's threshold tables hold 4 x 31 sector boundaries, K4's masks 128 sectors */
+    if (p->num_ring != 10 && p->num_ring != 20 && p->num_ring != 40) return SCL_ERR_UNSUPPORTED;
+    if (p->num_sector > 124 || p->num_ring * p->num_sector > 8192) return SCL_ERR_UNSUPPORTED;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return SCL_ERR_CUDA; /* no CPU fallback */
     if (cudaSetDevice(device) != cudaSuccess) return SCL_ERR_CUDA;

@@ -454,10 +454,26 @@ cudaError_t scl_launch_polar(const void* pts_dev, const int* offsets_dev, int n_
     if (p.bt.n_ring > kRingPad - 1 || p.bt.n_sec[0] > kSecPad - 1 || p.bt.n_sec[1] > kSecPad - 1 || p.bt.n_sec[2] > kSecPad - 1 ||
         p.bt.n_sec[3] > kSecPad - 1) return cudaErrorNotSupported;       /* up to 64 rings x 124 sectors */
     const size_t smem = (size_t)R * S * 8 + (size_t)R * 4;
-    dim3 grid(chunks, n_scans);
-    polar_bin_kernel<kPPT><<<grid, 256, smem, stream>>>(static_cast<const unsigned char*>(pts_dev), offsets_dev, stride_bytes, vec4, p,
-                                                       gbins, tickets, out_desc, out_keys, out_knorm, kn2max, out_ring, out_sector);
-    return cudaGetLastError();
+    if (smem > 48 * 1024) {
+        /* geometries above ~6100 bins need the opt-in (per device: the attribute belongs to the current device's context) */
+        static SclOncePerDevice once;
+        if (once.first()) {
+            cudaError_t ea = cudaFuncSetAttribute(polar_bin_kernel<kPPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (ea != cudaSuccess) return ea;
+        }
+        if (smem > 200 * 1024) return cudaErrorNotSupported;
+    }
+    /* gridDim.y is limited to 65535: larger batches go in slices (the per-scan scratch rows move with the slice) */
+    for (int s0 = 0; s0 < n_scans; s0 += 65535) {
+        const int ns = n_scans - s0 < 65535 ? n_scans - s0 : 65535;
+        dim3 grid(chunks, ns);
+        polar_bin_kernel<kPPT><<<grid, 256, smem, stream>>>(static_cast<const unsigned char*>(pts_dev), offsets_dev + s0, stride_bytes, vec4, p,
+                                                           gbins + (size_t)s0 * R * S, tickets + s0, out_desc + (size_t)s0 * R * S, out_keys + (size_t)s0 * R,
+                                                           out_knorm + s0, kn2max, out_ring, out_sector);
+        cudaError_t el = cudaGetLastError();
+        if (el != cudaSuccess) return el;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t scl_launch_ring_keys(const float* desc_dev, int n, int R, int S, float* keys, float* knorm, float* kn2max, double* cstat,

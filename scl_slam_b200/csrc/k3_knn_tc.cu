@@ -68,6 +68,8 @@ constexpr int kEpiThreads = 256;   /* 8 epilogue warps: query tile = (warp-4)/4,
 constexpr int kThreads = 384;
 constexpr int kNT = 256;           /* keys per tile: one TMA copy, one N = 256 accumulator per query tile */
 constexpr int kQPerCta = 256;
+constexpr int kSlotStride = 20;    /* ints per query in the slot array: K' (<= 16) range minima, then the query's DIRECT bound (below), 3 spare */
+constexpr int kDirect = 16;        /* index of the direct bound within a query's slots */
 constexpr int kNoThr = 0x7f7f7f7f; /* memset pattern of the slots: 3.39e38 = "nothing yet" */
 constexpr float kThrInit = 1.0e38f;
 
@@ -213,11 +215,39 @@ __global__ void __launch_bounds__(128) key_image_kernel(const float* __restrict_
     }
 }
 
-// A full hit queue is re-filtered with the threshold of the moment: groups queued under an earlier, looser bound whose
-// best score has risen to or above it can be dropped like any other key (they are >= the final cut). Rare, and kept
-// out of line so that the epilogue loop stays small.
-__device__ __noinline__ int compact_queue(uint4* q, int n, float thr)
+// A nearly full hit queue (rare on scattered databases; the rule on a trajectory, where every good key comes with a run of
+// near-duplicate neighbours in the same tile) is re-filtered. First a DIRECT bound is taken from the queue itself: its groups
+// are disjoint sets of keys, so the K-th smallest group minimum in it is undercut (or met) by K distinct keys of this range
+// alone and bounds the query's K-th best score from above — tight exactly when the best keys sit together, where the union
+// bound over range minima is loose. It is published for the whole query (atomicMin on the query's direct-bound word: the
+// service warps fold it into every range's threshold and the re-rank into its cut) and applied here; then groups queued
+// under an earlier, looser threshold whose best score is not below the new one are dropped like any other key.
+__device__ __noinline__ int compact_queue(uint4* q, int n, float thr, int K, int* direct_word, float* thr_out)
 {
+    float best[16];                                  /* the K smallest group minima so far, ascending (K <= 14) */
+#pragma unroll
+    for (int i = 0; i < 16; i++) best[i] = kThrInit;
+    for (int e = 0; e < n; e++) {
+        const uint4 a = __ldcg(q + 2 * e), b4 = __ldcg(q + 2 * e + 1);
+        const float g[4] = {__uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w), __uint_as_float(b4.x)};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float v = g[j];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {           /* bubble v through the sorted list (registers: no dynamic indexing) */
+                if (i < K) { const float lo = fminf(best[i], v); v = fmaxf(best[i], v); best[i] = lo; }
+            }
+        }
+    }
+    float kth = kThrInit;
+#pragma unroll
+    for (int i = 0; i < 16; i++) if (i == K - 1) kth = best[i];
+    if (kth < kThrInit) {
+        /* groups whose minimum is <= kth must stay: the threshold is the next float above it */
+        const float t = __int_as_float(__float_as_int(kth) + (kth >= 0.0f ? 1 : -1));
+        const float tt = kth == 0.0f ? 1.0e-45f : t;
+        if (tt < thr) { thr = tt; atomicMin(direct_word, ordered_int(tt)); }
+    }
     int w = 0;
     for (int e = 0; e < n; e++) {
         const uint4 a = __ldcg(q + 2 * e), b4 = __ldcg(q + 2 * e + 1);
@@ -227,6 +257,7 @@ __device__ __noinline__ int compact_queue(uint4* q, int n, float thr)
             w++;
         }
     }
+    *thr_out = thr;
     return w;
 }
 
@@ -238,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     int* __restrict__ slots /* [Q][K'] range minima by range % K' (ordered-int image) */,
     uint4* __restrict__ hq /* [Q][n_ranges][kQueueCap][2] hit queues: (first key of the chunk, best scores of its four groups) */, int* __restrict__ hq_cnt /* [Q][n_ranges] */,
     int* __restrict__ dbg /* null, or developer counters */, int dev_flags /* SCL_TC_FLAGS: timing experiments, results are then wrong */,
-    int kp /* K' of this launch: 12 or 16 */, int NS /* key tiles in flight: 2 .. C::NSTAGE (fewer leave shared memory to kernels of other lanes) */)
+    int kp /* K' of this launch: 12 or 16 */, int K /* neighbours asked for */, int NS /* key tiles in flight: 2 .. C::NSTAGE (fewer leave shared memory to kernels of other lanes) */)
 {
     using C = TcCfg<R>;
     constexpr int NSMAX = C::NSTAGE;
@@ -319,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         int n_slow = 0;                                 /* developer counter (SCL_TC_TIMES) */
         float thr = (live && !(dev_flags & 1)) ? kThrInit : -kThrInit;        /* rows beyond Q never queue anything */
         float published = kThrInit;
-        int* my_slot = slots + (size_t)(live ? qi : 0) * kKPrime + (range % kp);
+        int* my_slot = slots + (size_t)(live ? qi : 0) * kSlotStride + (range % kp);
         volatile int* my_sthr = sthr + qt * 128 + row;
         uint4* my_q = hq + ((size_t)(live ? qi : 0) * n_ranges + range) * (size_t)(2 * kQueueCap);
         // The four epilogue warps of a query tile are coupled through the accumulator hand-off (it is refilled only when all
@@ -420,7 +451,13 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             /* a new range minimum feeds the union bound (tiles wholly below key_hi only; thr is -inf for rows beyond Q) */
             if (key0 + kNT <= key_hi && tile_min < fminf(thr, published)) { published = tile_min; atomicMin(my_slot, ordered_int(tile_min)); }
             if (n_hit > kQueueCap - kNT / 32) {          /* no room for another tile's worth of chunks: compact (rare) */
-                n_hit = compact_queue(my_q, n_hit, thr);
+                float thr_new;
+                const int before = n_hit;
+                n_hit = compact_queue(my_q, n_hit, thr, K, slots + (size_t)(live ? qi : 0) * kSlotStride + kDirect, &thr_new);
+#ifdef SCL_DEV_SWITCHES
+                if (n_hit > kQueueCap - kNT / 32) printf("overflow q %d range %d tile %d of %d: %d -> %d entries, thr %g -> %g, shared bound %g\n", qi, range, it, n_tiles, before, n_hit, thr, thr_new, ordered_float(*my_sthr));
+#endif
+                thr = thr_new;
                 if (n_hit > kQueueCap - kNT / 32) { overflowed = true; n_hit = 0; thr = -kThrInit; }   /* sticky: nothing more is queued, the query is redone exactly */
             }
             if (live) next_thr = ordered_float(*my_sthr);
@@ -460,14 +497,16 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                 const int j = (warp - 2) * 128 + 32 * k + lane;
                 const int qi = q_base + j;
                 if (qi < Q) {
-                    const int4* p = reinterpret_cast<const int4*>(slots + (size_t)qi * kKPrime);
+                    const int4* p = reinterpret_cast<const int4*>(slots + (size_t)qi * kSlotStride);
                     int4 v[kKPrime / 4];
 #pragma unroll
                     for (int i = 0; i < kKPrime / 4; i++) v[i] = __ldcg(p + i);
+                    const int direct = __ldcg(slots + (size_t)qi * kSlotStride + kDirect);
                     int m = (int)0x80000000;
 #pragma unroll
                     for (int i = 0; i < kKPrime / 4; i++) if (4 * i < kp) m = max(m, max(max(v[i].x, v[i].y), max(v[i].z, v[i].w)));
-                    if (m < 0x7f000000) sthr[j] = m;     /* all K' slots filled: a valid bound */
+                    m = min(m, direct);                  /* the union bound (valid once all K' slots are filled) or a range's direct bound */
+                    if (m < 0x7f000000) sthr[j] = m;
                 }
             }
             sweeps++;
@@ -583,7 +622,8 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
     const unsigned lt_mask = (1u << lane) - 1u;
     const float inf = __int_as_float(0x7f800000);
     /* first trip: slots, the query's key, the queue counts, the largest key norm: all independent */
-    int gt = lane < kp ? __ldg(slots + (size_t)qi * kKPrime + lane) : (int)0x80000000;
+    int gt = lane < kp ? __ldg(slots + (size_t)qi * kSlotStride + lane) : (int)0x80000000;
+    const int direct = __ldg(slots + (size_t)qi * kSlotStride + kDirect);
     const float qv = lane < R ? __ldg(qkeys + (size_t)qi * R + lane) : 0.0f;
     const float qv2 = (R > 32 && lane + 32 < R) ? __ldg(qkeys + (size_t)qi * R + lane + 32) : 0.0f;
     const float knmax = __ldg(kn2max);
@@ -597,11 +637,11 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
     /* The cut: the query's final union bound (the maximum of its K' slots). Every group that was not queued had all its
      * scores >= it, so every key scoring below it sits in a queued group; queued groups whose best score is above it
      * cannot be certified anyway and are skipped: about K' groups survive. */
-    gt = __reduce_max_sync(0xffffffffu, gt);
+    gt = min(__reduce_max_sync(0xffffffffu, gt), direct);   /* every threshold a thread applied was >= this */
     const float cut = gt < 0x7f000000 ? ordered_float(gt) : inf;
     /* housekeeping that used to be two memsets per batch: this query's slots go back to "no key yet" for the next launch
      * (nobody else reads them), and the fail counter of the NEXT call is zeroed (calls alternate between two counters) */
-    if (lane < kKPrime) slots_rw[(size_t)qi * kKPrime + lane] = kNoThr;
+    if (lane < kSlotStride) slots_rw[(size_t)qi * kSlotStride + lane] = kNoThr;
     if (qi == 0 && lane == 0) *next_fail_count = 0;
     if (lane < R) s_q[lane] = qv;
     if (R > 32 && lane + 32 < R) s_q[lane + 32] = qv2;
@@ -668,10 +708,11 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
      * m_K is undercut by K keys: the K-th nearest neighbour has exact d2 <= m_K + |q|^2 + eps, and a group whose minimum
      * exceeds m_K + 2 eps holds no key that can beat it. About K of the ~3 K' groups remain. Groups that straddle the
      * search bound may owe their minimum to a key outside it: they do not vote for m_K and are always kept. */
-    if (METRIC == 0 && n_grp > K && n_grp <= 128) {
-        unsigned v[4]; bool whole[4];
+    if (METRIC == 0 && n_grp > K && n_grp <= kMaxGroups) {
+        constexpr int kPer = kMaxGroups / 32;          /* groups per lane */
+        unsigned v[kPer]; bool whole[kPer];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < kPer; j++) {
             const int c = lane + 32 * j;
             whole[j] = c < n_grp && s_key[c] + 7 < n_db;
             /* scores can be negative: order-preserving unsigned image of the float */
@@ -680,7 +721,9 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
         }
         unsigned mk = 0xffffffffu; int have = 0;
         for (int r = 0; r < K; r++) {
-            const unsigned loc = min(min(v[0], v[1]), min(v[2], v[3]));
+            unsigned loc = v[0];
+#pragma unroll
+            for (int j = 1; j < kPer; j++) loc = min(loc, v[j]);
             const unsigned w = __reduce_min_sync(0xffffffffu, loc);
             if (w == 0xffffffffu) break;
             /* remove ONE holder of the minimum (equal minima are distinct keys and count separately) */
@@ -688,7 +731,7 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
             if (lane == __ffs(holders) - 1) {
                 bool done = false;
 #pragma unroll
-                for (int j = 0; j < 4; j++) if (!done && v[j] == w) { v[j] = 0xffffffffu; done = true; }
+                for (int j = 0; j < kPer; j++) if (!done && v[j] == w) { v[j] = 0xffffffffu; done = true; }
             }
             mk = w; have++;
         }
@@ -698,7 +741,7 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
             /* compact the list in place: positions only move down, lanes work in index order */
             int n_new = 0;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < kPer; j++) {
                 const int c = lane + 32 * j;
                 const int key = c < n_grp ? s_key[c] : 0; const float g = c < n_grp ? s_g[c] : 0.0f;
                 const bool keep = c < n_grp && (!whole[j] || g <= lim);
@@ -836,6 +879,7 @@ int scl_knn_tc_ranges(int Q)
 }
 int scl_knn_tc_max_batch() { return 1024; }          /* larger batches are cut into launches of this many queries */
 int scl_knn_tc_kprime() { return kKPrime; }
+int scl_knn_tc_slot_stride() { return kSlotStride; }
 size_t scl_knn_tc_queue_bytes() { return (size_t)kQueueCap * 32; }          /* per (query, range) */
 size_t scl_knn_tc_image_bytes(int R, int n_keys)
 {
@@ -864,7 +908,7 @@ static constexpr int dev_flags_env() { return 0; }
 
 template <int R>
 static cudaError_t launch_tc(const float* qkeys, int Q, const unsigned char* img, int n_db, int n_ranges, int* slots,
-                              uint4* hq, int* hq_cnt, int* dbg, int kp, int stages, cudaStream_t stream)
+                              uint4* hq, int* hq_cnt, int* dbg, int kp, int K, int stages, cudaStream_t stream)
 {
     using C = TcCfg<R>;
     if (stages < 2) stages = 2;
@@ -895,8 +939,8 @@ static cudaError_t launch_tc(const float* qkeys, int Q, const unsigned char* img
     const int dev_flags = dev_flags_env();
     if (want_times) { cudaMalloc(&times, (size_t)nb * 16 * sizeof(long long)); cudaMemsetAsync(times, 0, (size_t)nb * 128, stream); }
     if (dev_flags & 64) {}
-    else if (want_times) knn_tc_kernel<R, true><<<nb, kThreads, smem_bytes, stream>>>(qkeys, Q, img, n_db, n_ranges, times, slots, hq, hq_cnt, dbg, dev_flags, kp, stages);
-    else knn_tc_kernel<R, false><<<nb, kThreads, smem_bytes, stream>>>(qkeys, Q, img, n_db, n_ranges, nullptr, slots, hq, hq_cnt, dbg, dev_flags, kp, stages);
+    else if (want_times) knn_tc_kernel<R, true><<<nb, kThreads, smem_bytes, stream>>>(qkeys, Q, img, n_db, n_ranges, times, slots, hq, hq_cnt, dbg, dev_flags, kp, K, stages);
+    else knn_tc_kernel<R, false><<<nb, kThreads, smem_bytes, stream>>>(qkeys, Q, img, n_db, n_ranges, nullptr, slots, hq, hq_cnt, dbg, dev_flags, kp, K, stages);
     if (want_times) {
         std::vector<long long> h((size_t)nb * 16);
         cudaStreamSynchronize(stream);
@@ -911,7 +955,7 @@ static cudaError_t launch_tc(const float* qkeys, int Q, const unsigned char* img
     }
 #else
     SCL_PREFER_SMEM((knn_tc_kernel<R, false>));
-    knn_tc_kernel<R, false><<<nb, kThreads, smem_bytes, stream>>>(qkeys, Q, img, n_db, n_ranges, nullptr, slots, hq, hq_cnt, dbg, 0, kp, stages);
+    knn_tc_kernel<R, false><<<nb, kThreads, smem_bytes, stream>>>(qkeys, Q, img, n_db, n_ranges, nullptr, slots, hq, hq_cnt, dbg, 0, kp, K, stages);
 #endif
     return cudaGetLastError();
 }
@@ -928,7 +972,7 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
     if (init_state) {
         /* first use of these buffers (or a call that was cut short): afterwards the re-rank kernel keeps them clean */
         err = cudaMemsetAsync(fail_count, 0, sizeof(int), stream);
-        if (err == cudaSuccess) err = cudaMemsetAsync(ws.slots, 0x7f, (size_t)(Q < max_b ? Q : max_b) * kKPrime * 4, stream);     /* 3.39e38: "no key yet" */
+        if (err == cudaSuccess) err = cudaMemsetAsync(ws.slots, 0x7f, (size_t)(Q < max_b ? Q : max_b) * kSlotStride * 4, stream);     /* 3.39e38: "no key yet" */
         if (err != cudaSuccess) return err;
     }
     for (int q0 = 0; q0 < Q; q0 += max_b) {
@@ -936,8 +980,8 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
         const int n_ranges = scl_knn_tc_ranges(Qc);
         if ((size_t)Qc * n_ranges > ws.capacity) return cudaErrorInvalidValue;
         const float* qk = qkeys + (size_t)q0 * R;
-        if (R == 20) err = launch_tc<20>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint4*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), kprime_for(K), stages, stream);
-        else err = launch_tc<40>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint4*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), kprime_for(K), stages, stream);
+        if (R == 20) err = launch_tc<20>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint4*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), kprime_for(K), K, stages, stream);
+        else err = launch_tc<40>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint4*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), kprime_for(K), K, stages, stream);
         if (err != cudaSuccess) return err;
 #define SCL_RERANK(M, RR)                                                                                                              \
     SCL_PREFER_SMEM((knn_rerank_kernel<M, RR>));                                                                                          \
@@ -958,10 +1002,10 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
         cudaStreamSynchronize(stream);
         {
             const int Qc = Q < max_b ? Q : max_b;
-            std::vector<int> sl((size_t)Qc * kKPrime);
+            std::vector<int> sl((size_t)Qc * kSlotStride);
             cudaMemcpy(sl.data(), ws.slots, sl.size() * 4, cudaMemcpyDeviceToHost);
             int per_slot[kKPrime] = {0};
-            for (int q = 0; q < Qc; q++) for (int k = 0; k < kKPrime; k++) if (sl[(size_t)q * kKPrime + k] >= 0x7f000000) per_slot[k]++;
+            for (int q = 0; q < Qc; q++) for (int k = 0; k < kKPrime; k++) if (sl[(size_t)q * kSlotStride + k] >= 0x7f000000) per_slot[k]++;
             fprintf(stderr, "[tc slots of the last launch, unfilled per slot]");
             for (int k = 0; k < kKPrime; k++) fprintf(stderr, " %d", per_slot[k]);
             fprintf(stderr, "\n");

@@ -37,7 +37,7 @@ cudaError_t scl_launch_knn_exact(const float* qkeys, int Q, const float* keys, i
 struct KnnTcWorkspace {
     uint32_t* hq;        // [Qc][ranges] hit queues of scl_knn_tc_queue_bytes() each (Qc = min(Q, scl_knn_tc_max_batch()))
     int* hq_cnt;         // [Qc][ranges] groups queued
-    int* slots;          // [Qc][K'] range minima by range % K' (K' = scl_knn_tc_kprime())
+    int* slots;          // [Qc][scl_knn_tc_slot_stride()]: K' range minima by range % K' (K' <= scl_knn_tc_kprime()), then the query's direct bound
     float* err_probe;    // null, or one float raised to the largest |prefilter score error| / eps seen (tests)
     size_t capacity;     // in (query, range) pairs
 };
@@ -45,6 +45,7 @@ bool scl_knn_tc_supported(int R);
 int scl_knn_tc_ranges(int Q);
 int scl_knn_tc_max_batch();
 int scl_knn_tc_kprime();
+int scl_knn_tc_slot_stride();       /* ints per query in KnnTcWorkspace::slots */
 size_t scl_knn_tc_queue_bytes();
 size_t scl_knn_tc_image_bytes(int R, int n_keys);
 cudaError_t scl_launch_key_image(const float* keys, const float* knorm, int k_lo, int k_hi, int R, unsigned char* img, cudaStream_t stream);
