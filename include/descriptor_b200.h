@@ -239,4 +239,87 @@ private:
 	int rs_;
 };
 
+/*
+ * The same six virtuals with the keyframe database sharded by keyframe index over several GPUs of the box
+ * (scl_create_sharded, include/scl_engine.h): still ONE object behind distributed_mapping's
+ * std::unique_ptr<scan_descriptor> (distributedMapping.h:333,402-405). devices = CUDA device ordinals; keys, ids and
+ * results mean exactly what they mean in scan_context_descriptor_b200.
+ */
+class scan_context_descriptor_b200_sharded : public scan_descriptor
+{
+public:
+	scan_context_descriptor_b200_sharded(const std::vector<int>& devices, int numRing = 20, int numSector = 60, int numCandidates = 3,
+		double distThres = 0.14, double lidarHeight = 1.65, double maxRadius = 80.0, int numExcludeRecent = 100,
+		int treeMakingPeriod = 10, double searchRatio = 0.1) : sharded_(nullptr), rs_(numRing * numSector)
+	{
+		scl_params p;
+		scl_default_params(&p);
+		p.num_ring = numRing; p.num_sector = numSector; p.num_candidates = numCandidates; p.dist_thres = distThres;
+		p.lidar_height = lidarHeight; p.max_radius = maxRadius; p.num_exclude_recent = numExcludeRecent;
+		p.tree_making_period = treeMakingPeriod; p.search_ratio = searchRatio;
+		const int rc = scl_create_sharded(&p, (int)devices.size(), devices.data(), 1024, numCandidates < 10 ? 10 : numCandidates, &sharded_);
+		if(rc != SCL_OK)
+		{
+			std::fprintf(stderr, "[scan_context_descriptor_b200_sharded] scl_create_sharded failed (%d): CUDA devices with peer access are required, there is no CPU fallback\n", rc);
+			std::abort();
+		}
+	}
+
+	~scan_context_descriptor_b200_sharded() { if(sharded_) scl_sharded_destroy(sharded_); }
+	scan_context_descriptor_b200_sharded(const scan_context_descriptor_b200_sharded&) = delete;
+	scan_context_descriptor_b200_sharded& operator=(const scan_context_descriptor_b200_sharded&) = delete;
+
+	std::vector<float> makeAndSaveDescriptorAndKey(const pcl::PointCloud<pcl::PointXYZI>& scan, const int8_t robot, const int index)
+	{
+		std::vector<float> vT(rs_, 0.0f);
+		const void* pts = scan.points.empty() ? nullptr : static_cast<const void*>(&scan.points[0]);
+		if(!check(scl_sharded_build_insert(sharded_, pts, (int)scan.points.size(), (int)sizeof(pcl::PointXYZI), robot, index, vT.data()), "makeAndSaveDescriptorAndKey"))
+		{
+			/* keep the key space dense (see scan_context_descriptor_b200::keep_keys_dense) */
+			std::fill(vT.begin(), vT.end(), 0.0f);
+			if(scl_sharded_insert_batch(sharded_, vT.data(), 1, &robot, &index) != SCL_OK) std::abort();
+		}
+		return vT;
+	}
+
+	void saveDescriptorAndKey(const float* descriptorMat, const int8_t robot, const int index)
+	{
+		check(scl_sharded_insert_batch(sharded_, descriptorMat, 1, &robot, &index), "saveDescriptorAndKey");
+	}
+
+	std::pair<int, float> detectIntraLoopClosureID(const int currentPtr)
+	{
+		int id = -1; float second = 0.0f;
+		check(scl_sharded_query_intra(sharded_, currentPtr, &id, &second), "detectIntraLoopClosureID");
+		return std::make_pair(id, second);
+	}
+
+	std::pair<int, float> detectInterLoopClosureID(const int currentPtr)
+	{
+		int id = -1; float second = 0.0f;
+		check(scl_sharded_query_inter(sharded_, currentPtr, &id, &second), "detectInterLoopClosureID");
+		return std::make_pair(id, second);
+	}
+
+	std::pair<int8_t, int> getIndex(const int key)
+	{
+		int8_t robot = -1; int index = -1;
+		check(scl_sharded_get_index(sharded_, key, &robot, &index), "getIndex");
+		return std::make_pair(robot, index);
+	}
+
+	int getSize(const int idIn = -1) { (void)idIn; return scl_sharded_size(sharded_); }
+
+private:
+	bool check(int rc, const char* what)
+	{
+		if(rc != SCL_OK)
+			std::fprintf(stderr, "[scan_context_descriptor_b200_sharded] %s failed (%d): %s\n", what, rc, scl_sharded_last_error(sharded_));
+		return rc == SCL_OK;
+	}
+
+	scl_sharded* sharded_;
+	int rs_;
+};
+
 #endif

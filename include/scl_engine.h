@@ -209,7 +209,7 @@ int scl_xchg_close(scl_engine* e);
  *   scl_shard_query_submit: host buffers, pipelined like scl_query_batch_submit (wait with scl_query_batch_wait). Every
  *                           rank passes the same whole batch in q->q_desc but uploads only its 1/world of the rows; a
  *                           gather kernel stores them into every peer's query area over NVLink, so the host link carries each
- *                           descriptor once. q->Q must be a multiple of the world size. */
+ *                           descriptor once. q->q_ids (optional, host) are the queries' own keys for the self-skip rule. */
 int scl_shard_query_dev(scl_engine* e, int lane, const scl_batch_query* q, scl_batch_result* r);
 int scl_shard_query_submit(scl_engine* e, const scl_batch_query* q, scl_batch_result* r, int* ticket);
 
@@ -287,6 +287,51 @@ int scl_build_insert_filtered(scl_engine* e, const void* pts, int n, int stride_
  * the clouds are concatenated in order and down-sampled with scl_voxel_grid(leaf); leaf <= 0 skips the down-sampling. */
 int scl_assemble_submap(scl_engine* e, const void* pts, const int* offsets, int n_clouds, int stride_bytes, const float* poses6,
                         float leaf, float* out_xyzi, int* n_out);
+
+/* ---- one database over the GPUs of a box, in one process (csrc/sharded.cu) ------------------------------------------
+ * distributed_mapping constructs ONE descriptor object (distributedMapping.h:333,402-405). scl_create_sharded is that
+ * object with the keyframe database sharded by keyframe index over `ndev` devices (key mod ndev; one engine per device,
+ * their exchange buffers mapped into each other by peer access). Keys, ids and results mean exactly what they mean on
+ * a single engine. max_q / max_k size the exchange buffers (largest batch and candidate count of a query). Queries take
+ * HOST buffers; up to scl_num_lanes() batches may be in flight (submit / wait, tickets in order).
+ * With ndev = 1 it is a plain engine behind the same calls. */
+typedef struct scl_sharded scl_sharded;
+int scl_create_sharded(const scl_params* p, int ndev, const int* devs, int max_q, int max_k, scl_sharded** out);
+int scl_sharded_destroy(scl_sharded* s);
+const char* scl_sharded_last_error(scl_sharded* s);
+int scl_sharded_world(scl_sharded* s);
+scl_engine* scl_sharded_engine(scl_sharded* s, int rank);       /* the shard's engine (descriptor build, ICP, ... are per device) */
+int scl_sharded_size(scl_sharded* s);                            /* getSize, descriptor.h:1763-1766 */
+int scl_sharded_get_index(scl_sharded* s, int key, int8_t* robot, int* index);   /* getIndex, :1758-1761 */
+int scl_sharded_get_descriptor(scl_sharded* s, int key, float* out_desc);
+int scl_sharded_insert_batch(scl_sharded* s, const float* descs, int n, const int8_t* robots, const int32_t* indices);   /* saveDescriptorAndKey */
+int scl_sharded_build_insert(scl_sharded* s, const void* pts, int n, int stride_bytes, int8_t robot, int index, float* out_desc);   /* makeAndSaveDescriptorAndKey */
+int scl_sharded_query_batch(scl_sharded* s, const scl_batch_query* q, scl_batch_result* r);
+int scl_sharded_query_submit(scl_sharded* s, const scl_batch_query* q, scl_batch_result* r, int* ticket);
+int scl_sharded_query_wait(scl_sharded* s, int ticket);
+int scl_sharded_query_intra(scl_sharded* s, int cur, int* id, float* second);    /* detectIntraLoopClosureID, :1613-1674 */
+int scl_sharded_query_inter(scl_sharded* s, int cur, int* id, float* second);    /* detectInterLoopClosureID, :1676-1756 */
+
+/* ---- the intra-robot verification as one call (distributedMapping.h:1096-1143) ---------------------------------------
+ * scl_store_keyframe_cloud keeps keyframe `key`'s cloud on the device (robots[id].keyFrameArray of the reference; keys are
+ * stored in order, key = number stored so far). scl_verify_intra then does what performIntraLoopClosure does after the
+ * descriptor stage: loopFindNearKeyframes(cur, 0) and loopFindNearKeyframes(pre, search_num) (:1163-1186: every cloud moved
+ * by its pose, merged, voxel-filtered with `leaf`), the size gates (< 300 / < 1000 points: no loop, :1102), the ICP of
+ * :1108-1121 and the fitness gate of :1122 — without a cloud leaving the device. poses6 = x, y, z, roll, pitch, yaw of
+ * every keyframe (cloudKeyPoses6D). out->T is icp.getFinalTransformation() (row-major 4x4); the pose between the two
+ * keyframes for loop_info follows with scl_wire_loop_between(out->T, pose_cur, pose_pre, ...) (include/scl_wire.h). */
+typedef struct {
+    int accepted;      /* converged and fitness <= threshold */
+    int converged;
+    int iterations;
+    float fitness;     /* icp.getFitnessScore(), the loop's noise (:1151) */
+    float T[16];
+    int n_src, n_tgt;  /* points of the two down-sampled clouds */
+} scl_intra_result;
+int scl_store_keyframe_cloud(scl_engine* e, int key, const void* pts, int n, int stride_bytes);
+int scl_keyframe_clouds(scl_engine* e);
+int scl_verify_intra(scl_engine* e, int key_cur, int key_pre, int search_num, const float* poses6, int n_poses, float leaf,
+                     const scl_icp_params* icp, float fitness_threshold, scl_intra_result* out);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libscl_b200.so")
-SOURCES = ["engine.cu", "k1_polar.cu", "k3_knn.cu", "k4_scdist.cu", "k5_icp.cu", "k3_knn_tc.cu", "k6_cloud.cu", "wire.cu", "k7_exchange.cu"]
+SOURCES = ["engine.cu", "k1_polar.cu", "k3_knn.cu", "k4_scdist.cu", "k5_icp.cu", "k3_knn_tc.cu", "k6_cloud.cu", "wire.cu", "k7_exchange.cu", "sharded.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--fmad=true"]
 

@@ -20,6 +20,11 @@ struct SclOncePerDevice {
         return !(seen.fetch_or(bit) & bit);
     }
 };
+// Load a kernel's code on the current device now. With CUDA's lazy module loading the FIRST launch of a kernel may need to
+// synchronise the context; a host thread that has just enqueued an exchange kernel (which waits for a peer) and then
+// launches a not-yet-loaded kernel on the same device would block before it can give the peer its work. scl_create loads
+// every kernel of the query path up front (scl_preload_*), so no launch on that path ever synchronises.
+#define SCL_TOUCH(kernel) do { cudaFuncAttributes _a; (void)cudaFuncGetAttributes(&_a, kernel); } while (0)
 #define SCL_PREFER_SMEM(kernel)                                                                                              \
     do {                                                                                                                     \
         static SclOncePerDevice _once;                                                                                       \

@@ -11,6 +11,7 @@
 // (robot, index) metadata stays on the host (descriptor.h:1599,1758-1761).
 // There is no CPU fallback anywhere in this file: every data-path call launches kernels.
 #include "engine_internal.h"
+#include "common.cuh"
 
 namespace {
 
@@ -431,6 +432,11 @@ int scl_create(const scl_params* p, int device, scl_engine** out)
     e->search_radius = (int)std::round(0.5 * p->search_ratio * p->num_sector);
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return SCL_ERR_CUDA; }
     if (cudaMalloc(&e->d_kn2max, 64) != cudaSuccess || cudaMemset(e->d_kn2max, 0, 64) != cudaSuccess) { delete e; return SCL_ERR_CUDA; }
+    {
+        /* once per device: load the query path's kernels now, so that no launch on it ever has to synchronise the context */
+        static SclOncePerDevice once;
+        if (once.first()) { scl_preload_k1(); scl_preload_k3(); scl_preload_k3_tc(); scl_preload_k4(); scl_preload_k7(); (void)cudaGetLastError(); }
+    }
     *out = e;
     return SCL_OK;
 }
@@ -453,7 +459,7 @@ int scl_destroy(scl_engine* e)
         if (e->xchg_buf) cudaFree(e->xchg_buf);
         cudaFree(e->d_desc); cudaFree(e->d_keys); cudaFree(e->d_knorm); cudaFree(e->d_cstat); cudaFree(e->d_kn2max); cudaFree(e->d_kimg);
         DevBuf* bufs[] = {&e->pts, &e->offsets, &e->gbins, &e->tickets, &e->stage_desc, &e->stage_keys, &e->stage_knorm,
-                          &e->bins_ring, &e->bins_sector, &e->icp_src, &e->icp_tgt, &e->icp_raw, &e->icp_acc, &e->icp_nn,
+                          &e->bins_ring, &e->bins_sector, &e->kf_arena, &e->icp_src, &e->icp_tgt, &e->icp_raw, &e->icp_acc, &e->icp_nn,
                           &e->icp_grid[0][0], &e->icp_grid[0][1], &e->icp_grid[0][2], &e->icp_grid[0][3], &e->icp_grid[0][4],
                           &e->icp_grid[1][0], &e->icp_grid[1][1], &e->icp_grid[1][2], &e->icp_grid[1][3], &e->icp_grid[1][4]};
         for (DevBuf* b : bufs) b->release();
@@ -858,11 +864,41 @@ int scl_xchg_bytes(scl_engine* e, int world, int max_q, int max_k, uint64_t* byt
     return SCL_OK;
 }
 
+namespace {
+// Every buffer a sharded step of up to max_q queries and max_k candidates touches on a lane, allocated NOW: a step must
+// never allocate (cudaMalloc / cudaFree may synchronise the device) between launching an exchange kernel, which waits for
+// a peer, and giving that peer its work — with one host thread driving several devices that would be a deadlock.
+int prealloc_lane(scl_engine* e, Lane& ln, int max_q, int max_k)
+{
+    const size_t Q = (size_t)max_q, QK = Q * max_k, R = e->p.num_ring, S = e->p.num_sector;
+    int rc = lane_begin(e, ln); if (rc) return rc;
+    CK(ln.qkeys.ensure(Q * R * 4)); CK(ln.qknorm.ensure(Q * 4)); CK(ln.qstat.ensure(Q * 2 * S * 8)); CK(ln.qlocal.ensure(Q * 4)); CK(ln.qids.ensure(Q * 4));
+    CK(ln.cand_local.ensure(QK * 4)); CK(ln.cand_ids.ensure(QK * 4)); CK(ln.cand_d2.ensure(QK * 4)); CK(ln.cand_dist.ensure(QK * 8)); CK(ln.cand_shift.ensure(QK * 4));
+    CK(ln.best_id.ensure(Q * 4)); CK(ln.best_dist.ensure(Q * 8)); CK(ln.best_shift.ensure(Q * 4));
+    CK(ln.part_ids.ensure(Q * 256 * max_k * 4)); CK(ln.part_d2.ensure(Q * 256 * max_k * 4));           /* up to 256 key splits in the exact kernel */
+    CK(ln.knn_tickets.ensure((Q / 128 + 16) * 4 + Q * 4));
+    CK(cudaMemsetAsync(ln.knn_tickets.p, 0, ln.knn_tickets.cap, ln.stream));
+    const int Qc = max_q < scl_knn_tc_max_batch() ? max_q : scl_knn_tc_max_batch();
+    const size_t pairs = (size_t)Qc * scl_knn_tc_ranges(Qc);
+    /* the tensor-core kNN runs from four queries up; one query group uses all 148 ranges */
+    const size_t pairs_max = std::max(pairs, (size_t)std::min(Qc, 256) * SCL_NUM_SMS);
+    CK(ln.tc_queues.ensure(pairs_max * scl_knn_tc_queue_bytes())); CK(ln.tc_queue_cnt.ensure(pairs_max * 4));
+    CK(ln.tc_fail_list.ensure(Q * 4)); CK(ln.tc_fail_count.ensure(128)); CK(ln.tc_slots.ensure((size_t)Qc * scl_knn_tc_slot_stride() * 4));
+    CK(cudaMemsetAsync(ln.tc_fail_count.p, 0, 128, ln.stream));
+    ln.tc_state_clean = false;
+    CK(ln.x_blob1.ensure(QK * 8)); CK(ln.x_blob2.ensure(QK * 12)); CK(ln.x_ids.ensure(QK * 4)); CK(ln.x_d2.ensure(QK * 4));
+    if (!ln.done) CK(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+    CK(cudaStreamSynchronize(ln.stream));
+    return SCL_OK;
+}
+} // namespace
+
 int scl_xchg_create(scl_engine* e, int world, int max_q, int max_k, unsigned char* handle64)
 {
     LOCK();
     if (world < 2 || world > 16 || max_q < 1 || max_k < 1 || max_k > 32 || !handle64) FAIL(SCL_ERR_INVALID, "bad arguments");
     if (e->xchg_buf) FAIL(SCL_ERR_INVALID, "exchange buffer exists already");
+    for (int l = 0; l < scl_engine::kLanes; l++) { int rc = prealloc_lane(e, e->lanes[l], max_q, max_k); if (rc) return rc; }
     e->xchg_bytes = xchg_layout(e, world, max_q, max_k);
     e->xchg_qk = max_q * max_k; e->xchg_q = max_q;
     CK(cudaMalloc(&e->xchg_buf, e->xchg_bytes));
@@ -980,7 +1016,7 @@ int scl_shard_query_submit(scl_engine* e, const scl_batch_query* q, scl_batch_re
     if (!q || !r || !ticket || !q->q_desc) FAIL(SCL_ERR_INVALID, "a sharded query needs host descriptors, a result and a ticket");
     if (!e->xchg_open) FAIL(SCL_ERR_INVALID, "exchange not open (scl_xchg_create / scl_xchg_open)");
     const int Q = q->Q, K = q->K, world = e->world, rank = e->rank;
-    if (Q < 1 || Q > e->xchg_q || Q % world) FAIL(SCL_ERR_INVALID, "Q must be a multiple of the world size within the size given to scl_xchg_create");
+    if (Q < 1 || Q > e->xchg_q) FAIL(SCL_ERR_INVALID, "Q must be within the size given to scl_xchg_create");
     Lane* lnp = nullptr; int t = 0;
     int rc = pipe_take_lane(e, &lnp, &t); if (rc) return rc;
     Lane& ln = *lnp;
@@ -992,9 +1028,17 @@ int scl_shard_query_submit(scl_engine* e, const scl_batch_query* q, scl_batch_re
     const XchgView& x = e->xchg[lane];
     const int seq_next = ln.xseq + 1;
     unsigned char* area = static_cast<unsigned char*>(e->xchg_buf) + x.data_off[2] + (size_t)(seq_next & 1) * x.slot_bytes[2];
-    const int rows = Q / world, row0 = rank * rows;
-    CK(cudaMemcpyAsync(area + (size_t)row0 * RS4, reinterpret_cast<const unsigned char*>(q->q_desc) + (size_t)row0 * RS4, (size_t)rows * RS4,
-                       cudaMemcpyHostToDevice, ln.stream));
+    const int per = (Q + world - 1) / world;
+    const int row0 = rank * per < Q ? rank * per : Q, rows = Q - row0 < per ? Q - row0 : per;     /* the last ranks may have nothing to bring */
+    if (rows > 0)
+        CK(cudaMemcpyAsync(area + (size_t)row0 * RS4, reinterpret_cast<const unsigned char*>(q->q_desc) + (size_t)row0 * RS4, (size_t)rows * RS4,
+                           cudaMemcpyHostToDevice, ln.stream));
+    const int32_t* di = nullptr;
+    if (q->q_ids) {                                   /* the keys of the queries (self-skip rule, descriptor.h:1731): a few bytes, every rank */
+        CK(ln.qids.ensure((size_t)Q * 4));
+        CK(cudaMemcpyAsync(ln.qids.p, q->q_ids, (size_t)Q * 4, cudaMemcpyHostToDevice, ln.stream));
+        di = ln.qids.as<int32_t>();
+    }
     /* the gather uses its own step counter space: exchange point 2 of step seq_next */
     CK(scl_launch_xchg_gather_queries(x, seq_next, area + (size_t)row0 * RS4, (size_t)row0 * RS4, (size_t)rows * RS4, ln.stream));
     const size_t QK = (size_t)Q * K;
@@ -1003,7 +1047,7 @@ int scl_shard_query_submit(scl_engine* e, const scl_batch_query* q, scl_batch_re
     CK(ln.cand_ids.ensure(QK * 4)); CK(ln.cand_d2.ensure(QK * 4));
     scl_batch_result d{ln.cand_ids.as<int32_t>(), ln.cand_d2.as<float>(), ln.cand_dist.as<double>(), ln.cand_shift.as<int32_t>(),
                        ln.best_id.as<int32_t>(), ln.best_dist.as<double>(), ln.best_shift.as<int32_t>()};
-    rc = shard_step(e, ln, lane, reinterpret_cast<const float*>(area), nullptr, Q, K, q->n_db, q->metric, &d); if (rc) return rc;
+    rc = shard_step(e, ln, lane, reinterpret_cast<const float*>(area), di, Q, K, q->n_db, q->metric, &d); if (rc) return rc;
     if (r->cand_ids) CK(cudaMemcpyAsync(r->cand_ids, d.cand_ids, QK * 4, cudaMemcpyDeviceToHost, ln.stream));
     if (r->cand_d2) CK(cudaMemcpyAsync(r->cand_d2, d.cand_d2, QK * 4, cudaMemcpyDeviceToHost, ln.stream));
     if (r->cand_dist) CK(cudaMemcpyAsync(r->cand_dist, d.cand_dist, QK * 8, cudaMemcpyDeviceToHost, ln.stream));
@@ -1188,6 +1232,107 @@ int scl_assemble_submap(scl_engine* e, const void* pts, const int* offsets, int 
         CK(cudaMemcpyAsync(out_xyzi, e->vg_world.p, (size_t)total * 16, cudaMemcpyDeviceToHost, e->stream));
     }
     CK(cudaStreamSynchronize(e->stream));
+    return SCL_OK;
+}
+
+// ---- device-resident keyframe clouds + the intra-robot verification as one call -------------------------------------------
+int scl_store_keyframe_cloud(scl_engine* e, int key, const void* pts, int n, int stride_bytes)
+{
+    LOCK();
+    if (n < 0 || (n > 0 && !pts)) FAIL(SCL_ERR_INVALID, "bad cloud");
+    if (stride_bytes < 16 || stride_bytes % 16) FAIL(SCL_ERR_UNSUPPORTED, "points must be 16-byte aligned x,y,z,intensity records");
+    if (key != (int)e->kf_off.size() - 1) FAIL(SCL_ERR_INVALID, "keyframe clouds are stored in key order (key = number stored so far), like keyFrameArray.push_back");
+    const size_t need = (e->kf_points + (size_t)n) * 16;
+    if (need > e->kf_arena.cap) {
+        /* grow the arena (append-only; doubling) keeping what is stored */
+        DevBuf bigger;
+        CK(bigger.ensure(need * 2 + (1 << 20)));
+        if (e->kf_points) CK(cudaMemcpyAsync(bigger.p, e->kf_arena.p, e->kf_points * 16, cudaMemcpyDeviceToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        e->kf_arena.release();
+        e->kf_arena = bigger;
+    }
+    if (n > 0) {
+        CK(e->vg_in.ensure((size_t)n * stride_bytes));
+        CK(cudaMemcpyAsync(e->vg_in.p, pts, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, e->stream));
+        CK(scl_launch_pack_xyzi(e->vg_in.p, n, stride_bytes, static_cast<unsigned char*>(e->kf_arena.p) + e->kf_points * 16, e->stream));
+        CK(cudaStreamSynchronize(e->stream));            /* the caller's cloud may go away */
+    }
+    e->kf_points += (size_t)n;
+    e->kf_off.push_back((int)e->kf_points);
+    return SCL_OK;
+}
+
+int scl_keyframe_clouds(scl_engine* e) { if (!e) return -1; std::lock_guard<std::mutex> lk(e->mu); return (int)e->kf_off.size() - 1; }
+
+namespace {
+// loopFindNearKeyframes (distributedMapping.h:1163-1186) on the stored clouds: keys key-search .. key+search (clipped), each
+// moved by its pose (transformPointCloud, :234-253), concatenated, down-sampled (downSizeFilterICP). Result: packed float4
+// in e->vg_out (leaf > 0) or e->vg_world (leaf <= 0), count in *n_out.
+int near_keyframes_dev(scl_engine* e, int key, int search, const float* poses6, int n_poses, float leaf, int* n_out, const void** where)
+{
+    *n_out = 0; *where = nullptr;
+    const int n_clouds_all = (int)e->kf_off.size() - 1;
+    int k0 = key - search, k1 = key + search;
+    if (k0 < 0) k0 = 0;
+    if (k1 >= n_clouds_all) k1 = n_clouds_all - 1;
+    if (k1 < k0) return SCL_OK;
+    if (k1 >= n_poses) FAIL(SCL_ERR_RANGE, "a stored keyframe has no pose");
+    const int nc = k1 - k0 + 1;
+    std::vector<float> T((size_t)nc * 12);
+    std::vector<int> off((size_t)nc + 1);
+    int max_points = 0;
+    for (int c = 0; c < nc; c++) {
+        const float* p = poses6 + (size_t)(k0 + c) * 6;
+        /* pcl::getTransformation(x, y, z, roll, pitch, yaw) in float with libm, as the reference calls it (:241) */
+        const float A = cosf(p[5]), B = sinf(p[5]), C = cosf(p[4]), D = sinf(p[4]), E = cosf(p[3]), F = sinf(p[3]), DE = D * E, DF = D * F;
+        float* t = &T[(size_t)c * 12];
+        t[0] = A * C; t[1] = A * DF - B * E; t[2] = B * F + A * DE; t[3] = p[0];
+        t[4] = B * C; t[5] = A * E + B * DF; t[6] = B * DE - A * F; t[7] = p[1];
+        t[8] = -D;    t[9] = C * F;          t[10] = C * E;         t[11] = p[2];
+        off[c] = e->kf_off[k0 + c] - e->kf_off[k0];
+        max_points = std::max(max_points, e->kf_off[k0 + c + 1] - e->kf_off[k0 + c]);
+    }
+    off[nc] = e->kf_off[k1 + 1] - e->kf_off[k0];
+    const int total = off[nc];
+    if (total <= 0) return SCL_OK;
+    CK(e->vg_world.ensure((size_t)total * 16));
+    CK(e->vg_T.ensure(T.size() * 4)); CK(e->vg_off.ensure((size_t)(nc + 1) * 4));
+    CK(cudaMemcpyAsync(e->vg_T.p, T.data(), T.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->vg_off.p, off.data(), (size_t)(nc + 1) * 4, cudaMemcpyHostToDevice, e->stream));
+    CK(scl_launch_transform_concat(static_cast<unsigned char*>(e->kf_arena.p) + (size_t)e->kf_off[k0] * 16, e->vg_off.as<int>(), nc, max_points, 16,
+                                   e->vg_T.as<float>(), e->vg_world.p, e->stream));
+    if (leaf > 0.0f) {
+        int rc = voxel_grid_dev(e, e->vg_world.p, total, 16, leaf, n_out); if (rc) return rc;    /* synchronises: T and off are consumed */
+        *where = e->vg_out.p;
+    } else {
+        CK(cudaStreamSynchronize(e->stream));
+        *n_out = total; *where = e->vg_world.p;
+    }
+    return SCL_OK;
+}
+} // namespace
+
+int scl_verify_intra(scl_engine* e, int key_cur, int key_pre, int search_num, const float* poses6, int n_poses, float leaf,
+                     const scl_icp_params* icp, float fitness_threshold, scl_intra_result* out)
+{
+    LOCK();
+    if (!poses6 || !icp || !out || search_num < 0) FAIL(SCL_ERR_INVALID, "bad arguments");
+    const int n_clouds = (int)e->kf_off.size() - 1;
+    if (key_cur < 0 || key_cur >= n_clouds || key_pre < 0 || key_pre >= n_clouds || key_cur >= n_poses) FAIL(SCL_ERR_RANGE, "keyframe out of range");
+    memset(out, 0, sizeof(*out));
+    for (int i = 0; i < 4; i++) out->T[5 * i] = 1.0f;
+    out->fitness = 3.402823466e+38f;
+    /* the current keyframe (searchNum 0) and the history submap, both in the world frame and down-sampled; the clouds never leave the device */
+    int n_src = 0, n_tgt = 0; const void* where = nullptr;
+    int rc = near_keyframes_dev(e, key_cur, 0, poses6, n_poses, leaf, &n_src, &where); if (rc) return rc;
+    rc = scl_icp_set_cloud_dev(e, 0, where, n_src); if (rc) return rc;
+    rc = near_keyframes_dev(e, key_pre, search_num, poses6, n_poses, leaf, &n_tgt, &where); if (rc) return rc;
+    rc = scl_icp_set_cloud_dev(e, 1, where, n_tgt); if (rc) return rc;
+    out->n_src = n_src; out->n_tgt = n_tgt;
+    if (n_src < 300 || n_tgt < 1000) return SCL_OK;                  /* distributedMapping.h:1102: too little to verify, no loop */
+    rc = scl_icp_device(e, n_src, n_tgt, icp, out->T, &out->fitness, &out->converged, &out->iterations); if (rc) return rc;
+    out->accepted = (out->converged && !(out->fitness > fitness_threshold)) ? 1 : 0;   /* :1122 */
     return SCL_OK;
 }
 

@@ -84,6 +84,9 @@ struct scl_engine {
     void* xchg_buf = nullptr; size_t xchg_bytes = 0; int xchg_qk = 0, xchg_q = 0;
     XchgView xchg[kLanes] = {}; bool xchg_open = false; void* xchg_peer_map[16] = {};
     DevBuf icp_src, icp_tgt, icp_raw, icp_grid[2][5], icp_acc, icp_nn;
+    /* device-resident keyframe clouds (robots[id].keyFrameArray of the reference): one append-only arena of packed
+     * x, y, z, intensity records; cloud k = points [kf_off[k], kf_off[k + 1]) */
+    DevBuf kf_arena; size_t kf_points = 0; std::vector<int> kf_off{0};
     DevBuf vg_in, vg_world, vg_out, vg_keys[2], vg_vals[2], vg_head, vg_ord, vg_temp, vg_misc, vg_T, vg_off;
     size_t gbins_scans = 0;
     /* per-stage event timing */
@@ -93,6 +96,9 @@ struct scl_engine {
 
     int RS() const { return p.num_ring * p.num_sector; }
 };
+
+int scl_icp_set_cloud_dev(scl_engine* e, int which, const void* xyzw_dev, int n);
+int scl_icp_device(scl_engine* e, int n_src, int n_tgt, const scl_icp_params* prm, float* T_out, float* fitness, int* converged, int* iterations);
 
 #define CK(call)                                                                                     \
     do {                                                                                             \

@@ -495,3 +495,9 @@ cudaError_t scl_launch_ring_keys(const float* desc_dev, int n, int R, int S, flo
     ring_key_kernel<<<blocks, warps * 32, smem, stream>>>(desc_dev, n, R, S, keys, knorm, kn2max, cstat);
     return cudaGetLastError();
 }
+
+void scl_preload_k1()
+{
+    SCL_TOUCH(polar_bin_kernel<4>); SCL_TOUCH(ring_key_kernel);
+    SCL_TOUCH((ring_key_fixed_kernel<20, 60, 4>)); SCL_TOUCH((ring_key_fixed_kernel<40, 120, 2>));
+}

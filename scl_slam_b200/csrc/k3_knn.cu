@@ -368,3 +368,12 @@ cudaError_t scl_launch_ids_to_local(const int32_t* ids, int n, int id_mul, int i
     ids_to_local_kernel<<<(n + 255) / 256, 256, 0, stream>>>(ids, n, id_mul, id_add, missing_to, ids_rewrite, local);
     return cudaGetLastError();
 }
+
+void scl_preload_k3()
+{
+    SCL_TOUCH((knn_exact_kernel<10, 0>)); SCL_TOUCH((knn_exact_kernel<10, 1>)); SCL_TOUCH((knn_exact_kernel<20, 0>)); SCL_TOUCH((knn_exact_kernel<20, 1>));
+    SCL_TOUCH((knn_exact_kernel<40, 0>)); SCL_TOUCH((knn_exact_kernel<40, 1>));
+    SCL_TOUCH((knn_exact_small_kernel<20, 0, 16>)); SCL_TOUCH((knn_exact_small_kernel<20, 1, 16>)); SCL_TOUCH((knn_exact_small_kernel<20, 0, 32>)); SCL_TOUCH((knn_exact_small_kernel<20, 1, 32>));
+    SCL_TOUCH((knn_exact_small_kernel<40, 0, 16>)); SCL_TOUCH((knn_exact_small_kernel<40, 1, 16>)); SCL_TOUCH((knn_exact_small_kernel<40, 0, 32>)); SCL_TOUCH((knn_exact_small_kernel<40, 1, 32>));
+    SCL_TOUCH(gather_rows_kernel); SCL_TOUCH(ids_to_local_kernel);
+}

@@ -1019,3 +1019,10 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
 #endif
     return cudaSuccess;
 }
+
+void scl_preload_k3_tc()
+{
+    SCL_TOUCH(key_image_kernel<20>); SCL_TOUCH(key_image_kernel<40>);
+    SCL_TOUCH((knn_tc_kernel<20, false>)); SCL_TOUCH((knn_tc_kernel<40, false>));
+    SCL_TOUCH((knn_rerank_kernel<0, 20>)); SCL_TOUCH((knn_rerank_kernel<1, 20>)); SCL_TOUCH((knn_rerank_kernel<0, 40>)); SCL_TOUCH((knn_rerank_kernel<1, 40>));
+}

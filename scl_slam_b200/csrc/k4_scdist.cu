@@ -810,3 +810,10 @@ cudaError_t scl_launch_combine_owned(int world, int Q, int K, const int32_t* q_i
                                                              best_id, best_dist, best_shift);
     return cudaGetLastError();
 }
+
+void scl_preload_k4()
+{
+    SCL_TOUCH((scdist_kernel<320, 2, 20, 60>)); SCL_TOUCH((scdist_kernel<512, 1, 20, 60>)); SCL_TOUCH((scdist_kernel<320, 2, 40, 120>));
+    SCL_TOUCH((scdist_kernel<512, 1, 40, 120>)); SCL_TOUCH((scdist_kernel<320, 2, 0, 0>)); SCL_TOUCH((scdist_kernel<512, 1, 0, 0>));
+    SCL_TOUCH(merge_shards_kernel); SCL_TOUCH(merge_topk_kernel); SCL_TOUCH(combine_owned_kernel);
+}

@@ -422,11 +422,7 @@ extern "C" int scl_icp(scl_engine* e, const void* src, int n_src, const void* tg
     LOCK();
     if (!prm || !T_out || !fitness || !converged) FAIL(SCL_ERR_INVALID, "null argument");
     if (n_src < 0 || n_tgt < 0 || stride_bytes < 12 || (stride_bytes & 3)) FAIL(SCL_ERR_INVALID, "bad cloud arguments");
-    double Tf[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-    for (int i = 0; i < 16; i++) T_out[i] = (float)Tf[i];
-    *fitness = 3.402823466e+38f; *converged = 0;
-    if (iterations) *iterations = 0;
-    if (n_src == 0 || n_tgt == 0) return SCL_OK;       /* PCL: nothing to align, not converged */
+    if (n_src == 0 || n_tgt == 0) return scl_icp_device(e, n_src, n_tgt, prm, T_out, fitness, converged, iterations);
     if (!src || !tgt) FAIL(SCL_ERR_INVALID, "null cloud");
 
     /* upload + pack to float4 */
@@ -440,6 +436,29 @@ extern "C" int scl_icp(scl_engine* e, const void* src, int n_src, const void* tg
     CK(cudaMemcpyAsync(e->icp_raw.p, tgt, tb, cudaMemcpyHostToDevice, e->stream));
     pack_xyz_kernel<<<(n_tgt + 255) / 256, 256, 0, e->stream>>>(e->icp_raw.as<unsigned char>(), n_tgt, stride_bytes, e->icp_tgt.as<float4>());
     CK(cudaGetLastError());
+    return scl_icp_device(e, n_src, n_tgt, prm, T_out, fitness, converged, iterations);
+}
+
+// A cloud that is already in device memory (packed 16-byte x, y, z, * records) becomes the ICP source (which = 0) or target
+// (1): same layout as the host path produces (w = the point's index). The caller holds the engine lock.
+int scl_icp_set_cloud_dev(scl_engine* e, int which, const void* xyzw_dev, int n)
+{
+    DevBuf& dst = which == 0 ? e->icp_src : e->icp_tgt;
+    if (n <= 0) return SCL_OK;
+    CK(dst.ensure((size_t)n * 16));
+    pack_xyz_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(static_cast<const unsigned char*>(xyzw_dev), n, 16, dst.as<float4>());
+    CK(cudaGetLastError());
+    return SCL_OK;
+}
+
+// ICP of the float4 clouds already in e->icp_src / e->icp_tgt (device memory); the caller holds the engine lock.
+int scl_icp_device(scl_engine* e, int n_src, int n_tgt, const scl_icp_params* prm, float* T_out, float* fitness, int* converged, int* iterations)
+{
+    double Tf[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    for (int i = 0; i < 16; i++) T_out[i] = (float)Tf[i];
+    *fitness = 3.402823466e+38f; *converged = 0;
+    if (iterations) *iterations = 0;
+    if (n_src == 0 || n_tgt == 0) return SCL_OK;       /* PCL: nothing to align, not converged */
 
     Grid fine, coarse;
     int rc = build_grid(e, e->icp_tgt.as<float4>(), n_tgt, 1.0f,

@@ -162,3 +162,8 @@ cudaError_t scl_launch_xchg_gather_queries(const XchgView& x, int seq, const voi
     xchg_gather_queries_kernel<<<blocks, 256, 0, stream>>>(x, seq, static_cast<const unsigned char*>(my_rows), row0_bytes, bytes);
     return cudaGetLastError();
 }
+
+void scl_preload_k7()
+{
+    SCL_TOUCH(xchg_gather_queries_kernel); SCL_TOUCH(xchg_merge_topk_kernel); SCL_TOUCH(xchg_combine_kernel);
+}

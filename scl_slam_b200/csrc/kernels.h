@@ -112,3 +112,10 @@ cudaError_t scl_launch_xchg_gather_queries(const XchgView& x, int seq, const voi
 cudaError_t scl_launch_xchg_merge_topk(const XchgView& x, int seq, int Q, int K, const void* my_block, int32_t* out_ids, float* out_d2, cudaStream_t stream);
 cudaError_t scl_launch_xchg_combine(const XchgView& x, int seq, int Q, int K, const void* my_block, const int32_t* q_ids, const int32_t* cand_ids,
                                     double* out_dist, int32_t* out_shift, int32_t* best_id, double* best_dist, int32_t* best_shift, cudaStream_t stream);
+
+// load every kernel of the query path on the current device (see SCL_TOUCH in common.cuh); called by scl_create
+void scl_preload_k1();
+void scl_preload_k3();
+void scl_preload_k3_tc();
+void scl_preload_k4();
+void scl_preload_k7();

@@ -30,7 +30,10 @@ EXPORTS = [
     "scl_query_batch_submit", "scl_query_batch_wait", "scl_voxel_grid", "scl_assemble_submap", "scl_build_insert_filtered",
     "scl_xchg_create", "scl_xchg_open", "scl_xchg_merge_topk_dev", "scl_xchg_combine_dev", "scl_xchg_close",
     "scl_xchg_open_local", "scl_xchg_buffer", "scl_xchg_bytes", "scl_num_lanes", "scl_query_batch_dev_lane", "scl_lanes_fork", "scl_lanes_join",
-    "scl_lane_sync", "scl_shard_query_dev", "scl_shard_query_submit",
+    "scl_lane_sync", "scl_shard_query_dev", "scl_shard_query_submit", "scl_store_keyframe_cloud", "scl_keyframe_clouds", "scl_verify_intra",
+    "scl_create_sharded", "scl_sharded_destroy", "scl_sharded_last_error", "scl_sharded_world", "scl_sharded_engine", "scl_sharded_size",
+    "scl_sharded_get_index", "scl_sharded_get_descriptor", "scl_sharded_insert_batch", "scl_sharded_build_insert", "scl_sharded_query_batch",
+    "scl_sharded_query_submit", "scl_sharded_query_wait", "scl_sharded_query_intra", "scl_sharded_query_inter",
     "scl_wire_pose6_to_transform", "scl_wire_loop_between", "scl_wire_make_loop_info", "scl_wire_make_global_descriptor",
     "scl_wire_encode_global_descriptor", "scl_wire_decode_global_descriptor", "scl_wire_encode_loop_info", "scl_wire_decode_loop_info",
 ]
@@ -93,6 +96,11 @@ class SclBatchResult(C.Structure):
 class SclIcpParams(C.Structure):
     _fields_ = [("max_corr_dist", C.c_double), ("max_iterations", C.c_int), ("trans_eps", C.c_double),
                 ("fitness_eps", C.c_double)]
+
+
+class SclIntraResult(C.Structure):
+    _fields_ = [("accepted", C.c_int), ("converged", C.c_int), ("iterations", C.c_int), ("fitness", C.c_float), ("T", C.c_float * 16),
+                ("n_src", C.c_int), ("n_tgt", C.c_int)]
 
 
 class SclRansacParams(C.Structure):
@@ -170,6 +178,27 @@ def load_library():
                                           C.c_uint64, C.POINTER(SclBatchResult)]
     lib.scl_verify_ransac.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(SclRansacParams),
                                       C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.scl_create_sharded.argtypes = [C.POINTER(SclParams), C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.scl_sharded_destroy.argtypes = [C.c_void_p]
+    lib.scl_sharded_last_error.argtypes = [C.c_void_p]
+    lib.scl_sharded_last_error.restype = C.c_char_p
+    lib.scl_sharded_world.argtypes = [C.c_void_p]
+    lib.scl_sharded_engine.argtypes = [C.c_void_p, C.c_int]
+    lib.scl_sharded_engine.restype = C.c_void_p
+    lib.scl_sharded_size.argtypes = [C.c_void_p]
+    lib.scl_sharded_get_index.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int8), C.POINTER(C.c_int)]
+    lib.scl_sharded_get_descriptor.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.scl_sharded_insert_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.scl_sharded_build_insert.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int8, C.c_int, C.c_void_p]
+    lib.scl_sharded_query_batch.argtypes = [C.c_void_p, C.POINTER(SclBatchQuery), C.POINTER(SclBatchResult)]
+    lib.scl_sharded_query_submit.argtypes = [C.c_void_p, C.POINTER(SclBatchQuery), C.POINTER(SclBatchResult), C.POINTER(C.c_int)]
+    lib.scl_sharded_query_wait.argtypes = [C.c_void_p, C.c_int]
+    lib.scl_sharded_query_intra.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+    lib.scl_sharded_query_inter.argtypes = lib.scl_sharded_query_intra.argtypes
+    lib.scl_store_keyframe_cloud.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    lib.scl_keyframe_clouds.argtypes = [C.c_void_p]
+    lib.scl_verify_intra.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.POINTER(SclIcpParams), C.c_float,
+                                     C.POINTER(SclIntraResult)]
     lib.scl_set_knn_mode.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.scl_set_scdist_mode.argtypes = [C.c_void_p, C.c_int]
     lib.scl_set_tc_stages.argtypes = [C.c_void_p, C.c_int]
@@ -492,6 +521,22 @@ class ScanContextB200:
                                             C.byref(nc), C.byref(ni), C.byref(ok)))
         return T.reshape(4, 4), nc.value, ni.value, bool(ok.value)
 
+    def store_keyframe_cloud(self, key, pts):
+        """robots[id].keyFrameArray.push_back(cloud): the cloud stays on the device for verify_intra."""
+        p, n, stride = _cloud(pts)
+        self._ck(self.lib.scl_store_keyframe_cloud(self.h, key, p.ctypes.data, n, stride))
+
+    def verify_intra(self, key_cur, key_pre, search_num, poses6, leaf, fitness_threshold=0.3, max_corr_dist=100.0, max_iterations=50,
+                     trans_eps=1e-6, fitness_eps=1e-6):
+        """performIntraLoopClosure after the descriptor stage (distributedMapping.h:1096-1143) as one call. Returns a dict."""
+        poses = np.ascontiguousarray(poses6, np.float32).reshape(-1, 6)
+        prm = SclIcpParams(max_corr_dist, max_iterations, trans_eps, fitness_eps)
+        r = SclIntraResult()
+        self._ck(self.lib.scl_verify_intra(self.h, key_cur, key_pre, search_num, poses.ctypes.data, poses.shape[0], leaf, C.byref(prm),
+                                           fitness_threshold, C.byref(r)))
+        return dict(accepted=bool(r.accepted), converged=bool(r.converged), iterations=r.iterations, fitness=r.fitness,
+                    T=np.array(list(r.T), np.float32).reshape(4, 4), n_src=r.n_src, n_tgt=r.n_tgt)
+
     def voxel_grid(self, pts, leaf):
         """pcl::VoxelGrid<PointXYZI> (distributedMapping.h:996-998, 1181-1185): (m, 4) float32 centroids x, y, z, intensity."""
         p, n, stride = _cloud(pts)
@@ -525,3 +570,84 @@ class ScanContextB200:
         self._ck(self.lib.scl_build_insert_filtered(self.h, p.ctypes.data, n, stride, leaf, robot, index,
                                                     out.ctypes.data, C.byref(m)))
         return out, m.value
+
+
+class ShardedScanContextB200:
+    """The same descriptor object with its keyframe database sharded by keyframe index over several GPUs of one box, in
+    one process (scl_create_sharded, include/scl_engine.h): the six scan_descriptor virtuals + the batched query."""
+
+    def __init__(self, devices, numRing=20, numSector=60, numCandidates=3, distThres=0.14, lidarHeight=1.65, maxRadius=80.0,
+                 numExcludeRecent=100, treeMakingPeriod=10, searchRatio=0.1, max_q=1024, max_k=10):
+        self.lib = load_library()
+        self.params = SclParams(numRing, numSector, numCandidates, distThres, lidarHeight, maxRadius, numExcludeRecent, treeMakingPeriod, searchRatio)
+        self.R, self.S, self.K = numRing, numSector, numCandidates
+        devs = np.ascontiguousarray(devices, np.int32)
+        self.h = C.c_void_p()
+        rc = self.lib.scl_create_sharded(C.byref(self.params), devs.size, devs.ctypes.data, max_q, max(max_k, numCandidates), C.byref(self.h))
+        if rc != SCL_OK:
+            self.h = None
+            raise RuntimeError(f"scl_create_sharded failed: {_STATUS.get(rc, rc)} (CUDA devices with peer access are required; no CPU fallback)")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.scl_sharded_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc != SCL_OK:
+            raise RuntimeError(f"{_STATUS.get(rc, rc)}: {self.lib.scl_sharded_last_error(self.h).decode()}")
+
+    def makeAndSaveDescriptorAndKey(self, scan, robot, index):
+        pts, n, stride = _cloud(scan)
+        out = np.empty(self.R * self.S, np.float32)
+        self._ck(self.lib.scl_sharded_build_insert(self.h, pts.ctypes.data, n, stride, robot, index, out.ctypes.data))
+        return out
+
+    def saveDescriptorAndKey(self, descriptorMat, robot, index):
+        d = np.ascontiguousarray(descriptorMat, np.float32).reshape(-1)
+        rb, ix = np.array([robot], np.int8), np.array([index], np.int32)
+        self._ck(self.lib.scl_sharded_insert_batch(self.h, d.ctypes.data, 1, rb.ctypes.data, ix.ctypes.data))
+
+    def insert_batch(self, descs, robots=None, indices=None):
+        d = np.ascontiguousarray(descs, np.float32).reshape(-1, self.R * self.S)
+        rb = None if robots is None else np.ascontiguousarray(robots, np.int8)
+        ix = None if indices is None else np.ascontiguousarray(indices, np.int32)
+        self._ck(self.lib.scl_sharded_insert_batch(self.h, d.ctypes.data, d.shape[0], _ptr(rb), _ptr(ix)))
+
+    def detectIntraLoopClosureID(self, currentPtr):
+        i, f = C.c_int(), C.c_float()
+        self._ck(self.lib.scl_sharded_query_intra(self.h, currentPtr, C.byref(i), C.byref(f)))
+        return i.value, f.value
+
+    def detectInterLoopClosureID(self, currentPtr):
+        i, f = C.c_int(), C.c_float()
+        self._ck(self.lib.scl_sharded_query_inter(self.h, currentPtr, C.byref(i), C.byref(f)))
+        return i.value, f.value
+
+    def getIndex(self, key):
+        r, i = C.c_int8(), C.c_int()
+        self._ck(self.lib.scl_sharded_get_index(self.h, key, C.byref(r), C.byref(i)))
+        return r.value, i.value
+
+    def getSize(self, idIn=-1):
+        return self.lib.scl_sharded_size(self.h)
+
+    def desc(self, key):
+        out = np.empty(self.R * self.S, np.float32)
+        self._ck(self.lib.scl_sharded_get_descriptor(self.h, key, out.ctypes.data))
+        return out.reshape(self.R, self.S)
+
+    def query_batch(self, q_desc, K=None, n_db=None, metric=0, q_ids=None):
+        K = K or self.K
+        qd = np.ascontiguousarray(q_desc, np.float32).reshape(-1, self.R * self.S)
+        qi = None if q_ids is None else np.ascontiguousarray(q_ids, np.int32)
+        Q = qd.shape[0]
+        n_db = self.getSize() if n_db is None else n_db
+        out = dict(cand_ids=np.empty((Q, K), np.int32), cand_d2=np.empty((Q, K), np.float32), cand_dist=np.empty((Q, K), np.float64),
+                   cand_shift=np.empty((Q, K), np.int32), best_id=np.empty(Q, np.int32), best_dist=np.empty(Q, np.float64), best_shift=np.empty(Q, np.int32))
+        q = SclBatchQuery(qd.ctypes.data, _ptr(qi), Q, K, n_db, metric)
+        r = SclBatchResult(*[out[k].ctypes.data for k in ("cand_ids", "cand_d2", "cand_dist", "cand_shift", "best_id", "best_dist", "best_shift")])
+        self._ck(self.lib.scl_sharded_query_batch(self.h, C.byref(q), C.byref(r)))
+        return out

@@ -2,7 +2,8 @@
 // scan_context_descriptor: through unique_ptr<scan_descriptor> (distributedMapping.h:333,404),
 // build+insert from a cloud (:1002), insert from a wire vector (:627), intra/inter queries
 // (:1078,1280), getIndex/getSize (:1072,1281-1284). Reads a small binary scenario written by
-// tests/test_dropin_cpp.py and prints one line per call for the test to compare with the oracle.
+// tests/test_dropin_cpp.py and prints one line per call for the test to compare with the oracle. With a second argument n
+// the object is scan_context_descriptor_b200_sharded over n GPUs (scl_create_sharded).
 #include "pcl_standin.h"
 #include "../../include/descriptor_b200.h"
 #include <cstdio>
@@ -16,7 +17,15 @@ int main(int argc, char** argv)
 	if(!f) return 2;
 	int n_clouds = 0, n_wires = 0, rs = 0;
 	if(std::fread(&n_clouds, 4, 1, f) != 1 || std::fread(&n_wires, 4, 1, f) != 1 || std::fread(&rs, 4, 1, f) != 1) return 2;
-	std::unique_ptr<scan_descriptor> scanDescriptor(new scan_context_descriptor_b200(20, 60, 10, 0.14, 1.65, 80.0, 30));
+	/* argv[2] = number of GPUs: the sharded adapter over devices 0 .. n-1 (still one object behind the same pointer) */
+	std::unique_ptr<scan_descriptor> scanDescriptor;
+	if(argc >= 3)
+	{
+		std::vector<int> devices;
+		for(int d = 0; d < std::atoi(argv[2]); d++) devices.push_back(d);
+		scanDescriptor.reset(new scan_context_descriptor_b200_sharded(devices, 20, 60, 10, 0.14, 1.65, 80.0, 30));
+	}
+	else scanDescriptor.reset(new scan_context_descriptor_b200(20, 60, 10, 0.14, 1.65, 80.0, 30));
 	for(int i = 0; i < n_clouds; i++)
 	{
 		int np = 0;

@@ -27,8 +27,13 @@ def test_dropin_class_compiles_and_links():
 
 
 @pytest.mark.gpu
-def test_dropin_class_runs_like_the_reference(tmp_path):
+@pytest.mark.parametrize("n_gpus", [0, 1, 2])
+def test_dropin_class_runs_like_the_reference(tmp_path, n_gpus):
+    """n_gpus = 0: scan_context_descriptor_b200; 1, 2: scan_context_descriptor_b200_sharded over that many devices."""
+    import torch
     from oracle_lib import Oracle
+    if n_gpus > torch.cuda.device_count():
+        pytest.skip("not enough GPUs")
     from scl_slam_b200 import synth
     _compile()
     world = synth.make_world(6, 200)
@@ -44,7 +49,7 @@ def test_dropin_class_runs_like_the_reference(tmp_path):
         for c in clouds:
             f.write(struct.pack("i", c.shape[0])); f.write(c.tobytes())
         f.write(wires.astype(np.float32).tobytes())
-    out = subprocess.run([EXE, str(path)], check=True, capture_output=True, text=True).stdout.splitlines()
+    out = subprocess.run([EXE, str(path)] + ([str(n_gpus)] if n_gpus else []), check=True, capture_output=True, text=True).stdout.splitlines()
     o = Oracle(num_candidates=10, num_exclude_recent=30)
     sums = [float(np.sum(o.makeAndSaveDescriptorAndKey(c, 0, i).astype(np.float64))) for i, c in enumerate(clouds)]
     for i in range(wires.shape[0]):

@@ -769,3 +769,95 @@ def test_lanes_concurrent_batches_equal_sequential(eng_mod):
                 assert torch.equal(seq[i][k].view(torch.uint8), par[i][k].view(torch.uint8)), (n_db, i, k)
         e.insert_batch_dev(db[n:].contiguous())          # grows the database between the two rounds
     assert e.knn_stats()["tc_queries"] > 0
+
+
+def test_verify_intra_one_call_equals_the_pieces(eng_mod):
+    """scl_verify_intra (device-resident keyframe clouds -> submaps -> voxel filter -> ICP -> fitness gate) against the same
+    steps made one by one through the host-buffer calls, and against the planted offset."""
+    world = synth.make_world(9, 260, area=400.0)
+    dirs = synth.lidar_dirs("livox", n_az=24000, seed=2)
+    n_kf = 12
+    poses = [(2.0 * k, 0.3 * np.sin(k), 0.02 * k) for k in range(n_kf)]
+    e = eng_mod.ScanContextB200()
+    clouds = []
+    for k, p in enumerate(poses):
+        c = synth.scan(world, p, dirs, seed=300 + k, max_range=120.0).astype(np.float32)
+        clouds.append(c)
+        e.store_keyframe_cloud(k, c)
+    poses6 = np.array([[x, y, 0.0, 0.0, 0.0, a] for x, y, a in poses], np.float32)
+    cur, pre, search = 10, 4, 3
+    # odometry drift of the current keyframe: its recorded pose is off by a known rigid motion
+    drift = poses6.copy()
+    drift[cur, 0] += 0.5; drift[cur, 1] -= 0.3; drift[cur, 5] += 0.04
+    got = e.verify_intra(cur, pre, search, drift, 0.4, fitness_threshold=0.3)
+    src = e.assemble_submap([clouds[cur]], drift[cur:cur + 1], 0.4)
+    tgt = e.assemble_submap(clouds[pre - search:pre + search + 1], drift[pre - search:pre + search + 1], 0.4)
+    assert got["n_src"] == src.shape[0] and got["n_tgt"] == tgt.shape[0]
+    T, fit, conv, it = e.icp(src, tgt)
+    assert got["converged"] == conv and got["iterations"] == it
+    assert np.array_equal(_bits(got["T"]), _bits(T)) and got["fitness"] == fit
+    assert got["accepted"] == (conv and fit <= 0.3)
+    # size gates (distributedMapping.h:1102)
+    e2 = eng_mod.ScanContextB200()
+    for k in range(3):
+        e2.store_keyframe_cloud(k, clouds[k][:200])
+    r = e2.verify_intra(2, 0, 1, poses6, 0.4)
+    assert not r["accepted"] and r["iterations"] == 0 and r["n_src"] < 300
+    with pytest.raises(RuntimeError):
+        e2.store_keyframe_cloud(7, clouds[0])                        # out of order
+
+
+def test_insert_and_query_from_two_threads(eng_mod):
+    """The reference inserts under mtxSC on the ROS / LIO threads (distributedMapping.h:625-628, 1001-1003) and queries
+    from loopClosureThread without the lock (:1078, 1280): a data race there, serialised inside the engine here. One
+    thread appends descriptors one call at a time (growing the arrays several times) while another keeps querying a fixed
+    key range, synchronously and pipelined: every answer must equal the one computed before the inserts began."""
+    import threading
+    n0, n_more, nq, K = 6000, 3000, 64, 10
+    db = synth.desc_db(n0 + n_more, seed=111).numpy()
+    q = synth.desc_queries(torch.from_numpy(db[:n0]), nq, seed=112)[0].numpy().reshape(nq, -1)
+    e = eng_mod.ScanContextB200(numCandidates=K)
+    e.insert_batch(db[:n0])
+    exp = e.query_batch(q_desc=q, K=K, n_db=n0 - 100)
+    errors = []
+
+    def producer():
+        try:
+            for i in range(n0, n0 + n_more):
+                e.saveDescriptorAndKey(db[i], 1, i)
+        except Exception as ex:                      # noqa: BLE001
+            errors.append(ex)
+
+    def consumer():
+        try:
+            names = ("cand_ids", "cand_d2", "cand_dist", "cand_shift", "best_id", "best_dist", "best_shift")
+            dt = dict(cand_ids=np.int32, cand_d2=np.float32, cand_dist=np.float64, cand_shift=np.int32, best_id=np.int32, best_dist=np.float64, best_shift=np.int32)
+            qp = torch.from_numpy(q).pin_memory().numpy()
+            outs = [{k: np.empty((nq, K) if k.startswith("cand") else nq, dt[k]) for k in names} for _ in range(2)]
+            rounds = 0
+            while t_ins.is_alive() or rounds < 5:
+                got = e.query_batch(q_desc=q, K=K, n_db=n0 - 100)
+                for k in exp:
+                    assert np.array_equal(got[k], exp[k], equal_nan=True), k
+                tk = [e.query_batch_submit(qp, outs[i], K=K, n_db=n0 - 100, metric=0) for i in range(2)]
+                for t in tk:
+                    e.query_batch_wait(t)
+                for o in outs:
+                    for k in exp:
+                        assert np.array_equal(o[k], exp[k], equal_nan=True), k
+                a = e.detectInterLoopClosureID(n0 - 1)
+                assert a[0] != n0 - 1
+                rounds += 1
+        except Exception as ex:                      # noqa: BLE001
+            errors.append(ex)
+    t_ins = threading.Thread(target=producer)
+    t_q = threading.Thread(target=consumer)
+    t_ins.start(); t_q.start()
+    t_ins.join(); t_q.join()
+    assert not errors, errors[:1]
+    assert e.getSize() == n0 + n_more
+    fresh = eng_mod.ScanContextB200(numCandidates=K)
+    fresh.insert_batch(db)
+    a, b = e.query_batch(q_desc=q, K=K), fresh.query_batch(q_desc=q, K=K)
+    for k in a:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
