@@ -804,7 +804,7 @@ int scdist_owned(scl_engine* e, Lane& ln, const float* q_desc_dev, const int32_t
                  double* dist_dev, int32_t* shift_dev, bool stats_ready /* knn_dev has just run on this lane for these very queries */)
 {
     /* the global candidate lists are spread over the shards: about K / world of a query's candidates live here */
-    ln.scdist_owned_hint = e->world > 1 ? (K + e->world - 1) / e->world + 1 : 0;
+    ln.scdist_owned_hint = e->world > 1 ? (K + e->world - 1) / e->world + (e->world <= 2 ? 1 : 0) : 0;
     const int rc = scdist_dev(e, ln, q_desc_dev, nullptr, q_ids_dev, Q, K, const_cast<int32_t*>(cand_ids_dev), 0, dist_dev, shift_dev, nullptr, nullptr, nullptr,
                               stats_ready && ln.qstat_of == q_desc_dev && ln.qstat_rows >= Q);
     ln.scdist_owned_hint = 0;

@@ -42,7 +42,7 @@ constexpr float kDistTol = 4.0e-5f;     /* window: |d32 - d| <= R u + 1e-6 (R-te
 constexpr float kSafeHi = 1.0e15f, kSafeLo = 1.0e-15f;   /* magnitudes outside: no FP32 prefilter for the pair */
 
 struct ScLayout {
-    int RS, S, warps;
+    int RS, S, warps, use_qdd;
     size_t off_qd, off_qx, off_qdd, off_qs, off_vq32, off_warp, warp_stride;
     size_t w_cd, w_cs, w_vc32, w_nc32, w_T, w_d32, w_cnt, w_list;
     size_t off_res, total;
@@ -50,14 +50,14 @@ struct ScLayout {
 
 __host__ __device__ inline size_t al16(size_t x) { return (x + 15) / 16 * 16; }
 
-__host__ __device__ inline ScLayout sc_layout(int R, int S, int K, int warps)
+__host__ __device__ inline ScLayout sc_layout(int R, int S, int K, int warps, int use_qdd = 1)
 {
     ScLayout L;
-    L.RS = R * S; L.S = S; L.warps = warps;
+    L.RS = R * S; L.S = S; L.warps = warps; L.use_qdd = use_qdd;
     size_t o = al16((size_t)(1 + warps) * 8);                  /* mbarriers */
     L.off_qd = o; o += al16((size_t)L.RS * 4);                 /* query descriptor as it arrives */
     L.off_qx = o; o += al16((size_t)R * (S + kQExt) * 4);      /* the same with rows S + kQExt wide */
-    L.off_qdd = o; o += al16((size_t)L.RS * 8);                /* widened to double once per CTA */
+    L.off_qdd = o; if (use_qdd) o += al16((size_t)L.RS * 8);   /* widened to double once per CTA (not on a shard: few pairs per query, shared memory buys more CTAs per SM) */
     L.off_qs = o; o += al16((size_t)2 * S * 8);                /* query sector key | column norms (double) */
     L.off_vq32 = o; o += al16((size_t)S * 4);
     L.off_warp = o;
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) scdist_kernel(const S
         sm = warp_sum(sm);
         if (lane == 0) s_q[0] = sm / (float)S;         /* NaN / inf here end up in the unsafe path below */
     }
-    for (int i = threadIdx.x; i < RS; i += blockDim.x) qdd[i] = (double)qd[i];
+    if (L.use_qdd) for (int i = threadIdx.x; i < RS; i += blockDim.x) qdd[i] = (double)qd[i];
     __syncthreads();
     const float centre = s_q[0];
     const double centre_d = (double)centre;
@@ -549,13 +549,23 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) scdist_kernel(const S
                         const double nab = cb < S ? nq[cb] : 0.0, nbb = cb < S ? nc[jb] : 0.0;
                         const bool cnta = ca < S && !((naa == 0.0) | (nba == 0.0)), cntb = cb < S && !((nab == 0.0) | (nbb == 0.0));
                         double dota = 0.0, dotb = 0.0;
-                        const double* qa = qdd + (ca < S ? ca : 0); const float* ka = cd + ja;
-                        const double* qb = qdd + (cb < S ? cb : 0); const float* kb = cd + jb;
+                        const int oa = ca < S ? ca : 0, ob = cb < S ? cb : 0;
+                        const float* ka = cd + ja; const float* kb = cd + jb;
                         if (cnta | cntb) {
+                            if (L.use_qdd) {
+                                const double* qa = qdd + oa; const double* qb = qdd + ob;
 #pragma unroll 4
-                            for (int r = 0; r < R; r++) {          /* exact products: fused multiply-add == mul, then add */
-                                dota = __fma_rn(qa[r * S], (double)ka[r * S], dota);
-                                dotb = __fma_rn(qb[r * S], (double)kb[r * S], dotb);
+                                for (int r = 0; r < R; r++) {      /* exact products: fused multiply-add == mul, then add */
+                                    dota = __fma_rn(qa[r * S], (double)ka[r * S], dota);
+                                    dotb = __fma_rn(qb[r * S], (double)kb[r * S], dotb);
+                                }
+                            } else {
+                                const float* qa = qd + oa; const float* qb = qd + ob;
+#pragma unroll 4
+                                for (int r = 0; r < R; r++) {
+                                    dota = __fma_rn((double)qa[r * S], (double)ka[r * S], dota);
+                                    dotb = __fma_rn((double)qb[r * S], (double)kb[r * S], dotb);
+                                }
                             }
                         }
                         const double sima = cnta ? __ddiv_rn(dota, __dmul_rn(naa, nba)) : 0.0;
@@ -748,11 +758,13 @@ cudaError_t scl_launch_scdist(const float* db_desc, const double* db_stat, const
     if (Q <= 0) return cudaSuccess;
     if (S > 128 || K > 32) return cudaErrorNotSupported;
     const size_t budget = 227 * 1024 - 2048;
+    const bool shard = owned_per_query > 0;
+    const int use_qdd = shard ? 0 : 1;
     int slots = K < 16 ? K : 16;
     /* a shard holds about K / world of a query's candidates: fewer candidate tiles per CTA then, so that more CTAs (queries) share an SM */
-    if (owned_per_query > 0 && owned_per_query < slots) slots = owned_per_query < 2 ? 2 : owned_per_query;
-    while (slots > 1 && sc_layout(R, S, K, slots).total > budget) slots--;
-    const ScLayout L = sc_layout(R, S, K, slots);
+    if (shard && owned_per_query < slots) slots = owned_per_query < 2 ? 2 : owned_per_query;
+    while (slots > 1 && sc_layout(R, S, K, slots, use_qdd).total > budget) slots--;
+    const ScLayout L = sc_layout(R, S, K, slots, use_qdd);
     if (L.total > budget) return cudaErrorNotSupported;
     const int warps = slots < 4 ? 4 : slots;           /* at least four warps prepare the query side */
     const int use_bulk = ((R * S) % 4 == 0) && ((reinterpret_cast<uintptr_t>(db_desc) & 15) == 0) &&
@@ -768,9 +780,10 @@ cudaError_t scl_launch_scdist(const float* db_desc, const double* db_stat, const
         SCL_PREFER_SMEM((scdist_kernel<MT, MB, RT, ST>));                                                                       \
         scdist_kernel<MT, MB, RT, ST><<<Q, warps * 32, L.total, stream>>>(a);                                                   \
     } while (0)
-    /* up to 10 warps and half an SM's shared memory: two CTAs per SM; otherwise one big CTA */
+    /* up to 10 warps and half an SM's shared memory: two CTAs per SM; otherwise one big CTA; a shard's small CTAs: six per SM */
     const bool two = warps <= 10 && L.total <= 113 * 1024;
-    if (R == 20 && S == 60) { if (two) SCL_SCDIST_LAUNCH(320, 2, 20, 60); else SCL_SCDIST_LAUNCH(512, 1, 20, 60); }
+    if (R == 20 && S == 60 && shard && warps == 4 && L.total <= 48 * 1024) SCL_SCDIST_LAUNCH(128, 6, 20, 60);
+    else if (R == 20 && S == 60) { if (two) SCL_SCDIST_LAUNCH(320, 2, 20, 60); else SCL_SCDIST_LAUNCH(512, 1, 20, 60); }
     else if (R == 40 && S == 120) { if (two) SCL_SCDIST_LAUNCH(320, 2, 40, 120); else SCL_SCDIST_LAUNCH(512, 1, 40, 120); }
     else { if (two) SCL_SCDIST_LAUNCH(320, 2, 0, 0); else SCL_SCDIST_LAUNCH(512, 1, 0, 0); }
 #undef SCL_SCDIST_LAUNCH
@@ -813,7 +826,7 @@ cudaError_t scl_launch_combine_owned(int world, int Q, int K, const int32_t* q_i
 
 void scl_preload_k4()
 {
-    SCL_TOUCH((scdist_kernel<320, 2, 20, 60>)); SCL_TOUCH((scdist_kernel<512, 1, 20, 60>)); SCL_TOUCH((scdist_kernel<320, 2, 40, 120>));
+    SCL_TOUCH((scdist_kernel<320, 2, 20, 60>)); SCL_TOUCH((scdist_kernel<512, 1, 20, 60>)); SCL_TOUCH((scdist_kernel<128, 6, 20, 60>)); SCL_TOUCH((scdist_kernel<320, 2, 40, 120>));
     SCL_TOUCH((scdist_kernel<512, 1, 40, 120>)); SCL_TOUCH((scdist_kernel<320, 2, 0, 0>)); SCL_TOUCH((scdist_kernel<512, 1, 0, 0>));
     SCL_TOUCH(merge_shards_kernel); SCL_TOUCH(merge_topk_kernel); SCL_TOUCH(combine_owned_kernel);
 }
