@@ -227,8 +227,8 @@ int scl_set_knn_mode(scl_engine* e, int mode, int count_fallbacks);
 int scl_set_scdist_mode(scl_engine* e, int mode);
 int scl_knn_stats(scl_engine* e, long long* tc_queries, long long* fallback_queries);
 /* Shared memory of the tensor-core kNN kernel: `stages` key tiles (32 KB each at 20 rings) are in flight per SM, 2..5
- * (default 5). Fewer stages leave shared memory to the kernels of other query lanes (re-rank, SC distance), which then run
- * on the same SMs at the same time; results do not depend on it. */
+ * (default 2: measured no slower than 5, the kernel is not TMA-bound). Fewer stages leave shared memory to the kernels of other
+ * query lanes (re-rank, SC distance), which then run on the same SMs at the same time; results do not depend on it. */
 int scl_set_tc_stages(scl_engine* e, int stages);
 
 /* ---- per-stage device timing (for roofline reports) ----------------------------------------

@@ -43,7 +43,7 @@ struct scl_engine {
     unsigned char* d_kimg = nullptr;       /* tensor-core key image: 128-key tiles in the tcgen05 operand layout (k3_knn_tc.cu) */
     int img_n = 0, img_cap = 0;            /* keys [0, img_n) have an image; capacity in keys */
     int knn_mode = 0;                      /* 0 auto, 1 exact CUDA-core kernel, 2 tensor-core prefilter */
-    int tc_stages = 5;                     /* key tiles knn_tc_kernel keeps in flight in shared memory (scl_set_tc_stages) */
+    int tc_stages = 2;                     /* key tiles knn_tc_kernel keeps in flight in shared memory (scl_set_tc_stages): two leave 127 KB of the SM to other lanes' kernels */
     long long stat_tc_queries = 0, stat_fallback_queries = 0;
     bool count_fallbacks = false;
     std::vector<std::pair<int8_t, int>> index;

@@ -161,8 +161,12 @@ __device__ __forceinline__ int align_exact_all(const double* __restrict__ vq, co
 }
 
 // RT/ST: compile-time rings/sectors (20x60, 40x120) so the row loops unroll and the index arithmetic folds; 0 = run time.
+// Registers: the ten-warp CTA is held to 88 per thread so that ONE such CTA fits beside a knn_tc_kernel CTA of another
+// query lane on the same SM (384 x 96 + 320 x 88 registers = 65 024 of 65 536; shared memory 100 KB + 113 KB): the SC
+// distances of one batch then run under the tensor-core pass of the next instead of after it.
 template <int kMaxThreads, int kMinBlocks, int RT, int ST>
-__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) scdist_kernel(const ScArgs a)
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) __maxnreg__(kMaxThreads == 320 ? 88 : (kMaxThreads == 128 ? 80 : 128))
+scdist_kernel(const ScArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int R = RT ? RT : a.R, S = ST ? ST : a.S, K = a.K;
