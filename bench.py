@@ -243,6 +243,8 @@ def run_ours(args):
     e.set_shard(rank, world)
     if args.tc_stages:
         e.set_tc_stages(args.tc_stages)
+    if args.scdist_tiles >= 0 and world == 1:
+        e.set_scdist_tiles(args.scdist_tiles)
     n_local = fill(e, dev, rank, world, n_db)
     D = max(1, min(args.in_flight, e.num_lanes()))
     steps = args.steps                                     # the last group is smaller when D does not divide K
@@ -916,6 +918,7 @@ def main():
     ap.add_argument("--n-db", type=int, default=N_DB, help="database size (default: the 1M workload)")
     ap.add_argument("--in-flight", type=int, default=8, help="batches in flight (query lanes used), 1..8")
     ap.add_argument("--tc-stages", type=int, default=0, help="key tiles the tensor-core kNN kernel keeps in flight (2..5; 0 = the engine's default)")
+    ap.add_argument("--scdist-tiles", type=int, default=-1, help="candidate tiles per K4 CTA (0 = one per candidate; -1 = the engine's default)")
     ap.add_argument("--cpu-sample", type=int, default=256, help="queries per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the secondary arms (C1, C2, C4, C5, robustness)")

@@ -225,6 +225,12 @@ int scl_set_knn_mode(scl_engine* e, int mode, int count_fallbacks);
  * bound of the best estimate) in FP64 with the operation order of distanceBtnScanContext (descriptor.h:1538-1569);
  * mode 1: every shift in FP64. Both give bit-identical distances and shifts; mode 1 exists for the tests. */
 int scl_set_scdist_mode(scl_engine* e, int mode);
+/* Candidate tiles (= scoring warps) of one K4 CTA on an unsharded engine: 0 (default) = one per candidate, up to 10 at 20x60;
+ * 2..16 = that many, every warp then scores several candidates in turn and the CTA keeps no double copy of the query.
+ * Small CTAs (4 tiles: 128 threads, 48 KB) fit beside a knn_tc_kernel CTA of another query lane on the same SM - its
+ * register file is divided by scheduler, 16 384 registers each, of which knn_tc holds 9 216 - so that the SC distances of
+ * one batch run under the tensor-core pass of the next. Results do not depend on it. */
+int scl_set_scdist_tiles(scl_engine* e, int tiles);
 int scl_knn_stats(scl_engine* e, long long* tc_queries, long long* fallback_queries);
 /* Shared memory of the tensor-core kNN kernel: `stages` key tiles (32 KB each at 20 rings) are in flight per SM, 2..5
  * (default 2: measured no slower than 5, the kernel is not TMA-bound). Fewer stages leave shared memory to the kernels of other

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libscl_b200.so")
-SOURCES = ["engine.cu", "k1_polar.cu", "k3_knn.cu", "k4_scdist.cu", "k5_icp.cu", "k3_knn_tc.cu", "k6_cloud.cu", "wire.cu", "k7_exchange.cu", "sharded.cu"]
+SOURCES = ["engine.cu", "k1_polar.cu", "k3_knn.cu", "k4_scdist.cu", "k5_icp.cu", "k3_knn_tc.cu", "k6_cloud.cu", "wire.cu", "k7_exchange.cu", "sharded.cu", "rowkey.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--fmad=true"]
 
@@ -20,7 +20,7 @@ def needs_build():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "scl_engine.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", h) for h in ("scl_engine.h", "scl_rowkey.h", "scl_wire.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

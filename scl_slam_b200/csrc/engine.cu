@@ -313,7 +313,7 @@ int scdist_dev(scl_engine* e, Lane& ln, const float* q_desc, const int32_t* q_lo
     }
     StageTimer st(e, 2, ln.stream);
     CK(scl_launch_scdist(e->d_desc, e->d_cstat, q_desc, q_stat, q_local, q_ids, cand_local, cand_ids, e->world, e->rank, Q, K, R, S, e->search_radius,
-                         cand_dist, cand_shift, best_id, best_dist, best_shift, ln.scdist_owned_hint, e->scdist_exact_all ? 1 : 0, ln.stream));
+                         cand_dist, cand_shift, best_id, best_dist, best_shift, e->world > 1 ? ln.scdist_owned_hint : e->scdist_tiles, e->scdist_exact_all ? 1 : 0, ln.stream));
     return SCL_OK;
 }
 
@@ -509,6 +509,14 @@ int scl_set_scdist_mode(scl_engine* e, int mode)
     LOCK();
     if (mode != 0 && mode != 1) FAIL(SCL_ERR_INVALID, "mode must be 0 (FP32 prefilter + exact evaluation of the shifts that can win) or 1 (every shift exactly)");
     e->scdist_exact_all = mode == 1;
+    return SCL_OK;
+}
+
+int scl_set_scdist_tiles(scl_engine* e, int tiles)
+{
+    LOCK();
+    if (tiles != 0 && (tiles < 2 || tiles > 16)) FAIL(SCL_ERR_INVALID, "0 (one tile per candidate) or 2..16 candidate tiles per CTA");
+    e->scdist_tiles = tiles;
     return SCL_OK;
 }
 

@@ -38,6 +38,7 @@ struct scl_engine {
     int n = 0, cap = 0;
     float *d_desc = nullptr, *d_keys = nullptr, *d_knorm = nullptr;
     double* d_cstat = nullptr;             /* [cap][2*S]: sector key | column norms of every entry (K4's per-entry cache) */
+    int scdist_tiles = 0;                  /* scl_set_scdist_tiles: candidate tiles per K4 CTA on an unsharded engine (0 = one per candidate) */
     bool scdist_exact_all = false;         /* scl_set_scdist_mode(1): K4 evaluates every shift in FP64 */
     float* d_kn2max = nullptr;             /* device scalar: largest squared ring-key norm in the database */
     unsigned char* d_kimg = nullptr;       /* tensor-core key image: 128-key tiles in the tcgen05 operand layout (k3_knn_tc.cu) */

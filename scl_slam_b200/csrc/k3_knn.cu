@@ -329,10 +329,11 @@ cudaError_t scl_launch_knn_exact(const float* qkeys, int Q, const float* keys, i
 {
     if (Q <= 0) return cudaSuccess;
     if (K < 1 || K > kMaxK) return cudaErrorInvalidValue;
-    if (!qlist && Q <= 8 && ws.tickets && (R == 20 || R == 40)) {       /* a handful of queries: thread = key */
+    if (!qlist && Q <= 8 && ws.tickets && (R == 20 || R == 40 || R == 80)) {       /* a handful of queries: thread = key */
         bool done = false;
         const cudaError_t e = R == 20 ? launch_exact_small<20>(qkeys, Q, keys, n_db, K, metric, id_mul, id_add, ws, out_ids, out_d2, stream, &done)
-                                      : launch_exact_small<40>(qkeys, Q, keys, n_db, K, metric, id_mul, id_add, ws, out_ids, out_d2, stream, &done);
+                            : R == 40 ? launch_exact_small<40>(qkeys, Q, keys, n_db, K, metric, id_mul, id_add, ws, out_ids, out_d2, stream, &done)
+                                      : launch_exact_small<80>(qkeys, Q, keys, n_db, K, metric, id_mul, id_add, ws, out_ids, out_d2, stream, &done);
         if (e != cudaSuccess || done) return e;
     }
     const int splits = scl_knn_splits(Q, n_db);
@@ -376,4 +377,7 @@ void scl_preload_k3()
     SCL_TOUCH((knn_exact_small_kernel<20, 0, 16>)); SCL_TOUCH((knn_exact_small_kernel<20, 1, 16>)); SCL_TOUCH((knn_exact_small_kernel<20, 0, 32>)); SCL_TOUCH((knn_exact_small_kernel<20, 1, 32>));
     SCL_TOUCH((knn_exact_small_kernel<40, 0, 16>)); SCL_TOUCH((knn_exact_small_kernel<40, 1, 16>)); SCL_TOUCH((knn_exact_small_kernel<40, 0, 32>)); SCL_TOUCH((knn_exact_small_kernel<40, 1, 32>));
     SCL_TOUCH(gather_rows_kernel); SCL_TOUCH(ids_to_local_kernel);
+    /* the 80-row keys of the row-key family (rowkey.cu) */
+    SCL_TOUCH((knn_exact_kernel<80, 0>)); SCL_TOUCH((knn_exact_kernel<80, 1>));
+    SCL_TOUCH((knn_exact_small_kernel<80, 0, 16>)); SCL_TOUCH((knn_exact_small_kernel<80, 1, 16>)); SCL_TOUCH((knn_exact_small_kernel<80, 0, 32>)); SCL_TOUCH((knn_exact_small_kernel<80, 1, 32>));
 }

@@ -151,19 +151,25 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 template <int R> struct TcCfg {
-    static constexpr int KTOT = (3 * R + 3 + 15) / 16 * 16;   /* GEMM K: 64 at R = 20, 128 at R = 40 */
+    /* Keys longer than 40 values (the 80-row keys of the Lidar-Iris family, descriptor.h:1087-1250) are handled as SEGS segments of
+     * RS values: the score is the sum of the segments' partial scores, i.e. ONE accumulation over SEGS key sub-tiles, which
+     * stream through the same 32 KB stages (the whole 256-key x 256-column operand would not fit beside the queries). */
+    static constexpr int SEGS = R > 40 ? R / 20 : 1;
+    static constexpr int RS = R / SEGS;                       /* key values per segment */
+    static constexpr int KTOT = (3 * RS + 3 + 15) / 16 * 16;  /* GEMM K per segment: 64 at RS = 20, 128 at RS = 40 */
     static constexpr int CHUNKS = KTOT / 8;                   /* 16-byte K chunks per row */
-    static constexpr int KSTEPS = KTOT / 16;                  /* tcgen05.mma instructions per 128x128 tile */
+    static constexpr int KSTEPS = KTOT / 16;                  /* tcgen05.mma instructions per 128x256 tile and segment */
     static constexpr uint32_t SBO = 128;                      /* 8-row core-matrix groups follow each other */
     static constexpr uint32_t LBO_A = 128 * 16;               /* distance between 16-byte K chunks: rows x 16 B */
     static constexpr uint32_t LBO_B = kNT * 16;
-    static constexpr uint32_t TILE_A = 128 * KTOT * 2;        /* one query tile: 16 KB / 32 KB */
-    static constexpr uint32_t TILE_B = kNT * KTOT * 2;        /* one key tile: 32 KB / 64 KB */
-    static constexpr int NSTAGE = R <= 20 ? 5 : 2;            /* most key tiles in flight in shared memory (the launch may ask for fewer) */
+    static constexpr uint32_t TILE_A = 128 * KTOT * 2;        /* one query tile, one segment: 16 KB / 32 KB */
+    static constexpr uint32_t TILE_B = kNT * KTOT * 2;        /* one key tile, one segment: 32 KB / 64 KB */
+    static constexpr uint32_t IMG_TILE = SEGS * TILE_B;       /* one key tile of the image: its segments one after the other */
+    static constexpr int NSTAGE = R <= 20 ? 5 : (SEGS > 1 ? 3 : 2);   /* most key (sub-)tiles in flight in shared memory (the launch may ask for fewer) */
     static constexpr uint32_t OFF_BAR = 0;                    /* mbarriers, tmem slot, flags */
     static constexpr uint32_t OFF_THR = 1024;                 /* [256] union bounds */
-    static constexpr uint32_t OFF_A = 2048;                   /* two query tiles */
-    static constexpr uint32_t OFF_B = OFF_A + 2 * TILE_A;
+    static constexpr uint32_t OFF_A = 2048;                   /* two query tiles x SEGS segments */
+    static constexpr uint32_t OFF_B = OFF_A + 2 * SEGS * TILE_A;
     static constexpr uint32_t TOTAL = OFF_B + NSTAGE * TILE_B;
     static constexpr uint32_t total(int stages) { return OFF_B + (uint32_t)stages * TILE_B; }
     /* D = F32, A = B = BF16, both K-major, N = kNT, M = 128 */
@@ -187,31 +193,36 @@ __global__ void __launch_bounds__(128) key_image_kernel(const float* __restrict_
                                                         unsigned char* __restrict__ img)
 {
     using C = TcCfg<R>;
+    constexpr int RS = C::RS;
     const int key = k_lo + blockIdx.x * 128 + threadIdx.x;
     if (key >= k_hi) return;
-    float k0[R], k1[R], nn[3];
-#pragma unroll
-    for (int g = 0; g < R / 4; g++) {
-        const float4 x = __ldg(reinterpret_cast<const float4*>(keys + (size_t)key * R) + g);
-        const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            k0[4 * g + i] = bf16_round(xs[i]);
-            k1[4 * g + i] = bf16_round(xs[i] - k0[4 * g + i]);
-        }
-    }
     const float n = __ldg(knorm + key);
-    nn[0] = bf16_round(n); nn[1] = bf16_round(n - nn[0]); nn[2] = bf16_round(n - nn[0] - nn[1]);
     const int row = key % kNT;
-    unsigned char* dst = img + (size_t)(key / kNT) * C::TILE_B + (uint32_t)(row >> 3) * C::SBO + (uint32_t)(row & 7) * 16;
+#pragma unroll 1
+    for (int seg = 0; seg < C::SEGS; seg++) {
+        float k0[RS], k1[RS], nn[3];
 #pragma unroll
-    for (int c = 0; c < C::CHUNKS; c++) {
-        uint4 v;
-        v.x = pack_bf16x2(b_column<R>(k0, k1, nn, 8 * c + 0), b_column<R>(k0, k1, nn, 8 * c + 1));
-        v.y = pack_bf16x2(b_column<R>(k0, k1, nn, 8 * c + 2), b_column<R>(k0, k1, nn, 8 * c + 3));
-        v.z = pack_bf16x2(b_column<R>(k0, k1, nn, 8 * c + 4), b_column<R>(k0, k1, nn, 8 * c + 5));
-        v.w = pack_bf16x2(b_column<R>(k0, k1, nn, 8 * c + 6), b_column<R>(k0, k1, nn, 8 * c + 7));
-        *reinterpret_cast<uint4*>(dst + (uint32_t)c * C::LBO_B) = v;
+        for (int g = 0; g < RS / 4; g++) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(keys + (size_t)key * R + seg * RS) + g);
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                k0[4 * g + i] = bf16_round(xs[i]);
+                k1[4 * g + i] = bf16_round(xs[i] - k0[4 * g + i]);
+            }
+        }
+        /* the squared norm of the whole key travels with the first segment */
+        nn[0] = seg == 0 ? bf16_round(n) : 0.0f; nn[1] = seg == 0 ? bf16_round(n - nn[0]) : 0.0f; nn[2] = seg == 0 ? bf16_round(n - nn[0] - nn[1]) : 0.0f;
+        unsigned char* dst = img + (size_t)(key / kNT) * C::IMG_TILE + (uint32_t)seg * C::TILE_B + (uint32_t)(row >> 3) * C::SBO + (uint32_t)(row & 7) * 16;
+#pragma unroll
+        for (int c = 0; c < C::CHUNKS; c++) {
+            uint4 v;
+            v.x = pack_bf16x2(b_column<RS>(k0, k1, nn, 8 * c + 0), b_column<RS>(k0, k1, nn, 8 * c + 1));
+            v.y = pack_bf16x2(b_column<RS>(k0, k1, nn, 8 * c + 2), b_column<RS>(k0, k1, nn, 8 * c + 3));
+            v.z = pack_bf16x2(b_column<RS>(k0, k1, nn, 8 * c + 4), b_column<RS>(k0, k1, nn, 8 * c + 5));
+            v.w = pack_bf16x2(b_column<RS>(k0, k1, nn, 8 * c + 6), b_column<RS>(k0, k1, nn, 8 * c + 7));
+            *reinterpret_cast<uint4*>(dst + (uint32_t)c * C::LBO_B) = v;
+        }
     }
 }
 
@@ -302,36 +313,40 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (threadIdx.x < kQPerCta) {
-        /* A operand: rows = the CTA's 256 queries, columns [-2 q0 | -2 q0 | -2 q1 | 1 1 1 0..]. One thread per row: its key
-         * is fetched with R/4 independent 16-byte loads (one L2 round trip), split, and written as CHUNKS 16-byte stores. */
+        /* A operand: rows = the CTA's 256 queries, columns [-2 q0 | -2 q0 | -2 q1 | 1 1 1 0..] per segment. One thread per row: its key
+         * segment is fetched with RS/4 independent 16-byte loads (one L2 round trip), split, and written as CHUNKS 16-byte stores. */
+        constexpr int RS = C::RS;
         const int m = threadIdx.x, qi = q_base + m;
-        float a0[R], a1[R];                             /* -2 q0, -2 q1 */
-#pragma unroll
-        for (int g = 0; g < R / 4; g++) {
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (qi < Q) x = __ldg(reinterpret_cast<const float4*>(qkeys + (size_t)qi * R) + g);
-            const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const float q0 = bf16_round(xs[i]);
-                a0[4 * g + i] = -2.0f * q0;
-                a1[4 * g + i] = -2.0f * bf16_round(xs[i] - q0);
-            }
-        }
-        const float one = qi < Q ? 1.0f : 0.0f;
         const int r = m & 127;
-        unsigned char* dst = smem + C::OFF_A + (uint32_t)(m >> 7) * C::TILE_A + (uint32_t)(r >> 3) * C::SBO + (uint32_t)(r & 7) * 16;
+#pragma unroll 1
+        for (int seg = 0; seg < C::SEGS; seg++) {
+            float a0[RS], a1[RS];                           /* -2 q0, -2 q1 */
 #pragma unroll
-        for (int c = 0; c < C::CHUNKS; c++) {
-            float v[8];
+            for (int g = 0; g < RS / 4; g++) {
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (qi < Q) x = __ldg(reinterpret_cast<const float4*>(qkeys + (size_t)qi * R + seg * RS) + g);
+                const float xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int idx = 8 * c + j;              /* compile-time after unrolling */
-                v[j] = idx < R ? a0[idx < R ? idx : 0] : idx < 2 * R ? a0[idx < 2 * R && idx >= R ? idx - R : 0]
-                     : idx < 3 * R ? a1[idx < 3 * R && idx >= 2 * R ? idx - 2 * R : 0] : idx < 3 * R + 3 ? one : 0.0f;
+                for (int i = 0; i < 4; i++) {
+                    const float q0 = bf16_round(xs[i]);
+                    a0[4 * g + i] = -2.0f * q0;
+                    a1[4 * g + i] = -2.0f * bf16_round(xs[i] - q0);
+                }
             }
-            *reinterpret_cast<uint4*>(dst + (uint32_t)c * C::LBO_A) =
-                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            const float one = qi < Q ? 1.0f : 0.0f;
+            unsigned char* dst = smem + C::OFF_A + (uint32_t)((m >> 7) * C::SEGS + seg) * C::TILE_A + (uint32_t)(r >> 3) * C::SBO + (uint32_t)(r & 7) * 16;
+#pragma unroll
+            for (int c = 0; c < C::CHUNKS; c++) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int idx = 8 * c + j;              /* compile-time after unrolling */
+                    v[j] = idx < RS ? a0[idx < RS ? idx : 0] : idx < 2 * RS ? a0[idx < 2 * RS && idx >= RS ? idx - RS : 0]
+                         : idx < 3 * RS ? a1[idx < 3 * RS && idx >= 2 * RS ? idx - 2 * RS : 0] : idx < 3 * RS + 3 ? one : 0.0f;
+                }
+                *reinterpret_cast<uint4*>(dst + (uint32_t)c * C::LBO_A) =
+                    make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            }
         }
     }
     fence_async_smem();
@@ -517,13 +532,20 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     } else if (warp == 1) {
         // ===== TMA issuer: one thread, one bulk copy per key tile =======================================
         if (lane == 0) {
-            const unsigned char* src = img + (size_t)range * C::TILE_B;
-            const size_t step = (size_t)n_ranges * C::TILE_B;
+            /* One copy per key tile, or, for segmented keys, per (key tile, query tile, segment) in the order the MMA issuer
+             * consumes them: the segments of a key tile pass through the ring once for each of the two query tiles. */
+            const unsigned char* src = img + (size_t)range * C::IMG_TILE;
+            const size_t step = (size_t)n_ranges * C::IMG_TILE;
+            constexpr int kPerTile = C::SEGS > 1 ? 2 * C::SEGS : 1;
+            int ld = 0;
             for (int tile = 0; tile < n_tiles; tile++) {
-                const int b = tile % NS; const uint32_t ph = (tile / NS) & 1;
-                scl_mbar_wait(&empty[b], ph ^ 1u);
-                scl_mbar_expect_tx(&full[b], C::TILE_B);
-                scl_bulk_g2s(smem + C::OFF_B + (uint32_t)b * C::TILE_B, src + (size_t)tile * step, C::TILE_B, &full[b]);
+#pragma unroll 1
+                for (int j = 0; j < kPerTile; j++, ld++) {
+                    const int b = ld % NS; const uint32_t ph = (ld / NS) & 1;
+                    scl_mbar_wait(&empty[b], ph ^ 1u);
+                    scl_mbar_expect_tx(&full[b], C::TILE_B);
+                    scl_bulk_g2s(smem + C::OFF_B + (uint32_t)b * C::TILE_B, src + (size_t)tile * step + (size_t)(j % C::SEGS) * C::TILE_B, C::TILE_B, &full[b]);
+                }
             }
         }
         __syncwarp();
@@ -532,29 +554,57 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         if (lane == 0) {
             const uint32_t a_base = scl_smem_u32(smem + C::OFF_A), b_base = scl_smem_u32(smem + C::OFF_B);
             long long t_te = 0, t_fu = 0, c0 = 0;
+            int ld = 0;                                             /* key (sub-)tiles consumed so far */
             for (int it = 0; it < n_tiles; it++) {
-                const int b = it % NS; const uint32_t bph = (it / NS) & 1;
-                if (TIMES) c0 = clock64();
-                scl_mbar_wait(&full[b], bph);                       /* key tile landed */
-                if (TIMES) { const long long c1 = clock64(); t_fu += c1 - c0; c0 = c1; }
-                const uint32_t bs = b_base + (uint32_t)b * C::TILE_B;
+                if (C::SEGS == 1) {
+                    const int b = ld % NS; const uint32_t bph = (ld / NS) & 1;
+                    ld++;
+                    if (TIMES) c0 = clock64();
+                    scl_mbar_wait(&full[b], bph);                       /* key tile landed */
+                    if (TIMES) { const long long c1 = clock64(); t_fu += c1 - c0; c0 = c1; }
+                    const uint32_t bs = b_base + (uint32_t)b * C::TILE_B;
 #pragma unroll
-                for (int qt = 0; qt < 2; qt++) {
-                    /* accumulator drained by its four epilogue warps? This one thread SPINS (a sleeping try_wait wakes up late:
-                     * measured 5 us per batch); a bound turns a protocol bug into a trap instead of a hung GPU */
-                    if (!mbar_test(&tempty[qt], (uint32_t)((it & 1) ^ 1))) {
-                        const long long w0 = clock64();
-                        while (!mbar_test(&tempty[qt], (uint32_t)((it & 1) ^ 1))) { if (clock64() - w0 > (4ll << 30)) __trap(); }
+                    for (int qt = 0; qt < 2; qt++) {
+                        /* accumulator drained by its four epilogue warps? This one thread SPINS (a sleeping try_wait wakes up late:
+                         * measured 5 us per batch); a bound turns a protocol bug into a trap instead of a hung GPU */
+                        if (!mbar_test(&tempty[qt], (uint32_t)((it & 1) ^ 1))) {
+                            const long long w0 = clock64();
+                            while (!mbar_test(&tempty[qt], (uint32_t)((it & 1) ^ 1))) { if (clock64() - w0 > (4ll << 30)) __trap(); }
+                        }
+                        tc_fence_after();
+                        const uint32_t d = tmem_base + (uint32_t)(qt * kNT);
+                        const uint32_t as = a_base + (uint32_t)qt * C::TILE_A;
+#pragma unroll
+                        for (int k = 0; k < C::KSTEPS; k++)
+                            if (!(dev_flags & 4)) tc_mma_bf16(d, make_desc(as + 2 * k * C::LBO_A, C::LBO_A, C::SBO), make_desc(bs + 2 * k * C::LBO_B, C::LBO_B, C::SBO), C::IDESC, k > 0 ? 1u : 0u);
+                        tc_commit(&tfull[qt]);                          /* accumulator ready for the epilogue */
                     }
-                    tc_fence_after();
-                    const uint32_t d = tmem_base + (uint32_t)(qt * kNT);
-                    const uint32_t as = a_base + (uint32_t)qt * C::TILE_A;
+                    tc_commit(&empty[b]);                               /* key tile reusable once these MMAs retire */
+                } else {
+                    /* segmented keys: per query tile, the SEGS sub-tiles of the key tile accumulate into one score */
+#pragma unroll 1
+                    for (int qt = 0; qt < 2; qt++) {
+                        if (!mbar_test(&tempty[qt], (uint32_t)((it & 1) ^ 1))) {
+                            const long long w0 = clock64();
+                            while (!mbar_test(&tempty[qt], (uint32_t)((it & 1) ^ 1))) { if (clock64() - w0 > (4ll << 30)) __trap(); }
+                        }
+                        tc_fence_after();
+                        const uint32_t d = tmem_base + (uint32_t)(qt * kNT);
+#pragma unroll 1
+                        for (int seg = 0; seg < C::SEGS; seg++, ld++) {
+                            const int b = ld % NS; const uint32_t bph = (ld / NS) & 1;
+                            scl_mbar_wait(&full[b], bph);
+                            tc_fence_after();
+                            const uint32_t bs = b_base + (uint32_t)b * C::TILE_B;
+                            const uint32_t as = a_base + (uint32_t)(qt * C::SEGS + seg) * C::TILE_A;
 #pragma unroll
-                    for (int k = 0; k < C::KSTEPS; k++)
-                        if (!(dev_flags & 4)) tc_mma_bf16(d, make_desc(as + 2 * k * C::LBO_A, C::LBO_A, C::SBO), make_desc(bs + 2 * k * C::LBO_B, C::LBO_B, C::SBO), C::IDESC, k > 0 ? 1u : 0u);
-                    tc_commit(&tfull[qt]);                          /* accumulator ready for the epilogue */
+                            for (int k = 0; k < C::KSTEPS; k++)
+                                tc_mma_bf16(d, make_desc(as + 2 * k * C::LBO_A, C::LBO_A, C::SBO), make_desc(bs + 2 * k * C::LBO_B, C::LBO_B, C::SBO), C::IDESC, (seg > 0 || k > 0) ? 1u : 0u);
+                            tc_commit(&empty[b]);                       /* sub-tile reusable once these MMAs retire */
+                        }
+                        tc_commit(&tfull[qt]);
+                    }
                 }
-                tc_commit(&empty[b]);                               /* key tile reusable once these MMAs retire */
                 if (TIMES) { const long long c1 = clock64(); t_te += c1 - c0; }
             }
             if (TIMES) { times[(size_t)blockIdx.x * 16 + 6] = t_fu; times[(size_t)blockIdx.x * 16 + 7] = t_te; times[(size_t)blockIdx.x * 16 + 8] = n_tiles; }
@@ -613,7 +663,7 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
     __shared__ float sh_d[kRrWarps][kMaxSel];           /* exact distances / ids of the keys that can still make the top-K */
     __shared__ int sh_id[kRrWarps][kMaxSel];
     __shared__ int sh_pre[kRrWarps][kMaxRanges + 1];
-    __shared__ float sh_q[kRrWarps][64];
+    __shared__ float sh_q[kRrWarps][96];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qi = blockIdx.x * kRrWarps + warp;
     if (qi >= Q) return;                                /* whole warp */
@@ -626,6 +676,7 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
     const int direct = __ldg(slots + (size_t)qi * kSlotStride + kDirect);
     const float qv = lane < R ? __ldg(qkeys + (size_t)qi * R + lane) : 0.0f;
     const float qv2 = (R > 32 && lane + 32 < R) ? __ldg(qkeys + (size_t)qi * R + lane + 32) : 0.0f;
+    const float qv3 = (R > 64 && lane + 64 < R) ? __ldg(qkeys + (size_t)qi * R + lane + 64) : 0.0f;
     const float knmax = __ldg(kn2max);
     constexpr int kCntPerLane = (kMaxRanges + 31) / 32;
     int cnt[kCntPerLane];
@@ -645,6 +696,7 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
     if (qi == 0 && lane == 0) *next_fail_count = 0;
     if (lane < R) s_q[lane] = qv;
     if (R > 32 && lane + 32 < R) s_q[lane + 32] = qv2;
+    if (R > 64 && lane + 64 < R) s_q[lane + 64] = qv3;
     bool overflow = false;
     int carry = 0;                                      /* exclusive prefix sums of the counts, 32 ranges at a time */
 #pragma unroll
@@ -663,6 +715,59 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
     __syncwarp();
     const int total = carry;
     if (dev_flags & 128) { if (lane == 0) out_ids[(size_t)qi * K] = total; return; }
+    float qn = 0.0f;
+    for (int d = 0; d < R; d++) qn = fmaf(s_q[d], s_q[d], qn);
+    const float sn = sqrtf(qn) + sqrtf(knmax);
+    const float eps0 = 3.0517578125e-05f * sn * sn;                 /* 2^-15 (|q| + |k|max)^2 */
+    /* Which groups VOTE in the bounds below. A group's minimum is the prefilter score of one of its keys, a distinct key per
+     * group. It counts as "a neighbour this close exists" unless (a) the group straddles the search bound (the minimum may
+     * belong to a key outside it) or (b), libnabo flavour, the key may be one the self-match rule removes (exact
+     * d2 <= FLT_EPSILON, i.e. score + |q|^2 <= FLT_EPSILON + eps). Groups that do not vote are always kept. */
+    const float self_lim = FLT_EPSILON + eps0 - qn;
+    /* A long queue (a smooth trajectory: the union bound is only as tight as the K'-th nearest TILE, and every key of the
+     * dozen tiles around the query's place passes it) is cut down before anything is stored: the K-th smallest voting group
+     * minimum m_K over ALL queued groups is undercut by K distinct keys, so the K-th nearest neighbour has exact
+     * d2 <= m_K + |q|^2 + eps and a voting group above m_K + 2 eps holds no key that can reach or tie with the top-K.
+     * One streaming pass: every lane keeps the K smallest of its share in registers, K rounds of warp minimum merge them. */
+    float cut_t = cut;
+    if (4 * total > kMaxGroups) {
+        float best[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) best[i] = inf;
+        int lo2 = 0;
+        for (int g = lane; g < total; g += 32) {
+            while (s_pre[lo2 + 1] <= g) lo2++;
+            const uint4* ep = hq + ((size_t)qi * n_ranges + lo2) * (size_t)(2 * kQueueCap) + 2 * (g - s_pre[lo2]);
+            const uint4 a = __ldcg(ep);
+            const uint32_t b = __ldcg(reinterpret_cast<const uint32_t*>(ep + 1));
+            const float gm[4] = {__uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w), __uint_as_float(b)};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int key = (int)a.x + 8 * j;
+                const bool votes = key + 7 < n_db && gm[j] == gm[j] && (METRIC == 0 || gm[j] > self_lim);
+                float v = votes ? gm[j] : inf;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {           /* bubble v through the sorted list (registers: no dynamic indexing) */
+                    if (i < K) { const float lw = fminf(best[i], v); v = fmaxf(best[i], v); best[i] = lw; }
+                }
+            }
+        }
+        const int inf_img = ordered_int(inf);
+        float mk = inf; int have = 0;
+        for (int r = 0; r < K; r++) {
+            const int head = ordered_int(best[0]);
+            const int w = __reduce_min_sync(0xffffffffu, head);
+            if (w >= inf_img) break;
+            const unsigned holders = __ballot_sync(0xffffffffu, head == w);      /* equal minima are distinct keys: one is taken per round */
+            if (lane == __ffs(holders) - 1) {
+#pragma unroll
+                for (int i = 0; i < 15; i++) best[i] = best[i + 1];
+                best[15] = inf;
+            }
+            mk = ordered_float(w); have++;
+        }
+        if (have == K) cut_t = fminf(cut, mk + 2.0f * eps0);
+    }
     /* second trip(s): the queue entries, UE per lane in flight; survivors are compacted with a ballot */
     int n_grp = 0;
     constexpr int UE = 4;
@@ -686,7 +791,8 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
 #pragma unroll
             for (int j = 0; j < 4; j++) {               /* the four 8-key groups of the chunk */
                 const int key = (int)ea[u].x + 8 * j;
-                const bool keep = gm[j] <= cut && key < n_db && ea[u].x != 0x7fffffffu;
+                const bool votes = key + 7 < n_db && (METRIC == 0 || gm[j] > self_lim);
+                const bool keep = gm[j] <= (votes ? cut_t : cut) && key < n_db && ea[u].x != 0x7fffffffu;
                 const unsigned m = __ballot_sync(0xffffffffu, keep);
                 const int pos = n_grp + __popc(m & lt_mask);
                 if (keep && pos < kMaxGroups) { s_key[pos] = key; s_g[pos] = gm[j]; }
@@ -697,24 +803,19 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
     if (n_grp > kMaxGroups) { overflow = true; n_grp = kMaxGroups; }
     __syncwarp();
     if (dev_flags & 256) { if (lane == 0) out_ids[(size_t)qi * K] = n_grp; return; }
-    float qn = 0.0f;
-    for (int d = 0; d < R; d++) qn = fmaf(s_q[d], s_q[d], qn);
-    const float sn = sqrtf(qn) + sqrtf(knmax);
-    const float eps0 = 3.0517578125e-05f * sn * sn;                 /* 2^-15 (|q| + |k|max)^2 */
     /* a certified top-K lies wholly below cut + |q|^2 (see below): keys at or above it need not enter the selection */
     const float d_lim = cut < inf ? cut + qn : inf;
-    /* Second, tighter filter before the key rows are fetched (nanoflann flavour only: libnabo's self-match rule can remove
-     * keys from the result). Every surviving group's minimum is the score of a distinct key, so the K-th smallest minimum
-     * m_K is undercut by K keys: the K-th nearest neighbour has exact d2 <= m_K + |q|^2 + eps, and a group whose minimum
-     * exceeds m_K + 2 eps holds no key that can beat it. About K of the ~3 K' groups remain. Groups that straddle the
-     * search bound may owe their minimum to a key outside it: they do not vote for m_K and are always kept. */
-    if (METRIC == 0 && n_grp > K && n_grp <= kMaxGroups) {
+    /* Second, tighter filter before the key rows are fetched. Every surviving voting group's minimum is the score of a
+     * distinct key that is a valid neighbour, so the K-th smallest such minimum m_K is undercut by K keys: the K-th nearest
+     * neighbour has exact d2 <= m_K + |q|^2 + eps, and a voting group whose minimum exceeds m_K + 2 eps holds no key that
+     * can beat it. About K of the ~3 K' groups remain. Groups that do not vote (see above) are always kept. */
+    if (n_grp > K && n_grp <= kMaxGroups) {
         constexpr int kPer = kMaxGroups / 32;          /* groups per lane */
         unsigned v[kPer]; bool whole[kPer];
 #pragma unroll
         for (int j = 0; j < kPer; j++) {
             const int c = lane + 32 * j;
-            whole[j] = c < n_grp && s_key[c] + 7 < n_db;
+            whole[j] = c < n_grp && s_key[c] + 7 < n_db && (METRIC == 0 || s_g[c] > self_lim);
             /* scores can be negative: order-preserving unsigned image of the float */
             const unsigned b = c < n_grp ? __float_as_uint(s_g[c]) : 0u;
             v[j] = whole[j] ? (b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u)) : 0xffffffffu;
@@ -757,7 +858,7 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
     }
     float worst_err = 0.0f;
     int n_sel = 0;
-    constexpr int UK = R <= 20 ? 4 : 2;                 /* key rows in flight per lane */
+    constexpr int UK = R <= 20 ? 4 : (R <= 40 ? 2 : 1); /* key rows in flight per lane */
     for (int base = 0; base < n_grp * 8; base += 32 * UK) {
         float4 kv[UK][R / 4];
         int id[UK];
@@ -849,7 +950,7 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
         bool certified = !overflow;
         if (cut < inf) {
             /* dropped keys have S >= cut, i.e. exact d2 > cut + |q|^2 - eps */
-            const float eps = eps0 + 2.0e-6f * dK;                  /* + exact-side rounding */
+            const float eps = eps0 + 1.0e-7f * (float)R * dK;       /* + exact-side rounding: R sequential float additions */
             certified = certified && (found == K) && (dK + eps < cut + qn);
         }
         if (!certified) { fail_list[atomicAdd(fail_count, 1)] = q_off + qi; atomicAdd(next_fail_count + 8, 1); }   /* + the engine's running total (third counter of the block) */
@@ -869,7 +970,7 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
 
 } // namespace
 
-bool scl_knn_tc_supported(int R) { return R == 20 || R == 40; }
+bool scl_knn_tc_supported(int R) { return R == 20 || R == 40 || R == 80; }
 
 int scl_knn_tc_ranges(int Q)
 {
@@ -884,7 +985,7 @@ size_t scl_knn_tc_queue_bytes() { return (size_t)kQueueCap * 32; }          /* p
 size_t scl_knn_tc_image_bytes(int R, int n_keys)
 {
     const size_t tiles = ((size_t)n_keys + kNT - 1) / kNT;
-    return tiles * (R == 20 ? TcCfg<20>::TILE_B : TcCfg<40>::TILE_B);
+    return tiles * (R == 20 ? TcCfg<20>::IMG_TILE : R == 40 ? TcCfg<40>::IMG_TILE : TcCfg<80>::IMG_TILE);
 }
 
 cudaError_t scl_launch_key_image(const float* keys, const float* knorm, int k_lo, int k_hi, int R, unsigned char* img, cudaStream_t stream)
@@ -893,6 +994,7 @@ cudaError_t scl_launch_key_image(const float* keys, const float* knorm, int k_lo
     const int blocks = (k_hi - k_lo + 127) / 128;
     if (R == 20) key_image_kernel<20><<<blocks, 128, 0, stream>>>(keys, knorm, k_lo, k_hi, img);
     else if (R == 40) key_image_kernel<40><<<blocks, 128, 0, stream>>>(keys, knorm, k_lo, k_hi, img);
+    else if (R == 80) key_image_kernel<80><<<blocks, 128, 0, stream>>>(keys, knorm, k_lo, k_hi, img);
     else return cudaErrorNotSupported;
     return cudaGetLastError();
 }
@@ -965,7 +1067,7 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
                                int32_t* fail_list, int* fail_count, int* next_fail_count, bool init_state, int stages, cudaStream_t stream)
 {
     if (Q <= 0) return cudaSuccess;
-    if (R != 20 && R != 40) return cudaErrorNotSupported;
+    if (!scl_knn_tc_supported(R)) return cudaErrorNotSupported;
     if (K > kKPrime - 2) return cudaErrorInvalidValue;
     cudaError_t err = cudaSuccess;
     const int max_b = scl_knn_tc_max_batch();
@@ -981,7 +1083,8 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
         if ((size_t)Qc * n_ranges > ws.capacity) return cudaErrorInvalidValue;
         const float* qk = qkeys + (size_t)q0 * R;
         if (R == 20) err = launch_tc<20>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint4*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), kprime_for(K), K, stages, stream);
-        else err = launch_tc<40>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint4*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), kprime_for(K), K, stages, stream);
+        else if (R == 40) err = launch_tc<40>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint4*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), kprime_for(K), K, stages, stream);
+        else err = launch_tc<80>(qk, Qc, img, n_db, n_ranges, ws.slots, reinterpret_cast<uint4*>(ws.hq), ws.hq_cnt, reinterpret_cast<int*>(ws.err_probe), kprime_for(K), K, stages, stream);
         if (err != cudaSuccess) return err;
 #define SCL_RERANK(M, RR)                                                                                                              \
     SCL_PREFER_SMEM((knn_rerank_kernel<M, RR>));                                                                                          \
@@ -991,7 +1094,8 @@ cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, cons
         const int dev_flags = dev_flags_env();     /* 0 in release builds */
         if (dev_flags & 16) {}
         else if (R == 20) { if (metric == 0) { SCL_RERANK(0, 20); } else { SCL_RERANK(1, 20); } }
-        else { if (metric == 0) { SCL_RERANK(0, 40); } else { SCL_RERANK(1, 40); } }
+        else if (R == 40) { if (metric == 0) { SCL_RERANK(0, 40); } else { SCL_RERANK(1, 40); } }
+        else { if (metric == 0) { SCL_RERANK(0, 80); } else { SCL_RERANK(1, 80); } }
 #undef SCL_RERANK
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;
@@ -1025,4 +1129,9 @@ void scl_preload_k3_tc()
     SCL_TOUCH(key_image_kernel<20>); SCL_TOUCH(key_image_kernel<40>);
     SCL_TOUCH((knn_tc_kernel<20, false>)); SCL_TOUCH((knn_tc_kernel<40, false>));
     SCL_TOUCH((knn_rerank_kernel<0, 20>)); SCL_TOUCH((knn_rerank_kernel<1, 20>)); SCL_TOUCH((knn_rerank_kernel<0, 40>)); SCL_TOUCH((knn_rerank_kernel<1, 40>));
+}
+
+void scl_preload_k3_tc80()
+{
+    SCL_TOUCH(key_image_kernel<80>); SCL_TOUCH((knn_tc_kernel<80, false>)); SCL_TOUCH((knn_rerank_kernel<0, 80>)); SCL_TOUCH((knn_rerank_kernel<1, 80>));
 }

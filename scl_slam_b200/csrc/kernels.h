@@ -117,5 +117,6 @@ cudaError_t scl_launch_xchg_combine(const XchgView& x, int seq, int Q, int K, co
 void scl_preload_k1();
 void scl_preload_k3();
 void scl_preload_k3_tc();
+void scl_preload_k3_tc80();   /* the 80-row variant (row-key family, rowkey.cu) */
 void scl_preload_k4();
 void scl_preload_k7();

@@ -289,3 +289,77 @@ def assemble_submap(clouds, poses6, leaf):
     out = np.empty((max(pts.shape[0], 1), 4), np.float32)
     m = lib.sco_assemble_submap(pts.reshape(-1), offs, len(clouds), st, poses.reshape(-1), leaf, out.reshape(-1))
     return out[:m].copy()
+
+
+# ---- row-key candidate stage of lidar_iris_descriptor (oracle/rowkey_oracle.h) ------------------------------------------
+IRIS_REF_SO = os.path.join(ORACLE_DIR, "_ref", "libiris_ref.so")
+_iris_libs = {}
+
+
+def have_iris_ref():
+    return os.path.exists(IRIS_REF_SO)
+
+
+def _load_iris(kind):
+    if kind not in _iris_libs:
+        lib = C.CDLL(PORT_SO if kind == "port" else IRIS_REF_SO)
+        lib.sco_iris_create.restype = C.c_void_p
+        lib.sco_iris_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int]
+        lib.sco_iris_destroy.argtypes = [C.c_void_p]
+        lib.sco_iris_save.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, C.c_float]
+        for f in (lib.sco_iris_detect_intra, lib.sco_iris_detect_inter):
+            f.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_int), _i32p, _f32p]
+        lib.sco_iris_get_index.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.sco_iris_size.restype = C.c_int
+        lib.sco_iris_size.argtypes = [C.c_void_p, C.c_int]
+        lib.sco_iris_knn_batch.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _f32p]
+        _iris_libs[kind] = lib
+    return _iris_libs[kind]
+
+
+def iris_compare(feat_a, tag_a, feat_b, tag_b):
+    """The stand-in compare() both oracle libraries use (rowkey_oracle.h): float |fa - fb|, bias (7 ta + 13 tb) % 360."""
+    return float(np.abs(np.float32(feat_a) - np.float32(feat_b))), (7 * int(tag_a) + 13 * int(tag_b)) % 360
+
+
+class IrisOracle:
+    """kind="port": oracle/rowkey_oracle.cpp; kind="ref": the reference's own text (oracle/_ref/libiris_ref.so)."""
+
+    def __init__(self, rows=80, num_exclude_recent=30, num_candidates=10, dist_thres=0.32, robot_num=1, this_id=0, kind="port"):
+        self.lib = _load_iris(kind)
+        self.K, self.rows = num_candidates, rows
+        self.h = self.lib.sco_iris_create(rows, num_exclude_recent, num_candidates, dist_thres, robot_num, this_id)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.sco_iris_destroy(self.h)
+            self.h = None
+
+    def save(self, key, robot, index, feature):
+        self.lib.sco_iris_save(self.h, np.ascontiguousarray(key, np.float32), robot, index, float(feature))
+
+    def _detect(self, fn, cur):
+        i, b, n = C.c_int(), C.c_float(), C.c_int()
+        cand = np.full(self.K, -1, np.int32); d2 = np.full(self.K, np.inf, np.float32)
+        fn(self.h, cur, C.byref(i), C.byref(b), C.byref(n), cand, d2)
+        return i.value, b.value, n.value, cand, d2
+
+    def detect_intra(self, cur):
+        return self._detect(self.lib.sco_iris_detect_intra, cur)
+
+    def detect_inter(self, cur):
+        return self._detect(self.lib.sco_iris_detect_inter, cur)
+
+    def get_index(self, key):
+        r, i = C.c_int(), C.c_int()
+        self.lib.sco_iris_get_index(self.h, key, C.byref(r), C.byref(i))
+        return r.value, i.value
+
+    def size(self, id_in=-1):
+        return self.lib.sco_iris_size(self.h, id_in)
+
+    def knn_batch(self, q_keys, robot, n, K, threads=1):
+        q = np.ascontiguousarray(q_keys, np.float32).reshape(-1, self.rows)
+        idx = np.empty((q.shape[0], K), np.int32); d2 = np.empty((q.shape[0], K), np.float32)
+        self.lib.sco_iris_knn_batch(self.h, q, q.shape[0], robot, n, K, threads, idx, d2)
+        return idx, d2

@@ -1,5 +1,5 @@
 """CPU-side checks of the drop-in boundary: the C-ABI library builds for sm_100a, loads, and
-exports every symbol include/scl_engine.h and include/scl_wire.h declare; without a GPU the engine refuses to come up
+exports every symbol include/scl_engine.h, include/scl_wire.h and include/scl_rowkey.h declare; without a GPU the engine refuses to come up
 (no CPU fallback). No compute calls here."""
 import ctypes as C
 import os
@@ -20,16 +20,17 @@ def lib():
 
 def test_header_symbols_all_exported(lib):
     from scl_slam_b200 import engine
-    hdr = open(os.path.join(ROOT, "include", "scl_engine.h")).read() + open(os.path.join(ROOT, "include", "scl_wire.h")).read()
-    declared = set(re.findall(r"\b(scl_[a-z_0-9]+)\s*\(", hdr))
-    assert declared == set(engine.EXPORTS), declared ^ set(engine.EXPORTS)
+    from scl_slam_b200 import rowkey
+    hdr = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("scl_engine.h", "scl_wire.h", "scl_rowkey.h"))
+    declared = set(re.findall(r"\b(scl_[a-z_0-9]+)\s*\(", hdr)) - {"scl_rowkey_compare_fn"}
+    assert declared == set(engine.EXPORTS) | set(rowkey.EXPORTS), declared ^ (set(engine.EXPORTS) | set(rowkey.EXPORTS))
     for name in declared:
         assert hasattr(lib, name), name
 
 
 def test_every_entry_point_is_in_the_integration_map():
     """INTEGRATION.md §2 maps each C-ABI entry point to the reference member it stands in for."""
-    hdr = open(os.path.join(ROOT, "include", "scl_engine.h")).read() + open(os.path.join(ROOT, "include", "scl_wire.h")).read()
+    hdr = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("scl_engine.h", "scl_wire.h", "scl_rowkey.h"))
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     missing = sorted(n for n in set(re.findall(r"\b(scl_[a-z_0-9]+)\s*\(", hdr)) if n not in doc)
     assert not missing, missing

@@ -664,14 +664,16 @@ def test_scdist_modes_agree_on_random_batches(eng_mod):
     db = synth.desc_db(5000, seed=81)
     q, _, _ = synth.desc_queries(db, 700, seed=82, noise_sigma=0.3, dropout=0.1)
     out = []
-    for mode in (0, 1):
+    for mode, tiles in ((0, 0), (1, 0), (0, 4), (0, 6)):
         e = eng_mod.ScanContextB200(numCandidates=10)
         e.set_scdist_mode(mode)
+        e.set_scdist_tiles(tiles)
         e.insert_batch(db.numpy())
         out.append(e.query_batch(q_desc=q.numpy(), K=10, n_db=5000))
-    for k in ("cand_ids", "cand_shift", "best_id", "best_shift"):
-        assert np.array_equal(out[0][k], out[1][k]), k
-    assert np.array_equal(_bits(out[0]["cand_dist"]), _bits(out[1]["cand_dist"]))
+    for other in out[1:]:
+        for k in ("cand_ids", "cand_shift", "best_id", "best_shift"):
+            assert np.array_equal(out[0][k], other[k]), k
+        assert np.array_equal(_bits(out[0]["cand_dist"]), _bits(other["cand_dist"]))
 
 
 def _k4_pairs(e, q, cand):
@@ -723,14 +725,15 @@ def test_scdist_all_pairs_adversarial(eng_mod, R, S, ratio):
     for i in range(q.shape[0]):
         for j in range(n):
             exp_d[i, j], exp_s[i, j] = o.distance_raw(q[i], db[j])
-    for mode in (0, 1):
+    for mode, tiles in ((0, 0), (1, 0), (0, 4), (1, 4), (0, 8)):   # tiles: candidates per CTA pass (scl_set_scdist_tiles), 4 = the small CTAs
         e = eng_mod.ScanContextB200(numRing=R, numSector=S, searchRatio=ratio)
         e.set_scdist_mode(mode)
+        e.set_scdist_tiles(tiles)
         e.insert_batch(db)
         dist, shift = _k4_pairs(e, q, cand)
         bad = _bits(dist) != _bits(exp_d)
-        assert not bad.any(), (mode, np.argwhere(bad)[:5], dist[bad][:5], exp_d[bad][:5])
-        assert np.array_equal(shift, exp_s), (mode, np.argwhere(shift != exp_s)[:5])
+        assert not bad.any(), (mode, tiles, np.argwhere(bad)[:5], dist[bad][:5], exp_d[bad][:5])
+        assert np.array_equal(shift, exp_s), (mode, tiles, np.argwhere(shift != exp_s)[:5])
 
 
 def test_lanes_concurrent_batches_equal_sequential(eng_mod):
@@ -861,3 +864,33 @@ def test_insert_and_query_from_two_threads(eng_mod):
     a, b = e.query_batch(q_desc=q, K=K), fresh.query_batch(q_desc=q, K=K)
     for k in a:
         assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_tensor_core_knn_on_a_smooth_trajectory(eng_mod, metric):
+    """One long smooth trajectory (ring keys drift slowly from keyframe to keyframe, places revisited once): the K nearest
+    keys of a query are temporal neighbours in the same key tile and every key of the dozen tiles around them passes the
+    prefilter's union bound. The re-rank's streaming cut (K-th smallest group minimum over the whole queue) has to keep
+    such queries on the tensor-core path, in both kNN flavours; results equal the exact kernel's."""
+    dev = torch.device("cuda", 0)
+    n, nq, K = 120000, 512, 10
+    g = torch.Generator(device="cpu").manual_seed(123)
+    base = synth.desc_db(1, seed=124)[0]                                   # one plausible descriptor
+    drift = torch.cumsum(torch.randn(n, 20, 1, generator=g) * 0.05, dim=0)  # per-ring height drift along the trajectory
+    half = n // 2
+    drift[half:] = drift[:half] + torch.randn(half, 20, 1, generator=g) * 0.01   # the second lap revisits the first
+    db = (base[None] + drift).clamp_min(0.0).float().contiguous()
+    src = torch.randint(0, n, (nq,), generator=g)
+    q = (db[src] + torch.randn(nq, 20, 60, generator=g) * 0.01).clamp_min(0.0).float().contiguous()
+    out = {}
+    for mode in (1, 2):
+        e = eng_mod.ScanContextB200(numCandidates=K)
+        e.set_knn_mode(mode, True)
+        e.insert_batch_dev(db.to(dev))
+        ids = torch.empty((nq, K), dtype=torch.int32, device=dev); d2 = torch.empty((nq, K), dtype=torch.float32, device=dev)
+        e.knn_batch_dev(q.to(dev), nq, K, n, metric, ids, d2)
+        torch.cuda.synchronize()
+        out[mode] = (ids.cpu().numpy(), d2.cpu().numpy(), e.knn_stats())
+    assert np.array_equal(out[1][0], out[2][0]) and np.array_equal(out[1][1].view(np.uint32), out[2][1].view(np.uint32))
+    st = out[2][2]
+    assert st["tc_queries"] == nq and st["fallback_queries"] <= nq // 20, st
