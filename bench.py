@@ -28,6 +28,7 @@ robots, 40x120) and a robustness arm on C3 (trajectory-ordered database, half th
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -515,6 +516,12 @@ def arm_robustness(engine, synth, dev, pk, depth):
     res["workload"] = "c3 robustness: 1,048,576 entries ordered like a trajectory (runs of 16 near-duplicate neighbours), 50 % of the queries match nothing"
     res["fallback_queries"] = res["knn"]["fallback_queries"]
     e.close()
+    # the harder ordering: ONE smooth trajectory (neighbouring ring keys millimetres apart, places revisited every 400 000 keyframes)
+    e, res2, _, _ = query_arm(engine, synth, dev, pk, N_DB, synth.desc_db_smooth, 5, depth, no_match_fraction=0.5)
+    res2["workload"] = "c3 robustness: 1,048,576 entries of one smooth trajectory (ring keys drift by millimetres per keyframe, every place seen two or three times), 50 % of the queries match nothing"
+    res2["fallback_queries"] = res2["knn"]["fallback_queries"]
+    e.close()
+    res["smooth_trajectory"] = res2
     return res
 
 
@@ -718,8 +725,79 @@ def arm_c1(engine, synth, dev, pk, cpu):
     return res
 
 
+def _smooth_keys(n, rows, seed, dev, start=0):
+    """Row keys of one smooth trajectory: per row a level plus three slow sinusoids in the keyframe index (synth.desc_db_smooth's drift)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    lvl = (0.5 + 5.5 * torch.rand(rows, generator=g)).to(dev)
+    amp = (0.3 + 1.2 * torch.rand(rows, 3, generator=g)).to(dev)
+    per = (3000.0 + 27000.0 * torch.rand(rows, 3, generator=g)).to(dev)
+    ph = torch.rand(rows, 3, generator=g).to(dev)
+    t = torch.arange(start, start + n, device=dev, dtype=torch.float64).view(-1, 1, 1)
+    k = lvl + (amp.double() * torch.sin(2 * math.pi * (t / per.double() + ph.double()))).sum(-1).float()
+    return (k + 0.01 * torch.randn(n, rows, device=dev, generator=torch.Generator(device=dev).manual_seed(seed + 1))).clamp_min(0.0).contiguous()
+
+
+@guarded
+def arm_rowkey(dev, pk, cpu):
+    """the row-key candidate search of the Lidar-Iris family (descriptor.h:1150-1209), 80-float keys, this robot's
+    batch of 1024 queries against the keys of two other robots (2 x 393,216), top-10, libnabo flavour."""
+    from scl_slam_b200 import rowkey
+    rows, n_other, nq = 80, 393216, Q
+    e = rowkey.LidarIrisRowKeysB200(rows=rows, numCandidates=K, robotNum=3, thisID=0)
+    e.set_stream(torch.cuda.current_stream().cuda_stream)
+    keys = {r: _smooth_keys(n_other, rows, 300 + r, dev) for r in (1, 2)}
+    for r in (1, 2):
+        e.save_batch(keys[r].cpu().numpy(), r)
+    g = torch.Generator(device="cpu").manual_seed(9)
+    src = torch.randint(0, n_other, (nq,), generator=g).to(dev)
+    q = (keys[1][src] + 0.02 * torch.randn(nq, rows, device=dev, generator=torch.Generator(device=dev).manual_seed(10))).clamp_min(0.0).contiguous()
+    idx = torch.empty((nq, K), dtype=torch.int32, device=dev); d2 = torch.empty((nq, K), dtype=torch.float32, device=dev)
+    res = {"workload": f"row keys: {rows}-float keys, 1024 queries of robot 0 against robots 1 and 2 ({n_other} keys each, smooth trajectories), top-{K}, libnabo flavour"}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for mode, name in ((2, "tensor_core"), (1, "exact")):
+        for _ in range(3):
+            e.knn_batch_dev(q, nq, 0, 0, K, mode, idx, d2)
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+        for a, b in evs:
+            flush.zero_()
+            a.record(); e.knn_batch_dev(q, nq, 0, 0, K, mode, idx, d2); b.record()
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+        alg = 4 * rows * 2 * n_other
+        res[name] = {"value": nq / (ms * 1e-3), "unit": "queries/s", "ms_per_batch": ms,
+                     "roofline": {"bound": "hbm", "algorithmic_bytes": alg, "achieved": alg / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / pk["hbm"]},
+                     "tensor_equivalent_tflops": 2.0 * rows * nq * 2 * n_other / (ms * 1e-3) / 1e12}
+        res[name + "_ids"] = idx.cpu().numpy().copy()
+    res["identical_lists"] = bool(np.array_equal(res.pop("tensor_core_ids"), res["exact_ids"]))
+    res["knn"] = e.knn_stats()
+    res["value"], res["unit"] = res["tensor_core"]["value"], "queries/s"
+    gpu_ids = res.pop("exact_ids")
+    if cpu:
+        oracle_lib, _ = _oracle(("port",))
+        o = oracle_lib.IrisOracle(rows=rows, num_candidates=K, robot_num=3, this_id=0)
+        sample = 32
+        hk = keys[1].cpu().numpy()
+        for i in range(n_other):
+            o.save(hk[i], 1, i, 0.0)
+        cores = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        ci, cd = o.knn_batch(q[:sample].cpu().numpy(), 1, n_other, K, threads=cores)
+        dt = time.perf_counter() - t0
+        # robot 1 comes first in the concatenation: its keys keep their positions; compare where robot 2 holds none of the top-K
+        only1 = (gpu_ids[:sample] < n_other).all(axis=1)
+        res["cpu_baseline"] = {"value": sample / dt / 2.0, "unit": "queries/s", "cores": cores, "kind": "port",
+                               "sample": f"{sample} queries against robot 1's {n_other} keys (half the key set: the figure is halved), linear scan with libnabo's rules; "
+                                         "the reference also rebuilds its KD-tree on every call (descriptor.h:1199), which is not charged here",
+                               "same_lists_where_comparable": bool(np.array_equal(ci[only1], gpu_ids[:sample][only1])), "comparable": int(only1.sum())}
+    e.close()
+    return res
+
+
 def other_configs(engine, synth, dev, pk, cpu, depth):
     out = {}
+    out["rowkey_lidar_iris_r80"] = arm_rowkey(dev, pk, cpu)
+    torch.cuda.empty_cache()
     out["c3_robustness"] = arm_robustness(engine, synth, dev, pk, depth)
     torch.cuda.empty_cache()
     out["c2_hdl64_db20k"] = arm_c2(engine, synth, dev, pk, cpu, depth)

@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(kTQ) knn_exact_kernel(const float* __restrict_
                                                         const int32_t* __restrict__ qlist, const int* __restrict__ qcount,
                                                         int32_t* __restrict__ part_ids, float* __restrict__ part_d2,
                                                         int* __restrict__ tickets /* [query tiles], zero between launches */,
-                                                        int32_t* __restrict__ out_ids, float* __restrict__ out_d2)
+                                                        int32_t* __restrict__ out_ids, float* __restrict__ out_d2,
+                                                        int min_count /* lists of up to this many queries were taken by knn_exact_small_kernel */)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* sk = reinterpret_cast<float*>(smem_raw);                 /* [kTK][R] */
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(kTQ) knn_exact_kernel(const float* __restrict_
     const int t = threadIdx.x;
     /* optional indirection: only the queries in qlist[0..*qcount) (the tensor-core path's fallback) */
     const int nq = qlist ? *qcount : Q;
-    if (blockIdx.y * kTQ >= nq) return;
+    if (blockIdx.y * kTQ >= nq || (qlist && nq <= min_count)) return;
     const int slot = blockIdx.y * kTQ + t;
     const bool active = slot < nq;
     const int qi = active ? (qlist ? qlist[slot] : slot) : 0;
@@ -185,13 +186,22 @@ template <int R, int METRIC, int KPT>
 __global__ void __launch_bounds__(kSmallThreads) knn_exact_small_kernel(const float* __restrict__ qkeys, const float* __restrict__ keys, int n_db,
                                                                         int K, int split_len, int id_mul, int id_add, int32_t* __restrict__ part_ids,
                                                                         float* __restrict__ part_d2, int* __restrict__ tickets,
-                                                                        int32_t* __restrict__ out_ids, float* __restrict__ out_d2)
+                                                                        int32_t* __restrict__ out_ids, float* __restrict__ out_d2,
+                                                                        const int32_t* __restrict__ qlist, const int* __restrict__ qcount)
 {
     __shared__ float s_d[kSmallThreads / 32];
     __shared__ int s_i[kSmallThreads / 32];
     __shared__ int s_last;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int qi = blockIdx.y;
+    /* optional indirection: the queries qlist[0 .. *qcount) when there are at most gridDim.y of them (the tensor-core path's
+     * uncertified queries: a handful, if any; a longer list is left to knn_exact_kernel) */
+    const int slot = blockIdx.y;
+    int qi = slot;
+    if (qlist) {
+        const int c = *qcount;
+        if (c > (int)gridDim.y || slot >= c) return;
+        qi = qlist[slot];
+    }
     const float inf = __int_as_float(0x7f800000);
     float q[R];
 #pragma unroll
@@ -211,7 +221,7 @@ __global__ void __launch_bounds__(kSmallThreads) knn_exact_small_kernel(const fl
         }
         d[i] = dd;
     }
-    const size_t o = ((size_t)qi * gridDim.x + blockIdx.x) * K;
+    const size_t o = ((size_t)slot * gridDim.x + blockIdx.x) * K;
     int r = 0;
     for (; r < K; r++) {
         float bd = inf; int bi = 0x7fffffff;
@@ -239,20 +249,22 @@ __global__ void __launch_bounds__(kSmallThreads) knn_exact_small_kernel(const fl
     if (t == 0) {
         for (; r < K; r++) { part_d2[o + r] = inf; part_ids[o + r] = 0x7fffffff; }
         __threadfence();
-        s_last = (atomicAdd(&tickets[qi], 1) == (int)gridDim.x - 1);
+        s_last = (atomicAdd(&tickets[slot], 1) == (int)gridDim.x - 1);
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (t == 0) tickets[qi] = 0;
+    if (t == 0) tickets[slot] = 0;
     if (warp == 0)
-        merge_splits_warp(part_ids + (size_t)qi * gridDim.x * K, part_d2 + (size_t)qi * gridDim.x * K, (int)gridDim.x, K, lane,
+        merge_splits_warp(part_ids + (size_t)slot * gridDim.x * K, part_d2 + (size_t)slot * gridDim.x * K, (int)gridDim.x, K, lane,
                           out_ids + (size_t)qi * K, out_d2 + (size_t)qi * K);
 }
 
+constexpr int kSmallList = 16;        /* uncertified queries of a tensor-core batch that the thread-per-key kernel takes */
 template <int R>
 cudaError_t launch_exact_small(const float* qkeys, int Q, const float* keys, int n_db, int K, int metric, int id_mul, int id_add,
-                               KnnWorkspace ws, int32_t* out_ids, float* out_d2, cudaStream_t stream, bool* done)
+                               KnnWorkspace ws, int32_t* out_ids, float* out_d2, cudaStream_t stream, bool* done,
+                               const int32_t* qlist = nullptr, const int* qcount = nullptr)
 {
     *done = false;
     int splits = (n_db + 1023) / 1024;
@@ -261,10 +273,11 @@ cudaError_t launch_exact_small(const float* qkeys, int Q, const float* keys, int
     int split_len = (n_db + splits - 1) / splits;
     split_len = (split_len + kSmallThreads - 1) / kSmallThreads * kSmallThreads;
     const int kpt = split_len / kSmallThreads;
+    if (qlist) Q = kSmallList;                                                       /* slots; CTAs beyond the list length exit at once */
     if (kpt > 32 || (size_t)Q * splits * K > ws.capacity) return cudaSuccess;        /* the general kernel takes it */
     dim3 grid(splits, Q);
 #define SCL_SMALL(M, P) SCL_PREFER_SMEM((knn_exact_small_kernel<R, M, P>)); knn_exact_small_kernel<R, M, P><<<grid, kSmallThreads, 0, stream>>>(qkeys, keys, n_db, K, split_len, id_mul, id_add, ws.part_ids, \
-                                                                                          ws.part_d2, ws.tickets, out_ids, out_d2)
+                                                                                          ws.part_d2, ws.tickets, out_ids, out_d2, qlist, qcount)
     if (kpt <= 16) { if (metric == 0) { SCL_SMALL(0, 16); } else { SCL_SMALL(1, 16); } }
     else { if (metric == 0) { SCL_SMALL(0, 32); } else { SCL_SMALL(1, 32); } }
 #undef SCL_SMALL
@@ -294,18 +307,18 @@ __global__ void ids_to_local_kernel(const int32_t* __restrict__ ids, int n, int 
 template <int R>
 cudaError_t launch_exact(const float* qkeys, int Q, const float* keys, int n_db, int K, int metric, int splits, int split_len,
                          int id_mul, int id_add, const int32_t* qlist, const int* qcount, KnnWorkspace ws, int32_t* out_ids, float* out_d2,
-                         cudaStream_t stream)
+                         cudaStream_t stream, int min_count)
 {
     const size_t smem = (size_t)kTK * R * 4 + (size_t)K * kTQ * 8;
     dim3 grid(splits, (Q + kTQ - 1) / kTQ);
     if (metric == 0) {
         SCL_PREFER_SMEM((knn_exact_kernel<R, 0>));
         knn_exact_kernel<R, 0><<<grid, kTQ, smem, stream>>>(qkeys, Q, keys, n_db, K, split_len, id_mul, id_add, qlist, qcount, ws.part_ids, ws.part_d2,
-                                                            ws.tickets, out_ids, out_d2);
+                                                            ws.tickets, out_ids, out_d2, min_count);
     } else {
         SCL_PREFER_SMEM((knn_exact_kernel<R, 1>));
         knn_exact_kernel<R, 1><<<grid, kTQ, smem, stream>>>(qkeys, Q, keys, n_db, K, split_len, id_mul, id_add, qlist, qcount, ws.part_ids, ws.part_d2,
-                                                            ws.tickets, out_ids, out_d2);
+                                                            ws.tickets, out_ids, out_d2, min_count);
     }
     return cudaGetLastError();
 }
@@ -329,12 +342,16 @@ cudaError_t scl_launch_knn_exact(const float* qkeys, int Q, const float* keys, i
 {
     if (Q <= 0) return cudaSuccess;
     if (K < 1 || K > kMaxK) return cudaErrorInvalidValue;
-    if (!qlist && Q <= 8 && ws.tickets && (R == 20 || R == 40 || R == 80)) {       /* a handful of queries: thread = key */
+    int min_count = 0;
+    if ((qlist || Q <= 8) && ws.tickets && (R == 20 || R == 40 || R == 80)) {
+        /* a handful of queries — the reference's own call pattern, or the uncertified queries of a tensor-core batch (thread =
+         * query would take 8.5 ms for six queries on a million smooth keys; thread = key takes 0.2) */
         bool done = false;
-        const cudaError_t e = R == 20 ? launch_exact_small<20>(qkeys, Q, keys, n_db, K, metric, id_mul, id_add, ws, out_ids, out_d2, stream, &done)
-                            : R == 40 ? launch_exact_small<40>(qkeys, Q, keys, n_db, K, metric, id_mul, id_add, ws, out_ids, out_d2, stream, &done)
-                                      : launch_exact_small<80>(qkeys, Q, keys, n_db, K, metric, id_mul, id_add, ws, out_ids, out_d2, stream, &done);
-        if (e != cudaSuccess || done) return e;
+        const cudaError_t e = R == 20 ? launch_exact_small<20>(qkeys, Q, keys, n_db, K, metric, id_mul, id_add, ws, out_ids, out_d2, stream, &done, qlist, qcount)
+                            : R == 40 ? launch_exact_small<40>(qkeys, Q, keys, n_db, K, metric, id_mul, id_add, ws, out_ids, out_d2, stream, &done, qlist, qcount)
+                                      : launch_exact_small<80>(qkeys, Q, keys, n_db, K, metric, id_mul, id_add, ws, out_ids, out_d2, stream, &done, qlist, qcount);
+        if (e != cudaSuccess || (done && !qlist)) return e;
+        if (done) min_count = kSmallList;               /* longer lists: the kernel below */
     }
     const int splits = scl_knn_splits(Q, n_db);
     int split_len = (n_db + splits - 1) / splits;
@@ -342,10 +359,10 @@ cudaError_t scl_launch_knn_exact(const float* qkeys, int Q, const float* keys, i
     if (split_len < kTK) split_len = kTK;
     if ((size_t)Q * splits * K > ws.capacity || !ws.tickets) return cudaErrorInvalidValue;
     cudaError_t err;
-    if (R == 20) err = launch_exact<20>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, out_ids, out_d2, stream);
-    else if (R == 40) err = launch_exact<40>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, out_ids, out_d2, stream);
-    else if (R == 10) err = launch_exact<10>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, out_ids, out_d2, stream);
-    else if (R == 80) err = launch_exact<80>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, out_ids, out_d2, stream);
+    if (R == 20) err = launch_exact<20>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, out_ids, out_d2, stream, min_count);
+    else if (R == 40) err = launch_exact<40>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, out_ids, out_d2, stream, min_count);
+    else if (R == 10) err = launch_exact<10>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, out_ids, out_d2, stream, min_count);
+    else if (R == 80) err = launch_exact<80>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, out_ids, out_d2, stream, min_count);
     else return cudaErrorNotSupported;
     return err;
 }

@@ -300,6 +300,21 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
     const int n_tiles_all = (key_hi + kNT - 1) / kNT;
     const int n_tiles = range < n_tiles_all ? (n_tiles_all - range + n_ranges - 1) / n_ranges : 0;
     const int n_service = min(n_ranges, n_tiles_all);                         /* ranges that hold keys */
+    /* ... and in a scattered order: the it-th tile a CTA visits is its (it * stride mod n_tiles)-th, stride about 0.618 n_tiles and
+     * coprime to it (a low-discrepancy walk). On a smooth trajectory a sweep in key order approaches the query's place
+     * monotonically: every new tile undercuts the bound so far, every chunk of it is queued and the queues churn; visited in
+     * scattered order the first few tiles already sample the whole trajectory and the bound settles early. */
+    int tile_stride = 1;
+    if (n_tiles > 2) {
+        tile_stride = (int)(0.6180339887f * (float)n_tiles);
+        if (tile_stride < 1) tile_stride = 1;
+        while (true) {
+            int a = tile_stride, b = n_tiles;
+            while (b) { const int t = a % b; a = b; b = t; }
+            if (a == 1) break;
+            tile_stride++;
+        }
+    }
     // ---- one-time setup -----------------------------------------------------------------------
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; s++) { scl_mbar_init(&full[s], 1); scl_mbar_init(&empty[s], 1); }
@@ -433,8 +448,10 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
         // the load of the next chunk is in flight while the current one is examined, and the accumulator is handed back to the
         // MMA issuer as soon as its last chunk is in registers.
 #pragma unroll 1
+        int tile_pos = 0;                                   /* it * tile_stride mod n_tiles */
         for (int it = 0; it < n_tiles; it++) {
-            const int key0 = (range + it * n_ranges) * kNT;
+            const int key0 = (range + tile_pos * n_ranges) * kNT;
+            tile_pos += tile_stride; if (tile_pos >= n_tiles) tile_pos -= n_tiles;
             if (it > 0) {
                 long long p0 = 0;
                 if (TIMES) p0 = clock64();
@@ -537,8 +554,8 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
             const unsigned char* src = img + (size_t)range * C::IMG_TILE;
             const size_t step = (size_t)n_ranges * C::IMG_TILE;
             constexpr int kPerTile = C::SEGS > 1 ? 2 * C::SEGS : 1;
-            int ld = 0;
-            for (int tile = 0; tile < n_tiles; tile++) {
+            int ld = 0, tile = 0;
+            for (int it = 0; it < n_tiles; it++) {
 #pragma unroll 1
                 for (int j = 0; j < kPerTile; j++, ld++) {
                     const int b = ld % NS; const uint32_t ph = (ld / NS) & 1;
@@ -546,6 +563,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_tc_kernel(
                     scl_mbar_expect_tx(&full[b], C::TILE_B);
                     scl_bulk_g2s(smem + C::OFF_B + (uint32_t)b * C::TILE_B, src + (size_t)tile * step + (size_t)(j % C::SEGS) * C::TILE_B, C::TILE_B, &full[b]);
                 }
+                tile += tile_stride; if (tile >= n_tiles) tile -= n_tiles;
             }
         }
         __syncwarp();
@@ -645,7 +663,8 @@ __device__ __forceinline__ float exact_d2(const float* __restrict__ q, const flo
 // prefix sums in the warp's shared memory), every lane reads a few independent entries per trip, the 8 keys of every
 // surviving group (best score at or below the cut) are re-scored exactly, four rows per lane in flight, and the warp
 // selects the top-K and certifies it.
-constexpr int kMaxGroups = 256;                         /* surviving groups per query (about 3 K' are expected: the cut is the LARGEST of K' slot minima) */
+constexpr int kMaxGroups = 512;                         /* surviving groups per query the list holds (about 3 K' are expected: the cut is the LARGEST of K' slot minima) */
+constexpr int kFilterGroups = 256;                      /* the second filter handles lists up to this long; longer ones are cut by the streaming pass first */
 constexpr int kMaxRanges = 160;
 constexpr int kMaxSel = 512;                            /* keys entering the top-K selection */
 constexpr int kRrWarps = 4;                             /* queries per CTA */
@@ -724,13 +743,48 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
      * belong to a key outside it) or (b), libnabo flavour, the key may be one the self-match rule removes (exact
      * d2 <= FLT_EPSILON, i.e. score + |q|^2 <= FLT_EPSILON + eps). Groups that do not vote are always kept. */
     const float self_lim = FLT_EPSILON + eps0 - qn;
-    /* A long queue (a smooth trajectory: the union bound is only as tight as the K'-th nearest TILE, and every key of the
-     * dozen tiles around the query's place passes it) is cut down before anything is stored: the K-th smallest voting group
+    /* The queue entries, UE per lane in flight; survivors are compacted with a ballot. If more groups survive the cut than the
+     * list holds (a smooth trajectory: the union bound is only as tight as the K'-th nearest TILE, and every key of the dozen
+     * tiles around the query's place passes it), the cut is tightened and the pass repeated: the K-th smallest voting group
      * minimum m_K over ALL queued groups is undercut by K distinct keys, so the K-th nearest neighbour has exact
-     * d2 <= m_K + |q|^2 + eps and a voting group above m_K + 2 eps holds no key that can reach or tie with the top-K.
-     * One streaming pass: every lane keeps the K smallest of its share in registers, K rounds of warp minimum merge them. */
+     * d2 <= m_K + |q|^2 + eps and a voting group above m_K + 2 eps holds no key that can reach or tie with the top-K
+     * (one streaming pass: every lane keeps the K smallest of its share in registers, K rounds of warp minimum merge them). */
     float cut_t = cut;
-    if (4 * total > kMaxGroups) {
+    int n_grp = 0;
+#pragma unroll 1
+    for (int attempt = 0; attempt < 2; attempt++) {
+        n_grp = 0;
+        constexpr int UE = 4;
+        int lo = 0;                                     /* the range that holds this lane's entry: advances monotonically */
+        for (int base = 0; base < total; base += 32 * UE) {
+            uint4 ea[UE]; uint32_t eb[UE];
+#pragma unroll
+            for (int u = 0; u < UE; u++) {
+                const int g = base + u * 32 + lane;
+                ea[u] = make_uint4(0x7fffffffu, 0x7f800000u, 0x7f800000u, 0x7f800000u); eb[u] = 0x7f800000u;
+                if (g < total) {
+                    while (s_pre[lo + 1] <= g) lo++;
+                    const uint4* ep = hq + ((size_t)qi * n_ranges + lo) * (size_t)(2 * kQueueCap) + 2 * (g - s_pre[lo]);
+                    ea[u] = __ldcg(ep);
+                    eb[u] = __ldcg(reinterpret_cast<const uint32_t*>(ep + 1));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UE; u++) {
+                const float gm[4] = {__uint_as_float(ea[u].y), __uint_as_float(ea[u].z), __uint_as_float(ea[u].w), __uint_as_float(eb[u])};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {           /* the four 8-key groups of the chunk */
+                    const int key = (int)ea[u].x + 8 * j;
+                    const bool votes = key + 7 < n_db && (METRIC == 0 || gm[j] > self_lim);
+                    const bool keep = gm[j] <= (votes ? cut_t : cut) && key < n_db && ea[u].x != 0x7fffffffu;
+                    const unsigned m = __ballot_sync(0xffffffffu, keep);
+                    const int pos = n_grp + __popc(m & lt_mask);
+                    if (keep && pos < kMaxGroups) { s_key[pos] = key; s_g[pos] = gm[j]; }
+                    n_grp += __popc(m);
+                }
+            }
+        }
+        if (n_grp <= kFilterGroups || attempt == 1) break;
         float best[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) best[i] = inf;
@@ -766,51 +820,21 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
             }
             mk = ordered_float(w); have++;
         }
-        if (have == K) cut_t = fminf(cut, mk + 2.0f * eps0);
-    }
-    /* second trip(s): the queue entries, UE per lane in flight; survivors are compacted with a ballot */
-    int n_grp = 0;
-    constexpr int UE = 4;
-    int lo = 0;                                         /* the range that holds this lane's entry: advances monotonically */
-    for (int base = 0; base < total; base += 32 * UE) {
-        uint4 ea[UE]; uint32_t eb[UE];
-#pragma unroll
-        for (int u = 0; u < UE; u++) {
-            const int g = base + u * 32 + lane;
-            ea[u] = make_uint4(0x7fffffffu, 0x7f800000u, 0x7f800000u, 0x7f800000u); eb[u] = 0x7f800000u;
-            if (g < total) {
-                while (s_pre[lo + 1] <= g) lo++;
-                const uint4* ep = hq + ((size_t)qi * n_ranges + lo) * (size_t)(2 * kQueueCap) + 2 * (g - s_pre[lo]);
-                ea[u] = __ldcg(ep);
-                eb[u] = __ldcg(reinterpret_cast<const uint32_t*>(ep + 1));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < UE; u++) {
-            const float gm[4] = {__uint_as_float(ea[u].y), __uint_as_float(ea[u].z), __uint_as_float(ea[u].w), __uint_as_float(eb[u])};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {               /* the four 8-key groups of the chunk */
-                const int key = (int)ea[u].x + 8 * j;
-                const bool votes = key + 7 < n_db && (METRIC == 0 || gm[j] > self_lim);
-                const bool keep = gm[j] <= (votes ? cut_t : cut) && key < n_db && ea[u].x != 0x7fffffffu;
-                const unsigned m = __ballot_sync(0xffffffffu, keep);
-                const int pos = n_grp + __popc(m & lt_mask);
-                if (keep && pos < kMaxGroups) { s_key[pos] = key; s_g[pos] = gm[j]; }
-                n_grp += __popc(m);
-            }
-        }
+        if (have < K || !(mk + 2.0f * eps0 < cut)) break;           /* nothing to gain: the query is redone exactly */
+        cut_t = mk + 2.0f * eps0;
+        __syncwarp();
     }
     if (n_grp > kMaxGroups) { overflow = true; n_grp = kMaxGroups; }
     __syncwarp();
     if (dev_flags & 256) { if (lane == 0) out_ids[(size_t)qi * K] = n_grp; return; }
     /* a certified top-K lies wholly below cut + |q|^2 (see below): keys at or above it need not enter the selection */
-    const float d_lim = cut < inf ? cut + qn : inf;
+    float d_lim = cut < inf ? cut + qn : inf;
     /* Second, tighter filter before the key rows are fetched. Every surviving voting group's minimum is the score of a
      * distinct key that is a valid neighbour, so the K-th smallest such minimum m_K is undercut by K keys: the K-th nearest
      * neighbour has exact d2 <= m_K + |q|^2 + eps, and a voting group whose minimum exceeds m_K + 2 eps holds no key that
      * can beat it. About K of the ~3 K' groups remain. Groups that do not vote (see above) are always kept. */
-    if (n_grp > K && n_grp <= kMaxGroups) {
-        constexpr int kPer = kMaxGroups / 32;          /* groups per lane */
+    if (n_grp > K && n_grp <= kFilterGroups) {
+        constexpr int kPer = kFilterGroups / 32;       /* groups per lane */
         unsigned v[kPer]; bool whole[kPer];
 #pragma unroll
         for (int j = 0; j < kPer; j++) {
@@ -860,6 +884,37 @@ __global__ void __launch_bounds__(32 * kRrWarps) knn_rerank_kernel(const float* 
     int n_sel = 0;
     constexpr int UK = R <= 20 ? 4 : (R <= 40 ? 2 : 1); /* key rows in flight per lane */
     for (int base = 0; base < n_grp * 8; base += 32 * UK) {
+        if (n_sel + 32 * UK > kMaxSel) {
+            /* The selection list is about to fill up (hundreds of keys within the prefilter's resolution of the K-th best: a
+             * flat stretch of a smooth trajectory). Keep its K best by (d2, id) and take their worst distance as the new
+             * limit: a later key enters only if it can still reach the top-K (equal distances included, the final selection
+             * decides them by id). */
+            for (int r = 0; r < K && r < n_sel; r++) {
+                float bd = inf; int bi = 0x7fffffff, bp = -1;
+                for (int c = r + lane; c < n_sel; c += 32) {
+                    const float d = s_d[c]; const int id = s_id[c];
+                    if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; bp = c; }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const float od = __shfl_xor_sync(0xffffffffu, bd, off); const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                    const int op = __shfl_xor_sync(0xffffffffu, bp, off);
+                    if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; bp = op; }
+                }
+                if (lane == 0 && bp >= 0 && bp != r) {
+                    const float td = s_d[r]; const int ti = s_id[r];
+                    s_d[r] = s_d[bp]; s_id[r] = s_id[bp]; s_d[bp] = td; s_id[bp] = ti;
+                }
+                __syncwarp();
+            }
+            if (n_sel > K) n_sel = K;
+            if (n_sel == K) {
+                const float dk = s_d[K - 1];
+                const float up = dk == 0.0f ? 1.0e-45f : __int_as_float(__float_as_int(dk) + 1);     /* distances are non-negative: the next float up */
+                d_lim = fminf(d_lim, up);
+            }
+            __syncwarp();
+        }
         float4 kv[UK][R / 4];
         int id[UK];
 #pragma unroll

@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libscl_b200.so")
+_SO = os.environ.get("SCL_B200_LIB") or os.path.join(_HERE, "libscl_b200.so")   # the override is for developer builds (tools/)
 
 SCL_OK = 0
 _STATUS = {1: "SCL_ERR_INVALID", 2: "SCL_ERR_CUDA", 3: "SCL_ERR_UNSUPPORTED", 4: "SCL_ERR_RANGE", 5: "SCL_ERR_NOMEM"}

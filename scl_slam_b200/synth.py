@@ -324,3 +324,31 @@ def desc_db_trajectory(n, num_ring=20, num_sector=60, seed=5, device="cpu", star
     out = torch.where(rot != 0, rot + 0.1 * g.view(n, R, S), rot)
     drop = _uniform(i.view(-1, 1) * (R * S) + bins, 54).view(n, R, S) < 0.01
     return torch.where(drop, torch.zeros_like(out), out).contiguous()
+
+
+def desc_db_smooth(n, num_ring=20, num_sector=60, seed=5, device="cpu", start=0, lap=400_000, chunk=65536):
+    """A database that is ONE long smooth trajectory (the second robustness arm of the bench): keyframe i sees the scene of
+    desc_db entry `seed` with every ring raised or lowered by a slowly varying amount (three sinusoids per ring with periods of
+    3 000 - 30 000 keyframes, amplitudes of 0.5 - 2 m), plus N(0, 0.02^2) per non-empty bin; the robot drives the same loop again
+    every `lap` keyframes, so places are revisited. Neighbouring ring keys differ by millimetres: the K nearest keys of a query
+    are its temporal neighbours, in the same key tile, and thousands of keys lie within any loose bound."""
+    R, S = num_ring, num_sector
+    dev = torch.device(device)
+    base = desc_db(1, R, S, seed=seed, device=dev)[0]                                     # [R,S]
+    rk = torch.arange(R * 3, device=dev, dtype=torch.int64) + seed * 0x3000005
+    amp = (0.5 + 1.5 * _uniform(rk, 61)).view(1, R, 3)
+    per = (3000.0 + 27000.0 * _uniform(rk, 62)).view(1, R, 3)
+    ph = _uniform(rk, 63).view(1, R, 3)
+    bins = torch.arange(R * S, device=dev, dtype=torch.int64).view(1, R * S)
+    out = torch.empty((n, R, S), dtype=torch.float32, device=dev)
+    for c0 in range(0, n, chunk):
+        c1 = min(n, c0 + chunk)
+        i = torch.arange(start + c0, start + c1, device=dev, dtype=torch.int64)
+        t = (i % lap).to(torch.float64).view(-1, 1, 1)
+        drift = (amp.double() * torch.sin(2 * math.pi * (t / per.double() + ph.double()))).sum(-1).float()      # [m,R]
+        u1 = _uniform(i.view(-1, 1) * (R * S) + bins, 64).clamp_min_(1e-7)
+        u2 = _uniform(i.view(-1, 1) * (R * S) + bins, 65)
+        g = (torch.sqrt(-2.0 * torch.log(u1)) * torch.cos(2 * math.pi * u2)).view(-1, R, S)
+        v = base.unsqueeze(0) + drift.unsqueeze(-1) + 0.02 * g
+        out[c0:c1] = torch.where(base.unsqueeze(0) != 0, v.clamp_min(0.05), torch.zeros_like(v))
+    return out

@@ -368,8 +368,10 @@ def test_tensor_core_knn_equals_oracle(eng_mod, R, S, K, n, nq, metric):
 
 def test_tensor_core_knn_fallback_on_ties(eng_mod):
     """Adversarial database: 1400 exact duplicates and near-duplicates around every query — more than the
-    re-rank's selection list holds (512 keys) — so the prefilter cannot certify a top-K; those queries must be
-    redone exactly and still match."""
+    re-rank's selection list holds (512 keys): the list is cut back to its K best whenever it fills, equal distances are
+    decided by id, and the result matches the oracle (until round 2 these queries had to be redone by the exact kernel).
+    Then a database in which libnabo's self-match rule leaves fewer than K neighbours: that cannot be certified, the
+    exact kernel redoes it, and the missing neighbours come out as the oracle reports them."""
     n, nq, K = 40000, 70, 10
     db = synth.desc_db(n, seed=93).numpy()
     rng = np.random.default_rng(5)
@@ -392,7 +394,22 @@ def test_tensor_core_knn_fallback_on_ties(eng_mod):
         assert np.array_equal(got["cand_ids"], exp["cand_ids"]), metric
         assert np.array_equal(_bits(got["cand_d2"]), _bits(exp["cand_d2"]))
         assert np.array_equal(got["best_id"], exp["best_id"]) and np.array_equal(got["best_shift"], exp["best_shift"])
-    assert e.knn_stats()["fallback_queries"] > 0
+    before = e.knn_stats()["fallback_queries"]
+    # 20 000 copies of one descriptor and five others: with libnabo's rule (metric 1) a query equal to the copies has five neighbours
+    n2 = 20000
+    db2 = np.repeat(db[1000:1001], n2, axis=0)
+    db2[[7, 5000, 9999, 15000, 19999]] = db[3000:3005]
+    q2 = np.repeat(db[1000:1001], 8, axis=0)
+    o2 = Oracle(num_candidates=K)
+    o2.bulk_load(np.concatenate([db2.reshape(n2, -1), q2.reshape(8, -1)]))
+    exp2 = o2.query_batch(np.arange(n2, n2 + 8), n2, K, 1, nthreads=8)
+    e2 = eng_mod.ScanContextB200(numCandidates=K)
+    e2.insert_batch(db2)
+    e2.set_knn_mode(2, True)
+    got2 = e2.query_batch(q_desc=q2, K=K, n_db=n2, metric=1)
+    assert np.array_equal(got2["cand_ids"], exp2["cand_ids"]) and (got2["cand_ids"][:, 5:] == -1).all()
+    assert np.array_equal(got2["best_id"], exp2["best_id"])
+    assert e2.knn_stats()["fallback_queries"] == 8 and before >= 0
 
 
 def test_pipelined_host_queries_equal_synchronous(eng_mod):
