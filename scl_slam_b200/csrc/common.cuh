@@ -43,48 +43,6 @@ __device__ __forceinline__ float scl_key_float(uint32_t k)
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// ---- float atan, bit-exact with glibc 2.39 atanf (fdlibm s_atanf) --------------------------
-// The reference's xy2theta calls atan(float) (descriptor.h:1357 with `using namespace std`,
-// :19). The oracle checks this sequence of IEEE operations against libm on all 2^32 inputs
-// (oracle/sc_oracle.cpp atanf_port, tests/test_oracle_ref.py). Every operation is an explicit
-// round-to-nearest intrinsic so the compiler can neither contract to FMA nor reassociate.
-__device__ __forceinline__ float scl_atanf(float x)
-{
-    const float atanhi[4] = {4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f};
-    const float atanlo[4] = {5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f};
-    const uint32_t hx = __float_as_uint(x), ix = hx & 0x7fffffffu;
-    int id;
-    if (ix >= 0x4c000000u) {
-        if (ix > 0x7f800000u) return __fadd_rn(x, x);
-        const float r = __fadd_rn(atanhi[3], atanlo[3]);
-        return (hx >> 31) ? -r : r;
-    }
-    if (ix < 0x3ee00000u) {
-        if (ix < 0x31000000u) return x;
-        id = -1;
-    } else {
-        x = fabsf(x);
-        if (ix < 0x3f980000u) {
-            if (ix < 0x3f300000u) { id = 0; x = __fdiv_rn(__fsub_rn(__fmul_rn(2.0f, x), 1.0f), __fadd_rn(2.0f, x)); }
-            else                  { id = 1; x = __fdiv_rn(__fsub_rn(x, 1.0f), __fadd_rn(x, 1.0f)); }
-        } else {
-            if (ix < 0x401c0000u) { id = 2; x = __fdiv_rn(__fsub_rn(x, 1.5f), __fadd_rn(1.0f, __fmul_rn(1.5f, x))); }
-            else                  { id = 3; x = __fdiv_rn(-1.0f, x); }
-        }
-    }
-    float z = __fmul_rn(x, x);
-    const float w = __fmul_rn(z, z);
-#define SCL_MA(a, b, c) __fadd_rn((a), __fmul_rn((b), (c))) /* a + b*c, two roundings */
-    const float s1 = __fmul_rn(z, SCL_MA(3.3333334327e-01f, w, SCL_MA(1.4285714924e-01f, w, SCL_MA(9.0908870101e-02f, w,
-                                  SCL_MA(6.6610731184e-02f, w, SCL_MA(4.9768779427e-02f, w, 1.6285819933e-02f))))));
-    const float s2 = __fmul_rn(w, SCL_MA(-2.0000000298e-01f, w, SCL_MA(-1.1111110449e-01f, w, SCL_MA(-7.6918758452e-02f, w,
-                                  SCL_MA(-5.8335702866e-02f, w, -3.6531571299e-02f)))));
-#undef SCL_MA
-    if (id < 0) return __fsub_rn(x, __fmul_rn(x, __fadd_rn(s1, s2)));
-    z = __fsub_rn(atanhi[id], __fsub_rn(__fsub_rn(__fmul_rn(x, __fadd_rn(s1, s2)), atanlo[id]), x));
-    return (hx >> 31) ? -z : z;
-}
-
 // int(ceil(v)) as x86-64 cvttsd2si does it: NaN / out of range -> INT_MIN (oracle: ceil_to_int)
 __device__ __forceinline__ int scl_ceil_to_int(double v)
 {

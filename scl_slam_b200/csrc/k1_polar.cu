@@ -52,6 +52,16 @@ inline uint32_t h_f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 inline float h_u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
 // libm's float atan restated (fdlibm s_atanf, bit-identical to glibc 2.39 on all 2^32 inputs — see oracle/sc_oracle.cpp)
+/* The algorithm and constants below are those of fdlibm's s_atanf.c, whose notice is kept as its licence asks:
+ * ====================================================
+ * Copyright (C) 1993 by Sun Microsystems, Inc. All rights reserved.
+ *
+ * Developed at SunPro, a Sun Microsystems, Inc. business.
+ * Permission to use, copy, modify, and distribute this
+ * software is freely granted, provided that this notice
+ * is preserved.
+ * ====================================================
+ */
 float h_atanf(float x)
 {
     static const float atanhi[4] = {4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f};
