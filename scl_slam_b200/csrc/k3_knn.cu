@@ -92,14 +92,17 @@ __device__ void merge_splits_warp(const int32_t* __restrict__ pi, const float* _
     }
 }
 
+// bx, by, gdx: the CTA's split, its query tile and the number of splits; nthreads >= kTQ threads run it (threads beyond kTQ
+// own no query and only help to stage the key tiles: the fallback kernel below runs this body in 256-thread CTAs).
 template <int R, int METRIC>
-__global__ void __launch_bounds__(kTQ) knn_exact_kernel(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys,
-                                                        int n_db, int K, int split_len, int id_mul, int id_add,
-                                                        const int32_t* __restrict__ qlist, const int* __restrict__ qcount,
-                                                        int32_t* __restrict__ part_ids, float* __restrict__ part_d2,
-                                                        int* __restrict__ tickets /* [query tiles], zero between launches */,
-                                                        int32_t* __restrict__ out_ids, float* __restrict__ out_d2,
-                                                        int min_count /* lists of up to this many queries were taken by knn_exact_small_kernel */)
+__device__ __forceinline__ void exact_body(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys,
+                                           int n_db, int K, int split_len, int id_mul, int id_add,
+                                           const int32_t* __restrict__ qlist, const int* __restrict__ qcount,
+                                           int32_t* __restrict__ part_ids, float* __restrict__ part_d2,
+                                           int* __restrict__ tickets /* [query tiles], zero between launches */,
+                                           int32_t* __restrict__ out_ids, float* __restrict__ out_d2,
+                                           int min_count /* lists of up to this many queries are taken by the thread-per-key body */,
+                                           const int bx, const int by, const int gdx, const int nthreads)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* sk = reinterpret_cast<float*>(smem_raw);                 /* [kTK][R] */
@@ -108,15 +111,15 @@ __global__ void __launch_bounds__(kTQ) knn_exact_kernel(const float* __restrict_
     const int t = threadIdx.x;
     /* optional indirection: only the queries in qlist[0..*qcount) (the tensor-core path's fallback) */
     const int nq = qlist ? *qcount : Q;
-    if (blockIdx.y * kTQ >= nq || (qlist && nq <= min_count)) return;
-    const int slot = blockIdx.y * kTQ + t;
-    const bool active = slot < nq;
+    if (by * kTQ >= nq || (qlist && nq <= min_count)) return;
+    const int slot = by * kTQ + (t < kTQ ? t : 0);
+    const bool active = t < kTQ && slot < nq;
     const int qi = active ? (qlist ? qlist[slot] : slot) : 0;
     float q[R];
 #pragma unroll
     for (int d = 0; d < R; d++) q[d] = active ? __ldg(qkeys + (size_t)qi * R + d) : 0.0f;
 
-    const int k0 = blockIdx.x * split_len;
+    const int k0 = bx * split_len;
     const int k1 = min(n_db, k0 + split_len);
     int count = 0;
     const float limit = (METRIC == 0) ? FLT_MAX : __int_as_float(0x7f800000);
@@ -129,8 +132,8 @@ __global__ void __launch_bounds__(kTQ) knn_exact_kernel(const float* __restrict_
             const float4* src = reinterpret_cast<const float4*>(keys + (size_t)base * R);
             float4* dst = reinterpret_cast<float4*>(sk);
             const int n4 = nk * R / 4;
-            for (int i = t; i < n4; i += kTQ) dst[i] = __ldg(src + i);
-            for (int i = n4 * 4 + t; i < nk * R; i += kTQ) sk[i] = __ldg(keys + (size_t)base * R + i);
+            for (int i = t; i < n4; i += nthreads) dst[i] = __ldg(src + i);
+            for (int i = n4 * 4 + t; i < nk * R; i += nthreads) sk[i] = __ldg(keys + (size_t)base * R + i);
         }
         __syncthreads();
         if (!active) continue;
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(kTQ) knn_exact_kernel(const float* __restrict_
         }
     }
     if (active) {
-        const size_t o = ((size_t)slot * gridDim.x + blockIdx.x) * K;
+        const size_t o = ((size_t)slot * gdx + bx) * K;
         for (int i = 0; i < K; i++) {
             part_d2[o + i] = i < count ? ld[i * kTQ + t] : __int_as_float(0x7f800000);
             part_ids[o + i] = i < count ? li[i * kTQ + t] : 0x7fffffff;
@@ -161,19 +164,30 @@ __global__ void __launch_bounds__(kTQ) knn_exact_kernel(const float* __restrict_
     __threadfence();
     __syncthreads();
     __shared__ int s_last;
-    if (t == 0) s_last = (atomicAdd(&tickets[blockIdx.y], 1) == (int)gridDim.x - 1);
+    if (t == 0) s_last = (atomicAdd(&tickets[by], 1) == gdx - 1);
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (t == 0) tickets[blockIdx.y] = 0;
+    if (t == 0) tickets[by] = 0;
     const int warp = t >> 5, lane = t & 31;
-    for (int s = warp; s < kTQ; s += kTQ / 32) {
-        const int sl = blockIdx.y * kTQ + s;
+    for (int s = warp; s < kTQ; s += nthreads / 32) {
+        const int sl = by * kTQ + s;
         if (sl >= nq) break;
         const int qq = qlist ? qlist[sl] : sl;
-        merge_splits_warp(part_ids + (size_t)sl * gridDim.x * K, part_d2 + (size_t)sl * gridDim.x * K, (int)gridDim.x, K, lane,
+        merge_splits_warp(part_ids + (size_t)sl * gdx * K, part_d2 + (size_t)sl * gdx * K, gdx, K, lane,
                           out_ids + (size_t)qq * K, out_d2 + (size_t)qq * K);
     }
+}
+
+template <int R, int METRIC>
+__global__ void __launch_bounds__(kTQ) knn_exact_kernel(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys,
+                                                        int n_db, int K, int split_len, int id_mul, int id_add,
+                                                        const int32_t* __restrict__ qlist, const int* __restrict__ qcount,
+                                                        int32_t* __restrict__ part_ids, float* __restrict__ part_d2, int* __restrict__ tickets,
+                                                        int32_t* __restrict__ out_ids, float* __restrict__ out_d2, int min_count)
+{
+    exact_body<R, METRIC>(qkeys, Q, keys, n_db, K, split_len, id_mul, id_add, qlist, qcount, part_ids, part_d2, tickets, out_ids, out_d2, min_count,
+                          (int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x, (int)blockDim.x);
 }
 
 // The same search for a HANDFUL of queries (the reference's own call pattern: one detect*LoopClosureID per keyframe).
@@ -182,31 +196,23 @@ __global__ void __launch_bounds__(kTQ) knn_exact_kernel(const float* __restrict_
 // smallest (d2, id) in K rounds of block-wide argmin, and the last CTA of the query (ticket) merges the splits.
 // grid = (key splits, queries).
 constexpr int kSmallThreads = 256;
+// bx, gdx: the CTA's key split and the number of splits; query qi, whose partial lists and ticket live in slot `slot`.
 template <int R, int METRIC, int KPT>
-__global__ void __launch_bounds__(kSmallThreads) knn_exact_small_kernel(const float* __restrict__ qkeys, const float* __restrict__ keys, int n_db,
-                                                                        int K, int split_len, int id_mul, int id_add, int32_t* __restrict__ part_ids,
-                                                                        float* __restrict__ part_d2, int* __restrict__ tickets,
-                                                                        int32_t* __restrict__ out_ids, float* __restrict__ out_d2,
-                                                                        const int32_t* __restrict__ qlist, const int* __restrict__ qcount)
+__device__ __forceinline__ void small_body(const float* __restrict__ qkeys, const float* __restrict__ keys, int n_db,
+                                           int K, int split_len, int id_mul, int id_add, int32_t* __restrict__ part_ids,
+                                           float* __restrict__ part_d2, int* __restrict__ tickets,
+                                           int32_t* __restrict__ out_ids, float* __restrict__ out_d2,
+                                           const int bx, const int gdx, const int slot, const int qi)
 {
     __shared__ float s_d[kSmallThreads / 32];
     __shared__ int s_i[kSmallThreads / 32];
     __shared__ int s_last;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    /* optional indirection: the queries qlist[0 .. *qcount) when there are at most gridDim.y of them (the tensor-core path's
-     * uncertified queries: a handful, if any; a longer list is left to knn_exact_kernel) */
-    const int slot = blockIdx.y;
-    int qi = slot;
-    if (qlist) {
-        const int c = *qcount;
-        if (c > (int)gridDim.y || slot >= c) return;
-        qi = qlist[slot];
-    }
     const float inf = __int_as_float(0x7f800000);
     float q[R];
 #pragma unroll
     for (int d = 0; d < R; d++) q[d] = __ldg(qkeys + (size_t)qi * R + d);
-    const int k0 = blockIdx.x * split_len;
+    const int k0 = bx * split_len;
     const int k1 = min(n_db, k0 + split_len);
     const float limit = (METRIC == 0) ? FLT_MAX : inf;
     float d[KPT];
@@ -221,7 +227,7 @@ __global__ void __launch_bounds__(kSmallThreads) knn_exact_small_kernel(const fl
         }
         d[i] = dd;
     }
-    const size_t o = ((size_t)slot * gridDim.x + blockIdx.x) * K;
+    const size_t o = ((size_t)slot * gdx + bx) * K;
     int r = 0;
     for (; r < K; r++) {
         float bd = inf; int bi = 0x7fffffff;
@@ -249,22 +255,60 @@ __global__ void __launch_bounds__(kSmallThreads) knn_exact_small_kernel(const fl
     if (t == 0) {
         for (; r < K; r++) { part_d2[o + r] = inf; part_ids[o + r] = 0x7fffffff; }
         __threadfence();
-        s_last = (atomicAdd(&tickets[slot], 1) == (int)gridDim.x - 1);
+        s_last = (atomicAdd(&tickets[slot], 1) == gdx - 1);
     }
     __syncthreads();
-    if (!s_last) return;
+    if (!s_last) return;                                /* block-uniform */
     __threadfence();
     if (t == 0) tickets[slot] = 0;
     if (warp == 0)
-        merge_splits_warp(part_ids + (size_t)slot * gridDim.x * K, part_d2 + (size_t)slot * gridDim.x * K, (int)gridDim.x, K, lane,
+        merge_splits_warp(part_ids + (size_t)slot * gdx * K, part_d2 + (size_t)slot * gdx * K, gdx, K, lane,
                           out_ids + (size_t)qi * K, out_d2 + (size_t)qi * K);
 }
 
-constexpr int kSmallList = 16;        /* uncertified queries of a tensor-core batch that the thread-per-key kernel takes */
+// grid = (key splits, queries): a handful of direct queries
+template <int R, int METRIC, int KPT>
+__global__ void __launch_bounds__(kSmallThreads) knn_exact_small_kernel(const float* __restrict__ qkeys, const float* __restrict__ keys, int n_db,
+                                                                        int K, int split_len, int id_mul, int id_add, int32_t* __restrict__ part_ids,
+                                                                        float* __restrict__ part_d2, int* __restrict__ tickets,
+                                                                        int32_t* __restrict__ out_ids, float* __restrict__ out_d2)
+{
+    small_body<R, METRIC, KPT>(qkeys, keys, n_db, K, split_len, id_mul, id_add, part_ids, part_d2, tickets, out_ids, out_d2,
+                               (int)blockIdx.x, (int)gridDim.x, (int)blockIdx.y, (int)blockIdx.y);
+}
+
+// The fallback of the tensor-core path as ONE launch: the queries qlist[0 .. *qcount) that could not be certified. Normally
+// there are none and every CTA leaves at its first branch. A short list (up to kSmallList queries: the rule when there is one
+// at all) is taken by the first n_small CTAs, thread = key, one listed query after the other; a longer list by the remaining
+// CTAs, thread = query (exact_body in 256-thread CTAs). Two launches — one per variant — cost 5 us per batch in launch gaps.
+constexpr int kSmallList = 16;
+template <int R, int METRIC, int KPT>
+__global__ void __launch_bounds__(kSmallThreads) knn_fallback_kernel(const float* __restrict__ qkeys, int Q, const float* __restrict__ keys, int n_db, int K,
+                                                                     int id_mul, int id_add, const int32_t* __restrict__ qlist, const int* __restrict__ qcount,
+                                                                     int32_t* __restrict__ part_ids, float* __restrict__ part_d2, int* __restrict__ tickets,
+                                                                     int32_t* __restrict__ out_ids, float* __restrict__ out_d2,
+                                                                     int n_small, int split_len_small, int splits_gen, int split_len_gen)
+{
+    const int c = *qcount;
+    if (c <= 0) return;
+    if ((int)blockIdx.x < n_small) {
+        if (c > kSmallList) return;
+        for (int slot = 0; slot < c; slot++) {
+            small_body<R, METRIC, KPT>(qkeys, keys, n_db, K, split_len_small, id_mul, id_add, part_ids, part_d2, tickets, out_ids, out_d2,
+                                       (int)blockIdx.x, n_small, slot, qlist[slot]);
+            __syncthreads();                             /* the body's shared scratch is reused by the next query */
+        }
+    } else {
+        if (c <= kSmallList) return;
+        const int g = (int)blockIdx.x - n_small;
+        exact_body<R, METRIC>(qkeys, Q, keys, n_db, K, split_len_gen, id_mul, id_add, qlist, qcount, part_ids, part_d2, tickets, out_ids, out_d2, 0,
+                              g % splits_gen, g / splits_gen, splits_gen, (int)blockDim.x);
+    }
+}
+
 template <int R>
 cudaError_t launch_exact_small(const float* qkeys, int Q, const float* keys, int n_db, int K, int metric, int id_mul, int id_add,
-                               KnnWorkspace ws, int32_t* out_ids, float* out_d2, cudaStream_t stream, bool* done,
-                               const int32_t* qlist = nullptr, const int* qcount = nullptr)
+                               KnnWorkspace ws, int32_t* out_ids, float* out_d2, cudaStream_t stream, bool* done)
 {
     *done = false;
     int splits = (n_db + 1023) / 1024;
@@ -273,14 +317,38 @@ cudaError_t launch_exact_small(const float* qkeys, int Q, const float* keys, int
     int split_len = (n_db + splits - 1) / splits;
     split_len = (split_len + kSmallThreads - 1) / kSmallThreads * kSmallThreads;
     const int kpt = split_len / kSmallThreads;
-    if (qlist) Q = kSmallList;                                                       /* slots; CTAs beyond the list length exit at once */
     if (kpt > 32 || (size_t)Q * splits * K > ws.capacity) return cudaSuccess;        /* the general kernel takes it */
     dim3 grid(splits, Q);
 #define SCL_SMALL(M, P) SCL_PREFER_SMEM((knn_exact_small_kernel<R, M, P>)); knn_exact_small_kernel<R, M, P><<<grid, kSmallThreads, 0, stream>>>(qkeys, keys, n_db, K, split_len, id_mul, id_add, ws.part_ids, \
-                                                                                          ws.part_d2, ws.tickets, out_ids, out_d2, qlist, qcount)
+                                                                                          ws.part_d2, ws.tickets, out_ids, out_d2)
     if (kpt <= 16) { if (metric == 0) { SCL_SMALL(0, 16); } else { SCL_SMALL(1, 16); } }
     else { if (metric == 0) { SCL_SMALL(0, 32); } else { SCL_SMALL(1, 32); } }
 #undef SCL_SMALL
+    *done = true;
+    return cudaGetLastError();
+}
+
+// the uncertified queries of a tensor-core batch (qlist[0 .. *qcount), normally none): one launch, see knn_fallback_kernel
+template <int R>
+cudaError_t launch_fallback(const float* qkeys, int Q, const float* keys, int n_db, int K, int metric, int id_mul, int id_add,
+                            const int32_t* qlist, const int* qcount, int splits_gen, int split_len_gen,
+                            KnnWorkspace ws, int32_t* out_ids, float* out_d2, cudaStream_t stream, bool* done)
+{
+    *done = false;
+    int splits = (n_db + 1023) / 1024;
+    if (splits > kMaxSplits) splits = kMaxSplits;
+    if (splits < 1) splits = 1;
+    int split_len = (n_db + splits - 1) / splits;
+    split_len = (split_len + kSmallThreads - 1) / kSmallThreads * kSmallThreads;
+    const int kpt = split_len / kSmallThreads;
+    const size_t smem = (size_t)kTK * R * 4 + (size_t)K * kTQ * 8;
+    if (kpt > 32 || (size_t)kSmallList * splits * K > ws.capacity || smem > 48 * 1024) return cudaSuccess;   /* knn_exact_kernel alone takes it */
+    const int n_gen = splits_gen * ((Q + kTQ - 1) / kTQ);
+#define SCL_FB(M, P) SCL_PREFER_SMEM((knn_fallback_kernel<R, M, P>)); knn_fallback_kernel<R, M, P><<<splits + n_gen, kSmallThreads, smem, stream>>>(qkeys, Q, keys, n_db, K, id_mul, id_add, qlist, qcount, \
+                                                      ws.part_ids, ws.part_d2, ws.tickets, out_ids, out_d2, splits, split_len, splits_gen, split_len_gen)
+    if (kpt <= 16) { if (metric == 0) { SCL_FB(0, 16); } else { SCL_FB(1, 16); } }
+    else { if (metric == 0) { SCL_FB(0, 32); } else { SCL_FB(1, 32); } }
+#undef SCL_FB
     *done = true;
     return cudaGetLastError();
 }
@@ -342,22 +410,28 @@ cudaError_t scl_launch_knn_exact(const float* qkeys, int Q, const float* keys, i
 {
     if (Q <= 0) return cudaSuccess;
     if (K < 1 || K > kMaxK) return cudaErrorInvalidValue;
-    int min_count = 0;
-    if ((qlist || Q <= 8) && ws.tickets && (R == 20 || R == 40 || R == 80)) {
-        /* a handful of queries — the reference's own call pattern, or the uncertified queries of a tensor-core batch (thread =
-         * query would take 8.5 ms for six queries on a million smooth keys; thread = key takes 0.2) */
+    if (!qlist && Q <= 8 && ws.tickets && (R == 20 || R == 40 || R == 80)) {       /* a handful of queries: thread = key */
         bool done = false;
-        const cudaError_t e = R == 20 ? launch_exact_small<20>(qkeys, Q, keys, n_db, K, metric, id_mul, id_add, ws, out_ids, out_d2, stream, &done, qlist, qcount)
-                            : R == 40 ? launch_exact_small<40>(qkeys, Q, keys, n_db, K, metric, id_mul, id_add, ws, out_ids, out_d2, stream, &done, qlist, qcount)
-                                      : launch_exact_small<80>(qkeys, Q, keys, n_db, K, metric, id_mul, id_add, ws, out_ids, out_d2, stream, &done, qlist, qcount);
-        if (e != cudaSuccess || (done && !qlist)) return e;
-        if (done) min_count = kSmallList;               /* longer lists: the kernel below */
+        const cudaError_t e = R == 20 ? launch_exact_small<20>(qkeys, Q, keys, n_db, K, metric, id_mul, id_add, ws, out_ids, out_d2, stream, &done)
+                            : R == 40 ? launch_exact_small<40>(qkeys, Q, keys, n_db, K, metric, id_mul, id_add, ws, out_ids, out_d2, stream, &done)
+                                      : launch_exact_small<80>(qkeys, Q, keys, n_db, K, metric, id_mul, id_add, ws, out_ids, out_d2, stream, &done);
+        if (e != cudaSuccess || done) return e;
     }
     const int splits = scl_knn_splits(Q, n_db);
     int split_len = (n_db + splits - 1) / splits;
     split_len = (split_len + kTK - 1) / kTK * kTK;
     if (split_len < kTK) split_len = kTK;
     if ((size_t)Q * splits * K > ws.capacity || !ws.tickets) return cudaErrorInvalidValue;
+    if (qlist && (R == 20 || R == 40 || R == 80)) {
+        /* the tensor-core path's uncertified queries: a short list goes thread = key (thread = query took 8.5 ms for six queries
+         * on a million smooth keys, thread = key 0.2 ms), a long one thread = query, both in one launch */
+        bool done = false;
+        const cudaError_t e = R == 20 ? launch_fallback<20>(qkeys, Q, keys, n_db, K, metric, id_mul, id_add, qlist, qcount, splits, split_len, ws, out_ids, out_d2, stream, &done)
+                            : R == 40 ? launch_fallback<40>(qkeys, Q, keys, n_db, K, metric, id_mul, id_add, qlist, qcount, splits, split_len, ws, out_ids, out_d2, stream, &done)
+                                      : launch_fallback<80>(qkeys, Q, keys, n_db, K, metric, id_mul, id_add, qlist, qcount, splits, split_len, ws, out_ids, out_d2, stream, &done);
+        if (e != cudaSuccess || done) return e;
+    }
+    const int min_count = 0;
     cudaError_t err;
     if (R == 20) err = launch_exact<20>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, out_ids, out_d2, stream, min_count);
     else if (R == 40) err = launch_exact<40>(qkeys, Q, keys, n_db, K, metric, splits, split_len, id_mul, id_add, qlist, qcount, ws, out_ids, out_d2, stream, min_count);
@@ -397,4 +471,7 @@ void scl_preload_k3()
     /* the 80-row keys of the row-key family (rowkey.cu) */
     SCL_TOUCH((knn_exact_kernel<80, 0>)); SCL_TOUCH((knn_exact_kernel<80, 1>));
     SCL_TOUCH((knn_exact_small_kernel<80, 0, 16>)); SCL_TOUCH((knn_exact_small_kernel<80, 1, 16>)); SCL_TOUCH((knn_exact_small_kernel<80, 0, 32>)); SCL_TOUCH((knn_exact_small_kernel<80, 1, 32>));
+    SCL_TOUCH((knn_fallback_kernel<20, 0, 16>)); SCL_TOUCH((knn_fallback_kernel<20, 1, 16>)); SCL_TOUCH((knn_fallback_kernel<20, 0, 32>)); SCL_TOUCH((knn_fallback_kernel<20, 1, 32>));
+    SCL_TOUCH((knn_fallback_kernel<40, 0, 16>)); SCL_TOUCH((knn_fallback_kernel<40, 1, 16>)); SCL_TOUCH((knn_fallback_kernel<40, 0, 32>)); SCL_TOUCH((knn_fallback_kernel<40, 1, 32>));
+    SCL_TOUCH((knn_fallback_kernel<80, 0, 16>)); SCL_TOUCH((knn_fallback_kernel<80, 1, 16>)); SCL_TOUCH((knn_fallback_kernel<80, 0, 32>)); SCL_TOUCH((knn_fallback_kernel<80, 1, 32>));
 }

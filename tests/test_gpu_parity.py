@@ -399,17 +399,20 @@ def test_tensor_core_knn_fallback_on_ties(eng_mod):
     n2 = 20000
     db2 = np.repeat(db[1000:1001], n2, axis=0)
     db2[[7, 5000, 9999, 15000, 19999]] = db[3000:3005]
-    q2 = np.repeat(db[1000:1001], 8, axis=0)
-    o2 = Oracle(num_candidates=K)
-    o2.bulk_load(np.concatenate([db2.reshape(n2, -1), q2.reshape(8, -1)]))
-    exp2 = o2.query_batch(np.arange(n2, n2 + 8), n2, K, 1, nthreads=8)
     e2 = eng_mod.ScanContextB200(numCandidates=K)
     e2.insert_batch(db2)
     e2.set_knn_mode(2, True)
-    got2 = e2.query_batch(q_desc=q2, K=K, n_db=n2, metric=1)
-    assert np.array_equal(got2["cand_ids"], exp2["cand_ids"]) and (got2["cand_ids"][:, 5:] == -1).all()
-    assert np.array_equal(got2["best_id"], exp2["best_id"])
-    assert e2.knn_stats()["fallback_queries"] == 8 and before >= 0
+    done = 0
+    for nq2 in (8, 40):                                      # a short list (thread-per-key role of the fallback kernel) and a long one (thread-per-query role)
+        q2 = np.repeat(db[1000:1001], nq2, axis=0)
+        o2 = Oracle(num_candidates=K)
+        o2.bulk_load(np.concatenate([db2.reshape(n2, -1), q2.reshape(nq2, -1)]))
+        exp2 = o2.query_batch(np.arange(n2, n2 + nq2), n2, K, 1, nthreads=8)
+        got2 = e2.query_batch(q_desc=q2, K=K, n_db=n2, metric=1)
+        assert np.array_equal(got2["cand_ids"], exp2["cand_ids"]) and (got2["cand_ids"][:, 5:] == -1).all()
+        assert np.array_equal(got2["best_id"], exp2["best_id"])
+        done += nq2
+        assert e2.knn_stats()["fallback_queries"] == done and before >= 0
 
 
 def test_pipelined_host_queries_equal_synchronous(eng_mod):
