@@ -60,3 +60,12 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle_lib" not in src and "liboracle" not in src and "sco_" not in src, f
+
+
+def test_headers_are_plain_c(tmp_path):
+    """The boundary is a C ABI: the three public headers compile as C99 on their own (no C++ types, no torch types)."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "scl_engine.h"\n#include "scl_wire.h"\n#include "scl_rowkey.h"\n'
+                   "int main(void) { scl_params p; scl_rowkey_params r; (void)p; (void)r; return (int)sizeof(scl_loop_info) == 0; }\n")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)], check=True)
