@@ -194,19 +194,19 @@ class Timed:
         lat_ms = sum(a.elapsed_time(b) for a, b in lat) / steps
         return lat_ms
 
-    def run_groups(self, steps):
-        n_groups = (steps + self.depth - 1) // self.depth
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_groups)]
-        done = 0
+    def run_groups(self, steps, repeats=3):
+        """Throughput: the K steps as ONE timed region (a CUDA-event pair on the launching stream around fork, K steps dealt
+        round-robin to the D lanes, join); the L2 flush sits before the region. Repeated `repeats` times, the median is reported."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(repeats)]
         for a, b in evs:
-            n = min(self.depth, steps - done)
+            self.flush.zero_()
             if self.align:
                 self.align()
-            a.record(); self.group(done, n); b.record()
-            self.flush.zero_()
-            done += n
+            a.record(); self.group(0, steps); b.record()
         self.barrier()
-        return sum(a.elapsed_time(b) for a, b in evs) / steps
+        t = sorted(a.elapsed_time(b) for a, b in evs)
+        self.repetitions_ms = [x / steps for x in t]
+        return t[len(t) // 2] / steps
 
 
 def run_ours(args):
@@ -281,7 +281,7 @@ def run_ours(args):
             dist.all_reduce(align_t)         # stream-ordered: every rank enters the timed group together
 
     timed = Timed(e, dev, step, D, barrier=barrier, align=align)
-    launches_per_step = 5 + (2 if world > 1 else 0)       # ring_key(+stats), knn_tc, knn_rerank, knn_exact (fallback list), scdist (+ the two exchange kernels)
+    launches_per_step = 5 + (2 if world > 1 else 0)       # ring_key(+stats), knn_tc, knn_rerank, knn_fallback (the uncertified queries, if any), scdist (+ the two exchange kernels)
     t_region0 = time.time()
     lat_ms = timed.run(steps, args.warmup, after_warmup=lambda: e.set_profiling(True))
     stage = {name: e.stage_time(i) for i, name in ((0, "k2_query_keys"), (1, "k3_knn"), (2, "k4_scdist"))}
@@ -427,8 +427,9 @@ def run_ours(args):
                    "sharding": f"key mod {world}" if world > 1 else "none",
                    "exchange": "nvlink peer memory, fused with the merge kernels (k7_exchange.cu), one region per query lane" if world > 1 else "none",
                    "in_flight": D,
-                   "l2": f"512 MB buffer rewritten between timed groups of {D} batches in flight (outside the per-group CUDA-event pairs); "
-                         "the one-at-a-time latency pass flushes between steps"},
+                   "l2": f"inputs exceed L2 (4.8 GB of descriptors and a 134 MB key image against 126 MB); a 512 MB buffer is rewritten before every timed pass "
+                         f"of the K steps ({D} batches in flight; outside the CUDA-event pair) and between the steps of the one-at-a-time latency pass",
+                   "timed_passes_ms_per_step": getattr(timed, "repetitions_ms", None)},
         "latency": {"ms_per_step": lat_ms, "value": Q / (lat_ms * 1e-3), "note": "one batch in flight, L2 flushed between steps"},
         "e2e": e2e, "gpu_launches": launches_per_step * steps,
         "stage_ms_per_step": {k: v[0] / max(v[1], 1) for k, v in stage.items()},
@@ -472,7 +473,7 @@ def guarded(fn):
     return inner
 
 
-def query_arm(engine, synth, dev, pk, n_db, gen, seed, depth, r=R, s=S, no_match_fraction=0.0, steps=20, knn_mode=0, label=""):
+def query_arm(engine, synth, dev, pk, n_db, gen, seed, depth, r=R, s=S, no_match_fraction=0.0, steps=20, knn_mode=0, label="", lap=0):
     """A database of n_db entries from `gen`, batches of Q queries (perturbed + rotated entries; a fraction replaced by
     fresh descriptors that match nothing), timed like the headline: one at a time and `depth` in flight."""
     e = engine.ScanContextB200(numRing=r, numSector=s, numCandidates=K)
@@ -503,6 +504,8 @@ def query_arm(engine, synth, dev, pk, n_db, gen, seed, depth, r=R, s=S, no_match
     res = {"value": Q / (thr * 1e-3), "unit": "queries/s", "ms_per_step": thr, "in_flight": depth, "latency_ms_per_step": lat, "stage_ms_per_step": stage,
            "db_keyframes": n_db, "rings": r, "sectors": s, "knn": e.knn_stats(),
            "source_recovered": float((bid[has] == src[has]).mean()) if has.any() else None,
+           # a smooth trajectory has no single right answer: the winner counts when it lies within 64 keyframes of the source or of a revisit of it
+           "winner_within_64_keyframes_of_the_place": (float((np.minimum((bid[has] - src[has]) % lap, (src[has] - bid[has]) % lap) <= 64).mean()) if (lap and has.any()) else None),
            "no_match_best_distance_above_threshold": float((outs[0]["best_dist"].cpu().numpy()[~has] >= 0.14).mean()) if (~has).any() else None,
            "roofline": {"bound": "hbm", "algorithmic_bytes": alg, "achieved": alg / (thr * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                         "frac": alg / (thr * 1e-3) / 1e9 / pk["hbm"]}}
@@ -517,7 +520,7 @@ def arm_robustness(engine, synth, dev, pk, depth):
     res["fallback_queries"] = res["knn"]["fallback_queries"]
     e.close()
     # the harder ordering: ONE smooth trajectory (neighbouring ring keys millimetres apart, places revisited every 400 000 keyframes)
-    e, res2, _, _ = query_arm(engine, synth, dev, pk, N_DB, synth.desc_db_smooth, 5, depth, no_match_fraction=0.5)
+    e, res2, _, _ = query_arm(engine, synth, dev, pk, N_DB, synth.desc_db_smooth, 5, depth, no_match_fraction=0.5, lap=400_000)
     res2["workload"] = "c3 robustness: 1,048,576 entries of one smooth trajectory (ring keys drift by millimetres per keyframe, every place seen two or three times), 50 % of the queries match nothing"
     res2["fallback_queries"] = res2["knn"]["fallback_queries"]
     e.close()
