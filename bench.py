@@ -247,6 +247,17 @@ def run_ours(args):
     if args.scdist_tiles >= 0 and world == 1:
         e.set_scdist_tiles(args.scdist_tiles)
     n_local = fill(e, dev, rank, world, n_db)
+    hybrid = world > 1 and args.hybrid != 0
+    if hybrid:
+        # hybrid sharding: the ring keys (80 B per keyframe) of all shards on every rank, in global key order; descriptors stay sharded
+        mine = torch.empty((n_local, R), dtype=torch.float32, device=dev)
+        e.export_keys_dev(mine, n_local)
+        allk = torch.empty((world, n_local, R), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(allk, mine)
+        glob = allk.permute(1, 0, 2).reshape(world * n_local, R).contiguous()       # global key = local * world + rank
+        e.set_replicated_keys_dev(glob, world * n_local)
+        del mine, allk, glob
+    n_search = world * n_local if hybrid else n_local      # with replicated keys the search bound is global
     D = max(1, min(args.in_flight, e.num_lanes()))
     steps = args.steps                                     # the last group is smaller when D does not divide K
     # D different query batches (seeds 4, 5, ...), one per lane; every one made of perturbed + rotated database entries
@@ -267,7 +278,7 @@ def run_ours(args):
         if world == 1:
             e.query_batch_dev_lane(lane, q_dev[i % D], None, Q, K, n_local, 0, outs[i % D])
         else:
-            e.shard_query_dev(lane, q_dev[i % D], Q, K, n_local, 0, outs[i % D])
+            e.shard_query_dev(lane, q_dev[i % D], Q, K, n_search, 0, outs[i % D])
 
     def barrier():
         if world > 1:
@@ -305,7 +316,7 @@ def run_ours(args):
     def submit(i):
         if world == 1:
             return e.query_batch_submit(q_host[i % D], res_np[i % len(res_np)], K=K, n_db=n_local, metric=0)
-        return e.shard_query_submit(q_host[i % D], res_np[i % len(res_np)], K=K, n_db=n_local, metric=0)
+        return e.shard_query_submit(q_host[i % D], res_np[i % len(res_np)], K=K, n_db=n_search, metric=0)
 
     def e2e_pipelined(n, depth):
         pending = []
@@ -393,7 +404,7 @@ def run_ours(args):
     pk = peaks()
     k3_ms, k3_n = stage["k3_knn"]
     k3_avg = k3_ms / max(k3_n, 1)
-    alg_bytes = 4 * R * n_local + 4 * R * Q + 8 * Q * K          # key matrix once + query keys + (id, d2) out
+    alg_bytes = 4 * R * n_search + 4 * R * Q + 8 * Q * K         # key matrix once (every key on a hybrid rank) + query keys + (id, d2) out
     alg_flops = 2.0 * R * Q * n_local
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -424,7 +435,7 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+f64",
         "data": "synthetic", "impl": "ours",
         "config": {"workload": WORKLOAD, "db_keyframes": n_db, "queries_per_step": Q, "top_k": K, "rings": R, "sectors": S,
-                   "sharding": f"key mod {world}" if world > 1 else "none",
+                   "sharding": (f"descriptors by key mod {world}; ring keys replicated, K3 query-parallel (hybrid)" if hybrid else f"key mod {world}") if world > 1 else "none",
                    "exchange": "nvlink peer memory, fused with the merge kernels (k7_exchange.cu), one region per query lane" if world > 1 else "none",
                    "in_flight": D,
                    "l2": f"inputs exceed L2 (4.8 GB of descriptors and a 134 MB key image against 126 MB); a 512 MB buffer is rewritten before every timed pass "
@@ -999,6 +1010,7 @@ def main():
     ap.add_argument("--n-db", type=int, default=N_DB, help="database size (default: the 1M workload)")
     ap.add_argument("--in-flight", type=int, default=8, help="batches in flight (query lanes used), 1..8")
     ap.add_argument("--tc-stages", type=int, default=0, help="key tiles the tensor-core kNN kernel keeps in flight (2..5; 0 = the engine's default)")
+    ap.add_argument("--hybrid", type=int, default=1, help="N > 1: 1 = ring keys replicated, K3 query-parallel, descriptors sharded (default); 0 = keys sharded too")
     ap.add_argument("--scdist-tiles", type=int, default=-1, help="candidate tiles per K4 CTA (0 = one per candidate; -1 = the engine's default)")
     ap.add_argument("--cpu-sample", type=int, default=256, help="queries per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -68,6 +68,15 @@ int scl_reserve(scl_engine* e, int capacity);
 /* Database sharding across ranks: local key l stands for global key
  * l*world + rank in every id this engine reports. Default rank 0, world 1. */
 int scl_set_shard(scl_engine* e, int rank, int world);
+/* Hybrid sharding: descriptors stay sharded by key mod world (what K4 gathers: 4.8 KB per candidate), the ring
+ * keys (80 B per keyframe) are REPLICATED on every rank, in global key order. K3 then runs query-parallel: a rank searches every
+ * key for its 1 / world of a batch and the other queries' lists stay empty, so the exchange's per-query merge returns the
+ * owner's list; no rank repeats K3 start-up, the re-rank or the fallback for all Q queries. With replicated keys set, n_db of
+ * scl_knn_batch_dev / scl_shard_query_dev / scl_shard_query_submit is the GLOBAL search bound. n_total = 0 returns to
+ * plain sharding. scl_export_keys_dev copies this engine's first n ring keys ([n][num_ring] floats, device to device), which
+ * the ranks all-gather and interleave (global key = local * world + rank) before handing them back. */
+int scl_export_keys_dev(scl_engine* e, float* keys_out_dev, int n);
+int scl_set_replicated_keys_dev(scl_engine* e, const float* keys_dev, int n_total);
 
 /* ---- descriptor build --------------------------------------------------------------------
  * replaces makeAndSaveDescriptorAndKey, descriptor.h:1604-1611 (call site distributedMapping.h:1002).

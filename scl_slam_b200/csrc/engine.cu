@@ -196,6 +196,7 @@ int knn_dev(scl_engine* e, Lane& ln, const float* q_desc, const int32_t* q_ids, 
     if (Q <= 0) return SCL_OK;
     if (K < 1 || K > 32) FAIL(SCL_ERR_INVALID, "K must be in 1..32");
     if (metric != 0 && metric != 1) FAIL(SCL_ERR_INVALID, "metric must be 0 or 1");
+    const int n_db_in = n_db;
     if (n_db < 0) n_db = 0;
     if (n_db > e->n) n_db = e->n;
     if (!q_desc && !q_ids) FAIL(SCL_ERR_INVALID, "q_desc and q_ids are both NULL");
@@ -204,9 +205,23 @@ int knn_dev(scl_engine* e, Lane& ln, const float* q_desc, const int32_t* q_ids, 
      * 182 us per call at Q = 9..128 against 800..1800 us for the exact kernel, and against 199 / 234 us for the thread-per-key
      * kernel at Q = 4 / 8; on 20 k keys and batches of 1024: 15.1 M against 5.0 M queries/s for the whole query); up to three queries and
      * databases under 16 384 keys (fewer key tiles than the union bound needs ranges) take the exact CUDA-core kernels. */
+    /* Hybrid sharding: with every ring key on every rank, this rank searches ALL keys (n_db is then the GLOBAL bound) for its
+     * 1 / world of the batch and reports global ids; the other queries' lists stay empty (-1) and the exchange's per-query merge
+     * of `world` lists returns the owner's. No per-rank K3 on all Q queries, no re-rank of all Q on every rank. */
+    const bool hybrid = e->world > 1 && e->r_n > 0 && q_desc != nullptr;
+    int q_lo = 0, Qk = Q, nk = n_db, id_mul = e->world, id_add = e->rank;
+    const float* keys = e->d_keys; const unsigned char* kimg = e->d_kimg; const float* kn2max = e->d_kn2max;
+    if (hybrid) {
+        const int per = (Q + e->world - 1) / e->world;
+        q_lo = e->rank * per < Q ? e->rank * per : Q;
+        Qk = Q - q_lo < per ? Q - q_lo : per;
+        nk = n_db_in < e->r_n ? (n_db_in < 0 ? 0 : n_db_in) : e->r_n;
+        keys = e->r_keys; kimg = e->r_kimg; kn2max = e->d_kn2max + 1; id_mul = 1; id_add = 0;
+    }
     const bool use_tc = scl_knn_tc_supported(R) && K <= scl_knn_tc_kprime() - 2 &&
-                        (e->knn_mode == 2 || (e->knn_mode == 0 && Q > 3 && n_db >= 16384));
-    if (use_tc) { int rc = sync_key_image(e); if (rc) return rc; }            /* on the engine stream */
+                        (e->knn_mode == 2 || (e->knn_mode == 0 && Qk > 3 && nk >= 16384));
+    if (use_tc && !hybrid) { int rc = sync_key_image(e); if (rc) return rc; }            /* on the engine stream */
+    if (!hybrid) kimg = e->d_kimg;                   /* sync_key_image may have (re)allocated it */
     { int rc = lane_begin(e, ln); if (rc) return rc; }
     const size_t QK = (size_t)Q * K;
     CK(ln.cand_local.ensure(QK * 4));
@@ -219,7 +234,7 @@ int knn_dev(scl_engine* e, Lane& ln, const float* q_desc, const int32_t* q_ids, 
         CK(ln.qlocal.ensure((size_t)Q * 4));
         q_local = ln.qlocal.as<int32_t>();
     }
-    const int splits = scl_knn_splits(Q, n_db);
+    const int splits = scl_knn_splits(Qk > 0 ? Qk : 1, nk);
     KnnWorkspace ws;
     CK(ln.part_ids.ensure((size_t)Q * splits * K * 4));
     CK(ln.part_d2.ensure((size_t)Q * splits * K * 4));
@@ -228,7 +243,7 @@ int knn_dev(scl_engine* e, Lane& ln, const float* q_desc, const int32_t* q_ids, 
         CK(ln.knn_tickets.ensure(((size_t)Q / 128 + 16) * 4));          /* per 128-query tile, or per query of a handful */
         if (old != ln.knn_tickets.p) CK(cudaMemsetAsync(ln.knn_tickets.p, 0, ln.knn_tickets.cap, ln.stream));   /* the kernel leaves them zero */
     }
-    ws.part_ids = ln.part_ids.as<int32_t>(); ws.part_d2 = ln.part_d2.as<float>(); ws.tickets = ln.knn_tickets.as<int>(); ws.capacity = (size_t)Q * splits * K;
+    ws.part_ids = ln.part_ids.as<int32_t>(); ws.part_d2 = ln.part_d2.as<float>(); ws.tickets = ln.knn_tickets.as<int>(); ws.capacity = (size_t)Q * splits * K;   /* sized for all Q; a hybrid rank uses Qk of them */
     if (q_desc) {
         StageTimer st(e, 0, ln.stream);
         CK(scl_launch_ring_keys(q_desc, Q, R, S, ln.qkeys.as<float>(), ln.qknorm.as<float>(), nullptr, ln.qstat.as<double>(), ln.stream));
@@ -237,10 +252,13 @@ int knn_dev(scl_engine* e, Lane& ln, const float* q_desc, const int32_t* q_ids, 
         CK(scl_launch_ids_to_local(q_ids, Q, e->world, e->rank, -1, nullptr, q_local, ln.stream));
         CK(scl_launch_gather_rows(e->d_keys, q_local, Q, R, ln.qkeys.as<float>(), ln.stream));
     }
-    {
+    if (hybrid) CK(cudaMemsetAsync(cand_ids, 0xff, QK * 4, ln.stream));            /* -1: the lists of the other ranks' queries are empty */
+    const float* qk = ln.qkeys.as<float>() + (size_t)q_lo * R;
+    int32_t* o_ids = cand_ids + (size_t)q_lo * K; float* o_d2 = cand_d2 + (size_t)q_lo * K;
+    if (Qk > 0) {
         StageTimer st(e, 1, ln.stream);
         if (use_tc) {
-            const int Qc = Q < scl_knn_tc_max_batch() ? Q : scl_knn_tc_max_batch();
+            const int Qc = Qk < scl_knn_tc_max_batch() ? Qk : scl_knn_tc_max_batch();
             const int ranges = scl_knn_tc_ranges(Qc);
             const size_t pairs = (size_t)Qc * ranges;
             CK(ln.tc_queues.ensure(pairs * scl_knn_tc_queue_bytes())); CK(ln.tc_queue_cnt.ensure(pairs * 4));
@@ -261,17 +279,16 @@ int knn_dev(scl_engine* e, Lane& ln, const float* q_desc, const int32_t* q_ids, 
                 probe = ln.tc_err_probe.as<float>();
             }
             KnnTcWorkspace tw{ln.tc_queues.as<uint32_t>(), ln.tc_queue_cnt.as<int>(), ln.tc_slots.as<int>(), probe, pairs};
-            CK(scl_launch_knn_tc(ln.qkeys.as<float>(), Q, e->d_keys, e->d_kimg, e->d_kn2max, n_db, R, K, metric, e->world, e->rank, tw,
-                                 cand_ids, cand_d2, ln.tc_fail_list.as<int32_t>(), fail_cur, fail_next, init_state, e->tc_stages, ln.stream));
+            CK(scl_launch_knn_tc(qk, Qk, keys, kimg, kn2max, nk, R, K, metric, id_mul, id_add, tw,
+                                 o_ids, o_d2, ln.tc_fail_list.as<int32_t>(), fail_cur, fail_next, init_state, e->tc_stages, ln.stream));
             ln.tc_state_clean = true; ln.tc_slots_rows = Qc;
             /* uncertified queries (normally none) are redone exactly; CTAs beyond the list length exit at once */
-            CK(scl_launch_knn_exact(ln.qkeys.as<float>(), Q, e->d_keys, n_db, R, K, metric, e->world, e->rank,
-                                    ln.tc_fail_list.as<int32_t>(), fail_cur, ws, cand_ids, cand_d2, ln.stream));
+            CK(scl_launch_knn_exact(qk, Qk, keys, nk, R, K, metric, id_mul, id_add,
+                                    ln.tc_fail_list.as<int32_t>(), fail_cur, ws, o_ids, o_d2, ln.stream));
             ln.tc_last_fail = fail_cur;
-            e->stat_tc_queries += Q;
+            e->stat_tc_queries += Qk;
         } else {
-            CK(scl_launch_knn_exact(ln.qkeys.as<float>(), Q, e->d_keys, n_db, R, K, metric, e->world, e->rank, nullptr, nullptr, ws,
-                                    cand_ids, cand_d2, ln.stream));
+            CK(scl_launch_knn_exact(qk, Qk, keys, nk, R, K, metric, id_mul, id_add, nullptr, nullptr, ws, o_ids, o_d2, ln.stream));
         }
     }
     if (use_tc && e->count_fallbacks) {
@@ -458,6 +475,9 @@ int scl_destroy(scl_engine* e)
         for (int r = 0; r < 16; r++) if (e->xchg_peer_map[r]) cudaIpcCloseMemHandle(e->xchg_peer_map[r]);
         if (e->xchg_buf) cudaFree(e->xchg_buf);
         cudaFree(e->d_desc); cudaFree(e->d_keys); cudaFree(e->d_knorm); cudaFree(e->d_cstat); cudaFree(e->d_kn2max); cudaFree(e->d_kimg);
+        if (e->r_keys) cudaFree(e->r_keys);
+        if (e->r_knorm) cudaFree(e->r_knorm);
+        if (e->r_kimg) cudaFree(e->r_kimg);
         DevBuf* bufs[] = {&e->pts, &e->offsets, &e->gbins, &e->tickets, &e->stage_desc, &e->stage_keys, &e->stage_knorm,
                           &e->bins_ring, &e->bins_sector, &e->kf_arena, &e->icp_src, &e->icp_tgt, &e->icp_raw, &e->icp_acc, &e->icp_nn,
                           &e->icp_grid[0][0], &e->icp_grid[0][1], &e->icp_grid[0][2], &e->icp_grid[0][3], &e->icp_grid[0][4],
@@ -566,6 +586,44 @@ int scl_set_shard(scl_engine* e, int rank, int world)
     LOCK();
     if (world < 1 || rank < 0 || rank >= world) FAIL(SCL_ERR_INVALID, "bad shard");
     e->rank = rank; e->world = world;
+    return SCL_OK;
+}
+
+int scl_export_keys_dev(scl_engine* e, float* keys_out_dev, int n)
+{
+    LOCK();
+    if (!keys_out_dev || n < 0 || n > e->n) FAIL(SCL_ERR_RANGE, "n must be within the engine's size");
+    if (n) CK(cudaMemcpyAsync(keys_out_dev, e->d_keys, (size_t)n * e->p.num_ring * 4, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SCL_OK;
+}
+
+int scl_set_replicated_keys_dev(scl_engine* e, const float* keys_dev, int n_total)
+{
+    LOCK();
+    const int R = e->p.num_ring;
+    if (n_total < 0 || (n_total > 0 && !keys_dev)) FAIL(SCL_ERR_INVALID, "keys_dev is NULL or n_total < 0");
+    if (n_total > 0 && !scl_knn_tc_supported(R) && R != 10) FAIL(SCL_ERR_UNSUPPORTED, "key length");
+    CK(cudaStreamSynchronize(e->stream));
+    for (int l = 1; l < scl_engine::kLanes; l++) if (e->lanes[l].stream) CK(cudaStreamSynchronize(e->lanes[l].stream));
+    if (e->r_keys) cudaFree(e->r_keys);
+    if (e->r_knorm) cudaFree(e->r_knorm);
+    if (e->r_kimg) cudaFree(e->r_kimg);
+    e->r_keys = e->r_knorm = nullptr; e->r_kimg = nullptr; e->r_n = 0;
+    if (n_total == 0) return SCL_OK;
+    CK(cudaMalloc(&e->r_keys, (size_t)n_total * R * 4));
+    CK(cudaMalloc(&e->r_knorm, (size_t)n_total * 4));
+    CK(cudaMemcpyAsync(e->r_keys, keys_dev, (size_t)n_total * R * 4, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemsetAsync(e->d_kn2max + 1, 0, 4, e->stream));
+    CK(scl_launch_key_norms(e->r_keys, 0, n_total, R, e->r_knorm, e->d_kn2max + 1, e->stream));
+    if (scl_knn_tc_supported(R)) {
+        const size_t bytes = scl_knn_tc_image_bytes(R, n_total);
+        CK(cudaMalloc(&e->r_kimg, bytes));
+        CK(cudaMemsetAsync(e->r_kimg, 0, bytes, e->stream));
+        CK(scl_launch_key_image(e->r_keys, e->r_knorm, 0, n_total, R, e->r_kimg, e->stream));
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    e->r_n = n_total;
     return SCL_OK;
 }
 

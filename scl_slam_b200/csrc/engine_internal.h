@@ -43,6 +43,9 @@ struct scl_engine {
     float* d_kn2max = nullptr;             /* device scalar: largest squared ring-key norm in the database */
     unsigned char* d_kimg = nullptr;       /* tensor-core key image: 128-key tiles in the tcgen05 operand layout (k3_knn_tc.cu) */
     int img_n = 0, img_cap = 0;            /* keys [0, img_n) have an image; capacity in keys */
+    /* Hybrid sharding (scl_set_replicated_keys_dev): ALL ring keys, in global key order, on every rank, so that K3 runs
+     * query-parallel (this rank's 1 / world of the batch against every key); descriptors stay sharded for K4 */
+    float *r_keys = nullptr, *r_knorm = nullptr; unsigned char* r_kimg = nullptr; int r_n = 0;
     int knn_mode = 0;                      /* 0 auto, 1 exact CUDA-core kernel, 2 tensor-core prefilter */
     int tc_stages = 2;                     /* key tiles knn_tc_kernel keeps in flight in shared memory (scl_set_tc_stages): two leave 127 KB of the SM to other lanes' kernels */
     long long stat_tc_queries = 0, stat_fallback_queries = 0;

@@ -49,6 +49,8 @@ int scl_knn_tc_slot_stride();       /* ints per query in KnnTcWorkspace::slots *
 size_t scl_knn_tc_queue_bytes();
 size_t scl_knn_tc_image_bytes(int R, int n_keys);
 cudaError_t scl_launch_key_image(const float* keys, const float* knorm, int k_lo, int k_hi, int R, unsigned char* img, cudaStream_t stream);
+// squared norms of keys [k_lo, k_hi) (prefilter only) and their maximum (kn2max, a device float raised by atomicMax on its bits); rowkey.cu
+cudaError_t scl_launch_key_norms(const float* keys, int k_lo, int k_hi, int R, float* knorm, float* kn2max, cudaStream_t stream);
 cudaError_t scl_launch_knn_tc(const float* qkeys, int Q, const float* keys, const unsigned char* img, const float* kn2max, int n_db, int R, int K,
                                int metric, int id_mul, int id_add, KnnTcWorkspace ws, int32_t* out_ids, float* out_d2,
                                int32_t* fail_list, int* fail_count, int* next_fail_count /* zeroed by the re-rank for the next call */,

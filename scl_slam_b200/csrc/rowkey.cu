@@ -39,6 +39,17 @@ __global__ void rowkey_map_kernel(const int32_t* __restrict__ concat_idx, int n,
     global_key[i] = (c >= 0 && c < n_l2g) ? l2g[c] : -1;
 }
 
+}  // namespace
+
+cudaError_t scl_launch_key_norms(const float* keys, int k_lo, int k_hi, int R, float* knorm, float* kn2max, cudaStream_t stream)
+{
+    if (k_hi <= k_lo) return cudaSuccess;
+    rowkey_norm_kernel<<<(k_hi - k_lo + 127) / 128, 128, 0, stream>>>(keys, k_lo, k_hi, R, knorm, kn2max);
+    return cudaGetLastError();
+}
+
+namespace {
+
 struct KeyStore {
     float* keys = nullptr; float* knorm = nullptr; unsigned char* kimg = nullptr;
     int n = 0, cap = 0, norm_n = 0, img_n = 0, img_cap = 0;
@@ -130,8 +141,7 @@ int sync_image(scl_rowkey* e, KeyStore& s)
 {
     const int R = e->p.rows;
     if (s.norm_n < s.n) {
-        rowkey_norm_kernel<<<(s.n - s.norm_n + 127) / 128, 128, 0, e->stream>>>(s.keys, s.norm_n, s.n, R, s.knorm, e->d_kn2max);
-        CK(cudaGetLastError());
+        CK(scl_launch_key_norms(s.keys, s.norm_n, s.n, R, s.knorm, e->d_kn2max, e->stream));
         s.norm_n = s.n;
     }
     if (s.img_cap < s.cap) {

@@ -25,7 +25,7 @@ EXPORTS = [
     "scl_reserve", "scl_set_shard", "scl_build_insert", "scl_make_scancontext", "scl_build_batch", "scl_build_batch_dev",
     "scl_insert", "scl_insert_batch", "scl_insert_batch_dev", "scl_get_index", "scl_size", "scl_get_descriptor",
     "scl_get_ring_key", "scl_query_intra", "scl_query_inter", "scl_query_batch", "scl_query_batch_dev",
-    "scl_merge_shards_dev", "scl_icp", "scl_set_profiling", "scl_stage_time", "scl_set_knn_mode", "scl_set_scdist_mode", "scl_set_scdist_tiles", "scl_set_tc_stages", "scl_knn_stats",
+    "scl_merge_shards_dev", "scl_icp", "scl_set_profiling", "scl_stage_time", "scl_set_knn_mode", "scl_set_scdist_mode", "scl_set_scdist_tiles", "scl_set_tc_stages", "scl_export_keys_dev", "scl_set_replicated_keys_dev", "scl_knn_stats",
     "scl_default_ransac_params", "scl_verify_ransac", "scl_knn_batch_dev", "scl_merge_topk_dev", "scl_scdist_owned_dev", "scl_combine_owned_dev",
     "scl_query_batch_submit", "scl_query_batch_wait", "scl_voxel_grid", "scl_assemble_submap", "scl_build_insert_filtered",
     "scl_xchg_create", "scl_xchg_open", "scl_xchg_merge_topk_dev", "scl_xchg_combine_dev", "scl_xchg_close",
@@ -203,6 +203,8 @@ def load_library():
     lib.scl_set_scdist_mode.argtypes = [C.c_void_p, C.c_int]
     lib.scl_set_tc_stages.argtypes = [C.c_void_p, C.c_int]
     lib.scl_set_scdist_tiles.argtypes = [C.c_void_p, C.c_int]
+    lib.scl_export_keys_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.scl_set_replicated_keys_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.scl_knn_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     lib.scl_set_profiling.argtypes = [C.c_void_p, C.c_int]
     lib.scl_stage_time.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
@@ -403,6 +405,14 @@ class ScanContextB200:
 
     def set_tc_stages(self, stages):
         self._ck(self.lib.scl_set_tc_stages(self.h, stages))
+
+    def export_keys_dev(self, keys_out_dev, n):
+        """This engine's first n ring keys [n][R] (device to device)."""
+        self._ck(self.lib.scl_export_keys_dev(self.h, _ptr(keys_out_dev), n))
+
+    def set_replicated_keys_dev(self, keys_dev, n_total):
+        """Hybrid sharding: every ring key, in global key order, on this rank (n_total = 0: back to plain sharding)."""
+        self._ck(self.lib.scl_set_replicated_keys_dev(self.h, _ptr(keys_dev), n_total))
 
     def set_scdist_tiles(self, tiles):
         """Candidate tiles per K4 CTA (0 = one per candidate; 4 = small CTAs that fit beside the tensor-core kNN pass)."""

@@ -450,10 +450,12 @@ def test_pipelined_host_queries_equal_synchronous(eng_mod):
             assert np.array_equal(outs[i][k], exp[i][k], equal_nan=True), (i, k)
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_two_phase_exchange_equals_unsharded(eng_mod, world):
+@pytest.mark.parametrize("world,hybrid", [(2, False), (3, False), (2, True), (3, True), (8, True)])
+def test_two_phase_exchange_equals_unsharded(eng_mod, world, hybrid):
     """The N>1 path bench.py runs (kNN per shard -> gather (id,d2) -> global top-K -> SC distance on the owned
-    candidates only -> gather (dist,shift) -> combine), emulated with `world` engines on one GPU."""
+    candidates only -> gather (dist,shift) -> combine), emulated with `world` engines on one GPU. hybrid: the ring keys are
+    replicated (scl_set_replicated_keys_dev), every engine searches ALL keys for its 1 / world of the queries and leaves the
+    other lists empty; descriptors stay sharded."""
     from scl_slam_b200 import sharding
     n, nq, K = 5003, 80, 10
     db = synth.desc_db(n, seed=83)
@@ -469,14 +471,21 @@ def test_two_phase_exchange_equals_unsharded(eng_mod, world):
     gath1 = torch.empty((world, QK * 8), dtype=torch.uint8, device=dev)
     gath2 = torch.empty((world, QK * 12), dtype=torch.uint8, device=dev)
     engines = []
+    all_keys = torch.empty((n, 20), dtype=torch.float32, device=dev)
+    full.export_keys_dev(all_keys, n)
     for r in range(world):
         e = eng_mod.ScanContextB200(numCandidates=K)
         e.set_shard(r, world)
         e.insert_batch(dbn[sharding.local_rows(n, r, world)])
-        e.knn_batch_dev(qd, nq, K, sharding.local_search_bound(n - 101, r, world), 0,
+        if hybrid:
+            e.set_replicated_keys_dev(all_keys, n)
+        e.knn_batch_dev(qd, nq, K, (n - 101) if hybrid else sharding.local_search_bound(n - 101, r, world), 0,
                         gath1[r, :QK * 4].view(torch.int32), gath1[r, QK * 4:].view(torch.float32))
         engines.append(e)
     torch.cuda.synchronize()
+    if hybrid:                                    # every list comes from exactly one engine
+        ids = gath1[:, :QK * 4].contiguous().view(torch.int32).view(world, nq, K).cpu().numpy()
+        assert ((ids[:, :, 0] >= 0).sum(axis=0) == 1).all()
     m_ids = torch.empty((nq, K), dtype=torch.int32, device=dev)
     m_d2 = torch.empty((nq, K), dtype=torch.float32, device=dev)
     engines[0].merge_topk_dev(world, nq, K, gath1, gath1[:, QK * 4:], QK * 8, m_ids, m_d2)
@@ -914,3 +923,36 @@ def test_tensor_core_knn_on_a_smooth_trajectory(eng_mod, metric):
     assert np.array_equal(out[1][0], out[2][0]) and np.array_equal(out[1][1].view(np.uint32), out[2][1].view(np.uint32))
     st = out[2][2]
     assert st["tc_queries"] == nq and st["fallback_queries"] <= nq // 20, st
+
+
+def test_hybrid_sharding_knn_on_the_tensor_core_path(eng_mod):
+    """Hybrid sharding at a size where the tensor-core kNN runs: four engines with replicated ring keys, 128 of 512 queries
+    each against all 40 000 keys; the per-query merge of their lists equals the unsharded engine's candidates bit for bit."""
+    from scl_slam_b200 import sharding
+    dev = torch.device("cuda", 0)
+    n, nq, K, world = 40000, 512, 10, 4
+    db = synth.desc_db(n, seed=131, device=dev)
+    q = synth.desc_queries(db, nq, seed=132)[0].contiguous()
+    full = eng_mod.ScanContextB200(numCandidates=K)
+    full.insert_batch_dev(db)
+    exp_ids = torch.empty((nq, K), dtype=torch.int32, device=dev); exp_d2 = torch.empty((nq, K), dtype=torch.float32, device=dev)
+    full.knn_batch_dev(q, nq, K, n, 0, exp_ids, exp_d2)
+    all_keys = torch.empty((n, 20), dtype=torch.float32, device=dev)
+    full.export_keys_dev(all_keys, n)
+    QK = nq * K
+    gath = torch.empty((world, QK * 8), dtype=torch.uint8, device=dev)
+    tc = 0
+    for r in range(world):
+        e = eng_mod.ScanContextB200(numCandidates=K)
+        e.set_shard(r, world)
+        e.insert_batch_dev(db[r::world].contiguous())
+        e.set_replicated_keys_dev(all_keys, n)
+        e.set_knn_mode(0, True)
+        e.knn_batch_dev(q, nq, K, n, 0, gath[r, :QK * 4].view(torch.int32), gath[r, QK * 4:].view(torch.float32))
+        torch.cuda.synchronize()
+        tc += e.knn_stats()["tc_queries"]
+    assert tc == nq                                   # every query took the tensor-core path on exactly one engine
+    m_ids = torch.empty((nq, K), dtype=torch.int32, device=dev); m_d2 = torch.empty((nq, K), dtype=torch.float32, device=dev)
+    full.merge_topk_dev(world, nq, K, gath, gath[:, QK * 4:], QK * 8, m_ids, m_d2)
+    torch.cuda.synchronize()
+    assert torch.equal(m_ids, exp_ids) and torch.equal(m_d2.view(torch.int32), exp_d2.view(torch.int32))
