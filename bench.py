@@ -1010,7 +1010,8 @@ def main():
     ap.add_argument("--n-db", type=int, default=N_DB, help="database size (default: the 1M workload)")
     ap.add_argument("--in-flight", type=int, default=8, help="batches in flight (query lanes used), 1..8")
     ap.add_argument("--tc-stages", type=int, default=0, help="key tiles the tensor-core kNN kernel keeps in flight (2..5; 0 = the engine's default)")
-    ap.add_argument("--hybrid", type=int, default=1, help="N > 1: 1 = ring keys replicated, K3 query-parallel, descriptors sharded (default); 0 = keys sharded too")
+    ap.add_argument("--hybrid", type=int, default=0, help="N > 1: 1 = ring keys replicated, K3 query-parallel, descriptors sharded (measured: 9.5 against 9.2 M q/s at N = 2, "
+                                                           "13.1 against 15.7 M at N = 8: a rank's 128 queries fill half a query tile and meet 148 key ranges); 0 = keys sharded too (default)")
     ap.add_argument("--scdist-tiles", type=int, default=-1, help="candidate tiles per K4 CTA (0 = one per candidate; -1 = the engine's default)")
     ap.add_argument("--cpu-sample", type=int, default=256, help="queries per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
