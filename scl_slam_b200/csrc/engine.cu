@@ -86,8 +86,11 @@ int build_dev(scl_engine* e, const void* pts_dev, const int32_t* offsets_host, i
         if (c > max_points) max_points = c;
     }
     if (insert) { int rc = grow(e, e->n + n_scans); if (rc) return rc; }
-    CK(e->offsets.ensure((size_t)(n_scans + 1) * 4));
-    CK(cudaMemcpyAsync(e->offsets.p, offsets_host, (size_t)(n_scans + 1) * 4, cudaMemcpyHostToDevice, e->stream));
+    const bool inline_offsets = n_scans <= scl_polar_inline_scans();     /* the offsets travel as kernel parameters: no copy in front of the launch */
+    if (!inline_offsets) {
+        CK(e->offsets.ensure((size_t)(n_scans + 1) * 4));
+        CK(cudaMemcpyAsync(e->offsets.p, offsets_host, (size_t)(n_scans + 1) * 4, cudaMemcpyHostToDevice, e->stream));
+    }
     if ((size_t)n_scans > e->gbins_scans) {
         CK(e->gbins.ensure((size_t)n_scans * RS * 4));
         CK(e->tickets.ensure((size_t)n_scans * 4));
@@ -101,18 +104,19 @@ int build_dev(scl_engine* e, const void* pts_dev, const int32_t* offsets_host, i
         od = e->d_desc + (size_t)e->n * RS; ok = e->d_keys + (size_t)e->n * R; on = e->d_knorm + e->n;
         oc = e->d_cstat + (size_t)e->n * 2 * S;
     } else {
-        CK(e->stage_desc.ensure((size_t)n_scans * RS * 4));
+        if (!out_desc_dev) CK(e->stage_desc.ensure((size_t)n_scans * RS * 4));
         CK(e->stage_keys.ensure((size_t)n_scans * R * 4));
         CK(e->stage_knorm.ensure((size_t)n_scans * 4));
-        od = e->stage_desc.as<float>(); ok = e->stage_keys.as<float>(); on = e->stage_knorm.as<float>();
+        od = out_desc_dev ? out_desc_dev : e->stage_desc.as<float>();      /* no insert: the kernel writes the caller's buffer directly */
+        ok = e->stage_keys.as<float>(); on = e->stage_knorm.as<float>();
     }
     StageTimer st(e, 3, e->stream);
     e->db_dirty = e->db_dirty || insert;
-    CK(scl_launch_polar(pts_dev, e->offsets.as<int>(), n_scans, max_points, stride_bytes, R, S, e->p.lidar_height, e->p.max_radius,
-                        e->gbins.as<uint32_t>(), e->tickets.as<int>(), od, ok, on, insert ? e->d_kn2max : nullptr, ring_dev, sector_dev, e->stream));
-    /* the per-entry cache K4 reads: sector key + column norms of the new entries (descriptor.h:1541-1542 recomputes them per pair) */
-    if (oc) CK(scl_launch_ring_keys(od, n_scans, R, S, nullptr, nullptr, nullptr, oc, e->stream));
-    if (out_desc_dev) CK(cudaMemcpyAsync(out_desc_dev, od, (size_t)n_scans * RS * 4, cudaMemcpyDeviceToDevice, e->stream));
+    CK(scl_launch_polar(pts_dev, inline_offsets ? nullptr : e->offsets.as<int>(), offsets_host, n_scans, max_points, stride_bytes, R, S, e->p.lidar_height, e->p.max_radius,
+                        e->gbins.as<uint32_t>(), e->tickets.as<int>(), od, ok, on, insert ? e->d_kn2max : nullptr,
+                        oc /* the per-entry cache K4 reads: sector key + column norms of the new entries (descriptor.h:1541-1542 recomputes them per pair), written by the kernel's epilogue */,
+                        ring_dev, sector_dev, e->stream));
+    if (out_desc_dev && od != out_desc_dev) CK(cudaMemcpyAsync(out_desc_dev, od, (size_t)n_scans * RS * 4, cudaMemcpyDeviceToDevice, e->stream));
     if (where_desc) *where_desc = od;
     if (insert) { append_index(e, n_scans, robots, indices); e->n += n_scans; }
     return SCL_OK;

@@ -41,11 +41,14 @@ constexpr float kNoPoint = -1000.0f;   /* descriptor.h:1411 */
 // by bisection over float bit patterns, the exact floats at which each function steps; the kernel then needs
 // one float division and two binary searches per point — no atanf, no FP64 division — and is bit-exact by
 // construction, including at the sector boundaries.
+// The ring table goes one step further back: r = sqrtf(s) with s = fl(fl(x*x) + fl(y*y)) (:1425), and a correctly
+// rounded square root is monotone, so the ring is a monotone step function of s as well. The thresholds are
+// bisected in s (the host takes the correctly rounded sqrtf of every probe), and the kernel has no square root.
 struct BinTables {
-    int n_ring;            /* ring thresholds: ring = 1 + #(thr <= r) */
+    int n_ring;            /* ring thresholds: ring = 1 + #(thr <= s), s = fl(fl(x*x) + fl(y*y)) */
     int n_sec[4];          /* per quadrant: sector = base + dir * #(thr <= t) */
     int sec_base[4], sec_dir[4], sec_off[4];
-    float r_max;           /* largest float r with double(r) <= max_radius */
+    float s_max;           /* largest float s with double(sqrtf(s)) <= max_radius */
 };
 
 inline uint32_t h_f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
@@ -96,6 +99,10 @@ float h_atanf(float x)
     return (hx >> 31) ? -zz : zz;
 }
 
+// correctly rounded float square root (IEEE 754; the reference's sqrt of a float sum, descriptor.h:1425, rounds the same
+// way whether it goes through sqrtf or through the double sqrt: sqrt is immune to double rounding from 53 to 24 bits)
+float h_sqrtf(float s) { volatile float v = s; volatile float r = std::sqrt(v); return r; }
+
 int h_ceil_to_int(double v) { const double c = std::ceil(v); if (!(c >= -2147483648.0 && c <= 2147483647.0)) return (int)0x80000000; return (int)c; }
 
 int h_ring_of(float r, int R, double max_radius)
@@ -125,11 +132,11 @@ template <typename Pred> bool h_first_true(Pred pred, float* out, float upper = 
 void build_tables(int R, int S, double max_radius, BinTables& bt, std::vector<float>& tab)
 {
     tab.clear();
-    float rm = 0.0f;
-    h_first_true([&](float r) { return (double)r > max_radius; }, &rm);      /* smallest float beyond the radius ... */
-    bt.r_max = std::nextafterf(rm, 0.0f);                                     /* ... so this is the largest one inside */
-    /* ring thresholds are searched inside [0, r_max] only (beyond it int(ceil()) overflows, and the point is dropped anyway) */
-    for (int i = 1; i < R; i++) { float f; if (h_first_true([&](float r) { return h_ring_of(r, R, max_radius) > i; }, &f, bt.r_max)) tab.push_back(f); }
+    float sm = 0.0f;
+    h_first_true([&](float s) { return (double)h_sqrtf(s) > max_radius; }, &sm);   /* smallest s whose root lies beyond the radius (:1429) ... */
+    bt.s_max = std::nextafterf(sm, 0.0f);                                          /* ... so this is the largest one inside */
+    /* ring thresholds are searched inside [0, s_max] only (beyond it int(ceil()) overflows, and the point is dropped anyway) */
+    for (int i = 1; i < R; i++) { float f; if (h_first_true([&](float s) { return h_ring_of(h_sqrtf(s), R, max_radius) > i; }, &f, bt.s_max)) tab.push_back(f); }
     bt.n_ring = (int)tab.size();
     for (int qd = 0; qd < 4; qd++) {
         const int v0 = h_sector_of(qd, 0.0f, S), vinf = h_sector_of(qd, std::numeric_limits<float>::infinity(), S);
@@ -160,7 +167,7 @@ struct PolarSmem {
     int4 qd[4];            /* per quadrant: sector base, direction, -, - */
 };
 
-template <int TOP>       /* TOP = half the padded size: 32 -> 63 entries, 16 -> 31 entries */
+template <int TOP>       /* TOP = half the padded size: 32 -> 63 entries, 16 -> 31, 8 -> 15 */
 __device__ __forceinline__ int count_le_fixed(const float* __restrict__ t, float v)
 {
     int pos = 0;
@@ -169,29 +176,32 @@ __device__ __forceinline__ int count_le_fixed(const float* __restrict__ t, float
     return pos;
 }
 
-// Per-point bin: one float sqrt, one float division, two fixed-depth table searches, no divergent branch.
-// The ratio handed to the sector table is the one xy2theta hands to atan in each quadrant (y/x, y/-x, y/x, -y/x).
-__device__ __forceinline__ bool polar_bin(const PolarParams& p, const PolarSmem& ps, float x, float y, float z, double lidar_height,
+// Per-point bin: one float division, two fixed-depth table searches, no square root, no divergent branch.
+// s is the float sum the reference hands to sqrt (:1425); the ratio handed to the sector table is the one xy2theta
+// hands to atan in each quadrant (y/x, y/-x, y/x, -y/x). RING_TOP / SEC_TOP: search depths (2 TOP - 1 table entries).
+template <int RING_TOP, int SEC_TOP>
+__device__ __forceinline__ bool polar_bin(const PolarSmem& ps, float s_max, float x, float y, float z, double lidar_height,
                                           int& ring, int& sector, float& zf)
 {
     zf = __double2float_rn(__dadd_rn((double)z, lidar_height));                    /* :1422 */
-    const float azim_range = __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))); /* :1425 */
+    const float s = __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y));                   /* :1425, before the root */
     const bool xn = x < 0, yn = y < 0;
     const bool valid = (xn | (x >= 0)) & (yn | (y >= 0));      /* a NaN coordinate is UB in the reference: dropped (Q9) */
     const int qd = xn ? (yn ? 2 : 1) : (yn ? 3 : 0);
     const float num = qd == 3 ? -y : y, den = qd == 1 ? -x : x;
     const float t = __fdiv_rn(num, den);
-    ring = 1 + count_le_fixed<kRingPad / 2>(ps.ring, azim_range);
+    ring = 1 + count_le_fixed<RING_TOP>(ps.ring, s);
     const int4 q = ps.qd[qd];
-    const int cnt = count_le_fixed<kSecPad / 2>(ps.sec[qd], t);
+    const int cnt = count_le_fixed<SEC_TOP>(ps.sec[qd], t);
     sector = (t != t) ? 1 : q.x + q.y * cnt;    /* (0,0): theta = NaN -> int(ceil(NaN)) = INT_MIN -> clamped to 1 */
-    return valid & !(azim_range > p.bt.r_max);  /* double(r) > max_radius (:1429) */
+    return valid & !(s > s_max);                /* double(sqrtf(s)) > max_radius (:1429) */
 }
 
+template <bool VEC4>
 __device__ __forceinline__ void load_xyz(const unsigned char* base, size_t i, int stride, bool vec4, float& x, float& y, float& z)
 {
     const unsigned char* q = base + i * (size_t)stride;
-    if (vec4) {
+    if (VEC4 || vec4) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(q));
         x = v.x; y = v.y; z = v.z;
     } else {
@@ -200,14 +210,40 @@ __device__ __forceinline__ void load_xyz(const unsigned char* base, size_t i, in
     }
 }
 
-// grid = (chunks, scans); block = 256
-template <int kPointsPerThread>
-__global__ void __launch_bounds__(256) polar_bin_kernel(
-    const unsigned char* __restrict__ pts, const int* __restrict__ offsets, int stride, int vec4,
+// Per-entry cache of what distanceBtnScanContext recomputes for both operands of every pair (descriptor.h:1541-1542 ->
+// makeSectorkeyFromScancontext :1477-1489; distDirectSC's column norms :1521-1522): cstat[0..S) = column means (the
+// sector key), cstat[S..2S) = column Euclidean norms, both in double and in the reference's order (sequential over the
+// rows). v * v is exact in double for a float v, so the fused multiply-add rounds exactly like mul-then-add.
+// Worker `tid` of `nworkers` takes every nworkers-th column.
+__device__ __forceinline__ void column_stats(const float* __restrict__ tile, int R, int S, int pitch, int tid, int nworkers, double* __restrict__ out)
+{
+    for (int c = tid; c < S; c += nworkers) {
+        double s = 0.0, ss = 0.0;
+        for (int r = 0; r < R; r++) {
+            const double v = (double)tile[r * pitch + c];
+            s = __dadd_rn(s, v);
+            ss = __fma_rn(v, v, ss);
+        }
+        out[c] = __ddiv_rn(s, (double)R);
+        out[S + c] = __dsqrt_rn(ss);
+    }
+}
+
+// grid = (chunks, scans); block = kPolarThreads.
+// FAST: 16-byte aligned points (one LDG.128 each) and no per-point bin output: the production path. The generic
+// instantiation (any 4-byte aligned stride, optional per-point (ring, sector) for the parity tests) shares polar_bin.
+constexpr int kPolarThreads = 256;
+constexpr int kInlineScans = 256;          /* batches up to this many scans carry their offsets in the kernel parameters */
+struct ScanOffsets { int v[kInlineScans + 1]; };
+template <int kPointsPerThread, bool FAST, int RING_TOP, int SEC_TOP>
+// (48 registers: five CTAs per SM. Forcing six with __launch_bounds__(256, 6) costs 12 bytes of spill and measured slower, 64.6 against 60.6 us.)
+__global__ void __launch_bounds__(kPolarThreads) polar_bin_kernel(
+    const unsigned char* __restrict__ pts, const int* __restrict__ offsets /* null: inl holds them */, const ScanOffsets inl, int stride, int vec4,
     PolarParams p, uint32_t* __restrict__ gbins /* [scans][R*S], zero between launches */,
     int* __restrict__ tickets /* [scans], zero between launches */,
     float* __restrict__ out_desc /* [scans][R*S] */, float* __restrict__ out_keys /* [scans][R] */,
-    float* __restrict__ out_knorm /* [scans] */, float* __restrict__ kn2max, int* __restrict__ out_ring, int* __restrict__ out_sector)
+    float* __restrict__ out_knorm /* [scans] */, float* __restrict__ kn2max, double* __restrict__ out_cstat /* [scans][2*S] or null */,
+    int* __restrict__ out_ring, int* __restrict__ out_sector)
 {
     extern __shared__ uint32_t sbins[];   /* R*S keys, then R*S + R floats for the epilogue */
     __shared__ int s_last;
@@ -215,8 +251,8 @@ __global__ void __launch_bounds__(256) polar_bin_kernel(
     const int RS = p.R * p.S;
     {
         const float nan = __int_as_float(0x7fc00000);
-        for (int i = threadIdx.x; i < kRingPad; i += blockDim.x) ps.ring[i] = i < p.bt.n_ring ? __ldg(p.tab + i) : nan;
-        for (int i = threadIdx.x; i < 4 * kSecPad; i += blockDim.x) {
+        for (int i = threadIdx.x; i < kRingPad; i += kPolarThreads) ps.ring[i] = i < p.bt.n_ring ? __ldg(p.tab + i) : nan;
+        for (int i = threadIdx.x; i < 4 * kSecPad; i += kPolarThreads) {
             const int qd = i / kSecPad, k = i % kSecPad;
             const int n = qd == 0 ? p.bt.n_sec[0] : qd == 1 ? p.bt.n_sec[1] : qd == 2 ? p.bt.n_sec[2] : p.bt.n_sec[3];
             const int off = qd == 0 ? p.bt.sec_off[0] : qd == 1 ? p.bt.sec_off[1] : qd == 2 ? p.bt.sec_off[2] : p.bt.sec_off[3];
@@ -230,55 +266,61 @@ __global__ void __launch_bounds__(256) polar_bin_kernel(
         }
     }
     const double lidar_height = p.lidar_height;
+    const float s_max = p.bt.s_max;
+    const int S = p.S;
     const int scan = blockIdx.y;
-    const int p0 = offsets[scan], p1 = offsets[scan + 1];
+    const int p0 = offsets ? offsets[scan] : inl.v[scan], p1 = offsets ? offsets[scan + 1] : inl.v[scan + 1];
     const uint32_t key_none = scl_float_key(kNoPoint);
 
-    for (int i = threadIdx.x; i < RS; i += blockDim.x) sbins[i] = 0u;
+    for (int i = threadIdx.x; i < RS; i += kPolarThreads) sbins[i] = 0u;
     __syncthreads();
 
     /* Software pipeline: the loads of the next batch of kPointsPerThread points per thread are in flight while the current
      * batch is binned (40 % of the stall samples of the unpipelined loop were the first use of a freshly loaded point). */
-    const int chunk = blockDim.x * kPointsPerThread;
+    constexpr int chunk = kPolarThreads * kPointsPerThread;
     const int step = gridDim.x * chunk;
     const float qnan = __int_as_float(0x7fc00000);
+    const int lane = threadIdx.x & 31;
     float x[kPointsPerThread], y[kPointsPerThread], z[kPointsPerThread];
     float nx[kPointsPerThread], ny[kPointsPerThread], nz[kPointsPerThread];
-    int base = p0 + blockIdx.x * chunk;
+    int base = p0 + blockIdx.x * chunk;              /* uniform over the CTA: the loop below holds warp-wide collectives */
 #pragma unroll
     for (int j = 0; j < kPointsPerThread; j++) {
-        const int i = base + j * blockDim.x + threadIdx.x;
-        if (i < p1) load_xyz(pts, (size_t)i, stride, vec4 != 0, x[j], y[j], z[j]);
+        const int i = base + j * kPolarThreads + threadIdx.x;
+        if (i < p1) load_xyz<FAST>(pts, (size_t)i, stride, vec4 != 0, x[j], y[j], z[j]);
         else { x[j] = y[j] = z[j] = qnan; }
     }
     for (; base < p1; base += step) {
         const int nbase = base + step;
 #pragma unroll
         for (int j = 0; j < kPointsPerThread; j++) {
-            const int i = nbase + j * blockDim.x + threadIdx.x;
-            if (i < p1) load_xyz(pts, (size_t)i, stride, vec4 != 0, nx[j], ny[j], nz[j]);
+            const int i = nbase + j * kPolarThreads + threadIdx.x;
+            if (i < p1) load_xyz<FAST>(pts, (size_t)i, stride, vec4 != 0, nx[j], ny[j], nz[j]);
             else { nx[j] = ny[j] = nz[j] = qnan; }
         }
 #pragma unroll
         for (int j = 0; j < kPointsPerThread; j++) {
-            const int i = base + j * blockDim.x + threadIdx.x;
+            const int i = base + j * kPolarThreads + threadIdx.x;
             int ring = 0, sector = 0; float zf;
-            bool ok = polar_bin(p, ps, x[j], y[j], z[j], lidar_height, ring, sector, zf) && (i < p1);
-            if (out_ring != nullptr && i < p1) { out_ring[i] = ok ? ring : 0; out_sector[i] = ok ? sector : 0; }
+            /* a slot past the end of the scan holds NaN coordinates: not valid, never binned */
+            bool ok = polar_bin<RING_TOP, SEC_TOP>(ps, s_max, x[j], y[j], z[j], lidar_height, ring, sector, zf);
+            if (!FAST) {
+                if (out_ring != nullptr && i < p1) { out_ring[i] = ok ? ring : 0; out_sector[i] = ok ? sector : 0; }
+            }
             ok = ok && !(zf != zf);                     /* desc < NaN is false: NaN heights never win (:1438) */
-            const int bin = ok ? (ring - 1) * p.S + (sector - 1) : -1;
+            const int bin = ok ? (ring - 1) * S + (sector - 1) : -1;
             const uint32_t key = ok ? scl_float_key(zf) : 0u;
             /* warp-aggregated max: one shared atomic per distinct bin per warp */
             const unsigned peers = __match_any_sync(0xffffffffu, bin);
             const uint32_t m = __reduce_max_sync(peers, key);
-            if (ok && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicMax(&sbins[bin], m);
+            if (ok && (__ffs(peers) - 1) == lane) atomicMax(&sbins[bin], m);
         }
 #pragma unroll
         for (int j = 0; j < kPointsPerThread; j++) { x[j] = nx[j]; y[j] = ny[j]; z[j] = nz[j]; }
     }
     __syncthreads();
     uint32_t* g = gbins + (size_t)scan * RS;
-    for (int i = threadIdx.x; i < RS; i += blockDim.x) {
+    for (int i = threadIdx.x; i < RS; i += kPolarThreads) {
         const uint32_t k = sbins[i];
         if (k > key_none) atomicMax(&g[i], k);        /* values <= -1000 can never be the bin result */
     }
@@ -289,10 +331,10 @@ __global__ void __launch_bounds__(256) polar_bin_kernel(
     if (!s_last) return;
     __threadfence();
 
-    /* ---- epilogue by the last CTA of this scan: decode, zero the empties, wire image, ring key */
+    /* ---- epilogue by the last CTA of this scan: decode, zero the empties, wire image, ring key, column statistics */
     float* sdesc = reinterpret_cast<float*>(sbins + RS);
     float* od = out_desc + (size_t)scan * RS;
-    for (int i = threadIdx.x; i < RS; i += blockDim.x) {
+    for (int i = threadIdx.x; i < RS; i += kPolarThreads) {
         const uint32_t k = __ldcg(&g[i]);
         float v = (k > key_none) ? scl_key_float(k) : 0.0f;  /* max(-1000, ..) == -1000 -> 0 (:1450-1453) */
         sdesc[i] = v;
@@ -301,13 +343,18 @@ __global__ void __launch_bounds__(256) polar_bin_kernel(
     }
     if (threadIdx.x == 0) tickets[scan] = 0;
     __syncthreads();
-    /* K2: ring key = float(mean over the row in double, index order) (:1463-1475) */
-    for (int r = threadIdx.x; r < p.R; r += blockDim.x) {
-        double s = 0.0;
-        for (int c = 0; c < p.S; c++) s = __dadd_rn(s, (double)sdesc[r * p.S + c]);
-        const float kf = __double2float_rn(__ddiv_rn(s, (double)p.S));
-        out_keys[(size_t)scan * p.R + r] = kf;
-        sdesc[RS + r] = kf;
+    /* K2: ring key = float(mean over the row in double, index order) (:1463-1475); the upper warps take the per-entry
+     * cache K4 reads (sector key + column norms), so an insert needs no second launch over the new descriptors */
+    if (threadIdx.x < 32) {
+        for (int r = threadIdx.x; r < p.R; r += 32) {
+            double s = 0.0;
+            for (int c = 0; c < S; c++) s = __dadd_rn(s, (double)sdesc[r * S + c]);
+            const float kf = __double2float_rn(__ddiv_rn(s, (double)S));
+            out_keys[(size_t)scan * p.R + r] = kf;
+            sdesc[RS + r] = kf;
+        }
+    } else if (out_cstat) {
+        column_stats(sdesc, p.R, S, S, threadIdx.x - 32, kPolarThreads - 32, out_cstat + (size_t)scan * 2 * S);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -318,23 +365,6 @@ __global__ void __launch_bounds__(256) polar_bin_kernel(
     }
 }
 
-// Per-entry cache of what distanceBtnScanContext recomputes for both operands of every pair (descriptor.h:1541-1542 ->
-// makeSectorkeyFromScancontext :1477-1489; distDirectSC's column norms :1521-1522): cstat[0..S) = column means (the
-// sector key), cstat[S..2S) = column Euclidean norms, both in double and in the reference's order (sequential over the
-// rows). v * v is exact in double for a float v, so the fused multiply-add rounds exactly like mul-then-add.
-__device__ __forceinline__ void column_stats(const float* __restrict__ tile, int R, int S, int pitch, int lane, double* __restrict__ out)
-{
-    for (int c = lane; c < S; c += 32) {
-        double s = 0.0, ss = 0.0;
-        for (int r = 0; r < R; r++) {
-            const double v = (double)tile[r * pitch + c];
-            s = __dadd_rn(s, v);
-            ss = __fma_rn(v, v, ss);
-        }
-        out[c] = __ddiv_rn(s, (double)R);
-        out[S + c] = __dsqrt_rn(ss);
-    }
-}
 
 // K2 stand-alone: ring keys of n descriptors already in device memory (the insert path,
 // descriptor.h:1572-1599). One warp per descriptor; the descriptor is staged in shared memory
@@ -368,7 +398,7 @@ __global__ void __launch_bounds__(256) ring_key_kernel(const float* __restrict__
                 if (kn2max) atomicMax(reinterpret_cast<int*>(kn2max), __float_as_int(n2));
             }
         }
-        if (cstat) column_stats(my, R, S, pitch, lane, cstat + (size_t)d * 2 * S);
+        if (cstat) column_stats(my, R, S, pitch, lane, 32, cstat + (size_t)d * 2 * S);
         __syncwarp();
     }
 }
@@ -401,7 +431,7 @@ __global__ void __launch_bounds__(32 * kWarps) ring_key_fixed_kernel(const float
         }
     }
     __syncwarp();
-    if (cstat) column_stats(tile[warp], R, S, kPitch, lane, cstat + (size_t)d * 2 * S);
+    if (cstat) column_stats(tile[warp], R, S, kPitch, lane, 32, cstat + (size_t)d * 2 * S);
     if (!keys) return;
     for (int r = lane; r < R; r += 32) {
         double s = 0.0;
@@ -423,9 +453,9 @@ __global__ void __launch_bounds__(32 * kWarps) ring_key_fixed_kernel(const float
 
 } // namespace
 
-cudaError_t scl_launch_polar(const void* pts_dev, const int* offsets_dev, int n_scans, int max_points, int stride_bytes,
+cudaError_t scl_launch_polar(const void* pts_dev, const int* offsets_dev, const int* offsets_host, int n_scans, int max_points, int stride_bytes,
                              int R, int S, double lidar_height, double max_radius, uint32_t* gbins, int* tickets,
-                             float* out_desc, float* out_keys, float* out_knorm, float* kn2max, int* out_ring, int* out_sector,
+                             float* out_desc, float* out_keys, float* out_knorm, float* kn2max, double* out_cstat, int* out_ring, int* out_sector,
                              cudaStream_t stream)
 {
     if (n_scans <= 0) return cudaSuccess;
@@ -454,32 +484,59 @@ cudaError_t scl_launch_polar(const void* pts_dev, const int* offsets_dev, int n_
         p.R = R; p.S = S; p.lidar_height = lidar_height; p.bt = hit->bt; p.tab = hit->dev; p.n_tab = hit->n;
     }
     constexpr int kPPT = 4;        /* per batch; two batches per thread are live (software pipeline) */
-    const int chunk = 256 * kPPT;
+    const int chunk = kPolarThreads * kPPT;
     int chunks = (max_points + chunk - 1) / chunk;
     if (chunks < 1) chunks = 1;
-    /* enough CTAs to cover the machine about 8x (measured: 4x 86 us, 8x 76 us, 16x 75 us per 64 scans), but never more chunks than a scan has */
-    const int want = (8 * SCL_NUM_SMS + n_scans - 1) / n_scans;
-    if (chunks > want) chunks = want;
     const int vec4 = (stride_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(pts_dev) & 15) == 0);
-    if (p.bt.n_ring > kRingPad - 1 || p.bt.n_sec[0] > kSecPad - 1 || p.bt.n_sec[1] > kSecPad - 1 || p.bt.n_sec[2] > kSecPad - 1 ||
-        p.bt.n_sec[3] > kSecPad - 1) return cudaErrorNotSupported;       /* up to 64 rings x 124 sectors */
+    int max_sec = 0;
+    for (int q = 0; q < 4; q++) if (p.bt.n_sec[q] > max_sec) max_sec = p.bt.n_sec[q];
+    if (p.bt.n_ring > kRingPad - 1 || max_sec > kSecPad - 1) return cudaErrorNotSupported;       /* up to 64 rings x 124 sectors */
     const size_t smem = (size_t)R * S * 8 + (size_t)R * 4;
-    if (smem > 48 * 1024) {
-        /* geometries above ~6100 bins need the opt-in (per device: the attribute belongs to the current device's context) */
-        static SclOncePerDevice once;
-        if (once.first()) {
-            cudaError_t ea = cudaFuncSetAttribute(polar_bin_kernel<kPPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (ea != cudaSuccess) return ea;
-        }
-        if (smem > 200 * 1024) return cudaErrorNotSupported;
-    }
+    if (smem > 200 * 1024) return cudaErrorNotSupported;
+    /* The production path (16-byte aligned points, no per-point bin output) with the search depths the geometry needs:
+     * 20x60 has 19 ring and 15 sector thresholds per quadrant (5 + 4 steps), 40x120 has 39 and 30 (6 + 5). Everything else
+     * (packed 12-byte points, the parity tests' per-point bins) takes the generic instantiation. */
+    const bool fast = vec4 && out_ring == nullptr;
+    const int variant = !fast ? 0 : (p.bt.n_ring <= 31 && max_sec <= 15) ? 1 : 2;
+    /* Offsets: a batch of up to kInlineScans scans carries them in the kernel parameters (no copy-engine operation in front
+     * of the launch: a stream-ordered switch between the copy and the compute engine costs several microseconds). */
+    ScanOffsets inl;
+    const bool use_inl = offsets_host != nullptr && n_scans <= kInlineScans;
+    if (use_inl) for (int i = 0; i <= n_scans; i++) inl.v[i] = offsets_host[i];
+    else if (!offsets_dev) return cudaErrorInvalidValue;
+    /* Grid: two full waves of resident CTAs (ncu on 64 scans x 113k points: 1216 CTAs at 5 per SM were 1.64 waves and the
+     * SMs idled 19 % of the launch), but never more chunks than a scan has */
+    auto waves_grid = [&](int per_sm) {
+        const int want = (2 * per_sm * SCL_NUM_SMS) / n_scans;        /* measured on the same batch: 1 wave 61.4 us, 2 waves 60.6, 3 waves 62.9, 4 waves 64.0, 6 waves 65.5 */
+        if (want >= 1 && chunks > want) chunks = want;
+    };
     /* gridDim.y is limited to 65535: larger batches go in slices (the per-scan scratch rows move with the slice) */
     for (int s0 = 0; s0 < n_scans; s0 += 65535) {
         const int ns = n_scans - s0 < 65535 ? n_scans - s0 : 65535;
-        dim3 grid(chunks, ns);
-        polar_bin_kernel<kPPT><<<grid, 256, smem, stream>>>(static_cast<const unsigned char*>(pts_dev), offsets_dev + s0, stride_bytes, vec4, p,
-                                                           gbins + (size_t)s0 * R * S, tickets + s0, out_desc + (size_t)s0 * R * S, out_keys + (size_t)s0 * R,
-                                                           out_knorm + s0, kn2max, out_ring, out_sector);
+#define SCL_POLAR_LAUNCH(FAST, RT, ST)                                                                                              \
+        do {                                                                                                                       \
+            if (smem > 48 * 1024) {   /* geometries above ~6100 bins need the opt-in (per device: the attribute belongs to the current device's context) */ \
+                static SclOncePerDevice once;                                                                                      \
+                if (once.first()) {                                                                                                \
+                    cudaError_t ea = cudaFuncSetAttribute(polar_bin_kernel<kPPT, FAST, RT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+                    if (ea != cudaSuccess) return ea;                                                                              \
+                }                                                                                                                  \
+            }                                                                                                                      \
+            if (s0 == 0) {                                                                                                         \
+                int per_sm = 0;                                                                                                    \
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, polar_bin_kernel<kPPT, FAST, RT, ST>, kPolarThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 4; \
+                waves_grid(per_sm);                                                                                                \
+            }                                                                                                                      \
+            dim3 grid(chunks, ns);                                                                                                 \
+            polar_bin_kernel<kPPT, FAST, RT, ST><<<grid, kPolarThreads, smem, stream>>>(                                            \
+                static_cast<const unsigned char*>(pts_dev), use_inl ? nullptr : offsets_dev + s0, inl, stride_bytes, vec4, p, gbins + (size_t)s0 * R * S, tickets + s0, \
+                out_desc + (size_t)s0 * R * S, out_keys + (size_t)s0 * R, out_knorm + s0, kn2max,                                   \
+                out_cstat ? out_cstat + (size_t)s0 * 2 * S : nullptr, out_ring, out_sector);                                        \
+        } while (0)
+        if (variant == 1) SCL_POLAR_LAUNCH(true, 16, 8);
+        else if (variant == 2) SCL_POLAR_LAUNCH(true, 32, 16);
+        else SCL_POLAR_LAUNCH(false, 32, 16);
+#undef SCL_POLAR_LAUNCH
         cudaError_t el = cudaGetLastError();
         if (el != cudaSuccess) return el;
     }
@@ -506,8 +563,10 @@ cudaError_t scl_launch_ring_keys(const float* desc_dev, int n, int R, int S, flo
     return cudaGetLastError();
 }
 
+int scl_polar_inline_scans() { return kInlineScans; }
+
 void scl_preload_k1()
 {
-    SCL_TOUCH(polar_bin_kernel<4>); SCL_TOUCH(ring_key_kernel);
+    SCL_TOUCH((polar_bin_kernel<4, true, 16, 8>)); SCL_TOUCH((polar_bin_kernel<4, true, 32, 16>)); SCL_TOUCH((polar_bin_kernel<4, false, 32, 16>)); SCL_TOUCH(ring_key_kernel);
     SCL_TOUCH((ring_key_fixed_kernel<20, 60, 4>)); SCL_TOUCH((ring_key_fixed_kernel<40, 120, 2>));
 }

@@ -5,10 +5,14 @@
 #include <stdint.h>
 
 // K1 (+K2 epilogue): polar binning of a batch of scans. See k1_polar.cu.
-cudaError_t scl_launch_polar(const void* pts_dev, const int* offsets_dev, int n_scans, int max_points, int stride_bytes,
+// offsets_host (may be null): the same n_scans + 1 offsets on the host; batches of up to scl_polar_inline_scans() scans take them
+// from there (kernel parameters) and never read offsets_dev, which may then be null.
+int scl_polar_inline_scans();
+cudaError_t scl_launch_polar(const void* pts_dev, const int* offsets_dev, const int* offsets_host, int n_scans, int max_points, int stride_bytes,
                              int R, int S, double lidar_height, double max_radius, uint32_t* gbins, int* tickets,
-                             float* out_desc, float* out_keys, float* out_knorm, float* kn2max, int* out_ring, int* out_sector,
-                             cudaStream_t stream);
+                             float* out_desc, float* out_keys, float* out_knorm, float* kn2max,
+                             double* out_cstat /* per scan 2*S doubles (sector key | column norms, as scl_launch_ring_keys writes them) or null */,
+                             int* out_ring, int* out_sector, cudaStream_t stream);
 // K2: ring keys (+ squared key norms) of descriptors already in device memory.
 //     kn2max (device scalar, may be null) is raised to the largest squared norm seen (atomicMax on the float bits).
 //     cstat (may be null): per descriptor 2*S doubles, the column means (sector key, descriptor.h:1477-1489) and the column

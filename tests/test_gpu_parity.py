@@ -91,6 +91,67 @@ def test_atanf_device_bit_exact(eng_mod):
     assert np.array_equal(ring, oring)
 
 
+@pytest.mark.parametrize("rs", [(20, 60), (40, 120), (10, 36)])
+def test_polar_ring_edges_and_fast_path(eng_mod, rs):
+    """The ring table lives in s = fl(fl(x*x) + fl(y*y)) (no square root in the kernel): points a few ulps either side of
+    every ring boundary and of the radius limit, per-point bins against the oracle (generic instantiation) and the
+    descriptor of the production instantiation (16-byte points, no per-point output) against it as well."""
+    R, S = rs
+    e, o = eng_mod.ScanContextB200(numRing=R, numSector=S), Oracle(num_ring=R, num_sector=S)
+    rng = np.random.default_rng(5)
+    chunks = []
+    for k in range(1, R + 1):
+        r = np.float32(80.0 * k / R)
+        for a in rng.uniform(0, 2 * np.pi, 24):
+            x0, y0 = np.float32(r * np.cos(a)), np.float32(r * np.sin(a))
+            xs = [x0]
+            for _ in range(4):
+                xs.append(np.nextafter(xs[-1], np.float32(np.inf)))
+            for _ in range(4):
+                xs.insert(0, np.nextafter(xs[0], np.float32(-np.inf)))
+            for x in xs:
+                chunks.append((x, y0, rng.uniform(-2, 12)))
+        for d in (-3, -2, -1, 0, 1, 2, 3):       # on an axis: s = fl(x*x) exactly
+            x = r
+            for _ in range(abs(d)):
+                x = np.nextafter(x, np.float32(np.inf if d > 0 else -np.inf))
+            chunks.append((x, 0.0, 1.0)); chunks.append((0.0, -x, 2.0))
+    rad = np.exp(rng.uniform(np.log(1e-4), np.log(90.0), 200000))
+    ang = rng.uniform(0, 2 * np.pi, rad.size)
+    bulk = np.stack([rad * np.cos(ang), rad * np.sin(ang), rng.uniform(-3, 15, rad.size)], 1)
+    pts3 = np.concatenate([np.array(chunks, np.float64), bulk]).astype(np.float32)
+    pts = np.zeros((pts3.shape[0], 8), np.float32); pts[:, :3] = pts3
+    desc, ring, sector = e.make_scancontext(pts, want_bins=True)
+    odesc, oring, osector = o.make_scancontext(pts, want_bins=True)
+    assert np.array_equal(ring, oring), int((ring != oring).sum())
+    assert np.array_equal(sector, osector), int((sector != osector).sum())
+    assert np.array_equal(_bits(desc), _bits(odesc))
+    fast = e.make_scancontext(pts)                      # production instantiation
+    assert np.array_equal(_bits(fast), _bits(odesc))
+    packed16 = np.ascontiguousarray(pts[:, :4])         # 16-byte points: also the production instantiation
+    assert np.array_equal(_bits(e.make_scancontext(packed16)), _bits(odesc))
+    packed12 = np.ascontiguousarray(pts[:, :3])         # 12-byte points: generic instantiation without per-point output
+    assert np.array_equal(_bits(e.make_scancontext(packed12)), _bits(odesc))
+
+
+def test_build_writes_the_column_statistics(eng_mod):
+    """The K1 epilogue writes the per-entry cache K4 reads (sector key + column norms). Entries built from clouds and the same
+    descriptors inserted as wire images (statistics from the stand-alone K2 kernel) give identical SC distances and shifts."""
+    world = synth.make_world(6, 300)
+    traj = synth.trajectory(160, seed=6)
+    dirs = synth.lidar_dirs("vlp16", n_az=450)
+    clouds = [synth.to_pcl_xyzi(synth.scan(world, traj[i], dirs, seed=i)) for i in range(160)]
+    for R, S in [(20, 60), (40, 120)]:
+        a, b = eng_mod.ScanContextB200(numRing=R, numSector=S, numCandidates=6), eng_mod.ScanContextB200(numRing=R, numSector=S, numCandidates=6)
+        descs = a.build_batch(clouds, insert=True)
+        b.insert_batch(np.stack([d.reshape(-1) for d in descs]))
+        q = np.arange(40, 160, 7, dtype=np.int32)
+        ra, rb = a.query_batch(q_ids=q, K=6, n_db=120, metric=0), b.query_batch(q_ids=q, K=6, n_db=120, metric=0)
+        assert np.array_equal(ra["cand_ids"], rb["cand_ids"]) and np.array_equal(ra["cand_shift"], rb["cand_shift"])
+        assert np.array_equal(_bits(ra["cand_dist"]), _bits(rb["cand_dist"]))
+        assert np.array_equal(ra["best_id"], rb["best_id"])
+
+
 def test_build_batch_and_insert(eng_mod):
     world = synth.make_world(4, 300)
     traj = synth.trajectory(30, seed=4)
