@@ -22,6 +22,7 @@
 #include "kernels.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -464,9 +465,11 @@ cudaError_t scl_launch_polar(const void* pts_dev, const int* offsets_dev, const 
     static std::vector<Cached> cache;
     static std::mutex cache_mu;
     PolarParams p;
+    int p_device = 0;
     {
         std::lock_guard<std::mutex> lk(cache_mu);
         int device = 0; cudaGetDevice(&device);
+        p_device = device;
         const Cached* hit = nullptr;
         for (const Cached& c : cache) if (c.R == R && c.S == S && c.max_radius == max_radius && c.device == device) { hit = &c; break; }
         if (!hit) {
@@ -523,8 +526,18 @@ cudaError_t scl_launch_polar(const void* pts_dev, const int* offsets_dev, const 
                 }                                                                                                                  \
             }                                                                                                                      \
             if (s0 == 0) {                                                                                                         \
-                int per_sm = 0;                                                                                                    \
-                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, polar_bin_kernel<kPPT, FAST, RT, ST>, kPolarThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 4; \
+                /* resident CTAs per SM: asked once per (instantiation, device, shared-memory size), not per launch */               \
+                static std::atomic<long long> occ_cache[16];                                                                       \
+                const int dslot = p_device & 15;                                                                                   \
+                const long long tag = ((long long)smem << 8) | 1;                                                                  \
+                long long c = occ_cache[dslot].load(std::memory_order_relaxed);                                                    \
+                int per_sm = (int)(c & 0xff) - 1;                                                                                  \
+                if ((c >> 8) != (tag >> 8) || per_sm < 1) {                                                                        \
+                    per_sm = 0;                                                                                                    \
+                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, polar_bin_kernel<kPPT, FAST, RT, ST>, kPolarThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 4; \
+                    if (per_sm > 200) per_sm = 200;                                                                                \
+                    occ_cache[dslot].store(((long long)smem << 8) | (long long)(per_sm + 1), std::memory_order_relaxed);          \
+                }                                                                                                                  \
                 waves_grid(per_sm);                                                                                                \
             }                                                                                                                      \
             dim3 grid(chunks, ns);                                                                                                 \
