@@ -729,7 +729,7 @@ def arm_c1(engine, synth, dev, pk, cpu):
     dtb = time.perf_counter() - t0
     res = {"workload": "c1: 2,000-keyframe VLP-16 trajectory (two laps, 28.8k rays per scan), build + intra + inter query per keyframe",
            "value": n / dt, "unit": "keyframes/s (build + insert + both queries, one call each, host buffers; median of eight 250-keyframe segments)",
-           "whole_run_keyframes_per_s": n / dt_all, "loops_found": loops,
+           "whole_run_keyframes_per_s": n / dt_all, "segment_keyframes_per_s": [round(1.0 / t) for t in seg_t], "loops_found": loops,
            "points_per_scan": float(np.mean([c.shape[0] for c in clouds])), "batched_keyframes_per_s": n / dtb,
            "synthetic_scan_generation_s": t_gen, "batched_best_ids_found": int((res_b["best_id"] >= 0).sum())}
     if cpu:
