@@ -785,6 +785,7 @@ int scl_lane_sync(scl_engine* e, int lane)
         std::lock_guard<std::mutex> lk(e->mu);
         if (lane < 0 || lane >= scl_engine::kLanes) FAIL(SCL_ERR_INVALID, "no such lane");
         s = e->lanes[lane].stream;
+        if (!s && lane == 0) s = e->stream;          /* lane 0 is the engine's own stream, also before its first batch */
     }
     cudaSetDevice(e->device);
     if (s && cudaStreamSynchronize(s) != cudaSuccess) { std::lock_guard<std::mutex> lk(e->mu); FAIL(SCL_ERR_CUDA, "cudaStreamSynchronize failed"); }

@@ -55,24 +55,28 @@ __device__ __forceinline__ float key_d2(const float (&q)[R], const float* __rest
 }
 
 // k-way merge of the per-split sorted lists of one query by one warp; order = (d2, id). The lists were written by other
-// CTAs of the same launch: they are read through L2 (__ldcg).
+// CTAs of the same launch: they are read through L2 (__ldcg). Every lane keeps the HEAD RECORDS of its (up to eight) lists in
+// registers: one round trip fetches them all, and a round costs one more only for the lane whose head was taken. (The first
+// version re-read every head in every round inside the compare chain, and the compiler kept those loads in program order:
+// 16 dependent L2 round trips per round, 48 us for the merge of 256 splits — measured as the tail of knn_fallback_kernel,
+// profiles/r02i_launches_summary.md — against ~4 us now.)
 __device__ void merge_splits_warp(const int32_t* __restrict__ pi, const float* __restrict__ pd, int splits, int K, int lane,
                                   int32_t* __restrict__ out_ids, float* __restrict__ out_d2)
 {
     constexpr int kPer = kMaxSplits / 32;
-    int head[kPer];
+    const float inf = __int_as_float(0x7f800000);
+    int head[kPer]; float hd[kPer]; int hi[kPer];
 #pragma unroll
-    for (int s = 0; s < kPer; s++) head[s] = 0;
+    for (int s = 0; s < kPer; s++) {
+        const int sp = lane + 32 * s;
+        head[s] = 0; hd[s] = inf; hi[s] = 0x7fffffff;
+        if (sp < splits) { hd[s] = __ldcg(pd + (size_t)sp * K); hi[s] = __ldcg(pi + (size_t)sp * K); }
+    }
     for (int r = 0; r < K; r++) {
-        float bd = __int_as_float(0x7f800000); int bi = 0x7fffffff; int bs = -1;
+        float bd = inf; int bi = 0x7fffffff; int bs = -1;
 #pragma unroll
-        for (int s = 0; s < kPer; s++) {
-            const int sp = lane + 32 * s;
-            if (sp < splits && head[s] < K) {
-                const float d = __ldcg(pd + (size_t)sp * K + head[s]); const int id = __ldcg(pi + (size_t)sp * K + head[s]);
-                if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; bs = s; }
-            }
-        }
+        for (int s = 0; s < kPer; s++)
+            if (hd[s] < bd || (hd[s] == bd && hi[s] < bi)) { bd = hd[s]; bi = hi[s]; bs = s; }
         /* warp argmin on (d2, id) */
         float wd = bd; int wi = bi;
 #pragma unroll
@@ -81,9 +85,16 @@ __device__ void merge_splits_warp(const int32_t* __restrict__ pi, const float* _
             if (od < wd || (od == wd && oi < wi)) { wd = od; wi = oi; }
         }
         const bool found = wi != 0x7fffffff;
-        if (bs >= 0 && bi == wi && bd == wd && found) {
+        if (bs >= 0 && bi == wi && bd == wd && found) {     /* keys are distinct: exactly one lane owns the winner */
 #pragma unroll
-            for (int s = 0; s < kPer; s++) if (s == bs) head[s]++;
+            for (int s = 0; s < kPer; s++) {
+                if (s == bs) {
+                    const int sp = lane + 32 * s;
+                    head[s]++;
+                    hd[s] = inf; hi[s] = 0x7fffffff;
+                    if (head[s] < K) { hd[s] = __ldcg(pd + (size_t)sp * K + head[s]); hi[s] = __ldcg(pi + (size_t)sp * K + head[s]); }
+                }
+            }
         }
         if (lane == 0) {
             out_ids[r] = found ? wi : -1;
@@ -197,7 +208,8 @@ __global__ void __launch_bounds__(kTQ) knn_exact_kernel(const float* __restrict_
 // grid = (key splits, queries).
 constexpr int kSmallThreads = 256;
 // bx, gdx: the CTA's key split and the number of splits; query qi, whose partial lists and ticket live in slot `slot`.
-template <int R, int METRIC, int KPT>
+// MERGE = false: the per-split lists are left for the caller to merge (knn_fallback_kernel merges all listed queries at the end).
+template <int R, int METRIC, int KPT, bool MERGE = true>
 __device__ __forceinline__ void small_body(const float* __restrict__ qkeys, const float* __restrict__ keys, int n_db,
                                            int K, int split_len, int id_mul, int id_add, int32_t* __restrict__ part_ids,
                                            float* __restrict__ part_d2, int* __restrict__ tickets,
@@ -254,9 +266,12 @@ __device__ __forceinline__ void small_body(const float* __restrict__ qkeys, cons
     }
     if (t == 0) {
         for (; r < K; r++) { part_d2[o + r] = inf; part_ids[o + r] = 0x7fffffff; }
-        __threadfence();
-        s_last = (atomicAdd(&tickets[slot], 1) == gdx - 1);
+        if (MERGE) {
+            __threadfence();
+            s_last = (atomicAdd(&tickets[slot], 1) == gdx - 1);
+        }
     }
+    if (!MERGE) return;
     __syncthreads();
     if (!s_last) return;                                /* block-uniform */
     __threadfence();
@@ -294,9 +309,25 @@ __global__ void __launch_bounds__(kSmallThreads) knn_fallback_kernel(const float
     if ((int)blockIdx.x < n_small) {
         if (c > kSmallList) return;
         for (int slot = 0; slot < c; slot++) {
-            small_body<R, METRIC, KPT>(qkeys, keys, n_db, K, split_len_small, id_mul, id_add, part_ids, part_d2, tickets, out_ids, out_d2,
-                                       (int)blockIdx.x, n_small, slot, qlist[slot]);
+            small_body<R, METRIC, KPT, false>(qkeys, keys, n_db, K, split_len_small, id_mul, id_add, part_ids, part_d2, tickets, out_ids, out_d2,
+                                              (int)blockIdx.x, n_small, slot, qlist[slot]);
             __syncthreads();                             /* the body's shared scratch is reused by the next query */
+        }
+        /* ONE ticket for the whole list, and the last CTA merges every listed query, a warp each. A ticket and a merge per query
+         * made a chain: the CTA that merges query s arrives late at query s + 1, is the last one there again, merges again ...
+         * (five listed queries: 83 us of scans, 186 us of kernel; profiles/r02i_launches_summary.md). */
+        __shared__ int s_last_all;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last_all = (atomicAdd(&tickets[0], 1) == n_small - 1);
+        __syncthreads();
+        if (!s_last_all) return;
+        __threadfence();
+        if (threadIdx.x == 0) tickets[0] = 0;
+        for (int slot = (int)(threadIdx.x >> 5); slot < c; slot += kSmallThreads / 32) {
+            const int qq = qlist[slot];
+            merge_splits_warp(part_ids + (size_t)slot * n_small * K, part_d2 + (size_t)slot * n_small * K, n_small, K, (int)(threadIdx.x & 31),
+                              out_ids + (size_t)qq * K, out_d2 + (size_t)qq * K);
         }
     } else {
         if (c <= kSmallList) return;

@@ -229,6 +229,36 @@ def _cloud(points):
     return pts, pts.shape[0], pts.shape[1] * 4
 
 
+def _torch_stream_sync():
+    """Block the host until everything queued on torch's current CUDA stream has finished (no-op without torch / CUDA)."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.current_stream().synchronize()
+    except ImportError:
+        pass
+
+
+def _ordered_dev_call(fn):
+    """Device-pointer calls of an engine that runs on its OWN (non-blocking) stream are not ordered against the caller's stream:
+    a tensor torch is still filling may be read too early, and a temporary handed to the call may be freed and reused by torch's
+    allocator while the engine still reads it. The Python mirror therefore makes such a call synchronous on both sides; an
+    engine bound to the caller's stream (set_stream) is ordered by the stream itself and pays nothing."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **kw):
+        if getattr(self, "_bound", False):
+            return fn(self, *a, **kw)
+        _torch_stream_sync()
+        try:
+            return fn(self, *a, **kw)
+        finally:
+            if getattr(self, "h", None):
+                self.lib.scl_lane_sync(self.h, 0)
+    return wrapper
+
+
 class ScanContextB200:
     """Drop-in for scan_context_descriptor (descriptor.h:1304-1801); constructor arguments and
     defaults are those of descriptor.h:1307-1316."""
@@ -317,6 +347,7 @@ class ScanContextB200:
 
     def set_stream(self, cuda_stream_handle):
         self._ck(self.lib.scl_set_stream(self.h, C.c_void_p(cuda_stream_handle)))
+        self._bound = True                   # the caller's stream now orders the device-pointer calls
 
     def build_batch(self, clouds, insert=True, robots=None, indices=None):
         """clouds: list of [P_i, C] float32 arrays with one common C. Returns [n, R, S] descriptors."""
@@ -332,6 +363,7 @@ class ScanContextB200:
                                           _ptr(rb), _ptr(ix), out.ctypes.data))
         return out
 
+    @_ordered_dev_call
     def build_batch_dev(self, pts_dev, offsets, stride_bytes, insert=True, out_dev=None):
         offs = np.ascontiguousarray(offsets, np.int32)
         self._ck(self.lib.scl_build_batch_dev(self.h, _ptr(pts_dev), offs.ctypes.data, offs.size - 1, stride_bytes,
@@ -343,6 +375,7 @@ class ScanContextB200:
         ix = None if indices is None else np.ascontiguousarray(indices, np.int32)
         self._ck(self.lib.scl_insert_batch(self.h, d.ctypes.data, d.shape[0], _ptr(rb), _ptr(ix)))
 
+    @_ordered_dev_call
     def insert_batch_dev(self, descs_dev):
         """descs_dev: contiguous float32 CUDA tensor [n, R, S] (or [n, R*S])."""
         n = descs_dev.shape[0]
@@ -381,6 +414,7 @@ class ScanContextB200:
     def query_batch_wait(self, ticket):
         self._ck(self.lib.scl_query_batch_wait(self.h, ticket))
 
+    @_ordered_dev_call
     def query_batch_dev(self, q_desc_dev, q_ids_dev, Q, K, n_db, metric, out):
         """Device-pointer batch query, asynchronous on the engine's stream. `out` maps the
         scl_batch_result field names to CUDA tensors (missing names are not produced)."""
@@ -389,6 +423,7 @@ class ScanContextB200:
                              ("cand_ids", "cand_d2", "cand_dist", "cand_shift", "best_id", "best_dist", "best_shift")])
         self._ck(self.lib.scl_query_batch_dev(self.h, C.byref(q), C.byref(r)))
 
+    @_ordered_dev_call
     def merge_shards_dev(self, world, Q, K, q_ids_dev, all_ids, all_d2, all_dist, all_shift, out):
         r = SclBatchResult(*[_ptr(out.get(k)) for k in
                              ("cand_ids", "cand_d2", "cand_dist", "cand_shift", "best_id", "best_dist", "best_shift")])
@@ -406,10 +441,12 @@ class ScanContextB200:
     def set_tc_stages(self, stages):
         self._ck(self.lib.scl_set_tc_stages(self.h, stages))
 
+    @_ordered_dev_call
     def export_keys_dev(self, keys_out_dev, n):
         """This engine's first n ring keys [n][R] (device to device)."""
         self._ck(self.lib.scl_export_keys_dev(self.h, _ptr(keys_out_dev), n))
 
+    @_ordered_dev_call
     def set_replicated_keys_dev(self, keys_dev, n_total):
         """Hybrid sharding: every ring key, in global key order, on this rank (n_total = 0: back to plain sharding)."""
         self._ck(self.lib.scl_set_replicated_keys_dev(self.h, _ptr(keys_dev), n_total))
@@ -433,17 +470,21 @@ class ScanContextB200:
         return ms.value, n.value
 
     # ---- two-phase multi-GPU exchange (include/scl_engine.h) -------------------------------
+    @_ordered_dev_call
     def knn_batch_dev(self, q_desc_dev, Q, K, n_db, metric, ids_dev, d2_dev):
         q = SclBatchQuery(_ptr(q_desc_dev), None, Q, K, n_db, metric)
         self._ck(self.lib.scl_knn_batch_dev(self.h, C.byref(q), _ptr(ids_dev), _ptr(d2_dev)))
 
+    @_ordered_dev_call
     def merge_topk_dev(self, world, Q, K, ids_base, d2_base, rank_stride_bytes, out_ids, out_d2):
         self._ck(self.lib.scl_merge_topk_dev(self.h, world, Q, K, _ptr(ids_base), _ptr(d2_base), rank_stride_bytes,
                                              _ptr(out_ids), _ptr(out_d2)))
 
+    @_ordered_dev_call
     def scdist_owned_dev(self, q_desc_dev, Q, K, cand_ids_dev, dist_dev, shift_dev):
         self._ck(self.lib.scl_scdist_owned_dev(self.h, _ptr(q_desc_dev), None, Q, K, _ptr(cand_ids_dev), _ptr(dist_dev), _ptr(shift_dev)))
 
+    @_ordered_dev_call
     def combine_owned_dev(self, world, Q, K, cand_ids, dist_base, shift_base, rank_stride_bytes, out):
         r = SclBatchResult(*[_ptr(out.get(k)) for k in
                              ("cand_ids", "cand_d2", "cand_dist", "cand_shift", "best_id", "best_dist", "best_shift")])
@@ -501,9 +542,11 @@ class ScanContextB200:
     def xchg_close(self):
         self._ck(self.lib.scl_xchg_close(self.h))
 
+    @_ordered_dev_call
     def xchg_merge_topk_dev(self, seq, Q, K, my_block, out_ids, out_d2):
         self._ck(self.lib.scl_xchg_merge_topk_dev(self.h, seq, Q, K, _ptr(my_block), _ptr(out_ids), _ptr(out_d2)))
 
+    @_ordered_dev_call
     def xchg_combine_dev(self, seq, Q, K, my_block, cand_ids, out):
         r = SclBatchResult(*[_ptr(out.get(k)) for k in
                              ("cand_ids", "cand_d2", "cand_dist", "cand_shift", "best_id", "best_dist", "best_shift")])

@@ -146,10 +146,19 @@ class LidarIrisRowKeysB200:
         return idx, gk, d2
 
     def knn_batch_dev(self, q_dev, Q, from_robot, n_limit, K, knn_mode, idx_dev, d2_dev):
+        """Asynchronous on the object's stream. An object that still runs on its own (non-blocking) stream is not ordered against
+        torch's: the call is then made synchronous on both sides (see engine._ordered_dev_call); bind it with set_stream to avoid that."""
+        bound = getattr(self, "_bound", False)
+        if not bound:
+            import torch
+            torch.cuda.current_stream().synchronize()
         self._ck(self.lib.scl_rowkey_knn_batch_dev(self.h, q_dev.data_ptr(), Q, from_robot, n_limit, K, knn_mode, idx_dev.data_ptr(), d2_dev.data_ptr()))
+        if not bound:
+            torch.cuda.synchronize()
 
     def set_stream(self, cuda_stream):
         self._ck(self.lib.scl_rowkey_set_stream(self.h, cuda_stream))
+        self._bound = True
 
     def knn_stats(self):
         a, b = C.c_longlong(), C.c_longlong()
