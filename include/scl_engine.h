@@ -88,6 +88,16 @@ int scl_build_insert(scl_engine* e, const void* pts, int n, int stride_bytes, in
  * may be NULL) receive the 1-based bin of every point, 0 for dropped points (parity checks). */
 int scl_make_scancontext(scl_engine* e, const void* pts, int n, int stride_bytes, float* out_desc,
                          int32_t* out_ring, int32_t* out_sector);
+/* The bin tables of a geometry (host code only, no device needed; for inspection and for the CPU parity test). The kernel does
+ * not evaluate atanf, sqrt or the double-precision index formulas of descriptor.h:1352-1374,1425-1435 per point: ring and
+ * sector are monotone step functions of one float each, and these are the exact floats at which they step.
+ *   ring   = 1 + #{ i < *n_ring : ring_thr[i] <= s },  s = fl(fl(x*x) + fl(y*y))   (the float the reference hands to sqrt);
+ *            a point is dropped when s > *s_max  (double(sqrtf(s)) > max_radius, :1429)
+ *   sector = sec_base[q] + sec_dir[q] * #{ k < n_sec[q] : sec_thr[31*q + k] <= t },  q = quadrant (0: x>=0,y>=0; 1: x<0,y>=0;
+ *            2: x<0,y<0; 3: x>=0,y<0),  t = fl(|y| / |x|) as xy2theta hands it to atan; t NaN -> sector 1
+ * ring_thr: room for 63 floats, sec_thr: 4 x 31 floats, n_sec / sec_base / sec_dir: 4 ints each. Any pointer may be NULL. */
+int scl_polar_tables(const scl_params* p, float* ring_thr, int32_t* n_ring, float* s_max, float* sec_thr, int32_t* n_sec,
+                     int32_t* sec_base, int32_t* sec_dir);
 /* Batched build: n_scans clouds concatenated in pts; scan i is points [offsets[i], offsets[i+1]).
  * insert != 0 appends them (robots/indices give the metadata, may be NULL -> robot 0, index = key).
  * out_desc: n_scans*R*S floats or NULL. */

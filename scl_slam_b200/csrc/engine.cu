@@ -631,6 +631,13 @@ int scl_set_replicated_keys_dev(scl_engine* e, const float* keys_dev, int n_tota
     return SCL_OK;
 }
 
+int scl_polar_tables(const scl_params* p, float* ring_thr, int32_t* n_ring, float* s_max, float* sec_thr, int32_t* n_sec, int32_t* sec_base, int32_t* sec_dir)
+{
+    if (!p) return SCL_ERR_INVALID;
+    const int rc = scl_polar_tables_host(p->num_ring, p->num_sector, p->max_radius, ring_thr, n_ring, s_max, sec_thr, n_sec, sec_base, sec_dir);
+    return rc == 0 ? SCL_OK : (rc == 1 ? SCL_ERR_INVALID : SCL_ERR_UNSUPPORTED);
+}
+
 int scl_build_insert(scl_engine* e, const void* pts, int n, int stride_bytes, int8_t robot, int index, float* out_desc)
 {
     LOCK();

@@ -576,6 +576,29 @@ cudaError_t scl_launch_ring_keys(const float* desc_dev, int n, int R, int S, flo
     return cudaGetLastError();
 }
 
+// The bin tables of a geometry, for inspection (include/scl_engine.h: scl_polar_tables). Pure host code: this is what the
+// kernel keeps in shared memory, so a CPU test can check the tables against the oracle's per-point bins without a GPU.
+int scl_polar_tables_host(int R, int S, double max_radius, float* ring_thr, int* n_ring, float* s_max,
+                          float* sec_thr, int* n_sec, int* sec_base, int* sec_dir)
+{
+    if (R < 1 || S < 1 || !(max_radius > 0.0)) return 1;
+    BinTables bt; std::vector<float> tab;
+    build_tables(R, S, max_radius, bt, tab);
+    int max_sec = 0;
+    for (int q = 0; q < 4; q++) if (bt.n_sec[q] > max_sec) max_sec = bt.n_sec[q];
+    if (bt.n_ring > kRingPad - 1 || max_sec > kSecPad - 1) return 2;
+    if (n_ring) *n_ring = bt.n_ring;
+    if (s_max) *s_max = bt.s_max;
+    if (ring_thr) for (int i = 0; i < bt.n_ring; i++) ring_thr[i] = tab[i];
+    for (int q = 0; q < 4; q++) {
+        if (n_sec) n_sec[q] = bt.n_sec[q];
+        if (sec_base) sec_base[q] = bt.sec_base[q];
+        if (sec_dir) sec_dir[q] = bt.sec_dir[q];
+        if (sec_thr) for (int k = 0; k < bt.n_sec[q]; k++) sec_thr[q * (kSecPad - 1) + k] = tab[bt.sec_off[q] + k];
+    }
+    return 0;
+}
+
 int scl_polar_inline_scans() { return kInlineScans; }
 
 void scl_preload_k1()

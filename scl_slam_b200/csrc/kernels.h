@@ -8,6 +8,9 @@
 // offsets_host (may be null): the same n_scans + 1 offsets on the host; batches of up to scl_polar_inline_scans() scans take them
 // from there (kernel parameters) and never read offsets_dev, which may then be null.
 int scl_polar_inline_scans();
+// host only: the threshold tables polar_bin_kernel keeps in shared memory (ring_thr: up to 63, sec_thr: 4 x 31); 0 = ok
+int scl_polar_tables_host(int R, int S, double max_radius, float* ring_thr, int* n_ring, float* s_max,
+                          float* sec_thr, int* n_sec, int* sec_base, int* sec_dir);
 cudaError_t scl_launch_polar(const void* pts_dev, const int* offsets_dev, const int* offsets_host, int n_scans, int max_points, int stride_bytes,
                              int R, int S, double lidar_height, double max_radius, uint32_t* gbins, int* tickets,
                              float* out_desc, float* out_keys, float* out_knorm, float* kn2max,

@@ -22,7 +22,7 @@ _STATUS = {1: "SCL_ERR_INVALID", 2: "SCL_ERR_CUDA", 3: "SCL_ERR_UNSUPPORTED", 4:
 # every symbol include/scl_engine.h declares (tests check the library exports all of them)
 EXPORTS = [
     "scl_default_params", "scl_default_icp_params", "scl_create", "scl_destroy", "scl_last_error", "scl_set_stream",
-    "scl_reserve", "scl_set_shard", "scl_build_insert", "scl_make_scancontext", "scl_build_batch", "scl_build_batch_dev",
+    "scl_reserve", "scl_set_shard", "scl_build_insert", "scl_make_scancontext", "scl_polar_tables", "scl_build_batch", "scl_build_batch_dev",
     "scl_insert", "scl_insert_batch", "scl_insert_batch_dev", "scl_get_index", "scl_size", "scl_get_descriptor",
     "scl_get_ring_key", "scl_query_intra", "scl_query_inter", "scl_query_batch", "scl_query_batch_dev",
     "scl_merge_shards_dev", "scl_icp", "scl_set_profiling", "scl_stage_time", "scl_set_knn_mode", "scl_set_scdist_mode", "scl_set_scdist_tiles", "scl_set_tc_stages", "scl_export_keys_dev", "scl_set_replicated_keys_dev", "scl_knn_stats",
@@ -128,6 +128,7 @@ def load_library():
     lib.scl_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.scl_build_insert.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int8, C.c_int, C.c_void_p]
     lib.scl_make_scancontext.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.scl_polar_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 7
     lib.scl_build_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.scl_build_batch_dev.argtypes = lib.scl_build_batch.argtypes
     lib.scl_insert.argtypes = [C.c_void_p, C.c_void_p, C.c_int8, C.c_int]
@@ -227,6 +228,22 @@ def _cloud(points):
     if pts.ndim != 2 or pts.shape[1] < 3:
         raise ValueError("points must be [P, >=3] float32 (x, y, z first)")
     return pts, pts.shape[0], pts.shape[1] * 4
+
+
+def polar_tables(numRing=20, numSector=60, maxRadius=80.0):
+    """The bin tables of a geometry (scl_polar_tables; host code, no GPU needed): dict with ring_thr, s_max, and per quadrant
+    sec_thr[q], sec_base[q], sec_dir[q]."""
+    lib = load_library()
+    p = SclParams(numRing, numSector, 3, 0.14, 1.65, maxRadius, 100, 10, 0.1)
+    ring = np.zeros(63, np.float32); sec = np.zeros((4, 31), np.float32)
+    n_ring = C.c_int32(); s_max = C.c_float()
+    n_sec = np.zeros(4, np.int32); base = np.zeros(4, np.int32); sdir = np.zeros(4, np.int32)
+    rc = lib.scl_polar_tables(C.byref(p), ring.ctypes.data, C.addressof(n_ring), C.addressof(s_max), sec.ctypes.data,
+                              n_sec.ctypes.data, base.ctypes.data, sdir.ctypes.data)
+    if rc != SCL_OK:
+        raise RuntimeError(f"scl_polar_tables: {_STATUS.get(rc, rc)}")
+    return {"ring_thr": ring[:n_ring.value].copy(), "s_max": np.float32(s_max.value),
+            "sec_thr": [sec[q, :n_sec[q]].copy() for q in range(4)], "sec_base": base.tolist(), "sec_dir": sdir.tolist()}
 
 
 def _torch_stream_sync():
