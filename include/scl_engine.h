@@ -61,7 +61,12 @@ void scl_default_params(scl_params* p);
 int scl_create(const scl_params* p, int device, scl_engine** out);
 int scl_destroy(scl_engine* e);
 const char* scl_last_error(scl_engine* e);
-/* run on the caller's CUDA stream (a cudaStream_t) instead of the engine's own */
+/* Run on the caller's CUDA stream (a cudaStream_t) instead of the engine's own.
+ * Ordering contract of the device-pointer entry points (*_dev): they are ASYNCHRONOUS on the engine's stream, which is a
+ * non-blocking stream of its own until this call replaces it. The engine does not order itself against the streams that
+ * produce its inputs or consume its outputs: either bind it to that stream here (then plain stream order does it, and a
+ * stream-ordered allocator may recycle a buffer right after the call), or synchronise around the call (inputs complete
+ * before it, scl_lane_sync(e, 0) before the outputs are read or the inputs freed). Host-pointer entry points are synchronous. */
 int scl_set_stream(scl_engine* e, void* cuda_stream);
 /* pre-size the database arrays in HBM (they otherwise grow by doubling) */
 int scl_reserve(scl_engine* e, int capacity);
