@@ -6,18 +6,24 @@
 //
 // Layout: clouds arrive as the caller's array-of-structs (pcl::PointXYZI, 32 B/point, x y z at
 // byte 0 4 8); with 16-byte aligned points one LDG.128 fetches x,y,z,pad per point. A batch of
-// scans is one launch: grid = (chunks per scan, scans). Each CTA bins its chunk into a
+// scans is one launch: grid = (chunks per scan, scans), two full waves of resident CTAs; the
+// offsets of up to 256 scans travel as kernel parameters. Each CTA bins its chunks into a
 // shared-memory R x S array of order-preserving uint keys with a warp-aggregated atomicMax
 // (lanes that hit the same bin are first reduced with __match_any_sync/__reduce_max_sync, so
 // one ATOMS per distinct bin per warp), merges that array into the scan's global bin array with
 // atomicMax, and the LAST CTA of the scan (ticket counter) decodes the bins, applies the
-// "-1000 -> 0" rule, writes the R*S float wire image straight into the database slot and
-// reduces the ring key. Because max is order-free and heights are plain floats, bin contents
-// are bit-exact whatever the arrival order.
+// "-1000 -> 0" rule, writes the R*S float wire image straight into the database slot (or the
+// caller's buffer), reduces the ring key and writes the per-entry column statistics K4 reads.
+// Because max is order-free and heights are plain floats, bin contents are bit-exact whatever
+// the arrival order.
+//
+// Per point the kernel does one float division and two fixed-depth table searches: no atanf, no
+// square root, no double-precision index arithmetic (see "exact bin tables" below); 130
+// instructions per point in the production instantiation.
 //
 // Roofline: HBM streaming, 32 B/point read in place (16 B/point algorithmic for packed input),
-// R*S*4 + R*4 B written per scan; arithmetic per point is ~60 FP32/FP64 ops (the bit-exact
-// atanf and the double-precision index math).
+// R*S*4 + R*4 B written per scan. Measured (profiles/r02i_*): 62 us per 64 scans of 113 k
+// points = 3.7 TB/s in place (57 % of the HBM peak); bound by instruction issue at five CTAs/SM.
 #include "common.cuh"
 #include "kernels.h"
 
